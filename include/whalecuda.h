@@ -1,0 +1,178 @@
+/*
+ * libwhalecuda — C ABI of the B200-native ALE/DLWGD likelihood engine.
+ *
+ * This is the drop-in boundary for ONE hot path of arzwa/Whale.jl (reference paths are relative to the
+ * reference checkout): the per-family amalgamated-likelihood recursion `logpdf`/`logpdf!` -> `whale!`
+ * (src/core.jl:29-199), the slice tables it consumes (src/model.jl:162-191, src/bdputil.jl:6-11), the
+ * conditioning term (src/condition.jl:11-29) and the stochastic backtracker (src/track.jl:190-414).
+ * The reference is pure Julia and has no FFI; the seam is cut at Julia method dispatch (see
+ * INTEGRATION.md for the `ccall` glue a maintainer would add).  Conventions:
+ *
+ *   - plain C types only; every entry point returns a status (0 = WHALE_OK) and never throws/aborts;
+ *     the message of the last failure on the calling thread is available via whale_last_error();
+ *   - all indices crossing the ABI are 0-based (the Julia glue subtracts 1 from ids);
+ *   - the caller owns every buffer it passes (valid for the duration of the call); the library copies
+ *     what it needs at *_create time and owns device memory behind the opaque handles;
+ *   - a handle is used by one host thread at a time; calls synchronise before returning unless the
+ *     name ends in `_async`;
+ *   - numerical non-events follow the reference: L <= 0 or a non-finite total gives -Inf
+ *     (src/core.jl:15,36), never an error.
+ *
+ * There is no CPU fallback: every compute entry point fails with WHALE_ERR_CUDA when no sm_100 device
+ * is usable.
+ */
+#ifndef WHALECUDA_H
+#define WHALECUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WHALE_OK 0
+#define WHALE_ERR_ARG 1      /* invalid argument / inconsistent description            */
+#define WHALE_ERR_CUDA 2     /* CUDA runtime failure (message has the CUDA error text) */
+#define WHALE_ERR_CAPACITY 3 /* a family does not fit the on-chip working set          */
+#define WHALE_ERR_STATE 4    /* call sequence error (e.g. backtrack without keep_ell)  */
+
+/* node kinds (src/model.jl:54, NewickTree isleaf/isroot) */
+#define WHALE_LEAF 0
+#define WHALE_INTERNAL 1
+#define WHALE_WGD 2
+#define WHALE_ROOT 3
+
+/* conditioning (src/condition.jl:11-29) */
+#define WHALE_COND_NONE 0       /* NoCondition          */
+#define WHALE_COND_ROOT 1       /* RootCondition        */
+#define WHALE_COND_NONEXTINCT 2 /* NonExtinctCondition  */
+
+/* flags for whale_logpdf_grad */
+#define WHALE_WANT_GRAD 1u  /* also return d loglik / d raw parameter                          */
+#define WHALE_KEEP_ELL 2u   /* logpdf! semantics: keep the full ℓ on the device (src/core.jl:29) */
+
+typedef struct whale_model* whale_model_t;
+typedef struct whale_data* whale_data_t;
+
+/*
+ * Species-tree model structure + parameter layout.
+ * Replaces: WhaleModel construction (src/model.jl:96-145: node order, ids, slices per branch),
+ * Slices (src/model.jl:16-22) and the rates structs' per-node lookup getθ (src/rmodels.jl:31-33,55-64).
+ * Node index = Julia node id - 1.  The raw parameter vector x has n_params entries on the scale the
+ * rates struct stores them (log scale for DLWGD, natural for ConstantDLWGD); *_slot give, per node,
+ * which entry of x it reads (-1: NaN rates, e.g. a root omitted from a DLWGD vector).  WGD nodes carry
+ * the slots of their nonwgdchild (src/rmodels.jl:56-58) and their own q slot (index by wgdid).
+ */
+typedef struct {
+    int32_t n_nodes;
+    const int32_t* order;    /* [n_nodes] processing order: leaves, then postorder (src/model.jl:124) */
+    const int32_t* child0;   /* [n_nodes] first child or -1                                            */
+    const int32_t* child1;   /* [n_nodes] second child or -1 (WGD nodes have one child)                */
+    const int32_t* kind;     /* [n_nodes] WHALE_LEAF / INTERNAL / WGD / ROOT                           */
+    const int32_t* n_slices; /* [n_nodes] n (the slices matrix has n+1 rows; root: 0)                  */
+    const double* slice_dt;  /* [n_nodes] slice length t/n (0 for the root)                            */
+    const double* leafP;     /* [n_nodes] Slices.leafℙ (src/model.jl:110-111)                          */
+    int32_t n_params;        /* P = length of x                                                        */
+    const int32_t* lam_slot; /* [n_nodes]                                                              */
+    const int32_t* mu_slot;  /* [n_nodes]                                                              */
+    const int32_t* q_slot;   /* [n_nodes] -1 unless WGD                                                */
+    int32_t eta_slot;
+    int32_t log_scale;       /* 1: λ = exp(x[lam_slot]) (DLWGD); 0: λ = x[lam_slot] (ConstantDLWGD)    */
+} whale_model_desc;
+
+/*
+ * A batch of CCDs in the reference's own layout, flattened (src/ccd.jl:80-89,102-121):
+ * clades of family f are clade_off[f] .. clade_off[f+1]-1, sorted by size (leaves first, the
+ * ubiquitous clade last); clade c's triples are split_off[c] .. split_off[c+1]-1 in file order with
+ * family-local clade ids g1/g2 and probability p; compat lists (ascending family-local clade ids) of
+ * family f at node e are compat_off[f*n_nodes+e] .. compat_off[f*n_nodes+e+1]-1.
+ * Clade ids must fit UInt16 like the reference's Triple{UInt16} (src/ccd.jl:13-20).
+ */
+typedef struct {
+    int32_t n_fam;
+    const int64_t* clade_off;   /* [n_fam+1]           */
+    const int32_t* clade_nleaf; /* [total clades]      */
+    const int64_t* split_off;   /* [total clades + 1]  */
+    const int32_t* g1;          /* [total triples]     */
+    const int32_t* g2;
+    const double* p;
+    const int64_t* compat_off;  /* [n_fam*n_nodes + 1] */
+    const int32_t* compat;
+} whale_ccd_desc;
+
+int32_t whale_version(void);
+/* copies the calling thread's last error message (NUL-terminated, truncated to n) */
+int32_t whale_last_error(char* buf, size_t n);
+/* number of usable CUDA devices (0 when none); selects the device used by subsequent *_create calls */
+int32_t whale_device_count(void);
+int32_t whale_set_device(int32_t device);
+
+int32_t whale_model_create(const whale_model_desc* desc, whale_model_t* out);
+int32_t whale_model_destroy(whale_model_t m);
+
+/* read_ale-time packing (src/ccd.jl:126-137 + CCD ctor): builds the device arena once */
+int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* desc, whale_data_t* out);
+int32_t whale_data_destroy(whale_data_t d);
+int32_t whale_data_nfam(whale_data_t d);
+/* bytes of the packed arena resident in HBM, and the algorithmic bytes one evaluation reads */
+int64_t whale_data_arena_bytes(whale_data_t d);
+/* copies the packed arena back (for the bit-exact packing tests); buf may be NULL to query the size */
+int64_t whale_data_arena_dump(whale_data_t d, void* buf, int64_t cap);
+
+/*
+ * logpdf / logpdf! over a vector of CCDs, fused with the forward-mode gradient
+ * (replaces src/core.jl:46-64 + ForwardDiff.gradient over it, test/runtests.jl:36-38):
+ *   *loglik  = Σ_f log L_f − n_fam·condition(model)          (ℓhood-guarded, src/core.jl:15)
+ *   grad[P]  = ∂ *loglik / ∂ x                                (NULL unless WHALE_WANT_GRAD)
+ *   ll_fam[F]= unconditioned per-family log L_f (nullable)    (for mixtures, src/core.jl:66-79)
+ *   grad_fam[F*P] (nullable) per-family ∂ log L_f / ∂ x
+ * p_leaf (nullable, [n_nodes]) = sampling-failure probabilities getp (src/rmodels.jl:14).
+ */
+int32_t whale_logpdf_grad(whale_model_t m, whale_data_t d, const double* x, const double* p_leaf,
+                          int32_t condition, uint32_t flags, double* loglik, double* grad, double* ll_fam,
+                          double* grad_fam);
+
+/*
+ * Device-resident variant: d_x (P doubles) and d_out (1+P doubles: loglik, grad) live in device memory;
+ * work is enqueued on `stream` (a cudaStream_t) and NOT synchronised.  Used by the benchmark's
+ * device-timed leg and by multi-GPU drivers that all-reduce d_out with NCCL on the same stream.
+ */
+int32_t whale_logpdf_grad_async(whale_model_t m, whale_data_t d, const double* d_x, int32_t condition,
+                                uint32_t flags, double* d_out, void* stream);
+
+/* slice tables for table-parity tests: rows of all nodes concatenated in node-index order,
+ * (n_slices[e]+1) rows each (src/model.jl:182-191) */
+int32_t whale_slices(whale_model_t m, const double* x, const double* p_leaf, double* eps, double* phi,
+                     double* psi);
+
+/* the full ℓ of family `fam` kept by the last WHALE_KEEP_ELL evaluation: concatenation over nodes
+ * (index order) of row-major (n_slices[e]+1) x C_e matrices (ccd.ℓ, src/ccd.jl:59-75) */
+int64_t whale_ell_size(whale_data_t d, int32_t fam);
+int32_t whale_ell_get(whale_data_t d, int32_t fam, double* out);
+
+/*
+ * backtrack(wm, ccd) (src/track.jl:190-414) for n_samples reconciliations per family, on the ℓ kept by
+ * the last WHALE_KEEP_ELL evaluation, with host-supplied uniforms instead of rand():
+ * sample s of family f consumes uniforms[(f*n_samples+s)*stride ...] in the order the reference calls
+ * rand().  Output per (f,s): node_count, and at most max_nodes nodes (gamma = clade id or -1 for loss
+ * nodes, e = node index, t = 1-based row index (0 for loss nodes), parent = index of the parent node in
+ * this tree or -1) in creation (DFS) order; status 0 ok, 1 "Backtracking failed" (src/track.jl:150),
+ * 2 node overflow, 3 uniforms exhausted.
+ */
+int32_t whale_backtrack(whale_model_t m, whale_data_t d, int32_t n_samples, const double* uniforms,
+                        int64_t stride, int32_t max_nodes, int32_t* node_count, int32_t* gamma, int32_t* e,
+                        int32_t* t, int32_t* parent, int32_t* status);
+
+/* counters for benchmarks: kernels launched by this library since load, and the last evaluation's
+ * algorithmic flop / byte counts (SURVEY §8d coefficients) */
+int64_t whale_launch_count(void);
+int32_t whale_work_estimate(whale_model_t m, whale_data_t d, uint32_t flags, double* flops, double* bytes);
+
+/* measured fp64 FMA peak of the current device (dependent-free DFMA microbenchmark), TFLOP/s */
+int32_t whale_fp64_peak(double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

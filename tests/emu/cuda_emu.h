@@ -1,0 +1,109 @@
+// TEST INFRASTRUCTURE ONLY — a minimal CUDA-on-host-threads shim.
+//
+// `make -C tests/emu` compiles whale.jl_b200/csrc/whalecuda.cu as plain C++ with -DWHALE_EMU against this
+// header into tests/emu/libwhalecuda_emu.so.  Each CTA runs as blockDim.x host threads with a real
+// barrier for __syncthreads(); CTAs run one after another.  It exists so the packer and the kernel logic
+// can be debugged (and regression-tested by `pytest -m "not gpu"`) on the GPU-less build container.
+// It is NOT a fallback: the package only ever loads whale.jl_b200/libwhalecuda.so, which requires a GPU.
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+#define __restrict__
+#define __shared__ static
+
+struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+inline thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+
+struct uint4 { unsigned x, y, z, w; };
+struct double2 { double x, y; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+template <class T> inline T __ldg(const T* p) { return *p; }
+inline double __hiloint2double(int hi, int lo) {
+    uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double d; memcpy(&d, &u, 8); return d;
+}
+inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+using std::min;
+using std::max;
+using std::isfinite;
+
+namespace emu {
+struct Barrier {
+    std::mutex mu; std::condition_variable cv; int n = 0, count = 0, gen = 0;
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        int g = gen;
+        if (++count == n) { count = 0; gen++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return g != gen; });
+    }
+};
+inline Barrier* g_bar = nullptr;
+inline unsigned char* g_smem = nullptr;
+inline void launch(int grid, int block, size_t smem, const std::function<void()>& body) {
+    std::vector<unsigned char> sm(smem + 64);
+    Barrier bar; bar.n = block;
+    g_bar = &bar;
+    g_smem = (unsigned char*)(((uintptr_t)sm.data() + 15) & ~(uintptr_t)15);
+    for (int b = 0; b < grid; b++) {
+        std::vector<std::thread> th;
+        for (int t = 0; t < block; t++)
+            th.emplace_back([&, t, b] {
+                threadIdx.x = t; blockIdx.x = b; blockDim.x = block; gridDim.x = grid;
+                body();
+            });
+        for (auto& x : th) x.join();
+    }
+}
+}  // namespace emu
+inline void __syncthreads() { emu::g_bar->wait(); }
+#define EXTERN_SHARED(name) unsigned char* name = emu::g_smem
+
+// ---- runtime API subset ----
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+typedef struct { std::chrono::steady_clock::time_point t; }* cudaEvent_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum { cudaStreamNonBlocking = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+struct cudaDeviceProp { int multiProcessorCount = 2; };
+inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
+inline cudaError_t cudaGetLastError() { return 0; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
+inline cudaError_t cudaSetDevice(int) { return 0; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { *p = cudaDeviceProp(); return 0; }
+inline cudaError_t cudaMalloc(void** p, size_t n) { *p = calloc(1, n ? n : 1); return 0; }
+inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = calloc(1, n ? n : 1); return 0; }
+inline cudaError_t cudaFree(void* p) { free(p); return 0; }
+inline cudaError_t cudaFreeHost(void* p) { free(p); return 0; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return 0; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return 0; }
+inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return 0; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+inline cudaError_t cudaDeviceSynchronize() { return 0; }
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new std::remove_pointer<cudaEvent_t>::type(); return 0; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = std::chrono::steady_clock::now(); return 0; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+    *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return 0;
+}

@@ -1,0 +1,97 @@
+"""`logpdf` / `logpdf!` / fused gradient — the reference-facing operator surface (src/core.jl:17-81).
+
+Every function here is a thin driver of the C ABI: pack once (`whale_model_create`, `whale_data_create`),
+then one `whale_logpdf_grad` call per evaluation.  No arithmetic of the hot path happens in Python.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import lib as _lib
+from .ccd import CCD, CCDVector
+from .model import CONDITIONS, WhaleModel
+
+
+def _model_handle(wm: WhaleModel):
+    L = _lib.get()
+    if wm._handle is None or wm._handle[0] is not L:
+        wm._handle = (L, L.model_create(wm))
+    return wm._handle[1]
+
+
+def _data_handle(wm: WhaleModel, xs: CCDVector):
+    L = _lib.get()
+    mh = _model_handle(wm)
+    key = (id(L), mh)
+    if key not in xs._data:
+        xs._data[key] = L.data_create(mh, xs.flatten(wm.nn))
+    return mh, xs._data[key]
+
+
+def _as_vector(x) -> tuple[CCDVector, bool]:
+    if isinstance(x, CCD):
+        if x._batch is None:
+            x._batch = CCDVector([x])
+        return x._batch, True
+    if not isinstance(x, CCDVector):
+        x = CCDVector(x)
+    return x, False
+
+
+def _eval(wm: WhaleModel, x, grad=False, keep=False, per_family=False, per_family_grad=False):
+    xs, single = _as_vector(x)
+    mh, dh = _data_handle(wm, xs)
+    # a single CCD is the *unconditioned* likelihood (src/core.jl:29-43); vectors subtract N·condition (:46-64)
+    cond = 0 if single else CONDITIONS[wm.condition]
+    return _lib.get().logpdf_grad(mh, dh, wm.x(), wm.p_leaf(), cond, want_grad=grad, keep_ell=keep,
+                                  per_family=per_family, per_family_grad=per_family_grad)
+
+
+def logpdf(wm: WhaleModel, x) -> float:
+    """`logpdf(wm, ccd)` / `logpdf(wm, ccds)` (src/core.jl:39-43,58-64)."""
+    return _eval(wm, x)[0]
+
+
+def logpdf_(wm: WhaleModel, x) -> float:
+    """`logpdf!(wm, ccd(s))` (src/core.jl:29,46-56): same value, and the full ℓ stays on the device for
+    `backtrack` / `ell`."""
+    return _eval(wm, x, keep=True)[0]
+
+
+loglikelihood = logpdf  # src/core.jl:17,81
+
+
+def logpdf_and_gradient(wm: WhaleModel, x):
+    """One fused pass: (ℓ, ∂ℓ/∂raw) with raw = [λ…, μ…, q…, η] on the rates struct's scale — what
+    `ForwardDiff.gradient(x -> logpdf(wm(rates(x)), ccd), raw)` returns (test/runtests.jl:36-38)."""
+    l, g, _, _ = _eval(wm, x, grad=True)
+    return l, g
+
+
+def logpdf_per_family(wm: WhaleModel, xs, grad=False):
+    """Unconditioned per-family log-likelihoods (and gradients) — the building block of the mixture /
+    model-array variants (src/core.jl:66-79)."""
+    l, g, lf, gf = _eval(wm, xs, grad=grad, per_family=True, per_family_grad=grad)
+    return lf, gf
+
+
+def ell(wm: WhaleModel, xs, fam: int = 0):
+    """ℓ matrices of one family after `logpdf_` (ccd.ℓ, src/ccd.jl:59-75): list over nodes (index order)
+    of (n_e+1) × C_e arrays."""
+    xs, _ = _as_vector(xs)
+    mh, dh = _data_handle(wm, xs)
+    flat = _lib.get().ell_get(dh, fam)
+    out, o = [], 0
+    for e in range(wm.nn):
+        r, c = int(wm.n_slices[e]) + 1, len(xs[fam].compat[e])
+        out.append(flat[o:o + r * c].reshape(r, c))
+        o += r * c
+    return out
+
+
+def slices(wm: WhaleModel):
+    """Per-node slice tables [ϵ ϕ ψ] computed on the device (src/model.jl:182-191): list over nodes of
+    (n_e+1) × 3 arrays."""
+    mh = _model_handle(wm)
+    eps, phi, psi = _lib.get().slices(mh, wm.x(), wm.p_leaf(), int(wm.row_off[-1]))
+    return [np.stack([eps[a:b], phi[a:b], psi[a:b]], axis=1) for a, b in zip(wm.row_off[:-1], wm.row_off[1:])]

@@ -1,0 +1,178 @@
+"""ctypes binding of libwhalecuda (include/whalecuda.h).
+
+The library is built in-tree (`whale.jl_b200/libwhalecuda.so`, see build.py) and is the ONLY compute path:
+if it is missing, or no CUDA device is usable, every call raises — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwhalecuda.so")
+
+i32p, i64p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double)
+
+WANT_GRAD, KEEP_ELL = 1, 2
+
+# every symbol include/whalecuda.h declares (tests check the built library exports all of them)
+SYMBOLS = ["whale_version", "whale_last_error", "whale_device_count", "whale_set_device", "whale_model_create",
+           "whale_model_destroy", "whale_data_create", "whale_data_destroy", "whale_data_nfam",
+           "whale_data_arena_bytes", "whale_data_arena_dump", "whale_logpdf_grad", "whale_logpdf_grad_async",
+           "whale_slices", "whale_ell_size", "whale_ell_get", "whale_backtrack", "whale_launch_count",
+           "whale_work_estimate", "whale_fp64_peak"]
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("order", i32p), ("child0", i32p), ("child1", i32p), ("kind", i32p),
+                ("n_slices", i32p), ("slice_dt", f64p), ("leafP", f64p), ("n_params", C.c_int32),
+                ("lam_slot", i32p), ("mu_slot", i32p), ("q_slot", i32p), ("eta_slot", C.c_int32),
+                ("log_scale", C.c_int32)]
+
+
+class CCDDesc(C.Structure):
+    _fields_ = [("n_fam", C.c_int32), ("clade_off", i64p), ("clade_nleaf", i32p), ("split_off", i64p),
+                ("g1", i32p), ("g2", i32p), ("p", f64p), ("compat_off", i64p), ("compat", i32p)]
+
+
+class WhaleCudaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libwhalecuda error {code}: {msg}")
+        self.code = code
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+class Lib:
+    """A loaded libwhalecuda with typed entry points."""
+
+    def __init__(self, path: str = LIB_PATH):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} not found: build the CUDA library first (python -m whale_jl_b200.build or "
+                f"__graft_entry__.build()); there is no CPU fallback")
+        self.path = path
+        L = self.L = C.CDLL(path)
+        vp = C.c_void_p
+        L.whale_version.restype = C.c_int32
+        L.whale_last_error.argtypes = [C.c_char_p, C.c_size_t]
+        L.whale_device_count.restype = C.c_int32
+        L.whale_set_device.argtypes = [C.c_int32]
+        L.whale_model_create.argtypes = [C.POINTER(ModelDesc), C.POINTER(vp)]
+        L.whale_model_destroy.argtypes = [vp]
+        L.whale_data_create.argtypes = [vp, C.POINTER(CCDDesc), C.POINTER(vp)]
+        L.whale_data_destroy.argtypes = [vp]
+        L.whale_data_nfam.argtypes = [vp]
+        L.whale_data_arena_bytes.argtypes = [vp]
+        L.whale_data_arena_bytes.restype = C.c_int64
+        L.whale_data_arena_dump.argtypes = [vp, vp, C.c_int64]
+        L.whale_data_arena_dump.restype = C.c_int64
+        L.whale_logpdf_grad.argtypes = [vp, vp, f64p, f64p, C.c_int32, C.c_uint32, f64p, f64p, f64p, f64p]
+        L.whale_logpdf_grad_async.argtypes = [vp, vp, vp, C.c_int32, C.c_uint32, vp, vp]
+        L.whale_slices.argtypes = [vp, f64p, f64p, f64p, f64p, f64p]
+        L.whale_ell_size.argtypes = [vp, C.c_int32]
+        L.whale_ell_size.restype = C.c_int64
+        L.whale_ell_get.argtypes = [vp, C.c_int32, f64p]
+        L.whale_backtrack.argtypes = [vp, vp, C.c_int32, f64p, C.c_int64, C.c_int32, i32p, i32p, i32p, i32p, i32p,
+                                      i32p]
+        L.whale_launch_count.restype = C.c_int64
+        L.whale_work_estimate.argtypes = [vp, vp, C.c_uint32, f64p, f64p]
+        L.whale_fp64_peak.argtypes = [f64p]
+
+    def check(self, rc):
+        if rc != 0:
+            buf = C.create_string_buffer(512)
+            self.L.whale_last_error(buf, 512)
+            raise WhaleCudaError(rc, buf.value.decode(errors="replace"))
+
+    # ---- handles ----
+    def model_create(self, m) -> int:
+        keep = [np.ascontiguousarray(a) for a in
+                (m.order, m.child0, m.child1, m.kind, m.n_slices, m.slice_dt, m.leafP, m.lam_slot, m.mu_slot,
+                 m.q_slot)]
+        d = ModelDesc(m.nn, _ptr(keep[0], i32p), _ptr(keep[1], i32p), _ptr(keep[2], i32p), _ptr(keep[3], i32p),
+                      _ptr(keep[4], i32p), _ptr(keep[5], f64p), _ptr(keep[6], f64p), m.n_params,
+                      _ptr(keep[7], i32p), _ptr(keep[8], i32p), _ptr(keep[9], i32p), m.eta_slot, m.log_scale)
+        h = C.c_void_p()
+        self.check(self.L.whale_model_create(C.byref(d), C.byref(h)))
+        return h.value
+
+    def data_create(self, mh: int, flat: dict) -> int:
+        d = CCDDesc(flat["n_fam"], _ptr(flat["clade_off"], i64p), _ptr(flat["clade_nleaf"], i32p),
+                    _ptr(flat["split_off"], i64p), _ptr(flat["g1"], i32p), _ptr(flat["g2"], i32p),
+                    _ptr(flat["p"], f64p), _ptr(flat["compat_off"], i64p), _ptr(flat["compat"], i32p))
+        h = C.c_void_p()
+        self.check(self.L.whale_data_create(mh, C.byref(d), C.byref(h)))
+        return h.value
+
+    def logpdf_grad(self, mh, dh, x, p_leaf, condition, want_grad=False, keep_ell=False, per_family=False,
+                    per_family_grad=False):
+        x = np.ascontiguousarray(x, np.float64)
+        pl = np.ascontiguousarray(p_leaf, np.float64)
+        F = self.L.whale_data_nfam(dh)
+        P = len(x)
+        ll = C.c_double()
+        g = np.zeros(P) if want_grad else None
+        lf = np.zeros(F) if per_family else None
+        gf = np.zeros((F, P)) if per_family_grad else None
+        flags = (WANT_GRAD if want_grad else 0) | (KEEP_ELL if keep_ell else 0)
+        self.check(self.L.whale_logpdf_grad(mh, dh, _ptr(x, f64p), _ptr(pl, f64p), condition, flags, C.byref(ll),
+                                            _ptr(g, f64p) if want_grad else None,
+                                            _ptr(lf, f64p) if per_family else None,
+                                            _ptr(gf, f64p) if per_family_grad else None))
+        return ll.value, g, lf, gf
+
+    def slices(self, mh, x, p_leaf, nrows):
+        x = np.ascontiguousarray(x, np.float64)
+        pl = np.ascontiguousarray(p_leaf, np.float64)
+        eps, phi, psi = np.zeros(nrows), np.zeros(nrows), np.zeros(nrows)
+        self.check(self.L.whale_slices(mh, _ptr(x, f64p), _ptr(pl, f64p), _ptr(eps, f64p), _ptr(phi, f64p),
+                                       _ptr(psi, f64p)))
+        return eps, phi, psi
+
+    def ell_get(self, dh, fam):
+        n = self.L.whale_ell_size(dh, fam)
+        if n < 0:
+            raise IndexError(fam)
+        out = np.zeros(n)
+        self.check(self.L.whale_ell_get(dh, fam, _ptr(out, f64p)))
+        return out
+
+    def arena_dump(self, dh) -> np.ndarray:
+        n = self.L.whale_data_arena_dump(dh, None, 0)
+        buf = np.zeros(n, np.uint8)
+        got = self.L.whale_data_arena_dump(dh, buf.ctypes.data_as(C.c_void_p), n)
+        if got != n:
+            raise WhaleCudaError(2, "arena dump failed")
+        return buf
+
+    def work_estimate(self, mh, dh, want_grad=True):
+        fl, by = C.c_double(), C.c_double()
+        self.check(self.L.whale_work_estimate(mh, dh, WANT_GRAD if want_grad else 0, C.byref(fl), C.byref(by)))
+        return fl.value, by.value
+
+    def fp64_peak(self) -> float:
+        t = C.c_double()
+        self.check(self.L.whale_fp64_peak(C.byref(t)))
+        return t.value
+
+
+_default: Lib | None = None
+
+
+def get() -> Lib:
+    """The process-wide library instance (loaded on first use)."""
+    global _default
+    if _default is None:
+        _default = Lib()
+    return _default
+
+
+def use(lib: Lib | None):
+    """Install another library instance (tests use this to run the host logic against the emulation build)."""
+    global _default
+    _default = lib
