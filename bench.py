@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py — family (log-likelihood + gradient) evaluations per second on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], "C2"): per GPU 1000 synthetic families x ~200 clades on the reference's
+9-taxon tree with 2 WGD nodes (Whale.extree + wgd_1/wgd_2, test/runtests.jl:8-11), ConstantDLWGD rates
+(P = 5: λ, μ, q1, q2, η), Δt = 0.05, RootCondition.  One *step* = one logpdf+∇ evaluation of every family
+for a NEW parameter vector (NUTS/MLE style: slice tables are recomputed each step).  Families shard across
+ranks (weak scaling: 1000 families per GPU); the only collective is the sum of 1+P doubles.
+
+Prints ONE JSON line (rank 0).  `value` = device-timed throughput with the arena resident in HBM (CUDA events
+per step, L2 flushed between steps, max over ranks); `e2e` = the same metric through the C-ABI call with HOST
+buffers (θ H2D and loglik+grad D2H inside the timed region); `roofline` = the DP kernel against the measured
+fp64 FMA peak (the DP never leaves shared memory), `roofline_hbm` the same launch against
+MEASURED_PEAKS.json's HBM bandwidth; `cpu_baseline` = the C++ oracle port on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "family loglik+grad evals/s"
+UNIT = "family-evals/s"
+BASE_X = np.array([0.2, 0.3, 0.2, 0.1, 0.67])  # λ, μ, q1, q2, η  
+DT = 0.05
+FAMILIES_PER_GPU = 1000
+SEED = 2
+
+
+def thetas(n, seed=0):
+    """A new θ per step (like successive NUTS/MLE iterates): 3 % log-normal jitter around the C2 point."""
+    rng = np.random.default_rng(1000 + seed)
+    x = BASE_X[None, :] * np.exp(0.03 * rng.standard_normal((n, len(BASE_X))))
+    x[:, 2:] = np.clip(x[:, 2:], 1e-3, 1 - 1e-3)
+    return np.ascontiguousarray(x)
+
+
+def dataset(rank, n_fam):
+    from whale_jl_b200 import synth
+    d = os.path.join(ROOT, ".synth_cache", f"c2_seed{SEED}_rank{rank}_n{n_fam}")
+    t0 = time.time()
+    synth.generate(d, n_fam, seed=SEED + 7919 * rank)
+    return d, time.time() - t0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_baseline(ale_dir, budget_s=12.0, nthreads=0):
+    """The oracle port (C++ restatement of the reference loops, OpenMP over families like Threads.@threads)
+    timed on a bounded sample of the same families, logpdf + ForwardDiff-style gradient."""
+    from oracle import flat, whale_oracle as wo
+    ow = wo.WhaleModel(wo.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), wo.c1_tree(), DT)
+    files = sorted(os.listdir(ale_dir))[:128]
+    spmap = {n.name: n.id for n in ow.order if n.isleaf()}
+    ccds = [wo.CCD(wo.parse_aleobserve(os.path.join(ale_dir, f)), ow, spmap) for f in files]
+    fm, ff = flat.FlatModel(ow), flat.FlatFams(ccds, len(ow))
+    xs = thetas(64, seed=99)
+    flat.logpdf(fm, ff, x=xs[0], grad=True, nthreads=nthreads)  # warm-up
+    t0, n = time.perf_counter(), 0
+    while time.perf_counter() - t0 < budget_s:
+        flat.logpdf(fm, ff, x=xs[n % len(xs)], grad=True, nthreads=nthreads)
+        n += 1
+    dt = time.perf_counter() - t0
+    cores = int(flat.lib().oracle_max_threads()) if nthreads == 0 else nthreads
+    return {"value": len(ccds) * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(ccds)} of the {FAMILIES_PER_GPU} C2 families x {n} evaluations (logpdf + Dual<5> gradient), "
+                      f"OMP_NUM_THREADS={cores}; JULIA_NUM_THREADS n/a (no julia in this image)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Julia original cannot run here) on the
+    same config, all host threads, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import flat, whale_oracle as wo
+    d, _ = dataset(0, FAMILIES_PER_GPU)
+    ow = wo.WhaleModel(wo.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), wo.c1_tree(), DT)
+    S = 256
+    spmap = {n.name: n.id for n in ow.order if n.isleaf()}
+    ccds = [wo.CCD(wo.parse_aleobserve(os.path.join(d, f)), ow, spmap) for f in sorted(os.listdir(d))[:S]]
+    fm, ff = flat.FlatModel(ow), flat.FlatFams(ccds, len(ow))
+    xs = thetas(args.steps + args.warmup)
+    for i in range(args.warmup):
+        flat.logpdf(fm, ff, x=xs[i], grad=True)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        flat.logpdf(fm, ff, x=xs[args.warmup + i], grad=True)
+    dt = time.perf_counter() - t0
+    cores = int(flat.lib().oracle_max_threads())
+    val = S * args.steps / dt
+    sample = f"{S} of the {FAMILIES_PER_GPU} C2 families per step, logpdf + Dual<5> gradient, {cores} OpenMP threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: 1000 synthetic families x ~200 clades, 9-taxon tree + 2 WGD, ConstantDLWGD P=5, dt=0.05"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--families", type=int, default=FAMILIES_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import whale_jl_b200 as W
+    from whale_jl_b200 import lib as wlib
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = wlib.get()
+    L.check(L.L.whale_set_device(local))
+
+    # ---- data: generate this rank's shard, read_ale, pack once ----
+    d, gen_s = dataset(rank, args.families)
+    model = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), W.synth.c1_species_tree(), DT)
+    t0 = time.time()
+    ccds = W.read_ale(d, model)
+    from whale_jl_b200.core import _data_handle
+    mh, dh = _data_handle(model, ccds)
+    pack_s = time.time() - t0
+    F, P = len(ccds), model.n_params
+    cond = 1  # RootCondition
+    flops, abytes = L.work_estimate(mh, dh, True)
+    arena_bytes = L.L.whale_data_arena_bytes(dh)
+
+    K, Wm = args.steps, args.warmup
+    xs = thetas(K + Wm, seed=rank * 0)  # same θ on every rank (one model, sharded data)
+    X = torch.tensor(xs, device="cuda", dtype=torch.float64)
+    OUT = torch.zeros(1 + P, device="cuda", dtype=torch.float64)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+    FLAGS = wlib.WANT_GRAD | wlib.PROFILE
+
+    def step(i, flags=FLAGS):
+        L.logpdf_grad_async(mh, dh, X[i].data_ptr(), cond, flags, OUT.data_ptr(), stream)
+        if world > 1:
+            dist.all_reduce(OUT)
+
+    for i in range(Wm):
+        step(i)
+    torch.cuda.synchronize()
+    launches0 = L.L.whale_launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    kms = np.zeros((K, 3))
+    wall0 = time.perf_counter()
+    for i in range(K):
+        flush.zero_()  # evict the arena from L2 (outside the timed event pair)
+        ev[i][0].record()
+        step(Wm + i)
+        ev[i][1].record()
+        ev[i][1].synchronize()
+        kms[i] = L.last_kernel_ms(dh)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    launches = L.L.whale_launch_count() - launches0
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    total_ms = float(step_ms.sum())
+    last = OUT.cpu().numpy().copy()
+    # keep the GPU under the same load a little longer if the region was too short for nvidia-smi to sample
+    t_probe = time.perf_counter()
+    while len(sampler.rows) < 8 and time.perf_counter() - t_probe < 3.0:
+        for i in range(Wm):
+            step(i, wlib.WANT_GRAD)
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = F * world * K / (total_ms * 1e-3)
+
+    # ---- e2e: the reference-facing call with HOST buffers ----
+    pin_x = torch.empty(P, dtype=torch.float64).pin_memory()
+    pin_o = torch.empty(1 + P, dtype=torch.float64).pin_memory()
+    Xd = torch.empty(P, device="cuda", dtype=torch.float64)
+
+    def e2e_step(i):
+        if world == 1:  # exactly the call the Julia glue makes: host pointers in, host pointers out
+            return L.logpdf_grad(mh, dh, xs[i], model.p_leaf(), cond, want_grad=True)[0]
+        pin_x.copy_(torch.from_numpy(xs[i]))
+        Xd.copy_(pin_x, non_blocking=True)
+        L.logpdf_grad_async(mh, dh, Xd.data_ptr(), cond, wlib.WANT_GRAD, OUT.data_ptr(), stream)
+        dist.all_reduce(OUT)
+        pin_o.copy_(OUT, non_blocking=True)
+        torch.cuda.synchronize()
+        return float(pin_o[0])
+
+    for i in range(Wm):
+        e2e_step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        ll_e2e = e2e_step(Wm + i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = F * world * K / e2e_s
+    assert np.isfinite(ll_e2e) and abs(ll_e2e - last[0]) <= 1e-9 * abs(last[0]), (ll_e2e, last[0])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_dp) ----
+    dp_ms = float(kms[:, 1].mean())
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    fp64_peak = L.fp64_peak()  # measured DFMA microbenchmark on this GPU (MEASURED_PEAKS.json has no fp64 entry)
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    ach_tf = flops / (dp_ms * 1e-3) / 1e12
+    ach_gb = abytes / (dp_ms * 1e-3) / 1e9
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C2: {F} synthetic families/GPU x ~200 clades (median), 9-taxon tree + 2 WGD "
+                               f"(19 nodes, {int(model.n_slices.sum())} slices), ConstantDLWGD P={P}, dt={DT}, "
+                               f"RootCondition, new theta each step",
+                   "families_total": F * world, "sharding": f"families/{world} ranks, all-reduce of {1 + P} f64",
+                   "l2": "flushed between steps (256 MiB memset outside the timed events)",
+                   "arena_bytes_per_gpu": int(arena_bytes), "gen_s": round(gen_s, 1), "pack_s": round(pack_s, 2)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 8 * (P + model.nn),
+                "d2h_bytes_per_step": 8 * (1 + P), "ms_per_step": 1e3 * e2e_s / K,
+                "note": "whale_logpdf_grad with host pointers; the packed CCD arena stays resident in HBM like "
+                        "the reference's CCD objects stay resident in RAM across logpdf calls"},
+        "gpu_launches": int(launches),
+        "kernels_ms": {"k_tables": float(kms[:, 0].mean()), "k_dp": dp_ms, "k_reduce": float(kms[:, 2].mean()),
+                       "step_events": float(step_ms.mean()), "wall_per_step_incl_flush": 1e3 * wall / K},
+        "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": ach_tf / fp64_peak, "traffic": None, "kernel": "k_dp<128>",
+                     "flops_per_launch": flops, "peak_source": "whale_fp64_peak DFMA microbenchmark, this GPU, this run"},
+        "roofline_hbm": {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": ach_gb / hbm_peak, "bytes_per_launch": abytes,
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+        "loglik_last": float(last[0]),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(d)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

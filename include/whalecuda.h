@@ -51,6 +51,7 @@ extern "C" {
 /* flags for whale_logpdf_grad */
 #define WHALE_WANT_GRAD 1u  /* also return d loglik / d raw parameter                          */
 #define WHALE_KEEP_ELL 2u   /* logpdf! semantics: keep the full ℓ on the device (src/core.jl:29) */
+#define WHALE_PROFILE 4u    /* record CUDA events around each kernel (see whale_last_kernel_ms)   */
 
 typedef struct whale_model* whale_model_t;
 typedef struct whale_data* whale_data_t;
@@ -168,6 +169,10 @@ int32_t whale_backtrack(whale_model_t m, whale_data_t d, int32_t n_samples, cons
  * algorithmic flop / byte counts (SURVEY §8d coefficients) */
 int64_t whale_launch_count(void);
 int32_t whale_work_estimate(whale_model_t m, whale_data_t d, uint32_t flags, double* flops, double* bytes);
+
+/* device time of the kernels of the last WHALE_PROFILE evaluation on this data handle, measured with CUDA
+ * events on the stream they were launched on (waits for that evaluation to finish) */
+int32_t whale_last_kernel_ms(whale_data_t d, double* tables_ms, double* dp_ms, double* reduce_ms);
 
 /* measured fp64 FMA peak of the current device (dependent-free DFMA microbenchmark), TFLOP/s */
 int32_t whale_fp64_peak(double* tflops);

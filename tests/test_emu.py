@@ -1,0 +1,48 @@
+"""Kernel logic exercised on the CPU through the emulation build (tests/emu): the same whalecuda.cu compiled
+against a host-thread CUDA shim.  Catches packer / indexing / tangent-plan bugs without a GPU; the parity tests
+proper are tests/test_gpu_parity.py (-m gpu)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from whale_jl_b200 import lib as wlib
+from conftest import ROOT, run_parity, load_golden, golden_model, golden_fams
+
+EMU = os.path.join(ROOT, "tests", "emu", "libwhalecuda_emu.so")
+
+
+@pytest.fixture(scope="module")
+def L():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "emu"), "-s"])
+    return wlib.Lib(EMU)
+
+
+def test_emu_known_answer_maxn5(L):
+    g = run_parity(L, "c1_maxn5")
+    assert g["tot_none"][0] == pytest.approx(-60.96367806571888, rel=1e-12)
+
+
+def test_emu_c1_subset(L):
+    run_parity(L, "c1_example1", sel=[0, 3], conds=["root"])
+
+
+def test_emu_constant_rates(L):
+    run_parity(L, "const_wgdturing", sel=[1, 7], conds=["nonextinct"])
+
+
+def test_emu_mul_tree(L):
+    run_parity(L, "mul_tree", sel=[2], conds=["root"])
+
+
+def test_emu_slices_and_ell(L):
+    g = load_golden("c1_example1")
+    mh = L.model_create(golden_model(g))
+    x = g["xs"][2]
+    n = int((g["m_nslices"] + 1).sum())
+    eps, phi, psi = L.slices(mh, x, g["m_pleaf"], n)
+    np.testing.assert_allclose(np.stack([eps, phi, psi], 1), g["slices"][2], rtol=1e-12)
+    dh = L.data_create(mh, golden_fams(g, [3]))
+    L.logpdf_grad(mh, dh, x, g["m_pleaf"], 1, keep_ell=True)
+    np.testing.assert_allclose(L.ell_get(dh, 0), g["ell_3"], rtol=1e-11, atol=0)

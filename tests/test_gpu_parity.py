@@ -1,0 +1,143 @@
+"""Parity of the CUDA path against the oracle, through the C ABI, on the B200 (-m gpu).
+
+Bar (north star): log-likelihoods and gradients within 1e-9 relative in fp64; integer packing bit-exact."""
+import numpy as np
+import pytest
+
+import whale_jl_b200 as W
+from whale_jl_b200 import lib as wlib, synth
+from conftest import run_parity, load_golden, golden_model, golden_fams
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    lib = wlib.Lib()  # the in-tree CUDA library; raises if it was not built
+    assert lib.L.whale_device_count() > 0, "no CUDA device"
+    wlib.use(lib)
+    return lib
+
+
+def test_known_answer_single_family(L):
+    """test/runtests.jl:15-19"""
+    g = run_parity(L, "c1_maxn5")
+    mh = L.model_create(golden_model(g))
+    dh = L.data_create(mh, golden_fams(g))
+    ll, *_ = L.logpdf_grad(mh, dh, g["xs"][0], g["m_pleaf"], 0)
+    assert ll == pytest.approx(-60.96367806571888, rel=1e-12)
+
+
+def test_known_answer_12_families(L):
+    """test/runtests.jl:21-34, all conditions, three parameter points incl. the critical λ=μ branch"""
+    g = run_parity(L, "c1_example1")
+    assert g["tot_root"][0] == pytest.approx(-592.0185620440255, rel=1e-12)
+
+
+def test_constant_rates_wgd_model(L):
+    run_parity(L, "const_wgdturing")
+
+
+def test_mul_tree(L):
+    """test/runtests.jl:111-122"""
+    run_parity(L, "mul_tree")
+
+
+def test_discretisation_fixture(L):
+    """test/runtests.jl:128-144 (critical getα branch on every branch)"""
+    a = run_parity(L, "ex5_dt0.1")
+    b = run_parity(L, "ex5_dt0.01")
+    assert abs(a["tot_root"][0] - b["tot_root"][0]) < 0.1
+
+
+def test_landplant_100_families(L):
+    """docs/src/tutorial.md:103-131: 15..1025 clades per family (ragged sizes, the largest CCD we have)"""
+    run_parity(L, "landplant100")
+
+
+def test_slices_tables(L):
+    for name in ("c1_example1", "const_wgdturing"):
+        g = load_golden(name)
+        mh = L.model_create(golden_model(g))
+        n = int((g["m_nslices"] + 1).sum())
+        for xi, x in enumerate(g["xs"]):
+            eps, phi, psi = L.slices(mh, x, g["m_pleaf"], n)
+            np.testing.assert_allclose(np.stack([eps, phi, psi], 1), g["slices"][xi], rtol=1e-12)
+
+
+def test_keep_ell(L):
+    """logpdf! keeps the full ℓ (src/core.jl:29): compare every cell with the oracle's ℓ"""
+    g = load_golden("c1_example1")
+    mh = L.model_create(golden_model(g))
+    dh = L.data_create(mh, golden_fams(g))
+    x = g["xs"][-1]
+    ll, *_ = L.logpdf_grad(mh, dh, x, g["m_pleaf"], 1, keep_ell=True)
+    assert ll == pytest.approx(g["tot_root"][-1], rel=1e-9)
+    for f in (0, 3):
+        np.testing.assert_allclose(L.ell_get(dh, f), g[f"ell_{f}"], rtol=1e-9, atol=0)
+
+
+def test_nan_root_rates_and_neg_inf(L):
+    """root rates do not matter (runtests.jl:44-49); impossible data gives -Inf not an error (src/core.jl:36)"""
+    g = load_golden("c1_example1")
+    mh = L.model_create(golden_model(g))
+    dh = L.data_create(mh, golden_fams(g))
+    x = g["xs"][0].copy()
+    ll0, *_ = L.logpdf_grad(mh, dh, x, g["m_pleaf"], 1)
+    root = int(g["m_order"][-1])
+    x[root] = np.nan
+    x[17 + root] = np.nan
+    ll1, *_ = L.logpdf_grad(mh, dh, x, g["m_pleaf"], 1)
+    assert ll1 == ll0
+    x = g["xs"][0].copy()
+    x[-1] = 1.0  # η = 1: no duplication at the root -> families needing root duplications get L = 0
+    x[:34] = -40.0  # and (almost) no duplication anywhere
+    ll2, grad, *_ = L.logpdf_grad(mh, dh, x, g["m_pleaf"], 1, want_grad=True)
+    assert ll2 == -np.inf and np.all(grad == 0.0)
+
+
+def test_synthetic_c2_shape_vs_oracle(L, tmp_path):
+    """BASELINE config 1 shape (9 taxa + 2 WGD, ~200 clades, constant rates) at a size the oracle does in
+    seconds, through the package API (read_ale -> pack -> logpdf_and_gradient)."""
+    from oracle import whale_oracle as wo, flat
+    d = synth.generate(str(tmp_path / "c2"), 64, seed=2)
+    w = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), synth.c1_species_tree(), 0.05)
+    ccd = W.read_ale(d, w)
+    ll, grad = W.logpdf_and_gradient(w, ccd)
+    ow = wo.WhaleModel(wo.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), wo.c1_tree(), 0.05)
+    fm, ff = flat.FlatModel(ow), flat.FlatFams(wo.read_ale(d, ow), len(ow))
+    tot, _, og, _ = flat.logpdf(fm, ff, grad=True)
+    assert ll == pytest.approx(tot, rel=1e-9)
+    np.testing.assert_allclose(grad, og, rtol=1e-9)
+    # branch-wise rates (BASELINE config 2 parameterisation, P = 37)
+    rng = np.random.default_rng(3)
+    r = W.DLWGD(lam=list(rng.normal(np.log(0.15), 0.3, 17)), mu=list(rng.normal(np.log(0.15), 0.3, 17)),
+                q=[0.2, 0.1], eta=0.67)
+    wb = W.WhaleModel(r, synth.c1_species_tree(), 0.05)
+    ccdb = W.read_ale(d, wb)
+    ll, grad = W.logpdf_and_gradient(wb, ccdb)
+    owb = wo.WhaleModel(wo.DLWGD(lam=r.lam, mu=r.mu, q=[0.2, 0.1], eta=0.67), wo.c1_tree(), 0.05)
+    fm, ff = flat.FlatModel(owb), flat.FlatFams(wo.read_ale(d, owb), len(owb))
+    tot, _, og, _ = flat.logpdf(fm, ff, grad=True)
+    assert ll == pytest.approx(tot, rel=1e-9)
+    np.testing.assert_allclose(grad, og, rtol=1e-9, atol=1e-9 * np.abs(og).max())
+
+
+def test_full_size_properties(L, tmp_path):
+    """BASELINE config 1 at full size (1000 families): size-independent properties — the batch sum equals the
+    sum of per-family values; shuffling families permutes per-family results and leaves the total unchanged
+    (up to summation order); the gradient of the total is the sum of per-family gradients."""
+    d = synth.generate(str(tmp_path / "c2full"), 1000, seed=2)
+    w = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67, ), synth.c1_species_tree(), 0.05,
+                     condition="none")
+    ccd = W.read_ale(d, w)
+    ll, grad = W.logpdf_and_gradient(w, ccd)
+    lf, gf = W.logpdf_per_family(w, ccd, grad=True)
+    assert np.all(np.isfinite(lf))
+    assert ll == pytest.approx(lf.sum(), rel=1e-12)
+    np.testing.assert_allclose(grad, gf.sum(0), rtol=1e-11)
+    perm = np.random.default_rng(0).permutation(len(ccd))
+    ccd2 = W.CCDVector([ccd[i] for i in perm])
+    lf2, _ = W.logpdf_per_family(w, ccd2)
+    assert np.array_equal(lf2, lf[perm])  # bit-identical per family, independent of batch position
+    assert W.logpdf(w, ccd2) == pytest.approx(ll, rel=1e-13)

@@ -597,13 +597,16 @@ struct whale_data {
     int F = 0;
     std::vector<FamHdr> hdr;
     std::vector<int> perm;
-    std::vector<unsigned char> arena_host;  // kept for arena_dump / backtrack host fallback-free checks
+    std::vector<unsigned char> arena_host;  // packing buffer (released after upload)
+    size_t arena_bytes = 0;
     unsigned char* d_arena = nullptr;
     FamHdr* d_hdr = nullptr;
     int* d_perm = nullptr;
     double* d_out_fam = nullptr;  // [F*Kmax(plan1)]
     double* d_partial = nullptr;
     double* d_ell = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
     uint64_t ell_total = 0;
     bool ell_valid = false;
     int maxSumCK[2] = {0, 0};   // max over families of Σ_e C_e K_e + max_e C_e K_e, per plan (doubles)
@@ -973,6 +976,8 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
     std::stable_sort(D->perm.begin(), D->perm.end(), [&](int a, int b) { return work[a] > work[b]; });
     CU(cudaMalloc((void**)&D->d_arena, std::max<size_t>(A.size(), 16)));
     CU(cudaMemcpy(D->d_arena, A.data(), A.size(), cudaMemcpyHostToDevice));
+    D->arena_bytes = A.size();
+    std::vector<unsigned char>().swap(A);
     CU(upload(D->hdr, &D->d_hdr));
     CU(upload(D->perm, &D->d_perm));
     CU(cudaMalloc((void**)&D->d_out_fam, (size_t)F * m->plan[1].Kmax * sizeof(double)));
@@ -986,15 +991,16 @@ int32_t whale_data_destroy(whale_data_t d) {
     cudaSetDevice(d->m->device);
     cudaFree(d->d_arena); cudaFree(d->d_hdr); cudaFree(d->d_perm); cudaFree(d->d_out_fam); cudaFree(d->d_partial);
     cudaFree(d->d_ell);
+    for (int i = 0; i < 4; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     delete d;
     return WHALE_OK;
 }
 
 int32_t whale_data_nfam(whale_data_t d) { return d ? d->F : 0; }
-int64_t whale_data_arena_bytes(whale_data_t d) { return d ? (int64_t)d->arena_host.size() : 0; }
+int64_t whale_data_arena_bytes(whale_data_t d) { return d ? (int64_t)d->arena_bytes : 0; }
 int64_t whale_data_arena_dump(whale_data_t d, void* buf, int64_t cap) {
     if (!d) return 0;
-    int64_t n = (int64_t)d->arena_host.size();
+    int64_t n = (int64_t)d->arena_bytes;
     if (buf && cap >= n) {
         // read back from the DEVICE copy: this is what the kernels see
         if (cudaMemcpy(buf, d->d_arena, n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
@@ -1011,10 +1017,14 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
     const int nn = m->nn, F = D->F;
     const bool keep = (flags & WHALE_KEEP_ELL) != 0;
     if (keep && !D->d_ell) CU(cudaMalloc((void**)&D->d_ell, std::max<uint64_t>(D->ell_total, 1) * sizeof(double)));
+    const bool prof = (flags & WHALE_PROFILE) != 0;
+    if (prof && !D->ev[0]) for (int i = 0; i < 4; i++) CU(cudaEventCreate(&D->ev[i]));
+    if (prof) CU(cudaEventRecord(D->ev[0], st));
     // K1
     int nw = std::min(32, std::max(1, nn));
     LAUNCH(k_tables, 1, nw * 32, 0, st, m->dev, pl.dev, d_x, m->d_pleaf);
     g_launches++;
+    if (prof) CU(cudaEventRecord(D->ev[1], st));
     // K2
     constexpr int NT = 128;
     if (pl.Kmax > NT) return fail(WHALE_ERR_CAPACITY, "K=%d tangent components exceed %d lanes (parameter chunking not built yet)", pl.Kmax, NT);
@@ -1028,6 +1038,7 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
     DPArgs a{m->dev, pl.dev, D->d_arena, D->d_hdr, D->d_perm, D->d_out_fam, keep ? D->d_ell : nullptr, F, keep ? 0 : 1};
     LAUNCH(k_dp<NT>, F, NT, smem, st, a);
     g_launches++;
+    if (prof) CU(cudaEventRecord(D->ev[2], st));
     // K3
     const int KR = pl.K[m->root];
     int nb = std::min(1024, (F + 255) / 256);
@@ -1035,6 +1046,8 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
     LAUNCH(k_reduce1, nb, 256, 0, st, D->d_out_fam, F, KR, chunk, D->d_partial);
     LAUNCH(k_reduce2, 1, 256, 0, st, D->d_partial, nb, KR, F, condition, pl.dev, m->root, m->P, d_out);
     g_launches += 2;
+    if (prof) CU(cudaEventRecord(D->ev[3], st));
+    D->ev_valid = prof;
     CU(cudaGetLastError());
     D->ell_valid = keep;
     return WHALE_OK;
@@ -1137,6 +1150,21 @@ int32_t whale_work_estimate(whale_model_t m, whale_data_t d, uint32_t flags, dou
     }
     if (flops) *flops = fl;
     if (bytes) *bytes = (double)d->algo_bytes + 8.0 * d->F * pl.K[m->root];
+    return WHALE_OK;
+}
+
+int32_t whale_last_kernel_ms(whale_data_t d, double* tables_ms, double* dp_ms, double* reduce_ms) {
+    if (!d) return fail(WHALE_ERR_ARG, "null argument");
+    if (!d->ev_valid) return fail(WHALE_ERR_STATE, "last evaluation was not run with WHALE_PROFILE");
+    CU(cudaSetDevice(d->m->device));
+    CU(cudaEventSynchronize(d->ev[3]));
+    float a = 0, b = 0, c = 0;
+    CU(cudaEventElapsedTime(&a, d->ev[0], d->ev[1]));
+    CU(cudaEventElapsedTime(&b, d->ev[1], d->ev[2]));
+    CU(cudaEventElapsedTime(&c, d->ev[2], d->ev[3]));
+    if (tables_ms) *tables_ms = a;
+    if (dp_ms) *dp_ms = b;
+    if (reduce_ms) *reduce_ms = c;
     return WHALE_OK;
 }
 

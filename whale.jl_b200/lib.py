@@ -15,14 +15,14 @@ LIB_PATH = os.path.join(_HERE, "libwhalecuda.so")
 
 i32p, i64p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double)
 
-WANT_GRAD, KEEP_ELL = 1, 2
+WANT_GRAD, KEEP_ELL, PROFILE = 1, 2, 4
 
 # every symbol include/whalecuda.h declares (tests check the built library exports all of them)
 SYMBOLS = ["whale_version", "whale_last_error", "whale_device_count", "whale_set_device", "whale_model_create",
            "whale_model_destroy", "whale_data_create", "whale_data_destroy", "whale_data_nfam",
            "whale_data_arena_bytes", "whale_data_arena_dump", "whale_logpdf_grad", "whale_logpdf_grad_async",
            "whale_slices", "whale_ell_size", "whale_ell_get", "whale_backtrack", "whale_launch_count",
-           "whale_work_estimate", "whale_fp64_peak"]
+           "whale_work_estimate", "whale_last_kernel_ms", "whale_fp64_peak"]
 
 
 class ModelDesc(C.Structure):
@@ -82,6 +82,7 @@ class Lib:
         L.whale_launch_count.restype = C.c_int64
         L.whale_work_estimate.argtypes = [vp, vp, C.c_uint32, f64p, f64p]
         L.whale_fp64_peak.argtypes = [f64p]
+        L.whale_last_kernel_ms.argtypes = [vp, f64p, f64p, f64p]
 
     def check(self, rc):
         if rc != 0:
@@ -154,6 +155,15 @@ class Lib:
         fl, by = C.c_double(), C.c_double()
         self.check(self.L.whale_work_estimate(mh, dh, WANT_GRAD if want_grad else 0, C.byref(fl), C.byref(by)))
         return fl.value, by.value
+
+    def last_kernel_ms(self, dh):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self.check(self.L.whale_last_kernel_ms(dh, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def logpdf_grad_async(self, mh, dh, d_x_ptr, condition, flags, d_out_ptr, stream_ptr):
+        """Device-resident evaluation enqueued on `stream_ptr` (a cudaStream_t as int); not synchronised."""
+        self.check(self.L.whale_logpdf_grad_async(mh, dh, d_x_ptr, condition, flags, d_out_ptr, stream_ptr))
 
     def fp64_peak(self) -> float:
         t = C.c_double()

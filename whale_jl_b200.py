@@ -1,8 +1,11 @@
-"""Import shim: the package directory is named `whale.jl_b200` (not an importable identifier), so this module
-exposes it as `whale_jl_b200` (with submodules `whale_jl_b200.lib`, `.core`, ...)."""
+"""Import shim: the package directory is named `whale.jl_b200` (not an importable identifier), so importing
+`whale_jl_b200` loads that directory as a regular package (submodules `whale_jl_b200.lib`, `.core`, ...)."""
+import importlib.util as _u
 import os as _os
+import sys as _sys
 
-__package__ = __name__
-__path__ = [_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "whale.jl_b200")]
-with open(_os.path.join(__path__[0], "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(__path__[0], "__init__.py"), "exec"))
+_dir = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "whale.jl_b200")
+_spec = _u.spec_from_file_location(__name__, _os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = _u.module_from_spec(_spec)
+_sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)
