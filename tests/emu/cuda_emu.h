@@ -54,11 +54,15 @@ struct Barrier {
     }
 };
 inline Barrier* g_bar = nullptr;
+inline std::vector<Barrier>* g_wbar = nullptr;
 inline unsigned char* g_smem = nullptr;
 inline void launch(int grid, int block, size_t smem, const std::function<void()>& body) {
     std::vector<unsigned char> sm(smem + 64);
     Barrier bar; bar.n = block;
     g_bar = &bar;
+    std::vector<Barrier> wb((block + 31) / 32);
+    for (size_t w = 0; w < wb.size(); w++) wb[w].n = std::min(32, block - (int)w * 32);
+    g_wbar = &wb;
     g_smem = (unsigned char*)(((uintptr_t)sm.data() + 15) & ~(uintptr_t)15);
     for (int b = 0; b < grid; b++) {
         std::vector<std::thread> th;
@@ -72,6 +76,7 @@ inline void launch(int grid, int block, size_t smem, const std::function<void()>
 }
 }  // namespace emu
 inline void __syncthreads() { emu::g_bar->wait(); }
+inline void __syncwarp() { (*emu::g_wbar)[threadIdx.x / 32].wait(); }
 #define EXTERN_SHARED(name) unsigned char* name = emu::g_smem
 
 // ---- runtime API subset ----
@@ -100,6 +105,9 @@ inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 inline cudaError_t cudaDeviceSynchronize() { return 0; }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
+enum { cudaEventDisableTiming = 2 };
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new std::remove_pointer<cudaEvent_t>::type(); return 0; }
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new std::remove_pointer<cudaEvent_t>::type(); return 0; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = std::chrono::steady_clock::now(); return 0; }

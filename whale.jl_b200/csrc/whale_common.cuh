@@ -1,0 +1,121 @@
+// Shared device-side structures of libwhalecuda (see whalecuda.cu for the overview).
+#pragma once
+#ifdef WHALE_EMU
+// Test-only build: tests/emu/cuda_emu.h maps the CUDA constructs used here onto host threads so the
+// kernel logic can be exercised on a machine without a GPU.  Never shipped, never loaded by the package.
+#include "cuda_emu.h"
+#define LAUNCH(kern, grid, block, smem, st, ...) emu::launch(grid, block, smem, [=]() { kern(__VA_ARGS__); })
+#else
+#include <cuda_runtime.h>
+#define LAUNCH(kern, grid, block, smem, st, ...) kern<<<grid, block, smem, st>>>(__VA_ARGS__)
+#define EXTERN_SHARED(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+#include <cstdint>
+
+#include "../../include/whalecuda.h"
+
+// one resolved clade-split term p * X[i1] * Y[i2]; indices are LOCAL cell indices of the branch row they
+// address (the reference resolves index[γ,e] at run time, src/ccd.jl:41-49; the packer does it once)
+struct __align__(16) Ent {
+    uint16_t i1, i2;
+    uint32_t pad;
+    double p;
+};
+static_assert(sizeof(Ent) == 16, "Ent must be 16 bytes");
+
+// per family, per species-tree node; offsets are relative to the family blob
+struct NodeRec {
+    uint32_t C;         // compatible clades (columns of ℓ[e])
+    uint32_t nonleaf;   // how many are non-leaf clades (they come last: clades are size-sorted)
+    uint32_t dptr_off;  // u32-word offset (multiple of 4) of dptr[C+1]: same-branch terms
+                        //   (within-branch duplication :178-185, Πwgdretention :187-194, Πroot :151-158)
+    uint32_t dent_off;  // 16-byte-entry offset of those terms
+    uint32_t ndent;
+    uint32_t tptr_off;  // u32-word offset (multiple of 4) of [tptr[C+1] | lossF[C] | lossG[C] | lev[nlev+1]]
+                        //   speciation terms at row 1 (:160-170), Πloss child indices (:172-176), root levels
+    uint32_t tent_off;
+    uint32_t ntent;
+};
+static_assert(sizeof(NodeRec) == 32, "NodeRec must be 32 bytes");
+
+struct FamHdr {
+    uint64_t base;         // byte offset of the blob in the arena (16-byte aligned)
+    uint64_t ell_off;      // offset (doubles) of this family's ℓ in the keep_ell buffer
+    uint32_t G;            // clades
+    uint32_t nlev;         // root levels (distinct clade sizes)
+    uint32_t rows_len[2];  // Σ_e C_e K_e per tangent plan (doubles)
+    uint32_t scr_len[2];   // scratch row length per plan (doubles)
+    uint32_t leafmax[2];   // max over leaf branches of C_e K_e per plan
+    uint32_t stage_bytes;  // staging buffer for one node's lists
+    uint32_t blob_bytes;
+};
+
+constexpr int MAX_WARPS = 8;  // scratch is sized for up to 8 warps working on leaf branches concurrently
+
+struct ModelDev {  // structure arrays (device pointers), node index = id-1
+    int nn;
+    const int* order;
+    const int* child0;
+    const int* child1;
+    const int* kind;
+    const int* nsl;
+    const double* dt;
+    const double* leafP;
+    const int* lam_slot;
+    const int* mu_slot;
+    const int* q_slot;
+    int eta_slot;
+    int log_scale;
+    int root;
+    int nlvl;              // nodes grouped by height (k_tables schedule)
+    const int* lvl_off;
+    const int* lvl_nodes;
+    int nleafnodes;        // leaf nodes, then the remaining nodes in processing order (k_dp schedule)
+    const int* leafnodes;
+    int ninner;
+    const int* inner;
+};
+
+struct PlanDev {  // tangent plan: which raw parameters each branch carries
+    int Kmax;
+    const int* K;          // [nn]
+    const int* act;        // [nn*Kmax] global parameter id of component k (act[e][0] = -1)
+    const int16_t* cmap;   // [nn*2*Kmax] component index in child j of parent's component k, or -1
+    const uint8_t* role;   // [nn*Kmax] bit0 own λ, bit1 own μ, bit2 own q, bit3 η
+    const int* toff;       // [nn] offset (doubles) of node e's table: (n_e+1) rows × K_e
+    double* eps;           // [tab_len]  ϵ rows (component-major within a row)
+    double2* pp;           // [tab_len]  (ϕ, ψ) rows
+    double2* uv;           // [tab_len]  projective ϵ = u/v (k_tables scratch)
+    double* ab;            // [nn*Kmax*2] per-branch (α, β) components
+    double* cx;            // [nn*Kmax]  row-1 coefficient X (WGD: 1−q+2qϵ_f ; root: (1−η)ξ/η)
+    double* cy;            // [nn*Kmax]  row-1 coefficient Y (WGD: q ; root: η(1−ϵ)/ξ²)
+    double* leaf;          // [nn*Kmax]  last-row value of a leaf clade on leaf branch e
+    double* cond;          // [3*Kmax]   condition() per kind, components of the root
+};
+
+// one-partial dual number: each lane carries the value and ITS tangent component
+struct D1 {
+    double v, d;
+};
+__device__ __forceinline__ D1 mk(double v, double d = 0.0) { return D1{v, d}; }
+__device__ __forceinline__ D1 operator+(D1 a, D1 b) { return D1{a.v + b.v, a.d + b.d}; }
+__device__ __forceinline__ D1 operator-(D1 a, D1 b) { return D1{a.v - b.v, a.d - b.d}; }
+__device__ __forceinline__ D1 operator*(D1 a, D1 b) { return D1{a.v * b.v, a.d * b.v + a.v * b.d}; }
+__device__ __forceinline__ D1 operator/(D1 a, D1 b) {
+    double q = a.v / b.v;
+    return D1{q, (a.d - q * b.d) / b.v};
+}
+__device__ __forceinline__ D1 operator+(double a, D1 b) { return D1{a + b.v, b.d}; }
+__device__ __forceinline__ D1 operator-(double a, D1 b) { return D1{a - b.v, -b.d}; }
+__device__ __forceinline__ D1 operator-(D1 a, double b) { return D1{a.v - b, a.d}; }
+__device__ __forceinline__ D1 operator*(double a, D1 b) { return D1{a * b.v, a * b.d}; }
+__device__ __forceinline__ D1 dexp(D1 a) {
+    double e = exp(a.v);
+    return D1{e, e * a.d};
+}
+__device__ __forceinline__ D1 dlog(D1 a) { return D1{log(a.v), a.d / a.v}; }
+__device__ __forceinline__ D1 dpowi(D1 a, int n) {  // a^n, n >= 0
+    double p = pow(a.v, (double)n);
+    return D1{p, n == 0 ? 0.0 : (double)n * (p / a.v) * a.d};
+}
+__device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }

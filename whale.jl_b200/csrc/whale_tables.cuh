@@ -1,0 +1,143 @@
+// K1 — slice tables (ϵ, ϕ, ψ) with forward tangents.  src/model.jl:162-191, src/bdputil.jl:6-11.
+//
+// The reference iterates ϵ_i = (α + (1−α−β)ϵ_{i−1}) / (1 − βϵ_{i−1}) slice by slice — one fp64 division on
+// the dependent chain per slice.  All slices of a branch share (α, β) (uniform Δt, src/model.jl:20), so the
+// step is ONE Möbius map; in projective form ϵ = u/v it is linear and division-free:
+//     u_i = (1−α−β) u_{i−1} + α v_{i−1},      v_i = v_{i−1} − β u_{i−1}
+// and 1 − βϵ_{i−1} = v_i / v_{i−1}, so  ϕ_i = g (v_{i−1}/v_i)²,  ψ_i = g β (v_{i−1}/v_i)³,  ϵ_i = u_i/v_i  with
+// g = (1−α)(1−β).  Phase A runs that short FMA chain per (node, component) level by level (children first);
+// phase B evaluates all rows of all nodes in parallel (the divisions are now independent).  The same exact
+// composition as the reference up to rounding (≲1e-14), including its value-based critical-case test.
+#pragma once
+#include "whale_common.cuh"
+
+__device__ __forceinline__ D1 child_eps_last(const ModelDev& M, const PlanDev& PL, int e, int j, int child, int k) {
+    const int Kc = PL.K[child];
+    const double2* row = PL.uv + PL.toff[child] + (size_t)M.nsl[child] * Kc;
+    const int kc = k == 0 ? 0 : PL.cmap[(e * 2 + j) * PL.Kmax + k];
+    const double2 a = row[0];
+    D1 u = mk(a.x), v = mk(a.y);
+    if (k > 0 && kc >= 0) {
+        const double2 b = row[kc];
+        u.d = b.x;
+        v.d = b.y;
+    }
+    return u / v;
+}
+
+__global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const double* __restrict__ x,
+                                                 const double* __restrict__ pleaf) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const double NaN = __longlong_as_double(0x7ff8000000000000LL);
+    // ---- phase A: per level, one warp per node, lanes over components; division-free chain ----
+    for (int L = 0; L < M.nlvl; L++) {
+        const int n0 = M.lvl_off[L], n1 = M.lvl_off[L + 1];
+        for (int j = n0 + warp; j < n1; j += nwarp) {
+            const int e = M.lvl_nodes[j];
+            const int K = PL.K[e], kind = M.kind[e], n = M.nsl[e];
+            for (int k = lane; k < K; k += 32) {
+                const unsigned role = k == 0 ? 0u : PL.role[e * PL.Kmax + k];
+                // getθ (src/rmodels.jl:31-33,55-64): raw -> rate, with the chain factor of the log scale
+                const int ls = M.lam_slot[e], ms = M.mu_slot[e];
+                const double lv = ls < 0 ? NaN : (M.log_scale ? exp(x[ls]) : x[ls]);
+                const double mv = ms < 0 ? NaN : (M.log_scale ? exp(x[ms]) : x[ms]);
+                const D1 lam = mk(lv, (role & 1u) ? (M.log_scale ? lv : 1.0) : 0.0);
+                const D1 mu = mk(mv, (role & 2u) ? (M.log_scale ? mv : 1.0) : 0.0);
+                D1 ep;
+                if (kind == WHALE_LEAF) {  // setnode! src/model.jl:170
+                    ep = mk(pleaf ? pleaf[e] : 0.0);
+                } else if (kind == WHALE_WGD) {  // setwgdnode! src/model.jl:175-180
+                    const D1 q = mk(x[M.q_slot[e]], (role & 4u) ? 1.0 : 0.0);
+                    const D1 ec = child_eps_last(M, PL, e, 0, M.child0[e], k);
+                    ep = q * (ec * ec) + (1.0 - q) * ec;
+                    const D1 w = (1.0 - q) + 2.0 * (q * ec);  // Πwgdloss coefficient src/core.jl:198
+                    PL.cx[e * PL.Kmax + k] = k == 0 ? w.v : w.d;
+                    PL.cy[e * PL.Kmax + k] = k == 0 ? q.v : q.d;
+                } else {  // internal / root: product of the children's last ϵ
+                    const D1 ef = child_eps_last(M, PL, e, 0, M.child0[e], k);
+                    const D1 eg = child_eps_last(M, PL, e, 1, M.child1[e], k);
+                    ep = ef * eg;
+                    if (kind == WHALE_ROOT) {  // whaleroot! src/core.jl:131-147 ; condition src/condition.jl
+                        const D1 eta = mk(x[M.eta_slot], (role & 8u) ? 1.0 : 0.0);
+                        const D1 xi = 1.0 - (1.0 - eta) * ep;
+                        const D1 A = (1.0 - eta) * xi / eta;
+                        const D1 B = eta * (1.0 - ep) / (xi * xi);
+                        PL.cx[e * PL.Kmax + k] = k == 0 ? A.v : A.d;
+                        PL.cy[e * PL.Kmax + k] = k == 0 ? B.v : B.d;
+                        // geompgf(η, s) = ηs/(1−(1−η)s)  src/bdputil.jl:67
+                        const D1 gr = eta * ep / (1.0 - (1.0 - eta) * ep);
+                        const D1 gf = eta * ef / (1.0 - (1.0 - eta) * ef);
+                        const D1 gg = eta * eg / (1.0 - (1.0 - eta) * eg);
+                        const D1 pr = ((1.0 - gf) - gg) + gr;  // RootCondition :21-29
+                        const D1 pn = 1.0 - gr;                // NonExtinctCondition :15-18
+                        const D1 cr = pr.v > 0.0 ? dlog(pr) : mk(-dinf(), 0.0);
+                        const D1 cn = dlog(pn);
+                        PL.cond[0 * PL.Kmax + k] = 0.0;
+                        PL.cond[1 * PL.Kmax + k] = k == 0 ? cr.v : cr.d;
+                        PL.cond[2 * PL.Kmax + k] = k == 0 ? cn.v : cn.d;
+                    }
+                }
+                double2* uvrow = PL.uv + PL.toff[e];
+                D1 u = ep, v = mk(1.0);
+                uvrow[k] = k == 0 ? make_double2(u.v, v.v) : make_double2(u.d, v.d);
+                D1 a = mk(0.0), b = mk(0.0);
+                if (n > 0) {
+                    // getα src/bdputil.jl:6-7 (critical branch decided on VALUES, like isapprox on Duals)
+                    const double t = M.dt[e];
+                    if (fabs(lam.v - mu.v) <= 1e-6) {
+                        a = (lam * mk(t)) / (1.0 + lam * mk(t));
+                    } else {
+                        const D1 ex = dexp(mk(t) * (lam - mu));
+                        a = mu * (ex - 1.0) / (lam * ex - mu);
+                    }
+                    b = (lam / mu) * a;
+                    const D1 c = (1.0 - a) - b;
+                    for (int i = 1; i <= n; i++) {
+                        const D1 un = c * u + a * v;
+                        const D1 vn = v - b * u;
+                        u = un;
+                        v = vn;
+                        uvrow[(size_t)i * K + k] = k == 0 ? make_double2(u.v, v.v) : make_double2(u.d, v.d);
+                    }
+                }
+                PL.ab[(e * PL.Kmax + k) * 2 + 0] = k == 0 ? a.v : a.d;
+                PL.ab[(e * PL.Kmax + k) * 2 + 1] = k == 0 ? b.v : b.d;
+                if (kind == WHALE_LEAF) {
+                    // leaf clade on a leaf branch: ℓ_n = leafℙ·Π_i ϕ_i = leafℙ·gⁿ·(v_0/v_n)²  (src/core.jl:94,123)
+                    const D1 g = (1.0 - a) * (1.0 - b);
+                    const D1 r = mk(1.0) / v;
+                    const D1 lf = mk(M.leafP[e]) * dpowi(g, n) * (r * r);
+                    PL.leaf[e * PL.Kmax + k] = k == 0 ? lf.v : lf.d;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- phase B: every row of every node in parallel ----
+    for (int e = 0; e < M.nn; e++) {
+        const int K = PL.K[e], n = M.nsl[e];
+        const double2* uvrow = PL.uv + PL.toff[e];
+        double* erow = PL.eps + PL.toff[e];
+        double2* prow = PL.pp + PL.toff[e];
+        for (int idx = threadIdx.x; idx < (n + 1) * K; idx += blockDim.x) {
+            const int i = idx / K, k = idx - i * K;
+            const double2 w0 = uvrow[(size_t)i * K], wk = uvrow[(size_t)i * K + k];
+            const D1 u = mk(w0.x, k == 0 ? 0.0 : wk.x), v = mk(w0.y, k == 0 ? 0.0 : wk.y);
+            const D1 ep = u / v;
+            erow[idx] = k == 0 ? ep.v : ep.d;
+            if (i == 0) {
+                prow[idx] = make_double2(k == 0 ? 1.0 : 0.0, k == 0 ? 1.0 : 0.0);  // ϕ_1 = 1 (src/model.jl:171)
+                continue;
+            }
+            const double2 p0 = uvrow[(size_t)(i - 1) * K], pk = uvrow[(size_t)(i - 1) * K + k];
+            const D1 vp = mk(p0.y, k == 0 ? 0.0 : pk.y);
+            const D1 a = mk(PL.ab[(e * PL.Kmax) * 2], k == 0 ? 0.0 : PL.ab[(e * PL.Kmax + k) * 2]);
+            const D1 b = mk(PL.ab[(e * PL.Kmax) * 2 + 1], k == 0 ? 0.0 : PL.ab[(e * PL.Kmax + k) * 2 + 1]);
+            const D1 g = (1.0 - a) * (1.0 - b);
+            const D1 r = vp / v;  // 1 / (1 − βϵ_{i−1})
+            const D1 phi = g * (r * r);
+            const D1 psi = (g * b) * (r * r * r);
+            prow[idx] = make_double2(k == 0 ? phi.v : phi.d, k == 0 ? psi.v : psi.d);
+        }
+    }
+}

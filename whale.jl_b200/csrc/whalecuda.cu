@@ -1,31 +1,27 @@
 // libwhalecuda — B200 (sm_100a) engine for Whale.jl's ALE/DLWGD likelihood + forward-mode gradient.
 //
 // Hot path replaced (reference paths relative to the reference checkout):
-//   slice tables   src/model.jl:162-191, src/bdputil.jl:6-11          -> k_tables
-//   the DP         src/core.jl:83-199 (whale!/whalewgd!/whaleroot!)   -> k_dp
-//   Σ − N·cond     src/core.jl:46-64, src/condition.jl:11-29          -> k_reduce1/2
+//   slice tables   src/model.jl:162-191, src/bdputil.jl:6-11          -> k_tables   (whale_tables.cuh)
+//   the DP         src/core.jl:83-199 (whale!/whalewgd!/whaleroot!)   -> k_dp       (whale_dp.cuh)
+//   Σ − N·cond     src/core.jl:46-64, src/condition.jl:11-29          -> k_reduce1/2 (whale_reduce.cuh)
 // Forward tangents replace ForwardDiff duals: every ℓ cell carries K_e = 1 + (#parameters that can
 // influence branch e) components; lanes span (clade cell × component).
 //
 // Data layout in HBM (built once by whale_data_create, the read_ale-time packer):
-//   FamHdr[F]   : per family {arena byte offset, Γ, #root levels, ℓ offset, work}
-//   arena blob  : per family  NodeRec[n_nodes] | per-node u32 CSR pointers | 16-byte triple entries
+//   FamHdr[F]   : per family {arena byte offset, Γ, #root levels, ℓ offset, shared-memory budget}
+//   arena blob  : per family  NodeRec[n_nodes] | per-node u32 CSR pointers | 16-byte term entries
 //                 {u16 i1, u16 i2, f64 p} with indices already resolved to the *local* cell index of the
 //                 branch they are used in (the reference resolves index[γ,e] at run time, src/ccd.jl:41-49)
 // On chip: one CTA per family; the last row of every branch (C_e × K_e doubles) lives in shared memory,
-// slices ping-pong between that row and a scratch row, one barrier per slice.  No tensor cores: the DP
-// is an irregular gather–multiply–accumulate in fp64.
+// slices ping-pong between that row and a scratch row.  Families are binned by shared-memory need and the
+// bins launched concurrently so ragged inputs do not drag occupancy down to the largest family.
+// No tensor cores: the DP is an irregular gather–multiply–accumulate in fp64.
 //
 // There is NO CPU fallback in this file: every entry point that computes needs a CUDA device.
-#ifdef WHALE_EMU
-// Test-only build: tests/emu/cuda_emu.h maps the CUDA constructs used here onto host threads so the
-// kernel logic can be exercised on a machine without a GPU.  Never shipped, never loaded by the package.
-#include "cuda_emu.h"
-#define LAUNCH(kern, grid, block, smem, st, ...) emu::launch(grid, block, smem, [=]() { kern(__VA_ARGS__); })
-#else
-#include <cuda_runtime.h>
-#define LAUNCH(kern, grid, block, smem, st, ...) kern<<<grid, block, smem, st>>>(__VA_ARGS__)
-#endif
+#include "whale_common.cuh"
+#include "whale_tables.cuh"
+#include "whale_dp.cuh"
+#include "whale_reduce.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -33,13 +29,12 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <numeric>
 #include <string>
 #include <vector>
-
-#include "../../include/whalecuda.h"
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -61,496 +56,6 @@ static int32_t fail(int32_t code, const char* fmt, ...) {
             return fail(WHALE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e),    \
                         __FILE__, __LINE__);                                                       \
     } while (0)
-
-// ------------------------------------------------------------------------------------------------
-// device-side structures
-// ------------------------------------------------------------------------------------------------
-struct __align__(16) Ent {  // one resolved clade-split term: p * X[i1] * Y[i2]
-    uint16_t i1, i2;
-    uint32_t pad;
-    double p;
-};
-static_assert(sizeof(Ent) == 16, "Ent must be 16 bytes");
-
-#ifndef WHALE_EMU
-#define EXTERN_SHARED(name) extern __shared__ __align__(16) unsigned char name[]
-#endif
-
-struct NodeRec {        // per family, per species-tree node (all offsets relative to the family blob)
-    uint32_t C;         // compatible clades (columns of ℓ[e])
-    uint32_t nonleaf;   // how many of them are non-leaf clades (they come last: clades are size-sorted)
-    uint32_t dptr_off;  // u32-word offset of dptr[C+1]  (within-branch / WGD / Πroot terms)
-    uint32_t dent_off;  // 16-byte-entry offset of the entries dptr points into
-    uint32_t tptr_off;  // u32-word offset of tptr[C+1]  (speciation terms at row 1; internal/root only)
-    uint32_t tent_off;  // 16-byte-entry offset of the speciation entries
-    uint32_t loss_off;  // u32-word offset of lossF[C], lossG[C] (int32 local index in child or -1)
-    uint32_t lev_off;   // root only: u32-word offset of level pointers lev[nlev+1]
-};
-
-struct FamHdr {
-    uint64_t base;     // byte offset of the blob in the arena
-    uint64_t ell_off;  // offset (doubles) of this family's ℓ in the keep_ell buffer
-    uint32_t G;        // clades
-    uint32_t nlev;     // root levels (distinct clade sizes)
-    uint32_t sumC;     // Σ_e C_e
-    uint32_t maxC;     // max_e C_e
-};
-
-struct ModelDev {  // structure arrays (device pointers), node index = id-1
-    int nn;
-    const int* order;
-    const int* child0;
-    const int* child1;
-    const int* kind;
-    const int* nsl;
-    const double* dt;
-    const double* leafP;
-    const int* lam_slot;
-    const int* mu_slot;
-    const int* q_slot;
-    int eta_slot;
-    int log_scale;
-    int root;
-    // tables-kernel schedule: nodes grouped by height
-    int nlvl;
-    const int* lvl_off;
-    const int* lvl_nodes;
-};
-
-struct PlanDev {  // tangent plan: which raw parameters each branch carries
-    int Kmax;
-    const int* K;          // [nn]
-    const int* act;        // [nn*Kmax] global parameter id of component k (act[e][0] = -1)
-    const int16_t* cmap;   // [nn*2*Kmax] component index in child j of parent's component k, or -1
-    const uint8_t* role;   // [nn*Kmax] bit0 own λ, bit1 own μ, bit2 own q, bit3 η
-    const int* toff;       // [nn] offset (doubles) of node e's table: (n_e+1) rows × K_e
-    // tables written by k_tables
-    double* eps;           // [tab_len]           ϵ rows (component-major within a row)
-    double2* pp;           // [tab_len]           (ϕ, ψ) rows
-    double* cx;            // [nn*Kmax]  row-1 coefficient X (WGD: 1−q+2qϵ_f ; root: (1−η)ξ/η)
-    double* cy;            // [nn*Kmax]  row-1 coefficient Y (WGD: q ; root: η(1−ϵ)/ξ²)
-    double* leaf;          // [nn*Kmax]  last-row value of a leaf clade on leaf branch e
-    double* cond;          // [3*Kmax]   condition() per kind, components of the root
-};
-
-// ------------------------------------------------------------------------------------------------
-// one-partial dual number: each lane carries the value and ITS tangent component
-// ------------------------------------------------------------------------------------------------
-struct D1 {
-    double v, d;
-};
-__device__ __forceinline__ D1 mk(double v, double d = 0.0) { return D1{v, d}; }
-__device__ __forceinline__ D1 operator+(D1 a, D1 b) { return D1{a.v + b.v, a.d + b.d}; }
-__device__ __forceinline__ D1 operator-(D1 a, D1 b) { return D1{a.v - b.v, a.d - b.d}; }
-__device__ __forceinline__ D1 operator*(D1 a, D1 b) { return D1{a.v * b.v, a.d * b.v + a.v * b.d}; }
-__device__ __forceinline__ D1 operator/(D1 a, D1 b) {
-    double q = a.v / b.v;
-    return D1{q, (a.d - q * b.d) / b.v};
-}
-__device__ __forceinline__ D1 operator+(double a, D1 b) { return D1{a + b.v, b.d}; }
-__device__ __forceinline__ D1 operator-(double a, D1 b) { return D1{a - b.v, -b.d}; }
-__device__ __forceinline__ D1 operator-(D1 a, double b) { return D1{a.v - b, a.d}; }
-__device__ __forceinline__ D1 operator*(double a, D1 b) { return D1{a * b.v, a * b.d}; }
-__device__ __forceinline__ D1 dexp(D1 a) {
-    double e = exp(a.v);
-    return D1{e, e * a.d};
-}
-__device__ __forceinline__ D1 dlog(D1 a) { return D1{log(a.v), a.d / a.v}; }
-
-// ------------------------------------------------------------------------------------------------
-// K1: slice tables (ϵ, ϕ, ψ) with tangents.  src/model.jl:162-191, src/bdputil.jl:6-11.
-// One CTA; nodes of equal height are independent -> one warp per node, lanes over components.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ D1 child_eps_last(const ModelDev& M, const PlanDev& PL, int e, int j, int child,
-                                              int k) {
-    int Kc = PL.K[child];
-    const double* row = PL.eps + PL.toff[child] + (size_t)M.nsl[child] * Kc;
-    int kc = k == 0 ? 0 : PL.cmap[(e * 2 + j) * PL.Kmax + k];
-    return mk(row[0], (k == 0 || kc < 0) ? 0.0 : row[kc]);
-}
-
-__global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const double* __restrict__ x,
-                                                 const double* __restrict__ pleaf) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    const double NaN = __longlong_as_double(0x7ff8000000000000LL);
-    for (int L = 0; L < M.nlvl; L++) {
-        int n0 = M.lvl_off[L], n1 = M.lvl_off[L + 1];
-        for (int j = n0 + warp; j < n1; j += nwarp) {
-            const int e = M.lvl_nodes[j];
-            const int K = PL.K[e], kind = M.kind[e], n = M.nsl[e];
-            for (int k = lane; k < K; k += 32) {
-                const unsigned role = k == 0 ? 0u : PL.role[e * PL.Kmax + k];
-                // getθ (src/rmodels.jl:31-33,55-64): raw -> rate, with the chain factor for the log scale
-                D1 lam, mu;
-                {
-                    int ls = M.lam_slot[e], ms = M.mu_slot[e];
-                    double lv = ls < 0 ? NaN : (M.log_scale ? exp(x[ls]) : x[ls]);
-                    double mv = ms < 0 ? NaN : (M.log_scale ? exp(x[ms]) : x[ms]);
-                    lam = mk(lv, (role & 1u) ? (M.log_scale ? lv : 1.0) : 0.0);
-                    mu = mk(mv, (role & 2u) ? (M.log_scale ? mv : 1.0) : 0.0);
-                }
-                D1 ep;
-                D1 q = mk(0.0);
-                if (kind == WHALE_LEAF) {  // setnode! src/model.jl:170
-                    ep = mk(pleaf ? pleaf[e] : 0.0);
-                } else if (kind == WHALE_WGD) {  // setwgdnode! src/model.jl:175-180
-                    q = mk(x[M.q_slot[e]], (role & 4u) ? 1.0 : 0.0);
-                    D1 ec = child_eps_last(M, PL, e, 0, M.child0[e], k);
-                    ep = q * (ec * ec) + (1.0 - q) * ec;
-                    D1 w = (1.0 - q) + 2.0 * (q * ec);  // Πwgdloss coefficient src/core.jl:198
-                    PL.cx[e * PL.Kmax + k] = k == 0 ? w.v : w.d;
-                    PL.cy[e * PL.Kmax + k] = k == 0 ? q.v : q.d;
-                } else {  // internal / root: product of the children's last ϵ
-                    D1 ef = child_eps_last(M, PL, e, 0, M.child0[e], k);
-                    D1 eg = child_eps_last(M, PL, e, 1, M.child1[e], k);
-                    ep = ef * eg;
-                    if (kind == WHALE_ROOT) {  // whaleroot! src/core.jl:131-147 ; condition src/condition.jl
-                        D1 eta = mk(x[M.eta_slot], (role & 8u) ? 1.0 : 0.0);
-                        D1 xi = 1.0 - (1.0 - eta) * ep;
-                        D1 A = (1.0 - eta) * xi / eta;
-                        D1 B = eta * (1.0 - ep) / (xi * xi);
-                        PL.cx[e * PL.Kmax + k] = k == 0 ? A.v : A.d;
-                        PL.cy[e * PL.Kmax + k] = k == 0 ? B.v : B.d;
-                        // geompgf(η, s) = ηs/(1−(1−η)s)  src/bdputil.jl:67
-                        D1 gr = eta * ep / (1.0 - (1.0 - eta) * ep);
-                        D1 gf = eta * ef / (1.0 - (1.0 - eta) * ef);
-                        D1 gg = eta * eg / (1.0 - (1.0 - eta) * eg);
-                        D1 pr = ((1.0 - gf) - gg) + gr;          // RootCondition :21-29
-                        D1 pn = 1.0 - gr;                        // NonExtinctCondition :15-18
-                        double inf = __longlong_as_double(0x7ff0000000000000LL);
-                        D1 cr = pr.v > 0.0 ? dlog(pr) : mk(-inf, 0.0);
-                        D1 cn = dlog(pn);
-                        PL.cond[0 * PL.Kmax + k] = 0.0;
-                        PL.cond[1 * PL.Kmax + k] = k == 0 ? cr.v : cr.d;
-                        PL.cond[2 * PL.Kmax + k] = k == 0 ? cn.v : cn.d;
-                    }
-                }
-                double* erow = PL.eps + PL.toff[e];
-                double2* prow = PL.pp + PL.toff[e];
-                erow[k] = k == 0 ? ep.v : ep.d;
-                prow[k] = make_double2(k == 0 ? 1.0 : 0.0, k == 0 ? 1.0 : 0.0);
-                if (n > 0) {
-                    // getα src/bdputil.jl:6-7 (critical branch decided on VALUES, like isapprox on Duals)
-                    const double t = M.dt[e];
-                    D1 a;
-                    if (fabs(lam.v - mu.v) <= 1e-6) {
-                        a = (lam * mk(t)) / (1.0 + lam * mk(t));
-                    } else {
-                        D1 ex = dexp(mk(t) * (lam - mu));
-                        a = mu * (ex - 1.0) / (lam * ex - mu);
-                    }
-                    D1 b = (lam / mu) * a;
-                    D1 oma = 1.0 - a, omb = 1.0 - b;
-                    D1 g = oma * omb;
-                    D1 lf = mk(M.leafP[e]);  // leaf clade on a leaf branch: ℓ_i = ϕ_i ℓ_{i−1} (src/core.jl:94,123)
-                    for (int i = 1; i <= n; i++) {  // setslices! src/model.jl:182-191
-                        D1 den = 1.0 - b * ep;
-                        D1 inv = mk(1.0) / den;
-                        D1 phi = g * (inv * inv);
-                        D1 psi = (g * b) * (inv * inv * inv);
-                        ep = (a + (oma - b) * ep) * inv;
-                        erow[(size_t)i * K + k] = k == 0 ? ep.v : ep.d;
-                        prow[(size_t)i * K + k] = make_double2(k == 0 ? phi.v : phi.d, k == 0 ? psi.v : psi.d);
-                        lf = phi * lf;
-                    }
-                    if (kind == WHALE_LEAF) PL.leaf[e * PL.Kmax + k] = k == 0 ? lf.v : lf.d;
-                } else if (kind == WHALE_LEAF) {
-                    PL.leaf[e * PL.Kmax + k] = k == 0 ? M.leafP[e] : 0.0;
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K2: the DP.  One CTA per family, NT threads; lanes span (cell, component).
-// ------------------------------------------------------------------------------------------------
-struct DPArgs {
-    ModelDev M;
-    PlanDev PL;
-    const unsigned char* arena;
-    const FamHdr* hdr;
-    const int* perm;   // launch order (decreasing work)
-    double* out_fam;   // [F * Kroot]  (log L_f, ∂ log L_f / ∂ component)
-    double* ell;       // keep_ell buffer or nullptr
-    int nfam;
-    int skip_leaf;     // share family-independent leaf-branch rows (off in keep_ell mode)
-};
-
-// Σ_t p_t X[i1] Y[i2] with the product rule for the lane's component; m = 0 for the value lane.
-__device__ __forceinline__ void pairsum(const Ent* __restrict__ ents, uint32_t tb, uint32_t te,
-                                        const double* __restrict__ X, int KX, int kx,
-                                        const double* __restrict__ Y, int KY, int ky, double m, double& S0,
-                                        double& Sk) {
-    double s0 = 0.0, sk = 0.0;
-    for (uint32_t t = tb; t < te; t++) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(ents + t));
-        const double p = __hiloint2double((int)raw.w, (int)raw.z);
-        const double* xp = X + (size_t)(raw.x & 0xffffu) * KX;
-        const double* yp = Y + (size_t)(raw.x >> 16) * KY;
-        double x0 = xp[0], y0 = yp[0];
-        double xk = kx >= 0 ? xp[kx] : 0.0;
-        double yk = ky >= 0 ? yp[ky] : 0.0;
-        double px = p * x0;
-        s0 = fma(px, y0, s0);
-        sk = fma(px, yk, sk);
-        sk = fma(m * (p * y0), xk, sk);
-    }
-    S0 = s0;
-    Sk = sk;
-}
-
-template <int NT>
-__global__ void __launch_bounds__(NT) k_dp(DPArgs A) {
-    EXTERN_SHARED(smem_raw);
-    const int tid = threadIdx.x;
-    const ModelDev& M = A.M;
-    const PlanDev& PL = A.PL;
-    const int nn = M.nn, Kmax = PL.Kmax;
-    const int fam = A.perm[blockIdx.x];
-    const FamHdr H = A.hdr[fam];
-    const unsigned char* blob = A.arena + H.base;
-    const NodeRec* nrec = reinterpret_cast<const NodeRec*>(blob);
-    const uint32_t* words = reinterpret_cast<const uint32_t*>(blob);
-    const Ent* ents = reinterpret_cast<const Ent*>(blob);
-
-    int* s_roff = reinterpret_cast<int*>(smem_raw);          // [nn+1] row offsets (doubles)
-    double* rows = reinterpret_cast<double*>(smem_raw + (((nn + 1) * sizeof(int) + 15) & ~size_t(15)));
-    if (tid == 0) {
-        int o = 0;
-        for (int e = 0; e < nn; e++) {
-            s_roff[e] = o;
-            o += (int)nrec[e].C * PL.K[e];
-        }
-        s_roff[nn] = o;
-    }
-    __syncthreads();
-    double* scr = rows + s_roff[nn];
-
-    for (int oi = 0; oi < nn; oi++) {
-        const int e = M.order[oi];
-        const NodeRec R = nrec[e];
-        const int C = (int)R.C;
-        if (C == 0) continue;
-        const int kind = M.kind[e], K = PL.K[e], n = M.nsl[e];
-        double* fin = rows + s_roff[e];
-        double* ellp = A.ell ? A.ell + H.ell_off : nullptr;
-        size_t ell_e = 0;
-        if (ellp) {  // offset of node e's matrix in the family's ℓ (node-index order)
-            for (int e2 = 0; e2 < e; e2++) ell_e += (size_t)(M.nsl[e2] + 1) * nrec[e2].C;
-            ellp += ell_e;
-        }
-        // lane -> (cell group, component): groups of K lanes, GP groups per pass
-        const int GP = NT / K;            // K <= NT is guaranteed by the host
-        const int grp = tid / K, k = tid - grp * K;
-        const bool lane_on = grp < GP;
-        const double m = k == 0 ? 0.0 : 1.0;
-
-        if (kind == WHALE_LEAF && R.nonleaf == 0 && A.skip_leaf) {
-            // every compatible clade is a leaf clade: the last row is family-independent (k_tables)
-            if (lane_on)
-                for (int c = grp; c < C; c += GP) fin[c * K + k] = PL.leaf[e * Kmax + k];
-            __syncthreads();
-            continue;
-        }
-
-        if (kind == WHALE_ROOT) {
-            // whaleroot! src/core.jl:130-149: clades ascending in size, level-synchronous
-            const int f = M.child0[e], g = M.child1[e];
-            const int KF = PL.K[f], KG = PL.K[g];
-            const double* finF = rows + s_roff[f];
-            const double* finG = rows + s_roff[g];
-            const int kf = k == 0 ? 0 : PL.cmap[(e * 2 + 0) * Kmax + k];
-            const int kg = k == 0 ? 0 : PL.cmap[(e * 2 + 1) * Kmax + k];
-            const double* epsF = PL.eps + PL.toff[f] + (size_t)M.nsl[f] * KF;
-            const double* epsG = PL.eps + PL.toff[g] + (size_t)M.nsl[g] * KG;
-            const double ef0 = epsF[0], eg0 = epsG[0];
-            const double efk = (k > 0 && kf >= 0) ? epsF[kf] : 0.0;
-            const double egk = (k > 0 && kg >= 0) ? epsG[kg] : 0.0;
-            const double cx0 = PL.cx[e * Kmax], cy0 = PL.cy[e * Kmax];
-            const double cxk = PL.cx[e * Kmax + k], cyk = PL.cy[e * Kmax + k];
-            const uint32_t* dptr = words + R.dptr_off;
-            const uint32_t* tptr = words + R.tptr_off;
-            const int32_t* lossF = reinterpret_cast<const int32_t*>(words + R.loss_off);
-            const int32_t* lossG = lossF + C;
-            const uint32_t* lev = words + R.lev_off;
-            for (uint32_t L = 0; L < H.nlev; L++) {
-                const int c0 = (int)lev[L], c1 = (int)lev[L + 1];
-                if (lane_on)
-                    for (int c = c0 + grp; c < c1; c += GP) {
-                        double a0, ak, b0, bk;
-                        pairsum(ents + R.dent_off, dptr[c], dptr[c + 1], fin, K, k, fin, K, k, m, a0, ak);
-                        pairsum(ents + R.tent_off, tptr[c], tptr[c + 1], finF, KF, kf, finG, KG, kg, m, b0, bk);
-                        const int lf = lossF[c], lg = lossG[c];
-                        double f0 = 0.0, fk = 0.0, g0 = 0.0, gk = 0.0;
-                        if (lf >= 0) { f0 = finF[lf * KF]; fk = kf >= 0 ? finF[lf * KF + kf] : 0.0; }
-                        if (lg >= 0) { g0 = finG[lg * KG]; gk = kg >= 0 ? finG[lg * KG + kg] : 0.0; }
-                        // Πloss src/core.jl:172-176
-                        double c0v = f0 * eg0 + g0 * ef0;
-                        double ckv = fk * eg0 + gk * ef0 + m * (f0 * egk + g0 * efk);
-                        double u0 = b0 + c0v, uk = bk + ckv;
-                        double r = cx0 * ak + cy0 * uk + m * (cxk * a0 + cyk * u0);
-                        fin[c * K + k] = r;
-                        if (ellp && k == 0) ellp[c] = r;
-                    }
-                __syncthreads();
-            }
-            // log L and its gradient  (src/core.jl:35-36)
-            if (tid < K) {
-                const double Lv = fin[(C - 1) * K];
-                double o;
-                if (Lv > 0.0) o = tid == 0 ? log(Lv) : fin[(C - 1) * K + tid] / Lv;
-                else o = tid == 0 ? -__longlong_as_double(0x7ff0000000000000LL) : 0.0;
-                A.out_fam[(size_t)fam * K + tid] = o;
-            }
-            continue;
-        }
-
-        // ---- row 1 of a non-root branch ----
-        double* cur = (n & 1) ? scr : fin;  // row i lives in fin iff (n − i) is even
-        if (kind == WHALE_LEAF) {           // src/core.jl:93-94
-            const int nleafc = C - (int)R.nonleaf;
-            if (lane_on)
-                for (int c = grp; c < C; c += GP) {
-                    double v = (c < nleafc && k == 0) ? M.leafP[e] : 0.0;
-                    cur[c * K + k] = v;
-                    if (ellp && k == 0) ellp[c] = v;
-                }
-        } else if (kind == WHALE_INTERNAL) {  // Πspeciation + Πloss, src/core.jl:95-98,160-176
-            const int f = M.child0[e], g = M.child1[e];
-            const int KF = PL.K[f], KG = PL.K[g];
-            const double* finF = rows + s_roff[f];
-            const double* finG = rows + s_roff[g];
-            const int kf = k == 0 ? 0 : PL.cmap[(e * 2 + 0) * Kmax + k];
-            const int kg = k == 0 ? 0 : PL.cmap[(e * 2 + 1) * Kmax + k];
-            const double* epsF = PL.eps + PL.toff[f] + (size_t)M.nsl[f] * KF;
-            const double* epsG = PL.eps + PL.toff[g] + (size_t)M.nsl[g] * KG;
-            const double ef0 = epsF[0], eg0 = epsG[0];
-            const double efk = (k > 0 && kf >= 0) ? epsF[kf] : 0.0;
-            const double egk = (k > 0 && kg >= 0) ? epsG[kg] : 0.0;
-            const uint32_t* tptr = words + R.tptr_off;
-            const int32_t* lossF = reinterpret_cast<const int32_t*>(words + R.loss_off);
-            const int32_t* lossG = lossF + C;
-            if (lane_on)
-                for (int c = grp; c < C; c += GP) {
-                    double b0, bk;
-                    pairsum(ents + R.tent_off, tptr[c], tptr[c + 1], finF, KF, kf, finG, KG, kg, m, b0, bk);
-                    const int lf = lossF[c], lg = lossG[c];
-                    double f0 = 0.0, fk = 0.0, g0 = 0.0, gk = 0.0;
-                    if (lf >= 0) { f0 = finF[lf * KF]; fk = kf >= 0 ? finF[lf * KF + kf] : 0.0; }
-                    if (lg >= 0) { g0 = finG[lg * KG]; gk = kg >= 0 ? finG[lg * KG + kg] : 0.0; }
-                    double c0v = f0 * eg0 + g0 * ef0;
-                    double ckv = fk * eg0 + gk * ef0 + m * (f0 * egk + g0 * efk);
-                    double r = k == 0 ? b0 + c0v : bk + ckv;
-                    cur[c * K + k] = r;
-                    if (ellp && k == 0) ellp[c] = r;
-                }
-        } else {  // WGD: q·Σ p ℓ_f[γ1]ℓ_f[γ2] + (1−q+2qϵ_f)·ℓ_f[γ]   src/core.jl:103-119,187-199
-            const int f = M.child0[e];
-            const int KF = PL.K[f];
-            const double* finF = rows + s_roff[f];
-            const int kf = k == 0 ? 0 : PL.cmap[(e * 2 + 0) * Kmax + k];
-            const double cx0 = PL.cx[e * Kmax], cy0 = PL.cy[e * Kmax];
-            const double cxk = PL.cx[e * Kmax + k], cyk = PL.cy[e * Kmax + k];
-            const uint32_t* dptr = words + R.dptr_off;
-            if (lane_on)
-                for (int c = grp; c < C; c += GP) {
-                    double s0, sk;
-                    pairsum(ents + R.dent_off, dptr[c], dptr[c + 1], finF, KF, kf, finF, KF, kf, m, s0, sk);
-                    double u0 = finF[c * KF];
-                    double uk = kf >= 0 ? finF[c * KF + kf] : 0.0;
-                    double r = cy0 * sk + cx0 * uk + m * (cyk * s0 + cxk * u0);
-                    cur[c * K + k] = r;
-                    if (ellp && k == 0) ellp[c] = r;
-                }
-        }
-        __syncthreads();
-
-        // ---- slices: ℓ_i = ϕ_i ℓ_{i−1} + ψ_i Σ_t p ℓ_{i−1}[γ1] ℓ_{i−1}[γ2]   src/core.jl:121-128,178-185 ----
-        const uint32_t* dptr = words + R.dptr_off;
-        const Ent* dents = ents + R.dent_off;
-        const double2* pprow = PL.pp + PL.toff[e];
-        // the lane's first cell keeps its triple range in registers across all slices
-        uint32_t tb0 = 0, te0 = 0;
-        if (lane_on && grp < C) { tb0 = dptr[grp]; te0 = dptr[grp + 1]; }
-        for (int i = 1; i <= n; i++) {
-            const double* src = cur;
-            double* dst = (cur == fin) ? scr : fin;
-            if (lane_on && grp < C) {
-                const double2 c0 = pprow[(size_t)i * K];
-                const double2 ck = pprow[(size_t)i * K + k];
-                for (int c = grp; c < C; c += GP) {
-                    uint32_t tb = tb0, te = te0;
-                    if (c != grp) { tb = dptr[c]; te = dptr[c + 1]; }
-                    double s0, sk;
-                    pairsum(dents, tb, te, src, K, k, src, K, k, m, s0, sk);
-                    double o0 = src[c * K], ok = src[c * K + k];
-                    double r = c0.x * ok + c0.y * sk + m * (ck.x * o0 + ck.y * s0);
-                    dst[c * K + k] = r;
-                    if (ellp && k == 0) ellp[(size_t)i * C + c] = r;
-                }
-            }
-            cur = dst;
-            __syncthreads();
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K3: deterministic reduction over families + conditioning.  src/core.jl:54,63 ; src/condition.jl
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_reduce1(const double* __restrict__ out_fam, int F, int K, int chunk,
-                                                 double* __restrict__ partial) {
-    __shared__ double sh[256];
-    const int b = blockIdx.x, f0 = b * chunk, f1 = min(F, f0 + chunk);
-    for (int k = 0; k < K; k++) {
-        double s = 0.0;
-        for (int f = f0 + threadIdx.x; f < f1; f += 256) s += out_fam[(size_t)f * K + k];
-        sh[threadIdx.x] = s;
-        __syncthreads();
-        for (int w = 128; w > 0; w >>= 1) {
-            if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) partial[(size_t)b * K + k] = sh[0];
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(256) k_reduce2(const double* __restrict__ partial, int nb, int K, int F,
-                                                 int cond_kind, PlanDev PL, int root, int P,
-                                                 double* __restrict__ out) {
-    __shared__ double tot[256];
-    __shared__ int finite;
-    for (int k = threadIdx.x; k < K; k += 256) {
-        double s = 0.0;
-        for (int b = 0; b < nb; b++) s += partial[(size_t)b * K + k];
-        s -= (double)F * PL.cond[cond_kind * PL.Kmax + k];
-        tot[k] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) finite = isfinite(tot[0]) ? 1 : 0;  // ℓhood src/core.jl:15
-    __syncthreads();
-    for (int i = threadIdx.x; i <= P; i += 256) out[i] = 0.0;
-    __syncthreads();
-    for (int k = threadIdx.x; k < K; k += 256) {
-        if (k == 0) out[0] = finite ? tot[0] : -__longlong_as_double(0x7ff0000000000000LL);
-        else out[1 + PL.act[root * PL.Kmax + k]] = finite ? tot[k] : 0.0;
-    }
-}
-
-// dependent-free DFMA microbenchmark (fp64 roofline denominator)
-__global__ void __launch_bounds__(256) k_dfma(double* out, int iters) {
-    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
-           a7 = a0 + 7;
-    const double b = 1.0000001, c = 1e-9;
-    for (int i = 0; i < iters; i++) {
-        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
-        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
-}
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -581,7 +86,7 @@ struct whale_model {
     std::vector<int> order, child0, child1, kind, nsl, lam_slot, mu_slot, q_slot;
     std::vector<double> dt, leafP;
     int eta_slot = 0, log_scale = 0;
-    std::vector<int> lvl_off, lvl_nodes;
+    std::vector<int> lvl_off, lvl_nodes, leafnodes, inner;
     ModelDev dev{};
     std::vector<void*> owned;
     Plan plan[2];  // 0: value only, 1: all raw parameters
@@ -592,16 +97,26 @@ struct whale_model {
     cudaStream_t stream = nullptr;
 };
 
+constexpr int MAX_BINS = 8;
+struct Bin {
+    int off, count;
+    size_t smem;
+};
+
 struct whale_data {
     whale_model* m = nullptr;
     int F = 0;
     std::vector<FamHdr> hdr;
-    std::vector<int> perm;
+    std::vector<int> perm[2];
+    std::vector<Bin> bins[2];
+    cudaStream_t side[MAX_BINS] = {};
+    cudaEvent_t ev_join[MAX_BINS] = {};
+    cudaEvent_t ev_fork = nullptr;
     std::vector<unsigned char> arena_host;  // packing buffer (released after upload)
     size_t arena_bytes = 0;
     unsigned char* d_arena = nullptr;
     FamHdr* d_hdr = nullptr;
-    int* d_perm = nullptr;
+    int* d_perm[2] = {nullptr, nullptr};
     double* d_out_fam = nullptr;  // [F*Kmax(plan1)]
     double* d_partial = nullptr;
     double* d_ell = nullptr;
@@ -609,7 +124,6 @@ struct whale_data {
     bool ev_valid = false;
     uint64_t ell_total = 0;
     bool ell_valid = false;
-    int maxSumCK[2] = {0, 0};   // max over families of Σ_e C_e K_e + max_e C_e K_e, per plan (doubles)
     // aggregated work counters per node (over families): Σ C_e, Σ T_e (unfiltered triples of compat clades)
     std::vector<double> aggC, aggT;
     double aggG = 0, aggTroot = 0;
@@ -683,23 +197,26 @@ static cudaError_t upload_plan(Plan& pl, int nn) {
     if ((e = upload(pl.toff, &dtoff)) != cudaSuccess) return e;
     if ((e = upload(pl.cmap, &dcmap)) != cudaSuccess) return e;
     if ((e = upload(pl.role, &drole)) != cudaSuccess) return e;
-    double *eps, *cx, *cy, *leaf, *cond;
-    double2* pp;
+    double *eps, *cx, *cy, *leaf, *cond, *ab;
+    double2 *pp, *uv;
     if ((e = cudaMalloc((void**)&eps, std::max<size_t>(pl.tab_len, 1) * sizeof(double))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&pp, std::max<size_t>(pl.tab_len, 1) * sizeof(double2))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&uv, std::max<size_t>(pl.tab_len, 1) * sizeof(double2))) != cudaSuccess) return e;
     size_t nk = (size_t)nn * pl.Kmax * sizeof(double);
+    if ((e = cudaMalloc((void**)&ab, 2 * nk)) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&cx, nk)) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&cy, nk)) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&leaf, nk)) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&cond, 3 * pl.Kmax * sizeof(double))) != cudaSuccess) return e;
     cudaMemset(cx, 0, nk); cudaMemset(cy, 0, nk); cudaMemset(leaf, 0, nk);
     cudaMemset(cond, 0, 3 * pl.Kmax * sizeof(double));
-    pl.owned = {dK, dact, dtoff, dcmap, drole, eps, pp, cx, cy, leaf, cond};
-    pl.dev = PlanDev{pl.Kmax, dK, dact, dcmap, drole, dtoff, eps, pp, cx, cy, leaf, cond};
+    pl.owned = {dK, dact, dtoff, dcmap, drole, eps, pp, uv, ab, cx, cy, leaf, cond};
+    pl.dev = PlanDev{pl.Kmax, dK, dact, dcmap, drole, dtoff, eps, pp, uv, ab, cx, cy, leaf, cond};
     return cudaSuccess;
 }
 
 static int g_device = 0;
+constexpr int DP_NT = 128;  // threads per family CTA
 
 extern "C" {
 
@@ -778,14 +295,19 @@ int32_t whale_model_create(const whale_model_desc* d, whale_model_t* out) {
         for (int oi = 0; oi < nn; oi++) if (height[m->order[oi]] == h) m->lvl_nodes.push_back(m->order[oi]);
         m->lvl_off.push_back((int)m->lvl_nodes.size());
     }
-    int *o, *c0, *c1, *kd, *ns, *ls, *ms, *qs, *lo, *ln;
+    for (int oi = 0; oi < nn; oi++) {
+        int e = m->order[oi];
+        (m->kind[e] == WHALE_LEAF ? m->leafnodes : m->inner).push_back(e);
+    }
+    int *o, *c0, *c1, *kd, *ns, *ls, *ms, *qs, *lo, *ln, *lfn, *inn;
     double *dt, *lp;
+    CU(upload(m->leafnodes, &lfn)); CU(upload(m->inner, &inn));
     CU(upload(m->order, &o)); CU(upload(m->child0, &c0)); CU(upload(m->child1, &c1)); CU(upload(m->kind, &kd));
     CU(upload(m->nsl, &ns)); CU(upload(m->lam_slot, &ls)); CU(upload(m->mu_slot, &ms)); CU(upload(m->q_slot, &qs));
     CU(upload(m->lvl_off, &lo)); CU(upload(m->lvl_nodes, &ln)); CU(upload(m->dt, &dt)); CU(upload(m->leafP, &lp));
-    m->owned = {o, c0, c1, kd, ns, ls, ms, qs, lo, ln, dt, lp};
+    m->owned = {o, c0, c1, kd, ns, ls, ms, qs, lo, ln, dt, lp, lfn, inn};
     m->dev = ModelDev{nn, o, c0, c1, kd, ns, dt, lp, ls, ms, qs, m->eta_slot, m->log_scale, m->root,
-                      (int)m->lvl_off.size() - 1, lo, ln};
+                      (int)m->lvl_off.size() - 1, lo, ln, (int)m->leafnodes.size(), lfn, (int)m->inner.size(), inn};
     for (int g = 0; g < 2; g++) {
         build_plan(*m, g == 1, m->plan[g]);
         CU(upload_plan(m->plan[g], nn));
@@ -813,6 +335,13 @@ int32_t whale_model_destroy(whale_model_t m) {
 }
 
 // ---- the packer: reference-layout CSR -> per-branch resolved device arena ----
+static inline void pad4(std::vector<uint32_t>& w) { while (w.size() & 3) w.push_back(0); }
+
+static size_t smem_need(const whale_model* m, const FamHdr& h, int plan) {
+    return ((((size_t)m->nn + 1) * sizeof(int) + 15) & ~size_t(15)) +
+           ((size_t)h.rows_len[plan] + h.scr_len[plan]) * sizeof(double) + h.stage_bytes;
+}
+
 int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t* out) {
     if (!m || !d || !out) return fail(WHALE_ERR_ARG, "null argument");
     const int nn = m->nn, F = d->n_fam;
@@ -840,7 +369,9 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
         lidx.assign((size_t)nn * G, -1);
         std::vector<uint32_t>& Cs = D->famC[f];
         Cs.assign(nn, 0);
-        const uint64_t fam_ell0 = ell_total;
+        FamHdr& H = D->hdr[f];
+        memset(&H, 0, sizeof(H));
+        H.ell_off = ell_total;
         for (int e = 0; e < nn; e++) {
             int C = (int)(coff[e + 1] - coff[e]);
             Cs[e] = C;
@@ -857,9 +388,10 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
             if (nleaf[c] < nleaf[c - 1]) { delete D; return fail(WHALE_ERR_ARG, "family %d: clades must be sorted by size", f); }
         // blob assembly
         std::vector<NodeRec> recs(nn);
-        std::vector<uint32_t> wordsv;   // pointer/loss/level words
-        std::vector<Ent> entsv;         // entries
-        uint32_t sumC = 0, maxC = 0;
+        std::vector<uint32_t> wordsv;   // pointer / loss / level words; every array starts on a 16-byte boundary
+        std::vector<Ent> entsv;         // term entries
+        uint32_t sumC = 0, nlev = 0;
+        size_t stage_bytes = 0;
         double wk = 0.0;
         for (int e = 0; e < nn; e++) {
             NodeRec& R = recs[e];
@@ -867,7 +399,6 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
             const int C = (int)Cs[e];
             R.C = C;
             sumC += C;
-            maxC = std::max<uint32_t>(maxC, C);
             const int kind = m->kind[e];
             int nonleaf = 0;
             double Te = 0;
@@ -882,6 +413,7 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
             // (1) same-branch terms: within-branch duplication (src/core.jl:178-185), Πroot (:151-158);
             //     for WGD nodes the same list drives Πwgdretention on the child's row (:187-194), the
             //     child's compat list being identical.
+            pad4(wordsv);
             R.dptr_off = (uint32_t)wordsv.size();
             R.dent_off = (uint32_t)entsv.size();
             {
@@ -899,13 +431,15 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
                     }
                 }
                 wordsv.push_back((uint32_t)entsv.size() - R.dent_off);
-                wk += (double)(entsv.size() - R.dent_off) * (m->nsl[e] + 1) + (double)C * (m->nsl[e] + 1);
+                R.ndent = (uint32_t)entsv.size() - R.dent_off;
+                wk += (double)R.ndent * (m->nsl[e] + 1) + (double)C * (m->nsl[e] + 1);
             }
-            // (2) speciation terms at row 1 (src/core.jl:160-170) and loss indices (:172-176)
+            // (2) speciation terms at row 1 (src/core.jl:160-170), Πloss child indices (:172-176), root levels
+            pad4(wordsv);
+            R.tptr_off = (uint32_t)wordsv.size();
+            R.tent_off = (uint32_t)entsv.size();
             if (kind == WHALE_INTERNAL || kind == WHALE_ROOT) {
                 const int fch = m->child0[e], gch = m->child1[e];
-                R.tptr_off = (uint32_t)wordsv.size();
-                R.tent_off = (uint32_t)entsv.size();
                 for (int j = 0; j < C; j++) {
                     int g = d->compat[coff[e] + j];
                     wordsv.push_back((uint32_t)entsv.size() - R.tent_off);
@@ -918,70 +452,100 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
                     }
                 }
                 wordsv.push_back((uint32_t)entsv.size() - R.tent_off);
-                wk += (double)(entsv.size() - R.tent_off);
-                R.loss_off = (uint32_t)wordsv.size();
+                R.ntent = (uint32_t)entsv.size() - R.tent_off;
+                wk += (double)R.ntent;
                 for (int j = 0; j < C; j++) wordsv.push_back((uint32_t)lidx[(size_t)fch * G + d->compat[coff[e] + j]]);
                 for (int j = 0; j < C; j++) wordsv.push_back((uint32_t)lidx[(size_t)gch * G + d->compat[coff[e] + j]]);
+                if (kind == WHALE_ROOT) {
+                    for (int c = 0; c < G; c++)
+                        if (c == 0 || nleaf[c] != nleaf[c - 1]) { wordsv.push_back((uint32_t)c); nlev++; }
+                    wordsv.push_back((uint32_t)G);
+                    D->aggTroot += (double)(soff[G] - soff[0]);
+                }
             }
-            if (kind == WHALE_ROOT) {
-                R.lev_off = (uint32_t)wordsv.size();
-                uint32_t nlev = 0;
-                for (int c = 0; c < G; c++)
-                    if (c == 0 || nleaf[c] != nleaf[c - 1]) { wordsv.push_back((uint32_t)c); nlev++; }
-                wordsv.push_back((uint32_t)G);
-                D->hdr[f].nlev = nlev;
-                D->aggTroot += (double)(soff[G] - soff[0]);
+            if (kind != WHALE_LEAF) {  // what k_dp stages in shared memory for this node
+                size_t nd16 = kind == WHALE_ROOT ? 0 : R.ndent;
+                size_t dp16 = ((size_t)C + 1 + 3) / 4;
+                size_t tp16 = kind == WHALE_WGD ? 0 : (3 * (size_t)C + 1 + (kind == WHALE_ROOT ? nlev + 1 : 0) + 3) / 4;
+                stage_bytes = std::max(stage_bytes, 16 * (nd16 + dp16 + tp16));
             }
             ell_total += (uint64_t)(m->nsl[e] + 1) * C;
         }
+        pad4(wordsv);
         D->aggG += G;
-        // serialise: NodeRec[nn] | words | (pad to 16) | entries ; fix offsets to be blob-relative
+        // serialise: NodeRec[nn] | words | entries ; make offsets blob-relative
         size_t base = (A.size() + 15) & ~size_t(15);
-        size_t rec_bytes = (size_t)nn * sizeof(NodeRec);
-        size_t words_at = rec_bytes;  // NodeRec is 32 bytes -> stays 4-byte aligned
-        size_t ents_at = (words_at + wordsv.size() * 4 + 15) & ~size_t(15);
+        size_t words_at = (size_t)nn * sizeof(NodeRec);  // 32-byte records: 16-byte aligned
+        size_t ents_at = words_at + wordsv.size() * 4;   // words padded to 4 -> 16-byte aligned
         size_t total = ents_at + entsv.size() * sizeof(Ent);
         A.resize(base + total, 0);
         for (int e = 0; e < nn; e++) {
             NodeRec& R = recs[e];
             R.dptr_off += (uint32_t)(words_at / 4);
             R.tptr_off += (uint32_t)(words_at / 4);
-            R.loss_off += (uint32_t)(words_at / 4);
-            R.lev_off += (uint32_t)(words_at / 4);
             R.dent_off += (uint32_t)(ents_at / 16);
             R.tent_off += (uint32_t)(ents_at / 16);
         }
-        memcpy(A.data() + base, recs.data(), rec_bytes);
+        memcpy(A.data() + base, recs.data(), words_at);
         if (!wordsv.empty()) memcpy(A.data() + base + words_at, wordsv.data(), wordsv.size() * 4);
         if (!entsv.empty()) memcpy(A.data() + base + ents_at, entsv.data(), entsv.size() * sizeof(Ent));
-        D->hdr[f].base = base;
-        D->hdr[f].G = G;
-        D->hdr[f].sumC = sumC;
-        D->hdr[f].maxC = maxC;
-        D->hdr[f].ell_off = fam_ell0;
+        H.base = base;
+        H.G = G;
+        H.nlev = nlev;
+        H.stage_bytes = (uint32_t)stage_bytes;
+        H.blob_bytes = (uint32_t)total;
         work[f] = wk;
         // SURVEY §8d algorithmic bytes per evaluation: 12·T + 2·Γ + 4·Σ_e C_e
         algo_bytes += 12 * (soff[G] - soff[0]) + 2 * (int64_t)G + 4 * (int64_t)sumC;
-        for (int g = 0; g < 2; g++) {
+        for (int g = 0; g < 2; g++) {  // shared-memory budget per tangent plan
             const Plan& pl = m->plan[g];
-            int s = 0, mx = 0;
-            for (int e = 0; e < nn; e++) { int ck = (int)Cs[e] * pl.K[e]; s += ck; mx = std::max(mx, ck); }
-            D->maxSumCK[g] = std::max(D->maxSumCK[g], s + mx);
+            uint32_t rows = 0, mxinner = 0, mxleaf = 0;
+            for (int e = 0; e < nn; e++) {
+                uint32_t ck = Cs[e] * (uint32_t)pl.K[e];
+                rows += ck;
+                if (m->kind[e] == WHALE_LEAF) mxleaf = std::max(mxleaf, ck);
+                else if (m->kind[e] != WHALE_ROOT) mxinner = std::max(mxinner, ck);
+            }
+            H.rows_len[g] = rows;
+            H.leafmax[g] = mxleaf;
+            H.scr_len[g] = (std::max(mxinner, (uint32_t)MAX_WARPS * mxleaf) + 1) & ~1u;
         }
     }
     D->ell_total = ell_total;
     D->algo_bytes = algo_bytes;
-    D->perm.resize(F);
-    std::iota(D->perm.begin(), D->perm.end(), 0);
-    std::stable_sort(D->perm.begin(), D->perm.end(), [&](int a, int b) { return work[a] > work[b]; });
+    // bins by shared-memory need (geometric, <= 25 % waste), launched concurrently; within a bin the
+    // heaviest families go first
+    for (int g = 0; g < 2; g++) {
+        std::vector<int>& perm = D->perm[g];
+        perm.resize(F);
+        std::iota(perm.begin(), perm.end(), 0);
+        std::vector<size_t> need(F);
+        for (int f = 0; f < F; f++) need[f] = smem_need(m, D->hdr[f], g);
+        std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return need[a] != need[b] ? need[a] > need[b] : work[a] > work[b]; });
+        std::vector<Bin>& bins = D->bins[g];
+        int i = 0;
+        while (i < F) {
+            Bin b{i, 0, need[perm[i]]};
+            while (i < F && (need[perm[i]] * 5 >= b.smem * 4 || b.count < 64 || (int)bins.size() >= MAX_BINS - 1)) { i++; b.count++; }
+            std::stable_sort(perm.begin() + b.off, perm.begin() + b.off + b.count, [&](int x, int y) { return work[x] > work[y]; });
+            bins.push_back(b);
+        }
+        // merge a tiny last bin into its predecessor
+        if (bins.size() > 1 && bins.back().count < 64) { bins[bins.size() - 2].count += bins.back().count; bins.pop_back(); }
+        CU(upload(perm, &D->d_perm[g]));
+    }
     CU(cudaMalloc((void**)&D->d_arena, std::max<size_t>(A.size(), 16)));
     CU(cudaMemcpy(D->d_arena, A.data(), A.size(), cudaMemcpyHostToDevice));
     D->arena_bytes = A.size();
     std::vector<unsigned char>().swap(A);
     CU(upload(D->hdr, &D->d_hdr));
-    CU(upload(D->perm, &D->d_perm));
     CU(cudaMalloc((void**)&D->d_out_fam, (size_t)F * m->plan[1].Kmax * sizeof(double)));
     CU(cudaMalloc((void**)&D->d_partial, (size_t)1024 * m->plan[1].Kmax * sizeof(double)));
+    for (int i = 0; i < MAX_BINS; i++) {
+        CU(cudaStreamCreateWithFlags(&D->side[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&D->ev_join[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&D->ev_fork, cudaEventDisableTiming));
     *out = D;
     return WHALE_OK;
 }
@@ -989,7 +553,13 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
 int32_t whale_data_destroy(whale_data_t d) {
     if (!d) return WHALE_OK;
     cudaSetDevice(d->m->device);
-    cudaFree(d->d_arena); cudaFree(d->d_hdr); cudaFree(d->d_perm); cudaFree(d->d_out_fam); cudaFree(d->d_partial);
+    cudaFree(d->d_arena); cudaFree(d->d_hdr); cudaFree(d->d_perm[0]); cudaFree(d->d_perm[1]);
+    cudaFree(d->d_out_fam); cudaFree(d->d_partial);
+    for (int i = 0; i < MAX_BINS; i++) {
+        if (d->side[i]) cudaStreamDestroy(d->side[i]);
+        if (d->ev_join[i]) cudaEventDestroy(d->ev_join[i]);
+    }
+    if (d->ev_fork) cudaEventDestroy(d->ev_fork);
     cudaFree(d->d_ell);
     for (int i = 0; i < 4; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     delete d;
@@ -1025,19 +595,29 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
     LAUNCH(k_tables, 1, nw * 32, 0, st, m->dev, pl.dev, d_x, m->d_pleaf);
     g_launches++;
     if (prof) CU(cudaEventRecord(D->ev[1], st));
-    // K2
-    constexpr int NT = 128;
-    if (pl.Kmax > NT) return fail(WHALE_ERR_CAPACITY, "K=%d tangent components exceed %d lanes (parameter chunking not built yet)", pl.Kmax, NT);
-    size_t smem = (((nn + 1) * sizeof(int) + 15) & ~size_t(15)) + (size_t)D->maxSumCK[g] * sizeof(double);
-    if (smem > 227 * 1024) return fail(WHALE_ERR_CAPACITY, "a family needs %zu bytes of shared memory (> 227 KB)", smem);
+    // K2: one launch per shared-memory bin, concurrently on side streams
+    if (pl.Kmax > DP_NT) return fail(WHALE_ERR_CAPACITY, "K=%d tangent components exceed %d lanes (parameter chunking not built yet)", pl.Kmax, DP_NT);
+    const std::vector<Bin>& bins = D->bins[g];
+    if (bins[0].smem > 227 * 1024) return fail(WHALE_ERR_CAPACITY, "a family needs %zu bytes of shared memory (> 227 KB)", bins[0].smem);
     static thread_local size_t smem_set = 0;
-    if (smem > smem_set) {
-        CU(cudaFuncSetAttribute(k_dp<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-        smem_set = smem;
+    if (bins[0].smem > smem_set) {
+        CU(cudaFuncSetAttribute(k_dp<DP_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        smem_set = 227 * 1024;
     }
-    DPArgs a{m->dev, pl.dev, D->d_arena, D->d_hdr, D->d_perm, D->d_out_fam, keep ? D->d_ell : nullptr, F, keep ? 0 : 1};
-    LAUNCH(k_dp<NT>, F, NT, smem, st, a);
-    g_launches++;
+    DPArgs a{m->dev, pl.dev, D->d_arena, D->d_hdr, D->d_perm[g], D->d_out_fam, keep ? D->d_ell : nullptr, g, keep ? 0 : 1};
+    if (bins.size() == 1) {
+        LAUNCH(k_dp<DP_NT>, bins[0].count, DP_NT, bins[0].smem, st, a, bins[0].off);
+        g_launches++;
+    } else {
+        CU(cudaEventRecord(D->ev_fork, st));
+        for (size_t b = 0; b < bins.size(); b++) {
+            CU(cudaStreamWaitEvent(D->side[b], D->ev_fork, 0));
+            LAUNCH(k_dp<DP_NT>, bins[b].count, DP_NT, bins[b].smem, D->side[b], a, bins[b].off);
+            g_launches++;
+            CU(cudaEventRecord(D->ev_join[b], D->side[b]));
+            CU(cudaStreamWaitEvent(st, D->ev_join[b], 0));
+        }
+    }
     if (prof) CU(cudaEventRecord(D->ev[2], st));
     // K3
     const int KR = pl.K[m->root];
