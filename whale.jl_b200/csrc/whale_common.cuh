@@ -43,14 +43,17 @@ struct FamHdr {
     uint64_t ell_off;      // offset (doubles) of this family's ℓ in the keep_ell buffer
     uint32_t G;            // clades
     uint32_t nlev;         // root levels (distinct clade sizes)
-    uint32_t rows_len[2];  // Σ_e C_e K_e per tangent plan (doubles)
-    uint32_t scr_len[2];   // scratch row length per plan (doubles)
-    uint32_t leafmax[2];   // max over leaf branches of C_e K_e per plan
-    uint32_t stage_bytes;  // staging buffer for one node's lists
+    // shared-memory budget (doubles unless stated), per tangent plan where it depends on K_e
+    uint32_t rows_len[2];   // Σ_e C_e K_e (even)
+    uint32_t scr_len[2];    // scratch row: max over internal/WGD nodes of C_e K_e (even)
+    uint32_t prod_len[2];   // P1 product window: max over internal/WGD nodes of max(ndent, ntent)·K_e (even)
+    uint32_t leafmax[2];    // per-warp scratch row: max over leaf branches of C_e K_e (even)
+    uint32_t leaf_prod[2];  // per-warp product window: max over leaf branches of ndent·K_e (even)
+    uint32_t stage_bytes;   // staging buffer for one internal node's lists (bytes, multiple of 16)
+    uint32_t leaf_stage;    // per-warp staging buffer for one leaf branch's lists (bytes, multiple of 16)
     uint32_t blob_bytes;
+    uint32_t pad;
 };
-
-constexpr int MAX_WARPS = 8;  // scratch is sized for up to 8 warps working on leaf branches concurrently
 
 struct ModelDev {  // structure arrays (device pointers), node index = id-1
     int nn;

@@ -2,14 +2,19 @@
 //
 // One CTA (NT threads) per family.  The LAST row of every branch (C_e × K_e doubles: K_e = 1 + #raw
 // parameters that can influence branch e) stays in shared memory for the parent; slices ping-pong between
-// that row and a scratch row (one barrier per slice).  Lanes span (clade cell × component); every lane also
-// recomputes the value part it needs, so no shuffles are required and the k = 0 lane is the plain logpdf.
+// that row and a scratch row.  Every Σ_t p_t·ℓ[γ1]·ℓ[γ2] of the reference (Πduplication, Πspeciation,
+// Πwgdretention, Πroot) is evaluated in two balanced phases instead of one serial loop per clade:
+//   P1  one thread per TERM t: products p·x·y with the product rule for all K components -> prod[k][t]
+//   P2  one lane per (cell, component): sums its contiguous range of prod (the reference's summation
+//       order), applies the row formula, writes the new row.
+// That removes the load imbalance of CCDs (a branch's largest clade typically owns ~10× the mean number of
+// splits; the ubiquitous clade ~100) from the critical path.
 //   phase A  leaf branches are independent of each other: one WARP per leaf branch, warp-level sync only;
 //            branches whose compatible clades are all leaf clades are family-independent and are filled
 //            from the table k_tables prepared (ℓ_n = leafℙ·Πϕ_i).
 //   phase B  internal / WGD / root nodes in the reference's order (children first), all warps cooperating;
-//            the node's pointer arrays and within-branch terms are staged in shared memory with cp.async
-//            while row 1 (speciation + loss) is being computed.
+//            the node's pointer arrays and within-branch terms are staged in shared memory.
+// ϕ/ψ rows are prefetched one slice ahead into registers, so the slice loop touches shared memory only.
 #pragma once
 #include "whale_common.cuh"
 
@@ -26,45 +31,63 @@ struct DPArgs {
 };
 
 #ifdef WHALE_EMU
-#define CP_ASYNC16(dst, src) (*(uint4*)(dst) = *(const uint4*)(src))
-#define CP_ASYNC_WAIT() ((void)0)
 #define PREFETCH_L2(p) ((void)0)
 #else
-#define CP_ASYNC16(dst, src)                                                                        \
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), \
-                 "l"(src) : "memory")
-#define CP_ASYNC_WAIT() asm volatile("cp.async.wait_all;" ::: "memory")
 #define PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #endif
 
-// Σ_t p_t X[i1] Y[i2] with the product rule for the lane's component; m = 0 on the value lane (k = 0,
-// kx = ky = 0), 1 on tangent lanes; a component absent from a child (kx < 0) contributes a zero tangent.
+template <bool WARP>
+__device__ __forceinline__ void scope_sync() {
+    if (WARP) __syncwarp();
+    else __syncthreads();
+}
+
+// copy n16 16-byte words global -> shared with all threads of the scope
+__device__ __forceinline__ void copy16(uint4* dst, const uint4* __restrict__ src, int n16, int tid, int nt) {
+    for (int i = tid; i < n16; i += nt) dst[i] = __ldg(src + i);
+}
+
+// P1: terms [ta, tb) of `ents` -> prod[k*cap + (t - ta)], k = 0..K-1.
+// X/Y are rows with KX/KY components; mapX/mapY translate the output component k into the component of
+// X/Y (identity if null; -1: the row does not depend on that parameter -> zero tangent).
 template <bool GLOBAL_ENTS>
-__device__ __forceinline__ void pairsum(const Ent* __restrict__ ents, uint32_t tb, uint32_t te,
-                                        const double* __restrict__ X, int KX, int kx,
-                                        const double* __restrict__ Y, int KY, int ky, double m, double& S0,
-                                        double& Sk) {
-    double s0 = 0.0, sk = 0.0;
-    for (uint32_t t = tb; t < te; t++) {
+__device__ __forceinline__ void terms(const Ent* __restrict__ ents, uint32_t ta, uint32_t tb,
+                                      const double* __restrict__ X, int KX, const int16_t* __restrict__ mapX,
+                                      const double* __restrict__ Y, int KY, const int16_t* __restrict__ mapY,
+                                      int K, double* __restrict__ prod, int cap, int tid, int nt) {
+    for (uint32_t t = ta + tid; t < tb; t += nt) {
         uint4 raw;
         if (GLOBAL_ENTS) raw = __ldg(reinterpret_cast<const uint4*>(ents + t));
         else raw = *reinterpret_cast<const uint4*>(ents + t);
         const double p = __hiloint2double((int)raw.w, (int)raw.z);
         const double* xp = X + (raw.x & 0xffffu) * KX;
         const double* yp = Y + (raw.x >> 16) * KY;
-        const double x0 = xp[0], y0 = yp[0];
-        const double xk = kx >= 0 ? xp[kx] : 0.0;
-        const double yk = ky >= 0 ? yp[ky] : 0.0;
-        const double px = p * x0;
-        s0 = fma(px, y0, s0);
-        sk = fma(px, yk, sk);
-        sk = fma(m * (p * y0), xk, sk);
+        const double px = p * xp[0], py = p * yp[0];
+        double* o = prod + (t - ta);
+        o[0] = px * yp[0];
+#pragma unroll 4
+        for (int k = 1; k < K; k++) {
+            const int kx = mapX ? mapX[k] : k, ky = mapY ? mapY[k] : k;
+            const double xv = kx >= 0 ? xp[kx] : 0.0, yv = ky >= 0 ? yp[ky] : 0.0;
+            o[(size_t)k * cap] = fma(px, yv, py * xv);
+        }
+    }
+}
+
+// P2 helper: (S0, Sk) of cell range [tb, te) (indices relative to the P1 window)
+__device__ __forceinline__ void cellsum(const double* __restrict__ prod, int cap, int k, uint32_t tb, uint32_t te,
+                                        double& S0, double& Sk) {
+    double s0 = 0.0, sk = 0.0;
+    const double* pk = prod + (size_t)k * cap;
+    for (uint32_t t = tb; t < te; t++) {
+        s0 += prod[t];
+        sk += pk[t];
     }
     S0 = s0;
     Sk = sk;
 }
 
-// Πloss (src/core.jl:172-176) for cell c with child indices lf/lg (−1: incompatible -> getl = 0)
+// Πloss (src/core.jl:172-176) for a cell with child indices lf/lg (−1: incompatible -> getl = 0)
 __device__ __forceinline__ void loss_term(int lf, int lg, const double* finF, int KF, int kf, const double* finG,
                                           int KG, int kg, double ef0, double efk, double eg0, double egk, double m,
                                           double& c0, double& ck) {
@@ -75,8 +98,49 @@ __device__ __forceinline__ void loss_term(int lf, int lg, const double* finF, in
     ck = fk * eg0 + gk * ef0 + m * (f0 * egk + g0 * efk);
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT) k_dp(DPArgs A, int perm_off) {
+// The n slices of one branch (src/core.jl:121-128,178-185):
+//   ℓ_i[γ] = ϕ_i ℓ_{i−1}[γ] + ψ_i Σ_t p_t ℓ_{i−1}[γ1] ℓ_{i−1}[γ2]
+// `cur` holds row 1 on entry; rows alternate between fin and scr so that row n+1 lands in fin.
+template <bool WARP>
+__device__ __forceinline__ void run_slices(int n, int C, int K, double* fin, double* scr, double* cur,
+                                           const Ent* s_dents, const uint32_t* s_dptr, uint32_t nd,
+                                           const double2* __restrict__ pprow, double* prod, int cap, double* ellp,
+                                           int tid, int nt) {
+    const int GP = nt / K;
+    const int grp = tid / K, k = tid - grp * K;
+    const bool on = grp < GP && grp < C;
+    const double m = k == 0 ? 0.0 : 1.0;
+    uint32_t tb0 = 0, te0 = 0;  // the lane's first cell keeps its term range in registers
+    if (on) { tb0 = s_dptr[grp]; te0 = s_dptr[grp + 1]; }
+    double2 c0 = make_double2(0, 0), ck = c0;
+    if (on && n >= 1) { c0 = __ldg(pprow + K); ck = __ldg(pprow + K + k); }
+    for (int i = 1; i <= n; i++) {
+        const double* src = cur;
+        double* dst = (cur == fin) ? scr : fin;
+        terms<false>(s_dents, 0, nd, src, K, nullptr, src, K, nullptr, K, prod, cap, tid, nt);
+        double2 n0 = c0, nk = ck;  // prefetch the next slice's ϕ/ψ while this one is computed
+        if (on && i < n) { n0 = __ldg(pprow + (size_t)(i + 1) * K); nk = __ldg(pprow + (size_t)(i + 1) * K + k); }
+        scope_sync<WARP>();
+        if (on)
+            for (int c = grp; c < C; c += GP) {
+                uint32_t tb = tb0, te = te0;
+                if (c != grp) { tb = s_dptr[c]; te = s_dptr[c + 1]; }
+                double s0, sk;
+                cellsum(prod, cap, k, tb, te, s0, sk);
+                const double o0 = src[c * K], ok = src[c * K + k];
+                const double r = c0.x * ok + c0.y * sk + m * (ck.x * o0 + ck.y * s0);
+                dst[c * K + k] = r;
+                if (ellp && k == 0) ellp[(size_t)i * C + c] = r;
+            }
+        c0 = n0;
+        ck = nk;
+        cur = dst;
+        scope_sync<WARP>();
+    }
+}
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
     EXTERN_SHARED(smem_raw);
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -85,19 +149,30 @@ __global__ void __launch_bounds__(NT) k_dp(DPArgs A, int perm_off) {
     const int nn = M.nn, Kmax = PL.Kmax;
     const int fam = A.perm[perm_off + blockIdx.x];
     const FamHdr* Hp = A.hdr + fam;
-    struct { uint64_t base, ell_off; uint32_t nlev, rows_len, scr_len, leafmax, blob_bytes; } H;
-    H.base = Hp->base; H.ell_off = Hp->ell_off; H.nlev = Hp->nlev; H.blob_bytes = Hp->blob_bytes;
-    H.rows_len = Hp->rows_len[A.plan]; H.scr_len = Hp->scr_len[A.plan]; H.leafmax = Hp->leafmax[A.plan];
-    const unsigned char* blob = A.arena + H.base;
+    const uint64_t base = Hp->base;
+    const uint32_t nlev = Hp->nlev, blob_bytes = Hp->blob_bytes;
+    const uint32_t rows_len = Hp->rows_len[A.plan], scr_len = Hp->scr_len[A.plan], prod_len = Hp->prod_len[A.plan];
+    const uint32_t leafmax = Hp->leafmax[A.plan], leaf_prod = Hp->leaf_prod[A.plan];
+    const uint32_t stage_bytes = Hp->stage_bytes, leaf_stage = Hp->leaf_stage;
+    const unsigned char* blob = A.arena + base;
     const NodeRec* nrec = reinterpret_cast<const NodeRec*>(blob);
     const uint32_t* words = reinterpret_cast<const uint32_t*>(blob);
     const Ent* ents = reinterpret_cast<const Ent*>(blob);
 
     // pull the whole blob towards L2 now; it is consumed node by node below
-    for (uint32_t o = tid * 128u; o < H.blob_bytes; o += NT * 128u) PREFETCH_L2(blob + o);
+    for (uint32_t o = tid * 128u; o < blob_bytes; o += NT * 128u) PREFETCH_L2(blob + o);
 
-    int* s_roff = reinterpret_cast<int*>(smem_raw);  // [nn+1] row offsets (doubles)
-    double* rows = reinterpret_cast<double*>(smem_raw + (((nn + 1) * sizeof(int) + 15) & ~size_t(15)));
+    // ---- shared memory carve-up ----
+    int* s_roff = reinterpret_cast<int*>(smem_raw);                      // [nn+1] row offsets (doubles)
+    int16_t* s_cmap = reinterpret_cast<int16_t*>(s_roff + nn + 1);       // [nn*2*Kmax]
+    const size_t hdr_bytes = (((nn + 1) * sizeof(int) + (size_t)nn * 2 * Kmax * sizeof(int16_t)) + 15) & ~size_t(15);
+    double* rows = reinterpret_cast<double*>(smem_raw + hdr_bytes);
+    double* scr = rows + rows_len;
+    double* prod = scr + scr_len;
+    unsigned char* stage = reinterpret_cast<unsigned char*>(prod + prod_len);
+    unsigned char* leaf_area = stage + stage_bytes;
+    const size_t leaf_area_bytes = (size_t)(leafmax + leaf_prod) * sizeof(double) + leaf_stage;
+    for (int i = tid; i < nn * 2 * Kmax; i += NT) s_cmap[i] = PL.cmap[i];
     if (tid == 0) {
         int o = 0;
         for (int e = 0; e < nn; e++) {
@@ -107,9 +182,7 @@ __global__ void __launch_bounds__(NT) k_dp(DPArgs A, int perm_off) {
         s_roff[nn] = o;
     }
     __syncthreads();
-    double* scr = rows + H.rows_len;
-    unsigned char* stage = reinterpret_cast<unsigned char*>(scr + H.scr_len);
-    double* const ell_base = A.ell ? A.ell + H.ell_off : nullptr;
+    double* const ell_base = A.ell ? A.ell + Hp->ell_off : nullptr;
     auto ell_of = [&](int e) -> double* {  // node e's matrix inside the family's ℓ (node-index order)
         if (!ell_base) return nullptr;
         size_t o = 0;
@@ -125,47 +198,29 @@ __global__ void __launch_bounds__(NT) k_dp(DPArgs A, int perm_off) {
         if (C == 0) continue;
         const int K = PL.K[e], n = M.nsl[e];
         double* fin = rows + s_roff[e];
-        const int GP = 32 / K;  // K_leaf <= 3
-        const int grp = lane / K, k = lane - grp * K;
-        const bool on = grp < GP;
-        const double m = k == 0 ? 0.0 : 1.0;
         if (R.nonleaf == 0 && A.skip_leaf) {  // family-independent: ℓ_n = leafℙ·Πϕ_i from k_tables
-            if (on)
-                for (int c = grp; c < C; c += GP) fin[c * K + k] = PL.leaf[e * Kmax + k];
+            for (int i = lane; i < C * K; i += 32) fin[i] = PL.leaf[e * Kmax + (i % K)];
             continue;
         }
         double* ellp = ell_of(e);
-        double* wscr = scr + warp * H.leafmax;
+        double* wscr = reinterpret_cast<double*>(leaf_area + warp * leaf_area_bytes);
+        double* wprod = wscr + leafmax;
+        uint4* wst = reinterpret_cast<uint4*>(wprod + leaf_prod);
+        const int nd16 = (int)R.ndent, dp16 = (C + 1 + 3) >> 2;
+        copy16(wst, reinterpret_cast<const uint4*>(ents + R.dent_off), nd16, lane, 32);
+        copy16(wst + nd16, reinterpret_cast<const uint4*>(words + R.dptr_off), dp16, lane, 32);
         double* cur = (n & 1) ? wscr : fin;  // row i lives in fin iff (n − i) is even
         const int nleafc = C - (int)R.nonleaf;
-        if (on)
-            for (int c = grp; c < C; c += GP) {
-                const double v = (c < nleafc && k == 0) ? M.leafP[e] : 0.0;
-                cur[c * K + k] = v;
-                if (ellp && k == 0) ellp[c] = v;
-            }
-        __syncwarp();
-        const uint32_t* dptr = words + R.dptr_off;
-        const Ent* dents = ents + R.dent_off;
-        const double2* pprow = PL.pp + PL.toff[e];
-        for (int i = 1; i <= n; i++) {
-            const double* src = cur;
-            double* dst = (cur == fin) ? wscr : fin;
-            if (on && grp < C) {
-                const double2 c0 = pprow[(size_t)i * K];
-                const double2 ck = pprow[(size_t)i * K + k];
-                for (int c = grp; c < C; c += GP) {
-                    double s0 = 0.0, sk = 0.0;
-                    if (c >= nleafc) pairsum<true>(dents, dptr[c], dptr[c + 1], src, K, k, src, K, k, m, s0, sk);
-                    const double o0 = src[c * K], ok = src[c * K + k];
-                    const double r = c0.x * ok + c0.y * sk + m * (ck.x * o0 + ck.y * s0);
-                    dst[c * K + k] = r;
-                    if (ellp && k == 0) ellp[(size_t)i * C + c] = r;
-                }
-            }
-            cur = dst;
-            __syncwarp();
+        for (int i = lane; i < C * K; i += 32) {
+            const int c = i / K, k = i - c * K;
+            const double v = (c < nleafc && k == 0) ? M.leafP[e] : 0.0;
+            cur[i] = v;
+            if (ellp && k == 0) ellp[c] = v;
         }
+        __syncwarp();
+        run_slices<true>(n, C, K, fin, wscr, cur, reinterpret_cast<const Ent*>(wst),
+                         reinterpret_cast<const uint32_t*>(wst + nd16), R.ndent, PL.pp + PL.toff[e], wprod,
+                         K > 0 ? (int)(leaf_prod / K) : 0, ellp, lane, 32);
     }
     __syncthreads();
 
@@ -178,139 +233,172 @@ __global__ void __launch_bounds__(NT) k_dp(DPArgs A, int perm_off) {
         const int kind = M.kind[e], K = PL.K[e], n = M.nsl[e];
         double* fin = rows + s_roff[e];
         double* ellp = ell_of(e);
-        // lane -> (cell group, component): groups of K lanes, GP groups per pass (K <= NT checked on the host)
+        const int cap = (int)(prod_len / K);
+        // lane -> (cell group, component) for the P2 passes of row 1
         const int GP = NT / K;
         const int grp = tid / K, k = tid - grp * K;
         const bool on = grp < GP;
         const double m = k == 0 ? 0.0 : 1.0;
 
         // ---- stage this node's lists: [dents | dptr | tptr,lossF,lossG,lev] ----
-        const int nd16 = (kind == WHALE_ROOT) ? 0 : (int)R.ndent;     // Πroot terms are read once: stay global
+        const int nd16 = (kind == WHALE_ROOT) ? 0 : (int)R.ndent;  // Πroot terms are read once: stay global
         const int dp16 = (C + 1 + 3) >> 2;
-        const int tp16 = (kind == WHALE_WGD) ? 0 : ((3 * C + 1 + (kind == WHALE_ROOT ? (int)H.nlev + 1 : 0) + 3) >> 2);
+        const int tp16 = (kind == WHALE_WGD) ? 0 : ((3 * C + 1 + (kind == WHALE_ROOT ? (int)nlev + 1 : 0) + 3) >> 2);
         uint4* st4 = reinterpret_cast<uint4*>(stage);
-        {
-            const uint4* g_de = reinterpret_cast<const uint4*>(ents + R.dent_off);
-            const uint4* g_dp = reinterpret_cast<const uint4*>(words + R.dptr_off);
-            const uint4* g_tp = reinterpret_cast<const uint4*>(words + R.tptr_off);
-            for (int i = tid; i < nd16; i += NT) CP_ASYNC16(st4 + i, g_de + i);
-            for (int i = tid; i < dp16; i += NT) CP_ASYNC16(st4 + nd16 + i, g_dp + i);
-            for (int i = tid; i < tp16; i += NT) CP_ASYNC16(st4 + nd16 + dp16 + i, g_tp + i);
-        }
+        copy16(st4, reinterpret_cast<const uint4*>(ents + R.dent_off), nd16, tid, NT);
+        copy16(st4 + nd16, reinterpret_cast<const uint4*>(words + R.dptr_off), dp16, tid, NT);
+        copy16(st4 + nd16 + dp16, reinterpret_cast<const uint4*>(words + R.tptr_off), tp16, tid, NT);
         const Ent* s_dents = reinterpret_cast<const Ent*>(stage);
         const uint32_t* s_dptr = reinterpret_cast<const uint32_t*>(st4 + nd16);
         const uint32_t* s_tptr = reinterpret_cast<const uint32_t*>(st4 + nd16 + dp16);
         const int32_t* s_lossF = reinterpret_cast<const int32_t*>(s_tptr + C + 1);
         const int32_t* s_lossG = s_lossF + C;
         const uint32_t* s_lev = reinterpret_cast<const uint32_t*>(s_lossG + C);
-        CP_ASYNC_WAIT();
-        __syncthreads();
 
-        // children, shared by row-1 formulas
+        // children, shared by the row-1 formulas
         const int f = M.child0[e], g = M.child1[e];
         const int KF = PL.K[f];
         const double* finF = rows + s_roff[f];
-        const int kf = k == 0 ? 0 : PL.cmap[(e * 2 + 0) * Kmax + k];
-
-        if (kind == WHALE_ROOT) {
-            // whaleroot! src/core.jl:130-149: clades ascending in size, level-synchronous, in place
-            const int KG = PL.K[g];
-            const double* finG = rows + s_roff[g];
-            const int kg = k == 0 ? 0 : PL.cmap[(e * 2 + 1) * Kmax + k];
-            const double* epsF = PL.eps + PL.toff[f] + (size_t)M.nsl[f] * KF;
-            const double* epsG = PL.eps + PL.toff[g] + (size_t)M.nsl[g] * KG;
-            const double ef0 = epsF[0], eg0 = epsG[0];
-            const double efk = (k > 0 && kf >= 0) ? epsF[kf] : 0.0;
-            const double egk = (k > 0 && kg >= 0) ? epsG[kg] : 0.0;
-            const double cx0 = PL.cx[e * Kmax], cy0 = PL.cy[e * Kmax];
-            const double cxk = PL.cx[e * Kmax + k], cyk = PL.cy[e * Kmax + k];
-            const Ent* g_dents = ents + R.dent_off;
-            const Ent* g_tents = ents + R.tent_off;
-            for (uint32_t L = 0; L < H.nlev; L++) {
-                const int c0 = (int)s_lev[L], c1 = (int)s_lev[L + 1];
-                if (on)
-                    for (int c = c0 + grp; c < c1; c += GP) {
-                        double a0, ak, b0, bk, l0, lk;
-                        pairsum<true>(g_dents, s_dptr[c], s_dptr[c + 1], fin, K, k, fin, K, k, m, a0, ak);
-                        pairsum<true>(g_tents, s_tptr[c], s_tptr[c + 1], finF, KF, kf, finG, KG, kg, m, b0, bk);
-                        loss_term(s_lossF[c], s_lossG[c], finF, KF, kf, finG, KG, kg, ef0, efk, eg0, egk, m, l0, lk);
-                        const double u0 = b0 + l0, uk = bk + lk;
-                        const double r = cx0 * ak + cy0 * uk + m * (cxk * a0 + cyk * u0);
-                        fin[c * K + k] = r;
-                        if (ellp && k == 0) ellp[c] = r;
-                    }
-                __syncthreads();
-            }
-            if (tid < K) {  // log L and its gradient (src/core.jl:35-36)
-                const double Lv = fin[(C - 1) * K];
-                double o;
-                if (Lv > 0.0) o = tid == 0 ? log(Lv) : fin[(C - 1) * K + tid] / Lv;
-                else o = tid == 0 ? -dinf() : 0.0;
-                A.out_fam[(size_t)fam * K + tid] = o;
-            }
-            continue;
-        }
-
-        // ---- row 1 of an internal / WGD branch ----
+        const int16_t* mapF = s_cmap + (e * 2 + 0) * Kmax;
+        const int16_t* mapG = s_cmap + (e * 2 + 1) * Kmax;
+        const int kf = mapF[k];
         double* cur = (n & 1) ? scr : fin;  // row i lives in fin iff (n − i) is even
-        if (kind == WHALE_INTERNAL) {  // Πspeciation + Πloss, src/core.jl:95-98,160-176
-            const int KG = PL.K[g];
-            const double* finG = rows + s_roff[g];
-            const int kg = k == 0 ? 0 : PL.cmap[(e * 2 + 1) * Kmax + k];
-            const double* epsF = PL.eps + PL.toff[f] + (size_t)M.nsl[f] * KF;
-            const double* epsG = PL.eps + PL.toff[g] + (size_t)M.nsl[g] * KG;
-            const double ef0 = epsF[0], eg0 = epsG[0];
-            const double efk = (k > 0 && kf >= 0) ? epsF[kf] : 0.0;
-            const double egk = (k > 0 && kg >= 0) ? epsG[kg] : 0.0;
-            const Ent* g_tents = ents + R.tent_off;
-            if (on)
-                for (int c = grp; c < C; c += GP) {
-                    double b0, bk, l0, lk;
-                    pairsum<true>(g_tents, s_tptr[c], s_tptr[c + 1], finF, KF, kf, finG, KG, kg, m, b0, bk);
-                    loss_term(s_lossF[c], s_lossG[c], finF, KF, kf, finG, KG, kg, ef0, efk, eg0, egk, m, l0, lk);
-                    const double r = k == 0 ? b0 + l0 : bk + lk;
-                    cur[c * K + k] = r;
-                    if (ellp && k == 0) ellp[c] = r;
-                }
-        } else {  // WGD: q·Σ p ℓ_f[γ1]ℓ_f[γ2] + (1−q+2qϵ_f)·ℓ_f[γ]   src/core.jl:103-119,187-199
+
+        if (kind == WHALE_WGD) {
+            // q·Σ p ℓ_f[γ1]ℓ_f[γ2] + (1−q+2qϵ_f)·ℓ_f[γ]   src/core.jl:103-119,187-199
+            __syncthreads();
+            terms<false>(s_dents, 0, R.ndent, finF, KF, mapF, finF, KF, mapF, K, prod, cap, tid, NT);
             const double cx0 = PL.cx[e * Kmax], cy0 = PL.cy[e * Kmax];
             const double cxk = PL.cx[e * Kmax + k], cyk = PL.cy[e * Kmax + k];
+            __syncthreads();
             if (on)
                 for (int c = grp; c < C; c += GP) {
                     double s0, sk;
-                    pairsum<false>(s_dents, s_dptr[c], s_dptr[c + 1], finF, KF, kf, finF, KF, kf, m, s0, sk);
+                    cellsum(prod, cap, k, s_dptr[c], s_dptr[c + 1], s0, sk);
                     const double u0 = finF[c * KF];
                     const double uk = kf >= 0 ? finF[c * KF + kf] : 0.0;
                     const double r = cy0 * sk + cx0 * uk + m * (cyk * s0 + cxk * u0);
                     cur[c * K + k] = r;
                     if (ellp && k == 0) ellp[c] = r;
                 }
-        }
-        __syncthreads();
-
-        // ---- slices: ℓ_i = ϕ_i ℓ_{i−1} + ψ_i Σ_t p ℓ_{i−1}[γ1] ℓ_{i−1}[γ2]   src/core.jl:121-128,178-185 ----
-        const double2* pprow = PL.pp + PL.toff[e];
-        uint32_t tb0 = 0, te0 = 0;  // the lane's first cell keeps its term range in registers
-        if (on && grp < C) { tb0 = s_dptr[grp]; te0 = s_dptr[grp + 1]; }
-        for (int i = 1; i <= n; i++) {
-            const double* src = cur;
-            double* dst = (cur == fin) ? scr : fin;
-            if (on && grp < C) {
-                const double2 c0 = pprow[(size_t)i * K];
-                const double2 ck = pprow[(size_t)i * K + k];
-                for (int c = grp; c < C; c += GP) {
-                    uint32_t tb = tb0, te = te0;
-                    if (c != grp) { tb = s_dptr[c]; te = s_dptr[c + 1]; }
-                    double s0, sk;
-                    pairsum<false>(s_dents, tb, te, src, K, k, src, K, k, m, s0, sk);
-                    const double o0 = src[c * K], ok = src[c * K + k];
-                    const double r = c0.x * ok + c0.y * sk + m * (ck.x * o0 + ck.y * s0);
-                    dst[c * K + k] = r;
-                    if (ellp && k == 0) ellp[(size_t)i * C + c] = r;
-                }
-            }
-            cur = dst;
             __syncthreads();
+            run_slices<false>(n, C, K, fin, scr, cur, s_dents, s_dptr, R.ndent, PL.pp + PL.toff[e], prod, cap, ellp,
+                              tid, NT);
+            continue;
+        }
+
+        // internal node or root: speciation + loss from the children's last rows (src/core.jl:160-176)
+        const int KG = PL.K[g];
+        const double* finG = rows + s_roff[g];
+        const int kg = mapG[k];
+        const double* epsF = PL.eps + PL.toff[f] + (size_t)M.nsl[f] * KF;
+        const double* epsG = PL.eps + PL.toff[g] + (size_t)M.nsl[g] * KG;
+        const double ef0 = epsF[0], eg0 = epsG[0];
+        const double efk = (k > 0 && kf >= 0) ? epsF[kf] : 0.0;
+        const double egk = (k > 0 && kg >= 0) ? epsG[kg] : 0.0;
+        const Ent* g_tents = ents + R.tent_off;
+        __syncthreads();  // staged lists visible
+        if (kind == WHALE_INTERNAL) {
+            // speciation terms may exceed the product window: process them in windows of `cap` terms, whole
+            // cells at a time (a single cell with more than `cap` terms falls back to a serial sum)
+            int cA = 0;
+            while (cA < C) {
+                const uint32_t ta = s_tptr[cA];
+                int cB = cA;
+                while (cB < C && s_tptr[cB + 1] - ta <= (uint32_t)cap) cB++;
+                if (cB == cA) {
+                    if (tid < K) {
+                        double s0 = 0.0, sk = 0.0;
+                        for (uint32_t t = ta; t < s_tptr[cA + 1]; t++) {
+                            const Ent en = g_tents[t];
+                            const double* xp = finF + en.i1 * KF;
+                            const double* yp = finG + en.i2 * KG;
+                            const double xv = kf >= 0 ? xp[kf] : 0.0, yv = kg >= 0 ? yp[kg] : 0.0;
+                            s0 = fma(en.p * xp[0], yp[0], s0);
+                            sk += fma(en.p * xp[0], yv, (en.p * yp[0]) * xv);
+                        }
+                        double l0, lk;
+                        loss_term(s_lossF[cA], s_lossG[cA], finF, KF, kf, finG, KG, kg, ef0, efk, eg0, egk, m, l0, lk);
+                        const double r = k == 0 ? s0 + l0 : sk + lk;
+                        cur[cA * K + k] = r;
+                        if (ellp && k == 0) ellp[cA] = r;
+                    }
+                    cB = cA + 1;
+                } else {
+                    terms<true>(g_tents, ta, s_tptr[cB], finF, KF, mapF, finG, KG, mapG, K, prod, cap, tid, NT);
+                    __syncthreads();
+                    if (on)
+                        for (int c = cA + grp; c < cB; c += GP) {
+                            double b0, bk, l0, lk;
+                            cellsum(prod, cap, k, s_tptr[c] - ta, s_tptr[c + 1] - ta, b0, bk);
+                            loss_term(s_lossF[c], s_lossG[c], finF, KF, kf, finG, KG, kg, ef0, efk, eg0, egk, m, l0, lk);
+                            const double r = k == 0 ? b0 + l0 : bk + lk;
+                            cur[c * K + k] = r;
+                            if (ellp && k == 0) ellp[c] = r;
+                        }
+                }
+                __syncthreads();
+                cA = cB;
+            }
+            run_slices<false>(n, C, K, fin, scr, cur, s_dents, s_dptr, R.ndent, PL.pp + PL.toff[e], prod, cap, ellp,
+                              tid, NT);
+            continue;
+        }
+
+        // ---- root: ℓ_r[γ] = (1−η)ξ/η·a + η(1−ϵ)/ξ²·(b + c),  a = Σ p ℓ_r[γ1]ℓ_r[γ2] over the SAME row
+        //      (src/core.jl:130-158) => clades in ascending size, one level (= clade size) at a time.
+        //      Per level P1 covers the level's Πroot terms (window [0, na)) and speciation terms ([na, na+nb)).
+        const double cx0 = PL.cx[e * Kmax], cy0 = PL.cy[e * Kmax];
+        const double cxk = PL.cx[e * Kmax + k], cyk = PL.cy[e * Kmax + k];
+        const Ent* g_dents = ents + R.dent_off;
+        for (uint32_t L = 0; L < nlev; L++) {
+            const int c0 = (int)s_lev[L], c1 = (int)s_lev[L + 1];
+            const uint32_t ta = s_dptr[c0], na = s_dptr[c1] - ta;
+            const uint32_t ua = s_tptr[c0], nb = s_tptr[c1] - ua;
+            const bool fits = na + nb <= (uint32_t)cap;
+            if (fits) {
+                terms<true>(g_dents, ta, ta + na, fin, K, nullptr, fin, K, nullptr, K, prod, cap, tid, NT);
+                terms<true>(g_tents, ua, ua + nb, finF, KF, mapF, finG, KG, mapG, K, prod + na, cap, tid, NT);
+                __syncthreads();
+            }
+            if (on)
+                for (int c = c0 + grp; c < c1; c += GP) {
+                    double a0 = 0.0, ak = 0.0, b0 = 0.0, bk = 0.0, l0, lk;
+                    if (fits) {
+                        cellsum(prod, cap, k, s_dptr[c] - ta, s_dptr[c + 1] - ta, a0, ak);
+                        cellsum(prod, cap, k, na + s_tptr[c] - ua, na + s_tptr[c + 1] - ua, b0, bk);
+                    } else {  // oversized level: serial sums per lane
+                        for (uint32_t t = s_dptr[c]; t < s_dptr[c + 1]; t++) {
+                            const Ent en = g_dents[t];
+                            const double* xp = fin + en.i1 * K;
+                            const double* yp = fin + en.i2 * K;
+                            a0 = fma(en.p * xp[0], yp[0], a0);
+                            ak += fma(en.p * xp[0], yp[k], (en.p * yp[0]) * xp[k]);
+                        }
+                        for (uint32_t t = s_tptr[c]; t < s_tptr[c + 1]; t++) {
+                            const Ent en = g_tents[t];
+                            const double* xp = finF + en.i1 * KF;
+                            const double* yp = finG + en.i2 * KG;
+                            const double xv = kf >= 0 ? xp[kf] : 0.0, yv = kg >= 0 ? yp[kg] : 0.0;
+                            b0 = fma(en.p * xp[0], yp[0], b0);
+                            bk += fma(en.p * xp[0], yv, (en.p * yp[0]) * xv);
+                        }
+                        if (k == 0) { ak = a0; bk = b0; }
+                    }
+                    loss_term(s_lossF[c], s_lossG[c], finF, KF, kf, finG, KG, kg, ef0, efk, eg0, egk, m, l0, lk);
+                    const double u0 = b0 + l0, uk = k == 0 ? u0 : bk + lk;
+                    const double r = cx0 * ak + cy0 * uk + m * (cxk * a0 + cyk * u0);
+                    fin[c * K + k] = r;
+                    if (ellp && k == 0) ellp[c] = r;
+                }
+            __syncthreads();
+        }
+        if (tid < K) {  // log L and its gradient (src/core.jl:35-36)
+            const double Lv = fin[(C - 1) * K];
+            double o;
+            if (Lv > 0.0) o = tid == 0 ? log(Lv) : fin[(C - 1) * K + tid] / Lv;
+            else o = tid == 0 ? -dinf() : 0.0;
+            A.out_fam[(size_t)fam * K + tid] = o;
         }
     }
 }

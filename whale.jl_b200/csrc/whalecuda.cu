@@ -97,6 +97,15 @@ struct whale_model {
     cudaStream_t stream = nullptr;
 };
 
+// threads per family CTA: 128 (7 CTAs/SM by registers) or 256 (4 CTAs/SM); WHALE_NT overrides for experiments
+static int dp_nt() {
+    static int nt = [] {
+        const char* s = getenv("WHALE_NT");
+        int v = s ? atoi(s) : 128;
+        return v == 256 ? 256 : 128;
+    }();
+    return nt;
+}
 constexpr int MAX_BINS = 8;
 struct Bin {
     int off, count;
@@ -216,7 +225,7 @@ static cudaError_t upload_plan(Plan& pl, int nn) {
 }
 
 static int g_device = 0;
-constexpr int DP_NT = 128;  // threads per family CTA
+
 
 extern "C" {
 
@@ -337,9 +346,11 @@ int32_t whale_model_destroy(whale_model_t m) {
 // ---- the packer: reference-layout CSR -> per-branch resolved device arena ----
 static inline void pad4(std::vector<uint32_t>& w) { while (w.size() & 3) w.push_back(0); }
 
-static size_t smem_need(const whale_model* m, const FamHdr& h, int plan) {
-    return ((((size_t)m->nn + 1) * sizeof(int) + 15) & ~size_t(15)) +
-           ((size_t)h.rows_len[plan] + h.scr_len[plan]) * sizeof(double) + h.stage_bytes;
+static size_t smem_need(const whale_model* m, const FamHdr& h, int plan) {  // mirrors the carve-up in k_dp
+    const size_t nn = m->nn, Kmax = m->plan[plan].Kmax, NW = dp_nt() / 32;
+    const size_t hdr = (((nn + 1) * sizeof(int) + nn * 2 * Kmax * sizeof(int16_t)) + 15) & ~size_t(15);
+    return hdr + ((size_t)h.rows_len[plan] + h.scr_len[plan] + h.prod_len[plan]) * sizeof(double) + h.stage_bytes +
+           NW * (((size_t)h.leafmax[plan] + h.leaf_prod[plan]) * sizeof(double) + h.leaf_stage);
 }
 
 int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t* out) {
@@ -391,7 +402,7 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
         std::vector<uint32_t> wordsv;   // pointer / loss / level words; every array starts on a 16-byte boundary
         std::vector<Ent> entsv;         // term entries
         uint32_t sumC = 0, nlev = 0;
-        size_t stage_bytes = 0;
+        size_t stage_bytes = 0, leaf_stage = 0;
         double wk = 0.0;
         for (int e = 0; e < nn; e++) {
             NodeRec& R = recs[e];
@@ -463,7 +474,9 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
                     D->aggTroot += (double)(soff[G] - soff[0]);
                 }
             }
-            if (kind != WHALE_LEAF) {  // what k_dp stages in shared memory for this node
+            if (kind == WHALE_LEAF) {
+                leaf_stage = std::max(leaf_stage, 16 * ((size_t)R.ndent + ((size_t)C + 1 + 3) / 4));
+            } else {  // what k_dp stages in shared memory for this node
                 size_t nd16 = kind == WHALE_ROOT ? 0 : R.ndent;
                 size_t dp16 = ((size_t)C + 1 + 3) / 4;
                 size_t tp16 = kind == WHALE_WGD ? 0 : (3 * (size_t)C + 1 + (kind == WHALE_ROOT ? nlev + 1 : 0) + 3) / 4;
@@ -493,22 +506,33 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
         H.G = G;
         H.nlev = nlev;
         H.stage_bytes = (uint32_t)stage_bytes;
+        H.leaf_stage = (uint32_t)leaf_stage;
         H.blob_bytes = (uint32_t)total;
         work[f] = wk;
         // SURVEY §8d algorithmic bytes per evaluation: 12·T + 2·Γ + 4·Σ_e C_e
         algo_bytes += 12 * (soff[G] - soff[0]) + 2 * (int64_t)G + 4 * (int64_t)sumC;
         for (int g = 0; g < 2; g++) {  // shared-memory budget per tangent plan
             const Plan& pl = m->plan[g];
-            uint32_t rows = 0, mxinner = 0, mxleaf = 0;
+            uint32_t rows = 0, mxinner = 0, mxleaf = 0, prod = 0, lprod = 0;
             for (int e = 0; e < nn; e++) {
-                uint32_t ck = Cs[e] * (uint32_t)pl.K[e];
+                const uint32_t K = (uint32_t)pl.K[e], ck = Cs[e] * K;
                 rows += ck;
-                if (m->kind[e] == WHALE_LEAF) mxleaf = std::max(mxleaf, ck);
-                else if (m->kind[e] != WHALE_ROOT) mxinner = std::max(mxinner, ck);
+                if (m->kind[e] == WHALE_LEAF) {
+                    mxleaf = std::max(mxleaf, ck);
+                    lprod = std::max(lprod, recs[e].ndent * K);
+                } else if (m->kind[e] != WHALE_ROOT) {
+                    mxinner = std::max(mxinner, ck);
+                    prod = std::max(prod, std::max(recs[e].ndent, recs[e].ntent) * K);
+                }
             }
-            H.rows_len[g] = rows;
-            H.leafmax[g] = mxleaf;
-            H.scr_len[g] = (std::max(mxinner, (uint32_t)MAX_WARPS * mxleaf) + 1) & ~1u;
+            // the root's levels use the same window; give it at least 64 terms so typical levels fit
+            prod = std::max(prod, 64u * (uint32_t)pl.K[m->root]);
+            auto even = [](uint32_t v) { return (v + 1) & ~1u; };
+            H.rows_len[g] = even(rows);
+            H.scr_len[g] = even(mxinner);
+            H.prod_len[g] = even(prod);
+            H.leafmax[g] = even(mxleaf);
+            H.leaf_prod[g] = even(lprod);
         }
     }
     D->ell_total = ell_total;
@@ -596,24 +620,29 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
     g_launches++;
     if (prof) CU(cudaEventRecord(D->ev[1], st));
     // K2: one launch per shared-memory bin, concurrently on side streams
-    if (pl.Kmax > DP_NT) return fail(WHALE_ERR_CAPACITY, "K=%d tangent components exceed %d lanes (parameter chunking not built yet)", pl.Kmax, DP_NT);
+    const int NT = dp_nt();
+    if (pl.Kmax > NT) return fail(WHALE_ERR_CAPACITY, "K=%d tangent components exceed %d lanes (parameter chunking not built yet)", pl.Kmax, NT);
     const std::vector<Bin>& bins = D->bins[g];
     if (bins[0].smem > 227 * 1024) return fail(WHALE_ERR_CAPACITY, "a family needs %zu bytes of shared memory (> 227 KB)", bins[0].smem);
-    static thread_local size_t smem_set = 0;
-    if (bins[0].smem > smem_set) {
-        CU(cudaFuncSetAttribute(k_dp<DP_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        smem_set = 227 * 1024;
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(k_dp<128, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CU(cudaFuncSetAttribute(k_dp<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
     }
     DPArgs a{m->dev, pl.dev, D->d_arena, D->d_hdr, D->d_perm[g], D->d_out_fam, keep ? D->d_ell : nullptr, g, keep ? 0 : 1};
-    if (bins.size() == 1) {
-        LAUNCH(k_dp<DP_NT>, bins[0].count, DP_NT, bins[0].smem, st, a, bins[0].off);
+    auto launch_bin = [&](const Bin& b, cudaStream_t s) {
+        if (NT == 256) LAUNCH((k_dp<256, 4>), b.count, 256, b.smem, s, a, b.off);
+        else LAUNCH((k_dp<128, 7>), b.count, 128, b.smem, s, a, b.off);
         g_launches++;
+    };
+    if (bins.size() == 1) {
+        launch_bin(bins[0], st);
     } else {
         CU(cudaEventRecord(D->ev_fork, st));
         for (size_t b = 0; b < bins.size(); b++) {
             CU(cudaStreamWaitEvent(D->side[b], D->ev_fork, 0));
-            LAUNCH(k_dp<DP_NT>, bins[b].count, DP_NT, bins[b].smem, D->side[b], a, bins[b].off);
-            g_launches++;
+            launch_bin(bins[b], D->side[b]);
             CU(cudaEventRecord(D->ev_join[b], D->side[b]));
             CU(cudaStreamWaitEvent(st, D->ev_join[b], 0));
         }
