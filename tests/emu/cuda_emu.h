@@ -32,6 +32,12 @@ inline thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 struct uint4 { unsigned x, y, z, w; };
 struct double2 { double x, y; };
+struct int4 { int x, y, z, w; };
+inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+// explicit round-to-nearest ops (the emulation build is compiled with -ffp-contract=off)
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline double __hiloint2double(int hi, int lo) {

@@ -46,3 +46,28 @@ def test_emu_slices_and_ell(L):
     dh = L.data_create(mh, golden_fams(g, [3]))
     L.logpdf_grad(mh, dh, x, g["m_pleaf"], 1, keep_ell=True)
     np.testing.assert_allclose(L.ell_get(dh, 0), g["ell_3"], rtol=1e-11, atol=0)
+
+
+def _check_backtrack(L, name, fams, nbt_check=None):
+    """Backtracked trees must be identical to the oracle's for the same uniforms (golden bt_* arrays)."""
+    g = load_golden(name)
+    seed, F, nbt, stride = (int(v) for v in g["bt_seed"])
+    U = np.random.default_rng(seed).random((F, nbt, stride))
+    counts = g["bt_counts"].reshape(F, nbt, 2)
+    starts = np.concatenate([[0], np.cumsum(g["bt_counts"][:, 0])])
+    mh = L.model_create(golden_model(g))
+    dh = L.data_create(mh, golden_fams(g, fams))
+    L.logpdf_grad(mh, dh, g["xs"][-1], g["m_pleaf"], 1, keep_ell=True)
+    cnt, st, nodes = L.backtrack(mh, dh, nbt, U[fams], max_nodes=256)
+    assert np.all(st == 0)
+    for i, f in enumerate(fams):
+        for s in range(nbt):
+            want = g["bt_nodes"][starts[f * nbt + s]:starts[f * nbt + s + 1]]
+            assert cnt[i, s] == counts[f, s, 0]
+            assert np.array_equal(nodes[i, s, :cnt[i, s]], want), (name, f, s)
+
+
+def test_emu_backtrack_matches_oracle(L):
+    _check_backtrack(L, "c1_example1", [0, 7])
+    _check_backtrack(L, "const_wgdturing", [2])
+    _check_backtrack(L, "mul_tree", [5])

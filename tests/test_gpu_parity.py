@@ -141,3 +141,43 @@ def test_full_size_properties(L, tmp_path):
     lf2, _ = W.logpdf_per_family(w, ccd2)
     assert np.array_equal(lf2, lf[perm])  # bit-identical per family, independent of batch position
     assert W.logpdf(w, ccd2) == pytest.approx(ll, rel=1e-13)
+
+
+@pytest.mark.parametrize("name", ["c1_example1", "const_wgdturing", "mul_tree"])
+def test_backtrack_identical_to_oracle(L, name):
+    """src/track.jl:190-414: same uniforms => identical reconciled trees (γ, e, t, parent) as the oracle, for
+    every family and sample of the golden fixture (DLWGD with 2 WGDs, constant rates, MUL tree)."""
+    g = load_golden(name)
+    seed, F, nbt, stride = (int(v) for v in g["bt_seed"])
+    U = np.random.default_rng(seed).random((F, nbt, stride))
+    starts = np.concatenate([[0], np.cumsum(g["bt_counts"][:, 0])])
+    mh = L.model_create(golden_model(g))
+    dh = L.data_create(mh, golden_fams(g))
+    L.logpdf_grad(mh, dh, g["xs"][-1], g["m_pleaf"], 1, keep_ell=True)
+    cnt, st, nodes = L.backtrack(mh, dh, nbt, U, max_nodes=256)
+    assert np.all(st == 0)
+    for f in range(F):
+        for s in range(nbt):
+            want = g["bt_nodes"][starts[f * nbt + s]:starts[f * nbt + s + 1]]
+            assert np.array_equal(nodes[f, s, :cnt[f, s]], want), (name, f, s)
+
+
+def test_backtrack_api_and_invariants(L, tmp_path):
+    """Package-level `backtrack` on synthetic families: every gene leaf exactly once per tree, parents precede
+    children, loss nodes carry t = 0; needs logpdf_ first (WHALE_ERR_STATE otherwise)."""
+    d = synth.generate(str(tmp_path / "bt"), 16, seed=5)
+    w = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), synth.c1_species_tree(), 0.05)
+    ccd = W.read_ale(d, w)
+    with pytest.raises(wlib.WhaleCudaError):
+        W.backtrack(w, ccd, n_samples=2, seed=1)
+    W.logpdf_(w, ccd)
+    trees = W.backtrack(w, ccd, n_samples=8, seed=1)
+    assert len(trees) == 16 and len(trees[0]) == 8
+    for f, fam in enumerate(trees):
+        nl = len(ccd[f].leaves)
+        for t in fam:
+            leafbranch = w.kind[t[:, 1]] == 0
+            term = t[(t[:, 0] >= 0) & (t[:, 0] < nl) & leafbranch]
+            assert sorted(term[:, 0].tolist()) == list(range(nl))
+            assert np.all(t[1:, 3] < np.arange(1, len(t))) and t[0, 3] == -1
+            assert np.all(t[t[:, 0] < 0, 2] == 0)

@@ -11,8 +11,9 @@ from .newick import Node, readnw, getlca, getleaves, postwalk, insertnode, nwstr
 from .rates import ConstantDLWGD, DLWGD
 from .model import WhaleModel
 from .ccd import CCD, CCDVector, read_ale
-from .core import (logpdf, logpdf_, loglikelihood, logpdf_and_gradient, logpdf_per_family, ell, slices)
+from .core import (logpdf, logpdf_, loglikelihood, logpdf_and_gradient, logpdf_per_family, ell, slices, backtrack,
+                   BacktrackFailed)
 
 __all__ = ["Node", "readnw", "getlca", "getleaves", "postwalk", "insertnode", "nwstr", "extree", "ConstantDLWGD",
            "DLWGD", "WhaleModel", "CCD", "CCDVector", "read_ale", "logpdf", "logpdf_", "loglikelihood",
-           "logpdf_and_gradient", "logpdf_per_family", "ell", "slices"]
+           "logpdf_and_gradient", "logpdf_per_family", "ell", "slices", "backtrack", "BacktrackFailed"]

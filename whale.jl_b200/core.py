@@ -95,3 +95,32 @@ def slices(wm: WhaleModel):
     mh = _model_handle(wm)
     eps, phi, psi = _lib.get().slices(mh, wm.x(), wm.p_leaf(), int(wm.row_off[-1]))
     return [np.stack([eps[a:b], phi[a:b], psi[a:b]], axis=1) for a, b in zip(wm.row_off[:-1], wm.row_off[1:])]
+
+
+class BacktrackFailed(RuntimeError):
+    """`error("Backtracking failed, ...")` (src/track.jl:150)."""
+
+
+def backtrack(wm: WhaleModel, x, n_samples: int = 1, uniforms=None, seed=None, max_nodes: int = 512):
+    """`backtrack(wm, ccd)` / `backtrack(wm, ccds)` (src/track.jl:188-194): sample reconciled trees from the ℓ
+    left on the device by `logpdf_(wm, x)`.  The reference draws from the global RNG; here the uniform stream
+    is explicit (`uniforms[F, n_samples, stride]`, or generated from `seed`), consumed in the reference's order.
+
+    Returns, per family, a list of `n_samples` int arrays of shape (n_nodes, 4): columns (γ, e, t, parent) in
+    creation (DFS) order — γ = clade index (−1 for loss nodes), e = species-tree node index, t = 1-based slice
+    row where the lineage enters the state (0 for loss nodes), parent = row of the parent node (−1: root).
+    Post-processing into timetrees / summaries (src/track.jl:428-488, src/rectree.jl) is host-side and out of
+    the hot path."""
+    xs, single = _as_vector(x)
+    mh, dh = _data_handle(wm, xs)
+    F = len(xs)
+    if uniforms is None:
+        uniforms = np.random.default_rng(seed).random((F, n_samples, 4 * max_nodes))
+    cnt, st, nodes = _lib.get().backtrack(mh, dh, n_samples, uniforms, max_nodes)
+    if np.any(st == 1):
+        f, s = np.argwhere(st == 1)[0]
+        raise BacktrackFailed(f"Backtracking failed for family {f}, sample {s}")
+    if np.any(st > 1):
+        raise _lib.WhaleCudaError(3, "backtrack: node buffer or uniform stream too small (raise max_nodes / stride)")
+    out = [[nodes[f, s, :cnt[f, s]].copy() for s in range(n_samples)] for f in range(F)]
+    return out[0] if single else out

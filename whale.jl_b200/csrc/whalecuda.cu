@@ -22,6 +22,7 @@
 #include "whale_tables.cuh"
 #include "whale_dp.cuh"
 #include "whale_reduce.cuh"
+#include "whale_track.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -90,6 +91,7 @@ struct whale_model {
     ModelDev dev{};
     std::vector<void*> owned;
     Plan plan[2];  // 0: value only, 1: all raw parameters
+    bool x_host_valid = false;  // d_x / d_pleaf hold the parameters of the last host-pointer evaluation
     double* d_x = nullptr;      // staging for host-pointer calls
     double* d_pleaf = nullptr;  // [nn]
     double* d_out = nullptr;    // [1+P]
@@ -458,8 +460,11 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
                         int g1 = d->g1[t], g2 = d->g2[t];
                         int f1 = lidx[(size_t)fch * G + g1], gg2 = lidx[(size_t)gch * G + g2];
                         int gg1 = lidx[(size_t)gch * G + g1], f2 = lidx[(size_t)fch * G + g2];
-                        if (f1 >= 0 && gg2 >= 0) entsv.push_back(Ent{(uint16_t)f1, (uint16_t)gg2, 0u, d->p[t]});
-                        if (gg1 >= 0 && f2 >= 0) entsv.push_back(Ent{(uint16_t)f2, (uint16_t)gg1, 0u, d->p[t]});
+                        // pad = (ordinal of the triple within its clade) << 1 | ("gf": γ1 goes to child g) — used by
+                        // the backtracker to keep the reference's per-triple order (src/track.jl:304-324,369-397)
+                        const uint32_t ord = (uint32_t)(t - soff[g]) << 1;
+                        if (f1 >= 0 && gg2 >= 0) entsv.push_back(Ent{(uint16_t)f1, (uint16_t)gg2, ord, d->p[t]});
+                        if (gg1 >= 0 && f2 >= 0) entsv.push_back(Ent{(uint16_t)f2, (uint16_t)gg1, ord | 1u, d->p[t]});
                     }
                 }
                 wordsv.push_back((uint32_t)entsv.size() - R.tent_off);
@@ -474,6 +479,9 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
                     D->aggTroot += (double)(soff[G] - soff[0]);
                 }
             }
+            // local cell -> clade id (the compat list itself), for the backtracker's output
+            pad4(wordsv);
+            for (int j = 0; j < C; j++) wordsv.push_back((uint32_t)d->compat[coff[e] + j]);
             if (kind == WHALE_LEAF) {
                 leaf_stage = std::max(leaf_stage, 16 * ((size_t)R.ndent + ((size_t)C + 1 + 3) / 4));
             } else {  // what k_dp stages in shared memory for this node
@@ -684,6 +692,7 @@ int32_t whale_logpdf_grad(whale_model_t m, whale_data_t d, const double* x, cons
     CU(cudaMemcpyAsync(m->d_pleaf, hp + P, nn * sizeof(double), cudaMemcpyHostToDevice, m->stream));
     int32_t rc = enqueue_eval(m, d, m->d_x, condition, flags, m->d_out, m->stream);
     if (rc != WHALE_OK) return rc;
+    m->x_host_valid = true;
     double* ho = hp + P + nn;
     CU(cudaMemcpyAsync(ho, m->d_out, (1 + P) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
     CU(cudaStreamSynchronize(m->stream));
@@ -741,9 +750,48 @@ int32_t whale_ell_get(whale_data_t d, int32_t fam, double* out) {
     return WHALE_OK;
 }
 
-int32_t whale_backtrack(whale_model_t, whale_data_t, int32_t, const double*, int64_t, int32_t, int32_t*, int32_t*,
-                        int32_t*, int32_t*, int32_t*, int32_t*) {
-    return fail(WHALE_ERR_STATE, "whale_backtrack: kernel not built yet");
+int32_t whale_backtrack(whale_model_t m, whale_data_t d, int32_t n_samples, const double* uniforms, int64_t stride,
+                        int32_t max_nodes, int32_t* node_count, int32_t* gamma, int32_t* e, int32_t* t, int32_t* parent,
+                        int32_t* status) {
+    if (!m || !d || !uniforms || !node_count || !gamma || !e || !t || !parent || !status)
+        return fail(WHALE_ERR_ARG, "null argument");
+    if (d->m != m) return fail(WHALE_ERR_ARG, "data handle belongs to another model");
+    if (n_samples <= 0 || stride <= 0 || max_nodes <= 1) return fail(WHALE_ERR_ARG, "n_samples, stride and max_nodes must be positive");
+    if (!d->ell_valid || !d->d_ell) return fail(WHALE_ERR_STATE, "no ℓ kept: evaluate with WHALE_KEEP_ELL (logpdf!) first");
+    if (!m->x_host_valid) return fail(WHALE_ERR_STATE, "backtracking needs the parameters of a host-pointer evaluation");
+    CU(cudaSetDevice(m->device));
+    const size_t W = (size_t)d->F * n_samples;
+    double* d_u = nullptr;
+    int32_t *d_cnt = nullptr, *d_g = nullptr, *d_e = nullptr, *d_t = nullptr, *d_p = nullptr, *d_st = nullptr;
+    int4* d_stack = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_u); cudaFree(d_cnt); cudaFree(d_g); cudaFree(d_e); cudaFree(d_t); cudaFree(d_p); cudaFree(d_st);
+        cudaFree(d_stack);
+    };
+#define CUB(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { cleanup(); return fail(WHALE_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); } } while (0)
+    CUB(cudaMalloc((void**)&d_u, W * stride * sizeof(double)));
+    CUB(cudaMemcpy(d_u, uniforms, W * stride * sizeof(double), cudaMemcpyHostToDevice));
+    CUB(cudaMalloc((void**)&d_cnt, W * 4)); CUB(cudaMalloc((void**)&d_st, W * 4));
+    CUB(cudaMalloc((void**)&d_g, W * max_nodes * 4)); CUB(cudaMalloc((void**)&d_e, W * max_nodes * 4));
+    CUB(cudaMalloc((void**)&d_t, W * max_nodes * 4)); CUB(cudaMalloc((void**)&d_p, W * max_nodes * 4));
+    CUB(cudaMalloc((void**)&d_stack, W * max_nodes * sizeof(int4)));
+    Plan& p0 = m->plan[0];
+    LAUNCH(k_tables, 1, std::min(32, m->nn) * 32, 0, m->stream, m->dev, p0.dev, m->d_x, m->d_pleaf);
+    BTArgs a{m->dev, p0.dev, d->d_arena, d->d_hdr, d->d_ell, m->d_x, d_u, (long long)stride, d->F, n_samples, max_nodes,
+             d_cnt, d_g, d_e, d_t, d_p, d_st, d_stack};
+    LAUNCH(k_backtrack, (int)((W + 127) / 128), 128, 0, m->stream, a);
+    g_launches += 2;
+    CUB(cudaGetLastError());
+    CUB(cudaStreamSynchronize(m->stream));
+    CUB(cudaMemcpy(node_count, d_cnt, W * 4, cudaMemcpyDeviceToHost));
+    CUB(cudaMemcpy(status, d_st, W * 4, cudaMemcpyDeviceToHost));
+    CUB(cudaMemcpy(gamma, d_g, W * max_nodes * 4, cudaMemcpyDeviceToHost));
+    CUB(cudaMemcpy(e, d_e, W * max_nodes * 4, cudaMemcpyDeviceToHost));
+    CUB(cudaMemcpy(t, d_t, W * max_nodes * 4, cudaMemcpyDeviceToHost));
+    CUB(cudaMemcpy(parent, d_p, W * max_nodes * 4, cudaMemcpyDeviceToHost));
+#undef CUB
+    cleanup();
+    return WHALE_OK;
 }
 
 int32_t whale_work_estimate(whale_model_t m, whale_data_t d, uint32_t flags, double* flops, double* bytes) {

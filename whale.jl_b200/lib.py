@@ -151,6 +151,20 @@ class Lib:
             raise WhaleCudaError(2, "arena dump failed")
         return buf
 
+    def backtrack(self, mh, dh, n_samples, uniforms, max_nodes=512):
+        """whale_backtrack: uniforms [F, n_samples, stride]; returns (counts[F,S], status[F,S], nodes[F,S,max_nodes,4])
+        with node columns (gamma, e, t, parent)."""
+        F = self.L.whale_data_nfam(dh)
+        u = np.ascontiguousarray(uniforms, np.float64).reshape(F, n_samples, -1)
+        stride = u.shape[2]
+        W = F * n_samples
+        cnt, st = np.zeros(W, np.int32), np.zeros(W, np.int32)
+        g, e, t, p = (np.zeros(W * max_nodes, np.int32) for _ in range(4))
+        self.check(self.L.whale_backtrack(mh, dh, n_samples, _ptr(u, f64p), stride, max_nodes, _ptr(cnt, i32p),
+                                          _ptr(g, i32p), _ptr(e, i32p), _ptr(t, i32p), _ptr(p, i32p), _ptr(st, i32p)))
+        nodes = np.stack([g, e, t, p], axis=1).reshape(F, n_samples, max_nodes, 4)
+        return cnt.reshape(F, n_samples), st.reshape(F, n_samples), nodes
+
     def work_estimate(self, mh, dh, want_grad=True):
         fl, by = C.c_double(), C.c_double()
         self.check(self.L.whale_work_estimate(mh, dh, WANT_GRAD if want_grad else 0, C.byref(fl), C.byref(by)))
