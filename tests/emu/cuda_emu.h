@@ -81,6 +81,18 @@ inline void launch(int grid, int block, size_t smem, const std::function<void()>
     }
 }
 }  // namespace emu
+namespace emu {
+inline double g_shfl[64][32];  // per-warp exchange buffer
+// warp shuffle (all 32 lanes of the warp must call it, as on the device with a full mask)
+inline double shfl_down(double v, int delta) {
+    const int w = threadIdx.x / 32, l = threadIdx.x % 32;
+    g_shfl[w][l] = v;
+    (*g_wbar)[w].wait();
+    const double r = (l + delta < 32) ? g_shfl[w][l + delta] : v;
+    (*g_wbar)[w].wait();
+    return r;
+}
+}  // namespace emu
 inline void __syncthreads() { emu::g_bar->wait(); }
 inline void __syncwarp() { (*emu::g_wbar)[threadIdx.x / 32].wait(); }
 #define EXTERN_SHARED(name) unsigned char* name = emu::g_smem

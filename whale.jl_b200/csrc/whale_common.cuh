@@ -31,28 +31,43 @@ struct NodeRec {
                         //   (within-branch duplication :178-185, Πwgdretention :187-194, Πroot :151-158)
     uint32_t dent_off;  // 16-byte-entry offset of those terms
     uint32_t ndent;
-    uint32_t tptr_off;  // u32-word offset (multiple of 4) of [tptr[C+1] | lossF[C] | lossG[C] | lev[nlev+1]]
-                        //   speciation terms at row 1 (:160-170), Πloss child indices (:172-176), root levels
+    uint32_t tptr_off;  // u32-word offset (multiple of 4) of [tptr[C+1] | lossF[C] | lossG[C] | lev[nlev+1]] pad4
+                        //   | cmp[C]: speciation terms at row 1 (:160-170), Πloss child indices (:172-176),
+                        //   root levels, local cell -> clade id
     uint32_t tent_off;
     uint32_t ntent;
+    uint32_t slot_off;  // u32-word offset (multiple of 4) of the slice-loop lane table (Slot[nslots])
+    uint32_t nslots;
+    uint32_t pad0, pad1;
 };
-static_assert(sizeof(NodeRec) == 32, "NodeRec must be 32 bytes");
+static_assert(sizeof(NodeRec) == 48, "NodeRec must be 48 bytes");
+
+// Slice-loop work descriptor of one lane (built by the packer; src/core.jl:178-185 balanced over lanes):
+// a clade cell with E same-branch terms is owned by a team of G = 2^glog adjacent lanes (G = 1 for E <= 2);
+// lane j of the team sums terms first, first+G, ... (cnt of them), the team leader (slot index multiple of G)
+// gets the total through a shuffle reduction and writes the cell.
+struct Slot {
+    uint16_t cell;    // local cell index, 0xFFFF = idle lane
+    uint8_t glog;
+    uint8_t cnt;
+    uint16_t first;   // index into the node's term list
+    uint16_t stride;  // = G
+};
+static_assert(sizeof(Slot) == 8, "Slot must be 8 bytes");
 
 struct FamHdr {
-    uint64_t base;         // byte offset of the blob in the arena (16-byte aligned)
-    uint64_t ell_off;      // offset (doubles) of this family's ℓ in the keep_ell buffer
-    uint32_t G;            // clades
-    uint32_t nlev;         // root levels (distinct clade sizes)
+    uint64_t base;           // byte offset of the blob in the arena (16-byte aligned)
+    uint64_t ell_off;        // offset (doubles) of this family's ℓ in the keep_ell buffer
+    uint32_t G;              // clades
+    uint32_t nlev;           // root levels (distinct clade sizes)
     // shared-memory budget (doubles unless stated), per tangent plan where it depends on K_e
-    uint32_t rows_len[2];   // Σ_e C_e K_e (even)
-    uint32_t scr_len[2];    // scratch row: max over internal/WGD nodes of C_e K_e (even)
-    uint32_t prod_len[2];   // P1 product window: max over internal/WGD nodes of max(ndent, ntent)·K_e (even)
-    uint32_t leafmax[2];    // per-warp scratch row: max over leaf branches of C_e K_e (even)
-    uint32_t leaf_prod[2];  // per-warp product window: max over leaf branches of ndent·K_e (even)
-    uint32_t stage_bytes;   // staging buffer for one internal node's lists (bytes, multiple of 16)
-    uint32_t leaf_stage;    // per-warp staging buffer for one leaf branch's lists (bytes, multiple of 16)
+    uint32_t rows_len[2];    // Σ_e C_e K_e (even)
+    uint32_t scr_len[2];     // scratch row: max over internal/WGD nodes of C_e K_e (even)
+    uint32_t prod_len[2];    // P1 product window (row 1 / root / K > 8 slices), even
+    uint32_t leafmax[2];     // per-warp scratch row: max over leaf branches of C_e K_e (even)
+    uint32_t stage_bytes[2]; // staging buffer for one internal node's lists + ϕ/ψ rows (bytes, multiple of 16)
+    uint32_t leaf_stage;     // per-warp staging buffer for one leaf branch's lists (bytes, multiple of 16)
     uint32_t blob_bytes;
-    uint32_t pad;
 };
 
 struct ModelDev {  // structure arrays (device pointers), node index = id-1

@@ -139,6 +139,131 @@ __device__ __forceinline__ void run_slices(int n, int C, int K, double* fin, dou
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fused slice loop for K <= 8 components (the common case: constant rates, or few branch-wise parameters).
+// Each lane owns one Slot of the packer's lane table for the whole branch and keeps its (up to two) terms in
+// registers, so a slice is: gather 2·K operands per term from the previous row, K fused multiply-adds per
+// term, a shuffle reduction inside teams that share a heavy clade, the ϕ/ψ update, one barrier.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int KMAX_FUSED = 8;
+
+#ifdef WHALE_EMU
+#define SHFL_DOWN(v, d) emu::shfl_down(v, d)
+#else
+#define SHFL_DOWN(v, d) __shfl_down_sync(0xffffffffu, v, d)
+#endif
+
+template <int K>
+struct LaneWork {
+    int cell, cnt, gsz, first;
+    int a1, a2, b1, b2;  // row offsets (elements) of the operands of the lane's first two terms
+    double pa, pb;
+};
+
+template <int K>
+__device__ __forceinline__ LaneWork<K> load_work(const Slot* s_slots, int nslots, const Ent* s_dents, int sidx) {
+    LaneWork<K> w;
+    w.cell = -1; w.cnt = 0; w.gsz = 1; w.first = 0;
+    w.a1 = w.a2 = w.b1 = w.b2 = 0;
+    w.pa = w.pb = 0.0;
+    if (sidx < nslots) {
+        const Slot sl = s_slots[sidx];
+        w.cell = sl.cell == 0xFFFFu ? -1 : (int)sl.cell;
+        w.cnt = sl.cnt; w.gsz = 1 << sl.glog; w.first = sl.first;
+        if (w.cnt > 0) { const Ent en = s_dents[w.first]; w.a1 = en.i1 * K; w.a2 = en.i2 * K; w.pa = en.p; }
+        if (w.cnt > 1) { const Ent en = s_dents[w.first + w.gsz]; w.b1 = en.i1 * K; w.b2 = en.i2 * K; w.pb = en.p; }
+    }
+    return w;
+}
+
+template <int K>
+__device__ __forceinline__ void accum(const double* __restrict__ src, int o1, int o2, double p, double (&s)[K]) {
+    const double* x = src + o1;
+    const double* y = src + o2;
+    const double px = p * x[0], py = p * y[0];
+    s[0] = fma(px, y[0], s[0]);
+#pragma unroll
+    for (int k = 1; k < K; k++) s[k] = fma(px, y[k], fma(py, x[k], s[k]));
+}
+
+// one pass of one slice for this lane; wg = team size of the warp's first lane (warp-uniform, 0: nothing to do)
+template <int K>
+__device__ __forceinline__ void slice_pass(const LaneWork<K>& w, int wg, int sidx, const double* __restrict__ src,
+                                           double* __restrict__ dst, const double2* ppi, const Ent* s_dents, int C,
+                                           int i, double* ellp) {
+    if (wg == 0) return;
+    double s[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) s[k] = 0.0;
+    if (w.cnt > 0) accum<K>(src, w.a1, w.a2, w.pa, s);
+    if (w.cnt > 1) accum<K>(src, w.b1, w.b2, w.pb, s);
+    for (int j = 2; j < w.cnt; j++) {
+        const Ent en = s_dents[w.first + j * w.gsz];
+        accum<K>(src, en.i1 * K, en.i2 * K, en.p, s);
+    }
+    for (int step = 1; step < wg; step <<= 1) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const double t = SHFL_DOWN(s[k], step);
+            if (step < w.gsz) s[k] += t;
+        }
+    }
+    if (w.cell >= 0 && (sidx & (w.gsz - 1)) == 0) {  // team leader: ℓ_i = ϕ_i ℓ_{i−1} + ψ_i Σ  (with tangents)
+        const int c = w.cell;
+        const double2 c0 = ppi[0];
+        const double o0 = src[c * K];
+        const double r0 = fma(c0.x, o0, c0.y * s[0]);
+        dst[c * K] = r0;
+        if (ellp) ellp[(size_t)i * C + c] = r0;
+#pragma unroll
+        for (int k = 1; k < K; k++) {
+            const double2 ck = ppi[k];
+            dst[c * K + k] = fma(c0.x, src[c * K + k], fma(c0.y, s[k], fma(ck.x, o0, ck.y * s[0])));
+        }
+    }
+}
+
+template <int K, bool WARP>
+__device__ __forceinline__ void run_slices_fused(int n, int C, double* fin, double* scr, double* cur,
+                                                 const Slot* s_slots, int nslots, const Ent* s_dents,
+                                                 const double2* pprow, double* ellp, int tid, int nt) {
+    // the first two passes keep their descriptors in registers
+    const int wbase = tid & ~31;
+    const LaneWork<K> w0 = load_work<K>(s_slots, nslots, s_dents, tid);
+    const LaneWork<K> w1 = load_work<K>(s_slots, nslots, s_dents, tid + nt);
+    // slots are sorted by team size (descending): the warp's first lane carries the warp's largest team
+    const int wg0 = wbase < nslots ? (1 << s_slots[wbase].glog) : 0;
+    const int wg1 = (wbase + nt) < nslots ? (1 << s_slots[wbase + nt].glog) : 0;
+    const int npass = (nslots + nt - 1) / nt;
+    for (int i = 1; i <= n; i++) {
+        const double* src = cur;
+        double* dst = (cur == fin) ? scr : fin;
+        const double2* ppi = pprow + (size_t)i * K;
+        slice_pass<K>(w0, wg0, tid, src, dst, ppi, s_dents, C, i, ellp);
+        slice_pass<K>(w1, wg1, tid + nt, src, dst, ppi, s_dents, C, i, ellp);
+        for (int q = 2; q < npass; q++) {  // oversized rows: descriptors reloaded from shared memory
+            const LaneWork<K> wq = load_work<K>(s_slots, nslots, s_dents, tid + q * nt);
+            const int wgq = (wbase + q * nt) < nslots ? (1 << s_slots[wbase + q * nt].glog) : 0;
+            slice_pass<K>(wq, wgq, tid + q * nt, src, dst, ppi, s_dents, C, i, ellp);
+        }
+        cur = dst;
+        scope_sync<WARP>();
+    }
+}
+
+// dispatch on the branch's component count
+template <bool WARP>
+__device__ __forceinline__ bool run_slices_fused_k(int K, int n, int C, double* fin, double* scr, double* cur,
+                                                   const Slot* s_slots, int nslots, const Ent* s_dents,
+                                                   const double2* pprow, double* ellp, int tid, int nt) {
+    switch (K) {
+#define CASEK(KK) case KK: run_slices_fused<KK, WARP>(n, C, fin, scr, cur, s_slots, nslots, s_dents, pprow, ellp, tid, nt); return true;
+        CASEK(1) CASEK(2) CASEK(3) CASEK(4) CASEK(5) CASEK(6) CASEK(7) CASEK(8)
+#undef CASEK
+        default: return false;
+    }
+}
+
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
     EXTERN_SHARED(smem_raw);
@@ -152,8 +277,8 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
     const uint64_t base = Hp->base;
     const uint32_t nlev = Hp->nlev, blob_bytes = Hp->blob_bytes;
     const uint32_t rows_len = Hp->rows_len[A.plan], scr_len = Hp->scr_len[A.plan], prod_len = Hp->prod_len[A.plan];
-    const uint32_t leafmax = Hp->leafmax[A.plan], leaf_prod = Hp->leaf_prod[A.plan];
-    const uint32_t stage_bytes = Hp->stage_bytes, leaf_stage = Hp->leaf_stage;
+    const uint32_t leafmax = Hp->leafmax[A.plan];
+    const uint32_t stage_bytes = Hp->stage_bytes[A.plan], leaf_stage = Hp->leaf_stage;
     const unsigned char* blob = A.arena + base;
     const NodeRec* nrec = reinterpret_cast<const NodeRec*>(blob);
     const uint32_t* words = reinterpret_cast<const uint32_t*>(blob);
@@ -162,22 +287,34 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
     // pull the whole blob towards L2 now; it is consumed node by node below
     for (uint32_t o = tid * 128u; o < blob_bytes; o += NT * 128u) PREFETCH_L2(blob + o);
 
-    // ---- shared memory carve-up ----
-    int* s_roff = reinterpret_cast<int*>(smem_raw);                      // [nn+1] row offsets (doubles)
+    // ---- shared memory carve-up (mirrored by smem_need() on the host) ----
+    // species-tree metadata (one coalesced read instead of dependent global loads at every node)
+    int* s_kind = reinterpret_cast<int*>(smem_raw);
+    int* s_nsl = s_kind + nn;
+    int* s_ch0 = s_nsl + nn;
+    int* s_ch1 = s_ch0 + nn;
+    int* s_K = s_ch1 + nn;
+    int* s_toff = s_K + nn;
+    int* s_roff = s_toff + nn;                                           // [nn+1] row offsets (doubles)
     int16_t* s_cmap = reinterpret_cast<int16_t*>(s_roff + nn + 1);       // [nn*2*Kmax]
-    const size_t hdr_bytes = (((nn + 1) * sizeof(int) + (size_t)nn * 2 * Kmax * sizeof(int16_t)) + 15) & ~size_t(15);
+    const size_t hdr_bytes = (((7 * nn + 1) * sizeof(int) + (size_t)nn * 2 * Kmax * sizeof(int16_t)) + 15) & ~size_t(15);
     double* rows = reinterpret_cast<double*>(smem_raw + hdr_bytes);
     double* scr = rows + rows_len;
     double* prod = scr + scr_len;
     unsigned char* stage = reinterpret_cast<unsigned char*>(prod + prod_len);
     unsigned char* leaf_area = stage + stage_bytes;
-    const size_t leaf_area_bytes = (size_t)(leafmax + leaf_prod) * sizeof(double) + leaf_stage;
+    const size_t leaf_area_bytes = (size_t)leafmax * sizeof(double) + leaf_stage;
+    for (int i = tid; i < nn; i += NT) {
+        s_kind[i] = M.kind[i]; s_nsl[i] = M.nsl[i]; s_ch0[i] = M.child0[i]; s_ch1[i] = M.child1[i];
+        s_K[i] = PL.K[i]; s_toff[i] = PL.toff[i];
+    }
     for (int i = tid; i < nn * 2 * Kmax; i += NT) s_cmap[i] = PL.cmap[i];
+    __syncthreads();
     if (tid == 0) {
         int o = 0;
         for (int e = 0; e < nn; e++) {
             s_roff[e] = o;
-            o += (int)nrec[e].C * PL.K[e];
+            o += (int)nrec[e].C * s_K[e];
         }
         s_roff[nn] = o;
     }
@@ -186,7 +323,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
     auto ell_of = [&](int e) -> double* {  // node e's matrix inside the family's ℓ (node-index order)
         if (!ell_base) return nullptr;
         size_t o = 0;
-        for (int e2 = 0; e2 < e; e2++) o += (size_t)(M.nsl[e2] + 1) * nrec[e2].C;
+        for (int e2 = 0; e2 < e; e2++) o += (size_t)(s_nsl[e2] + 1) * nrec[e2].C;
         return ell_base + o;
     };
 
@@ -196,7 +333,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         const NodeRec R = nrec[e];
         const int C = (int)R.C;
         if (C == 0) continue;
-        const int K = PL.K[e], n = M.nsl[e];
+        const int K = s_K[e], n = s_nsl[e];
         double* fin = rows + s_roff[e];
         if (R.nonleaf == 0 && A.skip_leaf) {  // family-independent: ℓ_n = leafℙ·Πϕ_i from k_tables
             for (int i = lane; i < C * K; i += 32) fin[i] = PL.leaf[e * Kmax + (i % K)];
@@ -204,11 +341,10 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         }
         double* ellp = ell_of(e);
         double* wscr = reinterpret_cast<double*>(leaf_area + warp * leaf_area_bytes);
-        double* wprod = wscr + leafmax;
-        uint4* wst = reinterpret_cast<uint4*>(wprod + leaf_prod);
-        const int nd16 = (int)R.ndent, dp16 = (C + 1 + 3) >> 2;
+        uint4* wst = reinterpret_cast<uint4*>(wscr + leafmax);
+        const int nd16 = (int)R.ndent, sl16 = ((int)R.nslots + 1) >> 1;
         copy16(wst, reinterpret_cast<const uint4*>(ents + R.dent_off), nd16, lane, 32);
-        copy16(wst + nd16, reinterpret_cast<const uint4*>(words + R.dptr_off), dp16, lane, 32);
+        copy16(wst + nd16, reinterpret_cast<const uint4*>(words + R.slot_off), sl16, lane, 32);
         double* cur = (n & 1) ? wscr : fin;  // row i lives in fin iff (n − i) is even
         const int nleafc = C - (int)R.nonleaf;
         for (int i = lane; i < C * K; i += 32) {
@@ -218,9 +354,8 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
             if (ellp && k == 0) ellp[c] = v;
         }
         __syncwarp();
-        run_slices<true>(n, C, K, fin, wscr, cur, reinterpret_cast<const Ent*>(wst),
-                         reinterpret_cast<const uint32_t*>(wst + nd16), R.ndent, PL.pp + PL.toff[e], wprod,
-                         K > 0 ? (int)(leaf_prod / K) : 0, ellp, lane, 32);
+        run_slices_fused_k<true>(K, n, C, fin, wscr, cur, reinterpret_cast<const Slot*>(wst + nd16), (int)R.nslots,
+                                 reinterpret_cast<const Ent*>(wst), PL.pp + s_toff[e], ellp, lane, 32);
     }
     __syncthreads();
 
@@ -230,34 +365,46 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         const NodeRec R = nrec[e];
         const int C = (int)R.C;
         if (C == 0) continue;
-        const int kind = M.kind[e], K = PL.K[e], n = M.nsl[e];
+        const int kind = s_kind[e], K = s_K[e], n = s_nsl[e];
         double* fin = rows + s_roff[e];
         double* ellp = ell_of(e);
         const int cap = (int)(prod_len / K);
+        const bool fused = K <= KMAX_FUSED;
         // lane -> (cell group, component) for the P2 passes of row 1
         const int GP = NT / K;
         const int grp = tid / K, k = tid - grp * K;
         const bool on = grp < GP;
         const double m = k == 0 ? 0.0 : 1.0;
 
-        // ---- stage this node's lists: [dents | dptr | tptr,lossF,lossG,lev] ----
+        // ---- stage this node's lists: [dents | slots | dptr | tptr,lossF,lossG,lev | ϕψ rows] ----
         const int nd16 = (kind == WHALE_ROOT) ? 0 : (int)R.ndent;  // Πroot terms are read once: stay global
+        const int sl16 = (kind == WHALE_ROOT) ? 0 : (((int)R.nslots + 1) >> 1);
         const int dp16 = (C + 1 + 3) >> 2;
         const int tp16 = (kind == WHALE_WGD) ? 0 : ((3 * C + 1 + (kind == WHALE_ROOT ? (int)nlev + 1 : 0) + 3) >> 2);
+        const int pp16 = fused ? (n + 1) * K : 0;
         uint4* st4 = reinterpret_cast<uint4*>(stage);
         copy16(st4, reinterpret_cast<const uint4*>(ents + R.dent_off), nd16, tid, NT);
-        copy16(st4 + nd16, reinterpret_cast<const uint4*>(words + R.dptr_off), dp16, tid, NT);
-        copy16(st4 + nd16 + dp16, reinterpret_cast<const uint4*>(words + R.tptr_off), tp16, tid, NT);
+        copy16(st4 + nd16, reinterpret_cast<const uint4*>(words + R.slot_off), sl16, tid, NT);
+        copy16(st4 + nd16 + sl16, reinterpret_cast<const uint4*>(words + R.dptr_off), dp16, tid, NT);
+        copy16(st4 + nd16 + sl16 + dp16, reinterpret_cast<const uint4*>(words + R.tptr_off), tp16, tid, NT);
+        copy16(st4 + nd16 + sl16 + dp16 + tp16, reinterpret_cast<const uint4*>(PL.pp + s_toff[e]), pp16, tid, NT);
         const Ent* s_dents = reinterpret_cast<const Ent*>(stage);
-        const uint32_t* s_dptr = reinterpret_cast<const uint32_t*>(st4 + nd16);
-        const uint32_t* s_tptr = reinterpret_cast<const uint32_t*>(st4 + nd16 + dp16);
+        const Slot* s_slots = reinterpret_cast<const Slot*>(st4 + nd16);
+        const uint32_t* s_dptr = reinterpret_cast<const uint32_t*>(st4 + nd16 + sl16);
+        const uint32_t* s_tptr = reinterpret_cast<const uint32_t*>(st4 + nd16 + sl16 + dp16);
         const int32_t* s_lossF = reinterpret_cast<const int32_t*>(s_tptr + C + 1);
         const int32_t* s_lossG = s_lossF + C;
         const uint32_t* s_lev = reinterpret_cast<const uint32_t*>(s_lossG + C);
+        const double2* s_pp = reinterpret_cast<const double2*>(st4 + nd16 + sl16 + dp16 + tp16);
+        auto slices = [&](double* cur) {
+            if (!run_slices_fused_k<false>(K, n, C, fin, scr, cur, s_slots, (int)R.nslots, s_dents, s_pp, ellp, tid, NT))
+                run_slices<false>(n, C, K, fin, scr, cur, s_dents, s_dptr, R.ndent, PL.pp + s_toff[e], prod, cap, ellp,
+                                  tid, NT);
+        };
 
         // children, shared by the row-1 formulas
-        const int f = M.child0[e], g = M.child1[e];
-        const int KF = PL.K[f];
+        const int f = s_ch0[e], g = s_ch1[e];
+        const int KF = s_K[f];
         const double* finF = rows + s_roff[f];
         const int16_t* mapF = s_cmap + (e * 2 + 0) * Kmax;
         const int16_t* mapG = s_cmap + (e * 2 + 1) * Kmax;
@@ -282,17 +429,16 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
                     if (ellp && k == 0) ellp[c] = r;
                 }
             __syncthreads();
-            run_slices<false>(n, C, K, fin, scr, cur, s_dents, s_dptr, R.ndent, PL.pp + PL.toff[e], prod, cap, ellp,
-                              tid, NT);
+            slices(cur);
             continue;
         }
 
         // internal node or root: speciation + loss from the children's last rows (src/core.jl:160-176)
-        const int KG = PL.K[g];
+        const int KG = s_K[g];
         const double* finG = rows + s_roff[g];
         const int kg = mapG[k];
-        const double* epsF = PL.eps + PL.toff[f] + (size_t)M.nsl[f] * KF;
-        const double* epsG = PL.eps + PL.toff[g] + (size_t)M.nsl[g] * KG;
+        const double* epsF = PL.eps + s_toff[f] + (size_t)s_nsl[f] * KF;
+        const double* epsG = PL.eps + s_toff[g] + (size_t)s_nsl[g] * KG;
         const double ef0 = epsF[0], eg0 = epsG[0];
         const double efk = (k > 0 && kf >= 0) ? epsF[kf] : 0.0;
         const double egk = (k > 0 && kg >= 0) ? epsG[kg] : 0.0;
@@ -340,8 +486,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
                 __syncthreads();
                 cA = cB;
             }
-            run_slices<false>(n, C, K, fin, scr, cur, s_dents, s_dptr, R.ndent, PL.pp + PL.toff[e], prod, cap, ellp,
-                              tid, NT);
+            slices(cur);
             continue;
         }
 

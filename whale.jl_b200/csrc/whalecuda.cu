@@ -99,15 +99,27 @@ struct whale_model {
     cudaStream_t stream = nullptr;
 };
 
-// threads per family CTA: 128 (7 CTAs/SM by registers) or 256 (4 CTAs/SM); WHALE_NT overrides for experiments
+// k_dp launch shape: threads per family CTA and the resident-CTA target that caps registers.
+// Defaults chosen from B200 measurements; WHALE_NT / WHALE_MINB override for experiments.
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
 static int dp_nt() {
-    static int nt = [] {
-        const char* s = getenv("WHALE_NT");
-        int v = s ? atoi(s) : 128;
-        return v == 256 ? 256 : 128;
-    }();
+    static int nt = [] { int v = env_int("WHALE_NT", 128); return (v == 64 || v == 256) ? v : 128; }();
     return nt;
 }
+static int dp_minb() {
+    static int mb = [] {
+        const int nt = dp_nt();
+        int v = env_int("WHALE_MINB", nt == 64 ? 12 : nt == 128 ? 6 : 3);
+        if (nt == 64) return 12;
+        if (nt == 128) return v <= 5 ? 5 : v == 6 ? 6 : 7;
+        return 3;
+    }();
+    return mb;
+}
+#define DP_VARIANTS(X) X(64, 12) X(128, 5) X(128, 6) X(128, 7) X(256, 3)
 constexpr int MAX_BINS = 8;
 struct Bin {
     int off, count;
@@ -350,9 +362,9 @@ static inline void pad4(std::vector<uint32_t>& w) { while (w.size() & 3) w.push_
 
 static size_t smem_need(const whale_model* m, const FamHdr& h, int plan) {  // mirrors the carve-up in k_dp
     const size_t nn = m->nn, Kmax = m->plan[plan].Kmax, NW = dp_nt() / 32;
-    const size_t hdr = (((nn + 1) * sizeof(int) + nn * 2 * Kmax * sizeof(int16_t)) + 15) & ~size_t(15);
-    return hdr + ((size_t)h.rows_len[plan] + h.scr_len[plan] + h.prod_len[plan]) * sizeof(double) + h.stage_bytes +
-           NW * (((size_t)h.leafmax[plan] + h.leaf_prod[plan]) * sizeof(double) + h.leaf_stage);
+    const size_t hdr = (((7 * nn + 1) * sizeof(int) + nn * 2 * Kmax * sizeof(int16_t)) + 15) & ~size_t(15);
+    return hdr + ((size_t)h.rows_len[plan] + h.scr_len[plan] + h.prod_len[plan]) * sizeof(double) +
+           h.stage_bytes[plan] + NW * ((size_t)h.leafmax[plan] * sizeof(double) + h.leaf_stage);
 }
 
 int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t* out) {
@@ -404,7 +416,8 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
         std::vector<uint32_t> wordsv;   // pointer / loss / level words; every array starts on a 16-byte boundary
         std::vector<Ent> entsv;         // term entries
         uint32_t sumC = 0, nlev = 0;
-        size_t stage_bytes = 0, leaf_stage = 0;
+        size_t leaf_stage = 0;
+        std::vector<size_t> stage16(nn, 0);  // 16-byte words staged per node, excluding the ϕ/ψ rows
         double wk = 0.0;
         for (int e = 0; e < nn; e++) {
             NodeRec& R = recs[e];
@@ -447,6 +460,38 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
                 R.ndent = (uint32_t)entsv.size() - R.dent_off;
                 wk += (double)R.ndent * (m->nsl[e] + 1) + (double)C * (m->nsl[e] + 1);
             }
+            // (1b) the slice loop's lane table: teams of 2^glog lanes per clade, at most ~2 terms per lane,
+            //      largest teams first (keeps teams aligned and makes the team size warp-uniform-monotone)
+            pad4(wordsv);
+            R.slot_off = (uint32_t)wordsv.size();
+            if (kind != WHALE_ROOT && m->nsl[e] > 0) {
+                if (R.ndent > 65535) { delete D; return fail(WHALE_ERR_CAPACITY, "family %d node %d: %u same-branch terms (> 65535)", f, e, R.ndent); }
+                const uint32_t* dp = wordsv.data() + R.dptr_off;
+                std::vector<std::pair<int, int>> order;  // (-glog, cell)
+                std::vector<int> glogs(C);
+                for (int j = 0; j < C; j++) {
+                    const uint32_t E = dp[j + 1] - dp[j];
+                    int gl = 0;
+                    while (gl < 5 && (2u << gl) < E) gl++;  // team size G = 2^gl >= ceil(E/2), capped at 32
+                    glogs[j] = gl;
+                    order.push_back({-gl, j});
+                }
+                std::stable_sort(order.begin(), order.end());
+                std::vector<Slot> slots;
+                for (auto& oc : order) {
+                    const int j = oc.second, gl = glogs[j], G = 1 << gl;
+                    const uint32_t E = dp[j + 1] - dp[j], first = dp[j];
+                    for (int l = 0; l < G; l++) {
+                        const uint32_t cnt = (uint32_t)l < E ? (E - l + G - 1) / G : 0;
+                        if (cnt > 255) { delete D; return fail(WHALE_ERR_CAPACITY, "family %d node %d: clade with %u terms", f, e, E); }
+                        slots.push_back(Slot{(uint16_t)j, (uint8_t)gl, (uint8_t)cnt, (uint16_t)(first + l), (uint16_t)G});
+                    }
+                }
+                R.nslots = (uint32_t)slots.size();
+                const size_t w0 = wordsv.size();
+                wordsv.resize(w0 + 2 * slots.size());
+                if (!slots.empty()) memcpy(wordsv.data() + w0, slots.data(), slots.size() * sizeof(Slot));
+            }
             // (2) speciation terms at row 1 (src/core.jl:160-170), Πloss child indices (:172-176), root levels
             pad4(wordsv);
             R.tptr_off = (uint32_t)wordsv.size();
@@ -483,12 +528,13 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
             pad4(wordsv);
             for (int j = 0; j < C; j++) wordsv.push_back((uint32_t)d->compat[coff[e] + j]);
             if (kind == WHALE_LEAF) {
-                leaf_stage = std::max(leaf_stage, 16 * ((size_t)R.ndent + ((size_t)C + 1 + 3) / 4));
+                leaf_stage = std::max(leaf_stage, 16 * ((size_t)R.ndent + ((size_t)R.nslots + 1) / 2));
             } else {  // what k_dp stages in shared memory for this node
                 size_t nd16 = kind == WHALE_ROOT ? 0 : R.ndent;
+                size_t sl16 = kind == WHALE_ROOT ? 0 : ((size_t)R.nslots + 1) / 2;
                 size_t dp16 = ((size_t)C + 1 + 3) / 4;
                 size_t tp16 = kind == WHALE_WGD ? 0 : (3 * (size_t)C + 1 + (kind == WHALE_ROOT ? nlev + 1 : 0) + 3) / 4;
-                stage_bytes = std::max(stage_bytes, 16 * (nd16 + dp16 + tp16));
+                stage16[e] = nd16 + sl16 + dp16 + tp16;
             }
             ell_total += (uint64_t)(m->nsl[e] + 1) * C;
         }
@@ -504,6 +550,7 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
             NodeRec& R = recs[e];
             R.dptr_off += (uint32_t)(words_at / 4);
             R.tptr_off += (uint32_t)(words_at / 4);
+            R.slot_off += (uint32_t)(words_at / 4);
             R.dent_off += (uint32_t)(ents_at / 16);
             R.tent_off += (uint32_t)(ents_at / 16);
         }
@@ -513,7 +560,6 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
         H.base = base;
         H.G = G;
         H.nlev = nlev;
-        H.stage_bytes = (uint32_t)stage_bytes;
         H.leaf_stage = (uint32_t)leaf_stage;
         H.blob_bytes = (uint32_t)total;
         work[f] = wk;
@@ -521,13 +567,15 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
         algo_bytes += 12 * (soff[G] - soff[0]) + 2 * (int64_t)G + 4 * (int64_t)sumC;
         for (int g = 0; g < 2; g++) {  // shared-memory budget per tangent plan
             const Plan& pl = m->plan[g];
-            uint32_t rows = 0, mxinner = 0, mxleaf = 0, prod = 0, lprod = 0;
+            uint32_t rows = 0, mxinner = 0, mxleaf = 0, prod = 0;
+            size_t stg = 0;
             for (int e = 0; e < nn; e++) {
                 const uint32_t K = (uint32_t)pl.K[e], ck = Cs[e] * K;
                 rows += ck;
+                if (m->kind[e] != WHALE_LEAF)  // lists + the ϕ/ψ rows of the fused slice loop (K <= 8)
+                    stg = std::max(stg, stage16[e] + (K <= 8 ? (size_t)(m->nsl[e] + 1) * K : 0));
                 if (m->kind[e] == WHALE_LEAF) {
                     mxleaf = std::max(mxleaf, ck);
-                    lprod = std::max(lprod, recs[e].ndent * K);
                 } else if (m->kind[e] != WHALE_ROOT) {
                     mxinner = std::max(mxinner, ck);
                     prod = std::max(prod, std::max(recs[e].ndent, recs[e].ntent) * K);
@@ -540,7 +588,7 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
             H.scr_len[g] = even(mxinner);
             H.prod_len[g] = even(prod);
             H.leafmax[g] = even(mxleaf);
-            H.leaf_prod[g] = even(lprod);
+            H.stage_bytes[g] = (uint32_t)(16 * stg);
         }
     }
     D->ell_total = ell_total;
@@ -634,14 +682,17 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
     if (bins[0].smem > 227 * 1024) return fail(WHALE_ERR_CAPACITY, "a family needs %zu bytes of shared memory (> 227 KB)", bins[0].smem);
     static thread_local bool attr_set = false;
     if (!attr_set) {
-        CU(cudaFuncSetAttribute(k_dp<128, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CU(cudaFuncSetAttribute(k_dp<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define SETATTR(NTV, MB) CU(cudaFuncSetAttribute(k_dp<NTV, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DP_VARIANTS(SETATTR)
+#undef SETATTR
         attr_set = true;
     }
     DPArgs a{m->dev, pl.dev, D->d_arena, D->d_hdr, D->d_perm[g], D->d_out_fam, keep ? D->d_ell : nullptr, g, keep ? 0 : 1};
+    const int MB = dp_minb();
     auto launch_bin = [&](const Bin& b, cudaStream_t s) {
-        if (NT == 256) LAUNCH((k_dp<256, 4>), b.count, 256, b.smem, s, a, b.off);
-        else LAUNCH((k_dp<128, 7>), b.count, 128, b.smem, s, a, b.off);
+#define LAUNCHV(NTV, MBV) if (NT == NTV && MB == MBV) LAUNCH((k_dp<NTV, MBV>), b.count, NTV, b.smem, s, a, b.off);
+        DP_VARIANTS(LAUNCHV)
+#undef LAUNCHV
         g_launches++;
     };
     if (bins.size() == 1) {
