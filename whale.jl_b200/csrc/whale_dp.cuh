@@ -28,7 +28,14 @@ struct DPArgs {
     double* ell;       // keep_ell buffer or nullptr
     int plan;          // 0 value only, 1 with tangents
     int skip_leaf;     // share family-independent leaf-branch rows (off in keep_ell mode)
+    long long* tim;    // optional per-family phase cycle counters [F][8] (profiling aid) or nullptr
 };
+
+#ifdef WHALE_EMU
+#define CLOCK64() 0LL
+#else
+#define CLOCK64() clock64()
+#endif
 
 #ifdef WHALE_EMU
 #define PREFETCH_L2(p) ((void)0)
@@ -235,10 +242,26 @@ __device__ __forceinline__ void run_slices_fused(int n, int C, double* fin, doub
     const int wg0 = wbase < nslots ? (1 << s_slots[wbase].glog) : 0;
     const int wg1 = (wbase + nt) < nslots ? (1 << s_slots[wbase + nt].glog) : 0;
     const int npass = (nslots + nt - 1) / nt;
+    // warp scope: ϕ/ψ rows come from global memory -> keep the current row in registers and fetch the next
+    // one while the slice is computed; block scope: rows were staged in shared memory
+    double2 pc[K], pn[K];
+    if (WARP) {
+#pragma unroll
+        for (int k = 0; k < K; k++) pn[k] = n >= 1 ? __ldg(pprow + K + k) : make_double2(0.0, 0.0);
+    }
     for (int i = 1; i <= n; i++) {
         const double* src = cur;
         double* dst = (cur == fin) ? scr : fin;
         const double2* ppi = pprow + (size_t)i * K;
+        if (WARP) {
+#pragma unroll
+            for (int k = 0; k < K; k++) pc[k] = pn[k];
+            if (i < n) {
+#pragma unroll
+                for (int k = 0; k < K; k++) pn[k] = __ldg(pprow + (size_t)(i + 1) * K + k);
+            }
+            ppi = pc;
+        }
         slice_pass<K>(w0, wg0, tid, src, dst, ppi, s_dents, C, i, ellp);
         slice_pass<K>(w1, wg1, tid + nt, src, dst, ppi, s_dents, C, i, ellp);
         for (int q = 2; q < npass; q++) {  // oversized rows: descriptors reloaded from shared memory
@@ -251,17 +274,24 @@ __device__ __forceinline__ void run_slices_fused(int n, int C, double* fin, doub
     }
 }
 
-// dispatch on the branch's component count
+// dispatch on the branch's component count (leaf branches carry at most value + own λ, μ: K <= 3)
 template <bool WARP>
 __device__ __forceinline__ bool run_slices_fused_k(int K, int n, int C, double* fin, double* scr, double* cur,
                                                    const Slot* s_slots, int nslots, const Ent* s_dents,
                                                    const double2* pprow, double* ellp, int tid, int nt) {
-    switch (K) {
 #define CASEK(KK) case KK: run_slices_fused<KK, WARP>(n, C, fin, scr, cur, s_slots, nslots, s_dents, pprow, ellp, tid, nt); return true;
-        CASEK(1) CASEK(2) CASEK(3) CASEK(4) CASEK(5) CASEK(6) CASEK(7) CASEK(8)
-#undef CASEK
-        default: return false;
+    if (WARP) {
+        switch (K) {
+            CASEK(1) CASEK(2) CASEK(3)
+            default: return false;
+        }
+    } else {
+        switch (K) {
+            CASEK(1) CASEK(2) CASEK(3) CASEK(4) CASEK(5) CASEK(6) CASEK(7) CASEK(8)
+            default: return false;
+        }
     }
+#undef CASEK
 }
 
 template <int NT, int MINB>
@@ -284,6 +314,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
     const uint32_t* words = reinterpret_cast<const uint32_t*>(blob);
     const Ent* ents = reinterpret_cast<const Ent*>(blob);
 
+    long long tc0 = CLOCK64(), tc1 = 0, acc_row1 = 0, acc_slices = 0, acc_stage = 0;
     // pull the whole blob towards L2 now; it is consumed node by node below
     for (uint32_t o = tid * 128u; o < blob_bytes; o += NT * 128u) PREFETCH_L2(blob + o);
 
@@ -327,6 +358,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         return ell_base + o;
     };
 
+    const long long tcA = CLOCK64();
     // ================= phase A: leaf branches, one warp each (src/core.jl:83-101,121-128) =================
     for (int li = warp; li < M.nleafnodes; li += NW) {
         const int e = M.leafnodes[li];
@@ -335,6 +367,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         if (C == 0) continue;
         const int K = s_K[e], n = s_nsl[e];
         double* fin = rows + s_roff[e];
+        if (R.nslots > 32 && !(R.nonleaf == 0 && A.skip_leaf)) continue;  // heavy branch: whole CTA, below
         if (R.nonleaf == 0 && A.skip_leaf) {  // family-independent: ℓ_n = leafℙ·Πϕ_i from k_tables
             for (int i = lane; i < C * K; i += 32) fin[i] = PL.leaf[e * Kmax + (i % K)];
             continue;
@@ -358,6 +391,34 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
                                  reinterpret_cast<const Ent*>(wst), PL.pp + s_toff[e], ellp, lane, 32);
     }
     __syncthreads();
+    // leaf branches with many in-paralog clades (more lanes of work than one warp): all warps cooperate
+    for (int li = 0; li < M.nleafnodes; li++) {
+        const int e = M.leafnodes[li];
+        const NodeRec R = nrec[e];
+        const int C = (int)R.C;
+        if (C == 0 || R.nslots <= 32 || (R.nonleaf == 0 && A.skip_leaf)) continue;
+        const int K = s_K[e], n = s_nsl[e];
+        double* fin = rows + s_roff[e];
+        double* ellp = ell_of(e);
+        const int nd16 = (int)R.ndent, sl16 = ((int)R.nslots + 1) >> 1, pp16 = (n + 1) * K;
+        uint4* st4 = reinterpret_cast<uint4*>(stage);
+        copy16(st4, reinterpret_cast<const uint4*>(ents + R.dent_off), nd16, tid, NT);
+        copy16(st4 + nd16, reinterpret_cast<const uint4*>(words + R.slot_off), sl16, tid, NT);
+        copy16(st4 + nd16 + sl16, reinterpret_cast<const uint4*>(PL.pp + s_toff[e]), pp16, tid, NT);
+        double* cur = (n & 1) ? scr : fin;
+        const int nleafc = C - (int)R.nonleaf;
+        for (int i = tid; i < C * K; i += NT) {
+            const int c = i / K, k = i - c * K;
+            const double v = (c < nleafc && k == 0) ? M.leafP[e] : 0.0;
+            cur[i] = v;
+            if (ellp && k == 0) ellp[c] = v;
+        }
+        __syncthreads();
+        run_slices_fused_k<false>(K, n, C, fin, scr, cur, reinterpret_cast<const Slot*>(st4 + nd16), (int)R.nslots,
+                                  reinterpret_cast<const Ent*>(st4), reinterpret_cast<const double2*>(st4 + nd16 + sl16),
+                                  ellp, tid, NT);
+    }
+    const long long tcB = CLOCK64();
 
     // ================= phase B: internal, WGD and root nodes, whole CTA =================
     for (int oi = 0; oi < M.ninner; oi++) {
@@ -376,6 +437,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         const bool on = grp < GP;
         const double m = k == 0 ? 0.0 : 1.0;
 
+        const long long tst = CLOCK64();
         // ---- stage this node's lists: [dents | slots | dptr | tptr,lossF,lossG,lev | ϕψ rows] ----
         const int nd16 = (kind == WHALE_ROOT) ? 0 : (int)R.ndent;  // Πroot terms are read once: stay global
         const int sl16 = (kind == WHALE_ROOT) ? 0 : (((int)R.nslots + 1) >> 1);
@@ -397,12 +459,17 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         const uint32_t* s_lev = reinterpret_cast<const uint32_t*>(s_lossG + C);
         const double2* s_pp = reinterpret_cast<const double2*>(st4 + nd16 + sl16 + dp16 + tp16);
         auto slices = [&](double* cur) {
+            const long long ts = CLOCK64();
+            acc_row1 += ts - tc1;
             if (!run_slices_fused_k<false>(K, n, C, fin, scr, cur, s_slots, (int)R.nslots, s_dents, s_pp, ellp, tid, NT))
                 run_slices<false>(n, C, K, fin, scr, cur, s_dents, s_dptr, R.ndent, PL.pp + s_toff[e], prod, cap, ellp,
                                   tid, NT);
+            acc_slices += CLOCK64() - ts;
         };
 
         // children, shared by the row-1 formulas
+        tc1 = CLOCK64();
+        acc_stage += tc1 - tst;
         const int f = s_ch0[e], g = s_ch1[e];
         const int KF = s_K[f];
         const double* finF = rows + s_roff[f];
@@ -544,6 +611,18 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
             if (Lv > 0.0) o = tid == 0 ? log(Lv) : fin[(C - 1) * K + tid] / Lv;
             else o = tid == 0 ? -dinf() : 0.0;
             A.out_fam[(size_t)fam * K + tid] = o;
+        }
+        if (A.tim && tid == 0) {
+            const long long te = CLOCK64();
+            long long* T = A.tim + (size_t)fam * 8;
+            T[0] = tcA - tc0;            // prologue
+            T[1] = tcB - tcA;            // leaf phase (incl. waiting for the slowest warp)
+            T[2] = acc_stage;            // staging copies issued (phase B)
+            T[3] = acc_row1;             // row 1 of internal/WGD nodes (incl. staging wait)
+            T[4] = acc_slices;           // slices of internal/WGD nodes
+            T[5] = te - tc1;             // root
+            T[6] = te - tc0;             // total
+            T[7] = 0;
         }
     }
 }

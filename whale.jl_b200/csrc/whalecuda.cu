@@ -109,17 +109,8 @@ static int dp_nt() {
     static int nt = [] { int v = env_int("WHALE_NT", 128); return (v == 64 || v == 256) ? v : 128; }();
     return nt;
 }
-static int dp_minb() {
-    static int mb = [] {
-        const int nt = dp_nt();
-        int v = env_int("WHALE_MINB", nt == 64 ? 12 : nt == 128 ? 6 : 3);
-        if (nt == 64) return 12;
-        if (nt == 128) return v <= 5 ? 5 : v == 6 ? 6 : 7;
-        return 3;
-    }();
-    return mb;
-}
-#define DP_VARIANTS(X) X(64, 12) X(128, 5) X(128, 6) X(128, 7) X(256, 3)
+static int dp_minb() { return dp_nt() == 64 ? 12 : dp_nt() == 128 ? 5 : 2; }
+#define DP_VARIANTS(X) X(64, 12) X(128, 5) X(256, 2)
 constexpr int MAX_BINS = 8;
 struct Bin {
     int off, count;
@@ -143,6 +134,7 @@ struct whale_data {
     double* d_out_fam = nullptr;  // [F*Kmax(plan1)]
     double* d_partial = nullptr;
     double* d_ell = nullptr;
+    long long* d_tim = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
     uint64_t ell_total = 0;
@@ -528,7 +520,8 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
             pad4(wordsv);
             for (int j = 0; j < C; j++) wordsv.push_back((uint32_t)d->compat[coff[e] + j]);
             if (kind == WHALE_LEAF) {
-                leaf_stage = std::max(leaf_stage, 16 * ((size_t)R.ndent + ((size_t)R.nslots + 1) / 2));
+                if (R.nslots <= 32) leaf_stage = std::max(leaf_stage, 16 * ((size_t)R.ndent + ((size_t)R.nslots + 1) / 2));
+                else stage16[e] = (size_t)R.ndent + ((size_t)R.nslots + 1) / 2;  // heavy leaf branch: block scope
             } else {  // what k_dp stages in shared memory for this node
                 size_t nd16 = kind == WHALE_ROOT ? 0 : R.ndent;
                 size_t sl16 = kind == WHALE_ROOT ? 0 : ((size_t)R.nslots + 1) / 2;
@@ -572,10 +565,11 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
             for (int e = 0; e < nn; e++) {
                 const uint32_t K = (uint32_t)pl.K[e], ck = Cs[e] * K;
                 rows += ck;
-                if (m->kind[e] != WHALE_LEAF)  // lists + the ϕ/ψ rows of the fused slice loop (K <= 8)
+                if (stage16[e] > 0)  // lists + the ϕ/ψ rows of the fused slice loop (K <= 8)
                     stg = std::max(stg, stage16[e] + (K <= 8 ? (size_t)(m->nsl[e] + 1) * K : 0));
                 if (m->kind[e] == WHALE_LEAF) {
-                    mxleaf = std::max(mxleaf, ck);
+                    if (recs[e].nslots <= 32) mxleaf = std::max(mxleaf, ck);
+                    else mxinner = std::max(mxinner, ck);  // uses the block-scope scratch row
                 } else if (m->kind[e] != WHALE_ROOT) {
                     mxinner = std::max(mxinner, ck);
                     prod = std::max(prod, std::max(recs[e].ndent, recs[e].ntent) * K);
@@ -640,7 +634,7 @@ int32_t whale_data_destroy(whale_data_t d) {
         if (d->ev_join[i]) cudaEventDestroy(d->ev_join[i]);
     }
     if (d->ev_fork) cudaEventDestroy(d->ev_fork);
-    cudaFree(d->d_ell);
+    cudaFree(d->d_ell); cudaFree(d->d_tim);
     for (int i = 0; i < 4; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     delete d;
     return WHALE_OK;
@@ -687,7 +681,9 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
 #undef SETATTR
         attr_set = true;
     }
-    DPArgs a{m->dev, pl.dev, D->d_arena, D->d_hdr, D->d_perm[g], D->d_out_fam, keep ? D->d_ell : nullptr, g, keep ? 0 : 1};
+    if (prof && !D->d_tim) CU(cudaMalloc((void**)&D->d_tim, (size_t)F * 8 * sizeof(long long)));
+    DPArgs a{m->dev, pl.dev, D->d_arena, D->d_hdr, D->d_perm[g], D->d_out_fam, keep ? D->d_ell : nullptr, g, keep ? 0 : 1,
+             prof ? D->d_tim : nullptr};
     const int MB = dp_minb();
     auto launch_bin = [&](const Bin& b, cudaStream_t s) {
 #define LAUNCHV(NTV, MBV) if (NT == NTV && MB == MBV) LAUNCH((k_dp<NTV, MBV>), b.count, NTV, b.smem, s, a, b.off);
@@ -873,6 +869,22 @@ int32_t whale_last_kernel_ms(whale_data_t d, double* tables_ms, double* dp_ms, d
     if (tables_ms) *tables_ms = a;
     if (dp_ms) *dp_ms = b;
     if (reduce_ms) *reduce_ms = c;
+    return WHALE_OK;
+}
+
+int32_t whale_last_phase_cycles(whale_data_t d, double* mean8, double* max8) {
+    if (!d || !mean8 || !max8) return fail(WHALE_ERR_ARG, "null argument");
+    if (!d->ev_valid || !d->d_tim) return fail(WHALE_ERR_STATE, "last evaluation was not run with WHALE_PROFILE");
+    CU(cudaSetDevice(d->m->device));
+    CU(cudaEventSynchronize(d->ev[3]));
+    std::vector<long long> h((size_t)d->F * 8);
+    CU(cudaMemcpy(h.data(), d->d_tim, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (int j = 0; j < 8; j++) {
+        double s = 0, mx = 0;
+        for (int f = 0; f < d->F; f++) { s += (double)h[(size_t)f * 8 + j]; mx = std::max(mx, (double)h[(size_t)f * 8 + j]); }
+        mean8[j] = s / d->F;
+        max8[j] = mx;
+    }
     return WHALE_OK;
 }
 

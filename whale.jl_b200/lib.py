@@ -22,7 +22,7 @@ SYMBOLS = ["whale_version", "whale_last_error", "whale_device_count", "whale_set
            "whale_model_destroy", "whale_data_create", "whale_data_destroy", "whale_data_nfam",
            "whale_data_arena_bytes", "whale_data_arena_dump", "whale_logpdf_grad", "whale_logpdf_grad_async",
            "whale_slices", "whale_ell_size", "whale_ell_get", "whale_backtrack", "whale_launch_count",
-           "whale_work_estimate", "whale_last_kernel_ms", "whale_fp64_peak"]
+           "whale_work_estimate", "whale_last_kernel_ms", "whale_last_phase_cycles", "whale_fp64_peak"]
 
 
 class ModelDesc(C.Structure):
@@ -83,6 +83,7 @@ class Lib:
         L.whale_work_estimate.argtypes = [vp, vp, C.c_uint32, f64p, f64p]
         L.whale_fp64_peak.argtypes = [f64p]
         L.whale_last_kernel_ms.argtypes = [vp, f64p, f64p, f64p]
+        L.whale_last_phase_cycles.argtypes = [vp, f64p, f64p]
 
     def check(self, rc):
         if rc != 0:
@@ -174,6 +175,12 @@ class Lib:
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         self.check(self.L.whale_last_kernel_ms(dh, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    def last_phase_cycles(self, dh):
+        mean, mx = np.zeros(8), np.zeros(8)
+        self.check(self.L.whale_last_phase_cycles(dh, _ptr(mean, f64p), _ptr(mx, f64p)))
+        names = ["prologue", "leaf_phase", "staging", "row1", "slices", "root", "total"]
+        return {n: (float(mean[i]), float(mx[i])) for i, n in enumerate(names)}
 
     def logpdf_grad_async(self, mh, dh, d_x_ptr, condition, flags, d_out_ptr, stream_ptr):
         """Device-resident evaluation enqueued on `stream_ptr` (a cudaStream_t as int); not synchronised."""
