@@ -71,3 +71,10 @@ def test_emu_backtrack_matches_oracle(L):
     _check_backtrack(L, "c1_example1", [0, 7])
     _check_backtrack(L, "const_wgdturing", [2])
     _check_backtrack(L, "mul_tree", [5])
+
+
+def test_emu_parameter_chunks(L, monkeypatch):
+    """Families whose full-tangent working set exceeds the shared-memory goal get their gradient in several
+    passes over parameter chunks; force that with a tiny goal and compare with the oracle (37 parameters)."""
+    monkeypatch.setenv("WHALE_SMEM_GOAL", "6000")
+    run_parity(L, "c1_example1", sel=[3], conds=["root"])

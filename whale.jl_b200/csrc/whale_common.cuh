@@ -55,17 +55,19 @@ struct Slot {
 };
 static_assert(sizeof(Slot) == 8, "Slot must be 8 bytes");
 
+constexpr int MAXPLAN = 10;  // tangent plans per data handle: [0] value only, [1..] gradient (parameter chunks)
+
 struct FamHdr {
     uint64_t base;           // byte offset of the blob in the arena (16-byte aligned)
     uint64_t ell_off;        // offset (doubles) of this family's ℓ in the keep_ell buffer
     uint32_t G;              // clades
     uint32_t nlev;           // root levels (distinct clade sizes)
     // shared-memory budget (doubles unless stated), per tangent plan where it depends on K_e
-    uint32_t rows_len[2];    // Σ_e C_e K_e (even)
-    uint32_t scr_len[2];     // scratch row: max over internal/WGD nodes of C_e K_e (even)
-    uint32_t prod_len[2];    // P1 product window (row 1 / root / K > 8 slices), even
-    uint32_t leafmax[2];     // per-warp scratch row: max over leaf branches of C_e K_e (even)
-    uint32_t stage_bytes[2]; // staging buffer for one internal node's lists + ϕ/ψ rows (bytes, multiple of 16)
+    uint32_t rows_len[MAXPLAN];    // Σ_e C_e K_e (even)
+    uint32_t scr_len[MAXPLAN];     // scratch row: max over internal/WGD nodes of C_e K_e (even)
+    uint32_t prod_len[MAXPLAN];    // P1 product window (row 1 / root / K > 8 slices), even
+    uint32_t leafmax[MAXPLAN];     // per-warp scratch row: max over leaf branches of C_e K_e (even)
+    uint32_t stage_bytes[MAXPLAN]; // staging buffer for one internal node's lists + ϕ/ψ rows (bytes, multiple of 16)
     uint32_t leaf_stage;     // per-warp staging buffer for one leaf branch's lists (bytes, multiple of 16)
     uint32_t blob_bytes;
 };

@@ -275,7 +275,7 @@ __device__ __forceinline__ void run_slices_fused(int n, int C, double* fin, doub
 }
 
 // dispatch on the branch's component count (leaf branches carry at most value + own λ, μ: K <= 3)
-template <bool WARP>
+template <bool WARP, int KCAP>
 __device__ __forceinline__ bool run_slices_fused_k(int K, int n, int C, double* fin, double* scr, double* cur,
                                                    const Slot* s_slots, int nslots, const Ent* s_dents,
                                                    const double2* pprow, double* ellp, int tid, int nt) {
@@ -286,15 +286,24 @@ __device__ __forceinline__ bool run_slices_fused_k(int K, int n, int C, double* 
             default: return false;
         }
     } else {
-        switch (K) {
-            CASEK(1) CASEK(2) CASEK(3) CASEK(4) CASEK(5) CASEK(6) CASEK(7) CASEK(8)
-            default: return false;
+        if (KCAP <= 6) {
+            switch (K) {
+                CASEK(1) CASEK(2) CASEK(3) CASEK(4) CASEK(5) CASEK(6)
+                default: return false;
+            }
+        } else {
+            switch (K) {
+                CASEK(1) CASEK(2) CASEK(3) CASEK(4) CASEK(5) CASEK(6) CASEK(7) CASEK(8)
+                default: return false;
+            }
         }
     }
 #undef CASEK
 }
 
-template <int NT, int MINB>
+// KCAP: largest component count with a fused slice loop compiled in (6 or 8); plans with larger K use the
+// generic two-phase slice loop
+template <int NT, int MINB, int KCAP>
 __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
     EXTERN_SHARED(smem_raw);
     constexpr int NW = NT / 32;
@@ -387,7 +396,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
             if (ellp && k == 0) ellp[c] = v;
         }
         __syncwarp();
-        run_slices_fused_k<true>(K, n, C, fin, wscr, cur, reinterpret_cast<const Slot*>(wst + nd16), (int)R.nslots,
+        run_slices_fused_k<true, KCAP>(K, n, C, fin, wscr, cur, reinterpret_cast<const Slot*>(wst + nd16), (int)R.nslots,
                                  reinterpret_cast<const Ent*>(wst), PL.pp + s_toff[e], ellp, lane, 32);
     }
     __syncthreads();
@@ -414,7 +423,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
             if (ellp && k == 0) ellp[c] = v;
         }
         __syncthreads();
-        run_slices_fused_k<false>(K, n, C, fin, scr, cur, reinterpret_cast<const Slot*>(st4 + nd16), (int)R.nslots,
+        run_slices_fused_k<false, KCAP>(K, n, C, fin, scr, cur, reinterpret_cast<const Slot*>(st4 + nd16), (int)R.nslots,
                                   reinterpret_cast<const Ent*>(st4), reinterpret_cast<const double2*>(st4 + nd16 + sl16),
                                   ellp, tid, NT);
     }
@@ -430,7 +439,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         double* fin = rows + s_roff[e];
         double* ellp = ell_of(e);
         const int cap = (int)(prod_len / K);
-        const bool fused = K <= KMAX_FUSED;
+        const bool fused = K <= KCAP;
         // lane -> (cell group, component) for the P2 passes of row 1
         const int GP = NT / K;
         const int grp = tid / K, k = tid - grp * K;
@@ -461,7 +470,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         auto slices = [&](double* cur) {
             const long long ts = CLOCK64();
             acc_row1 += ts - tc1;
-            if (!run_slices_fused_k<false>(K, n, C, fin, scr, cur, s_slots, (int)R.nslots, s_dents, s_pp, ellp, tid, NT))
+            if (!run_slices_fused_k<false, KCAP>(K, n, C, fin, scr, cur, s_slots, (int)R.nslots, s_dents, s_pp, ellp, tid, NT))
                 run_slices<false>(n, C, K, fin, scr, cur, s_dents, s_dptr, R.ndent, PL.pp + s_toff[e], prod, cap, ellp,
                                   tid, NT);
             acc_slices += CLOCK64() - ts;

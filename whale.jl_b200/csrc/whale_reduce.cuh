@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(256) k_reduce1(const double* __restrict__ out_
 }
 
 __global__ void __launch_bounds__(256) k_reduce2(const double* __restrict__ partial, int nb, int K, int F,
-                                                 int cond_kind, PlanDev PL, int root, int P,
+                                                 int cond_kind, PlanDev PL, int root, int first,
                                                  double* __restrict__ out) {
     __shared__ double tot[256];
     __shared__ int finite;
@@ -35,10 +35,10 @@ __global__ void __launch_bounds__(256) k_reduce2(const double* __restrict__ part
     __syncthreads();
     if (threadIdx.x == 0) finite = isfinite(tot[0]) ? 1 : 0;  // ℓhood src/core.jl:15
     __syncthreads();
-    for (int i = threadIdx.x; i <= P; i += 256) out[i] = 0.0;
-    __syncthreads();
+    // `out` was zeroed by the host; every gradient pass (parameter chunk) writes its own parameters, the first
+    // pass also the log-likelihood
     for (int k = threadIdx.x; k < K; k += 256) {
-        if (k == 0) out[0] = finite ? tot[0] : -dinf();
+        if (k == 0) { if (first) out[0] = finite ? tot[0] : -dinf(); }
         else out[1 + PL.act[root * PL.Kmax + k]] = finite ? tot[k] : 0.0;
     }
 }

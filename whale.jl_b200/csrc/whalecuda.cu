@@ -109,8 +109,7 @@ static int dp_nt() {
     static int nt = [] { int v = env_int("WHALE_NT", 128); return (v == 64 || v == 256) ? v : 128; }();
     return nt;
 }
-static int dp_minb() { return dp_nt() == 64 ? 12 : dp_nt() == 128 ? 5 : 2; }
-#define DP_VARIANTS(X) X(64, 12) X(128, 5) X(256, 2)
+#define DP_VARIANTS(X) X(64, 12, 6) X(64, 12, 8) X(128, 5, 6) X(128, 5, 8) X(256, 2, 6) X(256, 2, 8)
 constexpr int MAX_BINS = 8;
 struct Bin {
     int off, count;
@@ -121,8 +120,17 @@ struct whale_data {
     whale_model* m = nullptr;
     int F = 0;
     std::vector<FamHdr> hdr;
-    std::vector<int> perm[2];
-    std::vector<Bin> bins[2];
+    // tangent plans used for evaluations: plans[0] = value only; plans[1..] = gradient passes (one when the
+    // full-tangent working set fits shared memory, else several passes over parameter chunks)
+    std::vector<Plan*> plans;
+    std::vector<Plan> chunk_plans;       // owned chunk plans (empty when plans[1] is the model's full plan)
+    std::vector<size_t> out_off;         // offset (doubles) of each plan's per-family outputs in d_out_fam
+    std::vector<int> perm[MAXPLAN];
+    std::vector<Bin> bins[MAXPLAN];
+    // per family x node facts kept from packing (shared-memory budgets are recomputed per plan)
+    std::vector<uint32_t> f_ndent, f_ntent, f_nslots, f_stage16;
+    std::vector<double> work;
+    size_t out_total = 0;
     cudaStream_t side[MAX_BINS] = {};
     cudaEvent_t ev_join[MAX_BINS] = {};
     cudaEvent_t ev_fork = nullptr;
@@ -130,7 +138,7 @@ struct whale_data {
     size_t arena_bytes = 0;
     unsigned char* d_arena = nullptr;
     FamHdr* d_hdr = nullptr;
-    int* d_perm[2] = {nullptr, nullptr};
+    int* d_perm[MAXPLAN] = {};
     double* d_out_fam = nullptr;  // [F*Kmax(plan1)]
     double* d_partial = nullptr;
     double* d_ell = nullptr;
@@ -146,14 +154,16 @@ struct whale_data {
     std::vector<std::vector<uint32_t>> famC;  // [F][nn] compat counts (for ℓ layout)
 };
 
-static void build_plan(const whale_model& m, bool grad, Plan& pl) {
+// `subset`: which raw parameters this plan differentiates (empty = none: the value-only plan)
+static void build_plan(const whale_model& m, const std::vector<char>& subset, Plan& pl) {
+    const bool grad = !subset.empty();
     const int nn = m.nn;
     std::vector<std::vector<int>> act(nn);
     for (int oi = 0; oi < nn; oi++) {
         int e = m.order[oi];
         std::vector<int> a;
         if (grad) {
-            auto add = [&](int s) { if (s >= 0) a.push_back(s); };
+            auto add = [&](int s) { if (s >= 0 && subset[s]) a.push_back(s); };
             if (m.child0[e] >= 0) a.insert(a.end(), act[m.child0[e]].begin(), act[m.child0[e]].end());
             if (m.child1[e] >= 0) a.insert(a.end(), act[m.child1[e]].begin(), act[m.child1[e]].end());
             if (m.kind[e] == WHALE_ROOT) add(m.eta_slot);
@@ -324,7 +334,7 @@ int32_t whale_model_create(const whale_model_desc* d, whale_model_t* out) {
     m->dev = ModelDev{nn, o, c0, c1, kd, ns, dt, lp, ls, ms, qs, m->eta_slot, m->log_scale, m->root,
                       (int)m->lvl_off.size() - 1, lo, ln, (int)m->leafnodes.size(), lfn, (int)m->inner.size(), inn};
     for (int g = 0; g < 2; g++) {
-        build_plan(*m, g == 1, m->plan[g]);
+        build_plan(*m, g == 1 ? std::vector<char>(m->P, 1) : std::vector<char>(), m->plan[g]);
         CU(upload_plan(m->plan[g], nn));
     }
     CU(cudaMalloc((void**)&m->d_x, std::max(1, m->P) * sizeof(double)));
@@ -352,11 +362,51 @@ int32_t whale_model_destroy(whale_model_t m) {
 // ---- the packer: reference-layout CSR -> per-branch resolved device arena ----
 static inline void pad4(std::vector<uint32_t>& w) { while (w.size() & 3) w.push_back(0); }
 
-static size_t smem_need(const whale_model* m, const FamHdr& h, int plan) {  // mirrors the carve-up in k_dp
-    const size_t nn = m->nn, Kmax = m->plan[plan].Kmax, NW = dp_nt() / 32;
+static size_t smem_need(const whale_model* m, const FamHdr& h, int plan, int Kmax_) {  // mirrors the carve-up in k_dp
+    const size_t nn = m->nn, Kmax = Kmax_, NW = dp_nt() / 32;
     const size_t hdr = (((7 * nn + 1) * sizeof(int) + nn * 2 * Kmax * sizeof(int16_t)) + 15) & ~size_t(15);
     return hdr + ((size_t)h.rows_len[plan] + h.scr_len[plan] + h.prod_len[plan]) * sizeof(double) +
            h.stage_bytes[plan] + NW * ((size_t)h.leafmax[plan] * sizeof(double) + h.leaf_stage);
+}
+
+// shared-memory budget of every family under tangent plan `pl` (stored at index g); returns the largest need
+static size_t set_budgets(whale_data* D, int g, const Plan& pl) {
+    const whale_model* m = D->m;
+    const int nn = m->nn;
+    size_t worst = 0;
+    for (int f = 0; f < D->F; f++) {
+        FamHdr& H = D->hdr[f];
+        const std::vector<uint32_t>& Cs = D->famC[f];
+        const uint32_t* nd = D->f_ndent.data() + (size_t)f * nn;
+        const uint32_t* nt = D->f_ntent.data() + (size_t)f * nn;
+        const uint32_t* ns = D->f_nslots.data() + (size_t)f * nn;
+        const uint32_t* s16 = D->f_stage16.data() + (size_t)f * nn;
+        uint32_t rows = 0, mxinner = 0, mxleaf = 0, prod = 0;
+        size_t stg = 0;
+        for (int e = 0; e < nn; e++) {
+            const uint32_t K = (uint32_t)pl.K[e], ck = Cs[e] * K;
+            rows += ck;
+            if (s16[e] > 0)  // lists + the ϕ/ψ rows of the fused slice loop (K <= 8)
+                stg = std::max(stg, (size_t)s16[e] + (K <= 8 ? (size_t)(m->nsl[e] + 1) * K : 0));
+            if (m->kind[e] == WHALE_LEAF) {
+                if (ns[e] <= 32) mxleaf = std::max(mxleaf, ck);
+                else mxinner = std::max(mxinner, ck);  // heavy leaf branch: block-scope scratch row
+            } else if (m->kind[e] != WHALE_ROOT) {
+                mxinner = std::max(mxinner, ck);
+                prod = std::max(prod, std::max(nd[e], nt[e]) * K);
+            }
+        }
+        // the root's levels use the same window; give it at least 64 terms so typical levels fit
+        prod = std::max(prod, 64u * (uint32_t)pl.K[m->root]);
+        auto even = [](uint32_t v) { return (v + 1) & ~1u; };
+        H.rows_len[g] = even(rows);
+        H.scr_len[g] = even(mxinner);
+        H.prod_len[g] = even(prod);
+        H.leafmax[g] = even(mxleaf);
+        H.stage_bytes[g] = (uint32_t)(16 * stg);
+        worst = std::max(worst, smem_need(m, H, g, pl.Kmax));
+    }
+    return worst;
 }
 
 int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t* out) {
@@ -372,7 +422,7 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
     D->aggT.assign(nn, 0.0);
     D->famC.resize(F);
     std::vector<unsigned char>& A = D->arena_host;
-    std::vector<double> work(F, 0.0);
+    D->work.assign(F, 0.0);
     std::vector<int32_t> lidx;  // local index of clade γ at node e: lidx[e*G + γ]
     uint64_t ell_total = 0;
     int64_t algo_bytes = 0;
@@ -555,46 +605,75 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
         H.nlev = nlev;
         H.leaf_stage = (uint32_t)leaf_stage;
         H.blob_bytes = (uint32_t)total;
-        work[f] = wk;
+        D->work[f] = wk;
         // SURVEY §8d algorithmic bytes per evaluation: 12·T + 2·Γ + 4·Σ_e C_e
         algo_bytes += 12 * (soff[G] - soff[0]) + 2 * (int64_t)G + 4 * (int64_t)sumC;
-        for (int g = 0; g < 2; g++) {  // shared-memory budget per tangent plan
-            const Plan& pl = m->plan[g];
-            uint32_t rows = 0, mxinner = 0, mxleaf = 0, prod = 0;
-            size_t stg = 0;
-            for (int e = 0; e < nn; e++) {
-                const uint32_t K = (uint32_t)pl.K[e], ck = Cs[e] * K;
-                rows += ck;
-                if (stage16[e] > 0)  // lists + the ϕ/ψ rows of the fused slice loop (K <= 8)
-                    stg = std::max(stg, stage16[e] + (K <= 8 ? (size_t)(m->nsl[e] + 1) * K : 0));
-                if (m->kind[e] == WHALE_LEAF) {
-                    if (recs[e].nslots <= 32) mxleaf = std::max(mxleaf, ck);
-                    else mxinner = std::max(mxinner, ck);  // uses the block-scope scratch row
-                } else if (m->kind[e] != WHALE_ROOT) {
-                    mxinner = std::max(mxinner, ck);
-                    prod = std::max(prod, std::max(recs[e].ndent, recs[e].ntent) * K);
-                }
-            }
-            // the root's levels use the same window; give it at least 64 terms so typical levels fit
-            prod = std::max(prod, 64u * (uint32_t)pl.K[m->root]);
-            auto even = [](uint32_t v) { return (v + 1) & ~1u; };
-            H.rows_len[g] = even(rows);
-            H.scr_len[g] = even(mxinner);
-            H.prod_len[g] = even(prod);
-            H.leafmax[g] = even(mxleaf);
-            H.stage_bytes[g] = (uint32_t)(16 * stg);
+        for (int e = 0; e < nn; e++) {
+            D->f_ndent.push_back(recs[e].ndent);
+            D->f_ntent.push_back(recs[e].ntent);
+            D->f_nslots.push_back(recs[e].nslots);
+            D->f_stage16.push_back((uint32_t)stage16[e]);
         }
     }
     D->ell_total = ell_total;
     D->algo_bytes = algo_bytes;
+    // ---- tangent plans: one gradient pass if every family's working set fits, else parameter chunks ----
+    D->plans = {&m->plan[0], &m->plan[1]};
+    set_budgets(D, 0, m->plan[0]);
+    size_t need1 = set_budgets(D, 1, m->plan[1]);
+    const size_t SMEM_MAX = 227 * 1024;
+    const size_t SMEM_GOAL = (size_t)env_int("WHALE_SMEM_GOAL", 113 * 1024);  // default: at least two families per SM
+    if (need1 > SMEM_GOAL || m->plan[1].Kmax > dp_nt()) {
+        // parameters ordered by the node that owns them (subtrees stay together -> sparse chunks)
+        std::vector<int> porder;
+        std::vector<char> seen(m->P, 0);
+        auto addp = [&](int sl) { if (sl >= 0 && !seen[sl]) { seen[sl] = 1; porder.push_back(sl); } };
+        for (int oi = 0; oi < nn; oi++) {
+            int e = m->order[oi];
+            if (m->kind[e] != WHALE_ROOT) { addp(m->lam_slot[e]); addp(m->mu_slot[e]); }
+            if (m->kind[e] == WHALE_WGD) addp(m->q_slot[e]);
+        }
+        addp(m->eta_slot);
+        for (int p = 0; p < m->P; p++) addp(p);  // parameters no node reads (e.g. the root's rates): zero gradient
+        bool ok = false;
+        for (int nch = 2; nch <= MAXPLAN - 1 && !ok; nch++) {
+            for (Plan& cp : D->chunk_plans) for (void* q : cp.owned) cudaFree(q);
+            D->chunk_plans.assign(nch, Plan());
+            D->plans.assign(1, &m->plan[0]);
+            size_t worst = 0;
+            int kmax = 0;
+            for (int c = 0; c < nch; c++) {
+                std::vector<char> sub(m->P, 0);
+                const size_t lo = porder.size() * c / nch, hi = porder.size() * (c + 1) / nch;
+                for (size_t i = lo; i < hi; i++) sub[porder[i]] = 1;
+                build_plan(*m, sub, D->chunk_plans[c]);
+                worst = std::max(worst, set_budgets(D, 1 + c, D->chunk_plans[c]));
+                kmax = std::max(kmax, D->chunk_plans[c].Kmax);
+            }
+            ok = (worst <= SMEM_GOAL || (nch == MAXPLAN - 1 && worst <= SMEM_MAX)) && kmax <= dp_nt();
+            if (ok || nch == MAXPLAN - 1) {
+                for (int c = 0; c < nch; c++) {
+                    CU(upload_plan(D->chunk_plans[c], nn));
+                    D->plans.push_back(&D->chunk_plans[c]);
+                }
+                need1 = worst;
+            }
+        }
+    }
+    if (need1 > SMEM_MAX) { delete D; return fail(WHALE_ERR_CAPACITY, "a family needs %zu bytes of shared memory (> 227 KB) even with %d parameter chunks", need1, MAXPLAN - 1); }
     // bins by shared-memory need (geometric, <= 25 % waste), launched concurrently; within a bin the
     // heaviest families go first
-    for (int g = 0; g < 2; g++) {
+    size_t outsz = 0;
+    for (size_t g = 0; g < D->plans.size(); g++) {
+        const Plan& pl = *D->plans[g];
+        D->out_off.push_back(g == 0 ? 0 : outsz);  // the value plan shares the first gradient slot's space
+        if (g >= 1) outsz += (size_t)F * pl.K[m->root];
         std::vector<int>& perm = D->perm[g];
         perm.resize(F);
         std::iota(perm.begin(), perm.end(), 0);
         std::vector<size_t> need(F);
-        for (int f = 0; f < F; f++) need[f] = smem_need(m, D->hdr[f], g);
+        for (int f = 0; f < F; f++) need[f] = smem_need(m, D->hdr[f], (int)g, pl.Kmax);
+        const std::vector<double>& work = D->work;
         std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return need[a] != need[b] ? need[a] > need[b] : work[a] > work[b]; });
         std::vector<Bin>& bins = D->bins[g];
         int i = 0;
@@ -608,12 +687,13 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
         if (bins.size() > 1 && bins.back().count < 64) { bins[bins.size() - 2].count += bins.back().count; bins.pop_back(); }
         CU(upload(perm, &D->d_perm[g]));
     }
+    D->out_total = std::max<size_t>(outsz, (size_t)F);
     CU(cudaMalloc((void**)&D->d_arena, std::max<size_t>(A.size(), 16)));
     CU(cudaMemcpy(D->d_arena, A.data(), A.size(), cudaMemcpyHostToDevice));
     D->arena_bytes = A.size();
     std::vector<unsigned char>().swap(A);
     CU(upload(D->hdr, &D->d_hdr));
-    CU(cudaMalloc((void**)&D->d_out_fam, (size_t)F * m->plan[1].Kmax * sizeof(double)));
+    CU(cudaMalloc((void**)&D->d_out_fam, D->out_total * sizeof(double)));
     CU(cudaMalloc((void**)&D->d_partial, (size_t)1024 * m->plan[1].Kmax * sizeof(double)));
     for (int i = 0; i < MAX_BINS; i++) {
         CU(cudaStreamCreateWithFlags(&D->side[i], cudaStreamNonBlocking));
@@ -627,7 +707,9 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
 int32_t whale_data_destroy(whale_data_t d) {
     if (!d) return WHALE_OK;
     cudaSetDevice(d->m->device);
-    cudaFree(d->d_arena); cudaFree(d->d_hdr); cudaFree(d->d_perm[0]); cudaFree(d->d_perm[1]);
+    cudaFree(d->d_arena); cudaFree(d->d_hdr);
+    for (int g = 0; g < MAXPLAN; g++) cudaFree(d->d_perm[g]);
+    for (Plan& cp : d->chunk_plans) for (void* q : cp.owned) cudaFree(q);
     cudaFree(d->d_out_fam); cudaFree(d->d_partial);
     for (int i = 0; i < MAX_BINS; i++) {
         if (d->side[i]) cudaStreamDestroy(d->side[i]);
@@ -652,65 +734,69 @@ int64_t whale_data_arena_dump(whale_data_t d, void* buf, int64_t cap) {
     return n;
 }
 
-// enqueue tables -> DP -> reduction on `st`; result in d_out (1+P doubles)
+// enqueue [tables -> DP -> reduction] for every tangent plan of this evaluation on `st`; result in d_out
 static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, int32_t condition, uint32_t flags,
                             double* d_out, cudaStream_t st) {
     if (condition < 0 || condition > 2) return fail(WHALE_ERR_ARG, "unknown condition kind %d", condition);
-    const int g = (flags & WHALE_WANT_GRAD) ? 1 : 0;
-    Plan& pl = m->plan[g];
+    const bool grad = (flags & WHALE_WANT_GRAD) != 0;
     const int nn = m->nn, F = D->F;
     const bool keep = (flags & WHALE_KEEP_ELL) != 0;
     if (keep && !D->d_ell) CU(cudaMalloc((void**)&D->d_ell, std::max<uint64_t>(D->ell_total, 1) * sizeof(double)));
     const bool prof = (flags & WHALE_PROFILE) != 0;
     if (prof && !D->ev[0]) for (int i = 0; i < 4; i++) CU(cudaEventCreate(&D->ev[i]));
-    if (prof) CU(cudaEventRecord(D->ev[0], st));
-    // K1
-    int nw = std::min(32, std::max(1, nn));
-    LAUNCH(k_tables, 1, nw * 32, 0, st, m->dev, pl.dev, d_x, m->d_pleaf);
-    g_launches++;
-    if (prof) CU(cudaEventRecord(D->ev[1], st));
-    // K2: one launch per shared-memory bin, concurrently on side streams
-    const int NT = dp_nt();
-    if (pl.Kmax > NT) return fail(WHALE_ERR_CAPACITY, "K=%d tangent components exceed %d lanes (parameter chunking not built yet)", pl.Kmax, NT);
-    const std::vector<Bin>& bins = D->bins[g];
-    if (bins[0].smem > 227 * 1024) return fail(WHALE_ERR_CAPACITY, "a family needs %zu bytes of shared memory (> 227 KB)", bins[0].smem);
+    if (prof && !D->d_tim) CU(cudaMalloc((void**)&D->d_tim, (size_t)F * 8 * sizeof(long long)));
     static thread_local bool attr_set = false;
     if (!attr_set) {
-#define SETATTR(NTV, MB) CU(cudaFuncSetAttribute(k_dp<NTV, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define SETATTR(NTV, MB, KC) CU(cudaFuncSetAttribute(k_dp<NTV, MB, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         DP_VARIANTS(SETATTR)
 #undef SETATTR
         attr_set = true;
     }
-    if (prof && !D->d_tim) CU(cudaMalloc((void**)&D->d_tim, (size_t)F * 8 * sizeof(long long)));
-    DPArgs a{m->dev, pl.dev, D->d_arena, D->d_hdr, D->d_perm[g], D->d_out_fam, keep ? D->d_ell : nullptr, g, keep ? 0 : 1,
-             prof ? D->d_tim : nullptr};
-    const int MB = dp_minb();
-    auto launch_bin = [&](const Bin& b, cudaStream_t s) {
-#define LAUNCHV(NTV, MBV) if (NT == NTV && MB == MBV) LAUNCH((k_dp<NTV, MBV>), b.count, NTV, b.smem, s, a, b.off);
-        DP_VARIANTS(LAUNCHV)
-#undef LAUNCHV
+    const int NT = dp_nt();
+    const size_t g0 = grad ? 1 : 0, g1 = grad ? D->plans.size() : 1;
+    CU(cudaMemsetAsync(d_out, 0, (1 + m->P) * sizeof(double), st));
+    for (size_t g = g0; g < g1; g++) {
+        Plan& pl = *D->plans[g];
+        const bool first = g == g0;
+        if (prof && first) CU(cudaEventRecord(D->ev[0], st));
+        // K1: slice tables of this plan
+        LAUNCH(k_tables, 1, std::min(32, std::max(1, nn)) * 32, 0, st, m->dev, pl.dev, d_x, m->d_pleaf);
         g_launches++;
-    };
-    if (bins.size() == 1) {
-        launch_bin(bins[0], st);
-    } else {
-        CU(cudaEventRecord(D->ev_fork, st));
-        for (size_t b = 0; b < bins.size(); b++) {
-            CU(cudaStreamWaitEvent(D->side[b], D->ev_fork, 0));
-            launch_bin(bins[b], D->side[b]);
-            CU(cudaEventRecord(D->ev_join[b], D->side[b]));
-            CU(cudaStreamWaitEvent(st, D->ev_join[b], 0));
+        if (prof && first) CU(cudaEventRecord(D->ev[1], st));
+        // K2: one launch per shared-memory bin, concurrently on side streams
+        const std::vector<Bin>& bins = D->bins[g];
+        double* out_fam = D->d_out_fam + D->out_off[g];
+        // the ℓ kept for backtracking is written by the first pass only (values do not depend on the chunk)
+        DPArgs a{m->dev, pl.dev, D->d_arena, D->d_hdr, D->d_perm[g], out_fam, (keep && first) ? D->d_ell : nullptr, (int)g,
+                 keep ? 0 : 1, (prof && first) ? D->d_tim : nullptr};
+        const int KC = pl.Kmax <= 6 ? 6 : 8;
+        auto launch_bin = [&](const Bin& b, cudaStream_t s) {
+#define LAUNCHV(NTV, MBV, KCV) if (NT == NTV && KC == KCV) LAUNCH((k_dp<NTV, MBV, KCV>), b.count, NTV, b.smem, s, a, b.off);
+            DP_VARIANTS(LAUNCHV)
+#undef LAUNCHV
+            g_launches++;
+        };
+        if (bins.size() == 1) {
+            launch_bin(bins[0], st);
+        } else {
+            CU(cudaEventRecord(D->ev_fork, st));
+            for (size_t b = 0; b < bins.size(); b++) {
+                CU(cudaStreamWaitEvent(D->side[b], D->ev_fork, 0));
+                launch_bin(bins[b], D->side[b]);
+                CU(cudaEventRecord(D->ev_join[b], D->side[b]));
+                CU(cudaStreamWaitEvent(st, D->ev_join[b], 0));
+            }
         }
+        if (prof && first) CU(cudaEventRecord(D->ev[2], st));
+        // K3: Σ over families − N·condition; this plan's parameters scattered into d_out
+        const int KR = pl.K[m->root];
+        int nb = std::min(1024, (F + 255) / 256);
+        int chunk = (F + nb - 1) / nb;
+        LAUNCH(k_reduce1, nb, 256, 0, st, out_fam, F, KR, chunk, D->d_partial);
+        LAUNCH(k_reduce2, 1, 256, 0, st, D->d_partial, nb, KR, F, condition, pl.dev, m->root, first ? 1 : 0, d_out);
+        g_launches += 2;
+        if (prof && first) CU(cudaEventRecord(D->ev[3], st));
     }
-    if (prof) CU(cudaEventRecord(D->ev[2], st));
-    // K3
-    const int KR = pl.K[m->root];
-    int nb = std::min(1024, (F + 255) / 256);
-    int chunk = (F + nb - 1) / nb;
-    LAUNCH(k_reduce1, nb, 256, 0, st, D->d_out_fam, F, KR, chunk, D->d_partial);
-    LAUNCH(k_reduce2, 1, 256, 0, st, D->d_partial, nb, KR, F, condition, pl.dev, m->root, m->P, d_out);
-    g_launches += 2;
-    if (prof) CU(cudaEventRecord(D->ev[3], st));
     D->ev_valid = prof;
     CU(cudaGetLastError());
     D->ell_valid = keep;
@@ -746,15 +832,17 @@ int32_t whale_logpdf_grad(whale_model_t m, whale_data_t d, const double* x, cons
     *loglik = ho[0];
     if (grad) memcpy(grad, ho + 1, P * sizeof(double));
     if (ll_fam || grad_fam) {
-        const Plan& pl = m->plan[(flags & WHALE_WANT_GRAD) ? 1 : 0];
-        const int KR = pl.K[m->root];
-        std::vector<double> tmp((size_t)d->F * KR);
-        CU(cudaMemcpy(tmp.data(), d->d_out_fam, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
-        for (int f = 0; f < d->F; f++) {
-            if (ll_fam) ll_fam[f] = tmp[(size_t)f * KR];
-            if (grad_fam) {
-                for (int p = 0; p < P; p++) grad_fam[(size_t)f * P + p] = 0.0;
-                for (int k = 1; k < KR; k++) grad_fam[(size_t)f * P + pl.act[(size_t)m->root * pl.Kmax + k]] = tmp[(size_t)f * KR + k];
+        const bool grad_ = (flags & WHALE_WANT_GRAD) != 0;
+        if (grad_fam) for (size_t i = 0; i < (size_t)d->F * P; i++) grad_fam[i] = 0.0;
+        for (size_t g = grad_ ? 1 : 0; g < (grad_ ? d->plans.size() : 1); g++) {
+            const Plan& pl = *d->plans[g];
+            const int KR = pl.K[m->root];
+            std::vector<double> tmp((size_t)d->F * KR);
+            CU(cudaMemcpy(tmp.data(), d->d_out_fam + d->out_off[g], tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            for (int f = 0; f < d->F; f++) {
+                if (ll_fam) ll_fam[f] = tmp[(size_t)f * KR];
+                if (grad_fam)
+                    for (int k = 1; k < KR; k++) grad_fam[(size_t)f * P + pl.act[(size_t)m->root * pl.Kmax + k]] = tmp[(size_t)f * KR + k];
             }
         }
     }
@@ -843,7 +931,7 @@ int32_t whale_backtrack(whale_model_t m, whale_data_t d, int32_t n_samples, cons
 
 int32_t whale_work_estimate(whale_model_t m, whale_data_t d, uint32_t flags, double* flops, double* bytes) {
     if (!m || !d) return fail(WHALE_ERR_ARG, "null argument");
-    const Plan& pl = m->plan[(flags & WHALE_WANT_GRAD) ? 1 : 0];
+    const Plan& pl = m->plan[(flags & WHALE_WANT_GRAD) ? 1 : 0];  // the algorithmic count ignores chunking
     double fl = 0.0;
     for (int e = 0; e < m->nn; e++) {  // SURVEY §8d fixed coefficients
         const double C = d->aggC[e], T = d->aggT[e], Pe = pl.K[e] - 1, n = m->nsl[e];
