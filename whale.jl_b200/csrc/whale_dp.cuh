@@ -230,8 +230,10 @@ __device__ __forceinline__ void slice_pass(const LaneWork<K>& w, int wg, int sid
     }
 }
 
+// Not inlined on purpose: each component count gets its own register allocation; inlining all variants into
+// k_dp makes ptxas demote the per-lane accumulator arrays to local memory.
 template <int K, bool WARP>
-__device__ __forceinline__ void run_slices_fused(int n, int C, double* fin, double* scr, double* cur,
+__device__ __noinline__ void run_slices_fused(int n, int C, double* fin, double* scr, double* cur,
                                                  const Slot* s_slots, int nslots, const Ent* s_dents,
                                                  const double2* pprow, double* ellp, int tid, int nt) {
     // the first two passes keep their descriptors in registers

@@ -109,7 +109,16 @@ static int dp_nt() {
     static int nt = [] { int v = env_int("WHALE_NT", 128); return (v == 64 || v == 256) ? v : 128; }();
     return nt;
 }
-#define DP_VARIANTS(X) X(64, 12, 6) X(64, 12, 8) X(128, 5, 6) X(128, 5, 8) X(256, 2, 6) X(256, 2, 8)
+static int dp_minb() {  // resident CTAs per SM the register cap is chosen for
+    static int mb = [] {
+        const int nt = dp_nt(), v = env_int("WHALE_MINB", 0);
+        if (nt == 64) return 12;
+        if (nt == 256) return 2;
+        return (v == 6 || v == 7) ? v : 5;
+    }();
+    return mb;
+}
+#define DP_VARIANTS(X) X(64, 12, 6) X(64, 12, 8) X(128, 5, 6) X(128, 6, 6) X(128, 7, 6) X(128, 5, 8) X(256, 2, 6) X(256, 2, 8)
 constexpr int MAX_BINS = 8;
 struct Bin {
     int off, count;
@@ -770,8 +779,9 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
         DPArgs a{m->dev, pl.dev, D->d_arena, D->d_hdr, D->d_perm[g], out_fam, (keep && first) ? D->d_ell : nullptr, (int)g,
                  keep ? 0 : 1, (prof && first) ? D->d_tim : nullptr};
         const int KC = pl.Kmax <= 6 ? 6 : 8;
+        const int MB = (NT == 128 && KC == 8) ? 5 : dp_minb();
         auto launch_bin = [&](const Bin& b, cudaStream_t s) {
-#define LAUNCHV(NTV, MBV, KCV) if (NT == NTV && KC == KCV) LAUNCH((k_dp<NTV, MBV, KCV>), b.count, NTV, b.smem, s, a, b.off);
+#define LAUNCHV(NTV, MBV, KCV) if (NT == NTV && MB == MBV && KC == KCV) LAUNCH((k_dp<NTV, MBV, KCV>), b.count, NTV, b.smem, s, a, b.off);
             DP_VARIANTS(LAUNCHV)
 #undef LAUNCHV
             g_launches++;
