@@ -87,6 +87,7 @@ struct ModelDev {  // structure arrays (device pointers), node index = id-1
     int eta_slot;
     int log_scale;
     int root;
+    int n_params;
     int nlvl;              // nodes grouped by height (k_tables schedule)
     const int* lvl_off;
     const int* lvl_nodes;

@@ -49,10 +49,22 @@ __device__ __forceinline__ void scope_sync() {
     else __syncthreads();
 }
 
-// copy n16 16-byte words global -> shared with all threads of the scope
+// copy n16 16-byte words global -> shared with all threads of the scope.  cp.async keeps every copy of a
+// staging batch in flight at once (one memory latency per node instead of one per loop iteration); the batch
+// is completed by stage_wait() before the scope's barrier.
+#ifdef WHALE_EMU
 __device__ __forceinline__ void copy16(uint4* dst, const uint4* __restrict__ src, int n16, int tid, int nt) {
-    for (int i = tid; i < n16; i += nt) dst[i] = __ldg(src + i);
+    for (int i = tid; i < n16; i += nt) dst[i] = src[i];
 }
+__device__ __forceinline__ void stage_wait() {}
+#else
+__device__ __forceinline__ void copy16(uint4* dst, const uint4* __restrict__ src, int n16, int tid, int nt) {
+    for (int i = tid; i < n16; i += nt)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst + i)),
+                     "l"(src + i) : "memory");
+}
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif
 
 // P1: terms [ta, tb) of `ents` -> prod[k*cap + (t - ta)], k = 0..K-1.
 // X/Y are rows with KX/KY components; mapX/mapY translate the output component k into the component of
@@ -397,6 +409,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
             cur[i] = v;
             if (ellp && k == 0) ellp[c] = v;
         }
+        stage_wait();
         __syncwarp();
         run_slices_fused_k<true, KCAP>(K, n, C, fin, wscr, cur, reinterpret_cast<const Slot*>(wst + nd16), (int)R.nslots,
                                  reinterpret_cast<const Ent*>(wst), PL.pp + s_toff[e], ellp, lane, 32);
@@ -424,6 +437,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
             cur[i] = v;
             if (ellp && k == 0) ellp[c] = v;
         }
+        stage_wait();
         __syncthreads();
         run_slices_fused_k<false, KCAP>(K, n, C, fin, scr, cur, reinterpret_cast<const Slot*>(st4 + nd16), (int)R.nslots,
                                   reinterpret_cast<const Ent*>(st4), reinterpret_cast<const double2*>(st4 + nd16 + sl16),
@@ -455,12 +469,15 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         const int dp16 = (C + 1 + 3) >> 2;
         const int tp16 = (kind == WHALE_WGD) ? 0 : ((3 * C + 1 + (kind == WHALE_ROOT ? (int)nlev + 1 : 0) + 3) >> 2);
         const int pp16 = fused ? (n + 1) * K : 0;
+        const int te16 = (kind == WHALE_INTERNAL) ? (int)R.ntent : 0;  // speciation terms of row 1
         uint4* st4 = reinterpret_cast<uint4*>(stage);
         copy16(st4, reinterpret_cast<const uint4*>(ents + R.dent_off), nd16, tid, NT);
         copy16(st4 + nd16, reinterpret_cast<const uint4*>(words + R.slot_off), sl16, tid, NT);
         copy16(st4 + nd16 + sl16, reinterpret_cast<const uint4*>(words + R.dptr_off), dp16, tid, NT);
         copy16(st4 + nd16 + sl16 + dp16, reinterpret_cast<const uint4*>(words + R.tptr_off), tp16, tid, NT);
         copy16(st4 + nd16 + sl16 + dp16 + tp16, reinterpret_cast<const uint4*>(PL.pp + s_toff[e]), pp16, tid, NT);
+        copy16(st4 + nd16 + sl16 + dp16 + tp16 + pp16, reinterpret_cast<const uint4*>(ents + R.tent_off), te16, tid, NT);
+        stage_wait();
         const Ent* s_dents = reinterpret_cast<const Ent*>(stage);
         const Slot* s_slots = reinterpret_cast<const Slot*>(st4 + nd16);
         const uint32_t* s_dptr = reinterpret_cast<const uint32_t*>(st4 + nd16 + sl16);
@@ -521,6 +538,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         const double efk = (k > 0 && kf >= 0) ? epsF[kf] : 0.0;
         const double egk = (k > 0 && kg >= 0) ? epsG[kg] : 0.0;
         const Ent* g_tents = ents + R.tent_off;
+        const Ent* s_tents = reinterpret_cast<const Ent*>(st4 + nd16 + sl16 + dp16 + tp16 + pp16);
         __syncthreads();  // staged lists visible
         if (kind == WHALE_INTERNAL) {
             // speciation terms may exceed the product window: process them in windows of `cap` terms, whole
@@ -549,7 +567,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
                     }
                     cB = cA + 1;
                 } else {
-                    terms<true>(g_tents, ta, s_tptr[cB], finF, KF, mapF, finG, KG, mapG, K, prod, cap, tid, NT);
+                    terms<false>(s_tents, ta, s_tptr[cB], finF, KF, mapF, finG, KG, mapG, K, prod, cap, tid, NT);
                     __syncthreads();
                     if (on)
                         for (int c = cA + grp; c < cB; c += GP) {

@@ -11,10 +11,19 @@
 #pragma once
 #include "whale_common.cuh"
 
-__device__ __forceinline__ D1 child_eps_last(const ModelDev& M, const PlanDev& PL, int e, int j, int child, int k) {
-    const int Kc = PL.K[child];
-    const double2* row = PL.uv + PL.toff[child] + (size_t)M.nsl[child] * Kc;
-    const int kc = k == 0 ? 0 : PL.cmap[(e * 2 + j) * PL.Kmax + k];
+// species-tree metadata staged in shared memory: after an L2 flush every dependent global load of these tiny
+// arrays costs a DRAM round trip per level (measured: 60 µs of k_tables were mostly that)
+struct TabMeta {
+    const int *kind, *nsl, *ch0, *ch1, *ls, *ms, *qs, *K, *toff, *lvl_off, *lvl_nodes;
+    const double *dt, *leafP, *pleaf, *x;
+    const int16_t* cmap;
+    const uint8_t* role;
+};
+
+__device__ __forceinline__ D1 child_eps_last(const TabMeta& T, const PlanDev& PL, int e, int j, int child, int k) {
+    const int Kc = T.K[child];
+    const double2* row = PL.uv + T.toff[child] + (size_t)T.nsl[child] * Kc;
+    const int kc = k == 0 ? 0 : T.cmap[(e * 2 + j) * PL.Kmax + k];
     const double2 a = row[0];
     D1 u = mk(a.x), v = mk(a.y);
     if (k > 0 && kc >= 0) {
@@ -29,36 +38,55 @@ __global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const d
                                                  const double* __restrict__ pleaf) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const double NaN = __longlong_as_double(0x7ff8000000000000LL);
+    EXTERN_SHARED(tsm);
+    const int nn = M.nn, Kmax = PL.Kmax, P = M.n_params;
+    double* sd = reinterpret_cast<double*>(tsm);                 // dt, leafP, pleaf [nn each], x [P]
+    int* si = reinterpret_cast<int*>(sd + 3 * nn + P);           // 9 arrays [nn], lvl_off [nlvl+1], lvl_nodes [nn]
+    int16_t* s_cm = reinterpret_cast<int16_t*>(si + 10 * nn + M.nlvl + 1);
+    uint8_t* s_ro = reinterpret_cast<uint8_t*>(s_cm + nn * 2 * Kmax);
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+        sd[i] = M.dt[i]; sd[nn + i] = M.leafP[i]; sd[2 * nn + i] = pleaf ? pleaf[i] : 0.0;
+        si[i] = M.kind[i]; si[nn + i] = M.nsl[i]; si[2 * nn + i] = M.child0[i]; si[3 * nn + i] = M.child1[i];
+        si[4 * nn + i] = M.lam_slot[i]; si[5 * nn + i] = M.mu_slot[i]; si[6 * nn + i] = M.q_slot[i];
+        si[7 * nn + i] = PL.K[i]; si[8 * nn + i] = PL.toff[i]; si[9 * nn + M.nlvl + 1 + i] = M.lvl_nodes[i];
+    }
+    for (int i = threadIdx.x; i <= M.nlvl; i += blockDim.x) si[9 * nn + i] = M.lvl_off[i];
+    for (int i = threadIdx.x; i < P; i += blockDim.x) sd[3 * nn + i] = x[i];
+    for (int i = threadIdx.x; i < nn * 2 * Kmax; i += blockDim.x) s_cm[i] = PL.cmap[i];
+    for (int i = threadIdx.x; i < nn * Kmax; i += blockDim.x) s_ro[i] = PL.role[i];
+    __syncthreads();
+    TabMeta T{si, si + nn, si + 2 * nn, si + 3 * nn, si + 4 * nn, si + 5 * nn, si + 6 * nn, si + 7 * nn, si + 8 * nn,
+              si + 9 * nn, si + 9 * nn + M.nlvl + 1, sd, sd + nn, sd + 2 * nn, sd + 3 * nn, s_cm, s_ro};
     // ---- phase A: per level, one warp per node, lanes over components; division-free chain ----
     for (int L = 0; L < M.nlvl; L++) {
-        const int n0 = M.lvl_off[L], n1 = M.lvl_off[L + 1];
+        const int n0 = T.lvl_off[L], n1 = T.lvl_off[L + 1];
         for (int j = n0 + warp; j < n1; j += nwarp) {
-            const int e = M.lvl_nodes[j];
-            const int K = PL.K[e], kind = M.kind[e], n = M.nsl[e];
+            const int e = T.lvl_nodes[j];
+            const int K = T.K[e], kind = T.kind[e], n = T.nsl[e];
             for (int k = lane; k < K; k += 32) {
-                const unsigned role = k == 0 ? 0u : PL.role[e * PL.Kmax + k];
+                const unsigned role = k == 0 ? 0u : T.role[e * PL.Kmax + k];
                 // getθ (src/rmodels.jl:31-33,55-64): raw -> rate, with the chain factor of the log scale
-                const int ls = M.lam_slot[e], ms = M.mu_slot[e];
-                const double lv = ls < 0 ? NaN : (M.log_scale ? exp(x[ls]) : x[ls]);
-                const double mv = ms < 0 ? NaN : (M.log_scale ? exp(x[ms]) : x[ms]);
+                const int ls = T.ls[e], ms = T.ms[e];
+                const double lv = ls < 0 ? NaN : (M.log_scale ? exp(T.x[ls]) : T.x[ls]);
+                const double mv = ms < 0 ? NaN : (M.log_scale ? exp(T.x[ms]) : T.x[ms]);
                 const D1 lam = mk(lv, (role & 1u) ? (M.log_scale ? lv : 1.0) : 0.0);
                 const D1 mu = mk(mv, (role & 2u) ? (M.log_scale ? mv : 1.0) : 0.0);
                 D1 ep;
                 if (kind == WHALE_LEAF) {  // setnode! src/model.jl:170
-                    ep = mk(pleaf ? pleaf[e] : 0.0);
+                    ep = mk(T.pleaf[e]);
                 } else if (kind == WHALE_WGD) {  // setwgdnode! src/model.jl:175-180
-                    const D1 q = mk(x[M.q_slot[e]], (role & 4u) ? 1.0 : 0.0);
-                    const D1 ec = child_eps_last(M, PL, e, 0, M.child0[e], k);
+                    const D1 q = mk(T.x[T.qs[e]], (role & 4u) ? 1.0 : 0.0);
+                    const D1 ec = child_eps_last(T, PL, e, 0, T.ch0[e], k);
                     ep = q * (ec * ec) + (1.0 - q) * ec;
                     const D1 w = (1.0 - q) + 2.0 * (q * ec);  // Πwgdloss coefficient src/core.jl:198
                     PL.cx[e * PL.Kmax + k] = k == 0 ? w.v : w.d;
                     PL.cy[e * PL.Kmax + k] = k == 0 ? q.v : q.d;
                 } else {  // internal / root: product of the children's last ϵ
-                    const D1 ef = child_eps_last(M, PL, e, 0, M.child0[e], k);
-                    const D1 eg = child_eps_last(M, PL, e, 1, M.child1[e], k);
+                    const D1 ef = child_eps_last(T, PL, e, 0, T.ch0[e], k);
+                    const D1 eg = child_eps_last(T, PL, e, 1, T.ch1[e], k);
                     ep = ef * eg;
                     if (kind == WHALE_ROOT) {  // whaleroot! src/core.jl:131-147 ; condition src/condition.jl
-                        const D1 eta = mk(x[M.eta_slot], (role & 8u) ? 1.0 : 0.0);
+                        const D1 eta = mk(T.x[M.eta_slot], (role & 8u) ? 1.0 : 0.0);
                         const D1 xi = 1.0 - (1.0 - eta) * ep;
                         const D1 A = (1.0 - eta) * xi / eta;
                         const D1 B = eta * (1.0 - ep) / (xi * xi);
@@ -77,13 +105,13 @@ __global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const d
                         PL.cond[2 * PL.Kmax + k] = k == 0 ? cn.v : cn.d;
                     }
                 }
-                double2* uvrow = PL.uv + PL.toff[e];
+                double2* uvrow = PL.uv + T.toff[e];
                 D1 u = ep, v = mk(1.0);
                 uvrow[k] = k == 0 ? make_double2(u.v, v.v) : make_double2(u.d, v.d);
                 D1 a = mk(0.0), b = mk(0.0);
                 if (n > 0) {
                     // getα src/bdputil.jl:6-7 (critical branch decided on VALUES, like isapprox on Duals)
-                    const double t = M.dt[e];
+                    const double t = T.dt[e];
                     if (fabs(lam.v - mu.v) <= 1e-6) {
                         a = (lam * mk(t)) / (1.0 + lam * mk(t));
                     } else {
@@ -106,7 +134,7 @@ __global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const d
                     // leaf clade on a leaf branch: ℓ_n = leafℙ·Π_i ϕ_i = leafℙ·gⁿ·(v_0/v_n)²  (src/core.jl:94,123)
                     const D1 g = (1.0 - a) * (1.0 - b);
                     const D1 r = mk(1.0) / v;
-                    const D1 lf = mk(M.leafP[e]) * dpowi(g, n) * (r * r);
+                    const D1 lf = mk(T.leafP[e]) * dpowi(g, n) * (r * r);
                     PL.leaf[e * PL.Kmax + k] = k == 0 ? lf.v : lf.d;
                 }
             }
@@ -115,10 +143,10 @@ __global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const d
     }
     // ---- phase B: every row of every node in parallel ----
     for (int e = 0; e < M.nn; e++) {
-        const int K = PL.K[e], n = M.nsl[e];
-        const double2* uvrow = PL.uv + PL.toff[e];
-        double* erow = PL.eps + PL.toff[e];
-        double2* prow = PL.pp + PL.toff[e];
+        const int K = T.K[e], n = T.nsl[e];
+        const double2* uvrow = PL.uv + T.toff[e];
+        double* erow = PL.eps + T.toff[e];
+        double2* prow = PL.pp + T.toff[e];
         for (int idx = threadIdx.x; idx < (n + 1) * K; idx += blockDim.x) {
             const int i = idx / K, k = idx - i * K;
             const double2 w0 = uvrow[(size_t)i * K], wk = uvrow[(size_t)i * K + k];

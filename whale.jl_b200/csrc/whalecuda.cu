@@ -340,7 +340,7 @@ int32_t whale_model_create(const whale_model_desc* d, whale_model_t* out) {
     CU(upload(m->nsl, &ns)); CU(upload(m->lam_slot, &ls)); CU(upload(m->mu_slot, &ms)); CU(upload(m->q_slot, &qs));
     CU(upload(m->lvl_off, &lo)); CU(upload(m->lvl_nodes, &ln)); CU(upload(m->dt, &dt)); CU(upload(m->leafP, &lp));
     m->owned = {o, c0, c1, kd, ns, ls, ms, qs, lo, ln, dt, lp, lfn, inn};
-    m->dev = ModelDev{nn, o, c0, c1, kd, ns, dt, lp, ls, ms, qs, m->eta_slot, m->log_scale, m->root,
+    m->dev = ModelDev{nn, o, c0, c1, kd, ns, dt, lp, ls, ms, qs, m->eta_slot, m->log_scale, m->root, m->P,
                       (int)m->lvl_off.size() - 1, lo, ln, (int)m->leafnodes.size(), lfn, (int)m->inner.size(), inn};
     for (int g = 0; g < 2; g++) {
         build_plan(*m, g == 1 ? std::vector<char>(m->P, 1) : std::vector<char>(), m->plan[g]);
@@ -376,6 +376,12 @@ static size_t smem_need(const whale_model* m, const FamHdr& h, int plan, int Kma
     const size_t hdr = (((7 * nn + 1) * sizeof(int) + nn * 2 * Kmax * sizeof(int16_t)) + 15) & ~size_t(15);
     return hdr + ((size_t)h.rows_len[plan] + h.scr_len[plan] + h.prod_len[plan]) * sizeof(double) +
            h.stage_bytes[plan] + NW * ((size_t)h.leafmax[plan] * sizeof(double) + h.leaf_stage);
+}
+
+static size_t tables_smem(const whale_model* m, const Plan& pl) {  // mirrors the carve-up in k_tables
+    const size_t nn = m->nn, nlvl = m->lvl_off.size() - 1;
+    return (3 * nn + m->P) * sizeof(double) + (10 * nn + nlvl + 1) * sizeof(int) + nn * 2 * pl.Kmax * sizeof(int16_t) +
+           nn * pl.Kmax + 16;
 }
 
 // shared-memory budget of every family under tangent plan `pl` (stored at index g); returns the largest need
@@ -586,7 +592,8 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
                 size_t sl16 = kind == WHALE_ROOT ? 0 : ((size_t)R.nslots + 1) / 2;
                 size_t dp16 = ((size_t)C + 1 + 3) / 4;
                 size_t tp16 = kind == WHALE_WGD ? 0 : (3 * (size_t)C + 1 + (kind == WHALE_ROOT ? nlev + 1 : 0) + 3) / 4;
-                stage16[e] = nd16 + sl16 + dp16 + tp16;
+                size_t te16 = kind == WHALE_INTERNAL ? R.ntent : 0;
+                stage16[e] = nd16 + sl16 + dp16 + tp16 + te16;
             }
             ell_total += (uint64_t)(m->nsl[e] + 1) * C;
         }
@@ -769,7 +776,7 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
         const bool first = g == g0;
         if (prof && first) CU(cudaEventRecord(D->ev[0], st));
         // K1: slice tables of this plan
-        LAUNCH(k_tables, 1, std::min(32, std::max(1, nn)) * 32, 0, st, m->dev, pl.dev, d_x, m->d_pleaf);
+        LAUNCH(k_tables, 1, std::min(32, std::max(1, nn)) * 32, tables_smem(m, pl), st, m->dev, pl.dev, d_x, m->d_pleaf);
         g_launches++;
         if (prof && first) CU(cudaEventRecord(D->ev[1], st));
         // K2: one launch per shared-memory bin, concurrently on side streams
@@ -868,7 +875,7 @@ int32_t whale_slices(whale_model_t m, const double* x, const double* p_leaf, dou
     CU(cudaMemcpy(m->d_x, x, P * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(m->d_pleaf, pl.data(), nn * sizeof(double), cudaMemcpyHostToDevice));
     Plan& p0 = m->plan[0];
-    LAUNCH(k_tables, 1, std::min(32, nn) * 32, 0, m->stream, m->dev, p0.dev, m->d_x, m->d_pleaf);
+    LAUNCH(k_tables, 1, std::min(32, nn) * 32, tables_smem(m, p0), m->stream, m->dev, p0.dev, m->d_x, m->d_pleaf);
     g_launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(m->stream));
@@ -921,7 +928,7 @@ int32_t whale_backtrack(whale_model_t m, whale_data_t d, int32_t n_samples, cons
     CUB(cudaMalloc((void**)&d_t, W * max_nodes * 4)); CUB(cudaMalloc((void**)&d_p, W * max_nodes * 4));
     CUB(cudaMalloc((void**)&d_stack, W * max_nodes * sizeof(int4)));
     Plan& p0 = m->plan[0];
-    LAUNCH(k_tables, 1, std::min(32, m->nn) * 32, 0, m->stream, m->dev, p0.dev, m->d_x, m->d_pleaf);
+    LAUNCH(k_tables, 1, std::min(32, m->nn) * 32, tables_smem(m, p0), m->stream, m->dev, p0.dev, m->d_x, m->d_pleaf);
     BTArgs a{m->dev, p0.dev, d->d_arena, d->d_hdr, d->d_ell, m->d_x, d_u, (long long)stride, d->F, n_samples, max_nodes,
              d_cnt, d_g, d_e, d_t, d_p, d_st, d_stack};
     LAUNCH(k_backtrack, (int)((W + 127) / 128), 128, 0, m->stream, a);
