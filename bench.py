@@ -222,6 +222,7 @@ def main():
     wall = time.perf_counter() - wall0
     launches = L.L.whale_launch_count() - launches0
     phase_cycles = L.last_phase_cycles(dh)
+    tables_cycles = L.last_tables_cycles(mh, True)
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     total_ms = float(step_ms.sum())
     last = OUT.cpu().numpy().copy()
@@ -311,7 +312,7 @@ def main():
         "roofline_hbm": {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s",
                          "frac": ach_gb / hbm_peak, "bytes_per_launch": abytes,
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-        "dp_phase_cycles_mean_max": phase_cycles,
+        "dp_phase_cycles_mean_max": phase_cycles, "tables_cycles": tables_cycles,
         "loglik_last": float(last[0]),
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -178,6 +178,10 @@ int32_t whale_last_kernel_ms(whale_data_t d, double* tables_ms, double* dp_ms, d
  * over families): [prologue, leaf phase, staging, row 1, slices, root, total, 0] */
 int32_t whale_last_phase_cycles(whale_data_t d, double* mean8, double* max8);
 
+/* SM-cycle stamps of the last k_tables launch of the model's value / full-gradient plan: [0] metadata staged,
+ * [1+L] level L done, [30] all rows written, [31] number of levels */
+int32_t whale_last_tables_cycles(whale_model_t m, int32_t with_grad, double* out32);
+
 /* measured fp64 FMA peak of the current device (dependent-free DFMA microbenchmark), TFLOP/s */
 int32_t whale_fp64_peak(double* tflops);
 

@@ -93,6 +93,14 @@ inline double shfl_down(double v, int delta) {
     (*g_wbar)[w].wait();
     return r;
 }
+inline double shfl_idx(double v, int src) {
+    const int w = threadIdx.x / 32, l = threadIdx.x % 32;
+    g_shfl[w][l] = v;
+    (*g_wbar)[w].wait();
+    const double r = g_shfl[w][src & 31];
+    (*g_wbar)[w].wait();
+    return r;
+}
 }  // namespace emu
 inline void __syncthreads() { emu::g_bar->wait(); }
 inline void __syncwarp() { (*emu::g_wbar)[threadIdx.x / 32].wait(); }

@@ -38,7 +38,8 @@ struct NodeRec {
     uint32_t ntent;
     uint32_t slot_off;  // u32-word offset (multiple of 4) of the slice-loop lane table (Slot[nslots])
     uint32_t nslots;
-    uint32_t pad0, pad1;
+    uint32_t sptr_off;  // leaf branches in shape mode (see SHAPES below): u32-word offset of sptr[C+1], else 0
+    uint32_t sent_off;  //   16-byte-entry offset of {i1 = shape id, p = coefficient}
 };
 static_assert(sizeof(NodeRec) == 48, "NodeRec must be 48 bytes");
 
@@ -56,6 +57,17 @@ struct Slot {
 static_assert(sizeof(Slot) == 8, "Slot must be 8 bytes");
 
 constexpr int MAXPLAN = 10;  // tangent plans per data handle: [0] value only, [1..] gradient (parameter chunks)
+
+// Tree shapes for the closed form of leaf branches.  On a leaf branch e every leaf clade has the same
+// family-independent sequence w•_i = leafℙ·Π_{j<=i} ϕ_j, hence by induction over src/core.jl:121-128,178-185 every
+// clade γ made of in-paralogs satisfies ℓ_i[γ] = Σ_σ C_σ[γ]·wσ_i over rooted binary tree shapes σ with |γ| leaves,
+//   wσ_i = ϕ_i wσ_{i−1} + ψ_i w^a_{i−1} w^b_{i−1}   (σ = {a, b}),     C_σ[γ] = Σ_splits p Σ_{(σ1,σ2)→σ} C_σ1[γ1] C_σ2[γ2].
+// C depends only on the CCD (packer), w only on θ (k_leafshapes).  Shapes with <= 5 leaves:
+//   0 •   1 (•,•)   2 (•,1)   3 (•,2)   4 (1,1)   5 (•,3)   6 (•,4)   7 (1,2)
+constexpr int NSHAPE = 8;
+constexpr int SHAPE_MAXLEAVES = 5;
+#define SHAPE_A {0, 0, 0, 0, 1, 0, 0, 1}
+#define SHAPE_B {0, 0, 1, 2, 1, 3, 4, 2}
 
 struct FamHdr {
     uint64_t base;           // byte offset of the blob in the arena (16-byte aligned)
@@ -111,8 +123,18 @@ struct PlanDev {  // tangent plan: which raw parameters each branch carries
     double* cx;            // [nn*Kmax]  row-1 coefficient X (WGD: 1−q+2qϵ_f ; root: (1−η)ξ/η)
     double* cy;            // [nn*Kmax]  row-1 coefficient Y (WGD: q ; root: η(1−ϵ)/ξ²)
     double* leaf;          // [nn*Kmax]  last-row value of a leaf clade on leaf branch e
+    double* shapeW;        // [nn*NSHAPE*Kmax] last-row value wσ_n of every tree shape on leaf branch e
+    double2* ls_uv;        // [tab_len] k_leafshapes scratch (projective ϵ rows of leaf nodes)
+    double2* ls_pp;        // [tab_len] k_leafshapes scratch ((ϕ, ψ) rows of leaf nodes)
     double* cond;          // [3*Kmax]   condition() per kind, components of the root
+    long long* tim;        // [32] k_tables cycle stamps (profiling aid)
 };
+
+#ifdef WHALE_EMU
+#define CLOCK64() 0LL
+#else
+#define CLOCK64() clock64()
+#endif
 
 // one-partial dual number: each lane carries the value and ITS tangent component
 struct D1 {

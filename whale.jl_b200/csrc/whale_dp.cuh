@@ -31,11 +31,7 @@ struct DPArgs {
     long long* tim;    // optional per-family phase cycle counters [F][8] (profiling aid) or nullptr
 };
 
-#ifdef WHALE_EMU
-#define CLOCK64() 0LL
-#else
-#define CLOCK64() clock64()
-#endif
+
 
 #ifdef WHALE_EMU
 #define PREFETCH_L2(p) ((void)0)
@@ -390,6 +386,22 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         if (C == 0) continue;
         const int K = s_K[e], n = s_nsl[e];
         double* fin = rows + s_roff[e];
+        if (A.skip_leaf && R.sptr_off) {
+            // closed form over tree shapes: ℓ_n[γ] = Σ_σ C_σ[γ]·wσ_n  (C from the packer, w from k_leafshapes)
+            const uint32_t* sptr = words + R.sptr_off;
+            const Ent* sent = ents + R.sent_off;
+            const double* W = PL.shapeW + (size_t)e * NSHAPE * Kmax;
+            for (int i = lane; i < C * K; i += 32) {
+                const int c = i / K, k = i - c * K;
+                double v = 0.0;
+                for (uint32_t t = sptr[c]; t < sptr[c + 1]; t++) {
+                    const Ent en = sent[t];
+                    v = fma(en.p, W[en.i1 * Kmax + k], v);
+                }
+                fin[i] = v;
+            }
+            continue;
+        }
         if (R.nslots > 32 && !(R.nonleaf == 0 && A.skip_leaf)) continue;  // heavy branch: whole CTA, below
         if (R.nonleaf == 0 && A.skip_leaf) {  // family-independent: ℓ_n = leafℙ·Πϕ_i from k_tables
             for (int i = lane; i < C * K; i += 32) fin[i] = PL.leaf[e * Kmax + (i % K)];
@@ -420,7 +432,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         const int e = M.leafnodes[li];
         const NodeRec R = nrec[e];
         const int C = (int)R.C;
-        if (C == 0 || R.nslots <= 32 || (R.nonleaf == 0 && A.skip_leaf)) continue;
+        if (C == 0 || R.nslots <= 32 || (R.nonleaf == 0 && A.skip_leaf) || (A.skip_leaf && R.sptr_off)) continue;
         const int K = s_K[e], n = s_nsl[e];
         double* fin = rows + s_roff[e];
         double* ellp = ell_of(e);

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const d
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const double NaN = __longlong_as_double(0x7ff8000000000000LL);
     EXTERN_SHARED(tsm);
+    const long long tk0 = CLOCK64();
     const int nn = M.nn, Kmax = PL.Kmax, P = M.n_params;
     double* sd = reinterpret_cast<double*>(tsm);                 // dt, leafP, pleaf [nn each], x [P]
     int* si = reinterpret_cast<int*>(sd + 3 * nn + P);           // 9 arrays [nn], lvl_off [nlvl+1], lvl_nodes [nn]
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const d
     __syncthreads();
     TabMeta T{si, si + nn, si + 2 * nn, si + 3 * nn, si + 4 * nn, si + 5 * nn, si + 6 * nn, si + 7 * nn, si + 8 * nn,
               si + 9 * nn, si + 9 * nn + M.nlvl + 1, sd, sd + nn, sd + 2 * nn, sd + 3 * nn, s_cm, s_ro};
+    if (threadIdx.x == 0) PL.tim[0] = CLOCK64() - tk0;
     // ---- phase A: per level, one warp per node, lanes over components; division-free chain ----
     for (int L = 0; L < M.nlvl; L++) {
         const int n0 = T.lvl_off[L], n1 = T.lvl_off[L + 1];
@@ -140,32 +142,115 @@ __global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const d
             }
         }
         __syncthreads();
+        if (threadIdx.x == 0 && L < 28) PL.tim[1 + L] = CLOCK64() - tk0;
     }
-    // ---- phase B: every row of every node in parallel ----
-    for (int e = 0; e < M.nn; e++) {
-        const int K = T.K[e], n = T.nsl[e];
+    // ---- phase B: every (node, row, component) of the tables in parallel (one flat index space) ----
+    const int total = T.toff[nn - 1] + (T.nsl[nn - 1] + 1) * T.K[nn - 1];  // toff is ascending in node index
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        int lo = 0, hi = nn - 1;  // node e with toff[e] <= t < toff[e+1]
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (T.toff[mid] <= t) lo = mid; else hi = mid - 1;
+        }
+        const int e = lo, K = T.K[e];
+        const int idx = t - T.toff[e];
+        const int i = idx / K, k = idx - i * K;
         const double2* uvrow = PL.uv + T.toff[e];
-        double* erow = PL.eps + T.toff[e];
-        double2* prow = PL.pp + T.toff[e];
-        for (int idx = threadIdx.x; idx < (n + 1) * K; idx += blockDim.x) {
-            const int i = idx / K, k = idx - i * K;
-            const double2 w0 = uvrow[(size_t)i * K], wk = uvrow[(size_t)i * K + k];
-            const D1 u = mk(w0.x, k == 0 ? 0.0 : wk.x), v = mk(w0.y, k == 0 ? 0.0 : wk.y);
-            const D1 ep = u / v;
-            erow[idx] = k == 0 ? ep.v : ep.d;
-            if (i == 0) {
-                prow[idx] = make_double2(k == 0 ? 1.0 : 0.0, k == 0 ? 1.0 : 0.0);  // ϕ_1 = 1 (src/model.jl:171)
-                continue;
-            }
-            const double2 p0 = uvrow[(size_t)(i - 1) * K], pk = uvrow[(size_t)(i - 1) * K + k];
-            const D1 vp = mk(p0.y, k == 0 ? 0.0 : pk.y);
-            const D1 a = mk(PL.ab[(e * PL.Kmax) * 2], k == 0 ? 0.0 : PL.ab[(e * PL.Kmax + k) * 2]);
-            const D1 b = mk(PL.ab[(e * PL.Kmax) * 2 + 1], k == 0 ? 0.0 : PL.ab[(e * PL.Kmax + k) * 2 + 1]);
-            const D1 g = (1.0 - a) * (1.0 - b);
-            const D1 r = vp / v;  // 1 / (1 − βϵ_{i−1})
-            const D1 phi = g * (r * r);
-            const D1 psi = (g * b) * (r * r * r);
-            prow[idx] = make_double2(k == 0 ? phi.v : phi.d, k == 0 ? psi.v : psi.d);
+        const double2 w0 = uvrow[(size_t)i * K], wk = uvrow[(size_t)i * K + k];
+        const D1 u = mk(w0.x, k == 0 ? 0.0 : wk.x), v = mk(w0.y, k == 0 ? 0.0 : wk.y);
+        const D1 ep = u / v;
+        PL.eps[t] = k == 0 ? ep.v : ep.d;
+        if (i == 0) {
+            PL.pp[t] = make_double2(k == 0 ? 1.0 : 0.0, k == 0 ? 1.0 : 0.0);  // ϕ_1 = 1 (src/model.jl:171)
+            continue;
+        }
+        const double2 p0 = uvrow[(size_t)(i - 1) * K], pk = uvrow[(size_t)(i - 1) * K + k];
+        const D1 vp = mk(p0.y, k == 0 ? 0.0 : pk.y);
+        const D1 a = mk(PL.ab[(e * PL.Kmax) * 2], k == 0 ? 0.0 : PL.ab[(e * PL.Kmax + k) * 2]);
+        const D1 b = mk(PL.ab[(e * PL.Kmax) * 2 + 1], k == 0 ? 0.0 : PL.ab[(e * PL.Kmax + k) * 2 + 1]);
+        const D1 g = (1.0 - a) * (1.0 - b);
+        const D1 r = vp / v;  // 1 / (1 − βϵ_{i−1})
+        const D1 phi = g * (r * r);
+        const D1 psi = (g * b) * (r * r * r);
+        PL.pp[t] = make_double2(k == 0 ? phi.v : phi.d, k == 0 ? psi.v : psi.d);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { PL.tim[30] = CLOCK64() - tk0; PL.tim[31] = M.nlvl; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_leafshapes — last-row values wσ_n of the tree shapes on every leaf branch (see SHAPES in whale_common.cuh).
+// One warp per leaf node, lanes = (shape σ, component k).  Runs concurrently with k_tables on a side stream:
+// it recomputes its own branch's slice rows (a leaf branch depends on nothing below it).
+// ---------------------------------------------------------------------------------------------------------
+#ifdef WHALE_EMU
+#define SHFL_IDX(v, src) emu::shfl_idx(v, src)
+#else
+#define SHFL_IDX(v, src) __shfl_sync(0xffffffffu, v, src)
+#endif
+
+__global__ void __launch_bounds__(32) k_leafshapes(ModelDev M, PlanDev PL, const double* __restrict__ x,
+                                                   const double* __restrict__ pleaf) {
+    const int e = M.leafnodes[blockIdx.x];
+    const int lane = threadIdx.x;
+    const int K = PL.K[e], n = M.nsl[e];
+    const int sh = lane / K, k = lane - sh * K;
+    const bool on = sh < NSHAPE;  // 8·K <= 32 lanes (leaf branches have K <= 3)
+    const double NaN = __longlong_as_double(0x7ff8000000000000LL);
+    const unsigned role = (k == 0 || !on) ? 0u : PL.role[e * PL.Kmax + k];
+    const int ls = M.lam_slot[e], ms = M.mu_slot[e];
+    const double lv = ls < 0 ? NaN : (M.log_scale ? exp(x[ls]) : x[ls]);
+    const double mv = ms < 0 ? NaN : (M.log_scale ? exp(x[ms]) : x[ms]);
+    const D1 lam = mk(lv, (role & 1u) ? (M.log_scale ? lv : 1.0) : 0.0);
+    const D1 mu = mk(mv, (role & 2u) ? (M.log_scale ? mv : 1.0) : 0.0);
+    D1 a = mk(0.0), b = mk(0.0);
+    if (n > 0) {
+        const double t = M.dt[e];
+        if (fabs(lam.v - mu.v) <= 1e-6) a = (lam * mk(t)) / (1.0 + lam * mk(t));
+        else { const D1 ex = dexp(mk(t) * (lam - mu)); a = mu * (ex - 1.0) / (lam * ex - mu); }
+        b = (lam / mu) * a;
+    }
+    double2* uv = PL.ls_uv + PL.toff[e];
+    double2* pp = PL.ls_pp + PL.toff[e];
+    __shared__ double s_ab[8][4];  // (α, β) value / tangent per component, from the lanes of shape 0
+    // pass 1: the projective chain (lanes of shape 0 only), rows to scratch
+    if (sh == 0) {
+        s_ab[k][0] = a.v; s_ab[k][1] = a.d; s_ab[k][2] = b.v; s_ab[k][3] = b.d;
+        D1 u = mk(pleaf ? pleaf[e] : 0.0), v = mk(1.0);
+        const D1 c = (1.0 - a) - b;
+        uv[k] = k == 0 ? make_double2(u.v, v.v) : make_double2(u.d, v.d);
+        for (int i = 1; i <= n; i++) {
+            const D1 un = c * u + a * v, vn = v - b * u;
+            u = un; v = vn;
+            uv[(size_t)i * K + k] = k == 0 ? make_double2(u.v, v.v) : make_double2(u.d, v.d);
         }
     }
+    __syncwarp();
+    // pass 2: ϕ_i, ψ_i of every row in parallel
+    for (int idx = lane; idx < n * K; idx += 32) {
+        const int i = 1 + idx / K, kk = idx - (i - 1) * K;
+        const D1 aa = mk(s_ab[0][0], kk == 0 ? 0.0 : s_ab[kk][1]), bb = mk(s_ab[0][2], kk == 0 ? 0.0 : s_ab[kk][3]);
+        const D1 gg = (1.0 - aa) * (1.0 - bb);
+        const double2 w0 = uv[(size_t)i * K], wk = uv[(size_t)i * K + kk];
+        const double2 p0 = uv[(size_t)(i - 1) * K], pk = uv[(size_t)(i - 1) * K + kk];
+        const D1 v = mk(w0.y, kk == 0 ? 0.0 : wk.y), vp = mk(p0.y, kk == 0 ? 0.0 : pk.y);
+        const D1 r = vp / v;
+        const D1 phi = gg * (r * r), psi = (gg * bb) * (r * r * r);
+        pp[(size_t)i * K + kk] = make_double2(kk == 0 ? phi.v : phi.d, kk == 0 ? psi.v : psi.d);
+    }
+    __syncwarp();
+    // pass 3: the shape sequences, all shapes in lock-step (operands of shape σ come from the lanes of a, b)
+    const int SA[NSHAPE] = SHAPE_A, SB[NSHAPE] = SHAPE_B;
+    const int la_ = on ? SA[sh] * K + k : lane, lb_ = on ? SB[sh] * K + k : lane;
+    D1 w = mk((on && sh == 0) ? M.leafP[e] : 0.0, 0.0);
+    for (int i = 1; i <= n; i++) {
+        const double2 q0 = pp[(size_t)i * K], qk = pp[(size_t)i * K + (on ? k : 0)];
+        const D1 phi = mk(q0.x, k == 0 ? 0.0 : qk.x), psi = mk(q0.y, k == 0 ? 0.0 : qk.y);
+        const D1 wa = mk(SHFL_IDX(w.v, la_), SHFL_IDX(w.d, la_));
+        const D1 wb = mk(SHFL_IDX(w.v, lb_), SHFL_IDX(w.d, lb_));
+        D1 nw = phi * w;
+        if (on && sh > 0) nw = nw + psi * (wa * wb);
+        w = nw;
+    }
+    if (on) PL.shapeW[((size_t)e * NSHAPE + sh) * PL.Kmax + k] = k == 0 ? w.v : w.d;
 }

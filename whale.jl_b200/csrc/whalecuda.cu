@@ -142,7 +142,8 @@ struct whale_data {
     size_t out_total = 0;
     cudaStream_t side[MAX_BINS] = {};
     cudaEvent_t ev_join[MAX_BINS] = {};
-    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_tab = nullptr;
+    cudaStream_t side_tab = nullptr;
     std::vector<unsigned char> arena_host;  // packing buffer (released after upload)
     size_t arena_bytes = 0;
     unsigned char* d_arena = nullptr;
@@ -231,21 +232,27 @@ static cudaError_t upload_plan(Plan& pl, int nn) {
     if ((e = upload(pl.toff, &dtoff)) != cudaSuccess) return e;
     if ((e = upload(pl.cmap, &dcmap)) != cudaSuccess) return e;
     if ((e = upload(pl.role, &drole)) != cudaSuccess) return e;
-    double *eps, *cx, *cy, *leaf, *cond, *ab;
-    double2 *pp, *uv;
+    double *eps, *cx, *cy, *leaf, *cond, *ab, *shapeW;
+    double2 *pp, *uv, *lsuv, *lspp;
+    long long* tim;
+    if ((e = cudaMalloc((void**)&tim, 32 * sizeof(long long))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&eps, std::max<size_t>(pl.tab_len, 1) * sizeof(double))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&pp, std::max<size_t>(pl.tab_len, 1) * sizeof(double2))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&uv, std::max<size_t>(pl.tab_len, 1) * sizeof(double2))) != cudaSuccess) return e;
     size_t nk = (size_t)nn * pl.Kmax * sizeof(double);
     if ((e = cudaMalloc((void**)&ab, 2 * nk)) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&shapeW, NSHAPE * nk)) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&lsuv, std::max<size_t>(pl.tab_len, 1) * sizeof(double2))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&lspp, std::max<size_t>(pl.tab_len, 1) * sizeof(double2))) != cudaSuccess) return e;
+    cudaMemset(shapeW, 0, NSHAPE * nk);
     if ((e = cudaMalloc((void**)&cx, nk)) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&cy, nk)) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&leaf, nk)) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&cond, 3 * pl.Kmax * sizeof(double))) != cudaSuccess) return e;
     cudaMemset(cx, 0, nk); cudaMemset(cy, 0, nk); cudaMemset(leaf, 0, nk);
     cudaMemset(cond, 0, 3 * pl.Kmax * sizeof(double));
-    pl.owned = {dK, dact, dtoff, dcmap, drole, eps, pp, uv, ab, cx, cy, leaf, cond};
-    pl.dev = PlanDev{pl.Kmax, dK, dact, dcmap, drole, dtoff, eps, pp, uv, ab, cx, cy, leaf, cond};
+    pl.owned = {dK, dact, dtoff, dcmap, drole, eps, pp, uv, ab, cx, cy, leaf, shapeW, lsuv, lspp, cond, tim};
+    pl.dev = PlanDev{pl.Kmax, dK, dact, dcmap, drole, dtoff, eps, pp, uv, ab, cx, cy, leaf, shapeW, lsuv, lspp, cond, tim};
     return cudaSuccess;
 }
 
@@ -549,6 +556,46 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
                 wordsv.resize(w0 + 2 * slots.size());
                 if (!slots.empty()) memcpy(wordsv.data() + w0, slots.data(), slots.size() * sizeof(Slot));
             }
+            // (1c) leaf branch in closed form: coefficients C_σ[γ] over tree shapes (see SHAPES in whale_common.cuh)
+            if (kind == WHALE_LEAF && nonleaf > 0) {
+                int maxsz = 0;
+                for (int j = 0; j < C; j++) maxsz = std::max(maxsz, (int)nleaf[d->compat[coff[e] + j]]);
+                if (maxsz <= SHAPE_MAXLEAVES) {
+                    static const int SA[NSHAPE] = SHAPE_A, SB[NSHAPE] = SHAPE_B;
+                    auto compose = [&](int s1, int s2) -> int {
+                        const int lo = std::min(s1, s2), hi = std::max(s1, s2);
+                        for (int sg = 1; sg < NSHAPE; sg++) if (SA[sg] == lo && SB[sg] == hi) return sg;
+                        return -1;
+                    };
+                    std::vector<double> coef((size_t)C * NSHAPE, 0.0);
+                    const uint32_t* dp = wordsv.data() + R.dptr_off;
+                    for (int j = 0; j < C; j++) {
+                        if (dp[j + 1] == dp[j]) { if (nleaf[d->compat[coff[e] + j]] == 1) coef[(size_t)j * NSHAPE] = 1.0; continue; }
+                        for (uint32_t t = dp[j]; t < dp[j + 1]; t++) {
+                            const Ent& en = entsv[R.dent_off + t];
+                            for (int s1 = 0; s1 < NSHAPE; s1++) {
+                                const double c1 = coef[(size_t)en.i1 * NSHAPE + s1];
+                                if (c1 == 0.0) continue;
+                                for (int s2 = 0; s2 < NSHAPE; s2++) {
+                                    const double c2 = coef[(size_t)en.i2 * NSHAPE + s2];
+                                    if (c2 == 0.0) continue;
+                                    const int sg = compose(s1, s2);
+                                    if (sg >= 0) coef[(size_t)j * NSHAPE + sg] += en.p * c1 * c2;
+                                }
+                            }
+                        }
+                    }
+                    pad4(wordsv);
+                    R.sptr_off = (uint32_t)wordsv.size();
+                    R.sent_off = (uint32_t)entsv.size();
+                    for (int j = 0; j < C; j++) {
+                        wordsv.push_back((uint32_t)entsv.size() - R.sent_off);
+                        for (int sg = 0; sg < NSHAPE; sg++)
+                            if (coef[(size_t)j * NSHAPE + sg] != 0.0) entsv.push_back(Ent{(uint16_t)sg, 0, 0u, coef[(size_t)j * NSHAPE + sg]});
+                    }
+                    wordsv.push_back((uint32_t)entsv.size() - R.sent_off);
+                }
+            }
             // (2) speciation terms at row 1 (src/core.jl:160-170), Πloss child indices (:172-176), root levels
             pad4(wordsv);
             R.tptr_off = (uint32_t)wordsv.size();
@@ -610,6 +657,7 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
             R.dptr_off += (uint32_t)(words_at / 4);
             R.tptr_off += (uint32_t)(words_at / 4);
             R.slot_off += (uint32_t)(words_at / 4);
+            if (R.sptr_off) { R.sptr_off += (uint32_t)(words_at / 4); R.sent_off += (uint32_t)(ents_at / 16); }
             R.dent_off += (uint32_t)(ents_at / 16);
             R.tent_off += (uint32_t)(ents_at / 16);
         }
@@ -716,6 +764,8 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
         CU(cudaEventCreateWithFlags(&D->ev_join[i], cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&D->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&D->ev_tab, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&D->side_tab, cudaStreamNonBlocking));
     *out = D;
     return WHALE_OK;
 }
@@ -732,6 +782,8 @@ int32_t whale_data_destroy(whale_data_t d) {
         if (d->ev_join[i]) cudaEventDestroy(d->ev_join[i]);
     }
     if (d->ev_fork) cudaEventDestroy(d->ev_fork);
+    if (d->ev_tab) cudaEventDestroy(d->ev_tab);
+    if (d->side_tab) cudaStreamDestroy(d->side_tab);
     cudaFree(d->d_ell); cudaFree(d->d_tim);
     for (int i = 0; i < 4; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     delete d;
@@ -775,9 +827,17 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
         Plan& pl = *D->plans[g];
         const bool first = g == g0;
         if (prof && first) CU(cudaEventRecord(D->ev[0], st));
-        // K1: slice tables of this plan
-        LAUNCH(k_tables, 1, std::min(32, std::max(1, nn)) * 32, tables_smem(m, pl), st, m->dev, pl.dev, d_x, m->d_pleaf);
+        // K1: slice tables of this plan; the leaf-branch shape tables run beside it on a side stream
+        if (!keep && !m->leafnodes.empty()) {
+            CU(cudaEventRecord(D->ev_fork, st));
+            CU(cudaStreamWaitEvent(D->side_tab, D->ev_fork, 0));
+            LAUNCH(k_leafshapes, (int)m->leafnodes.size(), 32, 0, D->side_tab, m->dev, pl.dev, d_x, m->d_pleaf);
+            CU(cudaEventRecord(D->ev_tab, D->side_tab));
+            g_launches++;
+        }
+        LAUNCH(k_tables, 1, 1024, tables_smem(m, pl), st, m->dev, pl.dev, d_x, m->d_pleaf);
         g_launches++;
+        if (!keep && !m->leafnodes.empty()) CU(cudaStreamWaitEvent(st, D->ev_tab, 0));
         if (prof && first) CU(cudaEventRecord(D->ev[1], st));
         // K2: one launch per shared-memory bin, concurrently on side streams
         const std::vector<Bin>& bins = D->bins[g];
@@ -990,6 +1050,16 @@ int32_t whale_last_phase_cycles(whale_data_t d, double* mean8, double* max8) {
         mean8[j] = s / d->F;
         max8[j] = mx;
     }
+    return WHALE_OK;
+}
+
+int32_t whale_last_tables_cycles(whale_model_t m, int32_t with_grad, double* out32) {
+    if (!m || !out32) return fail(WHALE_ERR_ARG, "null argument");
+    CU(cudaSetDevice(m->device));
+    CU(cudaDeviceSynchronize());
+    long long h[32];
+    CU(cudaMemcpy(h, m->plan[with_grad ? 1 : 0].dev.tim, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 32; i++) out32[i] = (double)h[i];
     return WHALE_OK;
 }
 

@@ -22,7 +22,7 @@ SYMBOLS = ["whale_version", "whale_last_error", "whale_device_count", "whale_set
            "whale_model_destroy", "whale_data_create", "whale_data_destroy", "whale_data_nfam",
            "whale_data_arena_bytes", "whale_data_arena_dump", "whale_logpdf_grad", "whale_logpdf_grad_async",
            "whale_slices", "whale_ell_size", "whale_ell_get", "whale_backtrack", "whale_launch_count",
-           "whale_work_estimate", "whale_last_kernel_ms", "whale_last_phase_cycles", "whale_fp64_peak"]
+           "whale_work_estimate", "whale_last_kernel_ms", "whale_last_phase_cycles", "whale_last_tables_cycles", "whale_fp64_peak"]
 
 
 class ModelDesc(C.Structure):
@@ -84,6 +84,7 @@ class Lib:
         L.whale_fp64_peak.argtypes = [f64p]
         L.whale_last_kernel_ms.argtypes = [vp, f64p, f64p, f64p]
         L.whale_last_phase_cycles.argtypes = [vp, f64p, f64p]
+        L.whale_last_tables_cycles.argtypes = [vp, C.c_int32, f64p]
 
     def check(self, rc):
         if rc != 0:
@@ -181,6 +182,12 @@ class Lib:
         self.check(self.L.whale_last_phase_cycles(dh, _ptr(mean, f64p), _ptr(mx, f64p)))
         names = ["prologue", "leaf_phase", "staging", "row1", "slices", "root", "total"]
         return {n: (float(mean[i]), float(mx[i])) for i, n in enumerate(names)}
+
+    def last_tables_cycles(self, mh, with_grad=True):
+        out = np.zeros(32)
+        self.check(self.L.whale_last_tables_cycles(mh, 1 if with_grad else 0, _ptr(out, f64p)))
+        n = int(out[31])
+        return {"meta": out[0], "levels": out[1:1 + n].tolist(), "total": out[30]}
 
     def logpdf_grad_async(self, mh, dh, d_x_ptr, condition, flags, d_out_ptr, stream_ptr):
         """Device-resident evaluation enqueued on `stream_ptr` (a cudaStream_t as int); not synchronised."""
