@@ -164,10 +164,8 @@ constexpr int KMAX_FUSED = 8;
 
 #ifdef WHALE_EMU
 #define SHFL_DOWN(v, d) emu::shfl_down(v, d)
-#define SHFL_XOR(v, d) emu::shfl_idx(v, (int)(threadIdx.x % 32) ^ (d))
 #else
 #define SHFL_DOWN(v, d) __shfl_down_sync(0xffffffffu, v, d)
-#define SHFL_XOR(v, d) __shfl_xor_sync(0xffffffffu, v, d)
 #endif
 
 template <int K>
@@ -616,11 +614,9 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
                 terms<true>(g_tents, ua, ua + nb, finF, KF, mapF, finG, KG, mapG, K, prod + na, cap, tid, NT);
                 __syncthreads();
             }
-            constexpr uint32_t HEAVY = 48;  // clades with more terms than this are summed by a whole warp below
             if (on)
                 for (int c = c0 + grp; c < c1; c += GP) {
                     double a0 = 0.0, ak = 0.0, b0 = 0.0, bk = 0.0, l0, lk;
-                    if (fits && K <= 32 && (s_dptr[c + 1] - s_dptr[c]) + (s_tptr[c + 1] - s_tptr[c]) > HEAVY) continue;
                     if (fits) {
                         cellsum(prod, cap, k, s_dptr[c] - ta, s_dptr[c + 1] - ta, a0, ak);
                         cellsum(prod, cap, k, na + s_tptr[c] - ua, na + s_tptr[c + 1] - ua, b0, bk);
@@ -648,39 +644,6 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
                     fin[c * K + k] = r;
                     if (ellp && k == 0) ellp[c] = r;
                 }
-            if (fits && K <= 32) {
-                // heavy clades (the ubiquitous clade has ~Γ/2 splits): one warp each, lanes stride over the products,
-                // shuffle-reduce per component, lane kk finishes component kk
-                int hc = 0;
-                for (int c = c0; c < c1; c++) {
-                    const uint32_t ea = s_dptr[c + 1] - s_dptr[c], eb = s_tptr[c + 1] - s_tptr[c];
-                    if (ea + eb <= HEAVY) continue;
-                    if ((hc++ % NW) != warp) continue;
-                    const double* pa = prod + (s_dptr[c] - ta);
-                    const double* pb = prod + na + (s_tptr[c] - ua);
-                    double a0 = 0.0, b0 = 0.0, amy = 0.0, bmy = 0.0;
-                    for (int kk = 0; kk < K; kk++) {
-                        double sa = 0.0, sb = 0.0;
-                        for (uint32_t t = lane; t < ea; t += 32) sa += pa[(size_t)kk * cap + t];
-                        for (uint32_t t = lane; t < eb; t += 32) sb += pb[(size_t)kk * cap + t];
-                        for (int st = 16; st > 0; st >>= 1) { sa += SHFL_XOR(sa, st); sb += SHFL_XOR(sb, st); }
-                        if (kk == 0) { a0 = sa; b0 = sb; }
-                        if (kk == lane) { amy = sa; bmy = sb; }
-                    }
-                    if (lane < K) {
-                        const int kk = lane;
-                        const double mm = kk == 0 ? 0.0 : 1.0;
-                        const int kf2 = mapF[kk], kg2 = mapG[kk];
-                        const double efk2 = (kk > 0 && kf2 >= 0) ? epsF[kf2] : 0.0, egk2 = (kk > 0 && kg2 >= 0) ? epsG[kg2] : 0.0;
-                        double l0, lk;
-                        loss_term(s_lossF[c], s_lossG[c], finF, KF, kf2, finG, KG, kg2, ef0, efk2, eg0, egk2, mm, l0, lk);
-                        const double u0 = b0 + l0, uk = kk == 0 ? u0 : bmy + lk;
-                        const double r = cx0 * amy + cy0 * uk + mm * (PL.cx[e * Kmax + kk] * a0 + PL.cy[e * Kmax + kk] * u0);
-                        fin[c * K + kk] = r;
-                        if (ellp && kk == 0) ellp[c] = r;
-                    }
-                }
-            }
             __syncthreads();
         }
         if (tid < K) {  // log L and its gradient (src/core.jl:35-36)

@@ -106,21 +106,19 @@ static int env_int(const char* name, int dflt) {
     return s ? atoi(s) : dflt;
 }
 static int dp_nt() {
-    static int nt = [] { int v = env_int("WHALE_NT", 128); return (v == 64 || v == 96 || v == 256) ? v : 128; }();
+    static int nt = [] { int v = env_int("WHALE_NT", 128); return (v == 64 || v == 256) ? v : 128; }();
     return nt;
 }
 static int dp_minb() {  // resident CTAs per SM the register cap is chosen for
     static int mb = [] {
         const int nt = dp_nt(), v = env_int("WHALE_MINB", 0);
         if (nt == 64) return 12;
-        if (nt == 96) return 7;
         if (nt == 256) return 2;
-        (void)v;
-        return 5;
+        return (v == 6 || v == 7) ? v : 5;
     }();
     return mb;
 }
-#define DP_VARIANTS(X) X(64, 12, 6) X(64, 12, 8) X(96, 7, 6) X(96, 7, 8) X(128, 5, 6) X(128, 5, 8) X(256, 2, 6) X(256, 2, 8)
+#define DP_VARIANTS(X) X(64, 12, 6) X(64, 12, 8) X(128, 5, 6) X(128, 6, 6) X(128, 7, 6) X(128, 5, 8) X(256, 2, 6) X(256, 2, 8)
 constexpr int MAX_BINS = 8;
 struct Bin {
     int off, count;
@@ -543,35 +541,15 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
                     order.push_back({-gl, j});
                 }
                 std::stable_sort(order.begin(), order.end());
-                // 32-lane blocks (block b is run by warp b % NW in pass b / NW): teams go, largest first, to the
-                // least-loaded block with room, so the shuffle reductions of heavy clades spread over the warps
-                // instead of piling up in the first one; inside a block teams stay sorted by size (aligned, and
-                // the block's first lane carries its largest team)
-                size_t lanes_total = 0;
-                for (int j = 0; j < C; j++) lanes_total += (size_t)1 << glogs[j];
-                std::vector<std::vector<int>> blk((lanes_total + 31) / 32);
-                std::vector<int> load(blk.size(), 0);
-                for (auto& oc : order) {
-                    const int G = 1 << glogs[oc.second];
-                    int best = -1;
-                    for (size_t bi = 0; bi < blk.size(); bi++)
-                        if (load[bi] + G <= 32 && (best < 0 || load[bi] < load[best])) best = (int)bi;
-                    if (best < 0) { blk.emplace_back(); load.push_back(0); best = (int)blk.size() - 1; }
-                    blk[best].push_back(oc.second);
-                    load[best] += G;
-                }
                 std::vector<Slot> slots;
-                for (size_t bi = 0; bi < blk.size(); bi++) {
-                    for (int j : blk[bi]) {
-                        const int gl = glogs[j], G = 1 << gl;
-                        const uint32_t E = dp[j + 1] - dp[j], first = dp[j];
-                        for (int l = 0; l < G; l++) {
-                            const uint32_t cnt = (uint32_t)l < E ? (E - l + G - 1) / G : 0;
-                            if (cnt > 255) { delete D; return fail(WHALE_ERR_CAPACITY, "family %d node %d: clade with %u terms", f, e, E); }
-                            slots.push_back(Slot{(uint16_t)j, (uint8_t)gl, (uint8_t)cnt, (uint16_t)(first + l), (uint16_t)G});
-                        }
+                for (auto& oc : order) {
+                    const int j = oc.second, gl = glogs[j], G = 1 << gl;
+                    const uint32_t E = dp[j + 1] - dp[j], first = dp[j];
+                    for (int l = 0; l < G; l++) {
+                        const uint32_t cnt = (uint32_t)l < E ? (E - l + G - 1) / G : 0;
+                        if (cnt > 255) { delete D; return fail(WHALE_ERR_CAPACITY, "family %d node %d: clade with %u terms", f, e, E); }
+                        slots.push_back(Slot{(uint16_t)j, (uint8_t)gl, (uint8_t)cnt, (uint16_t)(first + l), (uint16_t)G});
                     }
-                    while (slots.size() < (bi + 1) * 32) slots.push_back(Slot{0xFFFF, 0, 0, 0, 1});  // idle lanes
                 }
                 R.nslots = (uint32_t)slots.size();
                 const size_t w0 = wordsv.size();
@@ -868,7 +846,7 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
         DPArgs a{m->dev, pl.dev, D->d_arena, D->d_hdr, D->d_perm[g], out_fam, (keep && first) ? D->d_ell : nullptr, (int)g,
                  keep ? 0 : 1, (prof && first) ? D->d_tim : nullptr};
         const int KC = pl.Kmax <= 6 ? 6 : 8;
-        const int MB = dp_minb();
+        const int MB = (NT == 128 && KC == 8) ? 5 : dp_minb();
         auto launch_bin = [&](const Bin& b, cudaStream_t s) {
 #define LAUNCHV(NTV, MBV, KCV) if (NT == NTV && MB == MBV && KC == KCV) LAUNCH((k_dp<NTV, MBV, KCV>), b.count, NTV, b.smem, s, a, b.off);
             DP_VARIANTS(LAUNCHV)
