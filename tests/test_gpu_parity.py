@@ -181,3 +181,30 @@ def test_backtrack_api_and_invariants(L, tmp_path):
             assert sorted(term[:, 0].tolist()) == list(range(nl))
             assert np.all(t[1:, 3] < np.arange(1, len(t))) and t[0, 3] == -1
             assert np.all(t[t[:, 0] < 0, 2] == 0)
+
+
+def test_mixture_modelarray_and_track(L, tmp_path):
+    """src/core.jl:66-79 (mixture / ModelArray on top of per-family device outputs) against the oracle, and the
+    `track` driver loop (src/track.jl:30-63)."""
+    from oracle import whale_oracle as wo
+    d = synth.generate(str(tmp_path / "mix"), 6, seed=11)
+    tree = synth.c1_species_tree
+    comps = [W.WhaleModel(W.ConstantDLWGD(lam=l, mu=m, q=[0.2, 0.1], eta=0.67), tree(), 0.05) for l, m in
+             ((0.1, 0.2), (0.4, 0.3))]
+    ccd = W.read_ale(d, comps[0])
+    for c in comps:
+        W.set_probe(c, ccd[0])
+    got = W.logpdf_mixture(comps, [0.3, 0.7], ccd)
+    ocomps = [wo.WhaleModel(wo.ConstantDLWGD(lam=l, mu=m, q=[0.2, 0.1], eta=0.67), wo.c1_tree(), 0.05) for l, m in
+              ((0.1, 0.2), (0.4, 0.3))]
+    occd = wo.read_ale(d, ocomps[0])
+    M = np.array([[wo.logpdf(om, x) + np.log(p) - wo.condition(om) for om, p in zip(ocomps, (0.3, 0.7))] for x in occd])
+    want = float(np.sum(np.log(np.exp(M - M.max(1, keepdims=True)).sum(1)) + M.max(1)))
+    assert got == pytest.approx(want, rel=1e-9)
+    assert W.condition(comps[0]) == pytest.approx(wo.condition(ocomps[0]), rel=1e-9)
+    ma = W.logpdf_modelarray([comps[i % 2] for i in range(6)], ccd)
+    assert ma == pytest.approx(sum(wo.logpdf(ocomps[i % 2], occd[i]) for i in range(6)), rel=1e-9)
+    post = [dict(lam=0.15, mu=0.2, q=[0.1, 0.3], eta=0.7), dict(lam=0.3, mu=0.25, q=[0.5, 0.05], eta=0.6)]
+    trees = W.track(comps[0], ccd, post, 4, seed=3)
+    assert len(trees) == 6 and all(len(t) == 4 for t in trees)
+    assert all(t[0][0, 3] == -1 for t in trees)

@@ -124,3 +124,65 @@ def backtrack(wm: WhaleModel, x, n_samples: int = 1, uniforms=None, seed=None, m
         raise _lib.WhaleCudaError(3, "backtrack: node buffer or uniform stream too small (raise max_nodes / stride)")
     out = [[nodes[f, s, :cnt[f, s]].copy() for s in range(n_samples)] for f in range(F)]
     return out[0] if single else out
+
+
+def logpdf_mixture(components, weights, xs) -> float:
+    """`logpdf(mm::MixtureModel{…,<:WhaleModel}, xs)` (src/core.jl:66-76): per component j the per-family
+    unconditioned ℓ_ij from the device, plus log p_j − condition(component j); then Σ_i logsumexp_j."""
+    weights = np.asarray(weights, dtype=np.float64)
+    cols = []
+    for wm, pj in zip(components, weights):
+        lf, _ = logpdf_per_family(wm, xs)
+        cols.append(lf + np.log(pj) - condition(wm))
+    M = np.stack(cols, axis=1)
+    mx = M.max(axis=1, keepdims=True)
+    mx = np.where(np.isfinite(mx), mx, 0.0)
+    tot = float(np.sum(mx[:, 0] + np.log(np.exp(M - mx).sum(axis=1))))
+    return tot if np.isfinite(tot) else -np.inf
+
+
+def logpdf_modelarray(models, xs) -> float:
+    """`logpdf(m::ModelArray, xs)` (src/core.jl:78-79): family i under its own model i (unconditioned single-CCD
+    likelihoods, summed)."""
+    return float(sum(logpdf(m, x) for m, x in zip(models, xs)))
+
+
+def condition(wm: WhaleModel) -> float:
+    """`condition(wm)` (src/condition.jl:11-29) evaluated on the device's slice tables: the difference between
+    the unconditioned and the conditioned batch likelihood of any one family."""
+    if CONDITIONS[wm.condition] == 0:
+        return 0.0
+    probe = getattr(wm, "_probe", None)
+    if probe is None:
+        raise ValueError("condition(wm) needs a probe family: call set_probe(wm, ccd) once (any CCD of the model)")
+    xs, _ = _as_vector(probe)
+    mh, dh = _data_handle(wm, xs)
+    L = _lib.get()
+    a = L.logpdf_grad(mh, dh, wm.x(), wm.p_leaf(), 0)[0]
+    b = L.logpdf_grad(mh, dh, wm.x(), wm.p_leaf(), CONDITIONS[wm.condition])[0]
+    return a - b
+
+
+def set_probe(wm: WhaleModel, ccd):
+    """Remember one CCD of this model so `condition(wm)` can be read off the device."""
+    wm._probe = ccd
+    return wm
+
+
+def track(wm: WhaleModel, xs, posterior, n: int, fun=None, seed=None, max_nodes: int = 512):
+    """`track(TreeTracker(model, data, df, fun), N)` without the summaries (src/track.jl:30-63): for each of the
+    `n` samples draw a posterior row, re-parameterise the model (`fun(model, row)`, default `model(**row)`),
+    `logpdf!` and backtrack one tree per family.  Returns trees[family][sample] as (γ, e, t, parent) arrays.
+    Summaries (`sumtrees`, src/rectree.jl) are host-side post-processing outside the hot path."""
+    rng = np.random.default_rng(seed)
+    xs, _ = _as_vector(xs)
+    fun = fun or (lambda m, row: m(**row))
+    out = [[] for _ in range(len(xs))]
+    for _ in range(n):
+        row = posterior[int(rng.integers(len(posterior)))]
+        wmm = fun(wm, row)
+        logpdf_(wmm, xs)
+        trees = backtrack(wmm, xs, n_samples=1, seed=int(rng.integers(2 ** 31)), max_nodes=max_nodes)
+        for f, t in enumerate(trees):
+            out[f].append(t[0])
+    return out
