@@ -162,3 +162,65 @@ __device__ __forceinline__ D1 dpowi(D1 a, int n) {  // a^n, n >= 0
     return D1{p, n == 0 ? 0.0 : (double)n * (p / a.v) * a.d};
 }
 __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+// ---------------------------------------------------------------------------------------------------------
+// Row placement in shared memory.  A branch's last row is live from the moment it is computed until its
+// parent's row 1 has been formed (the root's children until the end), so rows are placed first-fit into the
+// gaps left by rows that are already dead; the peak is ~60 % of the plain sum Σ_e C_e K_e for a 9-taxon tree.
+// Runs identically on the host (budget, `set_budgets`) and on the device (thread 0 of k_dp).
+// ---------------------------------------------------------------------------------------------------------
+#ifndef WHALE_EMU
+#define WHALE_HD __host__ __device__
+#else
+#define WHALE_HD
+#endif
+constexpr int ROWALLOC_MAXBLK = 64;
+
+template <class CKfn>
+WHALE_HD inline int place_rows(int nn, int nleafnodes, const int* leafnodes, int ninner, const int* inner,
+                               const int* child0, const int* child1, const int* kind, CKfn ck, int* roff) {
+    int foff[ROWALLOC_MAXBLK], flen[ROWALLOC_MAXBLK];  // free blocks below `top`, sorted by offset
+    int nfree = 0, top = 0;
+    auto take = [&](int need) -> int {
+        if (need == 0) return 0;
+        for (int i = 0; i < nfree; i++)
+            if (flen[i] >= need) {
+                const int o = foff[i];
+                foff[i] += need; flen[i] -= need;
+                if (flen[i] == 0) { for (int j = i + 1; j < nfree; j++) { foff[j - 1] = foff[j]; flen[j - 1] = flen[j]; } nfree--; }
+                return o;
+            }
+        const int o = top;
+        top += need;
+        return o;
+    };
+    auto give = [&](int o, int len) {
+        if (len == 0) return;
+        int i = 0;
+        while (i < nfree && foff[i] < o) i++;
+        if (nfree >= ROWALLOC_MAXBLK) return;  // table full: leak the block (still correct, just less reuse)
+        for (int j = nfree; j > i; j--) { foff[j] = foff[j - 1]; flen[j] = flen[j - 1]; }
+        foff[i] = o; flen[i] = len; nfree++;
+        if (i + 1 < nfree && foff[i] + flen[i] == foff[i + 1]) {  // merge with the next block
+            flen[i] += flen[i + 1];
+            for (int j = i + 2; j < nfree; j++) { foff[j - 1] = foff[j]; flen[j - 1] = flen[j]; }
+            nfree--;
+        }
+        if (i > 0 && foff[i - 1] + flen[i - 1] == foff[i]) {  // merge with the previous block
+            flen[i - 1] += flen[i];
+            for (int j = i + 1; j < nfree; j++) { foff[j - 1] = foff[j]; flen[j - 1] = flen[j]; }
+            nfree--;
+        }
+    };
+    for (int i = 0; i < nleafnodes; i++) roff[leafnodes[i]] = take(ck(leafnodes[i]));
+    for (int i = 0; i < ninner; i++) {
+        const int e = inner[i];
+        roff[e] = take(ck(e));
+        if (kind[e] == WHALE_ROOT) continue;  // the root reads its children level by level: they stay
+        // the children are read for the last time while e's row 1 is formed; e's own slices then run in e's
+        // row and the scratch row, so later nodes may reuse the children's space
+        if (child0[e] >= 0) give(roff[child0[e]], ck(child0[e]));
+        if (child1[e] >= 0) give(roff[child1[e]], ck(child1[e]));
+    }
+    return top;
+}

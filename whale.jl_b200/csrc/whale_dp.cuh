@@ -360,14 +360,9 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
     }
     for (int i = tid; i < nn * 2 * Kmax; i += NT) s_cmap[i] = PL.cmap[i];
     __syncthreads();
-    if (tid == 0) {
-        int o = 0;
-        for (int e = 0; e < nn; e++) {
-            s_roff[e] = o;
-            o += (int)nrec[e].C * s_K[e];
-        }
-        s_roff[nn] = o;
-    }
+    if (tid == 0)
+        s_roff[nn] = place_rows(nn, M.nleafnodes, M.leafnodes, M.ninner, M.inner, s_ch0, s_ch1, s_kind,
+                                [&](int e2) { return (int)nrec[e2].C * s_K[e2]; }, s_roff);
     __syncthreads();
     double* const ell_base = A.ell ? A.ell + Hp->ell_off : nullptr;
     auto ell_of = [&](int e) -> double* {  // node e's matrix inside the family's ℓ (node-index order)
@@ -481,14 +476,12 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         const int dp16 = (C + 1 + 3) >> 2;
         const int tp16 = (kind == WHALE_WGD) ? 0 : ((3 * C + 1 + (kind == WHALE_ROOT ? (int)nlev + 1 : 0) + 3) >> 2);
         const int pp16 = fused ? (n + 1) * K : 0;
-        const int te16 = (kind == WHALE_INTERNAL) ? (int)R.ntent : 0;  // speciation terms of row 1
         uint4* st4 = reinterpret_cast<uint4*>(stage);
         copy16(st4, reinterpret_cast<const uint4*>(ents + R.dent_off), nd16, tid, NT);
         copy16(st4 + nd16, reinterpret_cast<const uint4*>(words + R.slot_off), sl16, tid, NT);
         copy16(st4 + nd16 + sl16, reinterpret_cast<const uint4*>(words + R.dptr_off), dp16, tid, NT);
         copy16(st4 + nd16 + sl16 + dp16, reinterpret_cast<const uint4*>(words + R.tptr_off), tp16, tid, NT);
         copy16(st4 + nd16 + sl16 + dp16 + tp16, reinterpret_cast<const uint4*>(PL.pp + s_toff[e]), pp16, tid, NT);
-        copy16(st4 + nd16 + sl16 + dp16 + tp16 + pp16, reinterpret_cast<const uint4*>(ents + R.tent_off), te16, tid, NT);
         stage_wait();
         const Ent* s_dents = reinterpret_cast<const Ent*>(stage);
         const Slot* s_slots = reinterpret_cast<const Slot*>(st4 + nd16);
@@ -521,21 +514,42 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         if (kind == WHALE_WGD) {
             // q·Σ p ℓ_f[γ1]ℓ_f[γ2] + (1−q+2qϵ_f)·ℓ_f[γ]   src/core.jl:103-119,187-199
             __syncthreads();
-            terms<false>(s_dents, 0, R.ndent, finF, KF, mapF, finF, KF, mapF, K, prod, cap, tid, NT);
             const double cx0 = PL.cx[e * Kmax], cy0 = PL.cy[e * Kmax];
             const double cxk = PL.cx[e * Kmax + k], cyk = PL.cy[e * Kmax + k];
-            __syncthreads();
-            if (on)
-                for (int c = grp; c < C; c += GP) {
-                    double s0, sk;
-                    cellsum(prod, cap, k, s_dptr[c], s_dptr[c + 1], s0, sk);
-                    const double u0 = finF[c * KF];
-                    const double uk = kf >= 0 ? finF[c * KF + kf] : 0.0;
-                    const double r = cy0 * sk + cx0 * uk + m * (cyk * s0 + cxk * u0);
-                    cur[c * K + k] = r;
-                    if (ellp && k == 0) ellp[c] = r;
-                }
-            __syncthreads();
+            // retention terms in windows of `cap` products, whole cells at a time
+            int cA = 0;
+            while (cA < C) {
+                const uint32_t ta = s_dptr[cA];
+                int cB = cA;
+                while (cB < C && s_dptr[cB + 1] - ta <= (uint32_t)cap) cB++;
+                const bool big = cB == cA;  // a single cell with more than `cap` terms: serial sum
+                if (big) cB = cA + 1;
+                else terms<false>(s_dents, ta, s_dptr[cB], finF, KF, mapF, finF, KF, mapF, K, prod, cap, tid, NT);
+                __syncthreads();
+                if (on)
+                    for (int c = cA + grp; c < cB; c += GP) {
+                        double s0 = 0.0, sk = 0.0;
+                        if (!big) cellsum(prod, cap, k, s_dptr[c] - ta, s_dptr[c + 1] - ta, s0, sk);
+                        else {
+                            for (uint32_t t = s_dptr[c]; t < s_dptr[c + 1]; t++) {
+                                const Ent en = s_dents[t];
+                                const double* xp = finF + en.i1 * KF;
+                                const double* yp = finF + en.i2 * KF;
+                                const double xv = kf >= 0 ? xp[kf] : 0.0, yv = kf >= 0 ? yp[kf] : 0.0;
+                                s0 = fma(en.p * xp[0], yp[0], s0);
+                                sk += fma(en.p * xp[0], yv, (en.p * yp[0]) * xv);
+                            }
+                            if (k == 0) sk = s0;
+                        }
+                        const double u0 = finF[c * KF];
+                        const double uk = kf >= 0 ? finF[c * KF + kf] : 0.0;
+                        const double r = cy0 * sk + cx0 * uk + m * (cyk * s0 + cxk * u0);
+                        cur[c * K + k] = r;
+                        if (ellp && k == 0) ellp[c] = r;
+                    }
+                __syncthreads();
+                cA = cB;
+            }
             slices(cur);
             continue;
         }
@@ -550,7 +564,6 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         const double efk = (k > 0 && kf >= 0) ? epsF[kf] : 0.0;
         const double egk = (k > 0 && kg >= 0) ? epsG[kg] : 0.0;
         const Ent* g_tents = ents + R.tent_off;
-        const Ent* s_tents = reinterpret_cast<const Ent*>(st4 + nd16 + sl16 + dp16 + tp16 + pp16);
         __syncthreads();  // staged lists visible
         if (kind == WHALE_INTERNAL) {
             // speciation terms may exceed the product window: process them in windows of `cap` terms, whole
@@ -579,7 +592,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
                     }
                     cB = cA + 1;
                 } else {
-                    terms<false>(s_tents, ta, s_tptr[cB], finF, KF, mapF, finG, KG, mapG, K, prod, cap, tid, NT);
+                    terms<true>(g_tents, ta, s_tptr[cB], finF, KF, mapF, finG, KG, mapG, K, prod, cap, tid, NT);
                     __syncthreads();
                     if (on)
                         for (int c = cA + grp; c < cB; c += GP) {
@@ -604,22 +617,25 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         const double cx0 = PL.cx[e * Kmax], cy0 = PL.cy[e * Kmax];
         const double cxk = PL.cx[e * Kmax + k], cyk = PL.cy[e * Kmax + k];
         const Ent* g_dents = ents + R.dent_off;
+        // the root works in place, so its product window spans the (idle) scratch row and the product window
+        double* const rprod = scr;
+        const int rcap = (int)((scr_len + prod_len) / K);
         for (uint32_t L = 0; L < nlev; L++) {
             const int c0 = (int)s_lev[L], c1 = (int)s_lev[L + 1];
             const uint32_t ta = s_dptr[c0], na = s_dptr[c1] - ta;
             const uint32_t ua = s_tptr[c0], nb = s_tptr[c1] - ua;
-            const bool fits = na + nb <= (uint32_t)cap;
+            const bool fits = na + nb <= (uint32_t)rcap;
             if (fits) {
-                terms<true>(g_dents, ta, ta + na, fin, K, nullptr, fin, K, nullptr, K, prod, cap, tid, NT);
-                terms<true>(g_tents, ua, ua + nb, finF, KF, mapF, finG, KG, mapG, K, prod + na, cap, tid, NT);
+                terms<true>(g_dents, ta, ta + na, fin, K, nullptr, fin, K, nullptr, K, rprod, rcap, tid, NT);
+                terms<true>(g_tents, ua, ua + nb, finF, KF, mapF, finG, KG, mapG, K, rprod + na, rcap, tid, NT);
                 __syncthreads();
             }
             if (on)
                 for (int c = c0 + grp; c < c1; c += GP) {
                     double a0 = 0.0, ak = 0.0, b0 = 0.0, bk = 0.0, l0, lk;
                     if (fits) {
-                        cellsum(prod, cap, k, s_dptr[c] - ta, s_dptr[c + 1] - ta, a0, ak);
-                        cellsum(prod, cap, k, na + s_tptr[c] - ua, na + s_tptr[c + 1] - ua, b0, bk);
+                        cellsum(rprod, rcap, k, s_dptr[c] - ta, s_dptr[c + 1] - ta, a0, ak);
+                        cellsum(rprod, rcap, k, na + s_tptr[c] - ua, na + s_tptr[c + 1] - ua, b0, bk);
                     } else {  // oversized level: serial sums per lane
                         for (uint32_t t = s_dptr[c]; t < s_dptr[c + 1]; t++) {
                             const Ent en = g_dents[t];

@@ -137,7 +137,7 @@ struct whale_data {
     std::vector<int> perm[MAXPLAN];
     std::vector<Bin> bins[MAXPLAN];
     // per family x node facts kept from packing (shared-memory budgets are recomputed per plan)
-    std::vector<uint32_t> f_ndent, f_ntent, f_nslots, f_stage16;
+    std::vector<uint32_t> f_ndent, f_ntent, f_nslots, f_stage16, f_rootwin;
     std::vector<double> work;
     size_t out_total = 0;
     cudaStream_t side[MAX_BINS] = {};
@@ -403,11 +403,11 @@ static size_t set_budgets(whale_data* D, int g, const Plan& pl) {
         const uint32_t* nt = D->f_ntent.data() + (size_t)f * nn;
         const uint32_t* ns = D->f_nslots.data() + (size_t)f * nn;
         const uint32_t* s16 = D->f_stage16.data() + (size_t)f * nn;
-        uint32_t rows = 0, mxinner = 0, mxleaf = 0, prod = 0;
+        uint32_t mxinner = 0, mxleaf = 0, prod = 0;
         size_t stg = 0;
+        constexpr uint32_t PROD_CAP = 128;  // row-1 products are formed in windows of at most this many terms
         for (int e = 0; e < nn; e++) {
             const uint32_t K = (uint32_t)pl.K[e], ck = Cs[e] * K;
-            rows += ck;
             if (s16[e] > 0)  // lists + the ϕ/ψ rows of the fused slice loop (K <= 8)
                 stg = std::max(stg, (size_t)s16[e] + (K <= 8 ? (size_t)(m->nsl[e] + 1) * K : 0));
             if (m->kind[e] == WHALE_LEAF) {
@@ -415,14 +415,21 @@ static size_t set_budgets(whale_data* D, int g, const Plan& pl) {
                 else mxinner = std::max(mxinner, ck);  // heavy leaf branch: block-scope scratch row
             } else if (m->kind[e] != WHALE_ROOT) {
                 mxinner = std::max(mxinner, ck);
-                prod = std::max(prod, std::max(nd[e], nt[e]) * K);
+                const uint32_t row1 = std::min(PROD_CAP, m->kind[e] == WHALE_WGD ? nd[e] : nt[e]);
+                prod = std::max(prod, (K <= 8 ? row1 : std::max(row1, nd[e])) * K);  // K > 8: generic slice loop
             }
         }
-        // the root's levels use the same window; give it at least 64 terms so typical levels fit
-        prod = std::max(prod, 64u * (uint32_t)pl.K[m->root]);
         auto even = [](uint32_t v) { return (v + 1) & ~1u; };
-        H.rows_len[g] = even(rows);
-        H.scr_len[g] = even(mxinner);
+        const uint32_t scr = even(mxinner);
+        // the root's levels use scratch row + product window together; size them so every level fits
+        const uint32_t rootneed = std::max(64u, D->f_rootwin[f]) * (uint32_t)pl.K[m->root];
+        if (scr + prod < rootneed) prod = rootneed - scr;
+        std::vector<int> roff(nn + 1);
+        const int rows = place_rows(nn, (int)m->leafnodes.size(), m->leafnodes.data(), (int)m->inner.size(), m->inner.data(),
+                                    m->child0.data(), m->child1.data(), m->kind.data(),
+                                    [&](int e2) { return (int)(Cs[e2] * (uint32_t)pl.K[e2]); }, roff.data());
+        H.rows_len[g] = even((uint32_t)rows);
+        H.scr_len[g] = scr;
         H.prod_len[g] = even(prod);
         H.leafmax[g] = even(mxleaf);
         H.stage_bytes[g] = (uint32_t)(16 * stg);
@@ -481,6 +488,7 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
         std::vector<Ent> entsv;         // term entries
         uint32_t sumC = 0, nlev = 0;
         size_t leaf_stage = 0;
+        uint32_t rootwin = 0;
         std::vector<size_t> stage16(nn, 0);  // 16-byte words staged per node, excluding the ϕ/ψ rows
         double wk = 0.0;
         for (int e = 0; e < nn; e++) {
@@ -626,6 +634,17 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
                         if (c == 0 || nleaf[c] != nleaf[c - 1]) { wordsv.push_back((uint32_t)c); nlev++; }
                     wordsv.push_back((uint32_t)G);
                     D->aggTroot += (double)(soff[G] - soff[0]);
+                    // largest number of products one root level needs at once (Πroot + speciation terms)
+                    const uint32_t* dpr = wordsv.data() + R.dptr_off;
+                    const uint32_t* tpr = wordsv.data() + R.tptr_off;
+                    uint32_t lvmax = 0;
+                    int cprev = 0;
+                    for (int c = 1; c <= G; c++)
+                        if (c == G || nleaf[c] != nleaf[c - 1]) {
+                            lvmax = std::max(lvmax, (dpr[c] - dpr[cprev]) + (tpr[c] - tpr[cprev]));
+                            cprev = c;
+                        }
+                    rootwin = lvmax;
                 }
             }
             // local cell -> clade id (the compat list itself), for the backtracker's output
@@ -639,8 +658,7 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
                 size_t sl16 = kind == WHALE_ROOT ? 0 : ((size_t)R.nslots + 1) / 2;
                 size_t dp16 = ((size_t)C + 1 + 3) / 4;
                 size_t tp16 = kind == WHALE_WGD ? 0 : (3 * (size_t)C + 1 + (kind == WHALE_ROOT ? nlev + 1 : 0) + 3) / 4;
-                size_t te16 = kind == WHALE_INTERNAL ? R.ntent : 0;
-                stage16[e] = nd16 + sl16 + dp16 + tp16 + te16;
+                stage16[e] = nd16 + sl16 + dp16 + tp16;
             }
             ell_total += (uint64_t)(m->nsl[e] + 1) * C;
         }
@@ -678,6 +696,7 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
             D->f_nslots.push_back(recs[e].nslots);
             D->f_stage16.push_back((uint32_t)stage16[e]);
         }
+        D->f_rootwin.push_back(rootwin);
     }
     D->ell_total = ell_total;
     D->algo_bytes = algo_bytes;
