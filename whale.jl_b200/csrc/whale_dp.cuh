@@ -24,6 +24,7 @@ struct DPArgs {
     const unsigned char* arena;
     const FamHdr* hdr;
     const int* perm;   // launch order
+    const uint32_t* roff;  // [F][nn] row offsets (doubles) of this plan, from place_rows on the host
     double* out_fam;   // [F * Kroot]  (log L_f, ∂ log L_f / ∂ component)
     double* ell;       // keep_ell buffer or nullptr
     int plan;          // 0 value only, 1 with tangents
@@ -360,9 +361,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
     }
     for (int i = tid; i < nn * 2 * Kmax; i += NT) s_cmap[i] = PL.cmap[i];
     __syncthreads();
-    if (tid == 0)
-        s_roff[nn] = place_rows(nn, M.nleafnodes, M.leafnodes, M.ninner, M.inner, s_ch0, s_ch1, s_kind,
-                                [&](int e2) { return (int)nrec[e2].C * s_K[e2]; }, s_roff);
+    for (int i = tid; i < nn; i += NT) s_roff[i] = (int)A.roff[(size_t)fam * nn + i];
     __syncthreads();
     double* const ell_base = A.ell ? A.ell + Hp->ell_off : nullptr;
     auto ell_of = [&](int e) -> double* {  // node e's matrix inside the family's ℓ (node-index order)
