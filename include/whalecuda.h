@@ -174,6 +174,9 @@ int32_t whale_work_estimate(whale_model_t m, whale_data_t d, uint32_t flags, dou
  * events on the stream they were launched on (waits for that evaluation to finish) */
 int32_t whale_last_kernel_ms(whale_data_t d, double* tables_ms, double* dp_ms, double* reduce_ms);
 
+/* device time of the k_backtrack launch of the last whale_backtrack call on this handle (CUDA events) */
+int32_t whale_last_backtrack_ms(whale_data_t d, double* ms);
+
 /* SM-cycle breakdown of the DP kernel over the families of the last WHALE_PROFILE evaluation (mean and max
  * over families): [prologue, leaf phase, staging, row 1, slices, root, total, 0] */
 int32_t whale_last_phase_cycles(whale_data_t d, double* mean8, double* max8);

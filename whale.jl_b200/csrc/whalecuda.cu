@@ -136,7 +136,9 @@ struct GraphSlot {  // one captured evaluation per (flags, condition)
     int64_t launches = 0;
 };
 static bool graphs_enabled() {
-    static bool on = [] { const char* s = getenv("WHALE_GRAPHS"); return !(s && atoi(s) == 0); }();
+    // opt-in: on B200 replaying the multi-stream evaluation as a graph measured SLOWER end to end than plain
+    // launches (0.53 vs 0.48 ms per C2 step), so the default is off
+    static bool on = [] { const char* s = getenv("WHALE_GRAPHS"); return s && atoi(s) != 0; }();
     return on;
 }
 
@@ -154,6 +156,7 @@ struct whale_data {
     // per family x node facts kept from packing (shared-memory budgets are recomputed per plan)
     std::vector<uint32_t> f_ndent, f_ntent, f_nslots, f_stage16, f_rootwin;
     std::vector<GraphSlot> graphs;
+    double last_bt_ms = 0.0;
     std::vector<uint32_t> roff_host[MAXPLAN];
     uint32_t* d_roff[MAXPLAN] = {};
     std::vector<double> work;
@@ -780,9 +783,12 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
         std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return need[a] != need[b] ? need[a] > need[b] : work[a] > work[b]; });
         std::vector<Bin>& bins = D->bins[g];
         int i = 0;
+        // a bin = families that allow the same number of resident CTAs per SM (capped by the register limit):
+        // a smaller shared-memory request buys nothing once registers are the limiter
+        auto cls = [&](size_t nd) { return std::min<size_t>((size_t)dp_minb(), (227 * 1024) / std::max<size_t>(nd, 1)); };
         while (i < F) {
             Bin b{i, 0, need[perm[i]]};
-            while (i < F && (need[perm[i]] * 5 >= b.smem * 4 || b.count < 64 || (int)bins.size() >= MAX_BINS - 1)) { i++; b.count++; }
+            while (i < F && (cls(need[perm[i]]) == cls(b.smem) || b.count < 64 || (int)bins.size() >= MAX_BINS - 1)) { i++; b.count++; }
             std::stable_sort(perm.begin() + b.off, perm.begin() + b.off + b.count, [&](int x, int y) { return work[x] > work[y]; });
             bins.push_back(b);
         }
@@ -1081,10 +1087,15 @@ int32_t whale_backtrack(whale_model_t m, whale_data_t d, int32_t n_samples, cons
     LAUNCH(k_tables, 1, std::min(32, m->nn) * 32, tables_smem(m, p0), m->stream, m->dev, p0.dev, m->d_x, m->d_pleaf);
     BTArgs a{m->dev, p0.dev, d->d_arena, d->d_hdr, d->d_ell, m->d_x, d_u, (long long)stride, d->F, n_samples, max_nodes,
              d_cnt, d_g, d_e, d_t, d_p, d_st, d_stack};
+    cudaEvent_t eb0 = nullptr, eb1 = nullptr;
+    CUB(cudaEventCreate(&eb0)); CUB(cudaEventCreate(&eb1));
+    CUB(cudaEventRecord(eb0, m->stream));
     LAUNCH(k_backtrack, (int)((W + 127) / 128), 128, 0, m->stream, a);
+    CUB(cudaEventRecord(eb1, m->stream));
     g_launches += 2;
     CUB(cudaGetLastError());
     CUB(cudaStreamSynchronize(m->stream));
+    { float ms = 0; cudaEventElapsedTime(&ms, eb0, eb1); d->last_bt_ms = ms; cudaEventDestroy(eb0); cudaEventDestroy(eb1); }
     CUB(cudaMemcpy(node_count, d_cnt, W * 4, cudaMemcpyDeviceToHost));
     CUB(cudaMemcpy(status, d_st, W * 4, cudaMemcpyDeviceToHost));
     CUB(cudaMemcpy(gamma, d_g, W * max_nodes * 4, cudaMemcpyDeviceToHost));
@@ -1124,6 +1135,12 @@ int32_t whale_last_kernel_ms(whale_data_t d, double* tables_ms, double* dp_ms, d
     if (tables_ms) *tables_ms = a;
     if (dp_ms) *dp_ms = b;
     if (reduce_ms) *reduce_ms = c;
+    return WHALE_OK;
+}
+
+int32_t whale_last_backtrack_ms(whale_data_t d, double* ms) {
+    if (!d || !ms) return fail(WHALE_ERR_ARG, "null argument");
+    *ms = d->last_bt_ms;
     return WHALE_OK;
 }
 

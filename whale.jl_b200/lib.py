@@ -22,7 +22,7 @@ SYMBOLS = ["whale_version", "whale_last_error", "whale_device_count", "whale_set
            "whale_model_destroy", "whale_data_create", "whale_data_destroy", "whale_data_nfam",
            "whale_data_arena_bytes", "whale_data_arena_dump", "whale_logpdf_grad", "whale_logpdf_grad_async",
            "whale_slices", "whale_ell_size", "whale_ell_get", "whale_backtrack", "whale_launch_count",
-           "whale_work_estimate", "whale_last_kernel_ms", "whale_last_phase_cycles", "whale_last_tables_cycles", "whale_fp64_peak"]
+           "whale_work_estimate", "whale_last_kernel_ms", "whale_last_phase_cycles", "whale_last_tables_cycles", "whale_last_backtrack_ms", "whale_fp64_peak"]
 
 
 class ModelDesc(C.Structure):
@@ -85,6 +85,7 @@ class Lib:
         L.whale_last_kernel_ms.argtypes = [vp, f64p, f64p, f64p]
         L.whale_last_phase_cycles.argtypes = [vp, f64p, f64p]
         L.whale_last_tables_cycles.argtypes = [vp, C.c_int32, f64p]
+        L.whale_last_backtrack_ms.argtypes = [vp, f64p]
 
     def check(self, rc):
         if rc != 0:
@@ -182,6 +183,11 @@ class Lib:
         self.check(self.L.whale_last_phase_cycles(dh, _ptr(mean, f64p), _ptr(mx, f64p)))
         names = ["prologue", "leaf_phase", "staging", "row1", "slices", "root", "total"]
         return {n: (float(mean[i]), float(mx[i])) for i, n in enumerate(names)}
+
+    def last_backtrack_ms(self, dh) -> float:
+        ms = C.c_double()
+        self.check(self.L.whale_last_backtrack_ms(dh, C.byref(ms)))
+        return ms.value
 
     def last_tables_cycles(self, mh, with_grad=True):
         out = np.zeros(32)
