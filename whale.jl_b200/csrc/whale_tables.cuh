@@ -42,9 +42,10 @@ __global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const d
     const long long tk0 = CLOCK64();
     const int nn = M.nn, Kmax = PL.Kmax, P = M.n_params;
     double* sd = reinterpret_cast<double*>(tsm);                 // dt, leafP, pleaf [nn each], x [P]
-    int* si = reinterpret_cast<int*>(sd + 3 * nn + P);           // 9 arrays [nn], lvl_off [nlvl+1], lvl_nodes [nn]
+    int* si = reinterpret_cast<int*>(sd + 3 * nn + P + 2 * nn * Kmax);  // 9 arrays [nn], lvl_off [nlvl+1], lvl_nodes [nn]
     int16_t* s_cm = reinterpret_cast<int16_t*>(si + 10 * nn + M.nlvl + 1);
     uint8_t* s_ro = reinterpret_cast<uint8_t*>(s_cm + nn * 2 * Kmax);
+    double* s_ab = sd + 3 * nn + P;  // placed behind x below: [nn*Kmax*2] (α, β) components per node
     for (int i = threadIdx.x; i < nn; i += blockDim.x) {
         sd[i] = M.dt[i]; sd[nn + i] = M.leafP[i]; sd[2 * nn + i] = pleaf ? pleaf[i] : 0.0;
         si[i] = M.kind[i]; si[nn + i] = M.nsl[i]; si[2 * nn + i] = M.child0[i]; si[3 * nn + i] = M.child1[i];
@@ -58,6 +59,36 @@ __global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const d
     __syncthreads();
     TabMeta T{si, si + nn, si + 2 * nn, si + 3 * nn, si + 4 * nn, si + 5 * nn, si + 6 * nn, si + 7 * nn, si + 8 * nn,
               si + 9 * nn, si + 9 * nn + M.nlvl + 1, sd, sd + nn, sd + 2 * nn, sd + 3 * nn, s_cm, s_ro};
+    // ---- phase A0: (α, β) of every branch — they depend on the branch's own rates only, so all nodes go in
+    //      parallel (one warp per node) instead of paying exp + divisions on every level of the chain below ----
+    for (int e = warp; e < nn; e += nwarp) {
+        const int K = T.K[e];
+        for (int k = lane; k < K; k += 32) {
+            const unsigned role = k == 0 ? 0u : T.role[e * PL.Kmax + k];
+            const int ls = T.ls[e], ms = T.ms[e];
+            const double lv = ls < 0 ? NaN : (M.log_scale ? exp(T.x[ls]) : T.x[ls]);
+            const double mv = ms < 0 ? NaN : (M.log_scale ? exp(T.x[ms]) : T.x[ms]);
+            const D1 lam = mk(lv, (role & 1u) ? (M.log_scale ? lv : 1.0) : 0.0);
+            const D1 mu = mk(mv, (role & 2u) ? (M.log_scale ? mv : 1.0) : 0.0);
+            D1 a = mk(0.0), b = mk(0.0);
+            if (T.nsl[e] > 0) {
+                // getα src/bdputil.jl:6-7 (critical branch decided on VALUES, like isapprox on Duals)
+                const double t = T.dt[e];
+                if (fabs(lam.v - mu.v) <= 1e-6) {
+                    a = (lam * mk(t)) / (1.0 + lam * mk(t));
+                } else {
+                    const D1 ex = dexp(mk(t) * (lam - mu));
+                    a = mu * (ex - 1.0) / (lam * ex - mu);
+                }
+                b = (lam / mu) * a;
+            }
+            s_ab[(e * Kmax + k) * 2 + 0] = k == 0 ? a.v : a.d;
+            s_ab[(e * Kmax + k) * 2 + 1] = k == 0 ? b.v : b.d;
+            PL.ab[(e * PL.Kmax + k) * 2 + 0] = k == 0 ? a.v : a.d;
+            PL.ab[(e * PL.Kmax + k) * 2 + 1] = k == 0 ? b.v : b.d;
+        }
+    }
+    __syncthreads();
     if (threadIdx.x == 0) PL.tim[0] = CLOCK64() - tk0;
     // ---- phase A: per level, one warp per node, lanes over components; division-free chain ----
     for (int L = 0; L < M.nlvl; L++) {
@@ -67,12 +98,6 @@ __global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const d
             const int K = T.K[e], kind = T.kind[e], n = T.nsl[e];
             for (int k = lane; k < K; k += 32) {
                 const unsigned role = k == 0 ? 0u : T.role[e * PL.Kmax + k];
-                // getθ (src/rmodels.jl:31-33,55-64): raw -> rate, with the chain factor of the log scale
-                const int ls = T.ls[e], ms = T.ms[e];
-                const double lv = ls < 0 ? NaN : (M.log_scale ? exp(T.x[ls]) : T.x[ls]);
-                const double mv = ms < 0 ? NaN : (M.log_scale ? exp(T.x[ms]) : T.x[ms]);
-                const D1 lam = mk(lv, (role & 1u) ? (M.log_scale ? lv : 1.0) : 0.0);
-                const D1 mu = mk(mv, (role & 2u) ? (M.log_scale ? mv : 1.0) : 0.0);
                 D1 ep;
                 if (kind == WHALE_LEAF) {  // setnode! src/model.jl:170
                     ep = mk(T.pleaf[e]);
@@ -110,17 +135,9 @@ __global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const d
                 double2* uvrow = PL.uv + T.toff[e];
                 D1 u = ep, v = mk(1.0);
                 uvrow[k] = k == 0 ? make_double2(u.v, v.v) : make_double2(u.d, v.d);
-                D1 a = mk(0.0), b = mk(0.0);
+                const D1 a = mk(s_ab[(e * Kmax) * 2], k == 0 ? 0.0 : s_ab[(e * Kmax + k) * 2]);
+                const D1 b = mk(s_ab[(e * Kmax) * 2 + 1], k == 0 ? 0.0 : s_ab[(e * Kmax + k) * 2 + 1]);
                 if (n > 0) {
-                    // getα src/bdputil.jl:6-7 (critical branch decided on VALUES, like isapprox on Duals)
-                    const double t = T.dt[e];
-                    if (fabs(lam.v - mu.v) <= 1e-6) {
-                        a = (lam * mk(t)) / (1.0 + lam * mk(t));
-                    } else {
-                        const D1 ex = dexp(mk(t) * (lam - mu));
-                        a = mu * (ex - 1.0) / (lam * ex - mu);
-                    }
-                    b = (lam / mu) * a;
                     const D1 c = (1.0 - a) - b;
                     for (int i = 1; i <= n; i++) {
                         const D1 un = c * u + a * v;
@@ -130,8 +147,6 @@ __global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const d
                         uvrow[(size_t)i * K + k] = k == 0 ? make_double2(u.v, v.v) : make_double2(u.d, v.d);
                     }
                 }
-                PL.ab[(e * PL.Kmax + k) * 2 + 0] = k == 0 ? a.v : a.d;
-                PL.ab[(e * PL.Kmax + k) * 2 + 1] = k == 0 ? b.v : b.d;
                 if (kind == WHALE_LEAF) {
                     // leaf clade on a leaf branch: ℓ_n = leafℙ·Π_i ϕ_i = leafℙ·gⁿ·(v_0/v_n)²  (src/core.jl:94,123)
                     const D1 g = (1.0 - a) * (1.0 - b);
@@ -166,8 +181,8 @@ __global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const d
         }
         const double2 p0 = uvrow[(size_t)(i - 1) * K], pk = uvrow[(size_t)(i - 1) * K + k];
         const D1 vp = mk(p0.y, k == 0 ? 0.0 : pk.y);
-        const D1 a = mk(PL.ab[(e * PL.Kmax) * 2], k == 0 ? 0.0 : PL.ab[(e * PL.Kmax + k) * 2]);
-        const D1 b = mk(PL.ab[(e * PL.Kmax) * 2 + 1], k == 0 ? 0.0 : PL.ab[(e * PL.Kmax + k) * 2 + 1]);
+        const D1 a = mk(s_ab[(e * Kmax) * 2], k == 0 ? 0.0 : s_ab[(e * Kmax + k) * 2]);
+        const D1 b = mk(s_ab[(e * Kmax) * 2 + 1], k == 0 ? 0.0 : s_ab[(e * Kmax + k) * 2 + 1]);
         const D1 g = (1.0 - a) * (1.0 - b);
         const D1 r = vp / v;  // 1 / (1 − βϵ_{i−1})
         const D1 phi = g * (r * r);

@@ -406,9 +406,14 @@ static size_t smem_need(const whale_model* m, const FamHdr& h, int plan, int Kma
            h.stage_bytes[plan] + NW * ((size_t)h.leafmax[plan] * sizeof(double) + h.leaf_stage);
 }
 
+#ifdef WHALE_EMU
+constexpr int TABLES_NT = 128;  // host-thread emulation: keep the thread count small
+#else
+constexpr int TABLES_NT = 1024;
+#endif
 static size_t tables_smem(const whale_model* m, const Plan& pl) {  // mirrors the carve-up in k_tables
     const size_t nn = m->nn, nlvl = m->lvl_off.size() - 1;
-    return (3 * nn + m->P) * sizeof(double) + (10 * nn + nlvl + 1) * sizeof(int) + nn * 2 * pl.Kmax * sizeof(int16_t) +
+    return (3 * nn + m->P + 2 * nn * pl.Kmax) * sizeof(double) + (10 * nn + nlvl + 1) * sizeof(int) + nn * 2 * pl.Kmax * sizeof(int16_t) +
            nn * pl.Kmax + 16;
 }
 
@@ -884,7 +889,7 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
             CU(cudaEventRecord(D->ev_tab, D->side_tab));
             g_launches++;
         }
-        LAUNCH(k_tables, 1, 1024, tables_smem(m, pl), st, m->dev, pl.dev, d_x, m->d_pleaf);
+        LAUNCH(k_tables, 1, TABLES_NT, tables_smem(m, pl), st, m->dev, pl.dev, d_x, m->d_pleaf);
         g_launches++;
         if (!keep && !m->leafnodes.empty()) CU(cudaStreamWaitEvent(st, D->ev_tab, 0));
         if (prof && first) CU(cudaEventRecord(D->ev[1], st));
@@ -1031,7 +1036,7 @@ int32_t whale_slices(whale_model_t m, const double* x, const double* p_leaf, dou
     CU(cudaMemcpy(m->d_x, x, P * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(m->d_pleaf, pl.data(), nn * sizeof(double), cudaMemcpyHostToDevice));
     Plan& p0 = m->plan[0];
-    LAUNCH(k_tables, 1, std::min(32, nn) * 32, tables_smem(m, p0), m->stream, m->dev, p0.dev, m->d_x, m->d_pleaf);
+    LAUNCH(k_tables, 1, TABLES_NT, tables_smem(m, p0), m->stream, m->dev, p0.dev, m->d_x, m->d_pleaf);
     g_launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(m->stream));
@@ -1084,7 +1089,7 @@ int32_t whale_backtrack(whale_model_t m, whale_data_t d, int32_t n_samples, cons
     CUB(cudaMalloc((void**)&d_t, W * max_nodes * 4)); CUB(cudaMalloc((void**)&d_p, W * max_nodes * 4));
     CUB(cudaMalloc((void**)&d_stack, W * max_nodes * sizeof(int4)));
     Plan& p0 = m->plan[0];
-    LAUNCH(k_tables, 1, std::min(32, m->nn) * 32, tables_smem(m, p0), m->stream, m->dev, p0.dev, m->d_x, m->d_pleaf);
+    LAUNCH(k_tables, 1, TABLES_NT, tables_smem(m, p0), m->stream, m->dev, p0.dev, m->d_x, m->d_pleaf);
     BTArgs a{m->dev, p0.dev, d->d_arena, d->d_hdr, d->d_ell, m->d_x, d_u, (long long)stride, d->F, n_samples, max_nodes,
              d_cnt, d_g, d_e, d_t, d_p, d_st, d_stack};
     cudaEvent_t eb0 = nullptr, eb1 = nullptr;
