@@ -181,6 +181,10 @@ int32_t whale_last_backtrack_ms(whale_data_t d, double* ms);
  * over families): [prologue, leaf phase, staging, row 1, slices, root, total, 0] */
 int32_t whale_last_phase_cycles(whale_data_t d, double* mean8, double* max8);
 
+/* same evaluation, per inner node in processing order (internal / WGD nodes, the root last): mean SM cycles of
+ * the slice loop and of staging + row 1; returns the number of entries written (<= cap) or a negative status */
+int32_t whale_last_node_cycles(whale_data_t d, double* slices_mean, double* row1_mean, int32_t cap);
+
 /* SM-cycle stamps of the last k_tables launch of the model's value / full-gradient plan: [0] metadata staged,
  * [1+L] level L done, [30] all rows written, [31] number of levels */
 int32_t whale_last_tables_cycles(whale_model_t m, int32_t with_grad, double* out32);

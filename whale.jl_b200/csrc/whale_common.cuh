@@ -37,24 +37,26 @@ struct NodeRec {
     uint32_t tent_off;
     uint32_t ntent;
     uint32_t slot_off;  // u32-word offset (multiple of 4) of the slice-loop lane table (Slot[nslots])
-    uint32_t nslots;
+    uint32_t nslots;    //   (a leaf branch with more than HEAVY_SLOTS slots is processed by the whole CTA)
     uint32_t sptr_off;  // leaf branches in shape mode (see SHAPES below): u32-word offset of sptr[C+1], else 0
     uint32_t sent_off;  //   16-byte-entry offset of {i1 = shape id, p = coefficient}
 };
 static_assert(sizeof(NodeRec) == 48, "NodeRec must be 48 bytes");
 
-// Slice-loop work descriptor of one lane (built by the packer; src/core.jl:178-185 balanced over lanes):
-// a clade cell with E same-branch terms is owned by a team of G = 2^glog adjacent lanes (G = 1 for E <= 2);
-// lane j of the team sums terms first, first+G, ... (cnt of them), the team leader (slot index multiple of G)
-// gets the total through a shuffle reduction and writes the cell.
+// Slice-loop work descriptor (built by the packer; src/core.jl:178-185 balanced over lanes): a clade cell with E
+// same-branch terms is owned by a team of G = 2^glog adjacent slots (G = 1 for E <= 2) so that no lane sums
+// more than two terms (E <= 64); slot j of the team sums terms first, first+G, ... (cnt of them).  At run time
+// every slot is expanded into K lanes (one per component), the team reduces its scalar partial results by
+// shuffles and the leader (slot index multiple of G) writes the cell component.
 struct Slot {
-    uint16_t cell;    // local cell index, 0xFFFF = idle lane
+    uint16_t cell;    // local cell index
     uint8_t glog;
     uint8_t cnt;
     uint16_t first;   // index into the node's term list
     uint16_t stride;  // = G
 };
 static_assert(sizeof(Slot) == 8, "Slot must be 8 bytes");
+constexpr uint32_t HEAVY_SLOTS = 24;
 
 constexpr int MAXPLAN = 10;  // tangent plans per data handle: [0] value only, [1..] gradient (parameter chunks)
 
@@ -77,7 +79,7 @@ struct FamHdr {
     // shared-memory budget (doubles unless stated), per tangent plan where it depends on K_e
     uint32_t rows_len[MAXPLAN];    // Σ_e C_e K_e (even)
     uint32_t scr_len[MAXPLAN];     // scratch row: max over internal/WGD nodes of C_e K_e (even)
-    uint32_t prod_len[MAXPLAN];    // P1 product window (row 1 / root / K > 8 slices), even
+    uint32_t prod_len[MAXPLAN];    // (unused: no products go through shared memory any more; kept 0)
     uint32_t leafmax[MAXPLAN];     // per-warp scratch row: max over leaf branches of C_e K_e (even)
     uint32_t stage_bytes[MAXPLAN]; // staging buffer for one internal node's lists + ϕ/ψ rows (bytes, multiple of 16)
     uint32_t leaf_stage;     // per-warp staging buffer for one leaf branch's lists (bytes, multiple of 16)
@@ -170,7 +172,7 @@ __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000
 // Runs identically on the host (budget, `set_budgets`) and on the device (thread 0 of k_dp).
 // ---------------------------------------------------------------------------------------------------------
 #ifndef WHALE_EMU
-#define WHALE_HD __host__ __device__
+#define WHALE_HD
 #else
 #define WHALE_HD
 #endif

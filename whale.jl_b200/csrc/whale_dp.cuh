@@ -2,19 +2,23 @@
 //
 // One CTA (NT threads) per family.  The LAST row of every branch (C_e × K_e doubles: K_e = 1 + #raw
 // parameters that can influence branch e) stays in shared memory for the parent; slices ping-pong between
-// that row and a scratch row.  Every Σ_t p_t·ℓ[γ1]·ℓ[γ2] of the reference (Πduplication, Πspeciation,
-// Πwgdretention, Πroot) is evaluated in two balanced phases instead of one serial loop per clade:
-//   P1  one thread per TERM t: products p·x·y with the product rule for all K components -> prod[k][t]
-//   P2  one lane per (cell, component): sums its contiguous range of prod (the reference's summation
-//       order), applies the row formula, writes the new row.
-// That removes the load imbalance of CCDs (a branch's largest clade typically owns ~10× the mean number of
-// splits; the ubiquitous clade ~100) from the critical path.
+// that row and a scratch row.
+//
+// Work decomposition: one LANE per (clade cell, component k) of the row being formed.  The lane walks (its
+// share of) the cell's clade-split terms Σ_t p_t·X[γ1]·Y[γ2] (Πduplication, Πspeciation, Πwgdretention, Πroot)
+// and forms ITS component with the product rule (value lanes k = 0; tangent lanes k > 0 need the operands'
+// value and their own component only), folds it into the row formula's linear part — a scalar — and writes
+// one double.  No products go through shared memory and K is a run-time number (one code path for every
+// tangent plan).  Where a cell has many terms (the slice loop's heavy clades, the root's last levels with the
+// ubiquitous clade) its terms are split over a team of 2^g adjacent lanes and the scalar partial results are
+// shuffle-reduced.
 //   phase A  leaf branches are independent of each other: one WARP per leaf branch, warp-level sync only;
 //            branches whose compatible clades are all leaf clades are family-independent and are filled
-//            from the table k_tables prepared (ℓ_n = leafℙ·Πϕ_i).
-//   phase B  internal / WGD / root nodes in the reference's order (children first), all warps cooperating;
-//            the node's pointer arrays and within-branch terms are staged in shared memory.
-// ϕ/ψ rows are prefetched one slice ahead into registers, so the slice loop touches shared memory only.
+//            from the table k_tables prepared (ℓ_n = leafℙ·Πϕ_i); small in-paralog clades use the closed
+//            form over tree shapes (k_leafshapes).
+//   phase B  internal / WGD / root nodes in the reference's order (children first); the node's lists and
+//            ϕ/ψ rows are staged in shared memory; only as many warps as the row has lanes take part in the
+//            slice loop (one warp: warp-level sync; several: a named barrier among them).
 #pragma once
 #include "whale_common.cuh"
 
@@ -29,22 +33,16 @@ struct DPArgs {
     double* ell;       // keep_ell buffer or nullptr
     int plan;          // 0 value only, 1 with tangents
     int skip_leaf;     // share family-independent leaf-branch rows (off in keep_ell mode)
-    long long* tim;    // optional per-family phase cycle counters [F][8] (profiling aid) or nullptr
+    long long* tim;    // optional per-family phase cycle counters [F][TIMW] (profiling aid) or nullptr
 };
-
-
+// tim layout: [0..7] phases, [8 + oi] slice-loop cycles of inner node oi, [8 + TIMN + oi] staging + row-1 cycles
+constexpr int TIMN = 32, TIMW = 8 + 2 * TIMN;
 
 #ifdef WHALE_EMU
 #define PREFETCH_L2(p) ((void)0)
 #else
 #define PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #endif
-
-template <bool WARP>
-__device__ __forceinline__ void scope_sync() {
-    if (WARP) __syncwarp();
-    else __syncthreads();
-}
 
 // copy n16 16-byte words global -> shared with all threads of the scope.  cp.async keeps every copy of a
 // staging batch in flight at once (one memory latency per node instead of one per loop iteration); the batch
@@ -63,44 +61,23 @@ __device__ __forceinline__ void copy16(uint4* dst, const uint4* __restrict__ src
 __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #endif
 
-// P1: terms [ta, tb) of `ents` -> prod[k*cap + (t - ta)], k = 0..K-1.
-// X/Y are rows with KX/KY components; mapX/mapY translate the output component k into the component of
-// X/Y (identity if null; -1: the row does not depend on that parameter -> zero tangent).
-template <bool GLOBAL_ENTS>
-__device__ __forceinline__ void terms(const Ent* __restrict__ ents, uint32_t ta, uint32_t tb,
-                                      const double* __restrict__ X, int KX, const int16_t* __restrict__ mapX,
-                                      const double* __restrict__ Y, int KY, const int16_t* __restrict__ mapY,
-                                      int K, double* __restrict__ prod, int cap, int tid, int nt) {
-    for (uint32_t t = ta + tid; t < tb; t += nt) {
-        uint4 raw;
-        if (GLOBAL_ENTS) raw = __ldg(reinterpret_cast<const uint4*>(ents + t));
-        else raw = *reinterpret_cast<const uint4*>(ents + t);
-        const double p = __hiloint2double((int)raw.w, (int)raw.z);
-        const double* xp = X + (raw.x & 0xffffu) * KX;
-        const double* yp = Y + (raw.x >> 16) * KY;
-        const double px = p * xp[0], py = p * yp[0];
-        double* o = prod + (t - ta);
-        o[0] = px * yp[0];
-#pragma unroll 4
-        for (int k = 1; k < K; k++) {
-            const int kx = mapX ? mapX[k] : k, ky = mapY ? mapY[k] : k;
-            const double xv = kx >= 0 ? xp[kx] : 0.0, yv = ky >= 0 ? yp[ky] : 0.0;
-            o[(size_t)k * cap] = fma(px, yv, py * xv);
-        }
-    }
-}
+#ifdef WHALE_EMU
+#define SHFL_DOWN(v, d) emu::shfl_down(v, d)
+#else
+#define SHFL_DOWN(v, d) __shfl_down_sync(0xffffffffu, v, d)
+#endif
 
-// P2 helper: (S0, Sk) of cell range [tb, te) (indices relative to the P1 window)
-__device__ __forceinline__ void cellsum(const double* __restrict__ prod, int cap, int k, uint32_t tb, uint32_t te,
-                                        double& S0, double& Sk) {
-    double s0 = 0.0, sk = 0.0;
-    const double* pk = prod + (size_t)k * cap;
-    for (uint32_t t = tb; t < te; t++) {
-        s0 += prod[t];
-        sk += pk[t];
-    }
-    S0 = s0;
-    Sk = sk;
+// barrier among the first `nw` warps of the CTA (the warps that own lanes of the current row)
+template <int NW>
+__device__ __forceinline__ void part_sync(int nw) {
+#ifdef WHALE_EMU
+    if (NW == 1) __syncwarp();
+    else __syncthreads();  // the emulation keeps every warp in the loop
+#else
+    if (NW == 1 || nw == 1) __syncwarp();
+    else if (nw == NW) __syncthreads();
+    else asm volatile("bar.sync 1, %0;" ::"r"(nw * 32) : "memory");
+#endif
 }
 
 // Πloss (src/core.jl:172-176) for a cell with child indices lf/lg (−1: incompatible -> getl = 0)
@@ -114,45 +91,263 @@ __device__ __forceinline__ void loss_term(int lf, int lg, const double* finF, in
     ck = fk * eg0 + gk * ef0 + m * (f0 * egk + g0 * efk);
 }
 
+// Σ_t p_t·X[i1]·Y[i2] over terms tb, tb+step, ... < te for ONE component: value s0 and the lane's own
+// component sk (product rule).  kx/ky: the component's index in X/Y (−1: that row does not depend on the
+// parameter -> zero tangent).  Two terms are in flight per iteration so the loads of one overlap the
+// arithmetic of the other.
+template <bool GLOBAL_ENTS>
+__device__ __forceinline__ void term_sum(const Ent* __restrict__ ents, uint32_t tb, uint32_t te, uint32_t step,
+                                         const double* __restrict__ X, int KX, int kx, const double* __restrict__ Y,
+                                         int KY, int ky, double& s0, double& sk) {
+    double a0 = 0.0, ak = 0.0, b0 = 0.0, bk = 0.0;
+    uint32_t t = tb;
+    for (; t + step < te; t += 2 * step) {
+        uint4 r1, r2;
+        if (GLOBAL_ENTS) { r1 = __ldg(reinterpret_cast<const uint4*>(ents + t)); r2 = __ldg(reinterpret_cast<const uint4*>(ents + t + step)); }
+        else { r1 = *reinterpret_cast<const uint4*>(ents + t); r2 = *reinterpret_cast<const uint4*>(ents + t + step); }
+        const double* x1 = X + (r1.x & 0xffffu) * KX;
+        const double* y1 = Y + (r1.x >> 16) * KY;
+        const double* x2 = X + (r2.x & 0xffffu) * KX;
+        const double* y2 = Y + (r2.x >> 16) * KY;
+        const double x10 = x1[0], y10 = y1[0], x20 = x2[0], y20 = y2[0];
+        const double x1k = kx >= 0 ? x1[kx] : 0.0, y1k = ky >= 0 ? y1[ky] : 0.0;
+        const double x2k = kx >= 0 ? x2[kx] : 0.0, y2k = ky >= 0 ? y2[ky] : 0.0;
+        const double p1 = __hiloint2double((int)r1.w, (int)r1.z), p2 = __hiloint2double((int)r2.w, (int)r2.z);
+        const double px1 = p1 * x10, px2 = p2 * x20;
+        a0 = fma(px1, y10, a0);
+        b0 = fma(px2, y20, b0);
+        ak = fma(px1, y1k, fma(p1 * y10, x1k, ak));
+        bk = fma(px2, y2k, fma(p2 * y20, x2k, bk));
+    }
+    if (t < te) {
+        uint4 r1;
+        if (GLOBAL_ENTS) r1 = __ldg(reinterpret_cast<const uint4*>(ents + t));
+        else r1 = *reinterpret_cast<const uint4*>(ents + t);
+        const double* x1 = X + (r1.x & 0xffffu) * KX;
+        const double* y1 = Y + (r1.x >> 16) * KY;
+        const double x10 = x1[0], y10 = y1[0];
+        const double x1k = kx >= 0 ? x1[kx] : 0.0, y1k = ky >= 0 ? y1[ky] : 0.0;
+        const double p1 = __hiloint2double((int)r1.w, (int)r1.z);
+        const double px1 = p1 * x10;
+        a0 = fma(px1, y10, a0);
+        ak = fma(px1, y1k, fma(p1 * y10, x1k, ak));
+    }
+    s0 = a0 + b0;
+    sk = ak + bk;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // The n slices of one branch (src/core.jl:121-128,178-185):
-//   ℓ_i[γ] = ϕ_i ℓ_{i−1}[γ] + ψ_i Σ_t p_t ℓ_{i−1}[γ1] ℓ_{i−1}[γ2]
+//   ℓ_i[γ] = ϕ_i ℓ_{i−1}[γ] + ψ_i Σ_t p_t ℓ_{i−1}[γ1] ℓ_{i−1}[γ2]        (+ tangents)
 // `cur` holds row 1 on entry; rows alternate between fin and scr so that row n+1 lands in fin.
-template <bool WARP>
-__device__ __forceinline__ void run_slices(int n, int C, int K, double* fin, double* scr, double* cur,
-                                           const Ent* s_dents, const uint32_t* s_dptr, uint32_t nd,
-                                           const double2* __restrict__ pprow, double* prod, int cap, double* ellp,
-                                           int tid, int nt) {
-    const int GP = nt / K;
-    const int grp = tid / K, k = tid - grp * K;
-    const bool on = grp < GP && grp < C;
-    const double m = k == 0 ? 0.0 : 1.0;
-    uint32_t tb0 = 0, te0 = 0;  // the lane's first cell keeps its term range in registers
-    if (on) { tb0 = s_dptr[grp]; te0 = s_dptr[grp + 1]; }
-    double2 c0 = make_double2(0, 0), ck = c0;
-    if (on && n >= 1) { c0 = __ldg(pprow + K); ck = __ldg(pprow + K + k); }
+// Lanes = (slot of the packer's lane table) × (group of KC components), group-major in blocks of `spad` lanes,
+// so a team's slots are adjacent lanes.  KC is chosen per branch so that the row needs at most two lane sets
+// per thread: short rows get one component per lane (the shortest dependent chain), long rows up to three.
+// Every lane keeps the row offsets and probabilities of its (at most two) terms in registers for the whole
+// branch and runs the same branch-free code: operand loads, the product rule for its components, the row
+// formula's linear part (ψ_i·Σ_k + ψ'_i·Σ_0) folded into one scalar per component, a shuffle reduction of those
+// scalars inside the team, and the leader's ϕ part + store.  The two lane sets of a thread are issued together
+// so their latencies overlap.
+// ---------------------------------------------------------------------------------------------------------
+struct LaneSK {
+    int c0k;         // offset (elements) of the cell's value component
+    int kb;          // first component of the lane's group
+    int gsz;         // team size (0: idle lane)
+    int lead;        // team leader: writes the cell
+    int cnt, first;  // the lane's share of the cell's terms: first, first+gsz, ...
+    int a1, a2, b1, b2;  // row offsets (elements) of the operands of its two terms
+    double pa, pb;
+};
+
+__device__ __forceinline__ LaneSK load_lane(const Slot* s_slots, int nslots, const Ent* s_dents, int spad, int K,
+                                            int KC, int total, int u) {
+    LaneSK w;
+    w.c0k = 0; w.kb = 0; w.gsz = 0; w.lead = 0; w.cnt = 0; w.first = 0;
+    w.a1 = w.a2 = w.b1 = w.b2 = 0;
+    w.pa = w.pb = 0.0;
+    if (u < total) {
+        const int g = u / spad, s = u - g * spad;
+        if (s < nslots) {
+            const Slot sl = s_slots[s];
+            w.kb = g * KC;
+            w.gsz = 1 << sl.glog;
+            w.lead = (s & (w.gsz - 1)) == 0;
+            w.c0k = (int)sl.cell * K;
+            w.cnt = sl.cnt; w.first = sl.first;
+            if (w.cnt > 0) { const Ent en = s_dents[w.first]; w.a1 = en.i1 * K; w.a2 = en.i2 * K; w.pa = en.p; }
+            if (w.cnt > 1) { const Ent en = s_dents[w.first + w.gsz]; w.b1 = en.i1 * K; w.b2 = en.i2 * K; w.pb = en.p; }
+        }
+    }
+    return w;
+}
+
+// team size of the warp's first lane = the warp's largest (slots are sorted by team size, descending)
+__device__ __forceinline__ int warp_team(const Slot* s_slots, int nslots, int spad, int total, int u0) {
+    if (u0 >= total) return 0;
+    if (spad < 32) return 1 << s_slots[0].glog;
+    const int s0 = u0 % spad;
+    return s0 < nslots ? (1 << s_slots[s0].glog) : 0;
+}
+
+// the lane's partials of ψ_i·Σ_k + ψ'_i·Σ_0 for one slice (branch-free for cnt <= 2)
+template <int KC>
+__device__ __forceinline__ void lane_partial(const LaneSK& w, const double* __restrict__ src, double2 c0,
+                                             const double2 (&ck)[KC], const Ent* s_dents, int K, double (&part)[KC]) {
+    const double* xa = src + w.a1;
+    const double* ya = src + w.a2;
+    const double* xb = src + w.b1;
+    const double* yb = src + w.b2;
+    const double x0 = xa[0], y0 = ya[0], u0 = xb[0], v0 = yb[0];
+    double xk[KC], yk[KC], uk[KC], vk[KC];
+#pragma unroll
+    for (int j = 0; j < KC; j++) {
+        const int k = min(w.kb + j, K - 1);
+        xk[j] = xa[k]; yk[j] = ya[k]; uk[j] = xb[k]; vk[j] = yb[k];
+    }
+    const double px = w.pa * x0, py = w.pa * y0, pu = w.pb * u0, pv = w.pb * v0;
+    double s0 = fma(px, y0, pu * v0);
+    double sk[KC];
+#pragma unroll
+    for (int j = 0; j < KC; j++) sk[j] = fma(px, yk[j], py * xk[j]) + fma(pu, vk[j], pv * uk[j]);
+    if (w.cnt > 2) {  // clades with more than 64 same-branch terms
+#pragma unroll
+        for (int j = 0; j < KC; j++) {
+            double r0, rk;
+            term_sum<false>(s_dents, (uint32_t)(w.first + 2 * w.gsz), (uint32_t)(w.first + w.cnt * w.gsz), (uint32_t)w.gsz,
+                            src, K, min(w.kb + j, K - 1), src, K, min(w.kb + j, K - 1), r0, rk);
+            if (j == 0) s0 += r0;
+            sk[j] += rk;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < KC; j++) part[j] = (w.kb + j == 0) ? c0.y * s0 : fma(c0.y, sk[j], ck[j].y * s0);
+}
+
+template <int KC>
+__device__ __forceinline__ void lane_finish(const LaneSK& w, int wg, double (&part)[KC], const double* __restrict__ src,
+                                            double* __restrict__ dst, double2 c0, const double2 (&ck)[KC], int K, int C,
+                                            int i, double* ellp) {
+    const double o0 = src[w.c0k];
+    double ok[KC];
+#pragma unroll
+    for (int j = 0; j < KC; j++) ok[j] = src[w.c0k + min(w.kb + j, K - 1)];
+    for (int step = 1; step < wg; step <<= 1) {
+#pragma unroll
+        for (int j = 0; j < KC; j++) {
+            const double t = SHFL_DOWN(part[j], step);
+            if (step < w.gsz) part[j] += t;
+        }
+    }
+    if (w.lead) {
+#pragma unroll
+        for (int j = 0; j < KC; j++) {
+            const int k = w.kb + j;
+            if (k < K) {
+                const double r = k == 0 ? fma(c0.x, o0, part[j]) : fma(c0.x, ok[j], fma(ck[j].x, o0, part[j]));
+                dst[w.c0k + k] = r;
+                if (ellp && k == 0) ellp[(size_t)i * C + w.c0k / K] = r;
+            }
+        }
+    }
+}
+
+// NWB: warps of the scope (1: a warp working alone — leaf branches; else the CTA's warp count).
+// PPG: the ϕ/ψ rows are read from global memory (prefetched one slice ahead into registers) instead of the
+// staging buffer.  KC: components per lane.
+template <int NWB, bool PPG, int KC>
+__device__ __noinline__ void run_slices(int n, int C, int K, double* fin, double* scr, double* cur,
+                                           const Slot* s_slots, int nslots, const Ent* s_dents, const double2* pprow,
+                                           double* ellp, int tid, int spad) {
+    constexpr int nt = NWB * 32;
+    const int total = spad * ((K + KC - 1) / KC);
+#ifdef WHALE_EMU
+    const int nwa = NWB;
+#else
+    const int nwa = min(NWB, (total + 31) >> 5);
+#endif
+    if ((tid >> 5) >= nwa) return;  // this warp owns no lane of the row
+    const int npass = (total + nt - 1) / nt;
+    const int wbase = tid & ~31;
+    const LaneSK w0 = load_lane(s_slots, nslots, s_dents, spad, K, KC, total, tid);
+    const LaneSK w1 = load_lane(s_slots, nslots, s_dents, spad, K, KC, total, tid + nt);
+    const int wg0 = warp_team(s_slots, nslots, spad, total, wbase);
+    const int wg1 = warp_team(s_slots, nslots, spad, total, wbase + nt);
+    int k0[KC], k1[KC];
+#pragma unroll
+    for (int j = 0; j < KC; j++) { k0[j] = min(w0.kb + j, K - 1); k1[j] = min(w1.kb + j, K - 1); }
+    double2 n0 = make_double2(0.0, 0.0), nk0[KC], nk1[KC];
+    if (PPG) {
+#pragma unroll
+        for (int j = 0; j < KC; j++) { nk0[j] = n0; nk1[j] = n0; }
+        if (n >= 1) {
+            n0 = __ldg(pprow + K);
+#pragma unroll
+            for (int j = 0; j < KC; j++) { nk0[j] = __ldg(pprow + K + k0[j]); nk1[j] = __ldg(pprow + K + k1[j]); }
+        }
+    }
     for (int i = 1; i <= n; i++) {
         const double* src = cur;
         double* dst = (cur == fin) ? scr : fin;
-        terms<false>(s_dents, 0, nd, src, K, nullptr, src, K, nullptr, K, prod, cap, tid, nt);
-        double2 n0 = c0, nk = ck;  // prefetch the next slice's ϕ/ψ while this one is computed
-        if (on && i < n) { n0 = __ldg(pprow + (size_t)(i + 1) * K); nk = __ldg(pprow + (size_t)(i + 1) * K + k); }
-        scope_sync<WARP>();
-        if (on)
-            for (int c = grp; c < C; c += GP) {
-                uint32_t tb = tb0, te = te0;
-                if (c != grp) { tb = s_dptr[c]; te = s_dptr[c + 1]; }
-                double s0, sk;
-                cellsum(prod, cap, k, tb, te, s0, sk);
-                const double o0 = src[c * K], ok = src[c * K + k];
-                const double r = c0.x * ok + c0.y * sk + m * (ck.x * o0 + ck.y * s0);
-                dst[c * K + k] = r;
-                if (ellp && k == 0) ellp[(size_t)i * C + c] = r;
+        const double2* ppi = pprow + (size_t)i * K;
+        double2 c0, ck0[KC], ck1[KC];
+        if (PPG) {
+            c0 = n0;
+#pragma unroll
+            for (int j = 0; j < KC; j++) { ck0[j] = nk0[j]; ck1[j] = nk1[j]; }
+            if (i < n) {
+                n0 = __ldg(ppi + K);
+#pragma unroll
+                for (int j = 0; j < KC; j++) { nk0[j] = __ldg(ppi + K + k0[j]); nk1[j] = __ldg(ppi + K + k1[j]); }
             }
-        c0 = n0;
-        ck = nk;
+        } else {
+            c0 = ppi[0];
+#pragma unroll
+            for (int j = 0; j < KC; j++) { ck0[j] = ppi[k0[j]]; ck1[j] = ppi[k1[j]]; }
+        }
+        if (wg1) {  // both lane sets: issue the loads of both before either reduction
+            double p0[KC], p1[KC];
+            lane_partial<KC>(w0, src, c0, ck0, s_dents, K, p0);
+            lane_partial<KC>(w1, src, c0, ck1, s_dents, K, p1);
+            lane_finish<KC>(w0, wg0, p0, src, dst, c0, ck0, K, C, i, ellp);
+            lane_finish<KC>(w1, wg1, p1, src, dst, c0, ck1, K, C, i, ellp);
+        } else if (wg0) {
+            double p0[KC];
+            lane_partial<KC>(w0, src, c0, ck0, s_dents, K, p0);
+            lane_finish<KC>(w0, wg0, p0, src, dst, c0, ck0, K, C, i, ellp);
+        }
+        for (int q = 2; q < npass; q++) {  // very long rows: descriptors reloaded from shared memory
+            const int wgq = warp_team(s_slots, nslots, spad, total, wbase + q * nt);
+            if (wgq == 0) continue;
+            const LaneSK wq = load_lane(s_slots, nslots, s_dents, spad, K, KC, total, tid + q * nt);
+            double2 ckq[KC];
+            double pq[KC];
+#pragma unroll
+            for (int j = 0; j < KC; j++) ckq[j] = PPG ? __ldg(ppi + min(wq.kb + j, K - 1)) : ppi[min(wq.kb + j, K - 1)];
+            lane_partial<KC>(wq, src, c0, ckq, s_dents, K, pq);
+            lane_finish<KC>(wq, wgq, pq, src, dst, c0, ckq, K, C, i, ellp);
+        }
         cur = dst;
-        scope_sync<WARP>();
+        part_sync<NWB>(nwa);
     }
+}
+
+// components per lane: the fewest that keep the row within two lane sets per thread (at most 3)
+template <int NWB, bool PPG>
+__device__ __forceinline__ void run_slices_kc(int n, int C, int K, double* fin, double* scr, double* cur,
+                                              const Slot* s_slots, int nslots, const Ent* s_dents, const double2* pprow,
+                                              double* ellp, int tid) {
+    int spad = (nslots + 31) & ~31;
+    if (nslots < 32) { spad = 1; while (spad < nslots) spad <<= 1; }
+    const int lanes2 = 2 * NWB * 32;
+    if (spad * K <= lanes2) run_slices<NWB, PPG, 1>(n, C, K, fin, scr, cur, s_slots, nslots, s_dents, pprow, ellp, tid, spad);
+    else if (spad * ((K + 1) >> 1) <= lanes2) run_slices<NWB, PPG, 2>(n, C, K, fin, scr, cur, s_slots, nslots, s_dents, pprow, ellp, tid, spad);
+    else run_slices<NWB, PPG, 3>(n, C, K, fin, scr, cur, s_slots, nslots, s_dents, pprow, ellp, tid, spad);
+}
+
+template <bool WARP>
+__device__ __forceinline__ void scope_sync() {
+    if (WARP) __syncwarp();
+    else __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -162,12 +357,6 @@ __device__ __forceinline__ void run_slices(int n, int C, int K, double* fin, dou
 // term, a shuffle reduction inside teams that share a heavy clade, the ϕ/ψ update, one barrier.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int KMAX_FUSED = 8;
-
-#ifdef WHALE_EMU
-#define SHFL_DOWN(v, d) emu::shfl_down(v, d)
-#else
-#define SHFL_DOWN(v, d) __shfl_down_sync(0xffffffffu, v, d)
-#endif
 
 template <int K>
 struct LaneWork {
@@ -286,7 +475,7 @@ __device__ __noinline__ void run_slices_fused(int n, int C, double* fin, double*
 }
 
 // dispatch on the branch's component count (leaf branches carry at most value + own λ, μ: K <= 3)
-template <bool WARP, int KCAP>
+template <bool WARP>
 __device__ __forceinline__ bool run_slices_fused_k(int K, int n, int C, double* fin, double* scr, double* cur,
                                                    const Slot* s_slots, int nslots, const Ent* s_dents,
                                                    const double2* pprow, double* ellp, int tid, int nt) {
@@ -297,28 +486,23 @@ __device__ __forceinline__ bool run_slices_fused_k(int K, int n, int C, double* 
             default: return false;
         }
     } else {
-        if (KCAP <= 6) {
-            switch (K) {
-                CASEK(1) CASEK(2) CASEK(3) CASEK(4) CASEK(5) CASEK(6)
-                default: return false;
-            }
-        } else {
-            switch (K) {
-                CASEK(1) CASEK(2) CASEK(3) CASEK(4) CASEK(5) CASEK(6) CASEK(7) CASEK(8)
-                default: return false;
-            }
+        switch (K) {
+            CASEK(1) CASEK(2) CASEK(3) CASEK(4) CASEK(5) CASEK(6) CASEK(7) CASEK(8)
+            default: return false;
         }
     }
 #undef CASEK
 }
 
-// KCAP: largest component count with a fused slice loop compiled in (6 or 8); plans with larger K use the
-// generic two-phase slice loop
-template <int NT, int MINB, int KCAP>
+template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
     EXTERN_SHARED(smem_raw);
     constexpr int NW = NT / 32;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // Warps are bound to the SM's four schedulers by their index, and the work of a row fills warps from the
+    // first one up, so co-resident families would all load the same scheduler: rotate the warp roles per CTA.
+    const int lane = threadIdx.x & 31;
+    const int warp = (int)(((threadIdx.x >> 5) + ((blockIdx.x * 2654435761u) >> 13)) % NW);
+    const int tid = warp * 32 + lane;
     const ModelDev& M = A.M;
     const PlanDev& PL = A.PL;
     const int nn = M.nn, Kmax = PL.Kmax;
@@ -326,7 +510,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
     const FamHdr* Hp = A.hdr + fam;
     const uint64_t base = Hp->base;
     const uint32_t nlev = Hp->nlev, blob_bytes = Hp->blob_bytes;
-    const uint32_t rows_len = Hp->rows_len[A.plan], scr_len = Hp->scr_len[A.plan], prod_len = Hp->prod_len[A.plan];
+    const uint32_t rows_len = Hp->rows_len[A.plan], scr_len = Hp->scr_len[A.plan];
     const uint32_t leafmax = Hp->leafmax[A.plan];
     const uint32_t stage_bytes = Hp->stage_bytes[A.plan], leaf_stage = Hp->leaf_stage;
     const unsigned char* blob = A.arena + base;
@@ -351,17 +535,15 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
     const size_t hdr_bytes = (((7 * nn + 1) * sizeof(int) + (size_t)nn * 2 * Kmax * sizeof(int16_t)) + 15) & ~size_t(15);
     double* rows = reinterpret_cast<double*>(smem_raw + hdr_bytes);
     double* scr = rows + rows_len;
-    double* prod = scr + scr_len;
-    unsigned char* stage = reinterpret_cast<unsigned char*>(prod + prod_len);
+    unsigned char* stage = reinterpret_cast<unsigned char*>(scr + scr_len);
     unsigned char* leaf_area = stage + stage_bytes;
     const size_t leaf_area_bytes = (size_t)leafmax * sizeof(double) + leaf_stage;
     for (int i = tid; i < nn; i += NT) {
         s_kind[i] = M.kind[i]; s_nsl[i] = M.nsl[i]; s_ch0[i] = M.child0[i]; s_ch1[i] = M.child1[i];
         s_K[i] = PL.K[i]; s_toff[i] = PL.toff[i];
+        s_roff[i] = (int)A.roff[(size_t)fam * nn + i];
     }
     for (int i = tid; i < nn * 2 * Kmax; i += NT) s_cmap[i] = PL.cmap[i];
-    __syncthreads();
-    for (int i = tid; i < nn; i += NT) s_roff[i] = (int)A.roff[(size_t)fam * nn + i];
     __syncthreads();
     double* const ell_base = A.ell ? A.ell + Hp->ell_off : nullptr;
     auto ell_of = [&](int e) -> double* {  // node e's matrix inside the family's ℓ (node-index order)
@@ -396,7 +578,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
             }
             continue;
         }
-        if (R.nslots > 32 && !(R.nonleaf == 0 && A.skip_leaf)) continue;  // heavy branch: whole CTA, below
+        if (R.nslots > HEAVY_SLOTS && !(R.nonleaf == 0 && A.skip_leaf)) continue;  // heavy branch: whole CTA, below
         if (R.nonleaf == 0 && A.skip_leaf) {  // family-independent: ℓ_n = leafℙ·Πϕ_i from k_tables
             for (int i = lane; i < C * K; i += 32) fin[i] = PL.leaf[e * Kmax + (i % K)];
             continue;
@@ -417,16 +599,18 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         }
         stage_wait();
         __syncwarp();
-        run_slices_fused_k<true, KCAP>(K, n, C, fin, wscr, cur, reinterpret_cast<const Slot*>(wst + nd16), (int)R.nslots,
-                                 reinterpret_cast<const Ent*>(wst), PL.pp + s_toff[e], ellp, lane, 32);
+        if (!run_slices_fused_k<true>(K, n, C, fin, wscr, cur, reinterpret_cast<const Slot*>(wst + nd16), (int)R.nslots,
+                                      reinterpret_cast<const Ent*>(wst), PL.pp + s_toff[e], ellp, lane, 32))
+            run_slices_kc<1, true>(n, C, K, fin, wscr, cur, reinterpret_cast<const Slot*>(wst + nd16), (int)R.nslots,
+                                   reinterpret_cast<const Ent*>(wst), PL.pp + s_toff[e], ellp, lane);
     }
     __syncthreads();
-    // leaf branches with many in-paralog clades (more lanes of work than one warp): all warps cooperate
+    // leaf branches with many in-paralog clades (more lanes of work than one warp handles well): whole CTA
     for (int li = 0; li < M.nleafnodes; li++) {
         const int e = M.leafnodes[li];
         const NodeRec R = nrec[e];
         const int C = (int)R.C;
-        if (C == 0 || R.nslots <= 32 || (R.nonleaf == 0 && A.skip_leaf) || (A.skip_leaf && R.sptr_off)) continue;
+        if (C == 0 || R.nslots <= HEAVY_SLOTS || (R.nonleaf == 0 && A.skip_leaf) || (A.skip_leaf && R.sptr_off)) continue;
         const int K = s_K[e], n = s_nsl[e];
         double* fin = rows + s_roff[e];
         double* ellp = ell_of(e);
@@ -445,9 +629,10 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         }
         stage_wait();
         __syncthreads();
-        run_slices_fused_k<false, KCAP>(K, n, C, fin, scr, cur, reinterpret_cast<const Slot*>(st4 + nd16), (int)R.nslots,
+        run_slices_fused_k<false>(K, n, C, fin, scr, cur, reinterpret_cast<const Slot*>(st4 + nd16), (int)R.nslots,
                                   reinterpret_cast<const Ent*>(st4), reinterpret_cast<const double2*>(st4 + nd16 + sl16),
                                   ellp, tid, NT);
+        __syncthreads();
     }
     const long long tcB = CLOCK64();
 
@@ -460,43 +645,44 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         const int kind = s_kind[e], K = s_K[e], n = s_nsl[e];
         double* fin = rows + s_roff[e];
         double* ellp = ell_of(e);
-        const int cap = (int)(prod_len / K);
-        const bool fused = K <= KCAP;
-        // lane -> (cell group, component) for the P2 passes of row 1
-        const int GP = NT / K;
-        const int grp = tid / K, k = tid - grp * K;
-        const bool on = grp < GP;
-        const double m = k == 0 ? 0.0 : 1.0;
+        const bool pps = K <= 8;  // ϕ/ψ rows staged in shared memory (else read from global, prefetched)
 
         const long long tst = CLOCK64();
-        // ---- stage this node's lists: [dents | slots | dptr | tptr,lossF,lossG,lev | ϕψ rows] ----
+        // ---- stage this node's lists: [dents | slots | dptr | tptr,lossF,lossG,lev | tents | ϕψ rows] ----
         const int nd16 = (kind == WHALE_ROOT) ? 0 : (int)R.ndent;  // Πroot terms are read once: stay global
         const int sl16 = (kind == WHALE_ROOT) ? 0 : (((int)R.nslots + 1) >> 1);
         const int dp16 = (C + 1 + 3) >> 2;
         const int tp16 = (kind == WHALE_WGD) ? 0 : ((3 * C + 1 + (kind == WHALE_ROOT ? (int)nlev + 1 : 0) + 3) >> 2);
-        const int pp16 = fused ? (n + 1) * K : 0;
+        const int tn16 = (kind == WHALE_INTERNAL) ? (int)R.ntent : 0;
+        const int pp16 = pps ? (n + 1) * K : 0;
         uint4* st4 = reinterpret_cast<uint4*>(stage);
         copy16(st4, reinterpret_cast<const uint4*>(ents + R.dent_off), nd16, tid, NT);
         copy16(st4 + nd16, reinterpret_cast<const uint4*>(words + R.slot_off), sl16, tid, NT);
-        copy16(st4 + nd16 + sl16, reinterpret_cast<const uint4*>(words + R.dptr_off), dp16, tid, NT);
-        copy16(st4 + nd16 + sl16 + dp16, reinterpret_cast<const uint4*>(words + R.tptr_off), tp16, tid, NT);
-        copy16(st4 + nd16 + sl16 + dp16 + tp16, reinterpret_cast<const uint4*>(PL.pp + s_toff[e]), pp16, tid, NT);
+        uint4* st5 = st4 + nd16 + sl16;
+        copy16(st5, reinterpret_cast<const uint4*>(words + R.dptr_off), dp16, tid, NT);
+        copy16(st5 + dp16, reinterpret_cast<const uint4*>(words + R.tptr_off), tp16, tid, NT);
+        copy16(st5 + dp16 + tp16, reinterpret_cast<const uint4*>(ents + R.tent_off), tn16, tid, NT);
+        copy16(st5 + dp16 + tp16 + tn16, reinterpret_cast<const uint4*>(PL.pp + s_toff[e]), pp16, tid, NT);
         stage_wait();
         const Ent* s_dents = reinterpret_cast<const Ent*>(stage);
         const Slot* s_slots = reinterpret_cast<const Slot*>(st4 + nd16);
-        const uint32_t* s_dptr = reinterpret_cast<const uint32_t*>(st4 + nd16 + sl16);
-        const uint32_t* s_tptr = reinterpret_cast<const uint32_t*>(st4 + nd16 + sl16 + dp16);
+        const uint32_t* s_dptr = reinterpret_cast<const uint32_t*>(st5);
+        const uint32_t* s_tptr = reinterpret_cast<const uint32_t*>(st5 + dp16);
         const int32_t* s_lossF = reinterpret_cast<const int32_t*>(s_tptr + C + 1);
         const int32_t* s_lossG = s_lossF + C;
         const uint32_t* s_lev = reinterpret_cast<const uint32_t*>(s_lossG + C);
-        const double2* s_pp = reinterpret_cast<const double2*>(st4 + nd16 + sl16 + dp16 + tp16);
+        const Ent* s_tents = reinterpret_cast<const Ent*>(st5 + dp16 + tp16);
+        const double2* s_pp = reinterpret_cast<const double2*>(st5 + dp16 + tp16 + tn16);
         auto slices = [&](double* cur) {
             const long long ts = CLOCK64();
             acc_row1 += ts - tc1;
-            if (!run_slices_fused_k<false, KCAP>(K, n, C, fin, scr, cur, s_slots, (int)R.nslots, s_dents, s_pp, ellp, tid, NT))
-                run_slices<false>(n, C, K, fin, scr, cur, s_dents, s_dptr, R.ndent, PL.pp + s_toff[e], prod, cap, ellp,
-                                  tid, NT);
-            acc_slices += CLOCK64() - ts;
+            if (A.tim && tid == 0 && oi < TIMN) A.tim[(size_t)fam * TIMW + 8 + TIMN + oi] = ts - tst;
+            if (pps) run_slices_fused_k<false>(K, n, C, fin, scr, cur, s_slots, (int)R.nslots, s_dents, s_pp, ellp, tid, NT);
+            else run_slices_kc<NW, true>(n, C, K, fin, scr, cur, s_slots, (int)R.nslots, s_dents, PL.pp + s_toff[e], ellp, tid);
+            __syncthreads();  // the last row is complete for every warp; the staging buffer may be reused
+            const long long tse = CLOCK64();
+            acc_slices += tse - ts;
+            if (A.tim && tid == 0 && oi < TIMN) A.tim[(size_t)fam * TIMW + 8 + oi] = tse - ts;
         };
 
         // children, shared by the row-1 formulas
@@ -507,48 +693,28 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         const double* finF = rows + s_roff[f];
         const int16_t* mapF = s_cmap + (e * 2 + 0) * Kmax;
         const int16_t* mapG = s_cmap + (e * 2 + 1) * Kmax;
-        const int kf = mapF[k];
         double* cur = (n & 1) ? scr : fin;  // row i lives in fin iff (n − i) is even
+        __syncthreads();  // staged lists visible
 
         if (kind == WHALE_WGD) {
             // q·Σ p ℓ_f[γ1]ℓ_f[γ2] + (1−q+2qϵ_f)·ℓ_f[γ]   src/core.jl:103-119,187-199
-            __syncthreads();
             const double cx0 = PL.cx[e * Kmax], cy0 = PL.cy[e * Kmax];
-            const double cxk = PL.cx[e * Kmax + k], cyk = PL.cy[e * Kmax + k];
-            // retention terms in windows of `cap` products, whole cells at a time
-            int cA = 0;
-            while (cA < C) {
-                const uint32_t ta = s_dptr[cA];
-                int cB = cA;
-                while (cB < C && s_dptr[cB + 1] - ta <= (uint32_t)cap) cB++;
-                const bool big = cB == cA;  // a single cell with more than `cap` terms: serial sum
-                if (big) cB = cA + 1;
-                else terms<false>(s_dents, ta, s_dptr[cB], finF, KF, mapF, finF, KF, mapF, K, prod, cap, tid, NT);
-                __syncthreads();
-                if (on)
-                    for (int c = cA + grp; c < cB; c += GP) {
-                        double s0 = 0.0, sk = 0.0;
-                        if (!big) cellsum(prod, cap, k, s_dptr[c] - ta, s_dptr[c + 1] - ta, s0, sk);
-                        else {
-                            for (uint32_t t = s_dptr[c]; t < s_dptr[c + 1]; t++) {
-                                const Ent en = s_dents[t];
-                                const double* xp = finF + en.i1 * KF;
-                                const double* yp = finF + en.i2 * KF;
-                                const double xv = kf >= 0 ? xp[kf] : 0.0, yv = kf >= 0 ? yp[kf] : 0.0;
-                                s0 = fma(en.p * xp[0], yp[0], s0);
-                                sk += fma(en.p * xp[0], yv, (en.p * yp[0]) * xv);
-                            }
-                            if (k == 0) sk = s0;
-                        }
-                        const double u0 = finF[c * KF];
-                        const double uk = kf >= 0 ? finF[c * KF + kf] : 0.0;
-                        const double r = cy0 * sk + cx0 * uk + m * (cyk * s0 + cxk * u0);
-                        cur[c * K + k] = r;
-                        if (ellp && k == 0) ellp[c] = r;
-                    }
-                __syncthreads();
-                cA = cB;
+            for (int u = tid; u < C * K; u += NT) {
+                const int c = u / K, k = u - c * K;
+                const int kf = mapF[k];
+                double s0, sk;
+                term_sum<false>(s_dents, s_dptr[c], s_dptr[c + 1], 1u, finF, KF, kf, finF, KF, kf, s0, sk);
+                const double u0 = finF[c * KF];
+                double r;
+                if (k == 0) r = fma(cy0, s0, cx0 * u0);
+                else {
+                    const double uk = kf >= 0 ? finF[c * KF + kf] : 0.0;
+                    r = fma(cy0, sk, fma(cx0, uk, fma(PL.cy[e * Kmax + k], s0, PL.cx[e * Kmax + k] * u0)));
+                }
+                cur[u] = r;
+                if (ellp && k == 0) ellp[c] = r;
             }
+            __syncthreads();
             slices(cur);
             continue;
         }
@@ -556,109 +722,70 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         // internal node or root: speciation + loss from the children's last rows (src/core.jl:160-176)
         const int KG = s_K[g];
         const double* finG = rows + s_roff[g];
-        const int kg = mapG[k];
         const double* epsF = PL.eps + s_toff[f] + (size_t)s_nsl[f] * KF;
         const double* epsG = PL.eps + s_toff[g] + (size_t)s_nsl[g] * KG;
         const double ef0 = epsF[0], eg0 = epsG[0];
-        const double efk = (k > 0 && kf >= 0) ? epsF[kf] : 0.0;
-        const double egk = (k > 0 && kg >= 0) ? epsG[kg] : 0.0;
-        const Ent* g_tents = ents + R.tent_off;
-        __syncthreads();  // staged lists visible
         if (kind == WHALE_INTERNAL) {
-            // speciation terms may exceed the product window: process them in windows of `cap` terms, whole
-            // cells at a time (a single cell with more than `cap` terms falls back to a serial sum)
-            int cA = 0;
-            while (cA < C) {
-                const uint32_t ta = s_tptr[cA];
-                int cB = cA;
-                while (cB < C && s_tptr[cB + 1] - ta <= (uint32_t)cap) cB++;
-                if (cB == cA) {
-                    if (tid < K) {
-                        double s0 = 0.0, sk = 0.0;
-                        for (uint32_t t = ta; t < s_tptr[cA + 1]; t++) {
-                            const Ent en = g_tents[t];
-                            const double* xp = finF + en.i1 * KF;
-                            const double* yp = finG + en.i2 * KG;
-                            const double xv = kf >= 0 ? xp[kf] : 0.0, yv = kg >= 0 ? yp[kg] : 0.0;
-                            s0 = fma(en.p * xp[0], yp[0], s0);
-                            sk += fma(en.p * xp[0], yv, (en.p * yp[0]) * xv);
-                        }
-                        double l0, lk;
-                        loss_term(s_lossF[cA], s_lossG[cA], finF, KF, kf, finG, KG, kg, ef0, efk, eg0, egk, m, l0, lk);
-                        const double r = k == 0 ? s0 + l0 : sk + lk;
-                        cur[cA * K + k] = r;
-                        if (ellp && k == 0) ellp[cA] = r;
-                    }
-                    cB = cA + 1;
-                } else {
-                    terms<true>(g_tents, ta, s_tptr[cB], finF, KF, mapF, finG, KG, mapG, K, prod, cap, tid, NT);
-                    __syncthreads();
-                    if (on)
-                        for (int c = cA + grp; c < cB; c += GP) {
-                            double b0, bk, l0, lk;
-                            cellsum(prod, cap, k, s_tptr[c] - ta, s_tptr[c + 1] - ta, b0, bk);
-                            loss_term(s_lossF[c], s_lossG[c], finF, KF, kf, finG, KG, kg, ef0, efk, eg0, egk, m, l0, lk);
-                            const double r = k == 0 ? b0 + l0 : bk + lk;
-                            cur[c * K + k] = r;
-                            if (ellp && k == 0) ellp[c] = r;
-                        }
-                }
-                __syncthreads();
-                cA = cB;
+            for (int u = tid; u < C * K; u += NT) {
+                const int c = u / K, k = u - c * K;
+                const int kf = mapF[k], kg = mapG[k];
+                const double efk = (k > 0 && kf >= 0) ? epsF[kf] : 0.0;
+                const double egk = (k > 0 && kg >= 0) ? epsG[kg] : 0.0;
+                double s0, sk, l0, lk;
+                term_sum<false>(s_tents, s_tptr[c], s_tptr[c + 1], 1u, finF, KF, kf, finG, KG, kg, s0, sk);
+                loss_term(s_lossF[c], s_lossG[c], finF, KF, kf, finG, KG, kg, ef0, efk, eg0, egk, k == 0 ? 0.0 : 1.0, l0, lk);
+                const double r = k == 0 ? s0 + l0 : sk + lk;
+                cur[u] = r;
+                if (ellp && k == 0) ellp[c] = r;
             }
+            __syncthreads();
             slices(cur);
             continue;
         }
 
         // ---- root: ℓ_r[γ] = (1−η)ξ/η·a + η(1−ϵ)/ξ²·(b + c),  a = Σ p ℓ_r[γ1]ℓ_r[γ2] over the SAME row
         //      (src/core.jl:130-158) => clades in ascending size, one level (= clade size) at a time.
-        //      Per level P1 covers the level's Πroot terms (window [0, na)) and speciation terms ([na, na+nb)).
+        //      A level with few cells gives each (cell, component) a team of G adjacent lanes; every lane forms the
+        //      combined partial result of its share of the Πroot and speciation terms, so the team reduces ONE
+        //      double by shuffles.
         const double cx0 = PL.cx[e * Kmax], cy0 = PL.cy[e * Kmax];
-        const double cxk = PL.cx[e * Kmax + k], cyk = PL.cy[e * Kmax + k];
         const Ent* g_dents = ents + R.dent_off;
-        // the root works in place, so its product window spans the (idle) scratch row and the product window
-        double* const rprod = scr;
-        const int rcap = (int)((scr_len + prod_len) / K);
+        const Ent* g_tents = ents + R.tent_off;
         for (uint32_t L = 0; L < nlev; L++) {
             const int c0 = (int)s_lev[L], c1 = (int)s_lev[L + 1];
-            const uint32_t ta = s_dptr[c0], na = s_dptr[c1] - ta;
-            const uint32_t ua = s_tptr[c0], nb = s_tptr[c1] - ua;
-            const bool fits = na + nb <= (uint32_t)rcap;
-            if (fits) {
-                terms<true>(g_dents, ta, ta + na, fin, K, nullptr, fin, K, nullptr, K, rprod, rcap, tid, NT);
-                terms<true>(g_tents, ua, ua + nb, finF, KF, mapF, finG, KG, mapG, K, rprod + na, rcap, tid, NT);
-                __syncthreads();
-            }
-            if (on)
-                for (int c = c0 + grp; c < c1; c += GP) {
-                    double a0 = 0.0, ak = 0.0, b0 = 0.0, bk = 0.0, l0, lk;
-                    if (fits) {
-                        cellsum(rprod, rcap, k, s_dptr[c] - ta, s_dptr[c + 1] - ta, a0, ak);
-                        cellsum(rprod, rcap, k, na + s_tptr[c] - ua, na + s_tptr[c + 1] - ua, b0, bk);
-                    } else {  // oversized level: serial sums per lane
-                        for (uint32_t t = s_dptr[c]; t < s_dptr[c + 1]; t++) {
-                            const Ent en = g_dents[t];
-                            const double* xp = fin + en.i1 * K;
-                            const double* yp = fin + en.i2 * K;
-                            a0 = fma(en.p * xp[0], yp[0], a0);
-                            ak += fma(en.p * xp[0], yp[k], (en.p * yp[0]) * xp[k]);
-                        }
-                        for (uint32_t t = s_tptr[c]; t < s_tptr[c + 1]; t++) {
-                            const Ent en = g_tents[t];
-                            const double* xp = finF + en.i1 * KF;
-                            const double* yp = finG + en.i2 * KG;
-                            const double xv = kf >= 0 ? xp[kf] : 0.0, yv = kg >= 0 ? yp[kg] : 0.0;
-                            b0 = fma(en.p * xp[0], yp[0], b0);
-                            bk += fma(en.p * xp[0], yv, (en.p * yp[0]) * xv);
-                        }
-                        if (k == 0) { ak = a0; bk = b0; }
-                    }
-                    loss_term(s_lossF[c], s_lossG[c], finF, KF, kf, finG, KG, kg, ef0, efk, eg0, egk, m, l0, lk);
-                    const double u0 = b0 + l0, uk = k == 0 ? u0 : bk + lk;
-                    const double r = cx0 * ak + cy0 * uk + m * (cxk * a0 + cyk * u0);
-                    fin[c * K + k] = r;
-                    if (ellp && k == 0) ellp[c] = r;
+            const int groups = (c1 - c0) * K;
+            int glog = 0;  // team size from the number of cells only: the value path must not depend on the plan's K
+            while (glog < 4 && ((c1 - c0) << (glog + 1)) <= 16) glog++;
+            const int G = 1 << glog;
+            const int lanes = groups << glog;
+            for (int ub = 0; ub < lanes; ub += NT) {  // uniform trip count: the shuffles below need whole warps
+                const int u = ub + tid;
+                const int gi = u >> glog, j = u & (G - 1);
+                const bool valid = gi < groups;
+                double v = 0.0;
+                int c = 0, k = 0, kf = 0, kg = 0;
+                if (valid) {
+                    const int cc = gi / K;
+                    c = c0 + cc; k = gi - cc * K;
+                    kf = mapF[k]; kg = mapG[k];
+                    double a0, ak, b0, bk;
+                    term_sum<true>(g_dents, s_dptr[c] + j, s_dptr[c + 1], (uint32_t)G, fin, K, k, fin, K, k, a0, ak);
+                    term_sum<true>(g_tents, s_tptr[c] + j, s_tptr[c + 1], (uint32_t)G, finF, KF, kf, finG, KG, kg, b0, bk);
+                    if (k == 0) v = fma(cx0, a0, cy0 * b0);
+                    else v = fma(cx0, ak, fma(cy0, bk, fma(PL.cx[e * Kmax + k], a0, PL.cy[e * Kmax + k] * b0)));
                 }
+                for (int step = 1; step < G; step <<= 1) v += SHFL_DOWN(v, step);
+                if (valid && j == 0) {
+                    const double efk = (k > 0 && kf >= 0) ? epsF[kf] : 0.0;
+                    const double egk = (k > 0 && kg >= 0) ? epsG[kg] : 0.0;
+                    double l0, lk;
+                    loss_term(s_lossF[c], s_lossG[c], finF, KF, kf, finG, KG, kg, ef0, efk, eg0, egk, k == 0 ? 0.0 : 1.0, l0, lk);
+                    if (k == 0) v = fma(cy0, l0, v);
+                    else v = fma(cy0, lk, fma(PL.cy[e * Kmax + k], l0, v));
+                    fin[c * K + k] = v;
+                    if (ellp && k == 0) ellp[c] = v;
+                }
+            }
             __syncthreads();
         }
         if (tid < K) {  // log L and its gradient (src/core.jl:35-36)
@@ -670,7 +797,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         }
         if (A.tim && tid == 0) {
             const long long te = CLOCK64();
-            long long* T = A.tim + (size_t)fam * 8;
+            long long* T = A.tim + (size_t)fam * TIMW;
             T[0] = tcA - tc0;            // prologue
             T[1] = tcB - tcA;            // leaf phase (incl. waiting for the slowest warp)
             T[2] = acc_stage;            // staging copies issued (phase B)

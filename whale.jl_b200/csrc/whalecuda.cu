@@ -112,13 +112,13 @@ static int dp_nt() {
 static int dp_minb() {  // resident CTAs per SM the register cap is chosen for
     static int mb = [] {
         const int nt = dp_nt(), v = env_int("WHALE_MINB", 0);
-        if (nt == 64) return 12;
-        if (nt == 256) return 2;
-        return (v == 6 || v == 7) ? v : 5;
+        if (nt == 64) return (v == 6 || v == 8 || v == 10) ? v : 12;
+        if (nt == 256) return v == 3 ? 3 : 2;
+        return (v == 3 || v == 5 || v == 6 || v == 7) ? v : 4;
     }();
     return mb;
 }
-#define DP_VARIANTS(X) X(64, 12, 6) X(64, 12, 8) X(128, 5, 6) X(128, 6, 6) X(128, 7, 6) X(128, 5, 8) X(256, 2, 6) X(256, 2, 8)
+#define DP_VARIANTS(X) X(64, 6) X(64, 8) X(64, 10) X(64, 12) X(128, 3) X(128, 4) X(128, 5) X(128, 6) X(128, 7) X(256, 2) X(256, 3)
 constexpr int MAX_BINS = 8;
 struct Bin {
     int off, count;
@@ -154,7 +154,7 @@ struct whale_data {
     std::vector<int> perm[MAXPLAN];
     std::vector<Bin> bins[MAXPLAN];
     // per family x node facts kept from packing (shared-memory budgets are recomputed per plan)
-    std::vector<uint32_t> f_ndent, f_ntent, f_nslots, f_stage16, f_rootwin;
+    std::vector<uint32_t> f_ndent, f_ntent, f_heavy, f_stage16, f_rootwin;
     std::vector<GraphSlot> graphs;
     double last_bt_ms = 0.0;
     std::vector<uint32_t> roff_host[MAXPLAN];
@@ -426,31 +426,24 @@ static size_t set_budgets(whale_data* D, int g, const Plan& pl) {
     for (int f = 0; f < D->F; f++) {
         FamHdr& H = D->hdr[f];
         const std::vector<uint32_t>& Cs = D->famC[f];
-        const uint32_t* nd = D->f_ndent.data() + (size_t)f * nn;
-        const uint32_t* nt = D->f_ntent.data() + (size_t)f * nn;
-        const uint32_t* ns = D->f_nslots.data() + (size_t)f * nn;
+        const uint32_t* ns = D->f_heavy.data() + (size_t)f * nn;  // heavy-leaf flags
         const uint32_t* s16 = D->f_stage16.data() + (size_t)f * nn;
-        uint32_t mxinner = 0, mxleaf = 0, prod = 0;
+        uint32_t mxinner = 0, mxleaf = 0;
+        const uint32_t prod = 0;
         size_t stg = 0;
-        constexpr uint32_t PROD_CAP = 128;  // row-1 products are formed in windows of at most this many terms
         for (int e = 0; e < nn; e++) {
             const uint32_t K = (uint32_t)pl.K[e], ck = Cs[e] * K;
-            if (s16[e] > 0)  // lists + the ϕ/ψ rows of the fused slice loop (K <= 8)
+            if (s16[e] > 0)  // lists + (inner nodes with K <= 8) the ϕ/ψ rows
                 stg = std::max(stg, (size_t)s16[e] + (K <= 8 ? (size_t)(m->nsl[e] + 1) * K : 0));
             if (m->kind[e] == WHALE_LEAF) {
-                if (ns[e] <= 32) mxleaf = std::max(mxleaf, ck);
+                if (!ns[e]) mxleaf = std::max(mxleaf, ck);
                 else mxinner = std::max(mxinner, ck);  // heavy leaf branch: block-scope scratch row
             } else if (m->kind[e] != WHALE_ROOT) {
                 mxinner = std::max(mxinner, ck);
-                const uint32_t row1 = std::min(PROD_CAP, m->kind[e] == WHALE_WGD ? nd[e] : nt[e]);
-                prod = std::max(prod, (K <= 8 ? row1 : std::max(row1, nd[e])) * K);  // K > 8: generic slice loop
             }
         }
         auto even = [](uint32_t v) { return (v + 1) & ~1u; };
         const uint32_t scr = even(mxinner);
-        // the root's levels use scratch row + product window together; size them so every level fits
-        const uint32_t rootneed = std::max(64u, D->f_rootwin[f]) * (uint32_t)pl.K[m->root];
-        if (scr + prod < rootneed) prod = rootneed - scr;
         std::vector<int> roff(nn + 1);
         const int rows = place_rows(nn, (int)m->leafnodes.size(), m->leafnodes.data(), (int)m->inner.size(), m->inner.data(),
                                     m->child0.data(), m->child1.data(), m->kind.data(),
@@ -462,6 +455,10 @@ static size_t set_budgets(whale_data* D, int g, const Plan& pl) {
         H.leafmax[g] = even(mxleaf);
         H.stage_bytes[g] = (uint32_t)(16 * stg);
         worst = std::max(worst, smem_need(m, H, g, pl.Kmax));
+        if (env_int("WHALE_DEBUG", 0) >= 2)
+            fprintf(stderr, "[whale] fam %d plan %d: G %u rows %u scr %u prod %u leafmax %u stage %u leaf_stage %u -> %zu B\n", f, g,
+                    H.G, H.rows_len[g], H.scr_len[g], H.prod_len[g], H.leafmax[g], H.stage_bytes[g], H.leaf_stage,
+                    smem_need(m, H, g, pl.Kmax));
     }
     return worst;
 }
@@ -560,7 +557,7 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
                 R.ndent = (uint32_t)entsv.size() - R.dent_off;
                 wk += (double)R.ndent * (m->nsl[e] + 1) + (double)C * (m->nsl[e] + 1);
             }
-            // (1b) the slice loop's lane table: teams of 2^glog lanes per clade, at most ~2 terms per lane,
+            // (1b) the slice loop's lane table: teams of 2^glog slots per clade, at most two terms per slot (E <= 64),
             //      largest teams first (keeps teams aligned and makes the team size warp-uniform-monotone)
             pad4(wordsv);
             R.slot_off = (uint32_t)wordsv.size();
@@ -679,14 +676,15 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
             pad4(wordsv);
             for (int j = 0; j < C; j++) wordsv.push_back((uint32_t)d->compat[coff[e] + j]);
             if (kind == WHALE_LEAF) {
-                if (R.nslots <= 32) leaf_stage = std::max(leaf_stage, 16 * ((size_t)R.ndent + ((size_t)R.nslots + 1) / 2));
-                else stage16[e] = (size_t)R.ndent + ((size_t)R.nslots + 1) / 2;  // heavy leaf branch: block scope
-            } else {  // what k_dp stages in shared memory for this node
+                const size_t l16 = (size_t)R.ndent + ((size_t)R.nslots + 1) / 2;  // [dents | slots]
+                if (R.nslots <= HEAVY_SLOTS) leaf_stage = std::max(leaf_stage, 16 * l16);
+                else stage16[e] = l16;  // heavy leaf branch: block scope
+            } else {  // what k_dp stages in shared memory for this node: [dents | slots | dptr | tptr.. | tents]
                 size_t nd16 = kind == WHALE_ROOT ? 0 : R.ndent;
-                size_t sl16 = kind == WHALE_ROOT ? 0 : ((size_t)R.nslots + 1) / 2;
-                size_t dp16 = ((size_t)C + 1 + 3) / 4;
+                size_t dp16 = ((size_t)C + 1 + 3) / 4 + (kind == WHALE_ROOT ? 0 : ((size_t)R.nslots + 1) / 2);
                 size_t tp16 = kind == WHALE_WGD ? 0 : (3 * (size_t)C + 1 + (kind == WHALE_ROOT ? nlev + 1 : 0) + 3) / 4;
-                stage16[e] = nd16 + sl16 + dp16 + tp16;
+                size_t tn16 = kind == WHALE_INTERNAL ? R.ntent : 0;
+                stage16[e] = nd16 + dp16 + tp16 + tn16;
             }
             ell_total += (uint64_t)(m->nsl[e] + 1) * C;
         }
@@ -701,8 +699,8 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
         for (int e = 0; e < nn; e++) {
             NodeRec& R = recs[e];
             R.dptr_off += (uint32_t)(words_at / 4);
-            R.tptr_off += (uint32_t)(words_at / 4);
             R.slot_off += (uint32_t)(words_at / 4);
+            R.tptr_off += (uint32_t)(words_at / 4);
             if (R.sptr_off) { R.sptr_off += (uint32_t)(words_at / 4); R.sent_off += (uint32_t)(ents_at / 16); }
             R.dent_off += (uint32_t)(ents_at / 16);
             R.tent_off += (uint32_t)(ents_at / 16);
@@ -721,7 +719,7 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
         for (int e = 0; e < nn; e++) {
             D->f_ndent.push_back(recs[e].ndent);
             D->f_ntent.push_back(recs[e].ntent);
-            D->f_nslots.push_back(recs[e].nslots);
+            D->f_heavy.push_back(recs[e].nslots > HEAVY_SLOTS ? 1u : 0u);
             D->f_stage16.push_back((uint32_t)stage16[e]);
         }
         D->f_rootwin.push_back(rootwin);
@@ -866,10 +864,13 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
     if (keep && !D->d_ell) CU(cudaMalloc((void**)&D->d_ell, std::max<uint64_t>(D->ell_total, 1) * sizeof(double)));
     const bool prof = (flags & WHALE_PROFILE) != 0;
     if (prof && !D->ev[0]) for (int i = 0; i < 4; i++) CU(cudaEventCreate(&D->ev[i]));
-    if (prof && !D->d_tim) CU(cudaMalloc((void**)&D->d_tim, (size_t)F * 8 * sizeof(long long)));
+    if (prof && !D->d_tim) {
+        CU(cudaMalloc((void**)&D->d_tim, (size_t)F * TIMW * sizeof(long long)));
+        CU(cudaMemset(D->d_tim, 0, (size_t)F * TIMW * sizeof(long long)));
+    }
     static thread_local bool attr_set = false;
     if (!attr_set) {
-#define SETATTR(NTV, MB, KC) CU(cudaFuncSetAttribute(k_dp<NTV, MB, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define SETATTR(NTV, MB) CU(cudaFuncSetAttribute(k_dp<NTV, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         DP_VARIANTS(SETATTR)
 #undef SETATTR
         attr_set = true;
@@ -899,10 +900,9 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
         // the ℓ kept for backtracking is written by the first pass only (values do not depend on the chunk)
         DPArgs a{m->dev, pl.dev, D->d_arena, D->d_hdr, D->d_perm[g], D->d_roff[g], out_fam, (keep && first) ? D->d_ell : nullptr, (int)g,
                  keep ? 0 : 1, (prof && first) ? D->d_tim : nullptr};
-        const int KC = pl.Kmax <= 6 ? 6 : 8;
-        const int MB = (NT == 128 && KC == 8) ? 5 : dp_minb();
+        const int MB = dp_minb();
         auto launch_bin = [&](const Bin& b, cudaStream_t s) {
-#define LAUNCHV(NTV, MBV, KCV) if (NT == NTV && MB == MBV && KC == KCV) LAUNCH((k_dp<NTV, MBV, KCV>), b.count, NTV, b.smem, s, a, b.off);
+#define LAUNCHV(NTV, MBV) if (NT == NTV && MB == MBV) LAUNCH((k_dp<NTV, MBV>), b.count, NTV, b.smem, s, a, b.off);
             DP_VARIANTS(LAUNCHV)
 #undef LAUNCHV
             g_launches++;
@@ -1154,15 +1154,32 @@ int32_t whale_last_phase_cycles(whale_data_t d, double* mean8, double* max8) {
     if (!d->ev_valid || !d->d_tim) return fail(WHALE_ERR_STATE, "last evaluation was not run with WHALE_PROFILE");
     CU(cudaSetDevice(d->m->device));
     CU(cudaEventSynchronize(d->ev[3]));
-    std::vector<long long> h((size_t)d->F * 8);
+    std::vector<long long> h((size_t)d->F * TIMW);
     CU(cudaMemcpy(h.data(), d->d_tim, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     for (int j = 0; j < 8; j++) {
         double s = 0, mx = 0;
-        for (int f = 0; f < d->F; f++) { s += (double)h[(size_t)f * 8 + j]; mx = std::max(mx, (double)h[(size_t)f * 8 + j]); }
+        for (int f = 0; f < d->F; f++) { s += (double)h[(size_t)f * TIMW + j]; mx = std::max(mx, (double)h[(size_t)f * TIMW + j]); }
         mean8[j] = s / d->F;
         max8[j] = mx;
     }
     return WHALE_OK;
+}
+
+int32_t whale_last_node_cycles(whale_data_t d, double* slices_mean, double* row1_mean, int32_t cap) {
+    if (!d || !slices_mean || !row1_mean) return fail(WHALE_ERR_ARG, "null argument");
+    if (!d->ev_valid || !d->d_tim) return fail(WHALE_ERR_STATE, "last evaluation was not run with WHALE_PROFILE");
+    CU(cudaSetDevice(d->m->device));
+    CU(cudaEventSynchronize(d->ev[3]));
+    std::vector<long long> h((size_t)d->F * TIMW);
+    CU(cudaMemcpy(h.data(), d->d_tim, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    const int n = std::min<int>({cap, TIMN, (int)d->m->inner.size()});
+    for (int j = 0; j < n; j++) {
+        double a = 0, b = 0;
+        for (int f = 0; f < d->F; f++) { a += (double)h[(size_t)f * TIMW + 8 + j]; b += (double)h[(size_t)f * TIMW + 8 + TIMN + j]; }
+        slices_mean[j] = a / d->F;
+        row1_mean[j] = b / d->F;
+    }
+    return n;
 }
 
 int32_t whale_last_tables_cycles(whale_model_t m, int32_t with_grad, double* out32) {

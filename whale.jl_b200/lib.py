@@ -22,7 +22,7 @@ SYMBOLS = ["whale_version", "whale_last_error", "whale_device_count", "whale_set
            "whale_model_destroy", "whale_data_create", "whale_data_destroy", "whale_data_nfam",
            "whale_data_arena_bytes", "whale_data_arena_dump", "whale_logpdf_grad", "whale_logpdf_grad_async",
            "whale_slices", "whale_ell_size", "whale_ell_get", "whale_backtrack", "whale_launch_count",
-           "whale_work_estimate", "whale_last_kernel_ms", "whale_last_phase_cycles", "whale_last_tables_cycles", "whale_last_backtrack_ms", "whale_fp64_peak"]
+           "whale_work_estimate", "whale_last_kernel_ms", "whale_last_phase_cycles", "whale_last_node_cycles", "whale_last_tables_cycles", "whale_last_backtrack_ms", "whale_fp64_peak"]
 
 
 class ModelDesc(C.Structure):
@@ -85,6 +85,7 @@ class Lib:
         L.whale_last_kernel_ms.argtypes = [vp, f64p, f64p, f64p]
         L.whale_last_phase_cycles.argtypes = [vp, f64p, f64p]
         L.whale_last_tables_cycles.argtypes = [vp, C.c_int32, f64p]
+        L.whale_last_node_cycles.argtypes = [vp, f64p, f64p, C.c_int32]
         L.whale_last_backtrack_ms.argtypes = [vp, f64p]
 
     def check(self, rc):
@@ -114,7 +115,7 @@ class Lib:
         return h.value
 
     def logpdf_grad(self, mh, dh, x, p_leaf, condition, want_grad=False, keep_ell=False, per_family=False,
-                    per_family_grad=False):
+                    per_family_grad=False, profile=False):
         x = np.ascontiguousarray(x, np.float64)
         pl = np.ascontiguousarray(p_leaf, np.float64)
         F = self.L.whale_data_nfam(dh)
@@ -123,7 +124,7 @@ class Lib:
         g = np.zeros(P) if want_grad else None
         lf = np.zeros(F) if per_family else None
         gf = np.zeros((F, P)) if per_family_grad else None
-        flags = (WANT_GRAD if want_grad else 0) | (KEEP_ELL if keep_ell else 0)
+        flags = (WANT_GRAD if want_grad else 0) | (KEEP_ELL if keep_ell else 0) | (PROFILE if profile else 0)
         self.check(self.L.whale_logpdf_grad(mh, dh, _ptr(x, f64p), _ptr(pl, f64p), condition, flags, C.byref(ll),
                                             _ptr(g, f64p) if want_grad else None,
                                             _ptr(lf, f64p) if per_family else None,
@@ -183,6 +184,13 @@ class Lib:
         self.check(self.L.whale_last_phase_cycles(dh, _ptr(mean, f64p), _ptr(mx, f64p)))
         names = ["prologue", "leaf_phase", "staging", "row1", "slices", "root", "total"]
         return {n: (float(mean[i]), float(mx[i])) for i, n in enumerate(names)}
+
+    def last_node_cycles(self, dh):
+        a, b = np.zeros(32), np.zeros(32)
+        n = self.L.whale_last_node_cycles(dh, _ptr(a, f64p), _ptr(b, f64p), 32)
+        if n < 0:
+            self.check(n)
+        return a[:n].tolist(), b[:n].tolist()
 
     def last_backtrack_ms(self, dh) -> float:
         ms = C.c_double()
