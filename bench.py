@@ -285,6 +285,15 @@ def main():
     except OSError:
         pass
     fp64_peak = L.fp64_peak()  # measured DFMA microbenchmark on this GPU (MEASURED_PEAKS.json has no fp64 entry)
+    # DRAM traffic of the k_dp launches of one step, from the committed `ncu --set full` capture of this command
+    # (profiles/r1_ncu_k_dp_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum over the step's k_dp launches)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_k_dp_traffic.json")))
+        if int(tj.get("families", 0)) == F:
+            traffic, traffic_src = float(tj["dram_bytes_per_step"]), tj.get("source")
+    except (OSError, ValueError, KeyError):
+        pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     ach_tf = flops / (dp_ms * 1e-3) / 1e12
     ach_gb = abytes / (dp_ms * 1e-3) / 1e9
@@ -307,7 +316,7 @@ def main():
         "kernels_ms": {"k_tables": float(kms[:, 0].mean()), "k_dp": dp_ms, "k_reduce": float(kms[:, 2].mean()),
                        "step_events": float(step_ms.mean()), "wall_per_step_incl_flush": 1e3 * wall / K},
         "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": ach_tf / fp64_peak, "traffic": None, "kernel": "k_dp<128>",
+                     "frac": ach_tf / fp64_peak, "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_dp<128,4>",
                      "flops_per_launch": flops, "peak_source": "whale_fp64_peak DFMA microbenchmark, this GPU, this run"},
         "roofline_hbm": {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s",
                          "frac": ach_gb / hbm_peak, "bytes_per_launch": abytes,

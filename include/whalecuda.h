@@ -183,6 +183,8 @@ int32_t whale_last_phase_cycles(whale_data_t d, double* mean8, double* max8);
 
 /* same evaluation, per inner node in processing order (internal / WGD nodes, the root last): mean SM cycles of
  * the slice loop and of staging + row 1; returns the number of entries written (<= cap) or a negative status */
+/* same evaluation, the eight phase counters of every family: out8[f*8 + j] */
+int32_t whale_last_family_cycles(whale_data_t d, double* out8);
 int32_t whale_last_node_cycles(whale_data_t d, double* slices_mean, double* row1_mean, int32_t cap);
 
 /* SM-cycle stamps of the last k_tables launch of the model's value / full-gradient plan: [0] metadata staged,

@@ -78,3 +78,11 @@ def test_emu_parameter_chunks(L, monkeypatch):
     passes over parameter chunks; force that with a tiny goal and compare with the oracle (37 parameters)."""
     monkeypatch.setenv("WHALE_SMEM_GOAL", "6000")
     run_parity(L, "c1_example1", sel=[3], conds=["root"])
+
+
+def test_emu_unstaged_lists(L, monkeypatch):
+    """Families whose lists exceed the staging limit (large CCDs, BASELINE config 3) are read from global memory
+    in place; force that path with a tiny limit."""
+    monkeypatch.setenv("WHALE_STAGE_MAX", "64")
+    run_parity(L, "c1_example1", sel=[5], conds=["root"])
+    _check_backtrack(L, "c1_example1", [5])

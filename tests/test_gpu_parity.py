@@ -123,6 +123,39 @@ def test_synthetic_c2_shape_vs_oracle(L, tmp_path):
     np.testing.assert_allclose(grad, og, rtol=1e-9, atol=1e-9 * np.abs(og).max())
 
 
+def test_c4_shape_vs_oracle(L, tmp_path):
+    """BASELINE config 3 shape: 30-taxon tree with 5 WGDs (64 nodes), CCDs of ~2,000 clades — lists too long to
+    stage in shared memory (read in place) and a gradient computed in parameter chunks; constant rates (P = 8)
+    and branch-wise rates (P = 122) against the oracle."""
+    from oracle import whale_oracle as wo, flat
+    from whale_jl_b200 import newick
+    tree = synth.c4_species_tree()
+    nws = newick.nwstr(tree, True) + ";"
+    d = synth.generate(str(tmp_path / "c4"), 3, seed=4, tree=synth.c4_species_tree(), **synth.C4_FAMILY)
+    q = [0.2, 0.1, 0.2, 0.1, 0.2]
+    w = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=q, eta=0.67), newick.readnw(nws), 0.05)
+    ccd = W.read_ale(d, w)
+    assert min(len(x.nleaf) for x in ccd) > 1500
+    ll, grad = W.logpdf_and_gradient(w, ccd)
+    ow = wo.WhaleModel(wo.ConstantDLWGD(lam=0.2, mu=0.3, q=q, eta=0.67), wo.readnw(nws), 0.05)
+    fm, ff = flat.FlatModel(ow), flat.FlatFams(wo.read_ale(d, ow), len(ow))
+    tot, _, og, _ = flat.logpdf(fm, ff, grad=True)
+    assert ll == pytest.approx(tot, rel=1e-9)
+    np.testing.assert_allclose(grad, og, rtol=1e-9, atol=1e-9 * np.abs(og).max())
+    assert W.logpdf(w, ccd) == pytest.approx(tot, rel=1e-9)
+    nr = 58  # non-WGD, non-root nodes carry their own rates; the root's are unused (NaN-safe)
+    rng = np.random.default_rng(5)
+    r = W.DLWGD(lam=list(rng.normal(np.log(0.15), 0.3, nr + 1)), mu=list(rng.normal(np.log(0.15), 0.3, nr + 1)), q=q, eta=0.67)
+    wb = W.WhaleModel(r, newick.readnw(nws), 0.05)
+    ccdb = W.read_ale(d, wb)
+    ll, grad = W.logpdf_and_gradient(wb, ccdb)
+    owb = wo.WhaleModel(wo.DLWGD(lam=r.lam, mu=r.mu, q=q, eta=0.67), wo.readnw(nws), 0.05)
+    fm, ff = flat.FlatModel(owb), flat.FlatFams(wo.read_ale(d, owb), len(owb))
+    tot, _, og, _ = flat.logpdf(fm, ff, grad=True)
+    assert ll == pytest.approx(tot, rel=1e-9)
+    np.testing.assert_allclose(grad, og, rtol=1e-9, atol=1e-9 * np.abs(og).max())
+
+
 def test_full_size_properties(L, tmp_path):
     """BASELINE config 1 at full size (1000 families): size-independent properties — the batch sum equals the
     sum of per-family values; shuffling families permutes per-family results and leaves the total unchanged

@@ -41,6 +41,11 @@ def main():
            "nodes": [{"node": e, "kind": int(w.kind[e]), "n_slices": int(w.n_slices[e]), "slices_cycles": round(a),
                       "per_slice": round(a / max(1, int(w.n_slices[e]))), "stage_row1_cycles": round(b)}
                      for e, a, b in zip(inner, sl, r1)]}
+    fc = L.last_family_cycles(dh)
+    order = np.argsort(-fc[:, 6])
+    out["family_total_percentiles"] = {str(q): float(np.percentile(fc[:, 6], q)) for q in (50, 90, 99, 100)}
+    out["slowest"] = [{"fam": int(f), "G": len(ccd[int(f)].nleaf), "leaves": len(ccd[int(f)].leaves),
+                       "phases": [round(v) for v in fc[f, :7]]} for f in order[:12]]
     print(json.dumps(out))
 
 

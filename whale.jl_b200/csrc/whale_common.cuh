@@ -58,7 +58,7 @@ struct Slot {
 static_assert(sizeof(Slot) == 8, "Slot must be 8 bytes");
 constexpr uint32_t HEAVY_SLOTS = 24;
 
-constexpr int MAXPLAN = 10;  // tangent plans per data handle: [0] value only, [1..] gradient (parameter chunks)
+constexpr int MAXPLAN = 64;  // tangent plans per data handle: [0] value only, [1..] gradient (parameter chunks)
 
 // Tree shapes for the closed form of leaf branches.  On a leaf branch e every leaf clade has the same
 // family-independent sequence w•_i = leafℙ·Π_{j<=i} ϕ_j, hence by induction over src/core.jl:121-128,178-185 every
@@ -84,6 +84,7 @@ struct FamHdr {
     uint32_t stage_bytes[MAXPLAN]; // staging buffer for one internal node's lists + ϕ/ψ rows (bytes, multiple of 16)
     uint32_t leaf_stage;     // per-warp staging buffer for one leaf branch's lists (bytes, multiple of 16)
     uint32_t blob_bytes;
+    uint32_t rootwin;        // most terms (Πroot + speciation) any one root level holds: size of a level buffer
 };
 
 struct ModelDev {  // structure arrays (device pointers), node index = id-1

@@ -52,6 +52,8 @@ __device__ __forceinline__ void copy16(uint4* dst, const uint4* __restrict__ src
     for (int i = tid; i < n16; i += nt) dst[i] = src[i];
 }
 __device__ __forceinline__ void stage_wait() {}
+__device__ __forceinline__ void stage_commit() {}
+__device__ __forceinline__ void stage_wait_prev() {}
 #else
 __device__ __forceinline__ void copy16(uint4* dst, const uint4* __restrict__ src, int n16, int tid, int nt) {
     for (int i = tid; i < n16; i += nt)
@@ -59,6 +61,9 @@ __device__ __forceinline__ void copy16(uint4* dst, const uint4* __restrict__ src
                      "l"(src + i) : "memory");
 }
 __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// double-buffered batches: commit the batch just issued / wait for everything but the newest batch
+__device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void stage_wait_prev() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 #endif
 
 #ifdef WHALE_EMU
@@ -538,6 +543,8 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
     unsigned char* stage = reinterpret_cast<unsigned char*>(scr + scr_len);
     unsigned char* leaf_area = stage + stage_bytes;
     const size_t leaf_area_bytes = (size_t)leafmax * sizeof(double) + leaf_stage;
+    // families whose lists are too long to stage (large CCDs) read them from global memory (L2) in place
+    const bool staged = stage_bytes != 0;
     for (int i = tid; i < nn; i += NT) {
         s_kind[i] = M.kind[i]; s_nsl[i] = M.nsl[i]; s_ch0[i] = M.child0[i]; s_ch1[i] = M.child1[i];
         s_K[i] = PL.K[i]; s_toff[i] = PL.toff[i];
@@ -615,10 +622,18 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         double* fin = rows + s_roff[e];
         double* ellp = ell_of(e);
         const int nd16 = (int)R.ndent, sl16 = ((int)R.nslots + 1) >> 1, pp16 = (n + 1) * K;
-        uint4* st4 = reinterpret_cast<uint4*>(stage);
-        copy16(st4, reinterpret_cast<const uint4*>(ents + R.dent_off), nd16, tid, NT);
-        copy16(st4 + nd16, reinterpret_cast<const uint4*>(words + R.slot_off), sl16, tid, NT);
-        copy16(st4 + nd16 + sl16, reinterpret_cast<const uint4*>(PL.pp + s_toff[e]), pp16, tid, NT);
+        const Ent* h_dents = ents + R.dent_off;
+        const Slot* h_slots = reinterpret_cast<const Slot*>(words + R.slot_off);
+        const double2* h_pp = PL.pp + s_toff[e];
+        if (staged) {
+            uint4* st4 = reinterpret_cast<uint4*>(stage);
+            copy16(st4, reinterpret_cast<const uint4*>(h_dents), nd16, tid, NT);
+            copy16(st4 + nd16, reinterpret_cast<const uint4*>(h_slots), sl16, tid, NT);
+            copy16(st4 + nd16 + sl16, reinterpret_cast<const uint4*>(h_pp), pp16, tid, NT);
+            h_dents = reinterpret_cast<const Ent*>(st4);
+            h_slots = reinterpret_cast<const Slot*>(st4 + nd16);
+            h_pp = reinterpret_cast<const double2*>(st4 + nd16 + sl16);
+        }
         double* cur = (n & 1) ? scr : fin;
         const int nleafc = C - (int)R.nonleaf;
         for (int i = tid; i < C * K; i += NT) {
@@ -629,9 +644,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         }
         stage_wait();
         __syncthreads();
-        run_slices_fused_k<false>(K, n, C, fin, scr, cur, reinterpret_cast<const Slot*>(st4 + nd16), (int)R.nslots,
-                                  reinterpret_cast<const Ent*>(st4), reinterpret_cast<const double2*>(st4 + nd16 + sl16),
-                                  ellp, tid, NT);
+        run_slices_fused_k<false>(K, n, C, fin, scr, cur, h_slots, (int)R.nslots, h_dents, h_pp, ellp, tid, NT);
         __syncthreads();
     }
     const long long tcB = CLOCK64();
@@ -656,23 +669,31 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         const int tn16 = (kind == WHALE_INTERNAL) ? (int)R.ntent : 0;
         const int pp16 = pps ? (n + 1) * K : 0;
         uint4* st4 = reinterpret_cast<uint4*>(stage);
-        copy16(st4, reinterpret_cast<const uint4*>(ents + R.dent_off), nd16, tid, NT);
-        copy16(st4 + nd16, reinterpret_cast<const uint4*>(words + R.slot_off), sl16, tid, NT);
         uint4* st5 = st4 + nd16 + sl16;
-        copy16(st5, reinterpret_cast<const uint4*>(words + R.dptr_off), dp16, tid, NT);
-        copy16(st5 + dp16, reinterpret_cast<const uint4*>(words + R.tptr_off), tp16, tid, NT);
-        copy16(st5 + dp16 + tp16, reinterpret_cast<const uint4*>(ents + R.tent_off), tn16, tid, NT);
-        copy16(st5 + dp16 + tp16 + tn16, reinterpret_cast<const uint4*>(PL.pp + s_toff[e]), pp16, tid, NT);
-        stage_wait();
-        const Ent* s_dents = reinterpret_cast<const Ent*>(stage);
-        const Slot* s_slots = reinterpret_cast<const Slot*>(st4 + nd16);
-        const uint32_t* s_dptr = reinterpret_cast<const uint32_t*>(st5);
-        const uint32_t* s_tptr = reinterpret_cast<const uint32_t*>(st5 + dp16);
+        const Ent* s_dents = ents + R.dent_off;
+        const Slot* s_slots = reinterpret_cast<const Slot*>(words + R.slot_off);
+        const uint32_t* s_dptr = words + R.dptr_off;
+        const uint32_t* s_tptr = words + R.tptr_off;
+        const Ent* s_tents = ents + R.tent_off;
+        const double2* s_pp = PL.pp + s_toff[e];
+        if (staged) {
+            copy16(st4, reinterpret_cast<const uint4*>(s_dents), nd16, tid, NT);
+            copy16(st4 + nd16, reinterpret_cast<const uint4*>(s_slots), sl16, tid, NT);
+            copy16(st5, reinterpret_cast<const uint4*>(s_dptr), dp16, tid, NT);
+            copy16(st5 + dp16, reinterpret_cast<const uint4*>(s_tptr), tp16, tid, NT);
+            copy16(st5 + dp16 + tp16, reinterpret_cast<const uint4*>(s_tents), tn16, tid, NT);
+            copy16(st5 + dp16 + tp16 + tn16, reinterpret_cast<const uint4*>(s_pp), pp16, tid, NT);
+            stage_wait();
+            s_dents = reinterpret_cast<const Ent*>(stage);
+            s_slots = reinterpret_cast<const Slot*>(st4 + nd16);
+            s_dptr = reinterpret_cast<const uint32_t*>(st5);
+            s_tptr = reinterpret_cast<const uint32_t*>(st5 + dp16);
+            s_tents = reinterpret_cast<const Ent*>(st5 + dp16 + tp16);
+            s_pp = reinterpret_cast<const double2*>(st5 + dp16 + tp16 + tn16);
+        }
         const int32_t* s_lossF = reinterpret_cast<const int32_t*>(s_tptr + C + 1);
         const int32_t* s_lossG = s_lossF + C;
         const uint32_t* s_lev = reinterpret_cast<const uint32_t*>(s_lossG + C);
-        const Ent* s_tents = reinterpret_cast<const Ent*>(st5 + dp16 + tp16);
-        const double2* s_pp = reinterpret_cast<const double2*>(st5 + dp16 + tp16 + tn16);
         auto slices = [&](double* cur) {
             const long long ts = CLOCK64();
             acc_row1 += ts - tc1;
@@ -748,11 +769,32 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         //      A level with few cells gives each (cell, component) a team of G adjacent lanes; every lane forms the
         //      combined partial result of its share of the Πroot and speciation terms, so the team reduces ONE
         //      double by shuffles.
+        //      The level's Πroot and speciation terms are staged in shared memory one level ahead (two buffers), so the
+        //      per-level critical path holds no global-memory latency.
         const double cx0 = PL.cx[e * Kmax], cy0 = PL.cy[e * Kmax];
         const Ent* g_dents = ents + R.dent_off;
         const Ent* g_tents = ents + R.tent_off;
-        for (uint32_t L = 0; L < nlev; L++) {
+        uint4* const lbuf = st5 + dp16 + tp16 + tn16 + pp16;
+        const uint32_t rootwin = Hp->rootwin;
+        auto issue_level = [&](uint32_t L) {
             const int c0 = (int)s_lev[L], c1 = (int)s_lev[L + 1];
+            const uint32_t da = s_dptr[c0], na = s_dptr[c1] - da, ta = s_tptr[c0], nb = s_tptr[c1] - ta;
+            uint4* dst = lbuf + (L & 1u) * rootwin;
+            copy16(dst, reinterpret_cast<const uint4*>(g_dents + da), (int)na, tid, NT);
+            copy16(dst + na, reinterpret_cast<const uint4*>(g_tents + ta), (int)nb, tid, NT);
+        };
+        if (staged) { issue_level(0); stage_commit(); }
+        for (uint32_t L = 0; L < nlev; L++) {
+            if (staged) {
+                if (L + 1 < nlev) issue_level(L + 1);
+                stage_commit();
+                stage_wait_prev();
+                __syncthreads();  // level L's terms are in shared memory for every thread
+            }
+            const int c0 = (int)s_lev[L], c1 = (int)s_lev[L + 1];
+            const uint32_t da = s_dptr[c0], ta = s_tptr[c0];
+            const Ent* l_dents = staged ? reinterpret_cast<const Ent*>(lbuf + (L & 1u) * rootwin) : g_dents + da;
+            const Ent* l_tents = staged ? l_dents + (s_dptr[c1] - da) : g_tents + ta;
             const int groups = (c1 - c0) * K;
             int glog = 0;  // team size from the number of cells only: the value path must not depend on the plan's K
             while (glog < 4 && ((c1 - c0) << (glog + 1)) <= 16) glog++;
@@ -769,8 +811,8 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
                     c = c0 + cc; k = gi - cc * K;
                     kf = mapF[k]; kg = mapG[k];
                     double a0, ak, b0, bk;
-                    term_sum<true>(g_dents, s_dptr[c] + j, s_dptr[c + 1], (uint32_t)G, fin, K, k, fin, K, k, a0, ak);
-                    term_sum<true>(g_tents, s_tptr[c] + j, s_tptr[c + 1], (uint32_t)G, finF, KF, kf, finG, KG, kg, b0, bk);
+                    term_sum<false>(l_dents, s_dptr[c] - da + j, s_dptr[c + 1] - da, (uint32_t)G, fin, K, k, fin, K, k, a0, ak);
+                    term_sum<false>(l_tents, s_tptr[c] - ta + j, s_tptr[c + 1] - ta, (uint32_t)G, finF, KF, kf, finG, KG, kg, b0, bk);
                     if (k == 0) v = fma(cx0, a0, cy0 * b0);
                     else v = fma(cx0, ak, fma(cy0, bk, fma(PL.cx[e * Kmax + k], a0, PL.cy[e * Kmax + k] * b0)));
                 }

@@ -453,7 +453,9 @@ static size_t set_budgets(whale_data* D, int g, const Plan& pl) {
         H.scr_len[g] = scr;
         H.prod_len[g] = even(prod);
         H.leafmax[g] = even(mxleaf);
-        H.stage_bytes[g] = (uint32_t)(16 * stg);
+        // long lists (large CCDs) are not staged: the kernel then reads them from global memory in place
+        const size_t STAGE_MAX = (size_t)env_int("WHALE_STAGE_MAX", 24 * 1024);
+        H.stage_bytes[g] = 16 * stg > STAGE_MAX ? 0u : (uint32_t)(16 * stg);
         worst = std::max(worst, smem_need(m, H, g, pl.Kmax));
         if (env_int("WHALE_DEBUG", 0) >= 2)
             fprintf(stderr, "[whale] fam %d plan %d: G %u rows %u scr %u prod %u leafmax %u stage %u leaf_stage %u -> %zu B\n", f, g,
@@ -684,7 +686,7 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
                 size_t dp16 = ((size_t)C + 1 + 3) / 4 + (kind == WHALE_ROOT ? 0 : ((size_t)R.nslots + 1) / 2);
                 size_t tp16 = kind == WHALE_WGD ? 0 : (3 * (size_t)C + 1 + (kind == WHALE_ROOT ? nlev + 1 : 0) + 3) / 4;
                 size_t tn16 = kind == WHALE_INTERNAL ? R.ntent : 0;
-                stage16[e] = nd16 + dp16 + tp16 + tn16;
+                stage16[e] = nd16 + dp16 + tp16 + tn16 + (kind == WHALE_ROOT ? 2 * (size_t)rootwin : 0);
             }
             ell_total += (uint64_t)(m->nsl[e] + 1) * C;
         }
@@ -713,6 +715,7 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
         H.nlev = nlev;
         H.leaf_stage = (uint32_t)leaf_stage;
         H.blob_bytes = (uint32_t)total;
+        H.rootwin = rootwin;
         D->work[f] = wk;
         // SURVEY §8d algorithmic bytes per evaluation: 12·T + 2·Γ + 4·Σ_e C_e
         algo_bytes += 12 * (soff[G] - soff[0]) + 2 * (int64_t)G + 4 * (int64_t)sumC;
@@ -744,8 +747,16 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
         }
         addp(m->eta_slot);
         for (int p = 0; p < m->P; p++) addp(p);  // parameters no node reads (e.g. the root's rates): zero gradient
+        // smallest chunk count (from a geometric ladder) whose worst family meets the goal; the last rung is taken
+        // as long as it fits the hardware limit at all
+        std::vector<int> ladder;
+        const int top = std::max(2, std::min(MAXPLAN - 1, m->P));
+        for (int v = 2; v < top; v = std::max(v + 1, v * 3 / 2)) ladder.push_back(v);
+        ladder.push_back(top);
         bool ok = false;
-        for (int nch = 2; nch <= MAXPLAN - 1 && !ok; nch++) {
+        for (size_t li = 0; li < ladder.size() && !ok; li++) {
+            const int nch = ladder[li];
+            const bool last = li + 1 == ladder.size();
             for (Plan& cp : D->chunk_plans) for (void* q : cp.owned) cudaFree(q);
             D->chunk_plans.assign(nch, Plan());
             D->plans.assign(1, &m->plan[0]);
@@ -759,8 +770,8 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
                 worst = std::max(worst, set_budgets(D, 1 + c, D->chunk_plans[c]));
                 kmax = std::max(kmax, D->chunk_plans[c].Kmax);
             }
-            ok = (worst <= SMEM_GOAL || (nch == MAXPLAN - 1 && worst <= SMEM_MAX)) && kmax <= dp_nt();
-            if (ok || nch == MAXPLAN - 1) {
+            ok = (worst <= SMEM_GOAL || (last && worst <= SMEM_MAX)) && kmax <= dp_nt();
+            if (ok || last) {
                 for (int c = 0; c < nch; c++) {
                     CU(upload_plan(D->chunk_plans[c], nn));
                     D->plans.push_back(&D->chunk_plans[c]);
@@ -1162,6 +1173,18 @@ int32_t whale_last_phase_cycles(whale_data_t d, double* mean8, double* max8) {
         mean8[j] = s / d->F;
         max8[j] = mx;
     }
+    return WHALE_OK;
+}
+
+int32_t whale_last_family_cycles(whale_data_t d, double* out8) {
+    if (!d || !out8) return fail(WHALE_ERR_ARG, "null argument");
+    if (!d->ev_valid || !d->d_tim) return fail(WHALE_ERR_STATE, "last evaluation was not run with WHALE_PROFILE");
+    CU(cudaSetDevice(d->m->device));
+    CU(cudaEventSynchronize(d->ev[3]));
+    std::vector<long long> h((size_t)d->F * TIMW);
+    CU(cudaMemcpy(h.data(), d->d_tim, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (int f = 0; f < d->F; f++)
+        for (int j = 0; j < 8; j++) out8[(size_t)f * 8 + j] = (double)h[(size_t)f * TIMW + j];
     return WHALE_OK;
 }
 

@@ -22,7 +22,7 @@ SYMBOLS = ["whale_version", "whale_last_error", "whale_device_count", "whale_set
            "whale_model_destroy", "whale_data_create", "whale_data_destroy", "whale_data_nfam",
            "whale_data_arena_bytes", "whale_data_arena_dump", "whale_logpdf_grad", "whale_logpdf_grad_async",
            "whale_slices", "whale_ell_size", "whale_ell_get", "whale_backtrack", "whale_launch_count",
-           "whale_work_estimate", "whale_last_kernel_ms", "whale_last_phase_cycles", "whale_last_node_cycles", "whale_last_tables_cycles", "whale_last_backtrack_ms", "whale_fp64_peak"]
+           "whale_work_estimate", "whale_last_kernel_ms", "whale_last_phase_cycles", "whale_last_node_cycles", "whale_last_family_cycles", "whale_last_tables_cycles", "whale_last_backtrack_ms", "whale_fp64_peak"]
 
 
 class ModelDesc(C.Structure):
@@ -86,6 +86,7 @@ class Lib:
         L.whale_last_phase_cycles.argtypes = [vp, f64p, f64p]
         L.whale_last_tables_cycles.argtypes = [vp, C.c_int32, f64p]
         L.whale_last_node_cycles.argtypes = [vp, f64p, f64p, C.c_int32]
+        L.whale_last_family_cycles.argtypes = [vp, f64p]
         L.whale_last_backtrack_ms.argtypes = [vp, f64p]
 
     def check(self, rc):
@@ -184,6 +185,11 @@ class Lib:
         self.check(self.L.whale_last_phase_cycles(dh, _ptr(mean, f64p), _ptr(mx, f64p)))
         names = ["prologue", "leaf_phase", "staging", "row1", "slices", "root", "total"]
         return {n: (float(mean[i]), float(mx[i])) for i, n in enumerate(names)}
+
+    def last_family_cycles(self, dh):
+        out = np.zeros((self.L.whale_data_nfam(dh), 8))
+        self.check(self.L.whale_last_family_cycles(dh, _ptr(out, f64p)))
+        return out
 
     def last_node_cycles(self, dh):
         a, b = np.zeros(32), np.zeros(32)

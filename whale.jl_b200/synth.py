@@ -234,6 +234,42 @@ def c1_species_tree() -> newick.Node:
     return t
 
 
+def random_species_tree(n_taxa: int, n_wgd: int, seed: int, height: float = 5.0) -> newick.Node:
+    """A random ultrametric species tree (coalescent-style joins, rescaled to `height` time units like
+    `Whale.extree`) with `n_wgd` WGD nodes inserted halfway along random non-root branches — the C4 shape of
+    BASELINE.json (30 taxa, 5 WGDs)."""
+    rng = np.random.default_rng([seed, n_taxa, n_wgd])
+    live = [(f"T{i:02d}", 0.0) for i in range(n_taxa)]  # (newick text, node height)
+    t = 0.0
+    while len(live) > 1:
+        k = len(live)
+        t += rng.exponential(1.0 / (k * (k - 1) / 2))
+        i, j = sorted(rng.choice(k, 2, replace=False))
+        (a, ha), (b, hb) = live[i], live[j]
+        node = (f"({a}:{t - ha:.6f},{b}:{t - hb:.6f})", t)
+        live = [x for m, x in enumerate(live) if m not in (i, j)] + [node]
+    text = live[0][0] + ";"
+    tree = newick.readnw(text)
+    scale = height / t
+    nodes = newick.postwalk(tree)
+    for n in nodes:
+        if not n.isroot:
+            n.distance *= scale
+    cand = [n for n in nodes if not n.isroot and n.distance > 0.3]
+    pick = rng.choice(len(cand), size=min(n_wgd, len(cand)), replace=False)
+    for w, i in enumerate(sorted(pick)):
+        newick.insertnode(cand[i], name=f"wgd_{w + 1}")
+    return tree
+
+
+def c4_species_tree() -> newick.Node:
+    """The C4 shape of BASELINE.json: 30 taxa, 5 WGD nodes (64 nodes)."""
+    return random_species_tree(30, 5, seed=4)
+
+
+C4_FAMILY = dict(min_leaves=60, max_leaves=100, n_trees=1000, nni_mean=12.0, q=(0.2, 0.1, 0.2, 0.1, 0.2))  # ~2,000 clades
+
+
 def generate(outdir: str, n_fam: int, seed: int, tree: newick.Node | None = None, **kw) -> str:
     """Write `n_fam` synthetic .ale files into outdir (idempotent: reuses a complete directory)."""
     tree = tree or c1_species_tree()
