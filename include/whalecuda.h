@@ -135,6 +135,18 @@ int32_t whale_logpdf_grad(whale_model_t m, whale_data_t d, const double* x, cons
                           double* grad_fam);
 
 /*
+ * Mixture of n_comp WhaleModels that share the species-tree structure and differ in their raw parameters
+ * (logpdf(mm::MixtureModel{…,<:WhaleModel}, xs), src/core.jl:66-76):
+ *     ℓ = Σ_i logsumexp_j ( log L_i(x_j) + log_w[j] − condition(x_j) )
+ * evaluated on the device: every component runs the fused tables -> DP pass, the F × n_comp matrix, its row-wise
+ * logsumexp and the responsibilities stay in HBM.  x is [n_comp][P] (row-major), log_w [n_comp].
+ * With WHALE_WANT_GRAD: grad_x [n_comp][P] = ∂ℓ/∂x_j and grad_logw [n_comp] = ∂ℓ/∂log_w[j] (= Σ_i responsibility_ij).
+ */
+int32_t whale_mixture_logpdf_grad(whale_model_t m, whale_data_t d, int32_t n_comp, const double* x, const double* log_w,
+                                  const double* p_leaf, int32_t condition, uint32_t flags, double* loglik,
+                                  double* grad_x, double* grad_logw);
+
+/*
  * Device-resident variant: d_x (P doubles) and d_out (1+P doubles: loglik, grad) live in device memory;
  * work is enqueued on `stream` (a cudaStream_t) and NOT synchronised.  Used by the benchmark's
  * device-timed leg and by multi-GPU drivers that all-reduce d_out with NCCL on the same stream.
@@ -167,6 +179,18 @@ int32_t whale_backtrack(whale_model_t m, whale_data_t d, int32_t n_samples, cons
 
 /* counters for benchmarks: kernels launched by this library since load, and the last evaluation's
  * algorithmic flop / byte counts (SURVEY §8d coefficients) */
+/*
+ * Fused track_and_sum inner loop (src/track.jl:47-63): for each of the n_theta parameter vectors (posterior draws,
+ * x is [n_theta][P]) run logpdf! over all families keeping ℓ and backtrack ONE reconciled tree per family from it,
+ * everything enqueued back to back on the device (no host round trip between the draws).  uniforms is
+ * [F][n_theta][stride]; outputs are laid out like whale_backtrack's with n_samples = n_theta.  loglik (nullable,
+ * [n_theta]) receives Σ_f log L_f − F·condition for every draw.  The reference draws a posterior row per (family,
+ * sample); here a draw is shared by all families of the batch (same marginal distribution per family).
+ */
+int32_t whale_track(whale_model_t m, whale_data_t d, int32_t n_theta, const double* x, const double* p_leaf,
+                    int32_t condition, const double* uniforms, int64_t stride, int32_t max_nodes, int32_t* node_count,
+                    int32_t* gamma, int32_t* e, int32_t* t, int32_t* parent, int32_t* status, double* loglik);
+
 int64_t whale_launch_count(void);
 int32_t whale_work_estimate(whale_model_t m, whale_data_t d, uint32_t flags, double* flops, double* bytes);
 

@@ -85,3 +85,62 @@ def run_parity(L, name, rtol=1e-9, sel=None, conds=None, check_family=True):
         L.L.whale_data_destroy(dh)
         L.L.whale_model_destroy(mh)
     return g
+
+
+def mixture_vs_oracle(tmp_path, n_fam=6, seed=11):
+    """Mixture of two ConstantDLWGD components on synthetic families: value and gradient (w.r.t. both components'
+    raw parameters and the log mixture weights) composed from the oracle's per-family outputs."""
+    import whale_jl_b200 as W
+    from whale_jl_b200 import synth
+    from oracle import whale_oracle as wo, flat
+    d = synth.generate(str(tmp_path / "mix"), n_fam, seed=seed)
+    pars = ((0.1, 0.2, [0.2, 0.1], 0.67), (0.4, 0.3, [0.3, 0.05], 0.6))
+    wts = np.array([0.3, 0.7])
+    comps = [W.WhaleModel(W.ConstantDLWGD(lam=l, mu=m, q=q, eta=e), synth.c1_species_tree(), 0.05) for l, m, q, e in pars]
+    ccd = W.read_ale(d, comps[0])
+    got, gx, gw = W.logpdf_mixture_and_gradient(comps, wts, ccd)
+    M, G, dC = [], [], []
+    for (l, m, q, e), pj in zip(pars, wts):
+        own = wo.WhaleModel(wo.ConstantDLWGD(lam=l, mu=m, q=q, eta=e), wo.c1_tree(), 0.05, condition="none")
+        owr = wo.WhaleModel(wo.ConstantDLWGD(lam=l, mu=m, q=q, eta=e), wo.c1_tree(), 0.05, condition="root")
+        ff = flat.FlatFams(wo.read_ale(d, own), len(own))
+        tot_n, lf, g_n, gf = flat.logpdf(flat.FlatModel(own), ff, grad=True, per_family=True)
+        tot_r, _, g_r, _ = flat.logpdf(flat.FlatModel(owr), ff, grad=True)
+        cond = (tot_n - tot_r) / n_fam
+        dC.append((g_n - g_r) / n_fam)
+        M.append(lf + np.log(pj) - cond)
+        G.append(gf)
+    M = np.stack(M, 1)
+    mx = M.max(1, keepdims=True)
+    lse = mx[:, 0] + np.log(np.exp(M - mx).sum(1))
+    R = np.exp(M - lse[:, None])
+    want = lse.sum()
+    wgx = np.stack([(R[:, j, None] * (G[j] - dC[j][None, :])).sum(0) for j in range(2)])
+    assert got == pytest.approx(want, rel=1e-9)
+    np.testing.assert_allclose(gx, wgx, rtol=1e-8, atol=1e-9 * np.abs(wgx).max())
+    np.testing.assert_allclose(gw, R.sum(0), rtol=1e-9)
+    assert W.logpdf_mixture(comps, wts, ccd) == pytest.approx(want, rel=1e-9)
+
+
+def fused_track_equals_stepwise(L, n_theta=3):
+    """whale_track (n_theta fused logpdf! + walk rounds) gives exactly the trees of n_theta separate
+    whale_logpdf_grad(KEEP_ELL) + whale_backtrack calls with the same uniforms, and the same log-likelihoods."""
+    g = load_golden("c1_example1")
+    mh = L.model_create(golden_model(g))
+    fl = golden_fams(g, [0, 4, 7])
+    dh = L.data_create(mh, fl)
+    F, MN = 3, 256
+    X = np.stack([g["xs"][i % len(g["xs"])] for i in range(n_theta)])
+    X[1:, -1] = np.clip(X[1:, -1] * np.linspace(0.9, 0.8, n_theta - 1), 0.05, 0.95)  # distinct draws
+    U = np.random.default_rng(9).random((F, n_theta, 4 * MN))
+    cnt, st, nodes, ll = L.track(mh, dh, X, g["m_pleaf"], 1, U, MN)
+    assert np.all(st == 0)
+    for s in range(n_theta):
+        l1 = L.logpdf_grad(mh, dh, X[s], g["m_pleaf"], 1, keep_ell=True)[0]
+        c1, s1, n1 = L.backtrack(mh, dh, 1, U[:, s:s + 1], MN)
+        assert ll[s] == l1
+        assert np.array_equal(c1[:, 0], cnt[:, s])
+        for f in range(F):
+            assert np.array_equal(n1[f, 0, :c1[f, 0]], nodes[f, s, :cnt[f, s]])
+    L.L.whale_data_destroy(dh)
+    L.L.whale_model_destroy(mh)

@@ -86,3 +86,17 @@ def test_emu_unstaged_lists(L, monkeypatch):
     monkeypatch.setenv("WHALE_STAGE_MAX", "64")
     run_parity(L, "c1_example1", sel=[5], conds=["root"])
     _check_backtrack(L, "c1_example1", [5])
+
+
+def test_emu_mixture(L, tmp_path):
+    from conftest import mixture_vs_oracle
+    wlib.use(L)
+    try:
+        mixture_vs_oracle(tmp_path, n_fam=3)
+    finally:
+        wlib.use(None)
+
+
+def test_emu_fused_track(L):
+    from conftest import fused_track_equals_stepwise
+    fused_track_equals_stepwise(L)

@@ -216,6 +216,19 @@ def test_backtrack_api_and_invariants(L, tmp_path):
             assert np.all(t[t[:, 0] < 0, 2] == 0)
 
 
+def test_mixture_on_device_with_gradient(L, tmp_path):
+    """src/core.jl:66-76 on the device (whale_mixture_logpdf_grad): value, ∂/∂ raw parameters of every component and
+    ∂/∂ log weights against the oracle's per-family outputs."""
+    from conftest import mixture_vs_oracle
+    mixture_vs_oracle(tmp_path, n_fam=24)
+
+
+def test_fused_track_equals_stepwise(L):
+    """src/track.jl:47-63 fused on the device (whale_track) against the step-by-step C-ABI sequence."""
+    from conftest import fused_track_equals_stepwise
+    fused_track_equals_stepwise(L, n_theta=5)
+
+
 def test_mixture_modelarray_and_track(L, tmp_path):
     """src/core.jl:66-79 (mixture / ModelArray on top of per-family device outputs) against the oracle, and the
     `track` driver loop (src/track.jl:30-63)."""

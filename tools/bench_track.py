@@ -50,6 +50,19 @@ def main():
            "kernel_trees_per_s": F * S / (kms * 1e-3), "ell_bytes_resident": int(ell_bytes), "families": F, "samples": S,
            "mean_nodes_per_tree": float(cnt.mean()), "call_s": dt, "logpdf_keep_ell_s": t_keep,
            "h2d_bytes": int(U.nbytes), "d2h_bytes": int(nodes.nbytes + cnt.nbytes + st.nbytes)}
+    # fused track_and_sum loop (src/track.jl:47-63): a new θ per sample, logpdf! + one walk per family, on the device
+    T = min(S, 50)
+    rng = np.random.default_rng(1)
+    X = w.x()[None, :] * np.exp(0.03 * rng.standard_normal((T, w.n_params)))
+    X[:, 2:] = np.clip(X[:, 2:], 1e-3, 1 - 1e-3)
+    L.track(mh, dh, X[:2], w.p_leaf(), 1, U[:, :2], MN)  # warm-up
+    t0 = time.perf_counter()
+    c2, s2, n2, ll2 = L.track(mh, dh, X, w.p_leaf(), 1, U[:, :T], MN)
+    dtt = time.perf_counter() - t0
+    assert np.all(s2 == 0)
+    out["fused_track"] = {"thetas": T, "trees_per_s_call": F * T / dtt, "device_ms": L.last_backtrack_ms(dh),
+                          "trees_per_s_device": F * T / (L.last_backtrack_ms(dh) * 1e-3),
+                          "note": "every tree from its own posterior draw: logpdf! (keep ℓ) + walk per draw, enqueued back to back"}
     # oracle on a sample
     from oracle import whale_oracle as wo, flat
     ow = wo.WhaleModel(wo.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), wo.c1_tree(), 0.05)

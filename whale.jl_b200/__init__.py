@@ -12,9 +12,9 @@ from .rates import ConstantDLWGD, DLWGD
 from .model import WhaleModel
 from .ccd import CCD, CCDVector, read_ale
 from .core import (logpdf, logpdf_, loglikelihood, logpdf_and_gradient, logpdf_per_family, ell, slices, backtrack,
-                   BacktrackFailed, logpdf_mixture, logpdf_modelarray, condition, set_probe, track)
+                   BacktrackFailed, logpdf_mixture, logpdf_mixture_and_gradient, logpdf_modelarray, condition, set_probe, track)
 
 __all__ = ["Node", "readnw", "getlca", "getleaves", "postwalk", "insertnode", "nwstr", "extree", "ConstantDLWGD",
            "DLWGD", "WhaleModel", "CCD", "CCDVector", "read_ale", "logpdf", "logpdf_", "loglikelihood",
-           "logpdf_and_gradient", "logpdf_per_family", "ell", "slices", "backtrack", "BacktrackFailed", "logpdf_mixture", "logpdf_modelarray", "condition",
+           "logpdf_and_gradient", "logpdf_per_family", "ell", "slices", "backtrack", "BacktrackFailed", "logpdf_mixture", "logpdf_mixture_and_gradient", "logpdf_modelarray", "condition",
            "set_probe", "track"]

@@ -126,19 +126,30 @@ def backtrack(wm: WhaleModel, x, n_samples: int = 1, uniforms=None, seed=None, m
     return out[0] if single else out
 
 
+def _mixture(components, weights, xs, grad):
+    wm0 = components[0]
+    for wm in components[1:]:
+        if wm.nn != wm0.nn or wm.n_params != wm0.n_params or not (np.array_equal(wm.kind, wm0.kind) and
+                                                                   np.array_equal(wm.n_slices, wm0.n_slices)):
+            raise ValueError("mixture components must share the species tree, slicing and rate parameterisation")
+    xs, _ = _as_vector(xs)
+    mh, dh = _data_handle(wm0, xs)
+    X = np.stack([wm.x() for wm in components])
+    lw = np.log(np.asarray(weights, dtype=np.float64))
+    return _lib.get().mixture_logpdf_grad(mh, dh, X, lw, wm0.p_leaf(), CONDITIONS[wm0.condition], want_grad=grad)
+
+
 def logpdf_mixture(components, weights, xs) -> float:
-    """`logpdf(mm::MixtureModel{…,<:WhaleModel}, xs)` (src/core.jl:66-76): per component j the per-family
-    unconditioned ℓ_ij from the device, plus log p_j − condition(component j); then Σ_i logsumexp_j."""
-    weights = np.asarray(weights, dtype=np.float64)
-    cols = []
-    for wm, pj in zip(components, weights):
-        lf, _ = logpdf_per_family(wm, xs)
-        cols.append(lf + np.log(pj) - condition(wm))
-    M = np.stack(cols, axis=1)
-    mx = M.max(axis=1, keepdims=True)
-    mx = np.where(np.isfinite(mx), mx, 0.0)
-    tot = float(np.sum(mx[:, 0] + np.log(np.exp(M - mx).sum(axis=1))))
-    return tot if np.isfinite(tot) else -np.inf
+    """`logpdf(mm::MixtureModel{…,<:WhaleModel}, xs)` (src/core.jl:66-76): Σ_i logsumexp_j (ℓ_ij + log p_j −
+    condition(component j)), evaluated on the device (`whale_mixture_logpdf_grad`): the F × K matrix never leaves
+    HBM.  Components share the species tree and differ in their rates."""
+    return _mixture(components, weights, xs, False)[0]
+
+
+def logpdf_mixture_and_gradient(components, weights, xs):
+    """The same with its gradient: (ℓ, ∂ℓ/∂raw parameters of every component [K × P], ∂ℓ/∂log p_j [K]) — what
+    ForwardDiff would propagate through the mixture's logsumexp."""
+    return _mixture(components, weights, xs, True)
 
 
 def logpdf_modelarray(models, xs) -> float:
@@ -169,20 +180,30 @@ def set_probe(wm: WhaleModel, ccd):
     return wm
 
 
-def track(wm: WhaleModel, xs, posterior, n: int, fun=None, seed=None, max_nodes: int = 512):
+def _trees_from(cnt, st, nodes, n_samples, F):
+    if np.any(st == 1):
+        raise BacktrackFailed("Backtracking failed (no event selected; numerically inconsistent ℓ)")
+    if np.any(st == 2):
+        raise RuntimeError("backtrack: max_nodes too small for a sampled tree")
+    if np.any(st == 3):
+        raise RuntimeError("backtrack: uniform stream exhausted (increase the stride)")
+    return [[nodes[f, s, :cnt[f, s]].copy() for s in range(n_samples)] for f in range(F)]
+
+
+def track(wm: WhaleModel, xs, posterior, n: int, fun=None, seed=None, max_nodes: int = 512, return_loglik=False):
     """`track(TreeTracker(model, data, df, fun), N)` without the summaries (src/track.jl:30-63): for each of the
     `n` samples draw a posterior row, re-parameterise the model (`fun(model, row)`, default `model(**row)`),
-    `logpdf!` and backtrack one tree per family.  Returns trees[family][sample] as (γ, e, t, parent) arrays.
-    Summaries (`sumtrees`, src/rectree.jl) are host-side post-processing outside the hot path."""
+    `logpdf!` and backtrack one tree per family — fused on the device (`whale_track`: the n evaluations and walks
+    are enqueued back to back, nothing returns to the host in between).  Returns trees[family][sample] as
+    (γ, e, t, parent) arrays.  Summaries (`sumtrees`, src/rectree.jl) are host-side post-processing outside the
+    hot path."""
     rng = np.random.default_rng(seed)
     xs, _ = _as_vector(xs)
     fun = fun or (lambda m, row: m(**row))
-    out = [[] for _ in range(len(xs))]
-    for _ in range(n):
-        row = posterior[int(rng.integers(len(posterior)))]
-        wmm = fun(wm, row)
-        logpdf_(wmm, xs)
-        trees = backtrack(wmm, xs, n_samples=1, seed=int(rng.integers(2 ** 31)), max_nodes=max_nodes)
-        for f, t in enumerate(trees):
-            out[f].append(t[0])
-    return out
+    mh, dh = _data_handle(wm, xs)
+    rows = [posterior[int(rng.integers(len(posterior)))] for _ in range(n)]
+    X = np.stack([fun(wm, row).x() for row in rows])
+    U = rng.random((len(xs), n, 4 * max_nodes))
+    cnt, st, nodes, ll = _lib.get().track(mh, dh, X, wm.p_leaf(), CONDITIONS[wm.condition], U, max_nodes)
+    trees = _trees_from(cnt, st, nodes, n, len(xs))
+    return (trees, ll) if return_loglik else trees

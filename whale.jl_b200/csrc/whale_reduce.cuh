@@ -43,6 +43,90 @@ __global__ void __launch_bounds__(256) k_reduce2(const double* __restrict__ part
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Mixture of WhaleModels (src/core.jl:66-76): ℓ = Σ_i logsumexp_j (ℓ_ij + log p_j − condition_j), with the
+// gradient w.r.t. every component's raw parameters and w.r.t. log p_j through the responsibilities.
+// ---------------------------------------------------------------------------------------------------------
+// scatter one tangent plan's per-family outputs (component layout of the root) into dense [F][1+P] rows
+__global__ void __launch_bounds__(256) k_mix_gather(const double* __restrict__ out_fam, int F, int KR,
+                                                    const int* __restrict__ act_root, int first,
+                                                    const double* __restrict__ cond, double* __restrict__ dense,
+                                                    double* __restrict__ condv, int P) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < (long long)F * KR) {
+        const int f = (int)(idx / KR), k = (int)(idx - (long long)f * KR);
+        if (k == 0) { if (first) dense[(size_t)f * (1 + P)] = out_fam[idx]; }
+        else dense[(size_t)f * (1 + P) + 1 + act_root[k]] = out_fam[idx];
+    }
+    if (idx < KR) {
+        const int k = (int)idx;
+        if (k == 0) { if (first) condv[0] = cond[0]; }
+        else condv[1 + act_root[k]] = cond[k];
+    }
+}
+
+// per family: lse_i and the responsibilities r_ij = exp(M_ij − lse_i)
+__global__ void __launch_bounds__(256) k_mix_resp(const double* __restrict__ dense, const double* __restrict__ condv,
+                                                  const double* __restrict__ logw, int F, int P, int J,
+                                                  double* __restrict__ lse, double* __restrict__ resp) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const size_t comp = (size_t)F * (1 + P);
+    double mx = -dinf();
+    for (int j = 0; j < J; j++) {
+        const double v = dense[j * comp + (size_t)f * (1 + P)] + logw[j] - condv[(size_t)j * (1 + P)];
+        mx = v > mx ? v : mx;
+    }
+    if (!(mx > -dinf())) {  // every component gives L <= 0 for this family
+        lse[f] = -dinf();
+        for (int j = 0; j < J; j++) resp[(size_t)f * J + j] = 0.0;
+        return;
+    }
+    double s = 0.0;
+    for (int j = 0; j < J; j++) {
+        const double v = dense[j * comp + (size_t)f * (1 + P)] + logw[j] - condv[(size_t)j * (1 + P)];
+        s += exp(v - mx);
+    }
+    const double l = mx + log(s);
+    lse[f] = l;
+    for (int j = 0; j < J; j++) {
+        const double v = dense[j * comp + (size_t)f * (1 + P)] + logw[j] - condv[(size_t)j * (1 + P)];
+        resp[(size_t)f * J + j] = exp(v - l);
+    }
+}
+
+// one block per output: q = 0 the total, q = 1 + j*(1+P) + 0 the gradient w.r.t. log p_j, + 1 + p w.r.t. x_jp;
+// fixed-order strided sums + tree (deterministic bits)
+__global__ void __launch_bounds__(256) k_mix_reduce(const double* __restrict__ dense, const double* __restrict__ condv,
+                                                    const double* __restrict__ lse, const double* __restrict__ resp,
+                                                    int F, int P, int J, double* __restrict__ out) {
+    __shared__ double sh[256];
+    const int q = blockIdx.x;
+    const size_t comp = (size_t)F * (1 + P);
+    double s = 0.0;
+    if (q == 0) {
+        for (int f = threadIdx.x; f < F; f += 256) s += lse[f];
+    } else {
+        const int j = (q - 1) / (1 + P), c = (q - 1) - j * (1 + P);
+        if (c == 0) {
+            for (int f = threadIdx.x; f < F; f += 256) s += resp[(size_t)f * J + j];
+        } else {
+            const double cv = condv[(size_t)j * (1 + P) + c];
+            for (int f = threadIdx.x; f < F; f += 256) {
+                const double r = resp[(size_t)f * J + j];
+                if (r != 0.0) s += r * (dense[j * comp + (size_t)f * (1 + P) + c] - cv);
+            }
+        }
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[q] = sh[0];
+}
+
 // dependent-free DFMA microbenchmark (fp64 roofline denominator)
 __global__ void __launch_bounds__(256) k_dfma(double* out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,

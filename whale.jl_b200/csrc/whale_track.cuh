@@ -25,21 +25,23 @@ struct BTArgs {
     const double* uniforms;  // [(f*S + s) * stride ...]
     long long stride;
     int nfam, nsamp, max_nodes;
+    int samp_off, samp_total;  // this launch covers samples [samp_off, samp_off + nsamp) of samp_total per family
     int32_t* node_count;     // [F*S]
     int32_t* gamma;          // [F*S*max_nodes]
     int32_t* enode;
     int32_t* trow;
     int32_t* parent;
     int32_t* status;         // [F*S]
-    int4* stack;             // [F*S*max_nodes] scratch
+    int4* stack;             // [F*nsamp*max_nodes] scratch of this launch
 };
 
 __device__ __forceinline__ double mul3(double a, double b, double c) { return __dmul_rn(__dmul_rn(a, b), c); }
 
 __global__ void __launch_bounds__(128) k_backtrack(BTArgs A) {
-    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= (long long)A.nfam * A.nsamp) return;
-    const int fam = (int)(w / A.nsamp);
+    const long long wl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wl >= (long long)A.nfam * A.nsamp) return;
+    const int fam = (int)(wl / A.nsamp);
+    const long long w = (long long)fam * A.samp_total + A.samp_off + (wl - (long long)fam * A.nsamp);
     const ModelDev& M = A.M;
     const PlanDev& PL = A.PL;
     const FamHdr* Hp = A.hdr + fam;
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(128) k_backtrack(BTArgs A) {
     int32_t* o_e = A.enode + w * A.max_nodes;
     int32_t* o_t = A.trow + w * A.max_nodes;
     int32_t* o_p = A.parent + w * A.max_nodes;
-    int4* stk = A.stack + w * A.max_nodes;
+    int4* stk = A.stack + wl * A.max_nodes;  // scratch is per launch
     const int nn = M.nn, root = M.root;
     const uint32_t nlev = Hp->nlev;
 

@@ -1038,6 +1038,74 @@ int32_t whale_logpdf_grad(whale_model_t m, whale_data_t d, const double* x, cons
     return WHALE_OK;
 }
 
+int32_t whale_mixture_logpdf_grad(whale_model_t m, whale_data_t d, int32_t n_comp, const double* x, const double* log_w,
+                                  const double* p_leaf, int32_t condition, uint32_t flags, double* loglik,
+                                  double* grad_x, double* grad_logw) {
+    if (!m || !d || !x || !log_w || !loglik || n_comp < 1) return fail(WHALE_ERR_ARG, "null argument");
+    if (d->m != m) return fail(WHALE_ERR_ARG, "data handle belongs to another model");
+    if (condition < 0 || condition > 2) return fail(WHALE_ERR_ARG, "unknown condition kind %d", condition);
+    const bool grad = (flags & WHALE_WANT_GRAD) != 0;
+    if ((grad_x || grad_logw) && !grad) return fail(WHALE_ERR_ARG, "grad requested without WHALE_WANT_GRAD");
+    CU(cudaSetDevice(m->device));
+    const int P = m->P, nn = m->nn, F = d->F, J = n_comp;
+    const size_t comp = (size_t)F * (1 + P);
+    double *dense = nullptr, *condv = nullptr, *logw = nullptr, *lse = nullptr, *resp = nullptr, *out = nullptr, *dx = nullptr;
+    const int Q = 1 + J * (1 + P);
+    auto cleanup = [&]() { cudaFree(dense); cudaFree(condv); cudaFree(logw); cudaFree(lse); cudaFree(resp); cudaFree(out); cudaFree(dx); };
+#define CUM(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(WHALE_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
+    CUM(cudaMalloc((void**)&dense, J * comp * sizeof(double)));
+    CUM(cudaMalloc((void**)&condv, (size_t)J * (1 + P) * sizeof(double)));
+    CUM(cudaMalloc((void**)&logw, J * sizeof(double)));
+    CUM(cudaMalloc((void**)&lse, (size_t)F * sizeof(double)));
+    CUM(cudaMalloc((void**)&resp, (size_t)F * J * sizeof(double)));
+    CUM(cudaMalloc((void**)&out, Q * sizeof(double)));
+    CUM(cudaMalloc((void**)&dx, (size_t)J * P * sizeof(double)));
+    cudaStream_t st = m->stream;
+    CUM(cudaMemsetAsync(dense, 0, J * comp * sizeof(double), st));
+    CUM(cudaMemsetAsync(condv, 0, (size_t)J * (1 + P) * sizeof(double), st));
+    CUM(cudaMemcpyAsync(logw, log_w, J * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUM(cudaMemcpyAsync(dx, x, (size_t)J * P * sizeof(double), cudaMemcpyHostToDevice, st));
+    std::vector<double> pl(nn, 0.0);
+    if (p_leaf) pl.assign(p_leaf, p_leaf + nn);
+    CUM(cudaMemcpyAsync(m->d_pleaf, pl.data(), nn * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUM(cudaStreamSynchronize(st));  // pl is a stack-lifetime buffer
+    for (int j = 0; j < J; j++) {
+        // per-family outputs of component j (every tangent plan), then scattered into its dense rows
+        int32_t rc = enqueue_eval(m, d, dx + (size_t)j * P, condition, flags & WHALE_WANT_GRAD, m->d_out, st);
+        if (rc != WHALE_OK) { cleanup(); return rc; }
+        const size_t g0 = grad ? 1 : 0, g1 = grad ? d->plans.size() : 1;
+        for (size_t g = g0; g < g1; g++) {
+            const Plan& plg = *d->plans[g];
+            const int KR = plg.K[m->root];
+            const long long tot = (long long)F * KR;
+            LAUNCH(k_mix_gather, (int)((tot + 255) / 256), 256, 0, st, d->d_out_fam + d->out_off[g], F, KR,
+                   plg.dev.act + (size_t)m->root * plg.Kmax, g == g0 ? 1 : 0, plg.dev.cond + (size_t)condition * plg.Kmax,
+                   dense + j * comp, condv + (size_t)j * (1 + P), P);
+            g_launches++;
+        }
+        // NOTE: with several gradient passes the plans' tables are reused by the next component only after these
+        // launches (same stream), so reading plg.dev.cond here is ordered correctly.
+    }
+    LAUNCH(k_mix_resp, (F + 255) / 256, 256, 0, st, dense, condv, logw, F, P, J, lse, resp);
+    LAUNCH(k_mix_reduce, grad ? Q : 1, 256, 0, st, dense, condv, lse, resp, F, P, J, out);
+    g_launches += 2;
+    std::vector<double> ho(Q, 0.0);
+    CUM(cudaMemcpyAsync(ho.data(), out, (grad ? Q : 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUM(cudaStreamSynchronize(st));
+    CUM(cudaGetLastError());
+#undef CUM
+    cleanup();
+    d->ell_valid = false;
+    d->ev_valid = false;
+    const bool fin = std::isfinite(ho[0]);
+    *loglik = fin ? ho[0] : -INFINITY;  // ℓhood src/core.jl:15
+    for (int j = 0; j < J; j++) {
+        if (grad_logw) grad_logw[j] = fin ? ho[1 + (size_t)j * (1 + P)] : 0.0;
+        if (grad_x) for (int p2 = 0; p2 < P; p2++) grad_x[(size_t)j * P + p2] = fin ? ho[1 + (size_t)j * (1 + P) + 1 + p2] : 0.0;
+    }
+    return WHALE_OK;
+}
+
 int32_t whale_slices(whale_model_t m, const double* x, const double* p_leaf, double* eps, double* phi, double* psi) {
     if (!m || !x || !eps || !phi || !psi) return fail(WHALE_ERR_ARG, "null argument");
     CU(cudaSetDevice(m->device));
@@ -1102,7 +1170,7 @@ int32_t whale_backtrack(whale_model_t m, whale_data_t d, int32_t n_samples, cons
     Plan& p0 = m->plan[0];
     LAUNCH(k_tables, 1, TABLES_NT, tables_smem(m, p0), m->stream, m->dev, p0.dev, m->d_x, m->d_pleaf);
     BTArgs a{m->dev, p0.dev, d->d_arena, d->d_hdr, d->d_ell, m->d_x, d_u, (long long)stride, d->F, n_samples, max_nodes,
-             d_cnt, d_g, d_e, d_t, d_p, d_st, d_stack};
+             0, n_samples, d_cnt, d_g, d_e, d_t, d_p, d_st, d_stack};
     cudaEvent_t eb0 = nullptr, eb1 = nullptr;
     CUB(cudaEventCreate(&eb0)); CUB(cudaEventCreate(&eb1));
     CUB(cudaEventRecord(eb0, m->stream));
@@ -1120,6 +1188,75 @@ int32_t whale_backtrack(whale_model_t m, whale_data_t d, int32_t n_samples, cons
     CUB(cudaMemcpy(parent, d_p, W * max_nodes * 4, cudaMemcpyDeviceToHost));
 #undef CUB
     cleanup();
+    return WHALE_OK;
+}
+
+int32_t whale_track(whale_model_t m, whale_data_t d, int32_t n_theta, const double* x, const double* p_leaf,
+                    int32_t condition, const double* uniforms, int64_t stride, int32_t max_nodes, int32_t* node_count,
+                    int32_t* gamma, int32_t* e, int32_t* t, int32_t* parent, int32_t* status, double* loglik) {
+    if (!m || !d || !x || !uniforms || !node_count || !gamma || !e || !t || !parent || !status)
+        return fail(WHALE_ERR_ARG, "null argument");
+    if (d->m != m) return fail(WHALE_ERR_ARG, "data handle belongs to another model");
+    if (n_theta <= 0 || stride <= 0 || max_nodes <= 1) return fail(WHALE_ERR_ARG, "n_theta, stride and max_nodes must be positive");
+    CU(cudaSetDevice(m->device));
+    const int P = m->P, nn = m->nn;
+    const size_t W = (size_t)d->F * n_theta;
+    double *d_u = nullptr, *d_xs = nullptr, *d_outs = nullptr;
+    int32_t *d_cnt = nullptr, *d_g = nullptr, *d_e = nullptr, *d_t = nullptr, *d_p = nullptr, *d_st = nullptr;
+    int4* d_stack = nullptr;
+    cudaEvent_t eb0 = nullptr, eb1 = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_u); cudaFree(d_xs); cudaFree(d_outs); cudaFree(d_cnt); cudaFree(d_g); cudaFree(d_e); cudaFree(d_t);
+        cudaFree(d_p); cudaFree(d_st); cudaFree(d_stack);
+        if (eb0) cudaEventDestroy(eb0);
+        if (eb1) cudaEventDestroy(eb1);
+    };
+#define CUB(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { cleanup(); return fail(WHALE_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); } } while (0)
+    cudaStream_t st = m->stream;
+    CUB(cudaMalloc((void**)&d_u, W * stride * sizeof(double)));
+    CUB(cudaMemcpyAsync(d_u, uniforms, W * stride * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUB(cudaMalloc((void**)&d_xs, (size_t)n_theta * P * sizeof(double)));
+    CUB(cudaMemcpyAsync(d_xs, x, (size_t)n_theta * P * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUB(cudaMalloc((void**)&d_outs, (size_t)n_theta * (1 + P) * sizeof(double)));
+    CUB(cudaMalloc((void**)&d_cnt, W * 4)); CUB(cudaMalloc((void**)&d_st, W * 4));
+    CUB(cudaMalloc((void**)&d_g, W * max_nodes * 4)); CUB(cudaMalloc((void**)&d_e, W * max_nodes * 4));
+    CUB(cudaMalloc((void**)&d_t, W * max_nodes * 4)); CUB(cudaMalloc((void**)&d_p, W * max_nodes * 4));
+    CUB(cudaMalloc((void**)&d_stack, (size_t)d->F * max_nodes * sizeof(int4)));  // one sample in flight at a time
+    std::vector<double> pl(nn, 0.0);
+    if (p_leaf) pl.assign(p_leaf, p_leaf + nn);
+    CUB(cudaMemcpyAsync(m->d_pleaf, pl.data(), nn * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUB(cudaStreamSynchronize(st));
+    CUB(cudaEventCreate(&eb0)); CUB(cudaEventCreate(&eb1));
+    CUB(cudaEventRecord(eb0, st));
+    Plan& p0 = m->plan[0];
+    for (int s = 0; s < n_theta; s++) {
+        // logpdf!(model(θ_s), ccds) keeping ℓ, then one walk per family from it — nothing returns to the host in between
+        int32_t rc = enqueue_eval(m, d, d_xs + (size_t)s * P, condition, WHALE_KEEP_ELL, d_outs + (size_t)s * (1 + P), st);
+        if (rc != WHALE_OK) { cleanup(); return rc; }
+        BTArgs a{m->dev, p0.dev, d->d_arena, d->d_hdr, d->d_ell, d_xs + (size_t)s * P, d_u, (long long)stride, d->F, 1, max_nodes,
+                 s, n_theta, d_cnt, d_g, d_e, d_t, d_p, d_st, d_stack};
+        LAUNCH(k_backtrack, (d->F + 127) / 128, 128, 0, st, a);
+        g_launches++;
+    }
+    CUB(cudaEventRecord(eb1, st));
+    CUB(cudaGetLastError());
+    CUB(cudaStreamSynchronize(st));
+    { float ms = 0; cudaEventElapsedTime(&ms, eb0, eb1); d->last_bt_ms = ms; }
+    CUB(cudaMemcpy(node_count, d_cnt, W * 4, cudaMemcpyDeviceToHost));
+    CUB(cudaMemcpy(status, d_st, W * 4, cudaMemcpyDeviceToHost));
+    CUB(cudaMemcpy(gamma, d_g, W * max_nodes * 4, cudaMemcpyDeviceToHost));
+    CUB(cudaMemcpy(e, d_e, W * max_nodes * 4, cudaMemcpyDeviceToHost));
+    CUB(cudaMemcpy(t, d_t, W * max_nodes * 4, cudaMemcpyDeviceToHost));
+    CUB(cudaMemcpy(parent, d_p, W * max_nodes * 4, cudaMemcpyDeviceToHost));
+    if (loglik) {
+        std::vector<double> ho((size_t)n_theta * (1 + P));
+        CUB(cudaMemcpy(ho.data(), d_outs, ho.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int s = 0; s < n_theta; s++) loglik[s] = ho[(size_t)s * (1 + P)];
+    }
+#undef CUB
+    cleanup();
+    d->ell_valid = true;      // ℓ of the last θ stays on the device
+    m->x_host_valid = false;  // ... but m->d_x does not hold it
     return WHALE_OK;
 }
 

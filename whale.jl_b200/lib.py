@@ -20,8 +20,8 @@ WANT_GRAD, KEEP_ELL, PROFILE = 1, 2, 4
 # every symbol include/whalecuda.h declares (tests check the built library exports all of them)
 SYMBOLS = ["whale_version", "whale_last_error", "whale_device_count", "whale_set_device", "whale_model_create",
            "whale_model_destroy", "whale_data_create", "whale_data_destroy", "whale_data_nfam",
-           "whale_data_arena_bytes", "whale_data_arena_dump", "whale_logpdf_grad", "whale_logpdf_grad_async",
-           "whale_slices", "whale_ell_size", "whale_ell_get", "whale_backtrack", "whale_launch_count",
+           "whale_data_arena_bytes", "whale_data_arena_dump", "whale_logpdf_grad", "whale_logpdf_grad_async", "whale_mixture_logpdf_grad",
+           "whale_slices", "whale_ell_size", "whale_ell_get", "whale_backtrack", "whale_track", "whale_launch_count",
            "whale_work_estimate", "whale_last_kernel_ms", "whale_last_phase_cycles", "whale_last_node_cycles", "whale_last_family_cycles", "whale_last_tables_cycles", "whale_last_backtrack_ms", "whale_fp64_peak"]
 
 
@@ -77,12 +77,16 @@ class Lib:
         L.whale_ell_size.argtypes = [vp, C.c_int32]
         L.whale_ell_size.restype = C.c_int64
         L.whale_ell_get.argtypes = [vp, C.c_int32, f64p]
+        L.whale_track.argtypes = [vp, vp, C.c_int32, f64p, f64p, C.c_int32, f64p, C.c_int64, C.c_int32, i32p, i32p, i32p,
+                                  i32p, i32p, i32p, f64p]
         L.whale_backtrack.argtypes = [vp, vp, C.c_int32, f64p, C.c_int64, C.c_int32, i32p, i32p, i32p, i32p, i32p,
                                       i32p]
         L.whale_launch_count.restype = C.c_int64
         L.whale_work_estimate.argtypes = [vp, vp, C.c_uint32, f64p, f64p]
         L.whale_fp64_peak.argtypes = [f64p]
         L.whale_last_kernel_ms.argtypes = [vp, f64p, f64p, f64p]
+        L.whale_mixture_logpdf_grad.argtypes = [vp, vp, C.c_int32, f64p, f64p, f64p, C.c_int32, C.c_uint32,
+                                                C.POINTER(C.c_double), f64p, f64p]
         L.whale_last_phase_cycles.argtypes = [vp, f64p, f64p]
         L.whale_last_tables_cycles.argtypes = [vp, C.c_int32, f64p]
         L.whale_last_node_cycles.argtypes = [vp, f64p, f64p, C.c_int32]
@@ -132,6 +136,20 @@ class Lib:
                                             _ptr(gf, f64p) if per_family_grad else None))
         return ll.value, g, lf, gf
 
+    def mixture_logpdf_grad(self, mh, dh, xs, log_w, p_leaf, condition, want_grad=False):
+        xs = np.ascontiguousarray(xs, np.float64)
+        lw = np.ascontiguousarray(log_w, np.float64)
+        pl = np.ascontiguousarray(p_leaf, np.float64)
+        J, P = xs.shape
+        ll = C.c_double()
+        gx = np.zeros((J, P)) if want_grad else None
+        gw = np.zeros(J) if want_grad else None
+        self.check(self.L.whale_mixture_logpdf_grad(mh, dh, J, _ptr(xs, f64p), _ptr(lw, f64p), _ptr(pl, f64p), condition,
+                                                    WANT_GRAD if want_grad else 0, C.byref(ll),
+                                                    _ptr(gx, f64p) if want_grad else None,
+                                                    _ptr(gw, f64p) if want_grad else None))
+        return ll.value, gx, gw
+
     def slices(self, mh, x, p_leaf, nrows):
         x = np.ascontiguousarray(x, np.float64)
         pl = np.ascontiguousarray(p_leaf, np.float64)
@@ -169,6 +187,25 @@ class Lib:
                                           _ptr(g, i32p), _ptr(e, i32p), _ptr(t, i32p), _ptr(p, i32p), _ptr(st, i32p)))
         nodes = np.stack([g, e, t, p], axis=1).reshape(F, n_samples, max_nodes, 4)
         return cnt.reshape(F, n_samples), st.reshape(F, n_samples), nodes
+
+    def track(self, mh, dh, xs, p_leaf, condition, uniforms, max_nodes=512):
+        """whale_track: xs [n_theta, P], uniforms [F, n_theta, stride]; returns (counts, status, nodes, loglik[n_theta])
+        laid out like `backtrack` with n_samples = n_theta."""
+        F = self.L.whale_data_nfam(dh)
+        xs = np.ascontiguousarray(xs, np.float64)
+        S = xs.shape[0]
+        pl = np.ascontiguousarray(p_leaf, np.float64)
+        u = np.ascontiguousarray(uniforms, np.float64).reshape(F, S, -1)
+        stride = u.shape[2]
+        W = F * S
+        cnt, st = np.zeros(W, np.int32), np.zeros(W, np.int32)
+        g, e, t, p = (np.zeros(W * max_nodes, np.int32) for _ in range(4))
+        ll = np.zeros(S)
+        self.check(self.L.whale_track(mh, dh, S, _ptr(xs, f64p), _ptr(pl, f64p), condition, _ptr(u, f64p), stride, max_nodes,
+                                      _ptr(cnt, i32p), _ptr(g, i32p), _ptr(e, i32p), _ptr(t, i32p), _ptr(p, i32p),
+                                      _ptr(st, i32p), _ptr(ll, f64p)))
+        nodes = np.stack([g, e, t, p], axis=1).reshape(F, S, max_nodes, 4)
+        return cnt.reshape(F, S), st.reshape(F, S), nodes, ll
 
     def work_estimate(self, mh, dh, want_grad=True):
         fl, by = C.c_double(), C.c_double()
