@@ -47,6 +47,7 @@ extern "C" {
 #define WHALE_COND_NONE 0       /* NoCondition          */
 #define WHALE_COND_ROOT 1       /* RootCondition        */
 #define WHALE_COND_NONEXTINCT 2 /* NonExtinctCondition  */
+#define WHALE_COND_NOWHERE 3    /* NowhereExtinctCondition (src/condition.jl:5-9,31-36; 2^L terms, L <= 20 leaves) */
 
 /* flags for whale_logpdf_grad */
 #define WHALE_WANT_GRAD 1u  /* also return d loglik / d raw parameter                          */

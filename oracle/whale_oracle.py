@@ -525,7 +525,58 @@ def condition(wm: WhaleModel, kind=None):
         eg = geompgf(eta, g.eps[-1])
         p = 1.0 - ef - eg + er
         return _log(p) if p > 0.0 else -math.inf
+    if kind == "nowhere":  # NowhereExtinctCondition src/condition.jl:5-9,31-36
+        p = treepgf_allbinary(wm)
+        s = treepgf_allbinary_sign(wm)
+        c = 1.0
+        for pi, si in zip(p[:-1], s[:-1]):  # sum((p .* e.s)[1:end-1])
+            c = c - pi * si
+        return _log(c) if 0.0 < c < 1.0 else -math.inf
     raise ValueError(kind)
+
+
+def bdp_pgf(lam, mu, t, s):
+    """pgf(::LinearBDP, s) src/bdputil.jl:58-64 (ρ = exp((μ−λ)t), :42)."""
+    if abs(value(lam) - value(mu)) <= LMATOL:
+        return (1.0 - (lam * t - 1.0) * (s - 1.0)) / (1.0 - lam * t * (s - 1.0))
+    rho = _exp((mu - lam) * t)
+    return (rho * (lam * s - mu) - mu * (s - 1.0)) / (rho * (lam * s - mu) - lam * (s - 1.0))
+
+
+def wgdpgf(q, s):  # src/bdputil.jl:73
+    return s * (1.0 - q + s * q)
+
+
+def treepgf_allbinary(wm: WhaleModel):
+    """src/bdputil.jl:109-121: the tree pgf at every binary argument f(0..0), f(1,0..0), …, f(1..1); children's
+    vectors combine as vec(prod.(Iterators.product(down...))) — the FIRST child's index runs fastest."""
+    def walk(n: MNode):
+        th = gettheta(wm.rates, n)
+        if n is wm.root:
+            f = lambda x: geompgf(th["eta"], x)
+        else:
+            f = lambda x: bdp_pgf(th["lam"], th["mu"], n.dist, x)
+        if n.isleaf():
+            return [f(0.0), f(1.0)]
+        down = [walk(c) for c in n.children]
+        xs = down[0]
+        for d in down[1:]:
+            xs = [a * b for b in d for a in xs]
+        return [f(wgdpgf(th["q"], x)) if n.iswgd() else f(x) for x in xs]
+    return walk(wm.root)
+
+
+def treepgf_allbinary_sign(wm: WhaleModel):
+    """src/bdputil.jl:125-133."""
+    def walk(n: MNode):
+        if n.isleaf():
+            return [1.0, -1.0]
+        down = [walk(c) for c in n.children]
+        xs = down[0]
+        for d in down[1:]:
+            xs = [a * b for b in d for a in xs]
+        return xs
+    return [math.copysign(1.0, v) for v in walk(wm.root)]
 
 
 # --------------------------------------------------------------------------------------------

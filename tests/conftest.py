@@ -144,3 +144,35 @@ def fused_track_equals_stepwise(L, n_theta=3):
             assert np.array_equal(n1[f, 0, :c1[f, 0]], nodes[f, s, :cnt[f, s]])
     L.L.whale_data_destroy(dh)
     L.L.whale_model_destroy(mh)
+
+
+def nowhere_condition_vs_oracle(L):
+    """NowhereExtinctCondition (src/condition.jl:31-36) on the device against the oracle's restatement of
+    treepgf_allbinary (src/bdputil.jl:109-133): batch log-likelihood and gradient for the C1 model at three
+    parameter points (incl. the critical λ = μ branch of the BDP pgf), DLWGD with 37 raw parameters."""
+    from oracle import whale_oracle as wo
+    g = load_golden("c1_example1")
+    mh = L.model_create(golden_model(g))
+    sel = [0, 5]
+    dh = L.data_create(mh, golden_fams(g, sel))
+    try:
+        rng = np.random.default_rng(3)
+        # moderate rates (at the C1 test point λ = μ = e the probability is ~1e-8 and the alternating sum is all
+        # cancellation): the critical λ = μ branch of the BDP pgf, and two generic points
+        pts = [np.concatenate([np.full(34, np.log(0.3)), [0.2, 0.1, 0.9]]),
+               np.concatenate([rng.normal(np.log(0.25), 0.3, 34), [0.35, 0.6, 0.66]]),
+               np.concatenate([rng.normal(np.log(0.15), 0.5, 34), [0.05, 0.9, 0.8]])]
+        for xi, x in enumerate(pts):
+            ll0, g0, _, _ = L.logpdf_grad(mh, dh, x, g["m_pleaf"], 0, want_grad=True)
+            ll3, g3, _, _ = L.logpdf_grad(mh, dh, x, g["m_pleaf"], 3, want_grad=True)
+            P = len(x)
+            duals = [wo.Dual(v, np.eye(P)[i]) for i, v in enumerate(x)]
+            base = wo.c1_model(condition="nowhere")
+            m = base.with_rates(wo.rates_from_vector(base.rates, duals))
+            wo.setmodel(m)
+            c = wo.condition(m)
+            assert (ll0 - ll3) / len(sel) == pytest.approx(c.v, rel=1e-9), xi
+            np.testing.assert_allclose((g0 - g3) / len(sel), c.d, rtol=1e-8, atol=1e-10 * np.abs(c.d).max())
+    finally:
+        L.L.whale_data_destroy(dh)
+        L.L.whale_model_destroy(mh)

@@ -36,6 +36,7 @@ struct double2 { double x, y; };
 struct int4 { int x, y, z, w; };
 inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 // explicit round-to-nearest ops (the emulation build is compiled with -ffp-contract=off)
+inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __ddiv_rn(double a, double b) { return a / b; }

@@ -100,3 +100,8 @@ def test_emu_mixture(L, tmp_path):
 def test_emu_fused_track(L):
     from conftest import fused_track_equals_stepwise
     fused_track_equals_stepwise(L)
+
+
+def test_emu_nowhere_extinct_condition(L):
+    from conftest import nowhere_condition_vs_oracle
+    nowhere_condition_vs_oracle(L)

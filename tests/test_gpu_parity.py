@@ -223,6 +223,12 @@ def test_mixture_on_device_with_gradient(L, tmp_path):
     mixture_vs_oracle(tmp_path, n_fam=24)
 
 
+def test_nowhere_extinct_condition(L):
+    """NowhereExtinctCondition (src/condition.jl:31-36, 2^9 inclusion–exclusion terms) on the device."""
+    from conftest import nowhere_condition_vs_oracle
+    nowhere_condition_vs_oracle(L)
+
+
 def test_fused_track_equals_stepwise(L):
     """src/track.jl:47-63 fused on the device (whale_track) against the step-by-step C-ABI sequence."""
     from conftest import fused_track_equals_stepwise

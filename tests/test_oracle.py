@@ -170,3 +170,60 @@ def _fams_from_golden(g):
                  _p(keep["f_g1"], i32p), _p(keep["f_g2"], i32p), _p(keep["f_p"], f64p),
                  _p(keep["f_compat_off"], i64p), _p(keep["f_compat"], i32p))
     return ff
+
+
+def test_nowhere_extinct_condition_reference_tests():
+    """test/runtests.jl:52-77: the probability of being extinct nowhere grows with the retention rates, and agrees
+    with a Monte-Carlo simulation of the DL+WGD process (the reference allows 20 %; this uses 200k lineages, 3 %)."""
+    p = -np.inf
+    for q in np.arange(0.0, 1.01, 0.1):
+        w = wo.WhaleModel(wo.ConstantDLWGD(lam=0.3, mu=0.4, q=[q, q], eta=0.66), wo.c1_tree(), 0.05, condition="nowhere")
+        c = wo.condition(w)
+        assert c > p
+        p = c
+    rng = np.random.default_rng(0)
+    lam, mu, q, eta, N = 0.3, 0.4, [0.35, 0.6], 0.66, 200000
+    w = wo.WhaleModel(wo.ConstantDLWGD(lam=lam, mu=mu, q=q, eta=eta), wo.c1_tree(), 0.05, condition="nowhere")
+
+    def evolve(n, t):  # linear BDP transition: each lineage dies out w.p. α, else leaves Geometric(1−β) copies
+        a = float(wo.getalpha(lam, mu, t))
+        b = lam / mu * a
+        surv = rng.binomial(n, 1.0 - a)
+        return surv + rng.negative_binomial(np.maximum(surv, 1), 1.0 - b) * (surv > 0)
+
+    def walk(node, n):
+        if node is not w.root:
+            n = evolve(n, node.dist)
+        if node.isleaf():
+            return n > 0
+        if node.iswgd():
+            n = n + rng.binomial(n, q[node.wgdid - 1])
+        ok = np.ones(N, bool)
+        for c in node.children:
+            ok &= walk(c, n)
+        return ok
+
+    ok = walk(w.root, rng.geometric(eta, N))
+    assert np.exp(wo.condition(w)) == pytest.approx(ok.mean(), rel=0.03)
+
+
+def test_nowhere_extinct_condition_gradient_by_differences():
+    # moderate rates: at λ ≈ μ ≈ e (the C1 test point) the probability is ~1e-8 and central differences of the
+    # alternating 2^9-term sum are pure cancellation noise
+    x0 = np.log(0.3) + np.linspace(-0.3, 0.2, 37)
+    x0[-3:] = [0.3, 0.15, 0.8]
+
+    def cond(x):
+        base = wo.c1_model(condition="nowhere")
+        m = base.with_rates(wo.rates_from_vector(base.rates, list(x)))
+        wo.setmodel(m)
+        return wo.condition(m)
+
+    P = len(x0)
+    c = cond([wo.Dual(v, np.eye(P)[i]) for i, v in enumerate(x0)])
+    for i in (0, 5, 16, 17, 30, 34, 35, 36):
+        h = 1e-5
+        xp, xm = x0.copy(), x0.copy()
+        xp[i] += h
+        xm[i] -= h
+        assert c.d[i] == pytest.approx((cond(xp) - cond(xm)) / (2 * h), rel=1e-5, abs=1e-8)

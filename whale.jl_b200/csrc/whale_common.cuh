@@ -129,7 +129,10 @@ struct PlanDev {  // tangent plan: which raw parameters each branch carries
     double* shapeW;        // [nn*NSHAPE*Kmax] last-row value wσ_n of every tree shape on leaf branch e
     double2* ls_uv;        // [tab_len] k_leafshapes scratch (projective ϵ rows of leaf nodes)
     double2* ls_pp;        // [tab_len] k_leafshapes scratch ((ϕ, ψ) rows of leaf nodes)
-    double* cond;          // [3*Kmax]   condition() per kind, components of the root
+    double* cond;          // [4*Kmax]   condition() per kind (none, root, nonextinct, nowhere), components of the root
+    const int* nwL;        // [nn] leaves below node e         } NowhereExtinctCondition scratch, allocated on
+    const long long* nwoff;  // [nn] offset of node e's pgf vector  } first use (k_nowhere)
+    double* nwvec;         // Σ_e 2^L_e · K_e doubles
     long long* tim;        // [32] k_tables cycle stamps (profiling aid)
 };
 

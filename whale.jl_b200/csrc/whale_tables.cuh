@@ -269,3 +269,104 @@ __global__ void __launch_bounds__(32) k_leafshapes(ModelDev M, PlanDev PL, const
     }
     if (on) PL.shapeW[((size_t)e * NSHAPE + sh) * PL.Kmax + k] = k == 0 ? w.v : w.d;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// k_nowhere — NowhereExtinctCondition (src/condition.jl:5-9,31-36): the probability that no leaf of the species
+// tree is left without a gene, by inclusion–exclusion over the tree pgf at all 2^L binary arguments
+// (treepgf_allbinary, src/bdputil.jl:109-133).  Node e carries the vector f_e(x) for x ∈ {0,1}^{leaves below e};
+// a parent's vector is the outer product of its children's (first child's index fastest) pushed through its own
+// branch pgf — LinearBDP(λ, μ, t) (:58-64), composed with the WGD pgf (:73) at WGD nodes, Geometric(η) at the
+// root.  Lanes = (argument index, component); tangents ride along as in k_tables.  One CTA; nodes in the model's
+// order (children first).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ D1 bdp_pgf(D1 lam, D1 mu, double t, D1 s) {
+    if (fabs(lam.v - mu.v) <= 1e-6) {  // isapprox(λ, μ, atol=ΛMATOL) on values
+        const D1 lt = lam * mk(t);
+        return (1.0 - (lt - 1.0) * (s - 1.0)) / (1.0 - lt * (s - 1.0));
+    }
+    const D1 rho = dexp((mu - lam) * mk(t));
+    const D1 a = rho * (lam * s - mu);
+    return (a - mu * (s - 1.0)) / (a - lam * (s - 1.0));
+}
+
+__global__ void __launch_bounds__(256) k_nowhere(ModelDev M, PlanDev PL, const double* __restrict__ x) {
+    __shared__ double sh[256];
+    const int Kmax = PL.Kmax;
+    const double NaN = __longlong_as_double(0x7ff8000000000000LL);
+    for (int oi = 0; oi < M.nn; oi++) {
+        const int e = M.order[oi];
+        const int K = PL.K[e], kind = M.kind[e], Le = PL.nwL[e];
+        const long long len = 1LL << Le;
+        double* ve = PL.nwvec + PL.nwoff[e];
+        const int c0 = M.child0[e], c1 = M.child1[e];
+        const int K0 = c0 >= 0 ? PL.K[c0] : 0, K1 = c1 >= 0 ? PL.K[c1] : 0;
+        const int L0 = c0 >= 0 ? PL.nwL[c0] : 0;
+        const double* v0 = c0 >= 0 ? PL.nwvec + PL.nwoff[c0] : nullptr;
+        const double* v1 = c1 >= 0 ? PL.nwvec + PL.nwoff[c1] : nullptr;
+        const int ls = M.lam_slot[e], ms = M.mu_slot[e];
+        const double lv = ls < 0 ? NaN : (M.log_scale ? exp(x[ls]) : x[ls]);
+        const double mv = ms < 0 ? NaN : (M.log_scale ? exp(x[ms]) : x[ms]);
+        const double t = M.dt[e] * (double)M.nsl[e];
+        for (long long idx = threadIdx.x; idx < len * K; idx += blockDim.x) {
+            const long long i = idx / K;
+            const int k = (int)(idx - i * K);
+            const unsigned role = k == 0 ? 0u : PL.role[e * Kmax + k];
+            D1 s;
+            if (kind == WHALE_LEAF) {
+                s = mk(i == 0 ? 0.0 : 1.0);
+            } else {
+                const long long i0 = c1 >= 0 ? (i & ((1LL << L0) - 1)) : i, i1 = c1 >= 0 ? (i >> L0) : 0;
+                const int k0 = k == 0 ? 0 : PL.cmap[(e * 2 + 0) * Kmax + k];
+                D1 a = mk(v0[i0 * K0], (k > 0 && k0 >= 0) ? v0[i0 * K0 + k0] : 0.0);
+                if (c1 >= 0) {
+                    const int k1 = k == 0 ? 0 : PL.cmap[(e * 2 + 1) * Kmax + k];
+                    const D1 b = mk(v1[i1 * K1], (k > 0 && k1 >= 0) ? v1[i1 * K1 + k1] : 0.0);
+                    a = a * b;
+                }
+                if (kind == WHALE_WGD) {  // wgdpgf(q, s) = s(1 − q + s q)
+                    const D1 q = mk(x[M.q_slot[e]], (role & 4u) ? 1.0 : 0.0);
+                    a = a * ((1.0 - q) + a * q);
+                }
+                s = a;
+            }
+            D1 r;
+            if (kind == WHALE_ROOT) {
+                const D1 eta = mk(x[M.eta_slot], (role & 8u) ? 1.0 : 0.0);
+                r = eta * s / (1.0 - (1.0 - eta) * s);  // geompgf
+            } else {
+                const D1 lam = mk(lv, (role & 1u) ? (M.log_scale ? lv : 1.0) : 0.0);
+                const D1 mu = mk(mv, (role & 2u) ? (M.log_scale ? mv : 1.0) : 0.0);
+                r = bdp_pgf(lam, mu, t, s);
+            }
+            ve[idx] = k == 0 ? r.v : r.d;
+        }
+        __syncthreads();
+    }
+    // c = 1 − Σ_{i < 2^L − 1} (−1)^{popcount(i)} p_i ; condition = log c for 0 < c < 1, else −Inf
+    const int root = M.root, KR = PL.K[root];
+    const long long len = 1LL << PL.nwL[root];
+    const double* p = PL.nwvec + PL.nwoff[root];
+    __shared__ double c0s;
+    for (int k = 0; k < KR; k++) {
+        double acc = 0.0;
+        for (long long i = threadIdx.x; i < len - 1; i += blockDim.x) {
+            const double v = p[i * KR + k];
+            acc += (__popcll((unsigned long long)i) & 1) ? -v : v;
+        }
+        sh[threadIdx.x] = acc;
+        __syncthreads();
+        for (int w = 128; w > 0; w >>= 1) {
+            if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            if (k == 0) {
+                c0s = 1.0 - sh[0];
+                PL.cond[3 * Kmax] = (c0s > 0.0 && c0s < 1.0) ? log(c0s) : -dinf();
+            } else {
+                PL.cond[3 * Kmax + k] = (c0s > 0.0 && c0s < 1.0) ? -sh[0] / c0s : 0.0;
+            }
+        }
+        __syncthreads();
+    }
+}

@@ -269,11 +269,11 @@ static cudaError_t upload_plan(Plan& pl, int nn) {
     if ((e = cudaMalloc((void**)&cx, nk)) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&cy, nk)) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&leaf, nk)) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void**)&cond, 3 * pl.Kmax * sizeof(double))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&cond, 4 * pl.Kmax * sizeof(double))) != cudaSuccess) return e;
     cudaMemset(cx, 0, nk); cudaMemset(cy, 0, nk); cudaMemset(leaf, 0, nk);
-    cudaMemset(cond, 0, 3 * pl.Kmax * sizeof(double));
+    cudaMemset(cond, 0, 4 * pl.Kmax * sizeof(double));
     pl.owned = {dK, dact, dtoff, dcmap, drole, eps, pp, uv, ab, cx, cy, leaf, shapeW, lsuv, lspp, cond, tim};
-    pl.dev = PlanDev{pl.Kmax, dK, dact, dcmap, drole, dtoff, eps, pp, uv, ab, cx, cy, leaf, shapeW, lsuv, lspp, cond, tim};
+    pl.dev = PlanDev{pl.Kmax, dK, dact, dcmap, drole, dtoff, eps, pp, uv, ab, cx, cy, leaf, shapeW, lsuv, lspp, cond, nullptr, nullptr, nullptr, tim};
     return cudaSuccess;
 }
 
@@ -865,10 +865,33 @@ int64_t whale_data_arena_dump(whale_data_t d, void* buf, int64_t cap) {
     return n;
 }
 
+// NowhereExtinctCondition scratch of a plan: Σ_e 2^L_e · K_e doubles (L_e = leaves below node e), on first use
+static int32_t ensure_nowhere(whale_model* m, Plan& pl) {
+    if (pl.dev.nwvec) return WHALE_OK;
+    const int nn = m->nn;
+    std::vector<int> L(nn, 0);
+    std::vector<long long> off(nn, 0);
+    long long tot = 0;
+    for (int oi = 0; oi < nn; oi++) {
+        const int e = m->order[oi];
+        L[e] = m->kind[e] == WHALE_LEAF ? 1 : (m->child0[e] >= 0 ? L[m->child0[e]] : 0) + (m->child1[e] >= 0 ? L[m->child1[e]] : 0);
+        if (L[e] > 20) return fail(WHALE_ERR_CAPACITY, "NowhereExtinctCondition needs 2^%d terms (more than 20 leaves)", L[e]);
+        off[e] = tot;
+        tot += (1LL << L[e]) * pl.K[e];
+    }
+    int* dL = nullptr; long long* doff = nullptr; double* dv = nullptr;
+    CU(upload(L, &dL));
+    CU(upload(off, &doff));
+    CU(cudaMalloc((void**)&dv, (size_t)tot * sizeof(double)));
+    pl.owned.push_back(dL); pl.owned.push_back(doff); pl.owned.push_back(dv);
+    pl.dev.nwL = dL; pl.dev.nwoff = doff; pl.dev.nwvec = dv;
+    return WHALE_OK;
+}
+
 // enqueue [tables -> DP -> reduction] for every tangent plan of this evaluation on `st`; result in d_out
 static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, int32_t condition, uint32_t flags,
                             double* d_out, cudaStream_t st) {
-    if (condition < 0 || condition > 2) return fail(WHALE_ERR_ARG, "unknown condition kind %d", condition);
+    if (condition < 0 || condition > 3) return fail(WHALE_ERR_ARG, "unknown condition kind %d", condition);
     const bool grad = (flags & WHALE_WANT_GRAD) != 0;
     const int nn = m->nn, F = D->F;
     const bool keep = (flags & WHALE_KEEP_ELL) != 0;
@@ -903,6 +926,12 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
         }
         LAUNCH(k_tables, 1, TABLES_NT, tables_smem(m, pl), st, m->dev, pl.dev, d_x, m->d_pleaf);
         g_launches++;
+        if (condition == WHALE_COND_NOWHERE) {
+            int32_t rcn = ensure_nowhere(m, pl);
+            if (rcn != WHALE_OK) return rcn;
+            LAUNCH(k_nowhere, 1, 256, 0, st, m->dev, pl.dev, d_x);
+            g_launches++;
+        }
         if (!keep && !m->leafnodes.empty()) CU(cudaStreamWaitEvent(st, D->ev_tab, 0));
         if (prof && first) CU(cudaEventRecord(D->ev[1], st));
         // K2: one launch per shared-memory bin, concurrently on side streams
@@ -1043,7 +1072,7 @@ int32_t whale_mixture_logpdf_grad(whale_model_t m, whale_data_t d, int32_t n_com
                                   double* grad_x, double* grad_logw) {
     if (!m || !d || !x || !log_w || !loglik || n_comp < 1) return fail(WHALE_ERR_ARG, "null argument");
     if (d->m != m) return fail(WHALE_ERR_ARG, "data handle belongs to another model");
-    if (condition < 0 || condition > 2) return fail(WHALE_ERR_ARG, "unknown condition kind %d", condition);
+    if (condition < 0 || condition > 3) return fail(WHALE_ERR_ARG, "unknown condition kind %d", condition);
     const bool grad = (flags & WHALE_WANT_GRAD) != 0;
     if ((grad_x || grad_logw) && !grad) return fail(WHALE_ERR_ARG, "grad requested without WHALE_WANT_GRAD");
     CU(cudaSetDevice(m->device));

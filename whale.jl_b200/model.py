@@ -19,8 +19,8 @@ from . import newick
 from .rates import ConstantDLWGD, DLWGD
 
 LEAF, INTERNAL, WGD, ROOT = 0, 1, 2, 3
-CONDITIONS = {"none": 0, "root": 1, "nonextinct": 2,
-              "NoCondition": 0, "RootCondition": 1, "NonExtinctCondition": 2}
+CONDITIONS = {"none": 0, "root": 1, "nonextinct": 2, "nowhere": 3,
+              "NoCondition": 0, "RootCondition": 1, "NonExtinctCondition": 2, "NowhereExtinctCondition": 3}
 
 
 def iswgd(name: str) -> bool:
