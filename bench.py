@@ -175,7 +175,7 @@ def main():
     d, gen_s = dataset(rank, args.families)
     model = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), W.synth.c1_species_tree(), DT)
     t0 = time.time()
-    ccds = W.read_ale(d, model)
+    ccds = W.read_ale_native(d, model)  # whale_read_ale: parse + CCD construction + packing in the library
     from whale_jl_b200.core import _data_handle
     mh, dh = _data_handle(model, ccds)
     pack_s = time.time() - t0

@@ -115,6 +115,17 @@ int32_t whale_model_destroy(whale_model_t m);
 
 /* read_ale-time packing (src/ccd.jl:126-137 + CCD ctor): builds the device arena once */
 int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* desc, whale_data_t* out);
+/*
+ * read_ale in one native call (src/ccd.jl:126-248): parse n_files ALEobserve `.ale` files on n_threads host
+ * threads (0 = all), build each CCD in the reference's layout (leaf clades, the ubiquitous clade, ids by size,
+ * split probabilities, compat lists) and pack the device arena.  The species tree contributes the gene-name
+ * prefix -> species id map (species_names/species_ids, `n_species` entries; MUL trees give several leaves one id,
+ * src/model.jl:133-135) and, per node, the species ids below it (node_clade_off[n_nodes+1], node_clade).
+ * n_clades (nullable, [n_files]) receives Γ of every family.
+ */
+int32_t whale_read_ale(whale_model_t m, int32_t n_files, const char* const* paths, int32_t n_species,
+                       const char* const* species_names, const int32_t* species_ids, const int64_t* node_clade_off,
+                       const int32_t* node_clade, int32_t n_threads, whale_data_t* out, int32_t* n_clades);
 int32_t whale_data_destroy(whale_data_t d);
 int32_t whale_data_nfam(whale_data_t d);
 /* bytes of the packed arena resident in HBM, and the algorithmic bytes one evaluation reads */

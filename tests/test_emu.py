@@ -105,3 +105,37 @@ def test_emu_fused_track(L):
 def test_emu_nowhere_extinct_condition(L):
     from conftest import nowhere_condition_vs_oracle
     nowhere_condition_vs_oracle(L)
+
+
+def test_emu_native_read_ale_is_bit_identical(L, tmp_path):
+    """whale_read_ale (C++ parser + CCD builder + packer, all host threads) produces byte-for-byte the arena that
+    the Python read_ale -> whale_data_create path produces: synthetic families on the C1 tree, and (when the
+    reference checkout is present) its example-1 / landplant / MUL-tree fixtures."""
+    import whale_jl_b200 as W
+    from whale_jl_b200 import synth, newick
+    from conftest import HAVE_REF, REF
+    wlib.use(L)
+    try:
+        cases = [(synth.generate(str(tmp_path / "nat"), 12, seed=21), synth.c1_species_tree(), 0.05)]
+        if HAVE_REF:
+            cases.append((os.path.join(REF, "example", "example-1", "ale"), synth.c1_species_tree(), 0.05))
+            t5 = newick.readnw(open(os.path.join(REF, "example", "example-5", "tree.nw")).read().strip())
+            lst = tmp_path / "ex5.txt"  # a text file listing paths (src/ccd.jl:131-133)
+            lst.write_text("".join(os.path.join(REF, "example", "example-5", f) + "\n" for f in ("OG0006450.ale", "OG0014587.ale")))
+            cases.append((str(lst), t5, 0.1))
+            cases.append((os.path.join(REF, "docs", "data", "landplant", "100fams"), None, 0.05))
+        for d, tree, dt in cases:
+            if tree is None:  # landplant fixture: 100 families, 15..1025 clades
+                tree = newick.readnw(open(os.path.join(REF, "docs", "data", "landplant", "speciestree.nw")).read().strip())
+            w = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1][:sum(1 for n in newick.postwalk(tree) if n.name.startswith("wgd"))], eta=0.67), tree, dt)
+            a = W.read_ale(d, w)
+            b = W.read_ale_native(d, w, n_threads=3)
+            from whale_jl_b200.core import _data_handle
+            mh, dha = _data_handle(w, a)
+            _, dhb = _data_handle(w, b)
+            assert len(a) == len(b) and [len(x.nleaf) for x in a] == b.n_clades.tolist()
+            assert np.array_equal(L.arena_dump(dha), L.arena_dump(dhb))
+            if len(a) <= 12:  # the emulated kernels are slow: evaluate only the small batches
+                assert W.logpdf(w, b) == W.logpdf(w, a)
+    finally:
+        wlib.use(None)

@@ -223,6 +223,20 @@ def test_mixture_on_device_with_gradient(L, tmp_path):
     mixture_vs_oracle(tmp_path, n_fam=24)
 
 
+def test_native_read_ale(L, tmp_path):
+    """whale_read_ale (native parse + build + pack) gives the arena and results of the Python read_ale path."""
+    from whale_jl_b200.core import _data_handle
+    d = synth.generate(str(tmp_path / "nat"), 40, seed=21)
+    w = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), synth.c1_species_tree(), 0.05)
+    a, b = W.read_ale(d, w), W.read_ale_native(d, w)
+    _, dha = _data_handle(w, a)
+    _, dhb = _data_handle(w, b)
+    assert np.array_equal(L.arena_dump(dha), L.arena_dump(dhb))
+    la, ga = W.logpdf_and_gradient(w, a)
+    lb, gb = W.logpdf_and_gradient(w, b)
+    assert la == lb and np.array_equal(ga, gb)
+
+
 def test_nowhere_extinct_condition(L):
     """NowhereExtinctCondition (src/condition.jl:31-36, 2^9 inclusion–exclusion terms) on the device."""
     from conftest import nowhere_condition_vs_oracle

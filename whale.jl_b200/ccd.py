@@ -167,6 +167,44 @@ class CCDVector(list):
                     p=p, compat_off=compat_off, compat=compat)
 
 
+def _ale_files(path: str) -> list[str]:
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"Not a file nor directory `{path}`")
+    if os.path.isfile(path) and path.endswith(".ale"):
+        files = [path]
+    elif os.path.isfile(path):
+        files = [l.strip() for l in open(path) if l.strip()]
+    else:
+        files = [os.path.join(path, f) for f in sorted(os.listdir(path))]
+    return [f for f in files if not f.startswith("#")]
+
+
+class NativeCCDVector:
+    """`Vector{CCD}` whose families were parsed, built and packed by the library itself (`whale_read_ale`): the
+    CCDs exist only as the device arena.  Usable wherever a batch is evaluated (`logpdf`, `logpdf_and_gradient`,
+    `logpdf_mixture`, `backtrack`, `track`); per-CCD host detail (`ell`, leaf names) needs `read_ale`."""
+
+    def __init__(self, files, n_clades, model, lib, handle):
+        self.files, self.n_clades = list(files), np.asarray(n_clades)
+        self._model_nn = model.nn
+        self._data = {(id(lib), model._handle[1]): handle}
+
+    def __len__(self):
+        return len(self.files)
+
+
+def read_ale_native(path: str, model: WhaleModel, n_threads: int = 0) -> NativeCCDVector:
+    """`read_ale(path, wm)` (src/ccd.jl:126-137) done natively: files parsed on all host threads straight into the
+    packed device arena (the reference parses under `tmap`, src/ccd.jl:134)."""
+    from . import lib as _lib
+    from .core import _model_handle
+    files = _ale_files(path)
+    L = _lib.get()
+    mh = _model_handle(model)
+    h, ncl = L.read_ale(mh, model, files, n_threads)
+    return NativeCCDVector(files, ncl, model, L, h)
+
+
 def read_ale(path: str, model: WhaleModel) -> CCDVector:
     """`read_ale(path, wm)` (src/ccd.jl:126-137): a `.ale` file, a directory of them (sorted like
     `readdir`), or a text file listing paths (lines starting with # skipped)."""

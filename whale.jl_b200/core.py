@@ -8,7 +8,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import lib as _lib
-from .ccd import CCD, CCDVector
+from .ccd import CCD, CCDVector, NativeCCDVector
 from .model import CONDITIONS, WhaleModel
 
 
@@ -24,11 +24,15 @@ def _data_handle(wm: WhaleModel, xs: CCDVector):
     mh = _model_handle(wm)
     key = (id(L), mh)
     if key not in xs._data:
+        if isinstance(xs, NativeCCDVector):
+            raise ValueError("a natively read batch belongs to the model it was read with (same structure handle)")
         xs._data[key] = L.data_create(mh, xs.flatten(wm.nn))
     return mh, xs._data[key]
 
 
 def _as_vector(x) -> tuple[CCDVector, bool]:
+    if isinstance(x, NativeCCDVector):
+        return x, False
     if isinstance(x, CCD):
         if x._batch is None:
             x._batch = CCDVector([x])

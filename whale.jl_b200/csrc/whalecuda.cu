@@ -23,6 +23,7 @@
 #include "whale_dp.cuh"
 #include "whale_reduce.cuh"
 #include "whale_track.cuh"
+#include "whale_ale.hpp"
 
 #include <algorithm>
 #include <atomic>
@@ -828,6 +829,54 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
     CU(cudaStreamCreateWithFlags(&D->side_tab, cudaStreamNonBlocking));
     *out = D;
     return WHALE_OK;
+}
+
+int32_t whale_read_ale(whale_model_t m, int32_t n_files, const char* const* paths, int32_t n_species,
+                       const char* const* species_names, const int32_t* species_ids, const int64_t* node_clade_off,
+                       const int32_t* node_clade, int32_t n_threads, whale_data_t* out, int32_t* n_clades) {
+    if (!m || !paths || !species_names || !species_ids || !node_clade_off || !node_clade || !out || n_files <= 0)
+        return fail(WHALE_ERR_ARG, "null argument");
+    const int nn = m->nn;
+    whale_ale::Species sp;
+    for (int i = 0; i < n_species; i++) {
+        if (species_ids[i] < 0) return fail(WHALE_ERR_ARG, "negative species id");
+        sp.id_of[species_names[i]] = species_ids[i];
+        sp.n_ids = std::max(sp.n_ids, (int)species_ids[i]);
+    }
+    for (int64_t i = 0; i < node_clade_off[nn]; i++) sp.n_ids = std::max(sp.n_ids, (int)node_clade[i]);
+    sp.words = (sp.n_ids + 64) / 64;
+    sp.node_mask.assign(nn, std::vector<uint64_t>(sp.words, 0));
+    for (int e = 0; e < nn; e++)
+        for (int64_t i = node_clade_off[e]; i < node_clade_off[e + 1]; i++) {
+            if (node_clade[i] < 0) return fail(WHALE_ERR_ARG, "negative species id");
+            sp.node_mask[e][node_clade[i] >> 6] |= 1ull << (node_clade[i] & 63);
+        }
+    std::vector<std::string> files(paths, paths + n_files);
+    std::vector<whale_ale::Family> fams;
+    whale_ale::parse_all(files, sp, nn, fams, n_threads);
+    for (int f = 0; f < n_files; f++)
+        if (!fams[f].error.empty()) return fail(WHALE_ERR_ARG, "%s", fams[f].error.c_str());
+    // concatenate into the flattened reference layout and pack
+    std::vector<int64_t> clade_off(1, 0), split_off(1, 0), compat_off(1, 0);
+    std::vector<int32_t> nleaf, g1, g2, compat;
+    std::vector<double> p;
+    for (int f = 0; f < n_files; f++) {
+        const whale_ale::Family& F = fams[f];
+        const int64_t sbase = (int64_t)g1.size(), cbase = (int64_t)compat.size();
+        clade_off.push_back(clade_off.back() + (int64_t)F.nleaf.size());
+        nleaf.insert(nleaf.end(), F.nleaf.begin(), F.nleaf.end());
+        for (size_t i = 1; i < F.split_off.size(); i++) split_off.push_back(sbase + F.split_off[i]);
+        g1.insert(g1.end(), F.g1.begin(), F.g1.end());
+        g2.insert(g2.end(), F.g2.begin(), F.g2.end());
+        p.insert(p.end(), F.p.begin(), F.p.end());
+        for (size_t i = 1; i < F.compat_off.size(); i++) compat_off.push_back(cbase + F.compat_off[i]);
+        compat.insert(compat.end(), F.compat.begin(), F.compat.end());
+        if (n_clades) n_clades[f] = (int32_t)F.nleaf.size();
+        fams[f] = whale_ale::Family();  // release as we go
+    }
+    whale_ccd_desc d{n_files, clade_off.data(), nleaf.data(), split_off.data(), g1.data(), g2.data(), p.data(),
+                     compat_off.data(), compat.data()};
+    return whale_data_create(m, &d, out);
 }
 
 int32_t whale_data_destroy(whale_data_t d) {

@@ -19,7 +19,7 @@ WANT_GRAD, KEEP_ELL, PROFILE = 1, 2, 4
 
 # every symbol include/whalecuda.h declares (tests check the built library exports all of them)
 SYMBOLS = ["whale_version", "whale_last_error", "whale_device_count", "whale_set_device", "whale_model_create",
-           "whale_model_destroy", "whale_data_create", "whale_data_destroy", "whale_data_nfam",
+           "whale_model_destroy", "whale_data_create", "whale_read_ale", "whale_data_destroy", "whale_data_nfam",
            "whale_data_arena_bytes", "whale_data_arena_dump", "whale_logpdf_grad", "whale_logpdf_grad_async", "whale_mixture_logpdf_grad",
            "whale_slices", "whale_ell_size", "whale_ell_get", "whale_backtrack", "whale_track", "whale_launch_count",
            "whale_work_estimate", "whale_last_kernel_ms", "whale_last_phase_cycles", "whale_last_node_cycles", "whale_last_family_cycles", "whale_last_tables_cycles", "whale_last_backtrack_ms", "whale_fp64_peak"]
@@ -85,6 +85,8 @@ class Lib:
         L.whale_work_estimate.argtypes = [vp, vp, C.c_uint32, f64p, f64p]
         L.whale_fp64_peak.argtypes = [f64p]
         L.whale_last_kernel_ms.argtypes = [vp, f64p, f64p, f64p]
+        L.whale_read_ale.argtypes = [vp, C.c_int32, C.POINTER(C.c_char_p), C.c_int32, C.POINTER(C.c_char_p), i32p, i64p, i32p,
+                                     C.c_int32, C.POINTER(vp), i32p]
         L.whale_mixture_logpdf_grad.argtypes = [vp, vp, C.c_int32, f64p, f64p, f64p, C.c_int32, C.c_uint32,
                                                 C.POINTER(C.c_double), f64p, f64p]
         L.whale_last_phase_cycles.argtypes = [vp, f64p, f64p]
@@ -118,6 +120,21 @@ class Lib:
         h = C.c_void_p()
         self.check(self.L.whale_data_create(mh, C.byref(d), C.byref(h)))
         return h.value
+
+    def read_ale(self, mh, model, files, n_threads=0):
+        """whale_read_ale: parse + build + pack natively; returns (data handle, clades per family)."""
+        names = list(model.spmap)
+        ids = np.array([model.spmap[n] for n in names], np.int32)
+        off = np.zeros(model.nn + 1, np.int64)
+        np.cumsum([len(model.clade[e]) for e in range(model.nn)], out=off[1:])
+        cl = np.array([s for e in range(model.nn) for s in sorted(model.clade[e])], np.int32)
+        cpaths = (C.c_char_p * len(files))(*[f.encode() for f in files])
+        cnames = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        ncl = np.zeros(len(files), np.int32)
+        h = C.c_void_p()
+        self.check(self.L.whale_read_ale(mh, len(files), cpaths, len(names), cnames, _ptr(ids, i32p), _ptr(off, i64p),
+                                         _ptr(cl, i32p), n_threads, C.byref(h), _ptr(ncl, i32p)))
+        return h.value, ncl
 
     def logpdf_grad(self, mh, dh, x, p_leaf, condition, want_grad=False, keep_ell=False, per_family=False,
                     per_family_grad=False, profile=False):
