@@ -166,8 +166,12 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a short collective timeout: a rank that falls out of step fails the run in two minutes instead of ten
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
     L = wlib.get()
     L.check(L.L.whale_set_device(local))
 
@@ -227,10 +231,11 @@ def main():
     total_ms = float(step_ms.sum())
     last = OUT.cpu().numpy().copy()
     # keep the GPU under the same load a little longer if the region was too short for nvidia-smi to sample
+    # (rank-local work only: the number of rounds differs between ranks, so no collective may be issued here)
     t_probe = time.perf_counter()
     while len(sampler.rows) < 8 and time.perf_counter() - t_probe < 3.0:
         for i in range(Wm):
-            step(i, wlib.WANT_GRAD)
+            L.logpdf_grad_async(mh, dh, X[i].data_ptr(), cond, wlib.WANT_GRAD, OUT.data_ptr(), stream)
         torch.cuda.synchronize()
     clocks = sampler.stop()
     if world > 1:

@@ -107,19 +107,20 @@ static int env_int(const char* name, int dflt) {
     return s ? atoi(s) : dflt;
 }
 static int dp_nt() {
-    static int nt = [] { int v = env_int("WHALE_NT", 128); return (v == 64 || v == 256) ? v : 128; }();
+    static int nt = [] { int v = env_int("WHALE_NT", 128); return (v == 64 || v == 96 || v == 256) ? v : 128; }();
     return nt;
 }
 static int dp_minb() {  // resident CTAs per SM the register cap is chosen for
     static int mb = [] {
         const int nt = dp_nt(), v = env_int("WHALE_MINB", 0);
         if (nt == 64) return (v == 6 || v == 8 || v == 10) ? v : 12;
+        if (nt == 96) return v == 6 ? 6 : 5;
         if (nt == 256) return v == 3 ? 3 : 2;
         return (v == 3 || v == 5 || v == 6 || v == 7) ? v : 4;
     }();
     return mb;
 }
-#define DP_VARIANTS(X) X(64, 6) X(64, 8) X(64, 10) X(64, 12) X(128, 3) X(128, 4) X(128, 5) X(128, 6) X(128, 7) X(256, 2) X(256, 3)
+#define DP_VARIANTS(X) X(96, 5) X(96, 6) X(64, 6) X(64, 8) X(64, 10) X(64, 12) X(128, 3) X(128, 4) X(128, 5) X(128, 6) X(128, 7) X(256, 2) X(256, 3)
 constexpr int MAX_BINS = 8;
 struct Bin {
     int off, count;
@@ -735,7 +736,7 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
     set_budgets(D, 0, m->plan[0]);
     size_t need1 = set_budgets(D, 1, m->plan[1]);
     const size_t SMEM_MAX = 227 * 1024;
-    const size_t SMEM_GOAL = (size_t)env_int("WHALE_SMEM_GOAL", 113 * 1024);  // default: at least two families per SM
+    const size_t SMEM_GOAL = (size_t)env_int("WHALE_SMEM_GOAL", 80000);  // default: at least two families per SM
     if (need1 > SMEM_GOAL || m->plan[1].Kmax > dp_nt()) {
         // parameters ordered by the node that owns them (subtrees stay together -> sparse chunks)
         std::vector<int> porder;
