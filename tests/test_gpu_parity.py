@@ -123,12 +123,14 @@ def test_synthetic_c2_shape_vs_oracle(L, tmp_path):
     np.testing.assert_allclose(grad, og, rtol=1e-9, atol=1e-9 * np.abs(og).max())
 
 
-def test_c4_shape_vs_oracle(L, tmp_path):
+@pytest.mark.parametrize("stage_max", ["24576", "163840"])
+def test_c4_shape_vs_oracle(L, tmp_path, monkeypatch, stage_max):
     """BASELINE config 3 shape: 30-taxon tree with 5 WGDs (64 nodes), CCDs of ~2,000 clades — lists too long to
     stage in shared memory (read in place) and a gradient computed in parameter chunks; constant rates (P = 8)
     and branch-wise rates (P = 122) against the oracle."""
     from oracle import whale_oracle as wo, flat
     from whale_jl_b200 import newick
+    monkeypatch.setenv("WHALE_STAGE_MAX", stage_max)  # lists read in place (large batches) / staged (small batches)
     tree = synth.c4_species_tree()
     nws = newick.nwstr(tree, True) + ";"
     d = synth.generate(str(tmp_path / "c4"), 3, seed=4, tree=synth.c4_species_tree(), **synth.C4_FAMILY)

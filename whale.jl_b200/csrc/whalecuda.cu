@@ -456,7 +456,9 @@ static size_t set_budgets(whale_data* D, int g, const Plan& pl) {
         H.prod_len[g] = even(prod);
         H.leafmax[g] = even(mxleaf);
         // long lists (large CCDs) are not staged: the kernel then reads them from global memory in place
-        const size_t STAGE_MAX = (size_t)env_int("WHALE_STAGE_MAX", 24 * 1024);
+        // (a batch smaller than the GPU is latency-bound: stage whatever fits, +20 % on 64 C4 families; a large batch is
+        //  bound by how many families an SM holds: keep the staging buffer small)
+        const size_t STAGE_MAX = (size_t)env_int("WHALE_STAGE_MAX", D->F <= 160 ? 160 * 1024 : 24 * 1024);
         H.stage_bytes[g] = 16 * stg > STAGE_MAX ? 0u : (uint32_t)(16 * stg);
         worst = std::max(worst, smem_need(m, H, g, pl.Kmax));
         if (env_int("WHALE_DEBUG", 0) >= 2)
@@ -782,6 +784,9 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
             }
         }
     }
+    if (env_int("WHALE_DEBUG", 0) >= 1)
+        fprintf(stderr, "[whale] %d families, P = %d: %zu gradient pass(es), worst family %zu B of shared memory\n", F, m->P,
+                D->plans.size() - 1, need1);
     if (need1 > SMEM_MAX) { delete D; return fail(WHALE_ERR_CAPACITY, "a family needs %zu bytes of shared memory (> 227 KB) even with %d parameter chunks", need1, MAXPLAN - 1); }
     // bins by shared-memory need (geometric, <= 25 % waste), launched concurrently; within a bin the
     // heaviest families go first
