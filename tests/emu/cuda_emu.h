@@ -7,6 +7,7 @@
 // It is NOT a fallback: the package only ever loads whale.jl_b200/libwhalecuda.so, which requires a GPU.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
@@ -104,6 +105,8 @@ inline double shfl_idx(double v, int src) {
 }
 }  // namespace emu
 inline void __syncthreads() { emu::g_bar->wait(); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline void __syncwarp() { (*emu::g_wbar)[threadIdx.x / 32].wait(); }
 #define EXTERN_SHARED(name) unsigned char* name = emu::g_smem
 

@@ -58,6 +58,11 @@ struct Slot {
 static_assert(sizeof(Slot) == 8, "Slot must be 8 bytes");
 constexpr uint32_t HEAVY_SLOTS = 24;
 
+#ifdef WHALE_EMU
+constexpr int TABLES_NT = 128;  // host-thread emulation: keep the thread count small
+#else
+constexpr int TABLES_NT = 512;
+#endif
 constexpr int MAXPLAN = 64;  // tangent plans per data handle: [0] value only, [1..] gradient (parameter chunks)
 
 // Tree shapes for the closed form of leaf branches.  On a leaf branch e every leaf clade has the same

@@ -34,6 +34,12 @@ struct DPArgs {
     int plan;          // 0 value only, 1 with tangents
     int skip_leaf;     // share family-independent leaf-branch rows (off in keep_ell mode)
     long long* tim;    // optional per-family phase cycle counters [F][TIMW] (profiling aid) or nullptr
+    // fused K3: the CTA that finishes last sums the per-family outputs (fixed order), subtracts N·condition and
+    // scatters the plan's components into `out`  (src/core.jl:54,63 ; src/condition.jl).  done == nullptr: off
+    unsigned int* done;  // CTAs of this plan finished so far (all bins); re-armed to 0 by the last one
+    int n_total;         // F
+    int cond_kind, first;
+    double* out;         // [1+P]
 };
 // tim layout: [0..7] phases, [8 + oi] slice-loop cycles of inner node oi, [8 + TIMN + oi] staging + row-1 cycles
 constexpr int TIMN = 32, TIMW = 8 + 2 * TIMN;
@@ -501,6 +507,48 @@ __device__ __forceinline__ bool run_slices_fused_k(int K, int n, int C, double* 
 #undef CASEK
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fused K3.  Every CTA publishes its family's (log L, ∇) and bumps a counter; the CTA that sees the last count
+// reduces: warp w owns the components k ≡ w (mod NW), lanes stride the families, a shuffle tree closes — the order
+// of the additions depends on (F, NT) only, never on which CTA happens to be last (deterministic bits).
+// ---------------------------------------------------------------------------------------------------------
+#ifdef WHALE_EMU
+#define LDCG(p) (*(p))
+#else
+#define LDCG(p) __ldcg(p)
+#endif
+template <int NT>
+__device__ __forceinline__ void dp_tail_reduce(const DPArgs& A, double* s_tot) {
+    __shared__ int s_last;
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    __syncthreads();  // this family's outputs are written
+    if (tid == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(A.done, 1u);
+        s_last = (prev + 1u == (unsigned)A.n_total) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int root = A.M.root, KR = A.PL.K[root], F = A.n_total, Kmax = A.PL.Kmax;
+    for (int k = warp; k < KR; k += NW) {
+        double s = 0.0;
+        for (int f = lane; f < F; f += 32) s += LDCG(A.out_fam + (size_t)f * KR + k);
+        for (int step = 16; step > 0; step >>= 1) s += SHFL_DOWN(s, step);
+        if (lane == 0) s_tot[k] = s - (double)F * A.PL.cond[A.cond_kind * Kmax + k];
+    }
+    __syncthreads();
+    const bool finite = isfinite(s_tot[0]);  // ℓhood src/core.jl:15
+    // `out` was zeroed by the host; every gradient pass (parameter chunk) writes its own parameters, the first
+    // pass also the log-likelihood
+    for (int k = tid; k < KR; k += NT) {
+        if (k == 0) { if (A.first) A.out[0] = finite ? s_tot[0] : -dinf(); }
+        else A.out[1 + A.PL.act[root * Kmax + k]] = finite ? s_tot[k] : 0.0;
+    }
+    if (tid == 0) *A.done = 0u;
+}
+
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
     EXTERN_SHARED(smem_raw);
@@ -852,4 +900,5 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
             T[7] = 0;
         }
     }
+    if (A.done) dp_tail_reduce<NT>(A, reinterpret_cast<double*>(smem_raw));
 }

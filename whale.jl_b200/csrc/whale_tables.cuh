@@ -1,76 +1,102 @@
 // K1 — slice tables (ϵ, ϕ, ψ) with forward tangents.  src/model.jl:162-191, src/bdputil.jl:6-11.
 //
-// The reference iterates ϵ_i = (α + (1−α−β)ϵ_{i−1}) / (1 − βϵ_{i−1}) slice by slice — one fp64 division on
-// the dependent chain per slice.  All slices of a branch share (α, β) (uniform Δt, src/model.jl:20), so the
-// step is ONE Möbius map; in projective form ϵ = u/v it is linear and division-free:
-//     u_i = (1−α−β) u_{i−1} + α v_{i−1},      v_i = v_{i−1} − β u_{i−1}
-// and 1 − βϵ_{i−1} = v_i / v_{i−1}, so  ϕ_i = g (v_{i−1}/v_i)²,  ψ_i = g β (v_{i−1}/v_i)³,  ϵ_i = u_i/v_i  with
-// g = (1−α)(1−β).  Phase A runs that short FMA chain per (node, component) level by level (children first);
-// phase B evaluates all rows of all nodes in parallel (the divisions are now independent).  The same exact
-// composition as the reference up to rounding (≲1e-14), including its value-based critical-case test.
+// The reference iterates ϵ_i = (α + (1−α−β)ϵ_{i−1}) / (1 − βϵ_{i−1}) slice by slice.  All slices of a branch share
+// (α, β) (uniform Δt, src/model.jl:20), so the step is ONE Möbius map M = [[1−α−β, α], [−β, 1]] and row i is M^i ϵ_0.
+//   * closed form (the normal case).  For the linear birth–death process the i-fold composition is the same map
+//     with (α, β) evaluated at time i·Δt:  ϵ_i = (α_i + (1−α_i−β_i)ϵ_0) / (1 − β_i ϵ_0),  α_i = getα(λ, μ, iΔt).
+//     Every row of every branch is then independent: the only serial part left is the chain over the species
+//     tree's height (ϵ_0 of a branch is the product of its children's last ϵ), a handful of flops per level.
+//     Row i is formed from ϵ_{i−1} exactly as the reference does (ϕ_i, ψ_i, ϵ_i from 1 − βϵ_{i−1}).
+//   * chain (fallback).  Near the critical case the reference's own arithmetic is what has to be mirrored: its
+//     getα switches to the λ = μ formula for |λ−μ| ≤ 1e-6 (an approximation whose composition is NOT the
+//     time-i·Δt map) and loses digits to cancellation in exp(Δt(λ−μ)) − 1 just above it.  Branches with
+//     |Δt(λ−μ)| < 1e-4 therefore run the per-slice recurrence, in projective form ϵ = u/v (division-free:
+//     u_i = (1−α−β)u_{i−1} + αv_{i−1},  v_i = v_{i−1} − βu_{i−1},  1 − βϵ_{i−1} = v_i/v_{i−1}).
+// Launch: G table CTAs + one CTA per leaf node (tree-shape rows, below).  Every table CTA runs the cheap
+// per-level chain redundantly (identical values) and takes a 1/G share of the rows; no inter-CTA dependency.
 #pragma once
 #include "whale_common.cuh"
 
+#ifdef WHALE_EMU
+#define SHFL_IDX(v, src) emu::shfl_idx(v, src)
+#else
+#define SHFL_IDX(v, src) __shfl_sync(0xffffffffu, v, src)
+#endif
+
+constexpr unsigned TAB_FORCE_CHAIN = 1u;  // flags: run the per-slice recurrence on every branch (tests, A/B)
+
 // species-tree metadata staged in shared memory: after an L2 flush every dependent global load of these tiny
-// arrays costs a DRAM round trip per level (measured: 60 µs of k_tables were mostly that)
+// arrays costs a DRAM round trip per level
 struct TabMeta {
     const int *kind, *nsl, *ch0, *ch1, *ls, *ms, *qs, *K, *toff, *lvl_off, *lvl_nodes;
+    int* mode;  // 1: closed form, 0: chain
     const double *dt, *leafP, *pleaf, *x;
     const int16_t* cmap;
     const uint8_t* role;
 };
 
-__device__ __forceinline__ D1 child_eps_last(const TabMeta& T, const PlanDev& PL, int e, int j, int child, int k) {
-    const int Kc = T.K[child];
-    const double2* row = PL.uv + T.toff[child] + (size_t)T.nsl[child] * Kc;
-    const int kc = k == 0 ? 0 : T.cmap[(e * 2 + j) * PL.Kmax + k];
-    const double2 a = row[0];
-    D1 u = mk(a.x), v = mk(a.y);
-    if (k > 0 && kc >= 0) {
-        const double2 b = row[kc];
-        u.d = b.x;
-        v.d = b.y;
-    }
-    return u / v;
+// getα, β of the linear BDP over time t, non-critical branch (src/bdputil.jl:6-7; β = (λ/μ)α src/model.jl:186)
+__device__ __forceinline__ void bdp_ab_t(D1 lam, D1 mu, double t, D1& a, D1& b) {
+    const D1 ex = dexp(mk(t) * (lam - mu));
+    a = mu * (ex - 1.0) / (lam * ex - mu);
+    b = (lam / mu) * a;
+}
+// one (α, β) map applied to ϵ
+__device__ __forceinline__ D1 eps_map(D1 a, D1 b, D1 e0) { return (a + ((1.0 - a) - b) * e0) / (1.0 - b * e0); }
+
+__device__ __forceinline__ void rates_of(const TabMeta& T, const ModelDev& M, int e, unsigned role, D1& lam, D1& mu) {
+    const double NaN = __longlong_as_double(0x7ff8000000000000LL);
+    const int ls = T.ls[e], ms = T.ms[e];
+    const double lv = ls < 0 ? NaN : (M.log_scale ? exp(T.x[ls]) : T.x[ls]);
+    const double mv = ms < 0 ? NaN : (M.log_scale ? exp(T.x[ms]) : T.x[ms]);
+    lam = mk(lv, (role & 1u) ? (M.log_scale ? lv : 1.0) : 0.0);
+    mu = mk(mv, (role & 2u) ? (M.log_scale ? mv : 1.0) : 0.0);
 }
 
-__global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const double* __restrict__ x,
-                                                 const double* __restrict__ pleaf) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    const double NaN = __longlong_as_double(0x7ff8000000000000LL);
+__device__ void leafshapes_block(const ModelDev& M, const PlanDev& PL, const double* __restrict__ x,
+                                 const double* __restrict__ pleaf, int li, unsigned char* tsm);
+
+__global__ void __launch_bounds__(TABLES_NT) k_tables(ModelDev M, PlanDev PL, const double* __restrict__ x,
+                                                      const double* __restrict__ pleaf, int G, unsigned flags) {
     EXTERN_SHARED(tsm);
+    if ((int)blockIdx.x >= G) {  // tree-shape rows of one leaf branch
+        leafshapes_block(M, PL, x, pleaf, (int)blockIdx.x - G, tsm);
+        return;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const bool writer = blockIdx.x == 0;  // the per-branch outputs are identical in every table CTA: one writes
     const long long tk0 = CLOCK64();
     const int nn = M.nn, Kmax = PL.Kmax, P = M.n_params;
-    double* sd = reinterpret_cast<double*>(tsm);                 // dt, leafP, pleaf [nn each], x [P]
-    int* si = reinterpret_cast<int*>(sd + 3 * nn + P + 2 * nn * Kmax);  // 9 arrays [nn], lvl_off [nlvl+1], lvl_nodes [nn]
-    int16_t* s_cm = reinterpret_cast<int16_t*>(si + 10 * nn + M.nlvl + 1);
+    double* sd = reinterpret_cast<double*>(tsm);  // dt, leafP, pleaf [nn each], x [P], (α,β) [nn*Kmax*2], ϵ_0, ϵ_n [nn*Kmax each]
+    double* s_ab = sd + 3 * nn + P;
+    double* s_e0 = s_ab + 2 * nn * Kmax;
+    double* s_en = s_e0 + nn * Kmax;
+    int* si = reinterpret_cast<int*>(s_en + nn * Kmax);  // 10 arrays [nn], lvl_off [nlvl+1], lvl_nodes [nn]
+    int16_t* s_cm = reinterpret_cast<int16_t*>(si + 11 * nn + M.nlvl + 1);
     uint8_t* s_ro = reinterpret_cast<uint8_t*>(s_cm + nn * 2 * Kmax);
-    double* s_ab = sd + 3 * nn + P;  // placed behind x below: [nn*Kmax*2] (α, β) components per node
     for (int i = threadIdx.x; i < nn; i += blockDim.x) {
         sd[i] = M.dt[i]; sd[nn + i] = M.leafP[i]; sd[2 * nn + i] = pleaf ? pleaf[i] : 0.0;
         si[i] = M.kind[i]; si[nn + i] = M.nsl[i]; si[2 * nn + i] = M.child0[i]; si[3 * nn + i] = M.child1[i];
         si[4 * nn + i] = M.lam_slot[i]; si[5 * nn + i] = M.mu_slot[i]; si[6 * nn + i] = M.q_slot[i];
-        si[7 * nn + i] = PL.K[i]; si[8 * nn + i] = PL.toff[i]; si[9 * nn + M.nlvl + 1 + i] = M.lvl_nodes[i];
+        si[7 * nn + i] = PL.K[i]; si[8 * nn + i] = PL.toff[i]; si[10 * nn + M.nlvl + 1 + i] = M.lvl_nodes[i];
     }
-    for (int i = threadIdx.x; i <= M.nlvl; i += blockDim.x) si[9 * nn + i] = M.lvl_off[i];
+    for (int i = threadIdx.x; i <= M.nlvl; i += blockDim.x) si[10 * nn + i] = M.lvl_off[i];
     for (int i = threadIdx.x; i < P; i += blockDim.x) sd[3 * nn + i] = x[i];
     for (int i = threadIdx.x; i < nn * 2 * Kmax; i += blockDim.x) s_cm[i] = PL.cmap[i];
     for (int i = threadIdx.x; i < nn * Kmax; i += blockDim.x) s_ro[i] = PL.role[i];
     __syncthreads();
     TabMeta T{si, si + nn, si + 2 * nn, si + 3 * nn, si + 4 * nn, si + 5 * nn, si + 6 * nn, si + 7 * nn, si + 8 * nn,
-              si + 9 * nn, si + 9 * nn + M.nlvl + 1, sd, sd + nn, sd + 2 * nn, sd + 3 * nn, s_cm, s_ro};
-    // ---- phase A0: (α, β) of every branch — they depend on the branch's own rates only, so all nodes go in
-    //      parallel (one warp per node) instead of paying exp + divisions on every level of the chain below ----
+              si + 10 * nn, si + 10 * nn + M.nlvl + 1, si + 9 * nn, sd, sd + nn, sd + 2 * nn, sd + 3 * nn, s_cm, s_ro};
+    // ---- phase A0: per-slice (α, β) of every branch and its mode — they depend on the branch's own rates only,
+    //      so all nodes go in parallel (one warp per node) ----
     for (int e = warp; e < nn; e += nwarp) {
         const int K = T.K[e];
         for (int k = lane; k < K; k += 32) {
             const unsigned role = k == 0 ? 0u : T.role[e * PL.Kmax + k];
-            const int ls = T.ls[e], ms = T.ms[e];
-            const double lv = ls < 0 ? NaN : (M.log_scale ? exp(T.x[ls]) : T.x[ls]);
-            const double mv = ms < 0 ? NaN : (M.log_scale ? exp(T.x[ms]) : T.x[ms]);
-            const D1 lam = mk(lv, (role & 1u) ? (M.log_scale ? lv : 1.0) : 0.0);
-            const D1 mu = mk(mv, (role & 2u) ? (M.log_scale ? mv : 1.0) : 0.0);
+            D1 lam, mu;
+            rates_of(T, M, e, role, lam, mu);
             D1 a = mk(0.0), b = mk(0.0);
+            int closed = 0;
             if (T.nsl[e] > 0) {
                 // getα src/bdputil.jl:6-7 (critical branch decided on VALUES, like isapprox on Duals)
                 const double t = T.dt[e];
@@ -79,40 +105,52 @@ __global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const d
                 } else {
                     const D1 ex = dexp(mk(t) * (lam - mu));
                     a = mu * (ex - 1.0) / (lam * ex - mu);
+                    closed = (fabs(t * (lam.v - mu.v)) >= 1e-4 && !(flags & TAB_FORCE_CHAIN)) ? 1 : 0;
                 }
                 b = (lam / mu) * a;
             }
             s_ab[(e * Kmax + k) * 2 + 0] = k == 0 ? a.v : a.d;
             s_ab[(e * Kmax + k) * 2 + 1] = k == 0 ? b.v : b.d;
-            PL.ab[(e * PL.Kmax + k) * 2 + 0] = k == 0 ? a.v : a.d;
-            PL.ab[(e * PL.Kmax + k) * 2 + 1] = k == 0 ? b.v : b.d;
+            if (k == 0) T.mode[e] = closed;
+            if (writer) {
+                PL.ab[(e * PL.Kmax + k) * 2 + 0] = k == 0 ? a.v : a.d;
+                PL.ab[(e * PL.Kmax + k) * 2 + 1] = k == 0 ? b.v : b.d;
+            }
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) PL.tim[0] = CLOCK64() - tk0;
-    // ---- phase A: per level, one warp per node, lanes over components; division-free chain ----
+    if (writer && threadIdx.x == 0) PL.tim[0] = CLOCK64() - tk0;
+    // ---- phase A: the chain over the tree's height.  Per level, one warp per node, lanes over components:
+    //      ϵ_0 from the children's last ϵ (shared memory), then the branch's last ϵ ----
     for (int L = 0; L < M.nlvl; L++) {
         const int n0 = T.lvl_off[L], n1 = T.lvl_off[L + 1];
         for (int j = n0 + warp; j < n1; j += nwarp) {
             const int e = T.lvl_nodes[j];
             const int K = T.K[e], kind = T.kind[e], n = T.nsl[e];
+            const int closed = T.mode[e];
             for (int k = lane; k < K; k += 32) {
                 const unsigned role = k == 0 ? 0u : T.role[e * PL.Kmax + k];
+                auto child_last = [&](int jc, int child) -> D1 {  // the child's last ϵ, this lane's component
+                    const int kc = k == 0 ? 0 : T.cmap[(e * 2 + jc) * Kmax + k];
+                    return mk(s_en[child * Kmax], (k > 0 && kc >= 0) ? s_en[child * Kmax + kc] : 0.0);
+                };
                 D1 ep;
                 if (kind == WHALE_LEAF) {  // setnode! src/model.jl:170
                     ep = mk(T.pleaf[e]);
                 } else if (kind == WHALE_WGD) {  // setwgdnode! src/model.jl:175-180
                     const D1 q = mk(T.x[T.qs[e]], (role & 4u) ? 1.0 : 0.0);
-                    const D1 ec = child_eps_last(T, PL, e, 0, T.ch0[e], k);
+                    const D1 ec = child_last(0, T.ch0[e]);
                     ep = q * (ec * ec) + (1.0 - q) * ec;
                     const D1 w = (1.0 - q) + 2.0 * (q * ec);  // Πwgdloss coefficient src/core.jl:198
-                    PL.cx[e * PL.Kmax + k] = k == 0 ? w.v : w.d;
-                    PL.cy[e * PL.Kmax + k] = k == 0 ? q.v : q.d;
+                    if (writer) {
+                        PL.cx[e * PL.Kmax + k] = k == 0 ? w.v : w.d;
+                        PL.cy[e * PL.Kmax + k] = k == 0 ? q.v : q.d;
+                    }
                 } else {  // internal / root: product of the children's last ϵ
-                    const D1 ef = child_eps_last(T, PL, e, 0, T.ch0[e], k);
-                    const D1 eg = child_eps_last(T, PL, e, 1, T.ch1[e], k);
+                    const D1 ef = child_last(0, T.ch0[e]);
+                    const D1 eg = child_last(1, T.ch1[e]);
                     ep = ef * eg;
-                    if (kind == WHALE_ROOT) {  // whaleroot! src/core.jl:131-147 ; condition src/condition.jl
+                    if (kind == WHALE_ROOT && writer) {  // whaleroot! src/core.jl:131-147 ; condition src/condition.jl
                         const D1 eta = mk(T.x[M.eta_slot], (role & 8u) ? 1.0 : 0.0);
                         const D1 xi = 1.0 - (1.0 - eta) * ep;
                         const D1 A = (1.0 - eta) * xi / eta;
@@ -132,12 +170,23 @@ __global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const d
                         PL.cond[2 * PL.Kmax + k] = k == 0 ? cn.v : cn.d;
                     }
                 }
-                double2* uvrow = PL.uv + T.toff[e];
-                D1 u = ep, v = mk(1.0);
-                uvrow[k] = k == 0 ? make_double2(u.v, v.v) : make_double2(u.d, v.d);
-                const D1 a = mk(s_ab[(e * Kmax) * 2], k == 0 ? 0.0 : s_ab[(e * Kmax + k) * 2]);
-                const D1 b = mk(s_ab[(e * Kmax) * 2 + 1], k == 0 ? 0.0 : s_ab[(e * Kmax + k) * 2 + 1]);
-                if (n > 0) {
+                s_e0[e * Kmax + k] = k == 0 ? ep.v : ep.d;
+                D1 en = ep, lf = mk(0.0);
+                if (n > 0 && closed) {
+                    D1 lam, mu, an, bn;
+                    rates_of(T, M, e, role, lam, mu);
+                    bdp_ab_t(lam, mu, T.dt[e] * (double)n, an, bn);
+                    const D1 r = mk(1.0) / (1.0 - bn * ep);
+                    en = (an + ((1.0 - an) - bn) * ep) * r;
+                    // leaf clade on a leaf branch: ℓ_n = leafℙ·Π_i ϕ_i (src/core.jl:94,123) = leafℙ·ϕ over the whole
+                    // branch: Π_i ϕ_i = (1−α_n)(1−β_n)/(1−β_n ϵ_0)²  (det M^n = ((1−α)(1−β))^n)
+                    if (kind == WHALE_LEAF) lf = mk(T.leafP[e]) * (((1.0 - an) * (1.0 - bn)) * (r * r));
+                } else if (n > 0) {
+                    double2* uvrow = PL.uv + T.toff[e];  // every table CTA writes the same values and reads its own
+                    D1 u = ep, v = mk(1.0);
+                    uvrow[k] = k == 0 ? make_double2(u.v, v.v) : make_double2(u.d, v.d);
+                    const D1 a = mk(s_ab[(e * Kmax) * 2], k == 0 ? 0.0 : s_ab[(e * Kmax + k) * 2]);
+                    const D1 b = mk(s_ab[(e * Kmax) * 2 + 1], k == 0 ? 0.0 : s_ab[(e * Kmax + k) * 2 + 1]);
                     const D1 c = (1.0 - a) - b;
                     for (int i = 1; i <= n; i++) {
                         const D1 un = c * u + a * v;
@@ -146,22 +195,25 @@ __global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const d
                         v = vn;
                         uvrow[(size_t)i * K + k] = k == 0 ? make_double2(u.v, v.v) : make_double2(u.d, v.d);
                     }
+                    en = u / v;
+                    if (kind == WHALE_LEAF) {  // ℓ_n = leafℙ·gⁿ·(v_0/v_n)²
+                        const D1 g = (1.0 - a) * (1.0 - b);
+                        const D1 r = mk(1.0) / v;
+                        lf = mk(T.leafP[e]) * dpowi(g, n) * (r * r);
+                    }
+                } else if (kind == WHALE_LEAF) {
+                    lf = mk(T.leafP[e]);
                 }
-                if (kind == WHALE_LEAF) {
-                    // leaf clade on a leaf branch: ℓ_n = leafℙ·Π_i ϕ_i = leafℙ·gⁿ·(v_0/v_n)²  (src/core.jl:94,123)
-                    const D1 g = (1.0 - a) * (1.0 - b);
-                    const D1 r = mk(1.0) / v;
-                    const D1 lf = mk(T.leafP[e]) * dpowi(g, n) * (r * r);
-                    PL.leaf[e * PL.Kmax + k] = k == 0 ? lf.v : lf.d;
-                }
+                s_en[e * Kmax + k] = k == 0 ? en.v : en.d;
+                if (kind == WHALE_LEAF && writer) PL.leaf[e * PL.Kmax + k] = k == 0 ? lf.v : lf.d;
             }
         }
         __syncthreads();
-        if (threadIdx.x == 0 && L < 28) PL.tim[1 + L] = CLOCK64() - tk0;
+        if (writer && threadIdx.x == 0 && L < 28) PL.tim[1 + L] = CLOCK64() - tk0;
     }
-    // ---- phase B: every (node, row, component) of the tables in parallel (one flat index space) ----
+    // ---- phase B: every (node, row, component) of the tables in parallel (one flat index space, 1/G per CTA) ----
     const int total = T.toff[nn - 1] + (T.nsl[nn - 1] + 1) * T.K[nn - 1];  // toff is ascending in node index
-    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += G * blockDim.x) {
         int lo = 0, hi = nn - 1;  // node e with toff[e] <= t < toff[e+1]
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
@@ -170,66 +222,78 @@ __global__ void __launch_bounds__(1024) k_tables(ModelDev M, PlanDev PL, const d
         const int e = lo, K = T.K[e];
         const int idx = t - T.toff[e];
         const int i = idx / K, k = idx - i * K;
-        const double2* uvrow = PL.uv + T.toff[e];
-        const double2 w0 = uvrow[(size_t)i * K], wk = uvrow[(size_t)i * K + k];
-        const D1 u = mk(w0.x, k == 0 ? 0.0 : wk.x), v = mk(w0.y, k == 0 ? 0.0 : wk.y);
-        const D1 ep = u / v;
-        PL.eps[t] = k == 0 ? ep.v : ep.d;
         if (i == 0) {
+            PL.eps[t] = s_e0[e * Kmax + k];
             PL.pp[t] = make_double2(k == 0 ? 1.0 : 0.0, k == 0 ? 1.0 : 0.0);  // ϕ_1 = 1 (src/model.jl:171)
             continue;
         }
-        const double2 p0 = uvrow[(size_t)(i - 1) * K], pk = uvrow[(size_t)(i - 1) * K + k];
-        const D1 vp = mk(p0.y, k == 0 ? 0.0 : pk.y);
         const D1 a = mk(s_ab[(e * Kmax) * 2], k == 0 ? 0.0 : s_ab[(e * Kmax + k) * 2]);
         const D1 b = mk(s_ab[(e * Kmax) * 2 + 1], k == 0 ? 0.0 : s_ab[(e * Kmax + k) * 2 + 1]);
         const D1 g = (1.0 - a) * (1.0 - b);
-        const D1 r = vp / v;  // 1 / (1 − βϵ_{i−1})
+        D1 ep, r;  // ϵ_i and 1 / (1 − βϵ_{i−1})
+        if (T.mode[e]) {
+            D1 prev = mk(s_e0[e * Kmax], k == 0 ? 0.0 : s_e0[e * Kmax + k]);
+            if (i > 1) {
+                const unsigned role = k == 0 ? 0u : T.role[e * PL.Kmax + k];
+                D1 lam, mu, ai, bi;
+                rates_of(T, M, e, role, lam, mu);
+                bdp_ab_t(lam, mu, T.dt[e] * (double)(i - 1), ai, bi);
+                prev = eps_map(ai, bi, prev);
+            }
+            r = mk(1.0) / (1.0 - b * prev);
+            ep = (a + ((1.0 - a) - b) * prev) * r;
+        } else {
+            const double2* uvrow = PL.uv + T.toff[e];
+            const double2 w0 = uvrow[(size_t)i * K], wk = uvrow[(size_t)i * K + k];
+            const D1 u = mk(w0.x, k == 0 ? 0.0 : wk.x), v = mk(w0.y, k == 0 ? 0.0 : wk.y);
+            const double2 p0 = uvrow[(size_t)(i - 1) * K], pk = uvrow[(size_t)(i - 1) * K + k];
+            const D1 vp = mk(p0.y, k == 0 ? 0.0 : pk.y);
+            ep = u / v;
+            r = vp / v;
+        }
+        PL.eps[t] = k == 0 ? ep.v : ep.d;
         const D1 phi = g * (r * r);
         const D1 psi = (g * b) * (r * r * r);
         PL.pp[t] = make_double2(k == 0 ? phi.v : phi.d, k == 0 ? psi.v : psi.d);
     }
     __syncthreads();
-    if (threadIdx.x == 0) { PL.tim[30] = CLOCK64() - tk0; PL.tim[31] = M.nlvl; }
+    if (writer && threadIdx.x == 0) { PL.tim[30] = CLOCK64() - tk0; PL.tim[31] = M.nlvl; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// k_leafshapes — last-row values wσ_n of the tree shapes on every leaf branch (see SHAPES in whale_common.cuh).
-// One warp per leaf node, lanes = (shape σ, component k).  Runs concurrently with k_tables on a side stream:
-// it recomputes its own branch's slice rows (a leaf branch depends on nothing below it).
+// Tree-shape rows — last-row values wσ_n of the tree shapes on a leaf branch (see SHAPES in whale_common.cuh).
+// One CTA per leaf node beside the table CTAs of k_tables; a leaf branch depends on nothing below it, so the
+// block recomputes its own branch's slice rows in shared memory: warp 0 runs the projective chain (lanes of
+// shape 0), all threads turn it into (ϕ_i, ψ_i) rows, warp 0 runs the shape sequences in lock-step with
+// lanes = (shape σ, component k).
 // ---------------------------------------------------------------------------------------------------------
-#ifdef WHALE_EMU
-#define SHFL_IDX(v, src) emu::shfl_idx(v, src)
-#else
-#define SHFL_IDX(v, src) __shfl_sync(0xffffffffu, v, src)
-#endif
-
-__global__ void __launch_bounds__(32) k_leafshapes(ModelDev M, PlanDev PL, const double* __restrict__ x,
-                                                   const double* __restrict__ pleaf) {
-    const int e = M.leafnodes[blockIdx.x];
-    const int lane = threadIdx.x;
+__device__ void leafshapes_block(const ModelDev& M, const PlanDev& PL, const double* __restrict__ x,
+                                 const double* __restrict__ pleaf, int li, unsigned char* tsm) {
+    const int e = M.leafnodes[li];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool w0 = tid < 32;
     const int K = PL.K[e], n = M.nsl[e];
     const int sh = lane / K, k = lane - sh * K;
     const bool on = sh < NSHAPE;  // 8·K <= 32 lanes (leaf branches have K <= 3)
-    const double NaN = __longlong_as_double(0x7ff8000000000000LL);
-    const unsigned role = (k == 0 || !on) ? 0u : PL.role[e * PL.Kmax + k];
-    const int ls = M.lam_slot[e], ms = M.mu_slot[e];
-    const double lv = ls < 0 ? NaN : (M.log_scale ? exp(x[ls]) : x[ls]);
-    const double mv = ms < 0 ? NaN : (M.log_scale ? exp(x[ms]) : x[ms]);
-    const D1 lam = mk(lv, (role & 1u) ? (M.log_scale ? lv : 1.0) : 0.0);
-    const D1 mu = mk(mv, (role & 2u) ? (M.log_scale ? mv : 1.0) : 0.0);
-    D1 a = mk(0.0), b = mk(0.0);
-    if (n > 0) {
-        const double t = M.dt[e];
-        if (fabs(lam.v - mu.v) <= 1e-6) a = (lam * mk(t)) / (1.0 + lam * mk(t));
-        else { const D1 ex = dexp(mk(t) * (lam - mu)); a = mu * (ex - 1.0) / (lam * ex - mu); }
-        b = (lam / mu) * a;
-    }
-    double2* uv = PL.ls_uv + PL.toff[e];
-    double2* pp = PL.ls_pp + PL.toff[e];
+    double2* uv = reinterpret_cast<double2*>(tsm);  // [(n+1)*K] projective ϵ rows
+    double2* pp = uv + (size_t)(n + 1) * K;         // [(n+1)*K] (ϕ, ψ) rows
     __shared__ double s_ab[8][4];  // (α, β) value / tangent per component, from the lanes of shape 0
-    // pass 1: the projective chain (lanes of shape 0 only), rows to scratch
-    if (sh == 0) {
+    if (w0 && sh == 0) {
+        const double NaN = __longlong_as_double(0x7ff8000000000000LL);
+        const unsigned role = k == 0 ? 0u : PL.role[e * PL.Kmax + k];
+        const int ls = M.lam_slot[e], ms = M.mu_slot[e];
+        const double lv = ls < 0 ? NaN : (M.log_scale ? exp(x[ls]) : x[ls]);
+        const double mv = ms < 0 ? NaN : (M.log_scale ? exp(x[ms]) : x[ms]);
+        const D1 lam = mk(lv, (role & 1u) ? (M.log_scale ? lv : 1.0) : 0.0);
+        const D1 mu = mk(mv, (role & 2u) ? (M.log_scale ? mv : 1.0) : 0.0);
+        D1 a = mk(0.0), b = mk(0.0);
+        if (n > 0) {
+            const double t = M.dt[e];
+            if (fabs(lam.v - mu.v) <= 1e-6) a = (lam * mk(t)) / (1.0 + lam * mk(t));
+            else { const D1 ex = dexp(mk(t) * (lam - mu)); a = mu * (ex - 1.0) / (lam * ex - mu); }
+            b = (lam / mu) * a;
+        }
+        // pass 1: the projective chain, rows to shared memory
         s_ab[k][0] = a.v; s_ab[k][1] = a.d; s_ab[k][2] = b.v; s_ab[k][3] = b.d;
         D1 u = mk(pleaf ? pleaf[e] : 0.0), v = mk(1.0);
         const D1 c = (1.0 - a) - b;
@@ -240,20 +304,21 @@ __global__ void __launch_bounds__(32) k_leafshapes(ModelDev M, PlanDev PL, const
             uv[(size_t)i * K + k] = k == 0 ? make_double2(u.v, v.v) : make_double2(u.d, v.d);
         }
     }
-    __syncwarp();
-    // pass 2: ϕ_i, ψ_i of every row in parallel
-    for (int idx = lane; idx < n * K; idx += 32) {
+    __syncthreads();
+    // pass 2: ϕ_i, ψ_i of every row in parallel (all threads)
+    for (int idx = tid; idx < n * K; idx += blockDim.x) {
         const int i = 1 + idx / K, kk = idx - (i - 1) * K;
         const D1 aa = mk(s_ab[0][0], kk == 0 ? 0.0 : s_ab[kk][1]), bb = mk(s_ab[0][2], kk == 0 ? 0.0 : s_ab[kk][3]);
         const D1 gg = (1.0 - aa) * (1.0 - bb);
-        const double2 w0 = uv[(size_t)i * K], wk = uv[(size_t)i * K + kk];
+        const double2 w0_ = uv[(size_t)i * K], wk = uv[(size_t)i * K + kk];
         const double2 p0 = uv[(size_t)(i - 1) * K], pk = uv[(size_t)(i - 1) * K + kk];
-        const D1 v = mk(w0.y, kk == 0 ? 0.0 : wk.y), vp = mk(p0.y, kk == 0 ? 0.0 : pk.y);
+        const D1 v = mk(w0_.y, kk == 0 ? 0.0 : wk.y), vp = mk(p0.y, kk == 0 ? 0.0 : pk.y);
         const D1 r = vp / v;
         const D1 phi = gg * (r * r), psi = (gg * bb) * (r * r * r);
         pp[(size_t)i * K + kk] = make_double2(kk == 0 ? phi.v : phi.d, kk == 0 ? psi.v : psi.d);
     }
-    __syncwarp();
+    __syncthreads();
+    if (!w0) return;
     // pass 3: the shape sequences, all shapes in lock-step (operands of shape σ come from the lanes of a, b)
     const int SA[NSHAPE] = SHAPE_A, SB[NSHAPE] = SHAPE_B;
     const int la_ = on ? SA[sh] * K + k : lane, lb_ = on ? SB[sh] * K + k : lane;

@@ -120,7 +120,11 @@ static int dp_minb() {  // resident CTAs per SM the register cap is chosen for
     }();
     return mb;
 }
+#ifdef WHALE_DEV_BUILD  // quick experiment builds: the default variant only
+#define DP_VARIANTS(X) X(128, 4)
+#else
 #define DP_VARIANTS(X) X(96, 5) X(96, 6) X(64, 6) X(64, 8) X(64, 10) X(64, 12) X(128, 3) X(128, 4) X(128, 5) X(128, 6) X(128, 7) X(256, 2) X(256, 3)
+#endif
 constexpr int MAX_BINS = 8;
 struct Bin {
     int off, count;
@@ -174,6 +178,7 @@ struct whale_data {
     int* d_perm[MAXPLAN] = {};
     double* d_out_fam = nullptr;  // [F*Kmax(plan1)]
     double* d_partial = nullptr;
+    unsigned int* d_done = nullptr;  // k_dp's finished-CTA counter (fused reduction)
     double* d_ell = nullptr;
     long long* d_tim = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -408,15 +413,37 @@ static size_t smem_need(const whale_model* m, const FamHdr& h, int plan, int Kma
            h.stage_bytes[plan] + NW * ((size_t)h.leafmax[plan] * sizeof(double) + h.leaf_stage);
 }
 
-#ifdef WHALE_EMU
-constexpr int TABLES_NT = 128;  // host-thread emulation: keep the thread count small
-#else
-constexpr int TABLES_NT = 1024;
-#endif
-static size_t tables_smem(const whale_model* m, const Plan& pl) {  // mirrors the carve-up in k_tables
+static size_t tables_smem(const whale_model* m, const Plan& pl, bool shapes) {  // mirrors the carve-ups in k_tables
     const size_t nn = m->nn, nlvl = m->lvl_off.size() - 1;
-    return (3 * nn + m->P + 2 * nn * pl.Kmax) * sizeof(double) + (10 * nn + nlvl + 1) * sizeof(int) + nn * 2 * pl.Kmax * sizeof(int16_t) +
-           nn * pl.Kmax + 16;
+    size_t need = (3 * nn + m->P + 4 * nn * pl.Kmax) * sizeof(double) + (11 * nn + nlvl + 1) * sizeof(int) +
+                  nn * 2 * pl.Kmax * sizeof(int16_t) + nn * pl.Kmax + 16;
+    if (shapes)  // a leaf-shape CTA keeps its branch's projective and (ϕ, ψ) rows in shared memory
+        for (int e : m->leafnodes) need = std::max(need, 2 * (size_t)(m->nsl[e] + 1) * pl.K[e] * sizeof(double2));
+    return need;
+}
+
+// K1 launch: G table CTAs (each takes 1/G of the rows) + one CTA per leaf node for the tree-shape rows
+static bool fused_reduce() {
+    static bool f = env_int("WHALE_FUSED_REDUCE", 1) != 0;
+    return f;
+}
+static unsigned tables_flags() {
+    static unsigned f = env_int("WHALE_TABLES_CHAIN", 0) ? TAB_FORCE_CHAIN : 0u;
+    return f;
+}
+static cudaError_t launch_tables(whale_model* m, Plan& pl, const double* d_x, const double* d_pleaf, cudaStream_t st,
+                                 bool shapes) {
+    shapes = shapes && !m->leafnodes.empty();
+    const int G = (int)std::max<size_t>(1, std::min<size_t>(32, (pl.tab_len + TABLES_NT - 1) / TABLES_NT));
+    const size_t smem = tables_smem(m, pl, shapes);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    LAUNCH(k_tables, G + (shapes ? (int)m->leafnodes.size() : 0), TABLES_NT, smem, st, m->dev, pl.dev, d_x, d_pleaf, G,
+           tables_flags());
+    g_launches++;
+    return cudaSuccess;
 }
 
 // shared-memory budget of every family under tangent plan `pl` (stored at index g); returns the largest need
@@ -826,6 +853,8 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
     CU(upload(D->hdr, &D->d_hdr));
     CU(cudaMalloc((void**)&D->d_out_fam, D->out_total * sizeof(double)));
     CU(cudaMalloc((void**)&D->d_partial, (size_t)1024 * m->plan[1].Kmax * sizeof(double)));
+    CU(cudaMalloc((void**)&D->d_done, 16));
+    CU(cudaMemset(D->d_done, 0, 16));
     for (int i = 0; i < MAX_BINS; i++) {
         CU(cudaStreamCreateWithFlags(&D->side[i], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&D->ev_join[i], cudaEventDisableTiming));
@@ -891,7 +920,7 @@ int32_t whale_data_destroy(whale_data_t d) {
     cudaFree(d->d_arena); cudaFree(d->d_hdr);
     for (int g = 0; g < MAXPLAN; g++) { cudaFree(d->d_perm[g]); cudaFree(d->d_roff[g]); }
     for (Plan& cp : d->chunk_plans) for (void* q : cp.owned) cudaFree(q);
-    cudaFree(d->d_out_fam); cudaFree(d->d_partial);
+    cudaFree(d->d_out_fam); cudaFree(d->d_partial); cudaFree(d->d_done);
     for (int i = 0; i < MAX_BINS; i++) {
         if (d->side[i]) cudaStreamDestroy(d->side[i]);
         if (d->ev_join[i]) cudaEventDestroy(d->ev_join[i]);
@@ -971,30 +1000,24 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
         Plan& pl = *D->plans[g];
         const bool first = g == g0;
         if (prof && first) CU(cudaEventRecord(D->ev[0], st));
-        // K1: slice tables of this plan; the leaf-branch shape tables run beside it on a side stream
-        if (!keep && !m->leafnodes.empty()) {
-            CU(cudaEventRecord(D->ev_fork, st));
-            CU(cudaStreamWaitEvent(D->side_tab, D->ev_fork, 0));
-            LAUNCH(k_leafshapes, (int)m->leafnodes.size(), 32, 0, D->side_tab, m->dev, pl.dev, d_x, m->d_pleaf);
-            CU(cudaEventRecord(D->ev_tab, D->side_tab));
-            g_launches++;
-        }
-        LAUNCH(k_tables, 1, TABLES_NT, tables_smem(m, pl), st, m->dev, pl.dev, d_x, m->d_pleaf);
-        g_launches++;
+        // K1: slice tables of this plan (+ the leaf-branch shape tables, extra CTAs of the same launch)
+        CU(launch_tables(m, pl, d_x, m->d_pleaf, st, !keep));
         if (condition == WHALE_COND_NOWHERE) {
             int32_t rcn = ensure_nowhere(m, pl);
             if (rcn != WHALE_OK) return rcn;
             LAUNCH(k_nowhere, 1, 256, 0, st, m->dev, pl.dev, d_x);
             g_launches++;
         }
-        if (!keep && !m->leafnodes.empty()) CU(cudaStreamWaitEvent(st, D->ev_tab, 0));
         if (prof && first) CU(cudaEventRecord(D->ev[1], st));
         // K2: one launch per shared-memory bin, concurrently on side streams
         const std::vector<Bin>& bins = D->bins[g];
         double* out_fam = D->d_out_fam + D->out_off[g];
         // the ℓ kept for backtracking is written by the first pass only (values do not depend on the chunk)
         DPArgs a{m->dev, pl.dev, D->d_arena, D->d_hdr, D->d_perm[g], D->d_roff[g], out_fam, (keep && first) ? D->d_ell : nullptr, (int)g,
-                 keep ? 0 : 1, (prof && first) ? D->d_tim : nullptr};
+                 keep ? 0 : 1, (prof && first) ? D->d_tim : nullptr, nullptr, F, condition, first ? 1 : 0, d_out};
+        // K3 rides in the tail of K2 (the last CTA to finish reduces) unless the sum is too long for one CTA
+        const bool fused = fused_reduce() && (size_t)F * pl.K[m->root] <= ((size_t)1 << 20) && pl.K[m->root] <= 1024;
+        if (fused) a.done = D->d_done;
         const int MB = dp_minb();
         auto launch_bin = [&](const Bin& b, cudaStream_t s) {
 #define LAUNCHV(NTV, MBV) if (NT == NTV && MB == MBV) LAUNCH((k_dp<NTV, MBV>), b.count, NTV, b.smem, s, a, b.off);
@@ -1018,9 +1041,11 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
         const int KR = pl.K[m->root];
         int nb = std::min(1024, (F + 255) / 256);
         int chunk = (F + nb - 1) / nb;
-        LAUNCH(k_reduce1, nb, 256, 0, st, out_fam, F, KR, chunk, D->d_partial);
-        LAUNCH(k_reduce2, 1, 256, 0, st, D->d_partial, nb, KR, F, condition, pl.dev, m->root, first ? 1 : 0, d_out);
-        g_launches += 2;
+        if (!fused) {
+            LAUNCH(k_reduce1, nb, 256, 0, st, out_fam, F, KR, chunk, D->d_partial);
+            LAUNCH(k_reduce2, 1, 256, 0, st, D->d_partial, nb, KR, F, condition, pl.dev, m->root, first ? 1 : 0, d_out);
+            g_launches += 2;
+        }
         if (prof && first) CU(cudaEventRecord(D->ev[3], st));
     }
     D->ev_valid = prof;
@@ -1199,8 +1224,7 @@ int32_t whale_slices(whale_model_t m, const double* x, const double* p_leaf, dou
     CU(cudaMemcpy(m->d_x, x, P * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(m->d_pleaf, pl.data(), nn * sizeof(double), cudaMemcpyHostToDevice));
     Plan& p0 = m->plan[0];
-    LAUNCH(k_tables, 1, TABLES_NT, tables_smem(m, p0), m->stream, m->dev, p0.dev, m->d_x, m->d_pleaf);
-    g_launches++;
+    CU(launch_tables(m, p0, m->d_x, m->d_pleaf, m->stream, false));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(m->stream));
     std::vector<double> he(p0.tab_len);
@@ -1252,7 +1276,7 @@ int32_t whale_backtrack(whale_model_t m, whale_data_t d, int32_t n_samples, cons
     CUB(cudaMalloc((void**)&d_t, W * max_nodes * 4)); CUB(cudaMalloc((void**)&d_p, W * max_nodes * 4));
     CUB(cudaMalloc((void**)&d_stack, W * max_nodes * sizeof(int4)));
     Plan& p0 = m->plan[0];
-    LAUNCH(k_tables, 1, TABLES_NT, tables_smem(m, p0), m->stream, m->dev, p0.dev, m->d_x, m->d_pleaf);
+    CUB(launch_tables(m, p0, m->d_x, m->d_pleaf, m->stream, false));
     BTArgs a{m->dev, p0.dev, d->d_arena, d->d_hdr, d->d_ell, m->d_x, d_u, (long long)stride, d->F, n_samples, max_nodes,
              0, n_samples, d_cnt, d_g, d_e, d_t, d_p, d_st, d_stack};
     cudaEvent_t eb0 = nullptr, eb1 = nullptr;
