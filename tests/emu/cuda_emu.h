@@ -95,6 +95,15 @@ inline double shfl_down(double v, int delta) {
     (*g_wbar)[w].wait();
     return r;
 }
+inline bool warp_any(bool p) {
+    const int w = threadIdx.x / 32, l = threadIdx.x % 32;
+    g_shfl[w][l] = p ? 1.0 : 0.0;
+    (*g_wbar)[w].wait();
+    bool r = false;
+    for (int i = 0; i < (*g_wbar)[w].n; i++) r = r || g_shfl[w][i] != 0.0;
+    (*g_wbar)[w].wait();
+    return r;
+}
 inline double shfl_idx(double v, int src) {
     const int w = threadIdx.x / 32, l = threadIdx.x % 32;
     g_shfl[w][l] = v;

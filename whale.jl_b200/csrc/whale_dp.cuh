@@ -74,8 +74,10 @@ __device__ __forceinline__ void stage_wait_prev() { asm volatile("cp.async.wait_
 
 #ifdef WHALE_EMU
 #define SHFL_DOWN(v, d) emu::shfl_down(v, d)
+#define WARP_ANY(p) emu::warp_any(p)
 #else
 #define SHFL_DOWN(v, d) __shfl_down_sync(0xffffffffu, v, d)
+#define WARP_ANY(p) (__any_sync(0xffffffffu, (p)) != 0)
 #endif
 
 // barrier among the first `nw` warps of the CTA (the warps that own lanes of the current row)
@@ -402,15 +404,19 @@ __device__ __forceinline__ void accum(const double* __restrict__ src, int o1, in
     for (int k = 1; k < K; k++) s[k] = fma(px, y[k], fma(py, x[k], s[k]));
 }
 
-// one pass of one slice for this lane; wg = team size of the warp's first lane (warp-uniform, 0: nothing to do)
+// one pass of one slice for this lane; wg = team size of the warp's first lane (warp-uniform, 0: nothing to do).
+// two = some lane of the warp owns a second term, more = some lane owns more than two (both warp-uniform, fixed
+// for the branch): the first two terms run branch-free for every lane (an absent term has p = 0 and reads cell 0),
+// so the 4·K operand loads of a slice are in flight together and the warp never diverges before the reduction.
 template <int K>
-__device__ __forceinline__ void slice_pass(const LaneWork<K>& w, int wg, int sidx, const double* __restrict__ src,
-                                           double* __restrict__ dst, const double2* ppi, const Ent* s_dents, int C,
-                                           int i, double* ellp) {
+__device__ __forceinline__ void slice_pass(const LaneWork<K>& w, int wg, bool two, bool more, int sidx,
+                                           const double* __restrict__ src, double* __restrict__ dst, const double2* ppi,
+                                           const Ent* s_dents, int C, int i, double* ellp) {
     if (wg == 0) return;
     double s[K];
 #pragma unroll
     for (int k = 0; k < K; k++) s[k] = 0.0;
+#ifdef WHALE_SLICE_V1
     if (w.cnt > 0) accum<K>(src, w.a1, w.a2, w.pa, s);
     if (w.cnt > 1) accum<K>(src, w.b1, w.b2, w.pb, s);
     for (int j = 2; j < w.cnt; j++) {
@@ -424,6 +430,50 @@ __device__ __forceinline__ void slice_pass(const LaneWork<K>& w, int wg, int sid
             if (step < w.gsz) s[k] += t;
         }
     }
+#else
+    if (two) {
+        const double* xa = src + w.a1;
+        const double* ya = src + w.a2;
+        const double* xb = src + w.b1;
+        const double* yb = src + w.b2;
+        const double pxa = w.pa * xa[0], pya = w.pa * ya[0], pxb = w.pb * xb[0], pyb = w.pb * yb[0];
+        s[0] = fma(pxb, yb[0], pxa * ya[0]);
+#pragma unroll
+        for (int k = 1; k < K; k++) s[k] = fma(pxa, ya[k], pya * xa[k]) + fma(pxb, yb[k], pyb * xb[k]);
+    } else {
+        accum<K>(src, w.a1, w.a2, w.pa, s);
+    }
+    if (more) {
+        for (int j = 2; j < w.cnt; j++) {
+            const Ent en = s_dents[w.first + j * w.gsz];
+            accum<K>(src, en.i1 * K, en.i2 * K, en.p, s);
+        }
+    }
+    // the leader's operands (ϕ_i, ψ_i with tangents, the cell's previous value) are fetched before the reduction so
+    // their latency hides behind the shuffles; every lane loads (valid addresses), only leaders use them
+    const bool lead = w.cell >= 0 && (sidx & (w.gsz - 1)) == 0;
+    const int cK = max(w.cell, 0) * K;
+    double2 pk[K];
+    double o[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { pk[k] = ppi[k]; o[k] = src[cK + k]; }
+    // team reduction: lane j adds lane j+step while step is inside its own team.  The mask multiplies instead of
+    // selecting (one DFMA per component and step; fma(t, 1, s) is the correctly rounded s + t)
+    for (int step = 1; step < wg; step <<= 1) {
+        const double m = step < w.gsz ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < K; k++) s[k] = fma(SHFL_DOWN(s[k], step), m, s[k]);
+    }
+    if (lead) {  // team leader: ℓ_i = ϕ_i ℓ_{i−1} + ψ_i Σ  (with tangents)
+        const double r0 = fma(pk[0].x, o[0], pk[0].y * s[0]);
+        dst[cK] = r0;
+        if (ellp) ellp[(size_t)i * C + w.cell] = r0;
+#pragma unroll
+        for (int k = 1; k < K; k++)
+            dst[cK + k] = fma(pk[0].x, o[k], fma(pk[0].y, s[k], fma(pk[k].x, o[0], pk[k].y * s[0])));
+    }
+    return;
+#endif
     if (w.cell >= 0 && (sidx & (w.gsz - 1)) == 0) {  // team leader: ℓ_i = ϕ_i ℓ_{i−1} + ψ_i Σ  (with tangents)
         const int c = w.cell;
         const double2 c0 = ppi[0];
@@ -455,6 +505,8 @@ __device__ __noinline__ void run_slices_fused(int n, int C, double* fin, double*
     const int wg0 = wbase < nslots ? (1 << s_slots[wbase].glog) : 0;
     const int wg1 = (wbase + nt) < nslots ? (1 << s_slots[wbase + nt].glog) : 0;
     const int npass = (nslots + nt - 1) / nt;
+    const bool two0 = WARP_ANY(w0.cnt > 1), more0 = WARP_ANY(w0.cnt > 2);
+    const bool two1 = WARP_ANY(w1.cnt > 1), more1 = WARP_ANY(w1.cnt > 2);
     // warp scope: ϕ/ψ rows come from global memory -> keep the current row in registers and fetch the next
     // one while the slice is computed; block scope: rows were staged in shared memory
     double2 pc[K], pn[K];
@@ -475,12 +527,12 @@ __device__ __noinline__ void run_slices_fused(int n, int C, double* fin, double*
             }
             ppi = pc;
         }
-        slice_pass<K>(w0, wg0, tid, src, dst, ppi, s_dents, C, i, ellp);
-        slice_pass<K>(w1, wg1, tid + nt, src, dst, ppi, s_dents, C, i, ellp);
+        slice_pass<K>(w0, wg0, two0, more0, tid, src, dst, ppi, s_dents, C, i, ellp);
+        slice_pass<K>(w1, wg1, two1, more1, tid + nt, src, dst, ppi, s_dents, C, i, ellp);
         for (int q = 2; q < npass; q++) {  // oversized rows: descriptors reloaded from shared memory
             const LaneWork<K> wq = load_work<K>(s_slots, nslots, s_dents, tid + q * nt);
             const int wgq = (wbase + q * nt) < nslots ? (1 << s_slots[wbase + q * nt].glog) : 0;
-            slice_pass<K>(wq, wgq, tid + q * nt, src, dst, ppi, s_dents, C, i, ellp);
+            slice_pass<K>(wq, wgq, WARP_ANY(wq.cnt > 1), WARP_ANY(wq.cnt > 2), tid + q * nt, src, dst, ppi, s_dents, C, i, ellp);
         }
         cur = dst;
         scope_sync<WARP>();
