@@ -449,6 +449,14 @@ __device__ __forceinline__ void slice_pass(const LaneWork<K>& w, int wg, bool tw
             accum<K>(src, en.i1 * K, en.i2 * K, en.p, s);
         }
     }
+    // team reduction: lane j adds lane j+step while step is inside its own team.  The mask multiplies instead of
+    // selecting (one DFMA per component and step; fma(t, 1, s) is the correctly rounded s + t)
+#define TEAM_REDUCE()                                                               \
+    for (int step = 1; step < wg; step <<= 1) {                                     \
+        const double m = step < w.gsz ? 1.0 : 0.0;                                  \
+        _Pragma("unroll") for (int k = 0; k < K; k++) s[k] = fma(SHFL_DOWN(s[k], step), m, s[k]); \
+    }
+#ifndef WHALE_SLICE_NOHOIST
     // the leader's operands (ϕ_i, ψ_i with tangents, the cell's previous value) are fetched before the reduction so
     // their latency hides behind the shuffles; every lane loads (valid addresses), only leaders use them
     const bool lead = w.cell >= 0 && (sidx & (w.gsz - 1)) == 0;
@@ -457,13 +465,7 @@ __device__ __forceinline__ void slice_pass(const LaneWork<K>& w, int wg, bool tw
     double o[K];
 #pragma unroll
     for (int k = 0; k < K; k++) { pk[k] = ppi[k]; o[k] = src[cK + k]; }
-    // team reduction: lane j adds lane j+step while step is inside its own team.  The mask multiplies instead of
-    // selecting (one DFMA per component and step; fma(t, 1, s) is the correctly rounded s + t)
-    for (int step = 1; step < wg; step <<= 1) {
-        const double m = step < w.gsz ? 1.0 : 0.0;
-#pragma unroll
-        for (int k = 0; k < K; k++) s[k] = fma(SHFL_DOWN(s[k], step), m, s[k]);
-    }
+    TEAM_REDUCE()
     if (lead) {  // team leader: ℓ_i = ϕ_i ℓ_{i−1} + ψ_i Σ  (with tangents)
         const double r0 = fma(pk[0].x, o[0], pk[0].y * s[0]);
         dst[cK] = r0;
@@ -473,6 +475,10 @@ __device__ __forceinline__ void slice_pass(const LaneWork<K>& w, int wg, bool tw
             dst[cK + k] = fma(pk[0].x, o[k], fma(pk[0].y, s[k], fma(pk[k].x, o[0], pk[k].y * s[0])));
     }
     return;
+#else
+    TEAM_REDUCE()
+#endif
+#undef TEAM_REDUCE
 #endif
     if (w.cell >= 0 && (sidx & (w.gsz - 1)) == 0) {  // team leader: ℓ_i = ϕ_i ℓ_{i−1} + ψ_i Σ  (with tangents)
         const int c = w.cell;
