@@ -176,3 +176,28 @@ def nowhere_condition_vs_oracle(L):
     finally:
         L.L.whale_data_destroy(dh)
         L.L.whale_model_destroy(mh)
+
+
+def near_critical_vs_oracle(tmp_path, n_fam=3, seed=5):
+    """Slice tables around the critical case λ ≈ μ (src/bdputil.jl:6-7): exactly critical, inside the reference's
+    1e-6 `isapprox` window, just outside it (the reference's own exp(Δt(λ−μ)) − 1 cancellation regime, where k_tables
+    keeps the per-slice recurrence) and far enough for the closed-form rows; log-likelihood and gradient against
+    the oracle at the north-star tolerance."""
+    import whale_jl_b200 as W
+    from whale_jl_b200 import synth
+    from oracle import whale_oracle as wo, flat
+    d = synth.generate(str(tmp_path / "crit"), n_fam, seed=seed)
+    ccd = None
+    for lam, mu in ((0.3, 0.3), (0.3, 0.3 + 5e-7), (0.3, 0.3001), (0.3, 0.301), (0.3, 0.31), (0.25, 0.4)):
+        w = W.WhaleModel(W.ConstantDLWGD(lam=lam, mu=mu, q=[0.2, 0.1], eta=0.67), synth.c1_species_tree(), 0.05)
+        ccd = W.read_ale(d, w) if ccd is None else ccd
+        got, gg = W.logpdf_and_gradient(w, ccd)
+        ow = wo.WhaleModel(wo.ConstantDLWGD(lam=lam, mu=mu, q=[0.2, 0.1], eta=0.67), wo.c1_tree(), 0.05, condition="root")
+        ff = flat.FlatFams(wo.read_ale(d, ow), len(ow))
+        want, wg = flat.logpdf(flat.FlatModel(ow), ff, grad=True)[0], flat.logpdf(flat.FlatModel(ow), ff, grad=True)[2]
+        assert got == pytest.approx(want, rel=1e-9), (lam, mu)
+        # just outside the isapprox window the reference's own gradient is cancellation noise (∂α/∂λ loses
+        # ~|λ−μ|⁻¹·1e-11 relative to one ulp of exp), so two correct implementations agree only loosely there
+        d_ = abs(lam - mu)
+        np.testing.assert_allclose(gg, wg, rtol=1e-5 if 1e-6 < d_ < 1e-3 else 1e-9, atol=1e-9 * np.abs(wg).max(),
+                                   err_msg=f"lam {lam} mu {mu}")

@@ -114,6 +114,18 @@ inline double shfl_idx(double v, int src) {
 }
 }  // namespace emu
 inline void __syncthreads() { emu::g_bar->wait(); }
+namespace emu { inline int g_or_flag[2] = {0, 0}; }
+inline int __syncthreads_or(int p) {  // barrier + OR of the predicate over the CTA (double-buffered flag)
+    static thread_local int phase = 0;
+    const int ph = phase; phase ^= 1;
+    if (p) __atomic_store_n(&emu::g_or_flag[ph], 1, __ATOMIC_SEQ_CST);
+    emu::g_bar->wait();
+    const int r = __atomic_load_n(&emu::g_or_flag[ph], __ATOMIC_SEQ_CST);
+    emu::g_bar->wait();
+    if (threadIdx.x == 0) emu::g_or_flag[ph] = 0;
+    emu::g_bar->wait();
+    return r;
+}
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline void __syncwarp() { (*emu::g_wbar)[threadIdx.x / 32].wait(); }

@@ -139,3 +139,25 @@ def test_emu_native_read_ale_is_bit_identical(L, tmp_path):
                 assert W.logpdf(w, b) == W.logpdf(w, a)
     finally:
         wlib.use(None)
+
+
+def test_emu_near_critical_rates(L, tmp_path):
+    from conftest import near_critical_vs_oracle
+    wlib.use(L)
+    try:
+        near_critical_vs_oracle(tmp_path)
+    finally:
+        wlib.use(None)
+
+
+def test_emu_chain_tables_and_unfused_reduction():
+    """The fallbacks behind WHALE_TABLES_CHAIN=1 (per-slice recurrence on every branch) and WHALE_FUSED_REDUCE=0
+    (K3 as separate kernels) are process-wide switches: exercise them in a child process."""
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from whale_jl_b200 import lib as wlib\nfrom conftest import run_parity\n"
+            "run_parity(wlib.Lib(%r), 'c1_example1', sel=[0, 3], conds=['root'])\nprint('ok')\n"
+            % (ROOT, os.path.join(ROOT, "tests"), EMU))
+    env = dict(os.environ, WHALE_TABLES_CHAIN="1", WHALE_FUSED_REDUCE="0")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]

@@ -276,3 +276,10 @@ def test_mixture_modelarray_and_track(L, tmp_path):
     trees = W.track(comps[0], ccd, post, 4, seed=3)
     assert len(trees) == 6 and all(len(t) == 4 for t in trees)
     assert all(t[0][0, 3] == -1 for t in trees)
+
+
+def test_near_critical_rates(L, tmp_path):
+    """λ ≈ μ: the reference's isapprox window, its cancellation regime just outside it (k_tables keeps the
+    per-slice recurrence there) and the closed-form rows, against the oracle."""
+    from conftest import near_critical_vs_oracle
+    near_critical_vs_oracle(tmp_path, n_fam=6)

@@ -577,17 +577,16 @@ __device__ __forceinline__ bool run_slices_fused_k(int K, int n, int C, double* 
 #endif
 template <int NT>
 __device__ __forceinline__ void dp_tail_reduce(const DPArgs& A, double* s_tot) {
-    __shared__ int s_last;
-    constexpr int NW = NT / 32;
+    constexpr int NW = NT / 32;  // (no static shared memory here: k_dp opts in to the full 227 KB dynamically)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     __syncthreads();  // this family's outputs are written
+    int last = 0;
     if (tid == 0) {
         __threadfence();
         const unsigned prev = atomicAdd(A.done, 1u);
-        s_last = (prev + 1u == (unsigned)A.n_total) ? 1 : 0;
+        last = (prev + 1u == (unsigned)A.n_total) ? 1 : 0;
     }
-    __syncthreads();
-    if (!s_last) return;
+    if (!__syncthreads_or(last)) return;
     __threadfence();
     const int root = A.M.root, KR = A.PL.K[root], F = A.n_total, Kmax = A.PL.Kmax;
     for (int k = warp; k < KR; k += NW) {
