@@ -567,8 +567,8 @@ __device__ __forceinline__ bool run_slices_fused_k(int K, int n, int C, double* 
 
 // ---------------------------------------------------------------------------------------------------------
 // Fused K3.  Every CTA publishes its family's (log L, ∇) and bumps a counter; the CTA that sees the last count
-// reduces: warp w owns the components k ≡ w (mod NW), lanes stride the families, a shuffle tree closes — the order
-// of the additions depends on (F, NT) only, never on which CTA happens to be last (deterministic bits).
+// reduces: thread (r, k) sums component k over the families f ≡ r (mod NT/KR), thread k adds those partial sums —
+// the order of the additions depends on (F, NT, KR) only, never on which CTA happens to be last (deterministic bits).
 // ---------------------------------------------------------------------------------------------------------
 #ifdef WHALE_EMU
 #define LDCG(p) (*(p))
@@ -589,11 +589,36 @@ __device__ __forceinline__ void dp_tail_reduce(const DPArgs& A, double* s_tot) {
     if (!__syncthreads_or(last)) return;
     __threadfence();
     const int root = A.M.root, KR = A.PL.K[root], F = A.n_total, Kmax = A.PL.Kmax;
-    for (int k = warp; k < KR; k += NW) {
-        double s = 0.0;
-        for (int f = lane; f < F; f += 32) s += LDCG(A.out_fam + (size_t)f * KR + k);
-        for (int step = 16; step > 0; step >>= 1) s += SHFL_DOWN(s, step);
-        if (lane == 0) s_tot[k] = s - (double)F * A.PL.cond[A.cond_kind * Kmax + k];
+    if (KR <= NT / 2) {
+        // R = NT/KR row groups: thread (r, k) sums component k of the families f ≡ r (mod R), eight loads in flight;
+        // thread k then adds the R partial sums in order
+        const int R = NT / KR, r = tid / KR, k = tid - r * KR;
+        double* part = s_tot + KR;  // [R*KR]
+        if (r < R) {
+            const double* p = A.out_fam + (size_t)r * KR + k;
+            const size_t st = (size_t)R * KR;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0;
+            int f = r;
+            for (; f + 7 * R < F; f += 8 * R, p += 8 * st) {
+                a0 += LDCG(p); a1 += LDCG(p + st); a2 += LDCG(p + 2 * st); a3 += LDCG(p + 3 * st);
+                a4 += LDCG(p + 4 * st); a5 += LDCG(p + 5 * st); a6 += LDCG(p + 6 * st); a7 += LDCG(p + 7 * st);
+            }
+            for (; f < F; f += R, p += st) a0 += LDCG(p);
+            part[tid] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+        }
+        __syncthreads();
+        if (tid < KR) {
+            double s = 0.0;
+            for (int q = 0; q < R; q++) s += part[q * KR + tid];
+            s_tot[tid] = s - (double)F * A.PL.cond[A.cond_kind * Kmax + tid];
+        }
+    } else {
+        for (int k = warp; k < KR; k += NW) {
+            double s = 0.0;
+            for (int f = lane; f < F; f += 32) s += LDCG(A.out_fam + (size_t)f * KR + k);
+            for (int step = 16; step > 0; step >>= 1) s += SHFL_DOWN(s, step);
+            if (lane == 0) s_tot[k] = s - (double)F * A.PL.cond[A.cond_kind * Kmax + k];
+        }
     }
     __syncthreads();
     const bool finite = isfinite(s_tot[0]);  // ℓhood src/core.jl:15
@@ -626,7 +651,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
     const uint32_t leafmax = Hp->leafmax[A.plan];
     const uint32_t stage_bytes = Hp->stage_bytes[A.plan], leaf_stage = Hp->leaf_stage;
     const unsigned char* blob = A.arena + base;
-    const NodeRec* nrec = reinterpret_cast<const NodeRec*>(blob);
+    const NodeRec* const g_nrec = reinterpret_cast<const NodeRec*>(blob);
     const uint32_t* words = reinterpret_cast<const uint32_t*>(blob);
     const Ent* ents = reinterpret_cast<const Ent*>(blob);
 
@@ -644,7 +669,12 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
     int* s_toff = s_K + nn;
     int* s_roff = s_toff + nn;                                           // [nn+1] row offsets (doubles)
     int16_t* s_cmap = reinterpret_cast<int16_t*>(s_roff + nn + 1);       // [nn*2*Kmax]
-    const size_t hdr_bytes = (((7 * nn + 1) * sizeof(int) + (size_t)nn * 2 * Kmax * sizeof(int16_t)) + 15) & ~size_t(15);
+    const size_t meta_bytes = (((7 * nn + 1) * sizeof(int) + (size_t)nn * 2 * Kmax * sizeof(int16_t)) + 15) & ~size_t(15);
+    // the family's node records (48 B per node, the head of its blob): one coalesced read here instead of a
+    // dependent L2 round trip at every node of phase B
+    NodeRec* s_nrec = reinterpret_cast<NodeRec*>(smem_raw + meta_bytes);
+    const NodeRec* const nrec = s_nrec;
+    const size_t hdr_bytes = meta_bytes + (size_t)nn * sizeof(NodeRec);
     double* rows = reinterpret_cast<double*>(smem_raw + hdr_bytes);
     double* scr = rows + rows_len;
     unsigned char* stage = reinterpret_cast<unsigned char*>(scr + scr_len);
@@ -658,6 +688,8 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         s_roff[i] = (int)A.roff[(size_t)fam * nn + i];
     }
     for (int i = tid; i < nn * 2 * Kmax; i += NT) s_cmap[i] = PL.cmap[i];
+    for (int i = tid; i < nn * 3; i += NT)
+        reinterpret_cast<uint4*>(s_nrec)[i] = __ldg(reinterpret_cast<const uint4*>(g_nrec) + i);
     __syncthreads();
     double* const ell_base = A.ell ? A.ell + Hp->ell_off : nullptr;
     auto ell_of = [&](int e) -> double* {  // node e's matrix inside the family's ℓ (node-index order)

@@ -68,22 +68,52 @@ __global__ void __launch_bounds__(TABLES_NT) k_tables(ModelDev M, PlanDev PL, co
     const long long tk0 = CLOCK64();
     const int nn = M.nn, Kmax = PL.Kmax, P = M.n_params;
     double* sd = reinterpret_cast<double*>(tsm);  // dt, leafP, pleaf [nn each], x [P], (α,β) [nn*Kmax*2], ϵ_0, ϵ_n [nn*Kmax each]
-    double* s_ab = sd + 3 * nn + P;
-    double* s_e0 = s_ab + 2 * nn * Kmax;
+    double* s_ab = sd + 3 * nn + P;           // per-slice (α, β) components
+    double* s_abn = s_ab + 2 * nn * Kmax;     // whole-branch (α_n, β_n) components (closed-form branches)
+    double* s_e0 = s_abn + 2 * nn * Kmax;
     double* s_en = s_e0 + nn * Kmax;
     int* si = reinterpret_cast<int*>(s_en + nn * Kmax);  // 10 arrays [nn], lvl_off [nlvl+1], lvl_nodes [nn]
     int16_t* s_cm = reinterpret_cast<int16_t*>(si + 11 * nn + M.nlvl + 1);
     uint8_t* s_ro = reinterpret_cast<uint8_t*>(s_cm + nn * 2 * Kmax);
-    for (int i = threadIdx.x; i < nn; i += blockDim.x) {
-        sd[i] = M.dt[i]; sd[nn + i] = M.leafP[i]; sd[2 * nn + i] = pleaf ? pleaf[i] : 0.0;
-        si[i] = M.kind[i]; si[nn + i] = M.nsl[i]; si[2 * nn + i] = M.child0[i]; si[3 * nn + i] = M.child1[i];
-        si[4 * nn + i] = M.lam_slot[i]; si[5 * nn + i] = M.mu_slot[i]; si[6 * nn + i] = M.q_slot[i];
-        si[7 * nn + i] = PL.K[i]; si[8 * nn + i] = PL.toff[i]; si[10 * nn + M.nlvl + 1 + i] = M.lvl_nodes[i];
+    {
+        // one round trip: the first blockDim elements of every array are requested before anything is stored
+        // (after an L2 flush each dependent round costs a DRAM latency); longer arrays finish in the loops below
+        const int t = threadIdx.x, nt = blockDim.x;
+        double r_dt = 0.0, r_lp = 0.0, r_pl = 0.0, r_x = 0.0;
+        int r_kind = 0, r_nsl = 0, r_c0 = 0, r_c1 = 0, r_ls = 0, r_ms = 0, r_qs = 0, r_K = 0, r_to = 0, r_ln = 0, r_lo = 0;
+        int16_t r_cm = 0;
+        uint8_t r_ro = 0;
+        if (t < nn) {
+            r_dt = M.dt[t]; r_lp = M.leafP[t]; r_pl = pleaf ? pleaf[t] : 0.0;
+            r_kind = M.kind[t]; r_nsl = M.nsl[t]; r_c0 = M.child0[t]; r_c1 = M.child1[t];
+            r_ls = M.lam_slot[t]; r_ms = M.mu_slot[t]; r_qs = M.q_slot[t];
+            r_K = PL.K[t]; r_to = PL.toff[t]; r_ln = M.lvl_nodes[t];
+        }
+        if (t <= M.nlvl) r_lo = M.lvl_off[t];
+        if (t < P) r_x = x[t];
+        if (t < nn * 2 * Kmax) r_cm = PL.cmap[t];
+        if (t < nn * Kmax) r_ro = PL.role[t];
+        if (t < nn) {
+            sd[t] = r_dt; sd[nn + t] = r_lp; sd[2 * nn + t] = r_pl;
+            si[t] = r_kind; si[nn + t] = r_nsl; si[2 * nn + t] = r_c0; si[3 * nn + t] = r_c1;
+            si[4 * nn + t] = r_ls; si[5 * nn + t] = r_ms; si[6 * nn + t] = r_qs;
+            si[7 * nn + t] = r_K; si[8 * nn + t] = r_to; si[10 * nn + M.nlvl + 1 + t] = r_ln;
+        }
+        if (t <= M.nlvl) si[10 * nn + t] = r_lo;
+        if (t < P) sd[3 * nn + t] = r_x;
+        if (t < nn * 2 * Kmax) s_cm[t] = r_cm;
+        if (t < nn * Kmax) s_ro[t] = r_ro;
+        for (int i = t + nt; i < nn; i += nt) {
+            sd[i] = M.dt[i]; sd[nn + i] = M.leafP[i]; sd[2 * nn + i] = pleaf ? pleaf[i] : 0.0;
+            si[i] = M.kind[i]; si[nn + i] = M.nsl[i]; si[2 * nn + i] = M.child0[i]; si[3 * nn + i] = M.child1[i];
+            si[4 * nn + i] = M.lam_slot[i]; si[5 * nn + i] = M.mu_slot[i]; si[6 * nn + i] = M.q_slot[i];
+            si[7 * nn + i] = PL.K[i]; si[8 * nn + i] = PL.toff[i]; si[10 * nn + M.nlvl + 1 + i] = M.lvl_nodes[i];
+        }
+        for (int i = t + nt; i <= M.nlvl; i += nt) si[10 * nn + i] = M.lvl_off[i];
+        for (int i = t + nt; i < P; i += nt) sd[3 * nn + i] = x[i];
+        for (int i = t + nt; i < nn * 2 * Kmax; i += nt) s_cm[i] = PL.cmap[i];
+        for (int i = t + nt; i < nn * Kmax; i += nt) s_ro[i] = PL.role[i];
     }
-    for (int i = threadIdx.x; i <= M.nlvl; i += blockDim.x) si[10 * nn + i] = M.lvl_off[i];
-    for (int i = threadIdx.x; i < P; i += blockDim.x) sd[3 * nn + i] = x[i];
-    for (int i = threadIdx.x; i < nn * 2 * Kmax; i += blockDim.x) s_cm[i] = PL.cmap[i];
-    for (int i = threadIdx.x; i < nn * Kmax; i += blockDim.x) s_ro[i] = PL.role[i];
     __syncthreads();
     TabMeta T{si, si + nn, si + 2 * nn, si + 3 * nn, si + 4 * nn, si + 5 * nn, si + 6 * nn, si + 7 * nn, si + 8 * nn,
               si + 10 * nn, si + 10 * nn + M.nlvl + 1, si + 9 * nn, sd, sd + nn, sd + 2 * nn, sd + 3 * nn, s_cm, s_ro};
@@ -108,6 +138,12 @@ __global__ void __launch_bounds__(TABLES_NT) k_tables(ModelDev M, PlanDev PL, co
                     closed = (fabs(t * (lam.v - mu.v)) >= 1e-4 && !(flags & TAB_FORCE_CHAIN)) ? 1 : 0;
                 }
                 b = (lam / mu) * a;
+                if (closed) {  // the whole branch as one map (time n·Δt): all the chain over levels needs from this branch
+                    D1 an, bn;
+                    bdp_ab_t(lam, mu, t * (double)T.nsl[e], an, bn);
+                    s_abn[(e * Kmax + k) * 2 + 0] = k == 0 ? an.v : an.d;
+                    s_abn[(e * Kmax + k) * 2 + 1] = k == 0 ? bn.v : bn.d;
+                }
             }
             s_ab[(e * Kmax + k) * 2 + 0] = k == 0 ? a.v : a.d;
             s_ab[(e * Kmax + k) * 2 + 1] = k == 0 ? b.v : b.d;
@@ -173,9 +209,8 @@ __global__ void __launch_bounds__(TABLES_NT) k_tables(ModelDev M, PlanDev PL, co
                 s_e0[e * Kmax + k] = k == 0 ? ep.v : ep.d;
                 D1 en = ep, lf = mk(0.0);
                 if (n > 0 && closed) {
-                    D1 lam, mu, an, bn;
-                    rates_of(T, M, e, role, lam, mu);
-                    bdp_ab_t(lam, mu, T.dt[e] * (double)n, an, bn);
+                    const D1 an = mk(s_abn[(e * Kmax) * 2], k == 0 ? 0.0 : s_abn[(e * Kmax + k) * 2]);
+                    const D1 bn = mk(s_abn[(e * Kmax) * 2 + 1], k == 0 ? 0.0 : s_abn[(e * Kmax + k) * 2 + 1]);
                     const D1 r = mk(1.0) / (1.0 - bn * ep);
                     en = (an + ((1.0 - an) - bn) * ep) * r;
                     // leaf clade on a leaf branch: ℓ_n = leafℙ·Π_i ϕ_i (src/core.jl:94,123) = leafℙ·ϕ over the whole

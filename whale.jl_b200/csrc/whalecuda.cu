@@ -408,14 +408,14 @@ static inline void pad4(std::vector<uint32_t>& w) { while (w.size() & 3) w.push_
 
 static size_t smem_need(const whale_model* m, const FamHdr& h, int plan, int Kmax_) {  // mirrors the carve-up in k_dp
     const size_t nn = m->nn, Kmax = Kmax_, NW = dp_nt() / 32;
-    const size_t hdr = (((7 * nn + 1) * sizeof(int) + nn * 2 * Kmax * sizeof(int16_t)) + 15) & ~size_t(15);
+    const size_t hdr = ((((7 * nn + 1) * sizeof(int) + nn * 2 * Kmax * sizeof(int16_t)) + 15) & ~size_t(15)) + nn * sizeof(NodeRec);
     return hdr + ((size_t)h.rows_len[plan] + h.scr_len[plan] + h.prod_len[plan]) * sizeof(double) +
            h.stage_bytes[plan] + NW * ((size_t)h.leafmax[plan] * sizeof(double) + h.leaf_stage);
 }
 
 static size_t tables_smem(const whale_model* m, const Plan& pl, bool shapes) {  // mirrors the carve-ups in k_tables
     const size_t nn = m->nn, nlvl = m->lvl_off.size() - 1;
-    size_t need = (3 * nn + m->P + 4 * nn * pl.Kmax) * sizeof(double) + (11 * nn + nlvl + 1) * sizeof(int) +
+    size_t need = (3 * nn + m->P + 6 * nn * pl.Kmax) * sizeof(double) + (11 * nn + nlvl + 1) * sizeof(int) +
                   nn * 2 * pl.Kmax * sizeof(int16_t) + nn * pl.Kmax + 16;
     if (shapes)  // a leaf-shape CTA keeps its branch's projective and (ϕ, ψ) rows in shared memory
         for (int e : m->leafnodes) need = std::max(need, 2 * (size_t)(m->nsl[e] + 1) * pl.K[e] * sizeof(double2));
@@ -1019,8 +1019,9 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
         const bool fused = fused_reduce() && (size_t)F * pl.K[m->root] <= ((size_t)1 << 20) && pl.K[m->root] <= 1024;
         if (fused) a.done = D->d_done;
         const int MB = dp_minb();
+        const size_t tail_smem = (size_t)(NT + 2 * pl.K[m->root] + 2) * sizeof(double);  // the fused reduction's scratch
         auto launch_bin = [&](const Bin& b, cudaStream_t s) {
-#define LAUNCHV(NTV, MBV) if (NT == NTV && MB == MBV) LAUNCH((k_dp<NTV, MBV>), b.count, NTV, b.smem, s, a, b.off);
+#define LAUNCHV(NTV, MBV) if (NT == NTV && MB == MBV) LAUNCH((k_dp<NTV, MBV>), b.count, NTV, std::max(b.smem, tail_smem), s, a, b.off);
             DP_VARIANTS(LAUNCHV)
 #undef LAUNCHV
             g_launches++;
