@@ -143,6 +143,7 @@ inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 inline cudaError_t cudaGetLastError() { return 0; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
 inline cudaError_t cudaSetDevice(int) { return 0; }
+inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { *p = cudaDeviceProp(); return 0; }
 inline cudaError_t cudaMalloc(void** p, size_t n) { *p = calloc(1, n ? n : 1); return 0; }
 inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = calloc(1, n ? n : 1); return 0; }

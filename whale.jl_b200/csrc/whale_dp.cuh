@@ -458,9 +458,10 @@ __device__ __forceinline__ void slice_pass(const LaneWork<K>& w, int wg, bool tw
     }
 #ifndef WHALE_SLICE_NOHOIST
     // the leader's operands (ϕ_i, ψ_i with tangents, the cell's previous value) are fetched before the reduction so
-    // their latency hides behind the shuffles; every lane loads (valid addresses), only leaders use them
+    // their latency hides behind the shuffles; every lane loads (valid addresses), only leaders use them — the other
+    // lanes all read cell 0 (one broadcast wavefront instead of a gather of their own cells)
     const bool lead = w.cell >= 0 && (sidx & (w.gsz - 1)) == 0;
-    const int cK = max(w.cell, 0) * K;
+    const int cK = lead ? w.cell * K : 0;
     double2 pk[K];
     double o[K];
 #pragma unroll

@@ -165,7 +165,8 @@ struct whale_data {
     double last_bt_ms = 0.0;
     std::vector<uint32_t> roff_host[MAXPLAN];
     uint32_t* d_roff[MAXPLAN] = {};
-    std::vector<double> work;
+    std::vector<double> work;           // predicted flops per family (pack time)
+    std::vector<double> work_measured;  // SM cycles per family from the calibration pass (empty: not calibrated)
     size_t out_total = 0;
     cudaStream_t side[MAX_BINS] = {};
     cudaEvent_t ev_join[MAX_BINS] = {};
@@ -496,6 +497,47 @@ static size_t set_budgets(whale_data* D, int g, const Plan& pl) {
     return worst;
 }
 
+static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, int32_t condition, uint32_t flags,
+                            double* d_out, cudaStream_t st);
+
+// Launch order of plan g's families for a given per-family work vector (predicted flops at pack time, measured SM
+// cycles after the calibration pass).  Bins by shared-memory need (one per occupancy class, launched concurrently);
+// inside a bin the heaviest families go first (the hardware hands CTAs to SM slots in index order = LPT list
+// scheduling).  A "paired" order for the 1–2 wave case (heaviest alone, lightest + middle paired) was measured 4 %
+// SLOWER on the B200: an SM with fewer resident families runs each of them faster (the SM's shared-memory/issue
+// throughput is what is conserved, not the slot count), so LPT's ragged tail costs little.
+static cudaError_t order_families(whale_data* D, int g, const std::vector<double>& work) {
+    const whale_model* m = D->m;
+    const Plan& pl = *D->plans[g];
+    const int F = D->F;
+    std::vector<int>& perm = D->perm[g];
+    perm.resize(F);
+    std::iota(perm.begin(), perm.end(), 0);
+    std::vector<size_t> need(F);
+    for (int f = 0; f < F; f++) need[f] = smem_need(m, D->hdr[f], g, pl.Kmax);
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return need[a] != need[b] ? need[a] > need[b] : work[a] > work[b]; });
+    std::vector<Bin>& bins = D->bins[g];
+    bins.clear();
+    int i = 0;
+    // a bin = families that allow the same number of resident CTAs per SM (capped by the register limit):
+    // a smaller shared-memory request buys nothing once registers are the limiter
+    auto cls = [&](size_t nd) { return std::min<size_t>((size_t)dp_minb(), (227 * 1024) / std::max<size_t>(nd, 1)); };
+    while (i < F) {
+        Bin b{i, 0, need[perm[i]]};
+        while (i < F && (cls(need[perm[i]]) == cls(b.smem) || b.count < 64 || (int)bins.size() >= MAX_BINS - 1)) { i++; b.count++; }
+        bins.push_back(b);
+    }
+    // merge a tiny last bin into its predecessor
+    if (bins.size() > 1 && bins.back().count < 64) { bins[bins.size() - 2].count += bins.back().count; bins.pop_back(); }
+    for (const Bin& b : bins)
+        std::stable_sort(perm.begin() + b.off, perm.begin() + b.off + b.count, [&](int x, int y) { return work[x] > work[y]; });
+    if (!D->d_perm[g]) {
+        cudaError_t e = cudaMalloc((void**)&D->d_perm[g], std::max<size_t>(F, 1) * sizeof(int));
+        if (e != cudaSuccess) return e;
+    }
+    return cudaMemcpy(D->d_perm[g], perm.data(), (size_t)F * sizeof(int), cudaMemcpyHostToDevice);
+}
+
 int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t* out) {
     if (!m || !d || !out) return fail(WHALE_ERR_ARG, "null argument");
     const int nn = m->nn, F = d->n_fam;
@@ -815,34 +857,12 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
         fprintf(stderr, "[whale] %d families, P = %d: %zu gradient pass(es), worst family %zu B of shared memory\n", F, m->P,
                 D->plans.size() - 1, need1);
     if (need1 > SMEM_MAX) { delete D; return fail(WHALE_ERR_CAPACITY, "a family needs %zu bytes of shared memory (> 227 KB) even with %d parameter chunks", need1, MAXPLAN - 1); }
-    // bins by shared-memory need (geometric, <= 25 % waste), launched concurrently; within a bin the
-    // heaviest families go first
     size_t outsz = 0;
     for (size_t g = 0; g < D->plans.size(); g++) {
         const Plan& pl = *D->plans[g];
         D->out_off.push_back(g == 0 ? 0 : outsz);  // the value plan shares the first gradient slot's space
         if (g >= 1) outsz += (size_t)F * pl.K[m->root];
-        std::vector<int>& perm = D->perm[g];
-        perm.resize(F);
-        std::iota(perm.begin(), perm.end(), 0);
-        std::vector<size_t> need(F);
-        for (int f = 0; f < F; f++) need[f] = smem_need(m, D->hdr[f], (int)g, pl.Kmax);
-        const std::vector<double>& work = D->work;
-        std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return need[a] != need[b] ? need[a] > need[b] : work[a] > work[b]; });
-        std::vector<Bin>& bins = D->bins[g];
-        int i = 0;
-        // a bin = families that allow the same number of resident CTAs per SM (capped by the register limit):
-        // a smaller shared-memory request buys nothing once registers are the limiter
-        auto cls = [&](size_t nd) { return std::min<size_t>((size_t)dp_minb(), (227 * 1024) / std::max<size_t>(nd, 1)); };
-        while (i < F) {
-            Bin b{i, 0, need[perm[i]]};
-            while (i < F && (cls(need[perm[i]]) == cls(b.smem) || b.count < 64 || (int)bins.size() >= MAX_BINS - 1)) { i++; b.count++; }
-            std::stable_sort(perm.begin() + b.off, perm.begin() + b.off + b.count, [&](int x, int y) { return work[x] > work[y]; });
-            bins.push_back(b);
-        }
-        // merge a tiny last bin into its predecessor
-        if (bins.size() > 1 && bins.back().count < 64) { bins[bins.size() - 2].count += bins.back().count; bins.pop_back(); }
-        CU(upload(perm, &D->d_perm[g]));
+        CU(order_families(D, (int)g, D->work));
         CU(upload(D->roff_host[g], &D->d_roff[g]));
     }
     D->out_total = std::max<size_t>(outsz, (size_t)F);
@@ -863,6 +883,38 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
     CU(cudaEventCreateWithFlags(&D->ev_tab, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&D->side_tab, cudaStreamNonBlocking));
     *out = D;
+#ifndef WHALE_EMU
+    // Calibration pass: one profiled evaluation at a benign parameter point; the measured SM cycles of every family
+    // replace the packer's flop estimate as the scheduling weight (the estimate misses e.g. long leaf-branch chains).
+    // Results never depend on the launch order: per-family outputs are indexed by family, the sum runs in family order.
+    if (F > 1 && env_int("WHALE_CALIBRATE", 1)) {
+        std::vector<double> x(std::max(m->P, 1), 0.0);
+        for (int e = 0; e < nn; e++) {
+            if (m->lam_slot[e] >= 0) x[m->lam_slot[e]] = m->log_scale ? log(0.2) : 0.2;
+            if (m->mu_slot[e] >= 0) x[m->mu_slot[e]] = m->log_scale ? log(0.3) : 0.3;
+            if (m->q_slot[e] >= 0) x[m->q_slot[e]] = 0.2;
+        }
+        if (m->eta_slot >= 0) x[m->eta_slot] = 0.67;
+        CU(cudaMemcpy(m->d_x, x.data(), m->P * sizeof(double), cudaMemcpyHostToDevice));
+        CU(cudaMemset(m->d_pleaf, 0, nn * sizeof(double)));
+        m->x_host_valid = false;
+        for (int rep = 0; rep < 2; rep++) {  // the first run pays cold caches and lazy allocations
+            int32_t rc = enqueue_eval(m, D, m->d_x, 0, WHALE_WANT_GRAD | WHALE_PROFILE, m->d_out, m->stream);
+            if (rc != WHALE_OK) return rc;
+            CU(cudaStreamSynchronize(m->stream));
+        }
+        std::vector<long long> tim((size_t)F * TIMW);
+        CU(cudaMemcpy(tim.data(), D->d_tim, tim.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        std::vector<double> cyc(F);
+        bool ok = true;
+        for (int f = 0; f < F; f++) { cyc[f] = (double)tim[(size_t)f * TIMW + 6]; ok = ok && cyc[f] > 0.0; }
+        if (ok) {
+            D->work_measured = cyc;
+            for (size_t g = 0; g < D->plans.size(); g++) CU(order_families(D, (int)g, cyc));
+        }
+        D->ev_valid = false;
+    }
+#endif
     return WHALE_OK;
 }
 
