@@ -458,10 +458,10 @@ __device__ __forceinline__ void slice_pass(const LaneWork<K>& w, int wg, bool tw
     }
 #ifndef WHALE_SLICE_NOHOIST
     // the leader's operands (ϕ_i, ψ_i with tangents, the cell's previous value) are fetched before the reduction so
-    // their latency hides behind the shuffles; every lane loads (valid addresses), only leaders use them — the other
-    // lanes all read cell 0 (one broadcast wavefront instead of a gather of their own cells)
+    // their latency hides behind the shuffles; every lane loads (valid addresses), only leaders use them.  (Letting
+    // the non-leaders read one broadcast cell instead of their own measured 1 % slower.)
     const bool lead = w.cell >= 0 && (sidx & (w.gsz - 1)) == 0;
-    const int cK = lead ? w.cell * K : 0;
+    const int cK = max(w.cell, 0) * K;
     double2 pk[K];
     double o[K];
 #pragma unroll
