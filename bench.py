@@ -319,6 +319,7 @@ def main():
                         "the reference's CCD objects stay resident in RAM across logpdf calls"},
         "gpu_launches": int(launches),
         "kernels_ms": {"k_tables": float(kms[:, 0].mean()), "k_dp": dp_ms, "k_reduce": float(kms[:, 2].mean()),
+                       "k_reduce_note": "the reduction runs in the tail of k_dp; this is the gap to the step's end event",
                        "step_events": float(step_ms.mean()), "wall_per_step_incl_flush": 1e3 * wall / K},
         "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": ach_tf / fp64_peak, "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_dp<128,4>",

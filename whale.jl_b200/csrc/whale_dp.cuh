@@ -15,7 +15,7 @@
 //   phase A  leaf branches are independent of each other: one WARP per leaf branch, warp-level sync only;
 //            branches whose compatible clades are all leaf clades are family-independent and are filled
 //            from the table k_tables prepared (ℓ_n = leafℙ·Πϕ_i); small in-paralog clades use the closed
-//            form over tree shapes (k_leafshapes).
+//            form over tree shapes (leaf-shape CTAs of k_tables).
 //   phase B  internal / WGD / root nodes in the reference's order (children first); the node's lists and
 //            ϕ/ψ rows are staged in shared memory; only as many warps as the row has lanes take part in the
 //            slice loop (one warp: warp-level sync; several: a named barrier among them).
@@ -710,7 +710,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         const int K = s_K[e], n = s_nsl[e];
         double* fin = rows + s_roff[e];
         if (A.skip_leaf && R.sptr_off) {
-            // closed form over tree shapes: ℓ_n[γ] = Σ_σ C_σ[γ]·wσ_n  (C from the packer, w from k_leafshapes)
+            // closed form over tree shapes: ℓ_n[γ] = Σ_σ C_σ[γ]·wσ_n  (C from the packer, w from the leaf-shape CTAs of k_tables)
             const uint32_t* sptr = words + R.sptr_off;
             const Ent* sent = ents + R.sent_off;
             const double* W = PL.shapeW + (size_t)e * NSHAPE * Kmax;

@@ -1,9 +1,10 @@
 // libwhalecuda — B200 (sm_100a) engine for Whale.jl's ALE/DLWGD likelihood + forward-mode gradient.
 //
 // Hot path replaced (reference paths relative to the reference checkout):
-//   slice tables   src/model.jl:162-191, src/bdputil.jl:6-11          -> k_tables   (whale_tables.cuh)
+//   slice tables   src/model.jl:162-191, src/bdputil.jl:6-11          -> k_tables   (whale_tables.cuh; closed-form rows)
 //   the DP         src/core.jl:83-199 (whale!/whalewgd!/whaleroot!)   -> k_dp       (whale_dp.cuh)
-//   Σ − N·cond     src/core.jl:46-64, src/condition.jl:11-29          -> k_reduce1/2 (whale_reduce.cuh)
+//   Σ − N·cond     src/core.jl:46-64, src/condition.jl:11-29          -> tail of k_dp (dp_tail_reduce; k_reduce1/2 in
+//                                                                        whale_reduce.cuh for very large batches)
 // Forward tangents replace ForwardDiff duals: every ℓ cell carries K_e = 1 + (#parameters that can
 // influence branch e) components; lanes span (clade cell × component).
 //
@@ -170,8 +171,7 @@ struct whale_data {
     size_t out_total = 0;
     cudaStream_t side[MAX_BINS] = {};
     cudaEvent_t ev_join[MAX_BINS] = {};
-    cudaEvent_t ev_fork = nullptr, ev_tab = nullptr;
-    cudaStream_t side_tab = nullptr;
+    cudaEvent_t ev_fork = nullptr;
     std::vector<unsigned char> arena_host;  // packing buffer (released after upload)
     size_t arena_bytes = 0;
     unsigned char* d_arena = nullptr;
@@ -262,7 +262,7 @@ static cudaError_t upload_plan(Plan& pl, int nn) {
     if ((e = upload(pl.cmap, &dcmap)) != cudaSuccess) return e;
     if ((e = upload(pl.role, &drole)) != cudaSuccess) return e;
     double *eps, *cx, *cy, *leaf, *cond, *ab, *shapeW;
-    double2 *pp, *uv, *lsuv, *lspp;
+    double2 *pp, *uv;
     long long* tim;
     if ((e = cudaMalloc((void**)&tim, 32 * sizeof(long long))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&eps, std::max<size_t>(pl.tab_len, 1) * sizeof(double))) != cudaSuccess) return e;
@@ -271,8 +271,6 @@ static cudaError_t upload_plan(Plan& pl, int nn) {
     size_t nk = (size_t)nn * pl.Kmax * sizeof(double);
     if ((e = cudaMalloc((void**)&ab, 2 * nk)) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&shapeW, NSHAPE * nk)) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void**)&lsuv, std::max<size_t>(pl.tab_len, 1) * sizeof(double2))) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void**)&lspp, std::max<size_t>(pl.tab_len, 1) * sizeof(double2))) != cudaSuccess) return e;
     cudaMemset(shapeW, 0, NSHAPE * nk);
     if ((e = cudaMalloc((void**)&cx, nk)) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&cy, nk)) != cudaSuccess) return e;
@@ -280,8 +278,8 @@ static cudaError_t upload_plan(Plan& pl, int nn) {
     if ((e = cudaMalloc((void**)&cond, 4 * pl.Kmax * sizeof(double))) != cudaSuccess) return e;
     cudaMemset(cx, 0, nk); cudaMemset(cy, 0, nk); cudaMemset(leaf, 0, nk);
     cudaMemset(cond, 0, 4 * pl.Kmax * sizeof(double));
-    pl.owned = {dK, dact, dtoff, dcmap, drole, eps, pp, uv, ab, cx, cy, leaf, shapeW, lsuv, lspp, cond, tim};
-    pl.dev = PlanDev{pl.Kmax, dK, dact, dcmap, drole, dtoff, eps, pp, uv, ab, cx, cy, leaf, shapeW, lsuv, lspp, cond, nullptr, nullptr, nullptr, tim};
+    pl.owned = {dK, dact, dtoff, dcmap, drole, eps, pp, uv, ab, cx, cy, leaf, shapeW, cond, tim};
+    pl.dev = PlanDev{pl.Kmax, dK, dact, dcmap, drole, dtoff, eps, pp, uv, ab, cx, cy, leaf, shapeW, cond, nullptr, nullptr, nullptr, tim};
     return cudaSuccess;
 }
 
@@ -880,8 +878,6 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
         CU(cudaEventCreateWithFlags(&D->ev_join[i], cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&D->ev_fork, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&D->ev_tab, cudaEventDisableTiming));
-    CU(cudaStreamCreateWithFlags(&D->side_tab, cudaStreamNonBlocking));
     *out = D;
 #ifndef WHALE_EMU
     // Calibration pass: one profiled evaluation at a benign parameter point; the measured SM cycles of every family
@@ -981,8 +977,6 @@ int32_t whale_data_destroy(whale_data_t d) {
     for (auto& g : d->graphs) if (g.state == 2 && g.exec) cudaGraphExecDestroy(g.exec);
 #endif
     if (d->ev_fork) cudaEventDestroy(d->ev_fork);
-    if (d->ev_tab) cudaEventDestroy(d->ev_tab);
-    if (d->side_tab) cudaStreamDestroy(d->side_tab);
     cudaFree(d->d_ell); cudaFree(d->d_tim);
     for (int i = 0; i < 4; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     delete d;
