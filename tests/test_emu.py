@@ -65,6 +65,10 @@ def _check_backtrack(L, name, fams, nbt_check=None):
             want = g["bt_nodes"][starts[f * nbt + s]:starts[f * nbt + s + 1]]
             assert cnt[i, s] == counts[f, s, 0]
             assert np.array_equal(nodes[i, s, :cnt[i, s]], want), (name, f, s)
+        import whale_jl_b200 as W  # sumtrees over the family's samples (src/rectree.jl:113-133)
+        summ, clades = W.sumtrees([nodes[i, s, :cnt[i, s]] for s in range(nbt)])
+        assert sum(x["count"] for x in summ) == nbt and summ[0]["count"] >= summ[-1]["count"]
+        assert max(clades.values()) == nbt  # the root clade's reconciliation node is in every sample
 
 
 def test_emu_backtrack_matches_oracle(L):

@@ -133,3 +133,20 @@ def test_model_validation_errors():
     bad.order = w.order[::-1].copy()
     with pytest.raises(wlib.WhaleCudaError):
         L.model_create(bad)
+
+
+def test_sumtrees_identity_ignores_slice_times():
+    """`nodehash` (src/track.jl:105-113): reconciled trees that differ only in the slice at which events happen are
+    the same tree; a different branch for one event is a different tree; frequencies follow `sumtrees`
+    (src/rectree.jl:113-133)."""
+    import whale_jl_b200 as W
+    # (γ, e, t, parent): root duplication-free toy tree with one loss node (γ = −1)
+    a = np.array([[4, 6, 1, -1], [2, 5, 3, 0], [3, 4, 7, 0], [0, 1, 1, 1], [-1, 2, 0, 1], [1, 3, 1, 2]])
+    b = a.copy(); b[1, 2] = 5; b[2, 2] = 2            # other slice times only
+    c = a.copy(); c[2, 1] = 5                          # clade 3 reconciled on another branch
+    assert W.treekey(a) == W.treekey(b) != W.treekey(c)
+    summary, clades = W.sumtrees([a, c, b, a])
+    assert [s["count"] for s in summary] == [3, 1] and summary[0]["freq"] == 0.75
+    assert summary[0]["tree"] is a and summary[1]["tree"] is c
+    assert clades[(4, 6, frozenset({(2, 5), (3, 4)}))] == 3 and clades[(-1, 2, 0)] == 4
+    assert W.sumtrees([]) == ([], {})

@@ -211,3 +211,50 @@ def track(wm: WhaleModel, xs, posterior, n: int, fun=None, seed=None, max_nodes:
     cnt, st, nodes, ll = _lib.get().track(mh, dh, X, wm.p_leaf(), CONDITIONS[wm.condition], U, max_nodes)
     trees = _trees_from(cnt, st, nodes, n, len(xs))
     return (trees, ll) if return_loglik else trees
+
+
+def treekey(nodes) -> frozenset:
+    """Identity of a backtracked reconciled tree as the reference defines it (`nodehash`/`cladehash`,
+    src/track.jl:95-113): the SET over nodes of (γ, e, {(γ, e) of the children}) — a loss node is (loss, e, γ of its
+    sister) — so two samples that differ only in the slice `t` at which events happen are the same tree.  Here the
+    key is the set itself (exact), not a 64-bit hash of it.  `nodes`: one (n_nodes, 4) array from `backtrack`."""
+    nodes = np.asarray(nodes)
+    n = len(nodes)
+    ch = [[] for _ in range(n)]
+    for i in range(n):
+        p = int(nodes[i, 3])
+        if p >= 0:
+            ch[p].append(i)
+    keys = set()
+    for i in range(n):
+        g, e, p = int(nodes[i, 0]), int(nodes[i, 1]), int(nodes[i, 3])
+        if g < 0:  # loss node
+            sib = [j for j in ch[p] if j != i] if p >= 0 else []
+            keys.add((-1, e, int(nodes[sib[0], 0]) if sib else -2))
+        else:
+            keys.add((g, e, frozenset((int(nodes[j, 0]), int(nodes[j, 1])) for j in ch[i])))
+    return frozenset(keys)
+
+
+def sumtrees(trees):
+    """`sumtrees(trees, ccd, wm)` (src/rectree.jl:113-133) without the labelled event tables: the distinct
+    reconciled trees of ONE family among its N backtracked samples with their posterior frequencies, most frequent
+    first (ties: first sampled first), and the `cladecounts` table (src/rectree.jl:138: how many samples contain
+    each reconciled clade).  Host-side post-processing of `backtrack`/`track` output; for all families pass
+    `[sumtrees(t) for t in trees]` like the reference's matrix method (:110-111).
+
+    Returns (summary, clades): summary = list of dicts {freq, count, tree (the first sample with that identity),
+    key}; clades = dict reconciled-clade key -> number of samples containing it."""
+    N = len(trees)
+    if N == 0:
+        return [], {}
+    keys = [treekey(t) for t in trees]
+    first, counts, clades = {}, {}, {}
+    for i, k in enumerate(keys):
+        first.setdefault(k, i)
+        counts[k] = counts.get(k, 0) + 1
+        for c in k:
+            clades[c] = clades.get(c, 0) + 1
+    order = sorted(counts, key=lambda k: (-counts[k], first[k]))
+    summary = [{"freq": counts[k] / N, "count": counts[k], "tree": trees[first[k]], "key": k} for k in order]
+    return summary, clades
