@@ -227,3 +227,25 @@ def test_nowhere_extinct_condition_gradient_by_differences():
         xp[i] += h
         xm[i] -= h
         assert c.d[i] == pytest.approx((cond(xp) - cond(xm)) / (2 * h), rel=1e-5, abs=1e-8)
+
+
+def test_slice_recursion_equals_the_bdp_pgf_off_the_critical_branch():
+    """SURVEY §8c gap: both reference known answers use λ = μ, so the general branch of `getα` (src/bdputil.jl:6-7) is
+    pinned by the formula text alone.  Cross-check it against the reference's OTHER statement of the same process:
+    the per-slice ϵ recursion over a whole branch (src/model.jl:182-191) must equal the linear-BDP pgf at the branch
+    length, pgf(LinearBDP(λ, μ, t), ϵ₀) (src/bdputil.jl:58-64) — and stay continuous across the 1e-6 window."""
+    rng = np.random.default_rng(5)
+    for lam, mu in [(0.2, 0.3), (0.45, 0.1), (1.3, 1.1), (0.3, 0.3 + 2e-6), (0.3, 0.3 - 2e-6)] + \
+                   [tuple(rng.uniform(0.05, 1.5, 2)) for _ in range(5)]:
+        w = wo.WhaleModel(wo.ConstantDLWGD(lam=lam, mu=mu, q=[0.2, 0.1], eta=0.67), wo.c1_tree(), 0.05)
+        wo.setmodel(w)
+        for n in w.order:
+            if n.isroot() or len(n) == 1:
+                continue
+            want = wo.bdp_pgf(lam, mu, n.dist, n.eps[0])
+            # just outside the window exp(Δt(λ−μ)) − 1 cancels: the reference's recursion itself carries ~1e-16/(Δt|λ−μ|)
+            # per slice (2.5e-10 over a 64-slice branch at |λ−μ| = 2e-6) — why k_tables keeps the recurrence there
+            assert n.eps[-1] == pytest.approx(want, rel=1e-8 if abs(lam - mu) < 1e-5 else 1e-12), (lam, mu, n.name)
+    # continuity of getα across the isapprox window (critical formula on one side, general on the other)
+    a_in, a_out = wo.getalpha(0.3, 0.3 + 0.9e-6, 0.05), wo.getalpha(0.3, 0.3 + 1.1e-6, 0.05)
+    assert a_out == pytest.approx(a_in, rel=1e-5)  # the window itself is a 4e-6 step (λt/(1+λt) ignores μ)
