@@ -165,3 +165,38 @@ def test_emu_chain_tables_and_unfused_reduction():
     env = dict(os.environ, WHALE_TABLES_CHAIN="1", WHALE_FUSED_REDUCE="0")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_emu_mle_lbfgs_like_the_reference_mle_test(L, tmp_path):
+    """test/mle.jl's pattern (`optimize(f, g!, x0, LBFGS())` with f = −logpdf(model(rates), ccd) over (log λ, log μ),
+    η and q fixed, gradient from AD) with the fused loglik+∇ call in place of ForwardDiff: the optimiser must converge
+    to a stationary point, and the oracle must agree with the value there."""
+    from scipy.optimize import minimize
+    import whale_jl_b200 as W
+    from whale_jl_b200 import synth
+    from oracle import whale_oracle as wo, flat
+    wlib.use(L)
+    try:
+        d = synth.generate(str(tmp_path / "mle"), 4, seed=31)
+        tree = synth.c1_species_tree()
+        w0 = W.WhaleModel(W.ConstantDLWGD(lam=0.5, mu=0.4, q=[0.2, 0.1], eta=0.66), tree, 0.05)
+        ccd = W.read_ale(d, w0)
+        evals = []
+
+        def fg(x):
+            lam, mu = np.exp(x)
+            w = W.WhaleModel(W.ConstantDLWGD(lam=lam, mu=mu, q=[0.2, 0.1], eta=0.66), tree, 0.05)
+            ll, g = W.logpdf_and_gradient(w, ccd)  # raw gradient: (λ, μ, q1, q2, η) on the natural scale
+            evals.append(ll)
+            return -ll, -np.array([g[0] * lam, g[1] * mu])
+
+        f0, g0 = fg(np.log([0.5, 0.4]))
+        res = minimize(fg, np.log([0.5, 0.4]), jac=True, method="L-BFGS-B", options={"maxiter": 25, "gtol": 1e-6})
+        assert res.fun < f0 - 1e-3
+        assert np.abs(res.jac).max() < 1e-3 * max(1.0, np.abs(g0).max())
+        lam, mu = np.exp(res.x)
+        ow = wo.WhaleModel(wo.ConstantDLWGD(lam=lam, mu=mu, q=[0.2, 0.1], eta=0.66), wo.c1_tree(), 0.05)
+        ff = flat.FlatFams(wo.read_ale(d, ow), len(ow))
+        assert -res.fun == pytest.approx(flat.logpdf(flat.FlatModel(ow), ff, grad=False)[0], rel=1e-9)
+    finally:
+        wlib.use(None)
