@@ -113,7 +113,9 @@ int32_t whale_set_device(int32_t device);
 int32_t whale_model_create(const whale_model_desc* desc, whale_model_t* out);
 int32_t whale_model_destroy(whale_model_t m);
 
-/* read_ale-time packing (src/ccd.jl:126-137 + CCD ctor): builds the device arena once */
+/* read_ale-time packing (src/ccd.jl:126-137 + CCD ctor): builds the device arena once.  Ends with a calibration
+ * pass (two profiled evaluations at a benign parameter point on the model's stream) whose measured per-family SM
+ * cycles order the launch; results never depend on that order.  WHALE_CALIBRATE=0 skips it. */
 int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* desc, whale_data_t* out);
 /*
  * read_ale in one native call (src/ccd.jl:126-248): parse n_files ALEobserve `.ale` files on n_threads host
@@ -209,6 +211,8 @@ int32_t whale_work_estimate(whale_model_t m, whale_data_t d, uint32_t flags, dou
 /* device time of the kernels of the last WHALE_PROFILE evaluation on this data handle, measured with CUDA
  * events on the stream they were launched on (waits for that evaluation to finish) */
 int32_t whale_last_kernel_ms(whale_data_t d, double* tables_ms, double* dp_ms, double* reduce_ms);
+/* (the sum over families runs in the tail of k_dp: reduce_ms is then the gap between the end of k_dp and the end of
+ * the evaluation; with WHALE_FUSED_REDUCE=0 it times the separate reduction kernels) */
 
 /* device time of the k_backtrack launch of the last whale_backtrack call on this handle (CUDA events) */
 int32_t whale_last_backtrack_ms(whale_data_t d, double* ms);
