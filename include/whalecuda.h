@@ -128,6 +128,15 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* desc, whale_dat
 int32_t whale_read_ale(whale_model_t m, int32_t n_files, const char* const* paths, int32_t n_species,
                        const char* const* species_names, const int32_t* species_ids, const int64_t* node_clade_off,
                        const int32_t* node_clade, int32_t n_threads, whale_data_t* out, int32_t* n_clades);
+/*
+ * Binary arena cache (the "binary arena cache format" of the ingest row): whale_data_save writes the packed state
+ * of a handle (family headers, arena, packer facts); whale_data_load rebuilds a handle from it for a model with the
+ * same species tree and slicing (checked by a structure fingerprint) without parsing .ale files or re-packing —
+ * tangent plans, shared-memory budgets, launch order and calibration are redone for the loading process.
+ * Replaces re-running read_ale (src/ccd.jl:126-137) on an unchanged data set.
+ */
+int32_t whale_data_save(whale_data_t d, const char* path);
+int32_t whale_data_load(whale_model_t m, const char* path, whale_data_t* out);
 int32_t whale_data_destroy(whale_data_t d);
 int32_t whale_data_nfam(whale_data_t d);
 /* bytes of the packed arena resident in HBM, and the algorithmic bytes one evaluation reads */

@@ -200,3 +200,40 @@ def test_emu_mle_lbfgs_like_the_reference_mle_test(L, tmp_path):
         assert -res.fun == pytest.approx(flat.logpdf(flat.FlatModel(ow), ff, grad=False)[0], rel=1e-9)
     finally:
         wlib.use(None)
+
+
+def test_emu_arena_cache_round_trip(L, tmp_path):
+    """whale_data_save / whale_data_load: a handle rebuilt from the binary arena cache holds the same arena bytes and
+    gives bit-identical results; a cache is refused by a model with another species tree or slicing, and a truncated
+    file is an error, not a crash."""
+    import whale_jl_b200 as W
+    from whale_jl_b200 import synth, newick
+    from whale_jl_b200.core import _data_handle
+    wlib.use(L)
+    try:
+        d = synth.generate(str(tmp_path / "cache"), 5, seed=17)
+        w = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), synth.c1_species_tree(), 0.05)
+        a = W.read_ale(d, w)
+        path = str(tmp_path / "c.arena")
+        W.save_arena(a, w, path)
+        b = W.load_arena(path, w)
+        assert len(b) == len(a)
+        _, dha = _data_handle(w, a)
+        _, dhb = _data_handle(w, b)
+        assert np.array_equal(L.arena_dump(dha), L.arena_dump(dhb))
+        la, ga = W.logpdf_and_gradient(w, a)
+        lb, gb = W.logpdf_and_gradient(w, b)
+        assert la == lb and np.array_equal(ga, gb)
+        # another slicing (Δt) -> another model structure -> refused
+        w2 = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), synth.c1_species_tree(), 0.1)
+        with pytest.raises(wlib.WhaleCudaError, match="another model"):
+            W.load_arena(path, w2)
+        raw = open(path, "rb").read()
+        open(path, "wb").write(raw[:len(raw) // 2])
+        with pytest.raises(wlib.WhaleCudaError, match="truncated"):
+            W.load_arena(path, w)
+        open(path, "wb").write(b"not a cache")
+        with pytest.raises(wlib.WhaleCudaError, match="not a whalecuda arena cache"):
+            W.load_arena(path, w)
+    finally:
+        wlib.use(None)

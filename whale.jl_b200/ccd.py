@@ -205,6 +205,28 @@ def read_ale_native(path: str, model: WhaleModel, n_threads: int = 0) -> NativeC
     return NativeCCDVector(files, ncl, model, L, h)
 
 
+def save_arena(xs, model: WhaleModel, path: str) -> None:
+    """Write the packed device arena of a batch (`read_ale` / `read_ale_native` result) as a binary cache
+    (`whale_data_save`), so a later process can skip parsing and packing."""
+    from . import lib as _lib
+    from .core import _data_handle, _as_vector
+    xs, _ = _as_vector(xs)
+    _, dh = _data_handle(model, xs)
+    _lib.get().data_save(dh, path)
+
+
+def load_arena(path: str, model: WhaleModel) -> NativeCCDVector:
+    """A batch straight from an arena cache (`whale_data_load`) for a model with the same species tree and slicing
+    (a different one is refused).  Like `read_ale_native`, the CCDs then exist only as the device arena."""
+    from . import lib as _lib
+    from .core import _model_handle
+    L = _lib.get()
+    mh = _model_handle(model)
+    h = L.data_load(mh, path)
+    n = int(L.L.whale_data_nfam(h))
+    return NativeCCDVector([f"{path}#{i}" for i in range(n)], np.zeros(n, np.int32), model, L, h)
+
+
 def read_ale(path: str, model: WhaleModel) -> CCDVector:
     """`read_ale(path, wm)` (src/ccd.jl:126-137): a `.ale` file, a directory of them (sorted like
     `readdir`), or a text file listing paths (lines starting with # skipped)."""

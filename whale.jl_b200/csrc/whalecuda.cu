@@ -497,6 +497,7 @@ static size_t set_budgets(whale_data* D, int g, const Plan& pl) {
 
 static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, int32_t condition, uint32_t flags,
                             double* d_out, cudaStream_t st);
+static int32_t finalize_data(whale_model* m, whale_data* D, whale_data_t* out);
 
 // Launch order of plan g's families for a given per-family work vector (predicted flops at pack time, measured SM
 // cycles after the calibration pass).  Bins by shared-memory need (one per occupancy class, launched concurrently);
@@ -800,6 +801,15 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
     }
     D->ell_total = ell_total;
     D->algo_bytes = algo_bytes;
+    return finalize_data(m, D, out);
+}
+
+// Second half of whale_data_create, shared with whale_data_load: tangent plans and shared-memory budgets for this
+// model/plan (they depend on the runtime configuration, not on the CCDs), launch order, upload, calibration.
+// Takes ownership of D (deleted on failure).
+static int32_t finalize_data(whale_model* m, whale_data* D, whale_data_t* out) {
+    const int nn = m->nn, F = D->F;
+    std::vector<unsigned char>& A = D->arena_host;
     // ---- tangent plans: one gradient pass if every family's working set fits, else parameter chunks ----
     D->plans = {&m->plan[0], &m->plan[1]};
     set_budgets(D, 0, m->plan[0]);
@@ -961,6 +971,94 @@ int32_t whale_read_ale(whale_model_t m, int32_t n_files, const char* const* path
                      compat_off.data(), compat.data()};
     return whale_data_create(m, &d, out);
 }
+
+// ---- binary arena cache: the packed state of a data handle, so a later process skips parsing the
+//      .ale files and running the packer.  Layout: CacheHdr | FamHdr[F] | arena bytes | famC | per-node packer facts |
+//      work | aggregates.  Plans, shared-memory budgets, launch order and calibration are rebuilt on load (they depend
+//      on the runtime configuration).  A cache is valid for the model it was packed for (structure fingerprint). ----
+struct CacheHdr {
+    char magic[8];       // "WHALEAR1"
+    uint32_t version, nn;
+    uint64_t model_fp;   // species-tree structure + slicing
+    uint64_t F, arena_bytes, ell_total;
+    int64_t algo_bytes;
+    double aggG, aggTroot;
+};
+static uint64_t model_fingerprint(const whale_model* m) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) { h ^= v; h *= 1099511628211ull; };
+    mix((uint64_t)m->nn);
+    for (int e = 0; e < m->nn; e++) {
+        mix((uint64_t)(uint32_t)m->kind[e]); mix((uint64_t)(uint32_t)m->nsl[e]);
+        mix((uint64_t)(uint32_t)m->child0[e]); mix((uint64_t)(uint32_t)m->child1[e]); mix((uint64_t)(uint32_t)m->order[e]);
+    }
+    mix((uint64_t)sizeof(FamHdr)); mix((uint64_t)sizeof(NodeRec)); mix((uint64_t)HEAVY_SLOTS); mix((uint64_t)NSHAPE);
+    return h;
+}
+static bool put_raw(FILE* fp, const void* p, size_t bytes) { return bytes == 0 || fwrite(p, 1, bytes, fp) == bytes; }
+static bool get_raw(FILE* fp, void* p, size_t bytes) { return bytes == 0 || fread(p, 1, bytes, fp) == bytes; }
+#define put(fp, v) put_raw(fp, (v).data(), (v).size() * sizeof((v)[0]))
+#define get(fp, v, n) ((v).resize(n), get_raw(fp, (v).data(), (size_t)(n) * sizeof((v)[0])))
+
+int32_t whale_data_save(whale_data_t d, const char* path) {
+    if (!d || !path) return fail(WHALE_ERR_ARG, "null argument");
+    const whale_model* m = d->m;
+    const size_t F = (size_t)d->F, nn = (size_t)m->nn;
+    CU(cudaSetDevice(m->device));
+    std::vector<unsigned char> arena(d->arena_bytes);
+    if (d->arena_bytes) CU(cudaMemcpy(arena.data(), d->d_arena, d->arena_bytes, cudaMemcpyDeviceToHost));
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return fail(WHALE_ERR_ARG, "cannot open %s for writing", path);
+    CacheHdr h{};
+    memcpy(h.magic, "WHALEAR1", 8);
+    h.version = 1; h.nn = (uint32_t)nn; h.model_fp = model_fingerprint(m);
+    h.F = F; h.arena_bytes = d->arena_bytes; h.ell_total = d->ell_total; h.algo_bytes = d->algo_bytes;
+    h.aggG = d->aggG; h.aggTroot = d->aggTroot;
+    std::vector<uint32_t> famC(F * nn);
+    for (size_t f = 0; f < F; f++) for (size_t e = 0; e < nn; e++) famC[f * nn + e] = d->famC[f][e];
+    bool ok = fwrite(&h, sizeof(h), 1, fp) == 1 && put(fp, d->hdr) && put(fp, arena) && put(fp, famC) && put(fp, d->f_ndent) &&
+              put(fp, d->f_ntent) && put(fp, d->f_heavy) && put(fp, d->f_stage16) && put(fp, d->f_rootwin) && put(fp, d->work) &&
+              put(fp, d->aggC) && put(fp, d->aggT);
+    ok = (fclose(fp) == 0) && ok;
+    return ok ? WHALE_OK : fail(WHALE_ERR_ARG, "short write to %s", path);
+}
+
+int32_t whale_data_load(whale_model_t m, const char* path, whale_data_t* out) {
+    if (!m || !path || !out) return fail(WHALE_ERR_ARG, "null argument");
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return fail(WHALE_ERR_ARG, "cannot open %s", path);
+    CacheHdr h{};
+    if (fread(&h, sizeof(h), 1, fp) != 1 || memcmp(h.magic, "WHALEAR1", 8) != 0 || h.version != 1) {
+        fclose(fp);
+        return fail(WHALE_ERR_ARG, "%s is not a whalecuda arena cache (version 1)", path);
+    }
+    if (h.nn != (uint32_t)m->nn || h.model_fp != model_fingerprint(m) || h.F == 0 || h.F > 0x7fffffffull) {
+        fclose(fp);
+        return fail(WHALE_ERR_ARG, "%s was packed for another model (species tree / slicing differ)", path);
+    }
+    CU(cudaSetDevice(m->device));
+    auto* D = new whale_data();
+    D->m = m;
+    D->F = (int)h.F;
+    const size_t F = (size_t)h.F, nn = (size_t)m->nn;
+    std::vector<uint32_t> famC;
+    bool ok = get(fp, D->hdr, F) && get(fp, D->arena_host, (size_t)h.arena_bytes) && get(fp, famC, F * nn) &&
+              get(fp, D->f_ndent, F * nn) && get(fp, D->f_ntent, F * nn) && get(fp, D->f_heavy, F * nn) &&
+              get(fp, D->f_stage16, F * nn) && get(fp, D->f_rootwin, F) && get(fp, D->work, F) && get(fp, D->aggC, nn) &&
+              get(fp, D->aggT, nn);
+    ok = ok && fgetc(fp) == EOF;
+    fclose(fp);
+    if (!ok) { delete D; return fail(WHALE_ERR_ARG, "%s is truncated or has trailing bytes", path); }
+    D->famC.resize(F);
+    for (size_t f = 0; f < F; f++) D->famC[f].assign(famC.begin() + f * nn, famC.begin() + (f + 1) * nn);
+    D->ell_total = h.ell_total;
+    D->algo_bytes = h.algo_bytes;
+    D->aggG = h.aggG;
+    D->aggTroot = h.aggTroot;
+    return finalize_data(m, D, out);
+}
+#undef put
+#undef get
 
 int32_t whale_data_destroy(whale_data_t d) {
     if (!d) return WHALE_OK;

@@ -20,7 +20,7 @@ WANT_GRAD, KEEP_ELL, PROFILE = 1, 2, 4
 # every symbol include/whalecuda.h declares (tests check the built library exports all of them)
 SYMBOLS = ["whale_version", "whale_last_error", "whale_device_count", "whale_set_device", "whale_model_create",
            "whale_model_destroy", "whale_data_create", "whale_read_ale", "whale_data_destroy", "whale_data_nfam",
-           "whale_data_arena_bytes", "whale_data_arena_dump", "whale_logpdf_grad", "whale_logpdf_grad_async", "whale_mixture_logpdf_grad",
+           "whale_data_arena_bytes", "whale_data_arena_dump", "whale_data_save", "whale_data_load", "whale_logpdf_grad", "whale_logpdf_grad_async", "whale_mixture_logpdf_grad",
            "whale_slices", "whale_ell_size", "whale_ell_get", "whale_backtrack", "whale_track", "whale_launch_count",
            "whale_work_estimate", "whale_last_kernel_ms", "whale_last_phase_cycles", "whale_last_node_cycles", "whale_last_family_cycles", "whale_last_tables_cycles", "whale_last_backtrack_ms", "whale_fp64_peak"]
 
@@ -71,6 +71,8 @@ class Lib:
         L.whale_data_arena_bytes.restype = C.c_int64
         L.whale_data_arena_dump.argtypes = [vp, vp, C.c_int64]
         L.whale_data_arena_dump.restype = C.c_int64
+        L.whale_data_save.argtypes = [vp, C.c_char_p]
+        L.whale_data_load.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
         L.whale_logpdf_grad.argtypes = [vp, vp, f64p, f64p, C.c_int32, C.c_uint32, f64p, f64p, f64p, f64p]
         L.whale_logpdf_grad_async.argtypes = [vp, vp, vp, C.c_int32, C.c_uint32, vp, vp]
         L.whale_slices.argtypes = [vp, f64p, f64p, f64p, f64p, f64p]
@@ -119,6 +121,16 @@ class Lib:
                     _ptr(flat["p"], f64p), _ptr(flat["compat_off"], i64p), _ptr(flat["compat"], i32p))
         h = C.c_void_p()
         self.check(self.L.whale_data_create(mh, C.byref(d), C.byref(h)))
+        return h.value
+
+    def data_save(self, dh: int, path: str):
+        """whale_data_save: the packed state of a data handle as a binary arena cache."""
+        self.check(self.L.whale_data_save(dh, path.encode()))
+
+    def data_load(self, mh: int, path: str) -> int:
+        """whale_data_load: a data handle from an arena cache written for the same species tree and slicing."""
+        h = C.c_void_p()
+        self.check(self.L.whale_data_load(mh, path.encode(), C.byref(h)))
         return h.value
 
     def read_ale(self, mh, model, files, n_threads=0):
