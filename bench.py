@@ -321,7 +321,11 @@ def main():
         "kernels_ms": {"k_tables": float(kms[:, 0].mean()), "k_dp": dp_ms, "k_reduce": float(kms[:, 2].mean()),
                        "k_reduce_note": "the reduction runs in the tail of k_dp; this is the gap to the step's end event",
                        "step_events": float(step_ms.mean()), "wall_per_step_incl_flush": 1e3 * wall / K},
-        "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+        "roofline": {"bound": "fp64",
+                     "bound_note": "BASELINE.json's metric asks for the fp64 (CUDA-core FMA) roofline: the DP is an fp64 "
+                                   "gather-multiply-accumulate that neither streams HBM (see roofline_hbm) nor maps to "
+                                   "tensor cores",
+                     "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": ach_tf / fp64_peak, "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_dp<128,4>",
                      "flops_per_launch": flops, "peak_source": "whale_fp64_peak DFMA microbenchmark, this GPU, this run"},
         "roofline_hbm": {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s",
