@@ -237,3 +237,21 @@ def test_emu_arena_cache_round_trip(L, tmp_path):
             W.load_arena(path, w)
     finally:
         wlib.use(None)
+
+
+def test_emu_odd_row_stride_variant():
+    """The WHALE_ODD_STRIDE build (rows of even K padded to K+1 doubles per cell against shared-memory bank conflicts;
+    an experiment for round 2, off in the product build) must give the same numbers: known answer, 37-parameter
+    gradient with chunks, constant-rates WGD model, MUL tree, kept ℓ and backtracking."""
+    L2 = wlib.Lib(os.path.join(ROOT, "tests", "emu", "libwhalecuda_emu_oddstride.so"))
+    g = run_parity(L2, "c1_maxn5")
+    assert g["tot_none"][0] == pytest.approx(-60.96367806571888, rel=1e-12)
+    run_parity(L2, "c1_example1", sel=[0, 3], conds=["root"])
+    run_parity(L2, "const_wgdturing", sel=[1, 7], conds=["nonextinct"])
+    run_parity(L2, "mul_tree", sel=[2], conds=["root"])
+    _check_backtrack(L2, "const_wgdturing", [2])
+    g = load_golden("c1_example1")
+    mh = L2.model_create(golden_model(g))
+    dh = L2.data_create(mh, golden_fams(g, [3]))
+    L2.logpdf_grad(mh, dh, g["xs"][2], g["m_pleaf"], 1, keep_ell=True)
+    np.testing.assert_allclose(L2.ell_get(dh, 0), g["ell_3"], rtol=1e-11, atol=0)

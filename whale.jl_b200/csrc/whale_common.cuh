@@ -63,6 +63,14 @@ constexpr int TABLES_NT = 128;  // host-thread emulation: keep the thread count 
 #else
 constexpr int TABLES_NT = 512;
 #endif
+// Row stride (doubles) of a branch row with K components per cell.  WHALE_ODD_STRIDE (experiment, default off) pads even
+// K to K+1 so that cells no longer collide on shared-memory banks in the slice gathers (K = 4: cells ≡ mod 4 share
+// banks, 2.1 wavefronts per ideal one — profiles/r1_ncu_k_dp_v8_summary.txt).  Off: RS(K) is K, the code is unchanged.
+#ifdef WHALE_ODD_STRIDE
+#define RS(K) ((K) | 1)
+#else
+#define RS(K) (K)
+#endif
 constexpr int MAXPLAN = 64;  // tangent plans per data handle: [0] value only, [1..] gradient (parameter chunks)
 
 // Tree shapes for the closed form of leaf branches.  On a leaf branch e every leaf clade has the same

@@ -185,10 +185,10 @@ __device__ __forceinline__ LaneSK load_lane(const Slot* s_slots, int nslots, con
             w.kb = g * KC;
             w.gsz = 1 << sl.glog;
             w.lead = (s & (w.gsz - 1)) == 0;
-            w.c0k = (int)sl.cell * K;
+            w.c0k = (int)sl.cell * RS(K);
             w.cnt = sl.cnt; w.first = sl.first;
-            if (w.cnt > 0) { const Ent en = s_dents[w.first]; w.a1 = en.i1 * K; w.a2 = en.i2 * K; w.pa = en.p; }
-            if (w.cnt > 1) { const Ent en = s_dents[w.first + w.gsz]; w.b1 = en.i1 * K; w.b2 = en.i2 * K; w.pb = en.p; }
+            if (w.cnt > 0) { const Ent en = s_dents[w.first]; w.a1 = en.i1 * RS(K); w.a2 = en.i2 * RS(K); w.pa = en.p; }
+            if (w.cnt > 1) { const Ent en = s_dents[w.first + w.gsz]; w.b1 = en.i1 * RS(K); w.b2 = en.i2 * RS(K); w.pb = en.p; }
         }
     }
     return w;
@@ -227,7 +227,7 @@ __device__ __forceinline__ void lane_partial(const LaneSK& w, const double* __re
         for (int j = 0; j < KC; j++) {
             double r0, rk;
             term_sum<false>(s_dents, (uint32_t)(w.first + 2 * w.gsz), (uint32_t)(w.first + w.cnt * w.gsz), (uint32_t)w.gsz,
-                            src, K, min(w.kb + j, K - 1), src, K, min(w.kb + j, K - 1), r0, rk);
+                            src, RS(K), min(w.kb + j, K - 1), src, RS(K), min(w.kb + j, K - 1), r0, rk);
             if (j == 0) s0 += r0;
             sk[j] += rk;
         }
@@ -258,7 +258,7 @@ __device__ __forceinline__ void lane_finish(const LaneSK& w, int wg, double (&pa
             if (k < K) {
                 const double r = k == 0 ? fma(c0.x, o0, part[j]) : fma(c0.x, ok[j], fma(ck[j].x, o0, part[j]));
                 dst[w.c0k + k] = r;
-                if (ellp && k == 0) ellp[(size_t)i * C + w.c0k / K] = r;
+                if (ellp && k == 0) ellp[(size_t)i * C + w.c0k / RS(K)] = r;
             }
         }
     }
@@ -388,8 +388,8 @@ __device__ __forceinline__ LaneWork<K> load_work(const Slot* s_slots, int nslots
         const Slot sl = s_slots[sidx];
         w.cell = sl.cell == 0xFFFFu ? -1 : (int)sl.cell;
         w.cnt = sl.cnt; w.gsz = 1 << sl.glog; w.first = sl.first;
-        if (w.cnt > 0) { const Ent en = s_dents[w.first]; w.a1 = en.i1 * K; w.a2 = en.i2 * K; w.pa = en.p; }
-        if (w.cnt > 1) { const Ent en = s_dents[w.first + w.gsz]; w.b1 = en.i1 * K; w.b2 = en.i2 * K; w.pb = en.p; }
+        if (w.cnt > 0) { const Ent en = s_dents[w.first]; w.a1 = en.i1 * RS(K); w.a2 = en.i2 * RS(K); w.pa = en.p; }
+        if (w.cnt > 1) { const Ent en = s_dents[w.first + w.gsz]; w.b1 = en.i1 * RS(K); w.b2 = en.i2 * RS(K); w.pb = en.p; }
     }
     return w;
 }
@@ -421,7 +421,7 @@ __device__ __forceinline__ void slice_pass(const LaneWork<K>& w, int wg, bool tw
     if (w.cnt > 1) accum<K>(src, w.b1, w.b2, w.pb, s);
     for (int j = 2; j < w.cnt; j++) {
         const Ent en = s_dents[w.first + j * w.gsz];
-        accum<K>(src, en.i1 * K, en.i2 * K, en.p, s);
+        accum<K>(src, en.i1 * RS(K), en.i2 * RS(K), en.p, s);
     }
     for (int step = 1; step < wg; step <<= 1) {
 #pragma unroll
@@ -446,7 +446,7 @@ __device__ __forceinline__ void slice_pass(const LaneWork<K>& w, int wg, bool tw
     if (more) {
         for (int j = 2; j < w.cnt; j++) {
             const Ent en = s_dents[w.first + j * w.gsz];
-            accum<K>(src, en.i1 * K, en.i2 * K, en.p, s);
+            accum<K>(src, en.i1 * RS(K), en.i2 * RS(K), en.p, s);
         }
     }
     // team reduction: lane j adds lane j+step while step is inside its own team.  The mask multiplies instead of
@@ -461,7 +461,7 @@ __device__ __forceinline__ void slice_pass(const LaneWork<K>& w, int wg, bool tw
     // their latency hides behind the shuffles; every lane loads (valid addresses), only leaders use them.  (Letting
     // the non-leaders read one broadcast cell instead of their own measured 1 % slower.)
     const bool lead = w.cell >= 0 && (sidx & (w.gsz - 1)) == 0;
-    const int cK = max(w.cell, 0) * K;
+    const int cK = max(w.cell, 0) * RS(K);
     double2 pk[K];
     double o[K];
 #pragma unroll
@@ -484,14 +484,14 @@ __device__ __forceinline__ void slice_pass(const LaneWork<K>& w, int wg, bool tw
     if (w.cell >= 0 && (sidx & (w.gsz - 1)) == 0) {  // team leader: ℓ_i = ϕ_i ℓ_{i−1} + ψ_i Σ  (with tangents)
         const int c = w.cell;
         const double2 c0 = ppi[0];
-        const double o0 = src[c * K];
+        const double o0 = src[c * RS(K)];
         const double r0 = fma(c0.x, o0, c0.y * s[0]);
-        dst[c * K] = r0;
+        dst[c * RS(K)] = r0;
         if (ellp) ellp[(size_t)i * C + c] = r0;
 #pragma unroll
         for (int k = 1; k < K; k++) {
             const double2 ck = ppi[k];
-            dst[c * K + k] = fma(c0.x, src[c * K + k], fma(c0.y, s[k], fma(ck.x, o0, ck.y * s[0])));
+            dst[c * RS(K) + k] = fma(c0.x, src[c * RS(K) + k], fma(c0.y, s[k], fma(ck.x, o0, ck.y * s[0])));
         }
     }
 }
@@ -721,13 +721,13 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
                     const Ent en = sent[t];
                     v = fma(en.p, W[en.i1 * Kmax + k], v);
                 }
-                fin[i] = v;
+                fin[c * RS(K) + k] = v;
             }
             continue;
         }
         if (R.nslots > HEAVY_SLOTS && !(R.nonleaf == 0 && A.skip_leaf)) continue;  // heavy branch: whole CTA, below
         if (R.nonleaf == 0 && A.skip_leaf) {  // family-independent: ℓ_n = leafℙ·Πϕ_i from k_tables
-            for (int i = lane; i < C * K; i += 32) fin[i] = PL.leaf[e * Kmax + (i % K)];
+            for (int i = lane; i < C * K; i += 32) fin[(i / K) * RS(K) + (i % K)] = PL.leaf[e * Kmax + (i % K)];
             continue;
         }
         double* ellp = ell_of(e);
@@ -741,7 +741,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         for (int i = lane; i < C * K; i += 32) {
             const int c = i / K, k = i - c * K;
             const double v = (c < nleafc && k == 0) ? M.leafP[e] : 0.0;
-            cur[i] = v;
+            cur[c * RS(K) + k] = v;
             if (ellp && k == 0) ellp[c] = v;
         }
         stage_wait();
@@ -779,7 +779,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         for (int i = tid; i < C * K; i += NT) {
             const int c = i / K, k = i - c * K;
             const double v = (c < nleafc && k == 0) ? M.leafP[e] : 0.0;
-            cur[i] = v;
+            cur[c * RS(K) + k] = v;
             if (ellp && k == 0) ellp[c] = v;
         }
         stage_wait();
@@ -864,15 +864,15 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
                 const int c = u / K, k = u - c * K;
                 const int kf = mapF[k];
                 double s0, sk;
-                term_sum<false>(s_dents, s_dptr[c], s_dptr[c + 1], 1u, finF, KF, kf, finF, KF, kf, s0, sk);
-                const double u0 = finF[c * KF];
+                term_sum<false>(s_dents, s_dptr[c], s_dptr[c + 1], 1u, finF, RS(KF), kf, finF, RS(KF), kf, s0, sk);
+                const double u0 = finF[c * RS(KF)];
                 double r;
                 if (k == 0) r = fma(cy0, s0, cx0 * u0);
                 else {
-                    const double uk = kf >= 0 ? finF[c * KF + kf] : 0.0;
+                    const double uk = kf >= 0 ? finF[c * RS(KF) + kf] : 0.0;
                     r = fma(cy0, sk, fma(cx0, uk, fma(PL.cy[e * Kmax + k], s0, PL.cx[e * Kmax + k] * u0)));
                 }
-                cur[u] = r;
+                cur[c * RS(K) + k] = r;
                 if (ellp && k == 0) ellp[c] = r;
             }
             __syncthreads();
@@ -893,10 +893,10 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
                 const double efk = (k > 0 && kf >= 0) ? epsF[kf] : 0.0;
                 const double egk = (k > 0 && kg >= 0) ? epsG[kg] : 0.0;
                 double s0, sk, l0, lk;
-                term_sum<false>(s_tents, s_tptr[c], s_tptr[c + 1], 1u, finF, KF, kf, finG, KG, kg, s0, sk);
-                loss_term(s_lossF[c], s_lossG[c], finF, KF, kf, finG, KG, kg, ef0, efk, eg0, egk, k == 0 ? 0.0 : 1.0, l0, lk);
+                term_sum<false>(s_tents, s_tptr[c], s_tptr[c + 1], 1u, finF, RS(KF), kf, finG, RS(KG), kg, s0, sk);
+                loss_term(s_lossF[c], s_lossG[c], finF, RS(KF), kf, finG, RS(KG), kg, ef0, efk, eg0, egk, k == 0 ? 0.0 : 1.0, l0, lk);
                 const double r = k == 0 ? s0 + l0 : sk + lk;
-                cur[u] = r;
+                cur[c * RS(K) + k] = r;
                 if (ellp && k == 0) ellp[c] = r;
             }
             __syncthreads();
@@ -951,8 +951,8 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
                     c = c0 + cc; k = gi - cc * K;
                     kf = mapF[k]; kg = mapG[k];
                     double a0, ak, b0, bk;
-                    term_sum<false>(l_dents, s_dptr[c] - da + j, s_dptr[c + 1] - da, (uint32_t)G, fin, K, k, fin, K, k, a0, ak);
-                    term_sum<false>(l_tents, s_tptr[c] - ta + j, s_tptr[c + 1] - ta, (uint32_t)G, finF, KF, kf, finG, KG, kg, b0, bk);
+                    term_sum<false>(l_dents, s_dptr[c] - da + j, s_dptr[c + 1] - da, (uint32_t)G, fin, RS(K), k, fin, RS(K), k, a0, ak);
+                    term_sum<false>(l_tents, s_tptr[c] - ta + j, s_tptr[c + 1] - ta, (uint32_t)G, finF, RS(KF), kf, finG, RS(KG), kg, b0, bk);
                     if (k == 0) v = fma(cx0, a0, cy0 * b0);
                     else v = fma(cx0, ak, fma(cy0, bk, fma(PL.cx[e * Kmax + k], a0, PL.cy[e * Kmax + k] * b0)));
                 }
@@ -961,19 +961,19 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
                     const double efk = (k > 0 && kf >= 0) ? epsF[kf] : 0.0;
                     const double egk = (k > 0 && kg >= 0) ? epsG[kg] : 0.0;
                     double l0, lk;
-                    loss_term(s_lossF[c], s_lossG[c], finF, KF, kf, finG, KG, kg, ef0, efk, eg0, egk, k == 0 ? 0.0 : 1.0, l0, lk);
+                    loss_term(s_lossF[c], s_lossG[c], finF, RS(KF), kf, finG, RS(KG), kg, ef0, efk, eg0, egk, k == 0 ? 0.0 : 1.0, l0, lk);
                     if (k == 0) v = fma(cy0, l0, v);
                     else v = fma(cy0, lk, fma(PL.cy[e * Kmax + k], l0, v));
-                    fin[c * K + k] = v;
+                    fin[c * RS(K) + k] = v;
                     if (ellp && k == 0) ellp[c] = v;
                 }
             }
             __syncthreads();
         }
         if (tid < K) {  // log L and its gradient (src/core.jl:35-36)
-            const double Lv = fin[(C - 1) * K];
+            const double Lv = fin[(C - 1) * RS(K)];
             double o;
-            if (Lv > 0.0) o = tid == 0 ? log(Lv) : fin[(C - 1) * K + tid] / Lv;
+            if (Lv > 0.0) o = tid == 0 ? log(Lv) : fin[(C - 1) * RS(K) + tid] / Lv;
             else o = tid == 0 ? -dinf() : 0.0;
             A.out_fam[(size_t)fam * K + tid] = o;
         }

@@ -460,7 +460,7 @@ static size_t set_budgets(whale_data* D, int g, const Plan& pl) {
         const uint32_t prod = 0;
         size_t stg = 0;
         for (int e = 0; e < nn; e++) {
-            const uint32_t K = (uint32_t)pl.K[e], ck = Cs[e] * K;
+            const uint32_t K = (uint32_t)pl.K[e], ck = Cs[e] * (uint32_t)RS(K);
             if (s16[e] > 0)  // lists + (inner nodes with K <= 8) the ϕ/ψ rows
                 stg = std::max(stg, (size_t)s16[e] + (K <= 8 ? (size_t)(m->nsl[e] + 1) * K : 0));
             if (m->kind[e] == WHALE_LEAF) {
@@ -475,7 +475,7 @@ static size_t set_budgets(whale_data* D, int g, const Plan& pl) {
         std::vector<int> roff(nn + 1);
         const int rows = place_rows(nn, (int)m->leafnodes.size(), m->leafnodes.data(), (int)m->inner.size(), m->inner.data(),
                                     m->child0.data(), m->child1.data(), m->kind.data(),
-                                    [&](int e2) { return (int)(Cs[e2] * (uint32_t)pl.K[e2]); }, roff.data());
+                                    [&](int e2) { return (int)(Cs[e2] * (uint32_t)RS(pl.K[e2])); }, roff.data());
         H.rows_len[g] = even((uint32_t)rows);
         for (int e = 0; e < nn; e++) D->roff_host[g][(size_t)f * nn + e] = (uint32_t)roff[e];
         H.scr_len[g] = scr;
