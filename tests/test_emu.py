@@ -239,11 +239,26 @@ def test_emu_arena_cache_round_trip(L, tmp_path):
         wlib.use(None)
 
 
-def test_emu_odd_row_stride_variant():
-    """The WHALE_ODD_STRIDE build (rows of even K padded to K+1 doubles per cell against shared-memory bank conflicts;
-    an experiment for round 2, off in the product build) must give the same numbers: known answer, 37-parameter
-    gradient with chunks, constant-rates WGD model, MUL tree, kept ℓ and backtracking."""
+def test_emu_odd_row_stride_variant(tmp_path):
+    """The round-2 experiment build — WHALE_ODD_STRIDE (rows of even K padded to K+1 doubles per cell against
+    shared-memory bank conflicts) and WHALE_TAB_PROJ (division-free projective chain over the tree levels in k_tables),
+    both off in the product build — must give the same numbers: slice tables, known answer, 37-parameter gradient,
+    constant-rates WGD model, MUL tree, kept ℓ, backtracking, the rates around the critical case and the
+    Nowhere-extinct condition."""
     L2 = wlib.Lib(os.path.join(ROOT, "tests", "emu", "libwhalecuda_emu_oddstride.so"))
+    for name in ("c1_example1", "const_wgdturing"):
+        gg = load_golden(name)
+        mh_ = L2.model_create(golden_model(gg))
+        nrow = int((gg["m_nslices"] + 1).sum())
+        for xi, x in enumerate(gg["xs"]):
+            np.testing.assert_allclose(np.stack(L2.slices(mh_, x, gg["m_pleaf"], nrow), 1), gg["slices"][xi], rtol=1e-12)
+    from conftest import near_critical_vs_oracle, nowhere_condition_vs_oracle
+    wlib.use(L2)
+    try:
+        near_critical_vs_oracle(tmp_path, n_fam=2)
+    finally:
+        wlib.use(None)
+    nowhere_condition_vs_oracle(L2)
     g = run_parity(L2, "c1_maxn5")
     assert g["tot_none"][0] == pytest.approx(-60.96367806571888, rel=1e-12)
     run_parity(L2, "c1_example1", sel=[0, 3], conds=["root"])

@@ -414,7 +414,12 @@ static size_t smem_need(const whale_model* m, const FamHdr& h, int plan, int Kma
 
 static size_t tables_smem(const whale_model* m, const Plan& pl, bool shapes) {  // mirrors the carve-ups in k_tables
     const size_t nn = m->nn, nlvl = m->lvl_off.size() - 1;
-    size_t need = (3 * nn + m->P + 6 * nn * pl.Kmax) * sizeof(double) + (11 * nn + nlvl + 1) * sizeof(int) +
+    #ifdef WHALE_TAB_PROJ
+    const size_t ndbl = 9;  // + the denominators of ϵ_0 and of the last ϵ, and ϵ_0 itself
+#else
+    const size_t ndbl = 6;
+#endif
+    size_t need = (3 * nn + m->P + ndbl * nn * pl.Kmax) * sizeof(double) + (11 * nn + nlvl + 1) * sizeof(int) +
                   nn * 2 * pl.Kmax * sizeof(int16_t) + nn * pl.Kmax + 16;
     if (shapes)  // a leaf-shape CTA keeps its branch's projective and (ϕ, ψ) rows in shared memory
         for (int e : m->leafnodes) need = std::max(need, 2 * (size_t)(m->nsl[e] + 1) * pl.K[e] * sizeof(double2));
