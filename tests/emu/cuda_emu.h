@@ -1,8 +1,8 @@
 // TEST INFRASTRUCTURE ONLY — a minimal CUDA-on-host-threads shim.
 //
 // `make -C tests/emu` compiles whale.jl_b200/csrc/whalecuda.cu as plain C++ with -DWHALE_EMU against this
-// header into tests/emu/libwhalecuda_emu.so.  Each CTA runs as blockDim.x host threads with a real
-// barrier for __syncthreads(); CTAs run one after another.  It exists so the packer and the kernel logic
+// header into tests/emu/libwhalecuda_emu.so.  Each CTA runs as blockDim.x cooperative fibers on one host
+// thread (a barrier yields to a round-robin scheduler); a few host threads run independent CTAs concurrently.  It exists so the packer and the kernel logic
 // can be debugged (and regression-tested by `pytest -m "not gpu"`) on the GPU-less build container.
 // It is NOT a fallback: the package only ever loads whale.jl_b200/libwhalecuda.so, which requires a GPU.
 #pragma once
@@ -17,6 +17,7 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <ucontext.h>
 #include <vector>
 
 #define __global__
@@ -27,7 +28,7 @@
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
 #define __restrict__
-#define __shared__ static
+#define __shared__ static thread_local
 
 struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
 inline thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -53,82 +54,128 @@ using std::max;
 using std::isfinite;
 
 namespace emu {
-struct Barrier {
-    std::mutex mu; std::condition_variable cv; int n = 0, count = 0, gen = 0;
-    void wait() {
-        std::unique_lock<std::mutex> lk(mu);
-        int g = gen;
-        if (++count == n) { count = 0; gen++; cv.notify_all(); }
-        else cv.wait(lk, [&] { return g != gen; });
-    }
+// One CTA = blockDim.x cooperative fibers (ucontext) on ONE host thread; a barrier is "arrive, then yield to the
+// round-robin scheduler until the generation changes".  CTAs are independent, so a small pool of host threads
+// runs them concurrently; everything a CTA shares (barriers, shared memory, __shared__ statics) is thread_local.
+struct Barrier { int n = 0, count = 0, gen = 0; };
+struct Cta {
+    ucontext_t sched;
+    std::vector<ucontext_t> ctx;
+    std::vector<unsigned char> done;
+    std::vector<int> or_phase;
+    int cur = 0;
 };
-inline Barrier* g_bar = nullptr;
-inline std::vector<Barrier>* g_wbar = nullptr;
-inline unsigned char* g_smem = nullptr;
-inline void launch(int grid, int block, size_t smem, const std::function<void()>& body) {
+inline thread_local Cta* g_cta = nullptr;
+inline thread_local Barrier* g_bar = nullptr;
+inline thread_local std::vector<Barrier>* g_wbar = nullptr;
+inline thread_local unsigned char* g_smem = nullptr;
+inline thread_local const std::function<void()>* g_body = nullptr;
+inline void yield() {
+    Cta* c = g_cta;
+    const int me = c->cur;
+    swapcontext(&c->ctx[me], &c->sched);
+}
+inline void bar_wait(Barrier& b) {
+    const int g = b.gen;
+    if (++b.count == b.n) { b.count = 0; b.gen++; return; }
+    while (b.gen == g) yield();
+}
+inline void fiber_main() {
+    Cta* c = g_cta;
+    const int me = c->cur;
+    (*g_body)();
+    c->done[me] = 1;
+    swapcontext(&c->ctx[me], &c->sched);
+}
+constexpr size_t kFiberStack = 256 << 10;
+inline void run_cta(int b, int grid, int block, size_t smem, const std::function<void()>& body,
+                    std::vector<unsigned char>& stacks) {
     std::vector<unsigned char> sm(smem + 64);
     Barrier bar; bar.n = block;
-    g_bar = &bar;
     std::vector<Barrier> wb((block + 31) / 32);
     for (size_t w = 0; w < wb.size(); w++) wb[w].n = std::min(32, block - (int)w * 32);
-    g_wbar = &wb;
+    Cta cta;
+    cta.ctx.resize(block); cta.done.assign(block, 0); cta.or_phase.assign(block, 0);
+    g_cta = &cta; g_bar = &bar; g_wbar = &wb; g_body = &body;
     g_smem = (unsigned char*)(((uintptr_t)sm.data() + 15) & ~(uintptr_t)15);
-    for (int b = 0; b < grid; b++) {
-        std::vector<std::thread> th;
-        for (int t = 0; t < block; t++)
-            th.emplace_back([&, t, b] {
-                threadIdx.x = t; blockIdx.x = b; blockDim.x = block; gridDim.x = grid;
-                body();
-            });
-        for (auto& x : th) x.join();
+    blockIdx.x = b; blockDim.x = block; gridDim.x = grid;
+    for (int t = 0; t < block; t++) {
+        getcontext(&cta.ctx[t]);
+        cta.ctx[t].uc_stack.ss_sp = stacks.data() + (size_t)t * kFiberStack;
+        cta.ctx[t].uc_stack.ss_size = kFiberStack;
+        cta.ctx[t].uc_link = &cta.sched;
+        makecontext(&cta.ctx[t], (void (*)())fiber_main, 0);
     }
+    for (int live = block; live > 0;) {
+        for (int t = 0; t < block; t++) {
+            if (cta.done[t] == 2) continue;
+            cta.cur = t; threadIdx.x = t;
+            swapcontext(&cta.sched, &cta.ctx[t]);
+            if (cta.done[t] == 1) { cta.done[t] = 2; live--; }
+        }
+    }
+    g_cta = nullptr;
+}
+inline void launch(int grid, int block, size_t smem, const std::function<void()>& body) {
+    int nw = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("WHALE_EMU_THREADS")) nw = atoi(e);
+    nw = std::max(1, std::min(nw, grid));
+    std::atomic<int> next{0};
+    auto worker = [&] {
+        std::vector<unsigned char> stacks((size_t)block * kFiberStack);
+        for (int b; (b = next.fetch_add(1)) < grid;) run_cta(b, grid, block, smem, body, stacks);
+    };
+    if (nw == 1) { worker(); return; }
+    std::vector<std::thread> th;
+    for (int i = 0; i < nw; i++) th.emplace_back(worker);
+    for (auto& x : th) x.join();
 }
 }  // namespace emu
 namespace emu {
-inline double g_shfl[64][32];  // per-warp exchange buffer
+inline thread_local double g_shfl[64][32];  // per-warp exchange buffer
 // warp shuffle (all 32 lanes of the warp must call it, as on the device with a full mask)
 inline double shfl_down(double v, int delta) {
     const int w = threadIdx.x / 32, l = threadIdx.x % 32;
     g_shfl[w][l] = v;
-    (*g_wbar)[w].wait();
+    bar_wait((*g_wbar)[w]);
     const double r = (l + delta < 32) ? g_shfl[w][l + delta] : v;
-    (*g_wbar)[w].wait();
+    bar_wait((*g_wbar)[w]);
     return r;
 }
 inline bool warp_any(bool p) {
     const int w = threadIdx.x / 32, l = threadIdx.x % 32;
     g_shfl[w][l] = p ? 1.0 : 0.0;
-    (*g_wbar)[w].wait();
+    bar_wait((*g_wbar)[w]);
     bool r = false;
     for (int i = 0; i < (*g_wbar)[w].n; i++) r = r || g_shfl[w][i] != 0.0;
-    (*g_wbar)[w].wait();
+    bar_wait((*g_wbar)[w]);
     return r;
 }
 inline double shfl_idx(double v, int src) {
     const int w = threadIdx.x / 32, l = threadIdx.x % 32;
     g_shfl[w][l] = v;
-    (*g_wbar)[w].wait();
+    bar_wait((*g_wbar)[w]);
     const double r = g_shfl[w][src & 31];
-    (*g_wbar)[w].wait();
+    bar_wait((*g_wbar)[w]);
     return r;
 }
 }  // namespace emu
-inline void __syncthreads() { emu::g_bar->wait(); }
-namespace emu { inline int g_or_flag[2] = {0, 0}; }
+inline void __syncthreads() { emu::bar_wait(*emu::g_bar); }
+namespace emu { inline thread_local int g_or_flag[2] = {0, 0}; }
 inline int __syncthreads_or(int p) {  // barrier + OR of the predicate over the CTA (double-buffered flag)
-    static thread_local int phase = 0;
+    int& phase = emu::g_cta->or_phase[threadIdx.x];
     const int ph = phase; phase ^= 1;
-    if (p) __atomic_store_n(&emu::g_or_flag[ph], 1, __ATOMIC_SEQ_CST);
-    emu::g_bar->wait();
-    const int r = __atomic_load_n(&emu::g_or_flag[ph], __ATOMIC_SEQ_CST);
-    emu::g_bar->wait();
+    if (p) emu::g_or_flag[ph] = 1;
+    emu::bar_wait(*emu::g_bar);
+    const int r = emu::g_or_flag[ph];
+    emu::bar_wait(*emu::g_bar);
     if (threadIdx.x == 0) emu::g_or_flag[ph] = 0;
-    emu::g_bar->wait();
+    emu::bar_wait(*emu::g_bar);
     return r;
 }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
-inline void __syncwarp() { (*emu::g_wbar)[threadIdx.x / 32].wait(); }
+inline void __syncwarp() { emu::bar_wait((*emu::g_wbar)[threadIdx.x / 32]); }
 #define EXTERN_SHARED(name) unsigned char* name = emu::g_smem
 
 // ---- runtime API subset ----
