@@ -80,7 +80,9 @@ def test_emu_backtrack_matches_oracle(L):
 def test_emu_parameter_chunks(L, monkeypatch):
     """Families whose full-tangent working set exceeds the shared-memory goal get their gradient in several
     passes over parameter chunks; force that with a tiny goal and compare with the oracle (37 parameters)."""
-    monkeypatch.setenv("WHALE_SMEM_GOAL", "25000")  # -> 6 passes (a 6000-byte goal gives 37 and takes two minutes here)
+    monkeypatch.setenv("WHALE_SMEM_GOAL", "25000")  # -> 6 passes
+    run_parity(L, "c1_example1", sel=[3], conds=["root"])
+    monkeypatch.setenv("WHALE_SMEM_GOAL", "6000")  # -> one pass per parameter (37)
     run_parity(L, "c1_example1", sel=[3], conds=["root"])
 
 
@@ -261,8 +263,8 @@ def test_emu_odd_row_stride_variant(tmp_path):
     nowhere_condition_vs_oracle(L2)
     g = run_parity(L2, "c1_maxn5")
     assert g["tot_none"][0] == pytest.approx(-60.96367806571888, rel=1e-12)
-    run_parity(L2, "c1_example1", sel=[3], conds=["root"])
-    run_parity(L2, "const_wgdturing", sel=[1], conds=["nonextinct"])
+    run_parity(L2, "c1_example1", sel=[0, 3], conds=["root"])
+    run_parity(L2, "const_wgdturing", sel=[1, 7], conds=["nonextinct"])
     run_parity(L2, "mul_tree", sel=[2], conds=["root"])
     _check_backtrack(L2, "const_wgdturing", [2])
     g = load_golden("c1_example1")
