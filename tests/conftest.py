@@ -201,3 +201,65 @@ def near_critical_vs_oracle(tmp_path, n_fam=3, seed=5):
         d_ = abs(lam - mu)
         np.testing.assert_allclose(gg, wg, rtol=1e-5 if 1e-6 < d_ < 1e-3 else 1e-9, atol=1e-9 * np.abs(wg).max(),
                                    err_msg=f"lam {lam} mu {mu}")
+
+
+def synthetic_c2_shape_vs_oracle(tmp_path, n_fam=64):
+    """BASELINE config 1/2 shapes against the oracle through the package API (library chosen with lib.use)."""
+    import whale_jl_b200 as W
+    from whale_jl_b200 import synth
+    from oracle import whale_oracle as wo, flat
+    d = synth.generate(str(tmp_path / "c2"), n_fam, seed=2)
+    w = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), synth.c1_species_tree(), 0.05)
+    ccd = W.read_ale(d, w)
+    ll, grad = W.logpdf_and_gradient(w, ccd)
+    ow = wo.WhaleModel(wo.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), wo.c1_tree(), 0.05)
+    fm, ff = flat.FlatModel(ow), flat.FlatFams(wo.read_ale(d, ow), len(ow))
+    tot, _, og, _ = flat.logpdf(fm, ff, grad=True)
+    assert ll == pytest.approx(tot, rel=1e-9)
+    np.testing.assert_allclose(grad, og, rtol=1e-9)
+    # branch-wise rates (BASELINE config 2 parameterisation, P = 37)
+    rng = np.random.default_rng(3)
+    r = W.DLWGD(lam=list(rng.normal(np.log(0.15), 0.3, 17)), mu=list(rng.normal(np.log(0.15), 0.3, 17)),
+                q=[0.2, 0.1], eta=0.67)
+    wb = W.WhaleModel(r, synth.c1_species_tree(), 0.05)
+    ccdb = W.read_ale(d, wb)
+    ll, grad = W.logpdf_and_gradient(wb, ccdb)
+    owb = wo.WhaleModel(wo.DLWGD(lam=r.lam, mu=r.mu, q=[0.2, 0.1], eta=0.67), wo.c1_tree(), 0.05)
+    fm, ff = flat.FlatModel(owb), flat.FlatFams(wo.read_ale(d, owb), len(owb))
+    tot, _, og, _ = flat.logpdf(fm, ff, grad=True)
+    assert ll == pytest.approx(tot, rel=1e-9)
+    np.testing.assert_allclose(grad, og, rtol=1e-9, atol=1e-9 * np.abs(og).max())
+
+
+def c4_shape_vs_oracle(tmp_path, n_fam=3, branch_rates=True):
+    """BASELINE config 3 shape (30 taxa + 5 WGD, ~2,000 clades) against the oracle through the package API."""
+    import whale_jl_b200 as W
+    from whale_jl_b200 import synth, newick
+    from oracle import whale_oracle as wo, flat
+    tree = synth.c4_species_tree()
+    nws = newick.nwstr(tree, True) + ";"
+    d = synth.generate(str(tmp_path / "c4"), n_fam, seed=4, tree=synth.c4_species_tree(), **synth.C4_FAMILY)
+    q = [0.2, 0.1, 0.2, 0.1, 0.2]
+    w = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=q, eta=0.67), newick.readnw(nws), 0.05)
+    ccd = W.read_ale(d, w)
+    assert min(len(x.nleaf) for x in ccd) > 1500
+    ll, grad = W.logpdf_and_gradient(w, ccd)
+    ow = wo.WhaleModel(wo.ConstantDLWGD(lam=0.2, mu=0.3, q=q, eta=0.67), wo.readnw(nws), 0.05)
+    fm, ff = flat.FlatModel(ow), flat.FlatFams(wo.read_ale(d, ow), len(ow))
+    tot, _, og, _ = flat.logpdf(fm, ff, grad=True)
+    assert ll == pytest.approx(tot, rel=1e-9)
+    np.testing.assert_allclose(grad, og, rtol=1e-9, atol=1e-9 * np.abs(og).max())
+    assert W.logpdf(w, ccd) == pytest.approx(tot, rel=1e-9)
+    if not branch_rates:
+        return
+    nr = 58  # non-WGD, non-root nodes carry their own rates; the root's are unused (NaN-safe)
+    rng = np.random.default_rng(5)
+    r = W.DLWGD(lam=list(rng.normal(np.log(0.15), 0.3, nr + 1)), mu=list(rng.normal(np.log(0.15), 0.3, nr + 1)), q=q, eta=0.67)
+    wb = W.WhaleModel(r, newick.readnw(nws), 0.05)
+    ccdb = W.read_ale(d, wb)
+    ll, grad = W.logpdf_and_gradient(wb, ccdb)
+    owb = wo.WhaleModel(wo.DLWGD(lam=r.lam, mu=r.mu, q=q, eta=0.67), wo.readnw(nws), 0.05)
+    fm, ff = flat.FlatModel(owb), flat.FlatFams(wo.read_ale(d, owb), len(owb))
+    tot, _, og, _ = flat.logpdf(fm, ff, grad=True)
+    assert ll == pytest.approx(tot, rel=1e-9)
+    np.testing.assert_allclose(grad, og, rtol=1e-9, atol=1e-9 * np.abs(og).max())

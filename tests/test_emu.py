@@ -156,6 +156,28 @@ def test_emu_near_critical_rates(L, tmp_path):
         wlib.use(None)
 
 
+def test_emu_synthetic_c2_shape(L, tmp_path):
+    """BASELINE config 1/2 shapes (~200-clade families: full 125-lane rows, constant and branch-wise rates)."""
+    from conftest import synthetic_c2_shape_vs_oracle
+    wlib.use(L)
+    try:
+        synthetic_c2_shape_vs_oracle(tmp_path, n_fam=12)
+    finally:
+        wlib.use(None)
+
+
+@pytest.mark.parametrize("stage_max", ["24576", "163840"])
+def test_emu_c4_shape(L, tmp_path, monkeypatch, stage_max):
+    """BASELINE config 3 shape (64 nodes, ~2,000 clades): lists read in place / staged, constant rates (P = 8)."""
+    from conftest import c4_shape_vs_oracle
+    monkeypatch.setenv("WHALE_STAGE_MAX", stage_max)
+    wlib.use(L)
+    try:
+        c4_shape_vs_oracle(tmp_path, n_fam=1, branch_rates=False)  # P = 122 chunking: GPU test; P = 37 here above
+    finally:
+        wlib.use(None)
+
+
 def test_emu_chain_tables_and_unfused_reduction():
     """The fallbacks behind WHALE_TABLES_CHAIN=1 (per-slice recurrence on every branch) and WHALE_FUSED_REDUCE=0
     (K3 as separate kernels) are process-wide switches: exercise them in a child process."""

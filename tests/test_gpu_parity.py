@@ -99,28 +99,8 @@ def test_nan_root_rates_and_neg_inf(L):
 def test_synthetic_c2_shape_vs_oracle(L, tmp_path):
     """BASELINE config 1 shape (9 taxa + 2 WGD, ~200 clades, constant rates) at a size the oracle does in
     seconds, through the package API (read_ale -> pack -> logpdf_and_gradient)."""
-    from oracle import whale_oracle as wo, flat
-    d = synth.generate(str(tmp_path / "c2"), 64, seed=2)
-    w = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), synth.c1_species_tree(), 0.05)
-    ccd = W.read_ale(d, w)
-    ll, grad = W.logpdf_and_gradient(w, ccd)
-    ow = wo.WhaleModel(wo.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), wo.c1_tree(), 0.05)
-    fm, ff = flat.FlatModel(ow), flat.FlatFams(wo.read_ale(d, ow), len(ow))
-    tot, _, og, _ = flat.logpdf(fm, ff, grad=True)
-    assert ll == pytest.approx(tot, rel=1e-9)
-    np.testing.assert_allclose(grad, og, rtol=1e-9)
-    # branch-wise rates (BASELINE config 2 parameterisation, P = 37)
-    rng = np.random.default_rng(3)
-    r = W.DLWGD(lam=list(rng.normal(np.log(0.15), 0.3, 17)), mu=list(rng.normal(np.log(0.15), 0.3, 17)),
-                q=[0.2, 0.1], eta=0.67)
-    wb = W.WhaleModel(r, synth.c1_species_tree(), 0.05)
-    ccdb = W.read_ale(d, wb)
-    ll, grad = W.logpdf_and_gradient(wb, ccdb)
-    owb = wo.WhaleModel(wo.DLWGD(lam=r.lam, mu=r.mu, q=[0.2, 0.1], eta=0.67), wo.c1_tree(), 0.05)
-    fm, ff = flat.FlatModel(owb), flat.FlatFams(wo.read_ale(d, owb), len(owb))
-    tot, _, og, _ = flat.logpdf(fm, ff, grad=True)
-    assert ll == pytest.approx(tot, rel=1e-9)
-    np.testing.assert_allclose(grad, og, rtol=1e-9, atol=1e-9 * np.abs(og).max())
+    from conftest import synthetic_c2_shape_vs_oracle
+    synthetic_c2_shape_vs_oracle(tmp_path)
 
 
 @pytest.mark.parametrize("stage_max", ["24576", "163840"])
@@ -128,34 +108,9 @@ def test_c4_shape_vs_oracle(L, tmp_path, monkeypatch, stage_max):
     """BASELINE config 3 shape: 30-taxon tree with 5 WGDs (64 nodes), CCDs of ~2,000 clades — lists too long to
     stage in shared memory (read in place) and a gradient computed in parameter chunks; constant rates (P = 8)
     and branch-wise rates (P = 122) against the oracle."""
-    from oracle import whale_oracle as wo, flat
-    from whale_jl_b200 import newick
+    from conftest import c4_shape_vs_oracle
     monkeypatch.setenv("WHALE_STAGE_MAX", stage_max)  # lists read in place (large batches) / staged (small batches)
-    tree = synth.c4_species_tree()
-    nws = newick.nwstr(tree, True) + ";"
-    d = synth.generate(str(tmp_path / "c4"), 3, seed=4, tree=synth.c4_species_tree(), **synth.C4_FAMILY)
-    q = [0.2, 0.1, 0.2, 0.1, 0.2]
-    w = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=q, eta=0.67), newick.readnw(nws), 0.05)
-    ccd = W.read_ale(d, w)
-    assert min(len(x.nleaf) for x in ccd) > 1500
-    ll, grad = W.logpdf_and_gradient(w, ccd)
-    ow = wo.WhaleModel(wo.ConstantDLWGD(lam=0.2, mu=0.3, q=q, eta=0.67), wo.readnw(nws), 0.05)
-    fm, ff = flat.FlatModel(ow), flat.FlatFams(wo.read_ale(d, ow), len(ow))
-    tot, _, og, _ = flat.logpdf(fm, ff, grad=True)
-    assert ll == pytest.approx(tot, rel=1e-9)
-    np.testing.assert_allclose(grad, og, rtol=1e-9, atol=1e-9 * np.abs(og).max())
-    assert W.logpdf(w, ccd) == pytest.approx(tot, rel=1e-9)
-    nr = 58  # non-WGD, non-root nodes carry their own rates; the root's are unused (NaN-safe)
-    rng = np.random.default_rng(5)
-    r = W.DLWGD(lam=list(rng.normal(np.log(0.15), 0.3, nr + 1)), mu=list(rng.normal(np.log(0.15), 0.3, nr + 1)), q=q, eta=0.67)
-    wb = W.WhaleModel(r, newick.readnw(nws), 0.05)
-    ccdb = W.read_ale(d, wb)
-    ll, grad = W.logpdf_and_gradient(wb, ccdb)
-    owb = wo.WhaleModel(wo.DLWGD(lam=r.lam, mu=r.mu, q=q, eta=0.67), wo.readnw(nws), 0.05)
-    fm, ff = flat.FlatModel(owb), flat.FlatFams(wo.read_ale(d, owb), len(owb))
-    tot, _, og, _ = flat.logpdf(fm, ff, grad=True)
-    assert ll == pytest.approx(tot, rel=1e-9)
-    np.testing.assert_allclose(grad, og, rtol=1e-9, atol=1e-9 * np.abs(og).max())
+    c4_shape_vs_oracle(tmp_path)
 
 
 def test_full_size_properties(L, tmp_path):
