@@ -59,7 +59,7 @@ static_assert(sizeof(Slot) == 8, "Slot must be 8 bytes");
 constexpr uint32_t HEAVY_SLOTS = 24;
 
 #ifdef WHALE_EMU
-constexpr int TABLES_NT = 128;  // host-thread emulation: keep the thread count small
+constexpr int TABLES_NT = 128;  // emulation build: keep the fiber count small
 #else
 constexpr int TABLES_NT = 512;
 #endif
