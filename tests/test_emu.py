@@ -156,6 +156,18 @@ def test_emu_near_critical_rates(L, tmp_path):
         wlib.use(None)
 
 
+def test_emu_landplant_100_families(L):
+    """docs/src/tutorial.md:103-131 fixture: 100 families of 15..1025 clades, 21 nodes, 3,765 slices (dt = 0.01)."""
+    run_parity(L, "landplant100")
+
+
+def test_emu_discretisation_fixture(L):
+    """test/runtests.jl:128-144"""
+    a = run_parity(L, "ex5_dt0.1")
+    b = run_parity(L, "ex5_dt0.01")
+    assert abs(a["tot_root"][0] - b["tot_root"][0]) < 0.1
+
+
 def test_emu_synthetic_c2_shape(L, tmp_path):
     """BASELINE config 1/2 shapes (~200-clade families: full 125-lane rows, constant and branch-wise rates)."""
     from conftest import synthetic_c2_shape_vs_oracle
