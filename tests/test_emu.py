@@ -10,7 +10,8 @@ import pytest
 from whale_jl_b200 import lib as wlib
 from conftest import ROOT, run_parity, load_golden, golden_model, golden_fams
 
-EMU = os.path.join(ROOT, "tests", "emu", "libwhalecuda_emu.so")
+# WHALE_EMU_LIB: run this file against another emulation build (tools/emu_asan.sh: AddressSanitizer)
+EMU = os.environ.get("WHALE_EMU_LIB") or os.path.join(ROOT, "tests", "emu", "libwhalecuda_emu.so")
 
 
 @pytest.fixture(scope="module")
