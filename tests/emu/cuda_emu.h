@@ -106,8 +106,23 @@ inline void run_cta(int b, int grid, int block, size_t smem, const std::function
         cta.ctx[t].uc_link = &cta.sched;
         makecontext(&cta.ctx[t], (void (*)())fiber_main, 0);
     }
+    // WHALE_EMU_SCHED=reverse|random changes the order in which the fibers run between two barriers: a result that
+    // depends on it means a missing barrier (or a warp-lockstep assumption) in the kernel
+    static const int sched = [] {
+        const char* e = getenv("WHALE_EMU_SCHED");
+        return !e ? 0 : !strcmp(e, "reverse") ? 1 : !strcmp(e, "random") ? 2 : 0;
+    }();
+    std::vector<int> ord(block);
+    for (int t = 0; t < block; t++) ord[t] = sched == 1 ? block - 1 - t : t;
+    uint64_t rng = 0x9E3779B97F4A7C15ull * (uint64_t)(b + 1);
     for (int live = block; live > 0;) {
-        for (int t = 0; t < block; t++) {
+        if (sched == 2)
+            for (int i = block - 1; i > 0; i--) {
+                rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                std::swap(ord[i], ord[(int)((rng >> 33) % (uint64_t)(i + 1))]);
+            }
+        for (int k = 0; k < block; k++) {
+            const int t = ord[k];
             if (cta.done[t] == 2) continue;
             cta.cur = t; threadIdx.x = t;
             swapcontext(&cta.sched, &cta.ctx[t]);

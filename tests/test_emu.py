@@ -204,6 +204,25 @@ def test_emu_chain_tables_and_unfused_reduction():
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 
 
+@pytest.mark.parametrize("order", ["reverse", "random"])
+def test_emu_results_independent_of_thread_order(order):
+    """The shim runs a CTA's threads one after another between two barriers, in index order by default;
+    WHALE_EMU_SCHED changes that order.  A likelihood, gradient or sampled tree that moved with it would mean a
+    missing barrier or a warp-lockstep assumption in a kernel.  (Process-wide switch: child process.)"""
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from whale_jl_b200 import lib as wlib\nfrom conftest import run_parity\nimport test_emu\n"
+            "L = wlib.Lib(%r)\n"
+            "run_parity(L, 'c1_example1', sel=[0, 3], conds=['root'])\n"
+            "run_parity(L, 'const_wgdturing', sel=[1, 7], conds=['nonextinct'])\n"
+            "run_parity(L, 'landplant100', sel=list(range(0, 100, 7)))\n"
+            "test_emu._check_backtrack(L, 'const_wgdturing', [2])\nprint('ok')\n"
+            % (ROOT, os.path.join(ROOT, "tests"), EMU))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, WHALE_EMU_SCHED=order),
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
 def test_emu_mle_lbfgs_like_the_reference_mle_test(L, tmp_path):
     """test/mle.jl's pattern (`optimize(f, g!, x0, LBFGS())` with f = −logpdf(model(rates), ccd) over (log λ, log μ),
     η and q fixed, gradient from AD) with the fused loglik+∇ call in place of ForwardDiff: the optimiser must converge
