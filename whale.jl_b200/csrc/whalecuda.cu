@@ -1126,7 +1126,7 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
                             double* d_out, cudaStream_t st) {
     if (condition < 0 || condition > 3) return fail(WHALE_ERR_ARG, "unknown condition kind %d", condition);
     const bool grad = (flags & WHALE_WANT_GRAD) != 0;
-    const int nn = m->nn, F = D->F;
+    const int F = D->F;
     const bool keep = (flags & WHALE_KEEP_ELL) != 0;
     if (keep && !D->d_ell) CU(cudaMalloc((void**)&D->d_ell, std::max<uint64_t>(D->ell_total, 1) * sizeof(double)));
     const bool prof = (flags & WHALE_PROFILE) != 0;
