@@ -63,13 +63,14 @@ constexpr int TABLES_NT = 128;  // emulation build: keep the fiber count small
 #else
 constexpr int TABLES_NT = 512;
 #endif
-// Row stride (doubles) of a branch row with K components per cell.  WHALE_ODD_STRIDE (experiment, default off) pads even
-// K to K+1 so that cells no longer collide on shared-memory banks in the slice gathers (K = 4: cells ≡ mod 4 share
-// banks, 2.1 wavefronts per ideal one — profiles/r1_ncu_k_dp_v8_summary.txt).  Off: RS(K) is K, the code is unchanged.
-#ifdef WHALE_ODD_STRIDE
-#define RS(K) ((K) | 1)
-#else
+// Row stride (doubles) of a branch row with K components per cell: even K is padded to K+1 so that cells do not
+// collide on shared-memory banks in the slice gathers (K = 4: cells ≡ mod 4 share banks, 2.1 wavefronts per ideal one
+// — profiles/r1_ncu_k_dp_v8_summary.txt; measured on the B200 in round 2: +3.2 % evals/s on C2,
+// profiles/r2_ab_odd_stride.json vs r2_ab_base.json).  WHALE_EVEN_STRIDE restores the dense layout (A/B, tests).
+#ifdef WHALE_EVEN_STRIDE
 #define RS(K) (K)
+#else
+#define RS(K) ((K) | 1)
 #endif
 constexpr int MAXPLAN = 64;  // tangent plans per data handle: [0] value only, [1..] gradient (parameter chunks)
 
@@ -98,6 +99,36 @@ struct FamHdr {
     uint32_t leaf_stage;     // per-warp staging buffer for one leaf branch's lists (bytes, multiple of 16)
     uint32_t blob_bytes;
     uint32_t rootwin;        // most terms (Πroot + speciation) any one root level holds: size of a level buffer
+};
+
+// ---- reverse-mode (adjoint) gradient: the transposed lists of a family, built from its forward blob ----
+// Per node, relative to the family's REVERSE blob (RevRec[nn] | u32 words | 16-byte entries).  An entry
+// {i1 = π, i2 = σ, p} under cell γ' stands for the term p·ℓ̄[π]·ℓ[σ] of ℓ̄[γ']: π indexes the adjoint row of the
+// node that owns the term, σ the value row of the term's other operand.
+struct RevRec {
+    uint32_t bptr_off;   // u32-word offset of bptr[C+1]: transposed same-branch terms (slices; WGD row 1; Πroot)
+    uint32_t bent_off;   // 16-byte-entry offset of those entries (each forward term appears under both operands)
+    uint32_t nbent;
+    uint32_t bslot_off;  // lane table of the backward slice loop (Slot[nbslots]; non-root nodes with slices)
+    uint32_t nbslots;
+    uint32_t sF_off;     // internal/root: u32-word offset of [sFptr[C_F+1] | upF[C_F]]: transposed speciation terms
+    uint32_t sFent_off;  //   grouped by the FIRST child's cell (π = this node's cell, σ = second child's cell);
+    uint32_t nsFent;     //   upF = this node's cell holding the same clade (Πloss transposed)
+    uint32_t sG_off, sGent_off, nsGent;  // same for the second child
+    uint32_t hoff;       // offset (doubles) of this node's rows in the family's history: (n+1) rows of stride Cp
+};
+static_assert(sizeof(RevRec) == 48, "RevRec must be 48 bytes");
+
+struct RevHdr {
+    uint64_t base;          // byte offset of the reverse blob in the reverse arena (16-byte aligned)
+    uint32_t blob_bytes;
+    uint32_t hist_len;      // doubles: every row of every internal/WGD branch (the forward pass keeps them)
+    uint32_t rows_len;      // doubles: last rows under the hybrid plan (leaf branches keep theirs until the end)
+    uint32_t scr_len;       // scratch row
+    uint32_t leafmax;       // per-warp scratch row of a leaf branch
+    uint32_t stage_bytes;   // staging of one node's forward lists + ϕ/ψ rows, or of its backward slice lists
+    uint32_t arows_len;     // doubles: adjoint last rows, placed by (reverse) lifetime
+    uint32_t hbuf_len;      // doubles: one staged history row (largest padded C of an internal/WGD node)
 };
 
 struct ModelDev {  // structure arrays (device pointers), node index = id-1
@@ -194,12 +225,10 @@ __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000
 #endif
 constexpr int ROWALLOC_MAXBLK = 64;
 
-template <class CKfn>
-WHALE_HD inline int place_rows(int nn, int nleafnodes, const int* leafnodes, int ninner, const int* inner,
-                               const int* child0, const int* child1, const int* kind, CKfn ck, int* roff) {
-    int foff[ROWALLOC_MAXBLK], flen[ROWALLOC_MAXBLK];  // free blocks below `top`, sorted by offset
+struct RowAlloc {  // first-fit allocator over one linear region; free blocks below `top`, sorted by offset
+    int foff[ROWALLOC_MAXBLK], flen[ROWALLOC_MAXBLK];
     int nfree = 0, top = 0;
-    auto take = [&](int need) -> int {
+    int take(int need) {
         if (need == 0) return 0;
         for (int i = 0; i < nfree; i++)
             if (flen[i] >= need) {
@@ -211,8 +240,8 @@ WHALE_HD inline int place_rows(int nn, int nleafnodes, const int* leafnodes, int
         const int o = top;
         top += need;
         return o;
-    };
-    auto give = [&](int o, int len) {
+    }
+    void give(int o, int len) {
         if (len == 0) return;
         int i = 0;
         while (i < nfree && foff[i] < o) i++;
@@ -229,16 +258,42 @@ WHALE_HD inline int place_rows(int nn, int nleafnodes, const int* leafnodes, int
             for (int j = i + 1; j < nfree; j++) { foff[j - 1] = foff[j]; flen[j - 1] = flen[j]; }
             nfree--;
         }
-    };
-    for (int i = 0; i < nleafnodes; i++) roff[leafnodes[i]] = take(ck(leafnodes[i]));
+    }
+};
+
+template <class CKfn>
+WHALE_HD inline int place_rows(int nn, int nleafnodes, const int* leafnodes, int ninner, const int* inner,
+                               const int* child0, const int* child1, const int* kind, CKfn ck, int* roff,
+                               bool keep_leaf = false) {
+    RowAlloc al;
+    for (int i = 0; i < nleafnodes; i++) roff[leafnodes[i]] = al.take(ck(leafnodes[i]));
     for (int i = 0; i < ninner; i++) {
         const int e = inner[i];
-        roff[e] = take(ck(e));
+        roff[e] = al.take(ck(e));
         if (kind[e] == WHALE_ROOT) continue;  // the root reads its children level by level: they stay
         // the children are read for the last time while e's row 1 is formed; e's own slices then run in e's
         // row and the scratch row, so later nodes may reuse the children's space
-        if (child0[e] >= 0) give(roff[child0[e]], ck(child0[e]));
-        if (child1[e] >= 0) give(roff[child1[e]], ck(child1[e]));
+        // (reverse mode keeps the leaf branches' rows: their tangents are contracted in the backward pass)
+        if (child0[e] >= 0 && !(keep_leaf && kind[child0[e]] == WHALE_LEAF)) al.give(roff[child0[e]], ck(child0[e]));
+        if (child1[e] >= 0 && !(keep_leaf && kind[child1[e]] == WHALE_LEAF)) al.give(roff[child1[e]], ck(child1[e]));
     }
-    return top;
+    return al.top;
+}
+
+// Adjoint last rows ℓ̄_{e,n} of the internal/WGD/root nodes in the backward pass (nodes in reverse order): a node's
+// row is written while its parent's row 1 is transposed and dead once its own row 1 has been transposed.
+template <class Cfn>
+WHALE_HD inline int place_arows(int ninner, const int* inner, const int* child0, const int* child1, const int* kind,
+                                Cfn cf, int* aoff) {
+    RowAlloc al;
+    if (ninner > 0) aoff[inner[ninner - 1]] = al.take(cf(inner[ninner - 1]));  // the root
+    for (int i = ninner - 1; i >= 0; i--) {
+        const int e = inner[i];
+        for (int j = 0; j < 2; j++) {
+            const int c = j == 0 ? child0[e] : child1[e];
+            if (c >= 0 && kind[c] != WHALE_LEAF) aoff[c] = al.take(cf(c));
+        }
+        al.give(aoff[e], cf(e));
+    }
+    return al.top;
 }

@@ -576,20 +576,33 @@ __device__ __forceinline__ bool run_slices_fused_k(int K, int n, int C, double* 
 #else
 #define LDCG(p) __ldcg(p)
 #endif
+struct TailArgs {
+    unsigned int* done;     // families finished so far (all launches of this evaluation); re-armed to 0 by the last CTA
+    int n_total;            // F
+    int root;
+    const int* K;           // the output plan's component counts
+    int Kmax;
+    const double* out_fam;  // [F * K[root]]
+    const double* cond;     // [4 * Kmax]
+    int cond_kind, first;
+    double* out;            // [1+P]
+    const int* act;         // [nn * Kmax]
+};
+// `count` = families this CTA finished (1 for k_dp; the persistent CTAs of k_dp_rev report their share on exit)
 template <int NT>
-__device__ __forceinline__ void dp_tail_reduce(const DPArgs& A, double* s_tot) {
+__device__ __forceinline__ void dp_tail_reduce(const TailArgs& A, int count, double* s_tot) {
     constexpr int NW = NT / 32;  // (no static shared memory here: k_dp opts in to the full 227 KB dynamically)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    __syncthreads();  // this family's outputs are written
+    __syncthreads();  // this CTA's outputs are written
     int last = 0;
     if (tid == 0) {
         __threadfence();
-        const unsigned prev = atomicAdd(A.done, 1u);
-        last = (prev + 1u == (unsigned)A.n_total) ? 1 : 0;
+        const unsigned prev = atomicAdd(A.done, (unsigned)count);
+        last = (prev + (unsigned)count == (unsigned)A.n_total) ? 1 : 0;
     }
     if (!__syncthreads_or(last)) return;
     __threadfence();
-    const int root = A.M.root, KR = A.PL.K[root], F = A.n_total, Kmax = A.PL.Kmax;
+    const int root = A.root, KR = A.K[root], F = A.n_total, Kmax = A.Kmax;
     if (KR <= NT / 2) {
         // R = NT/KR row groups: thread (r, k) sums component k of the families f ≡ r (mod R), eight loads in flight;
         // thread k then adds the R partial sums in order
@@ -611,14 +624,14 @@ __device__ __forceinline__ void dp_tail_reduce(const DPArgs& A, double* s_tot) {
         if (tid < KR) {
             double s = 0.0;
             for (int q = 0; q < R; q++) s += part[q * KR + tid];
-            s_tot[tid] = s - (double)F * A.PL.cond[A.cond_kind * Kmax + tid];
+            s_tot[tid] = s - (double)F * A.cond[A.cond_kind * Kmax + tid];
         }
     } else {
         for (int k = warp; k < KR; k += NW) {
             double s = 0.0;
             for (int f = lane; f < F; f += 32) s += LDCG(A.out_fam + (size_t)f * KR + k);
             for (int step = 16; step > 0; step >>= 1) s += SHFL_DOWN(s, step);
-            if (lane == 0) s_tot[k] = s - (double)F * A.PL.cond[A.cond_kind * Kmax + k];
+            if (lane == 0) s_tot[k] = s - (double)F * A.cond[A.cond_kind * Kmax + k];
         }
     }
     __syncthreads();
@@ -627,7 +640,7 @@ __device__ __forceinline__ void dp_tail_reduce(const DPArgs& A, double* s_tot) {
     // pass also the log-likelihood
     for (int k = tid; k < KR; k += NT) {
         if (k == 0) { if (A.first) A.out[0] = finite ? s_tot[0] : -dinf(); }
-        else A.out[1 + A.PL.act[root * Kmax + k]] = finite ? s_tot[k] : 0.0;
+        else A.out[1 + A.act[root * Kmax + k]] = finite ? s_tot[k] : 0.0;
     }
     if (tid == 0) *A.done = 0u;
 }
@@ -990,5 +1003,8 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
             T[7] = 0;
         }
     }
-    if (A.done) dp_tail_reduce<NT>(A, reinterpret_cast<double*>(smem_raw));
+    if (A.done) {
+        const TailArgs TA{A.done, A.n_total, M.root, PL.K, PL.Kmax, A.out_fam, PL.cond, A.cond_kind, A.first, A.out, PL.act};
+        dp_tail_reduce<NT>(TA, 1, reinterpret_cast<double*>(smem_raw));
+    }
 }

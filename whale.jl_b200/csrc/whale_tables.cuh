@@ -56,15 +56,16 @@ __device__ __forceinline__ void rates_of(const TabMeta& T, const ModelDev& M, in
 __device__ void leafshapes_block(const ModelDev& M, const PlanDev& PL, const double* __restrict__ x,
                                  const double* __restrict__ pleaf, int li, unsigned char* tsm);
 
-__global__ void __launch_bounds__(TABLES_NT) k_tables(ModelDev M, PlanDev PL, const double* __restrict__ x,
-                                                      const double* __restrict__ pleaf, int G, unsigned flags) {
-    EXTERN_SHARED(tsm);
-    if ((int)blockIdx.x >= G) {  // tree-shape rows of one leaf branch
-        leafshapes_block(M, PL, x, pleaf, (int)blockIdx.x - G, tsm);
+// one CTA of the table launch for plan PL: CTA `bid` of G table CTAs, or (bid >= G) the leaf-shape CTA of leaf bid − G
+__device__ __forceinline__ void tables_block(const ModelDev& M, const PlanDev& PL, const double* __restrict__ x,
+                                             const double* __restrict__ pleaf, int G, unsigned flags, int bid,
+                                             unsigned char* tsm) {
+    if (bid >= G) {  // tree-shape rows of one leaf branch
+        leafshapes_block(M, PL, x, pleaf, bid - G, tsm);
         return;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    const bool writer = blockIdx.x == 0;  // the per-branch outputs are identical in every table CTA: one writes
+    const bool writer = bid == 0;  // the per-branch outputs are identical in every table CTA: one writes
     const long long tk0 = CLOCK64();
     const int nn = M.nn, Kmax = PL.Kmax, P = M.n_params;
     double* sd = reinterpret_cast<double*>(tsm);  // dt, leafP, pleaf [nn each], x [P], (α,β) [nn*Kmax*2], ϵ_0, ϵ_n [nn*Kmax each]
@@ -72,16 +73,9 @@ __global__ void __launch_bounds__(TABLES_NT) k_tables(ModelDev M, PlanDev PL, co
     double* s_abn = s_ab + 2 * nn * Kmax;     // whole-branch (α_n, β_n) components (closed-form branches)
     double* s_e0 = s_abn + 2 * nn * Kmax;
     double* s_en = s_e0 + nn * Kmax;
-#ifdef WHALE_TAB_PROJ
-    double* s_v0 = s_en + nn * Kmax;   // projective chain: ϵ_0 = s_e0/s_v0 until phase A2, last ϵ = s_en/s_vn
-    double* s_vn = s_v0 + nn * Kmax;
-    double* s_q0 = s_vn + nn * Kmax;   // ϵ_0 itself, from phase A2 (what phase B reads)
-    int* si = reinterpret_cast<int*>(s_q0 + nn * Kmax);
-    const double* const s_eps0 = s_q0;
-#else
     int* si = reinterpret_cast<int*>(s_en + nn * Kmax);
     const double* const s_eps0 = s_e0;
-#endif  // 10 arrays [nn], lvl_off [nlvl+1], lvl_nodes [nn]
+    // 10 arrays [nn], lvl_off [nlvl+1], lvl_nodes [nn]
     int16_t* s_cm = reinterpret_cast<int16_t*>(si + 11 * nn + M.nlvl + 1);
     uint8_t* s_ro = reinterpret_cast<uint8_t*>(s_cm + nn * 2 * Kmax);
     {
@@ -165,142 +159,6 @@ __global__ void __launch_bounds__(TABLES_NT) k_tables(ModelDev M, PlanDev PL, co
     }
     __syncthreads();
     if (writer && threadIdx.x == 0) PL.tim[0] = CLOCK64() - tk0;
-#ifdef WHALE_TAB_PROJ
-    // ---- phase A (experiment, WHALE_TAB_PROJ): the chain over the tree's height in PROJECTIVE form, division-free.
-    //      ϵ = u/v: a product of children is (u_f u_g)/(v_f v_g), a WGD node u_c(q u_c + (1−q) v_c)/v_c², a closed-form
-    //      branch (α_n v + (1−α_n−β_n) u)/(v − β_n u); v is rescaled by a power of two (exact) so it cannot drift.
-    //      Everything that needs a quotient (ϵ_0 values, WGD/root coefficients, conditions, leaf rows) moves to the
-    //      parallel phase A2 behind the chain. ----
-    auto d1at = [&](const double* a, int e_, int k_) -> D1 { return mk(a[e_ * Kmax], k_ == 0 ? 0.0 : a[e_ * Kmax + k_]); };
-    for (int L = 0; L < M.nlvl; L++) {
-        const int n0 = T.lvl_off[L], n1 = T.lvl_off[L + 1];
-        for (int j = n0 + warp; j < n1; j += nwarp) {
-            const int e = T.lvl_nodes[j];
-            const int K = T.K[e], kind = T.kind[e], n = T.nsl[e];
-            const int closed = T.mode[e];
-            for (int k = lane; k < K; k += 32) {
-                const unsigned role = k == 0 ? 0u : T.role[e * PL.Kmax + k];
-                auto child_uv = [&](int jc, int child, D1& cu, D1& cv) {
-                    const int kc = k == 0 ? 0 : T.cmap[(e * 2 + jc) * Kmax + k];
-                    cu = mk(s_en[child * Kmax], (k > 0 && kc >= 0) ? s_en[child * Kmax + kc] : 0.0);
-                    cv = mk(s_vn[child * Kmax], (k > 0 && kc >= 0) ? s_vn[child * Kmax + kc] : 0.0);
-                };
-                D1 u0, v0 = mk(1.0);
-                if (kind == WHALE_LEAF) {
-                    u0 = mk(T.pleaf[e]);
-                } else if (kind == WHALE_WGD) {
-                    const D1 q = mk(T.x[T.qs[e]], (role & 4u) ? 1.0 : 0.0);
-                    D1 uc, vc;
-                    child_uv(0, T.ch0[e], uc, vc);
-                    u0 = uc * (q * uc + (1.0 - q) * vc);
-                    v0 = vc * vc;
-                } else {
-                    D1 uf, vf, ug, vg;
-                    child_uv(0, T.ch0[e], uf, vf);
-                    child_uv(1, T.ch1[e], ug, vg);
-                    u0 = uf * ug;
-                    v0 = vf * vg;
-                }
-                s_e0[e * Kmax + k] = k == 0 ? u0.v : u0.d;
-                s_v0[e * Kmax + k] = k == 0 ? v0.v : v0.d;
-                D1 un = u0, vn = v0;
-                if (n > 0 && closed) {
-                    const D1 an = mk(s_abn[(e * Kmax) * 2], k == 0 ? 0.0 : s_abn[(e * Kmax + k) * 2]);
-                    const D1 bn = mk(s_abn[(e * Kmax) * 2 + 1], k == 0 ? 0.0 : s_abn[(e * Kmax + k) * 2 + 1]);
-                    un = an * v0 + ((1.0 - an) - bn) * u0;
-                    vn = v0 - bn * u0;
-                } else if (n > 0) {  // chain-mode branch: as in the default build, from the quotient
-                    const D1 ep = u0 / v0;
-                    double2* uvrow = PL.uv + T.toff[e];
-                    D1 u = ep, v = mk(1.0);
-                    uvrow[k] = k == 0 ? make_double2(u.v, v.v) : make_double2(u.d, v.d);
-                    const D1 a = mk(s_ab[(e * Kmax) * 2], k == 0 ? 0.0 : s_ab[(e * Kmax + k) * 2]);
-                    const D1 b = mk(s_ab[(e * Kmax) * 2 + 1], k == 0 ? 0.0 : s_ab[(e * Kmax + k) * 2 + 1]);
-                    const D1 c = (1.0 - a) - b;
-                    for (int i = 1; i <= n; i++) {
-                        const D1 un_ = c * u + a * v;
-                        const D1 vn_ = v - b * u;
-                        u = un_;
-                        v = vn_;
-                        uvrow[(size_t)i * K + k] = k == 0 ? make_double2(u.v, v.v) : make_double2(u.d, v.d);
-                    }
-                    un = u;
-                    vn = v;
-                    if (kind == WHALE_LEAF && writer) {  // ℓ_n = leafℙ·gⁿ·(v_0/v_n)²
-                        const D1 g = (1.0 - a) * (1.0 - b);
-                        const D1 r = mk(1.0) / v;
-                        const D1 lf = mk(T.leafP[e]) * dpowi(g, n) * (r * r);
-                        PL.leaf[e * PL.Kmax + k] = k == 0 ? lf.v : lf.d;
-                    }
-                }
-                // exact rescaling: the value lane's exponent, read from component 0 so that all lanes agree
-                s_en[e * Kmax + k] = k == 0 ? un.v : un.d;
-                s_vn[e * Kmax + k] = k == 0 ? vn.v : vn.d;
-            }
-            __syncwarp();
-            {
-                const int ex = ilogb(s_vn[e * Kmax]);
-                __syncwarp();
-                for (int k = lane; k < K; k += 32) {
-                    s_en[e * Kmax + k] = scalbn(s_en[e * Kmax + k], -ex);
-                    s_vn[e * Kmax + k] = scalbn(s_vn[e * Kmax + k], -ex);
-                }
-            }
-        }
-        __syncthreads();
-        if (writer && threadIdx.x == 0 && L < 28) PL.tim[1 + L] = CLOCK64() - tk0;
-    }
-    // ---- phase A2: the quotients, all nodes in parallel (one warp per node) ----
-    for (int e = warp; e < nn; e += nwarp) {
-        const int K = T.K[e], kind = T.kind[e], n = T.nsl[e];
-        for (int k = lane; k < K; k += 32) {
-            const unsigned role = k == 0 ? 0u : T.role[e * PL.Kmax + k];
-            auto child_eps = [&](int jc, int child) -> D1 {
-                const int kc = k == 0 ? 0 : T.cmap[(e * 2 + jc) * Kmax + k];
-                const D1 cu = mk(s_en[child * Kmax], (k > 0 && kc >= 0) ? s_en[child * Kmax + kc] : 0.0);
-                const D1 cv = mk(s_vn[child * Kmax], (k > 0 && kc >= 0) ? s_vn[child * Kmax + kc] : 0.0);
-                return cu / cv;
-            };
-            const D1 ep = d1at(s_e0, e, k) / d1at(s_v0, e, k);
-            if (kind == WHALE_WGD && writer) {
-                const D1 q = mk(T.x[T.qs[e]], (role & 4u) ? 1.0 : 0.0);
-                const D1 ec = child_eps(0, T.ch0[e]);
-                const D1 w = (1.0 - q) + 2.0 * (q * ec);  // Πwgdloss coefficient src/core.jl:198
-                PL.cx[e * PL.Kmax + k] = k == 0 ? w.v : w.d;
-                PL.cy[e * PL.Kmax + k] = k == 0 ? q.v : q.d;
-            } else if (kind == WHALE_ROOT && writer) {  // whaleroot! src/core.jl:131-147 ; condition src/condition.jl
-                const D1 ef = child_eps(0, T.ch0[e]), eg = child_eps(1, T.ch1[e]);
-                const D1 eta = mk(T.x[M.eta_slot], (role & 8u) ? 1.0 : 0.0);
-                const D1 xi = 1.0 - (1.0 - eta) * ep;
-                const D1 A = (1.0 - eta) * xi / eta;
-                const D1 B = eta * (1.0 - ep) / (xi * xi);
-                PL.cx[e * PL.Kmax + k] = k == 0 ? A.v : A.d;
-                PL.cy[e * PL.Kmax + k] = k == 0 ? B.v : B.d;
-                const D1 gr = eta * ep / (1.0 - (1.0 - eta) * ep);
-                const D1 gf = eta * ef / (1.0 - (1.0 - eta) * ef);
-                const D1 gg = eta * eg / (1.0 - (1.0 - eta) * eg);
-                const D1 pr = ((1.0 - gf) - gg) + gr;  // RootCondition :21-29
-                const D1 pn = 1.0 - gr;                // NonExtinctCondition :15-18
-                const D1 cr = pr.v > 0.0 ? dlog(pr) : mk(-dinf(), 0.0);
-                const D1 cn = dlog(pn);
-                PL.cond[0 * PL.Kmax + k] = 0.0;
-                PL.cond[1 * PL.Kmax + k] = k == 0 ? cr.v : cr.d;
-                PL.cond[2 * PL.Kmax + k] = k == 0 ? cn.v : cn.d;
-            } else if (kind == WHALE_LEAF && writer && (n == 0 || T.mode[e])) {
-                D1 lf = mk(T.leafP[e]);
-                if (n > 0) {  // Π_i ϕ_i = (1−α_n)(1−β_n)/(1−β_n ϵ_0)²
-                    const D1 an = mk(s_abn[(e * Kmax) * 2], k == 0 ? 0.0 : s_abn[(e * Kmax + k) * 2]);
-                    const D1 bn = mk(s_abn[(e * Kmax) * 2 + 1], k == 0 ? 0.0 : s_abn[(e * Kmax + k) * 2 + 1]);
-                    const D1 r = mk(1.0) / (1.0 - bn * ep);
-                    lf = lf * (((1.0 - an) * (1.0 - bn)) * (r * r));
-                }
-                PL.leaf[e * PL.Kmax + k] = k == 0 ? lf.v : lf.d;
-            }
-            s_q0[e * Kmax + k] = k == 0 ? ep.v : ep.d;
-        }
-    }
-    __syncthreads();
-#else
     // ---- phase A: the chain over the tree's height.  Per level, one warp per node, lanes over components:
     //      ϵ_0 from the children's last ϵ (shared memory), then the branch's last ϵ ----
     for (int L = 0; L < M.nlvl; L++) {
@@ -351,6 +209,7 @@ __global__ void __launch_bounds__(TABLES_NT) k_tables(ModelDev M, PlanDev PL, co
                         PL.cond[2 * PL.Kmax + k] = k == 0 ? cn.v : cn.d;
                     }
                 }
+                if (role & 16u) ep = mk(ep.v, 1.0);  // local plan: this component is ∂/∂ϵ_0 of the branch itself
                 s_e0[e * Kmax + k] = k == 0 ? ep.v : ep.d;
                 D1 en = ep, lf = mk(0.0);
                 if (n > 0 && closed) {
@@ -391,10 +250,9 @@ __global__ void __launch_bounds__(TABLES_NT) k_tables(ModelDev M, PlanDev PL, co
         __syncthreads();
         if (writer && threadIdx.x == 0 && L < 28) PL.tim[1 + L] = CLOCK64() - tk0;
     }
-#endif
     // ---- phase B: every (node, row, component) of the tables in parallel (one flat index space, 1/G per CTA) ----
     const int total = T.toff[nn - 1] + (T.nsl[nn - 1] + 1) * T.K[nn - 1];  // toff is ascending in node index
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += G * blockDim.x) {
+    for (int t = bid * blockDim.x + threadIdx.x; t < total; t += G * blockDim.x) {
         int lo = 0, hi = nn - 1;  // node e with toff[e] <= t < toff[e+1]
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
@@ -439,6 +297,29 @@ __global__ void __launch_bounds__(TABLES_NT) k_tables(ModelDev M, PlanDev PL, co
     }
     __syncthreads();
     if (writer && threadIdx.x == 0) { PL.tim[30] = CLOCK64() - tk0; PL.tim[31] = M.nlvl; }
+}
+
+__global__ void __launch_bounds__(TABLES_NT) k_tables(ModelDev M, PlanDev PL, const double* __restrict__ x,
+                                                      const double* __restrict__ pleaf, int G, unsigned flags) {
+    EXTERN_SHARED(tsm);
+    tables_block(M, PL, x, pleaf, G, flags, (int)blockIdx.x, tsm);
+}
+
+// The reverse-mode evaluation needs three table sets for the same θ — the hybrid plan the DP runs on (leaf branches
+// with their own λ, μ tangents, everything else value only; with the leaf-shape CTAs), the full plan (global tangents
+// of ϵ and of the row-1 coefficients, contracted with the adjoints at the end) and the local plan (∂ϕ_i, ∂ψ_i w.r.t.
+// the branch's own λ, μ and ϵ_0) — in ONE launch: CTAs [0, n0) serve plan 0, [n0, n0+n1) plan 1, the rest plan 2.
+struct Tables3 {
+    PlanDev PL[3];
+    int G[3];   // table CTAs per plan
+    int n[3];   // CTAs per plan (G + leaf-shape CTAs)
+};
+__global__ void __launch_bounds__(TABLES_NT) k_tables3(ModelDev M, Tables3 T3, const double* __restrict__ x,
+                                                       const double* __restrict__ pleaf, unsigned flags) {
+    EXTERN_SHARED(tsm);
+    int bid = (int)blockIdx.x, pi = 0;
+    while (pi < 2 && bid >= T3.n[pi]) { bid -= T3.n[pi]; pi++; }
+    tables_block(M, T3.PL[pi], x, pleaf, T3.G[pi], flags, bid, tsm);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -22,6 +22,7 @@
 #include "whale_common.cuh"
 #include "whale_tables.cuh"
 #include "whale_dp.cuh"
+#include "whale_rev.cuh"
 #include "whale_reduce.cuh"
 #include "whale_track.cuh"
 #include "whale_ale.hpp"
@@ -93,6 +94,14 @@ struct whale_model {
     ModelDev dev{};
     std::vector<void*> owned;
     Plan plan[2];  // 0: value only, 1: all raw parameters
+    // reverse-mode gradient (whale_rev.cuh): the hybrid plan the DP runs on (leaf branches: own λ, μ; else value only),
+    // the local plan (K = 4 on internal/WGD branches: ∂/∂ own λ, own μ, ϵ_0) and, for the full plan, the component of
+    // every root component in every node's list
+    Plan planR, planL;
+    std::vector<int16_t> rinv;
+    int16_t* d_rinv = nullptr;
+    int n_sm = 1;
+    bool attr_set = false;  // the kernels' dynamic shared-memory opt-in was done on this model's device
     bool x_host_valid = false;  // d_x / d_pleaf hold the parameters of the last host-pointer evaluation
     double* d_x = nullptr;      // staging for host-pointer calls
     double* d_pleaf = nullptr;  // [nn]
@@ -108,24 +117,26 @@ static int env_int(const char* name, int dflt) {
     return s ? atoi(s) : dflt;
 }
 static int dp_nt() {
-    static int nt = [] { int v = env_int("WHALE_NT", 128); return (v == 64 || v == 96 || v == 256) ? v : 128; }();
+    static int nt = [] { int v = env_int("WHALE_NT", 128); return (v == 64 || v == 256) ? v : 128; }();
     return nt;
 }
 static int dp_minb() {  // resident CTAs per SM the register cap is chosen for
     static int mb = [] {
         const int nt = dp_nt(), v = env_int("WHALE_MINB", 0);
-        if (nt == 64) return (v == 6 || v == 8 || v == 10) ? v : 12;
-        if (nt == 96) return v == 6 ? 6 : 5;
-        if (nt == 256) return v == 3 ? 3 : 2;
-        return (v == 3 || v == 5 || v == 6 || v == 7) ? v : 4;
+        if (nt == 64) return 8;
+        if (nt == 256) return 2;
+        return (v == 3 || v == 5 || v == 6) ? v : 4;
     }();
     return mb;
 }
+// launch shapes compiled in (k_dp and k_dp_rev); round 1's sweep over 13 shapes found nothing better than 128 x 4
+// (profiles/r1_occupancy_sweep_v8.txt), the others stay for experiments
 #ifdef WHALE_DEV_BUILD  // quick experiment builds: the default variant only
 #define DP_VARIANTS(X) X(128, 4)
 #else
-#define DP_VARIANTS(X) X(96, 5) X(96, 6) X(64, 6) X(64, 8) X(64, 10) X(64, 12) X(128, 3) X(128, 4) X(128, 5) X(128, 6) X(128, 7) X(256, 2) X(256, 3)
+#define DP_VARIANTS(X) X(64, 8) X(128, 3) X(128, 4) X(128, 5) X(128, 6) X(256, 2)
 #endif
+#define REV_VARIANTS(X) DP_VARIANTS(X)
 constexpr int MAX_BINS = 8;
 struct Bin {
     int off, count;
@@ -191,6 +202,20 @@ struct whale_data {
     double aggG = 0, aggTroot = 0;
     int64_t algo_bytes = 0;
     std::vector<std::vector<uint32_t>> famC;  // [F][nn] compat counts (for ℓ layout)
+    // reverse-mode gradient: transposed lists (a second arena), per-family budgets, adjoint-row offsets, the per-CTA
+    // history slots and the family counters of the persistent launches
+    bool rev = false;
+    std::vector<RevHdr> rhdr;
+    std::vector<unsigned char> rarena_host;
+    std::vector<uint32_t> aoff_host;
+    std::vector<int> rev_grid, rev_slot0;  // per bin: CTAs, first history slot
+    RevHdr* d_rhdr = nullptr;
+    unsigned char* d_rarena = nullptr;
+    size_t rarena_bytes = 0;
+    uint32_t* d_aoff = nullptr;
+    double* d_hist = nullptr;
+    size_t hist_stride = 0;
+    unsigned int* d_next = nullptr;
 };
 
 // `subset`: which raw parameters this plan differentiates (empty = none: the value-only plan)
@@ -247,6 +272,70 @@ static void build_plan(const whale_model& m, const std::vector<char>& subset, Pl
         }
         pl.cmap[((size_t)e * 2 + 0) * Kmax + 0] = 0;
         pl.cmap[((size_t)e * 2 + 1) * Kmax + 0] = 0;
+    }
+    pl.tab_len = off;
+}
+
+// The plan the reverse-mode DP runs on: a leaf branch carries its own λ, μ (it has no children, so K <= 3 whatever P
+// is), every other node is value only.
+static void build_plan_hybrid(const whale_model& m, Plan& pl) {
+    const int nn = m.nn;
+    std::vector<std::vector<int>> act(nn);
+    for (int e = 0; e < nn; e++) {
+        if (m.kind[e] != WHALE_LEAF) continue;
+        if (m.lam_slot[e] >= 0) act[e].push_back(m.lam_slot[e]);
+        if (m.mu_slot[e] >= 0) act[e].push_back(m.mu_slot[e]);
+        std::sort(act[e].begin(), act[e].end());
+        act[e].erase(std::unique(act[e].begin(), act[e].end()), act[e].end());
+    }
+    pl.Kmax = 1;
+    for (int e = 0; e < nn; e++) pl.Kmax = std::max(pl.Kmax, 1 + (int)act[e].size());
+    const int Kmax = pl.Kmax;
+    pl.K.assign(nn, 1);
+    pl.act.assign((size_t)nn * Kmax, -1);
+    pl.cmap.assign((size_t)nn * 2 * Kmax, -1);
+    pl.role.assign((size_t)nn * Kmax, 0);
+    pl.toff.assign(nn, 0);
+    size_t off = 0;
+    for (int e = 0; e < nn; e++) {
+        pl.K[e] = 1 + (int)act[e].size();
+        pl.toff[e] = (int)off;
+        off += (size_t)(m.nsl[e] + 1) * pl.K[e];
+        for (int k = 1; k < pl.K[e]; k++) {
+            const int gp = act[e][k - 1];
+            pl.act[(size_t)e * Kmax + k] = gp;
+            pl.role[(size_t)e * Kmax + k] = (uint8_t)((gp == m.lam_slot[e] ? 1 : 0) | (gp == m.mu_slot[e] ? 2 : 0));
+        }
+        pl.cmap[((size_t)e * 2 + 0) * Kmax + 0] = 0;
+        pl.cmap[((size_t)e * 2 + 1) * Kmax + 0] = 0;
+    }
+    pl.tab_len = off;
+}
+
+// The local plan: on an internal/WGD branch with slices, component 1 = the branch's own λ, 2 = its own μ (raw scale,
+// role bits as in the other plans) and 3 = ϵ_0 of the branch itself (role bit 16: k_tables seeds ∂ϵ_0 = 1).  ϕ_i and ψ_i
+// of a branch depend on nothing else, so these three partials are all the reverse pass needs from the slice tables.
+static void build_plan_local(const whale_model& m, Plan& pl) {
+    const int nn = m.nn;
+    pl.Kmax = 4;
+    pl.K.assign(nn, 1);
+    pl.act.assign((size_t)nn * 4, -1);
+    pl.cmap.assign((size_t)nn * 2 * 4, -1);
+    pl.role.assign((size_t)nn * 4, 0);
+    pl.toff.assign(nn, 0);
+    size_t off = 0;
+    for (int e = 0; e < nn; e++) {
+        const bool on = m.kind[e] != WHALE_LEAF && m.kind[e] != WHALE_ROOT && m.nsl[e] > 0;
+        pl.K[e] = on ? 4 : 1;
+        pl.toff[e] = (int)off;
+        off += (size_t)(m.nsl[e] + 1) * pl.K[e];
+        if (on) {
+            pl.act[(size_t)e * 4 + 1] = m.lam_slot[e]; pl.role[(size_t)e * 4 + 1] = 1;
+            pl.act[(size_t)e * 4 + 2] = m.mu_slot[e];  pl.role[(size_t)e * 4 + 2] = 2;
+            pl.role[(size_t)e * 4 + 3] = 16;
+        }
+        pl.cmap[((size_t)e * 2 + 0) * 4 + 0] = 0;
+        pl.cmap[((size_t)e * 2 + 1) * 4 + 0] = 0;
     }
     pl.tab_len = off;
 }
@@ -380,6 +469,29 @@ int32_t whale_model_create(const whale_model_desc* d, whale_model_t* out) {
         build_plan(*m, g == 1 ? std::vector<char>(m->P, 1) : std::vector<char>(), m->plan[g]);
         CU(upload_plan(m->plan[g], nn));
     }
+    build_plan_hybrid(*m, m->planR);
+    CU(upload_plan(m->planR, nn));
+    build_plan_local(*m, m->planL);
+    CU(upload_plan(m->planL, nn));
+    {
+        const Plan& pg = m->plan[1];
+        const int KR = pg.K[m->root];
+        m->rinv.assign((size_t)nn * KR, -1);
+        for (int e = 0; e < nn; e++) {
+            m->rinv[(size_t)e * KR] = 0;
+            for (int k = 1; k < KR; k++) {
+                const int gp = pg.act[(size_t)m->root * pg.Kmax + k];
+                for (int j = 1; j < pg.K[e]; j++)
+                    if (pg.act[(size_t)e * pg.Kmax + j] == gp) m->rinv[(size_t)e * KR + k] = (int16_t)j;
+            }
+        }
+        CU(upload(m->rinv, &m->d_rinv));
+    }
+    {
+        cudaDeviceProp pr;
+        CU(cudaGetDeviceProperties(&pr, g_device));
+        m->n_sm = std::max(1, pr.multiProcessorCount);
+    }
     CU(cudaMalloc((void**)&m->d_x, std::max(1, m->P) * sizeof(double)));
     CU(cudaMalloc((void**)&m->d_pleaf, nn * sizeof(double)));
     CU(cudaMemset(m->d_pleaf, 0, nn * sizeof(double)));
@@ -395,6 +507,9 @@ int32_t whale_model_destroy(whale_model_t m) {
     cudaSetDevice(m->device);
     for (void* p : m->owned) cudaFree(p);
     for (int g = 0; g < 2; g++) for (void* p : m->plan[g].owned) cudaFree(p);
+    for (void* p : m->planR.owned) cudaFree(p);
+    for (void* p : m->planL.owned) cudaFree(p);
+    cudaFree(m->d_rinv);
     cudaFree(m->d_x); cudaFree(m->d_pleaf); cudaFree(m->d_out);
     if (m->h_pin) cudaFreeHost(m->h_pin);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -414,11 +529,7 @@ static size_t smem_need(const whale_model* m, const FamHdr& h, int plan, int Kma
 
 static size_t tables_smem(const whale_model* m, const Plan& pl, bool shapes) {  // mirrors the carve-ups in k_tables
     const size_t nn = m->nn, nlvl = m->lvl_off.size() - 1;
-    #ifdef WHALE_TAB_PROJ
-    const size_t ndbl = 9;  // + the denominators of ϵ_0 and of the last ϵ, and ϵ_0 itself
-#else
     const size_t ndbl = 6;
-#endif
     size_t need = (3 * nn + m->P + ndbl * nn * pl.Kmax) * sizeof(double) + (11 * nn + nlvl + 1) * sizeof(int) +
                   nn * 2 * pl.Kmax * sizeof(int16_t) + nn * pl.Kmax + 16;
     if (shapes)  // a leaf-shape CTA keeps its branch's projective and (ϕ, ψ) rows in shared memory
@@ -446,6 +557,29 @@ static cudaError_t launch_tables(whale_model* m, Plan& pl, const double* d_x, co
     }
     LAUNCH(k_tables, G + (shapes ? (int)m->leafnodes.size() : 0), TABLES_NT, smem, st, m->dev, pl.dev, d_x, d_pleaf, G,
            tables_flags());
+    g_launches++;
+    return cudaSuccess;
+}
+
+// the three table sets of a reverse-mode evaluation in one launch (see Tables3 in whale_tables.cuh)
+static cudaError_t launch_tables3(whale_model* m, const double* d_x, const double* d_pleaf, cudaStream_t st) {
+    Plan* pls[3] = {&m->planR, &m->plan[1], &m->planL};
+    Tables3 T3;
+    size_t smem = 0;
+    int total = 0;
+    for (int i = 0; i < 3; i++) {
+        const bool shapes = i == 0 && !m->leafnodes.empty();
+        T3.PL[i] = pls[i]->dev;
+        T3.G[i] = (int)std::max<size_t>(1, std::min<size_t>(32, (pls[i]->tab_len + TABLES_NT - 1) / TABLES_NT));
+        T3.n[i] = T3.G[i] + (shapes ? (int)m->leafnodes.size() : 0);
+        total += T3.n[i];
+        smem = std::max(smem, tables_smem(m, *pls[i], shapes));
+    }
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_tables3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    LAUNCH(k_tables3, total, TABLES_NT, smem, st, m->dev, T3, d_x, d_pleaf, tables_flags());
     g_launches++;
     return cudaSuccess;
 }
@@ -510,6 +644,7 @@ static int32_t finalize_data(whale_model* m, whale_data* D, whale_data_t* out);
 // scheduling).  A "paired" order for the 1–2 wave case (heaviest alone, lightest + middle paired) was measured 4 %
 // SLOWER on the B200: an SM with fewer resident families runs each of them faster (the SM's shared-memory/issue
 // throughput is what is conserved, not the slot count), so LPT's ragged tail costs little.
+static size_t smem_need_rev(const whale_model* m, const FamHdr& h, const RevHdr& r);
 static cudaError_t order_families(whale_data* D, int g, const std::vector<double>& work) {
     const whale_model* m = D->m;
     const Plan& pl = *D->plans[g];
@@ -518,7 +653,8 @@ static cudaError_t order_families(whale_data* D, int g, const std::vector<double
     perm.resize(F);
     std::iota(perm.begin(), perm.end(), 0);
     std::vector<size_t> need(F);
-    for (int f = 0; f < F; f++) need[f] = smem_need(m, D->hdr[f], g, pl.Kmax);
+    const bool rev = D->rev && g == 1;
+    for (int f = 0; f < F; f++) need[f] = rev ? smem_need_rev(m, D->hdr[f], D->rhdr[f]) : smem_need(m, D->hdr[f], g, pl.Kmax);
     std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return need[a] != need[b] ? need[a] > need[b] : work[a] > work[b]; });
     std::vector<Bin>& bins = D->bins[g];
     bins.clear();
@@ -535,6 +671,21 @@ static cudaError_t order_families(whale_data* D, int g, const std::vector<double
     if (bins.size() > 1 && bins.back().count < 64) { bins[bins.size() - 2].count += bins.back().count; bins.pop_back(); }
     for (const Bin& b : bins)
         std::stable_sort(perm.begin() + b.off, perm.begin() + b.off + b.count, [&](int x, int y) { return work[x] > work[y]; });
+    if (rev) {  // persistent CTAs: as many as the GPU holds at this bin's shared-memory need, one history slot each
+        D->rev_grid.clear(); D->rev_slot0.clear();
+        int slot = 0;
+        for (const Bin& b : bins) {
+            const int per_sm = (int)std::max<size_t>(1, cls(b.smem));
+            const int cap = env_int("WHALE_REV_GRID", per_sm * m->n_sm);
+            const int grid = std::max(1, std::min(b.count, cap));
+            D->rev_grid.push_back(grid);
+            D->rev_slot0.push_back(slot);
+            slot += grid;
+        }
+        if (D->d_hist) { cudaFree(D->d_hist); D->d_hist = nullptr; }
+        cudaError_t e = cudaMalloc((void**)&D->d_hist, std::max<size_t>((size_t)slot * D->hist_stride, 1) * sizeof(double));
+        if (e != cudaSuccess) return e;
+    }
     if (!D->d_perm[g]) {
         cudaError_t e = cudaMalloc((void**)&D->d_perm[g], std::max<size_t>(F, 1) * sizeof(int));
         if (e != cudaSuccess) return e;
@@ -809,6 +960,221 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
     return finalize_data(m, D, out);
 }
 
+// ---- reverse-mode gradient: transposed lists, built from the forward blobs (so the arena cache needs nothing new) ----
+// lane table of a slice loop: teams of 2^glog slots per cell, at most two terms per slot while E <= 64, largest teams
+// first (keeps teams aligned and makes the team size monotone over the warps)
+static bool make_slots(const uint32_t* ptr, int C, std::vector<Slot>& slots) {
+    std::vector<std::pair<int, int>> order;  // (-glog, cell)
+    std::vector<int> glogs(C);
+    for (int j = 0; j < C; j++) {
+        const uint32_t E = ptr[j + 1] - ptr[j];
+        int gl = 0;
+        while (gl < 5 && (2u << gl) < E) gl++;
+        glogs[j] = gl;
+        order.push_back({-gl, j});
+    }
+    std::stable_sort(order.begin(), order.end());
+    slots.clear();
+    for (auto& oc : order) {
+        const int j = oc.second, gl = glogs[j], G = 1 << gl;
+        const uint32_t E = ptr[j + 1] - ptr[j], first = ptr[j];
+        for (int l = 0; l < G; l++) {
+            const uint32_t cnt = (uint32_t)l < E ? (E - l + G - 1) / G : 0;
+            if (cnt > 255 || first + l > 65535u) return false;
+            slots.push_back(Slot{(uint16_t)j, (uint8_t)gl, (uint8_t)cnt, (uint16_t)(first + l), (uint16_t)G});
+        }
+    }
+    return true;
+}
+
+// returns false when a family cannot be represented (u16 entry indices): the handle then keeps forward tangents
+static bool build_reverse(whale_data* D) {
+    const whale_model* m = D->m;
+    const int nn = m->nn, F = D->F;
+    const std::vector<unsigned char>& A = D->arena_host;
+    std::vector<unsigned char>& RA = D->rarena_host;
+    RA.clear();
+    D->rhdr.assign(F, RevHdr{});
+    for (int f = 0; f < F; f++) {
+        const unsigned char* blob = A.data() + D->hdr[f].base;
+        const NodeRec* recs = reinterpret_cast<const NodeRec*>(blob);
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(blob);
+        const Ent* ents = reinterpret_cast<const Ent*>(blob);
+        std::vector<RevRec> rr(nn);
+        std::vector<uint32_t> wv;
+        std::vector<Ent> ev;
+        uint64_t hoff = 0;
+        for (int e = 0; e < nn; e++) {
+            RevRec& Q = rr[e];
+            memset(&Q, 0, sizeof(Q));
+            const NodeRec& R = recs[e];
+            const int C = (int)R.C, kind = m->kind[e];
+            if (kind == WHALE_LEAF) continue;
+            // (1) same-branch terms, transposed: the term (c; i1, i2, p) appears under i1 as (c, i2) and under i2 as (c, i1)
+            {
+                const uint32_t* dptr = words + R.dptr_off;
+                const Ent* dents = ents + R.dent_off;
+                std::vector<std::vector<Ent>> lists(C);
+                for (int c = 0; c < C; c++)
+                    for (uint32_t t = dptr[c]; t < dptr[c + 1]; t++) {
+                        const Ent& en = dents[t];
+                        lists[en.i1].push_back(Ent{(uint16_t)c, en.i2, 0u, en.p});
+                        lists[en.i2].push_back(Ent{(uint16_t)c, en.i1, 0u, en.p});
+                    }
+                pad4(wv);
+                Q.bptr_off = (uint32_t)wv.size();
+                Q.bent_off = (uint32_t)ev.size();
+                for (int c = 0; c < C; c++) {
+                    wv.push_back((uint32_t)ev.size() - Q.bent_off);
+                    ev.insert(ev.end(), lists[c].begin(), lists[c].end());
+                }
+                wv.push_back((uint32_t)ev.size() - Q.bent_off);
+                Q.nbent = (uint32_t)ev.size() - Q.bent_off;
+                pad4(wv);
+                Q.bslot_off = (uint32_t)wv.size();
+                if (kind != WHALE_ROOT && m->nsl[e] > 0) {
+                    std::vector<Slot> slots;
+                    if (!make_slots(wv.data() + Q.bptr_off, C, slots)) return false;
+                    Q.nbslots = (uint32_t)slots.size();
+                    const size_t w0 = wv.size();
+                    wv.resize(w0 + 2 * slots.size());
+                    if (!slots.empty()) memcpy(wv.data() + w0, slots.data(), slots.size() * sizeof(Slot));
+                }
+            }
+            // (2) speciation terms at row 1, grouped by the child's cell; Πloss transposed (the parent's cell of a child's cell)
+            if (kind == WHALE_INTERNAL || kind == WHALE_ROOT) {
+                const uint32_t* tptr = words + R.tptr_off;
+                const Ent* tents = ents + R.tent_off;
+                const int32_t* lossF = reinterpret_cast<const int32_t*>(tptr + C + 1);
+                const int32_t* lossG = lossF + C;
+                for (int j = 0; j < 2; j++) {
+                    const int ch = j == 0 ? m->child0[e] : m->child1[e];
+                    const int Cc = (int)recs[ch].C;
+                    std::vector<std::vector<Ent>> lists(Cc);
+                    std::vector<uint32_t> up(Cc, 0xffffffffu);
+                    for (int c = 0; c < C; c++) {
+                        const int32_t lc = j == 0 ? lossF[c] : lossG[c];
+                        if (lc >= 0) up[lc] = (uint32_t)c;
+                        for (uint32_t t = tptr[c]; t < tptr[c + 1]; t++) {
+                            const Ent& en = tents[t];  // i1 = first child's cell, i2 = second child's cell
+                            if (j == 0) lists[en.i1].push_back(Ent{(uint16_t)c, en.i2, 0u, en.p});
+                            else lists[en.i2].push_back(Ent{(uint16_t)c, en.i1, 0u, en.p});
+                        }
+                    }
+                    for (int c = 0; c < Cc; c++) if (up[c] == 0xffffffffu) return false;  // (a child's clade is always the parent's)
+                    pad4(wv);
+                    const uint32_t woff = (uint32_t)wv.size(), eoff = (uint32_t)ev.size();
+                    for (int c = 0; c < Cc; c++) {
+                        wv.push_back((uint32_t)ev.size() - eoff);
+                        ev.insert(ev.end(), lists[c].begin(), lists[c].end());
+                    }
+                    wv.push_back((uint32_t)ev.size() - eoff);
+                    wv.insert(wv.end(), up.begin(), up.end());
+                    if (j == 0) { Q.sF_off = woff; Q.sFent_off = eoff; Q.nsFent = (uint32_t)ev.size() - eoff; }
+                    else { Q.sG_off = woff; Q.sGent_off = eoff; Q.nsGent = (uint32_t)ev.size() - eoff; }
+                }
+            }
+            if (kind != WHALE_ROOT) {
+                if (hoff > 0xffffffffull) return false;
+                Q.hoff = (uint32_t)hoff;
+                hoff += (uint64_t)(m->nsl[e] + 1) * ((C + 1) & ~1);
+            }
+        }
+        pad4(wv);
+        if (hoff > 0xffffffffull) return false;
+        const size_t base = (RA.size() + 15) & ~size_t(15);
+        const size_t words_at = (size_t)nn * sizeof(RevRec);
+        const size_t ents_at = words_at + wv.size() * 4;
+        const size_t total = ents_at + ev.size() * sizeof(Ent);
+        if (total > 0xffffffffull) return false;
+        RA.resize(base + total, 0);
+        for (int e = 0; e < nn; e++) {
+            RevRec& Q = rr[e];
+            Q.bptr_off += (uint32_t)(words_at / 4); Q.bslot_off += (uint32_t)(words_at / 4);
+            Q.sF_off += (uint32_t)(words_at / 4); Q.sG_off += (uint32_t)(words_at / 4);
+            Q.bent_off += (uint32_t)(ents_at / 16); Q.sFent_off += (uint32_t)(ents_at / 16); Q.sGent_off += (uint32_t)(ents_at / 16);
+        }
+        memcpy(RA.data() + base, rr.data(), words_at);
+        if (!wv.empty()) memcpy(RA.data() + base + words_at, wv.data(), wv.size() * 4);
+        if (!ev.empty()) memcpy(RA.data() + base + ents_at, ev.data(), ev.size() * sizeof(Ent));
+        RevHdr& H = D->rhdr[f];
+        H.base = base;
+        H.blob_bytes = (uint32_t)total;
+        H.hist_len = (uint32_t)hoff;
+    }
+    return true;
+}
+
+static size_t smem_need_rev(const whale_model* m, const FamHdr& h, const RevHdr& r) {  // mirrors the carve-up in k_dp_rev
+    const size_t nn = m->nn, NW = dp_nt() / 32;
+    const size_t hdr = ((((9 * nn + 4) * sizeof(int)) + 15) & ~size_t(15)) + nn * (sizeof(NodeRec) + sizeof(RevRec)) +
+                       (10 * nn + NW * 8 + 8) * sizeof(double);
+    const size_t leaf = NW * ((size_t)r.leafmax * sizeof(double) + h.leaf_stage);
+    const size_t back = ((size_t)r.arows_len + 3 * (size_t)r.hbuf_len) * sizeof(double);
+    return hdr + ((size_t)r.rows_len + r.scr_len) * sizeof(double) + r.stage_bytes + std::max(leaf, back);
+}
+
+// shared-memory budgets of the reverse-mode kernel (hybrid plan), row and adjoint-row placement; returns the largest need
+static size_t set_budgets_rev(whale_data* D) {
+    const whale_model* m = D->m;
+    const Plan& pl = m->planR;
+    const int nn = m->nn;
+    size_t worst = 0;
+    D->roff_host[1].assign((size_t)D->F * nn, 0);
+    D->aoff_host.assign((size_t)D->F * nn, 0);
+    size_t hist_max = 0;
+    auto even = [](uint32_t v) { return (v + 1) & ~1u; };
+    for (int f = 0; f < D->F; f++) {
+        RevHdr& H = D->rhdr[f];
+        const std::vector<uint32_t>& Cs = D->famC[f];
+        const NodeRec* recs = reinterpret_cast<const NodeRec*>(D->arena_host.data() + D->hdr[f].base);
+        const RevRec* rrs = reinterpret_cast<const RevRec*>(D->rarena_host.data() + H.base);
+        uint32_t mxinner = 0, mxleaf = 0, hbuf = 0;
+        size_t stg = 0;
+        for (int e = 0; e < nn; e++) {
+            const uint32_t K = (uint32_t)pl.K[e], ck = Cs[e] * (uint32_t)RS(K);
+            const size_t n1 = (size_t)m->nsl[e] + 1;
+            if (m->kind[e] == WHALE_LEAF) {
+                if (recs[e].nslots > HEAVY_SLOTS) {
+                    mxinner = std::max(mxinner, ck);
+                    stg = std::max(stg, (size_t)recs[e].ndent + (recs[e].nslots + 1) / 2 + n1 * K);
+                } else {
+                    mxleaf = std::max(mxleaf, ck);
+                }
+            } else if (m->kind[e] != WHALE_ROOT) {
+                mxinner = std::max(mxinner, even(Cs[e]));
+                hbuf = std::max(hbuf, even(Cs[e]));
+                stg = std::max(stg, (size_t)recs[e].ndent + (recs[e].nslots + 1) / 2 + n1);            // forward lists + ϕ/ψ rows
+                stg = std::max(stg, (size_t)rrs[e].nbent + (rrs[e].nbslots + 1) / 2 + 4 * n1);         // backward lists + local rows
+            }
+        }
+        std::vector<int> roff(nn + 1), aoff(nn + 1, 0);
+        const int rows = place_rows(nn, (int)m->leafnodes.size(), m->leafnodes.data(), (int)m->inner.size(), m->inner.data(),
+                                    m->child0.data(), m->child1.data(), m->kind.data(),
+                                    [&](int e2) { return (int)(Cs[e2] * (uint32_t)RS(pl.K[e2])); }, roff.data(), true);
+        const int arows = place_arows((int)m->inner.size(), m->inner.data(), m->child0.data(), m->child1.data(), m->kind.data(),
+                                      [&](int e2) { return (int)Cs[e2]; }, aoff.data());
+        for (int e = 0; e < nn; e++) {
+            D->roff_host[1][(size_t)f * nn + e] = (uint32_t)roff[e];
+            D->aoff_host[(size_t)f * nn + e] = (uint32_t)aoff[e];
+        }
+        H.rows_len = even((uint32_t)rows);
+        H.scr_len = even(mxinner);
+        H.leafmax = even(mxleaf);
+        H.arows_len = even((uint32_t)arows);
+        H.hbuf_len = hbuf;
+        const size_t STAGE_MAX = (size_t)env_int("WHALE_STAGE_MAX", D->F <= 160 ? 160 * 1024 : 24 * 1024);
+        H.stage_bytes = 16 * stg > STAGE_MAX ? 0u : (uint32_t)(16 * stg);
+        hist_max = std::max(hist_max, (size_t)H.hist_len);
+        worst = std::max(worst, smem_need_rev(m, D->hdr[f], H));
+        if (env_int("WHALE_DEBUG", 0) >= 2)
+            fprintf(stderr, "[whale] fam %d reverse: rows %u scr %u leafmax %u stage %u arows %u hbuf %u hist %u -> %zu B\n", f,
+                    H.rows_len, H.scr_len, H.leafmax, H.stage_bytes, H.arows_len, H.hbuf_len, H.hist_len, smem_need_rev(m, D->hdr[f], H));
+    }
+    D->hist_stride = (hist_max + 1) & ~size_t(1);
+    return worst;
+}
+
 // Second half of whale_data_create, shared with whale_data_load: tangent plans and shared-memory budgets for this
 // model/plan (they depend on the runtime configuration, not on the CCDs), launch order, upload, calibration.
 // Takes ownership of D (deleted on failure).
@@ -818,10 +1184,23 @@ static int32_t finalize_data(whale_model* m, whale_data* D, whale_data_t* out) {
     // ---- tangent plans: one gradient pass if every family's working set fits, else parameter chunks ----
     D->plans = {&m->plan[0], &m->plan[1]};
     set_budgets(D, 0, m->plan[0]);
-    size_t need1 = set_budgets(D, 1, m->plan[1]);
     const size_t SMEM_MAX = 227 * 1024;
     const size_t SMEM_GOAL = (size_t)env_int("WHALE_SMEM_GOAL", 80000);  // default: at least two families per SM
-    if (need1 > SMEM_GOAL || m->plan[1].Kmax > dp_nt()) {
+    // Gradient mode: reverse (adjoint) DP by default — one pass whatever P is; WHALE_GRAD_MODE=fwd keeps the forward
+    // tangents of k_dp (also the fallback when a family does not fit the reverse kernel's working set)
+    {
+        const char* gm = getenv("WHALE_GRAD_MODE");
+        if (!(gm && !strcmp(gm, "fwd")) && m->plan[1].K[m->root] <= dp_nt() && build_reverse(D)) {
+            const size_t need_rev = set_budgets_rev(D);
+            D->rev = need_rev <= SMEM_MAX;
+            if (env_int("WHALE_DEBUG", 0) >= 1)
+                fprintf(stderr, "[whale] %d families, P = %d: reverse-mode gradient, worst family %zu B of shared memory%s\n", F, m->P,
+                        need_rev, D->rev ? "" : " (does not fit: forward tangents)");
+        }
+        if (!D->rev) { std::vector<unsigned char>().swap(D->rarena_host); D->rhdr.clear(); }
+    }
+    size_t need1 = D->rev ? 0 : set_budgets(D, 1, m->plan[1]);
+    if (!D->rev && (need1 > SMEM_GOAL || m->plan[1].Kmax > dp_nt())) {
         // parameters ordered by the node that owns them (subtrees stay together -> sparse chunks)
         std::vector<int> porder;
         std::vector<char> seen(m->P, 0);
@@ -866,7 +1245,7 @@ static int32_t finalize_data(whale_model* m, whale_data* D, whale_data_t* out) {
             }
         }
     }
-    if (env_int("WHALE_DEBUG", 0) >= 1)
+    if (env_int("WHALE_DEBUG", 0) >= 1 && !D->rev)
         fprintf(stderr, "[whale] %d families, P = %d: %zu gradient pass(es), worst family %zu B of shared memory\n", F, m->P,
                 D->plans.size() - 1, need1);
     if (need1 > SMEM_MAX) { delete D; return fail(WHALE_ERR_CAPACITY, "a family needs %zu bytes of shared memory (> 227 KB) even with %d parameter chunks", need1, MAXPLAN - 1); }
@@ -883,6 +1262,16 @@ static int32_t finalize_data(whale_model* m, whale_data* D, whale_data_t* out) {
     CU(cudaMemcpy(D->d_arena, A.data(), A.size(), cudaMemcpyHostToDevice));
     D->arena_bytes = A.size();
     std::vector<unsigned char>().swap(A);
+    if (D->rev) {
+        CU(cudaMalloc((void**)&D->d_rarena, std::max<size_t>(D->rarena_host.size(), 16)));
+        CU(cudaMemcpy(D->d_rarena, D->rarena_host.data(), D->rarena_host.size(), cudaMemcpyHostToDevice));
+        D->rarena_bytes = D->rarena_host.size();
+        std::vector<unsigned char>().swap(D->rarena_host);
+        CU(upload(D->rhdr, &D->d_rhdr));
+        CU(upload(D->aoff_host, &D->d_aoff));
+        CU(cudaMalloc((void**)&D->d_next, MAX_BINS * sizeof(unsigned int)));
+        CU(cudaMemset(D->d_next, 0, MAX_BINS * sizeof(unsigned int)));
+    }
     CU(upload(D->hdr, &D->d_hdr));
     CU(cudaMalloc((void**)&D->d_out_fam, D->out_total * sizeof(double)));
     CU(cudaMalloc((void**)&D->d_partial, (size_t)1024 * m->plan[1].Kmax * sizeof(double)));
@@ -1072,6 +1461,7 @@ int32_t whale_data_destroy(whale_data_t d) {
     for (int g = 0; g < MAXPLAN; g++) { cudaFree(d->d_perm[g]); cudaFree(d->d_roff[g]); }
     for (Plan& cp : d->chunk_plans) for (void* q : cp.owned) cudaFree(q);
     cudaFree(d->d_out_fam); cudaFree(d->d_partial); cudaFree(d->d_done);
+    cudaFree(d->d_rarena); cudaFree(d->d_rhdr); cudaFree(d->d_aoff); cudaFree(d->d_hist); cudaFree(d->d_next);
     for (int i = 0; i < MAX_BINS; i++) {
         if (d->side[i]) cudaStreamDestroy(d->side[i]);
         if (d->ev_join[i]) cudaEventDestroy(d->ev_join[i]);
@@ -1121,6 +1511,62 @@ static int32_t ensure_nowhere(whale_model* m, Plan& pl) {
     return WHALE_OK;
 }
 
+// reverse-mode gradient evaluation: [three table sets in one launch -> k_dp_rev (persistent CTAs) -> reduction in its tail]
+static int32_t enqueue_eval_rev(whale_model* m, whale_data* D, const double* d_x, int32_t condition, uint32_t flags,
+                                double* d_out, cudaStream_t st) {
+    const int F = D->F, NT = dp_nt(), MB = dp_minb();
+    const bool prof = (flags & WHALE_PROFILE) != 0;
+    Plan& pg = m->plan[1];
+    CU(cudaMemsetAsync(d_out, 0, (1 + m->P) * sizeof(double), st));
+    CU(cudaMemsetAsync(D->d_next, 0, MAX_BINS * sizeof(unsigned int), st));
+    if (prof) CU(cudaEventRecord(D->ev[0], st));
+    CU(launch_tables3(m, d_x, m->d_pleaf, st));
+    if (condition == WHALE_COND_NOWHERE) {
+        int32_t rcn = ensure_nowhere(m, pg);
+        if (rcn != WHALE_OK) return rcn;
+        LAUNCH(k_nowhere, 1, 256, 0, st, m->dev, pg.dev, d_x);
+        g_launches++;
+    }
+    if (prof) CU(cudaEventRecord(D->ev[1], st));
+    const int KR = pg.K[m->root];
+    double* out_fam = D->d_out_fam + D->out_off[1];
+    const bool fused = fused_reduce() && (size_t)F * KR <= ((size_t)1 << 20) && KR <= 1024;
+    const std::vector<Bin>& bins = D->bins[1];
+    const size_t tail_smem = (size_t)(NT + 2 * KR + 2) * sizeof(double);
+    auto launch_bin = [&](size_t b, cudaStream_t s) {
+        RevArgs a{m->dev, m->planR.dev, pg.dev, m->planL.dev, D->d_arena, D->d_hdr, D->d_rarena, D->d_rhdr, D->d_perm[1],
+                  D->d_roff[1], D->d_aoff, m->d_rinv, out_fam, D->d_hist, (unsigned long long)D->hist_stride, D->d_next + b,
+                  bins[b].off, bins[b].count, D->rev_slot0[b], prof ? D->d_tim : nullptr, fused ? D->d_done : nullptr, F,
+                  condition, d_out};
+#define LAUNCHV(NTV, MBV) if (NT == NTV && MB == MBV) LAUNCH((k_dp_rev<NTV, MBV>), D->rev_grid[b], NTV, std::max(bins[b].smem, tail_smem), s, a);
+        REV_VARIANTS(LAUNCHV)
+#undef LAUNCHV
+        g_launches++;
+    };
+    if (bins.size() == 1) {
+        launch_bin(0, st);
+    } else {
+        CU(cudaEventRecord(D->ev_fork, st));
+        for (size_t b = 0; b < bins.size(); b++) {
+            CU(cudaStreamWaitEvent(D->side[b], D->ev_fork, 0));
+            launch_bin(b, D->side[b]);
+            CU(cudaEventRecord(D->ev_join[b], D->side[b]));
+            CU(cudaStreamWaitEvent(st, D->ev_join[b], 0));
+        }
+    }
+    if (prof) CU(cudaEventRecord(D->ev[2], st));
+    if (!fused) {
+        const int nb = std::min(1024, (F + 255) / 256), chunk = (F + nb - 1) / nb;
+        LAUNCH(k_reduce1, nb, 256, 0, st, out_fam, F, KR, chunk, D->d_partial);
+        LAUNCH(k_reduce2, 1, 256, 0, st, D->d_partial, nb, KR, F, condition, pg.dev, m->root, 1, d_out);
+        g_launches += 2;
+    }
+    if (prof) CU(cudaEventRecord(D->ev[3], st));
+    D->ev_valid = prof;
+    CU(cudaGetLastError());
+    return WHALE_OK;
+}
+
 // enqueue [tables -> DP -> reduction] for every tangent plan of this evaluation on `st`; result in d_out
 static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, int32_t condition, uint32_t flags,
                             double* d_out, cudaStream_t st) {
@@ -1135,14 +1581,23 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
         CU(cudaMalloc((void**)&D->d_tim, (size_t)F * TIMW * sizeof(long long)));
         CU(cudaMemset(D->d_tim, 0, (size_t)F * TIMW * sizeof(long long)));
     }
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
+    if (!m->attr_set) {  // function attributes are per device: once per model (a model lives on one device)
 #define SETATTR(NTV, MB) CU(cudaFuncSetAttribute(k_dp<NTV, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         DP_VARIANTS(SETATTR)
 #undef SETATTR
-        attr_set = true;
+#define SETATTR(NTV, MB) CU(cudaFuncSetAttribute(k_dp_rev<NTV, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        REV_VARIANTS(SETATTR)
+#undef SETATTR
+        m->attr_set = true;
     }
     const int NT = dp_nt();
+    if (grad && D->rev) {
+        if (keep) {  // logpdf! + gradient: ℓ comes from the value-only forward kernel, the gradient from the reverse pass
+            int32_t rck = enqueue_eval(m, D, d_x, condition, flags & ~WHALE_WANT_GRAD, d_out, st);
+            if (rck != WHALE_OK) return rck;
+        }
+        return enqueue_eval_rev(m, D, d_x, condition, flags, d_out, st);
+    }
     const size_t g0 = grad ? 1 : 0, g1 = grad ? D->plans.size() : 1;
     CU(cudaMemsetAsync(d_out, 0, (1 + m->P) * sizeof(double), st));
     for (size_t g = g0; g < g1; g++) {
