@@ -139,6 +139,11 @@ int32_t whale_data_save(whale_data_t d, const char* path);
 int32_t whale_data_load(whale_model_t m, const char* path, whale_data_t* out);
 int32_t whale_data_destroy(whale_data_t d);
 int32_t whale_data_nfam(whale_data_t d);
+/* how this handle computes gradients: 1 = reverse-mode (adjoint) DP, one pass whatever P is (the default);
+ * 0 = forward tangents (WHALE_GRAD_MODE=fwd, or a family that does not fit the reverse kernel's working set), in
+ * whale_data_grad_passes() passes over parameter chunks */
+int32_t whale_data_grad_mode(whale_data_t d);
+int32_t whale_data_grad_passes(whale_data_t d);
 /* bytes of the packed arena resident in HBM, and the algorithmic bytes one evaluation reads */
 int64_t whale_data_arena_bytes(whale_data_t d);
 /* copies the packed arena back (for the bit-exact packing tests); buf may be NULL to query the size */
@@ -227,7 +232,9 @@ int32_t whale_last_kernel_ms(whale_data_t d, double* tables_ms, double* dp_ms, d
 int32_t whale_last_backtrack_ms(whale_data_t d, double* ms);
 
 /* SM-cycle breakdown of the DP kernel over the families of the last WHALE_PROFILE evaluation (mean and max
- * over families): [prologue, leaf phase, staging, row 1, slices, root, total, 0] */
+ * over families): forward tangents [prologue, leaf phase, staging, row 1, slices, root, total, 0]; reverse mode
+ * [prologue, leaf phase, forward staging + row 1, transposed row 1, slices forward + transposed, root forward +
+ * transposed, total, contraction] */
 int32_t whale_last_phase_cycles(whale_data_t d, double* mean8, double* max8);
 
 /* same evaluation, per inner node in processing order (internal / WGD nodes, the root last): mean SM cycles of

@@ -81,6 +81,7 @@ def test_emu_backtrack_matches_oracle(L):
 def test_emu_parameter_chunks(L, monkeypatch):
     """Families whose full-tangent working set exceeds the shared-memory goal get their gradient in several
     passes over parameter chunks; force that with a tiny goal and compare with the oracle (37 parameters)."""
+    monkeypatch.setenv("WHALE_GRAD_MODE", "fwd")
     monkeypatch.setenv("WHALE_SMEM_GOAL", "25000")  # -> 6 passes
     run_parity(L, "c1_example1", sel=[3], conds=["root"])
     monkeypatch.setenv("WHALE_SMEM_GOAL", "6000")  # -> one pass per parameter (37)
@@ -295,31 +296,54 @@ def test_emu_arena_cache_round_trip(L, tmp_path):
         wlib.use(None)
 
 
-def test_emu_odd_row_stride_variant(tmp_path):
-    """The round-2 experiment build — WHALE_ODD_STRIDE (rows of even K padded to K+1 doubles per cell against
-    shared-memory bank conflicts) and WHALE_TAB_PROJ (division-free projective chain over the tree levels in k_tables),
-    both off in the product build — must give the same numbers: slice tables, known answer, 37-parameter gradient,
-    constant-rates WGD model, MUL tree, kept ℓ, backtracking, the rates around the critical case and the
-    Nowhere-extinct condition."""
-    L2 = wlib.Lib(os.path.join(ROOT, "tests", "emu", "libwhalecuda_emu_oddstride.so"))
-    for name in ("c1_example1", "const_wgdturing"):
-        gg = load_golden(name)
-        mh_ = L2.model_create(golden_model(gg))
-        nrow = int((gg["m_nslices"] + 1).sum())
-        for xi, x in enumerate(gg["xs"]):
-            np.testing.assert_allclose(np.stack(L2.slices(mh_, x, gg["m_pleaf"], nrow), 1), gg["slices"][xi], rtol=1e-12)
-    from conftest import near_critical_vs_oracle, nowhere_condition_vs_oracle
+def test_emu_forward_tangent_mode(monkeypatch, tmp_path):
+    """WHALE_GRAD_MODE=fwd keeps k_dp's forward tangents (the round-1 gradient path, still the fallback for families that
+    do not fit the reverse kernel's working set): same numbers as the default reverse-mode gradient."""
+    monkeypatch.setenv("WHALE_GRAD_MODE", "fwd")
+    L2 = wlib.Lib(EMU)
+    g = load_golden("c1_example1")
+    mh = L2.model_create(golden_model(g))
+    dh = L2.data_create(mh, golden_fams(g, [3]))
+    assert L2.L.whale_data_grad_mode(dh) == 0
+    L2.L.whale_data_destroy(dh)
+    L2.L.whale_model_destroy(mh)
+    run_parity(L2, "c1_example1", sel=[0, 3], conds=["root"])
+    run_parity(L2, "const_wgdturing", sel=[1, 7], conds=["nonextinct"])
+    run_parity(L2, "mul_tree", sel=[2], conds=["root"])
+    from conftest import near_critical_vs_oracle
     wlib.use(L2)
     try:
         near_critical_vs_oracle(tmp_path, n_fam=2)
     finally:
         wlib.use(None)
-    nowhere_condition_vs_oracle(L2)
-    g = run_parity(L2, "c1_maxn5")
-    assert g["tot_none"][0] == pytest.approx(-60.96367806571888, rel=1e-12)
-    run_parity(L2, "c1_example1", sel=[0, 3], conds=["root"])
-    run_parity(L2, "const_wgdturing", sel=[1, 7], conds=["nonextinct"])
-    run_parity(L2, "mul_tree", sel=[2], conds=["root"])
+
+
+def test_emu_reverse_mode_is_default_and_persistent(monkeypatch):
+    """The default gradient is the reverse-mode kernel; with ONE persistent CTA (WHALE_REV_GRID=1) every family goes
+    through the same CTA's loop (history slot, shared-memory carve-up and adjoint rows reused from family to family)."""
+    monkeypatch.setenv("WHALE_REV_GRID", "1")
+    L2 = wlib.Lib(EMU)
+    g = load_golden("c1_example1")
+    mh = L2.model_create(golden_model(g))
+    dh = L2.data_create(mh, golden_fams(g, [0, 1]))
+    assert L2.L.whale_data_grad_mode(dh) == 1 and L2.L.whale_data_grad_passes(dh) == 1
+    L2.L.whale_data_destroy(dh)
+    L2.L.whale_model_destroy(mh)
+    run_parity(L2, "c1_example1", sel=[5, 0, 9, 3], conds=["root"])
+    run_parity(L2, "const_wgdturing", sel=[1, 7, 2], conds=["none"])
+
+
+def test_emu_even_row_stride_variant(tmp_path):
+    """The dense row layout of round 1 (WHALE_EVEN_STRIDE; the product build pads rows of even K to K+1 doubles per cell
+    against shared-memory bank conflicts) must give the same numbers: forward-tangent gradient with 37 parameters,
+    constant-rates WGD model, kept ℓ, backtracking."""
+    L2 = wlib.Lib(os.path.join(ROOT, "tests", "emu", "libwhalecuda_emu_evenstride.so"))
+    os.environ["WHALE_GRAD_MODE"] = "fwd"
+    try:
+        run_parity(L2, "c1_example1", sel=[0, 3], conds=["root"])
+        run_parity(L2, "const_wgdturing", sel=[1, 7], conds=["nonextinct"])
+    finally:
+        del os.environ["WHALE_GRAD_MODE"]
     _check_backtrack(L2, "const_wgdturing", [2])
     g = load_golden("c1_example1")
     mh = L2.model_create(golden_model(g))

@@ -39,7 +39,9 @@ def main():
     ap.add_argument("--c3-families", type=int, default=2000)
     ap.add_argument("--c4-families", type=int, default=64)
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--only", default="", help="comma list of c3,c4 (default: both)")
     args = ap.parse_args()
+    only = set(filter(None, args.only.split(",")))
     import whale_jl_b200 as W
     from whale_jl_b200 import synth, newick, lib as wlib
     from whale_jl_b200.core import _data_handle
@@ -50,12 +52,18 @@ def main():
     d = synth.generate(os.path.join(ROOT, ".synth_cache", f"c3_seed3_n{args.c3_families}"), args.c3_families, seed=3)
     r = W.DLWGD(lam=list(rng.normal(np.log(0.15), 0.3, 17)), mu=list(rng.normal(np.log(0.15), 0.3, 17)), q=[0.2, 0.1], eta=0.67)
     w = W.WhaleModel(r, synth.c1_species_tree(), 0.05)
-    ccd = W.read_ale(d, w)
+    ccd = W.read_ale_native(d, w)
     mh, dh = _data_handle(w, ccd)
     x0 = w.x()
     xs = x0[None, :] + 0.02 * rng.standard_normal((args.reps + 3, len(x0)))
     xs[:, -3:] = np.clip(xs[:, -3:], 1e-3, 1 - 1e-3)
-    out["C3"] = dict(rate(L, mh, dh, w, xs, args.reps, len(ccd)), P=int(w.n_params), gradient_passes="see DESIGN §3.1")
+    out["C3"] = dict(rate(L, mh, dh, w, xs, args.reps, len(ccd)), P=int(w.n_params),
+                     grad_mode="reverse" if L.L.whale_data_grad_mode(dh) == 1 else "forward",
+                     gradient_passes=int(L.L.whale_data_grad_passes(dh)))
+    L.L.whale_data_destroy(dh)
+    if only and "c4" not in only:
+        print(json.dumps(out))
+        return
     # ---- C4: 30 taxa, 5 WGDs, ~2,000 clades ----
     nws = newick.nwstr(synth.c4_species_tree(), True) + ";"
     d = synth.generate(os.path.join(ROOT, ".synth_cache", f"c4_seed4_n{args.c4_families}"), args.c4_families, seed=4,

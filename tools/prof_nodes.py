@@ -36,7 +36,8 @@ def main():
     ms = np.array(ms)[3:]
     sl, r1 = L.last_node_cycles(dh)
     inner = [int(e) for e in w.order if w.kind[e] != 0]
-    out = {"kernels_ms": dict(zip(["k_tables", "k_dp", "k_reduce"], ms.mean(0).round(4).tolist())),
+    rev = L.L.whale_data_grad_mode(dh) == 1  # reverse mode: per node [forward total, transposed total] (whale_rev.cuh)
+    out = {"grad_mode": "reverse" if rev else "forward", "kernels_ms": dict(zip(["k_tables", "k_dp", "k_reduce"], ms.mean(0).round(4).tolist())),
            "phases": L.last_phase_cycles(dh),
            "nodes": [{"node": e, "kind": int(w.kind[e]), "n_slices": int(w.n_slices[e]), "slices_cycles": round(a),
                       "per_slice": round(a / max(1, int(w.n_slices[e]))), "stage_row1_cycles": round(b)}

@@ -18,7 +18,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT
     nvcc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", OUT, SRC]
+    # WHALE_DEV_BUILD=1: only the default launch shape of k_dp / k_dp_rev (a quarter of the compile time; experiments)
+    dev = ["-DWHALE_DEV_BUILD"] if os.environ.get("WHALE_DEV_BUILD") else []
+    cmd = [nvcc, *NVCC_FLAGS, *dev, *(["-Xptxas", "-v"] if verbose else []), "-o", OUT, SRC]
     subprocess.check_call(cmd)
     return OUT
 

@@ -176,6 +176,10 @@ struct PlanDev {  // tangent plan: which raw parameters each branch carries
     const long long* nwoff;  // [nn] offset of node e's pgf vector  } first use (k_nowhere)
     double* nwvec;         // Σ_e 2^L_e · K_e doubles
     long long* tim;        // [32] k_tables cycle stamps (profiling aid)
+    // reverse-mode gradient, full plan only: k_tables3 stops after the chain over the tree's height and writes the
+    // Jacobian of the local quantities the adjoint pass differentiates with respect to — jac[(e*8 + j)*KR + k], KR = K[root]
+    const int16_t* rinv;   // [nn][KR] component of root component k in node e's list (−1: none)
+    double* jac;
 };
 
 #ifdef WHALE_EMU

@@ -46,8 +46,10 @@ constexpr int TIMN = 32, TIMW = 8 + 2 * TIMN;
 
 #ifdef WHALE_EMU
 #define PREFETCH_L2(p) ((void)0)
+#define PREFETCH_L1(p) ((void)0)
 #else
 #define PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#define PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 #endif
 
 // copy n16 16-byte words global -> shared with all threads of the scope.  cp.async keeps every copy of a

@@ -40,7 +40,6 @@ struct RevArgs {
     const int* perm;
     const uint32_t* roff;  // [F][nn] last-row offsets (doubles) in `rows`
     const uint32_t* aoff;  // [F][nn] adjoint-row offsets (doubles) in `arows`
-    const int16_t* rinv;   // [nn][KR] component of root component k in node e's full-plan list (−1: none)
     double* out_fam;       // [F * KR]
     double* hist;          // per-CTA history slots
     unsigned long long hist_stride;  // doubles per slot
@@ -101,56 +100,131 @@ __device__ __forceinline__ void block_sum(double (&v)[N], double* s_red, double*
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// The n slices of one branch, transposed (see the header).  `cur` holds ℓ̄_n on entry; rows alternate between
-// arow and scr; returns the buffer holding ℓ̄_0.  hist = the branch's kept rows (global, row stride Cp), staged
-// into the three rotating buffers hb[0..2] (hlen doubles each): row i−1 is in use by slice i, row i−2 is landing,
-// row i−3 is being issued — one barrier per slice.  lpp = the local table rows (4 double2 per row: value, ∂λ, ∂μ,
-// ∂ϵ_0).  acc[0..2] += this thread's share of (λ̄, μ̄, ϵ̄⁰).
+// Slice loops of the reverse-mode kernel (K = 1: one double per cell).  A thread owns up to two slots of the packer's
+// lane table per slice ("passes" 0 and 1, descriptors in registers); both passes are carried through the gathers, the
+// team reduction and the leader's update TOGETHER, so their shuffle chains overlap instead of running back to back
+// (the slice is a latency chain, not a throughput problem: profiles/r2_ncu_k_dp_rev_v1_*).
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bslice_pass(const LaneWork<1>& w, int wg, bool two, bool more, int sidx,
-                                            const double* __restrict__ src, const double* __restrict__ val,
-                                            double* __restrict__ dst, const double2* __restrict__ lp,
-                                            const Ent* s_ents, double (&acc)[3]) {
-    if (wg == 0) return;
+struct Pass2 {
+    LaneWork<1> w0, w1;
+    int wg0, wg1;          // team size of the warp's first lane in each pass (0: the warp owns no slot of that pass)
+    bool two0, more0, two1, more1;
+    bool lead0, lead1;
+    int c0, c1;
+};
+__device__ __forceinline__ Pass2 load_pass2(const Slot* s_slots, int nslots, const Ent* s_ents, int tid, int nt) {
+    Pass2 P;
+    const int wbase = tid & ~31;
+    P.w0 = load_work<1>(s_slots, nslots, s_ents, tid);
+    P.w1 = load_work<1>(s_slots, nslots, s_ents, tid + nt);
+    P.wg0 = wbase < nslots ? (1 << s_slots[wbase].glog) : 0;
+    P.wg1 = (wbase + nt) < nslots ? (1 << s_slots[wbase + nt].glog) : 0;
+    P.two0 = WARP_ANY(P.w0.cnt > 1); P.more0 = WARP_ANY(P.w0.cnt > 2);
+    P.two1 = WARP_ANY(P.w1.cnt > 1); P.more1 = WARP_ANY(P.w1.cnt > 2);
+    P.lead0 = P.w0.cell >= 0 && (tid & (P.w0.gsz - 1)) == 0;
+    P.lead1 = P.w1.cell >= 0 && ((tid + nt) & (P.w1.gsz - 1)) == 0;
+    P.c0 = max(P.w0.cell, 0); P.c1 = max(P.w1.cell, 0);
+    return P;
+}
+// Σ over the lane's share of one cell's terms: p·X[i1]·Y[i2] (the first two terms from registers)
+__device__ __forceinline__ double lane_terms(const LaneWork<1>& w, bool two, bool more, const double* __restrict__ X,
+                                             const double* __restrict__ Y, const Ent* s_ents) {
     double s;
-    if (two) s = fma(w.pb * src[w.b1], val[w.b2], (w.pa * src[w.a1]) * val[w.a2]);
-    else s = (w.pa * src[w.a1]) * val[w.a2];
+    if (two) s = fma(w.pb * X[w.b1], Y[w.b2], (w.pa * X[w.a1]) * Y[w.a2]);
+    else s = (w.pa * X[w.a1]) * Y[w.a2];
     if (more) {
         for (int j = 2; j < w.cnt; j++) {
             const Ent en = s_ents[w.first + j * w.gsz];
-            s = fma(en.p * src[en.i1], val[en.i2], s);
+            s = fma(en.p * X[en.i1], Y[en.i2], s);
         }
     }
-    const bool lead = w.cell >= 0 && (sidx & (w.gsz - 1)) == 0;
-    const int c = max(w.cell, 0);
-    const double o = src[c], y = val[c];
-    const double2 t0 = lp[0], t1 = lp[1], t2 = lp[2], t3 = lp[3];
+    return s;
+}
+// team reduction of both passes' partial sums, interleaved (lane j adds lane j+step while step is inside its own team;
+// the mask multiplies instead of selecting: fma(t, 1, s) is the correctly rounded s + t)
+__device__ __forceinline__ void team_reduce2(const Pass2& P, double& s0, double& s1) {
+    for (int step = 1; step < P.wg0; step <<= 1) {  // slots are sorted by team size: wg1 <= wg0
+        const double m0 = step < P.w0.gsz ? 1.0 : 0.0, m1 = step < P.w1.gsz ? 1.0 : 0.0;
+        const double t0 = SHFL_DOWN(s0, step), t1 = SHFL_DOWN(s1, step);
+        s0 = fma(t0, m0, s0);
+        s1 = fma(t1, m1, s1);
+    }
+}
+__device__ __forceinline__ void team_reduce1(const LaneWork<1>& w, int wg, double& s) {
     for (int step = 1; step < wg; step <<= 1) {
         const double m = step < w.gsz ? 1.0 : 0.0;
         s = fma(SHFL_DOWN(s, step), m, s);
     }
-    if (lead) {
-        dst[c] = fma(t0.x, o, t0.y * s);
-        const double wphi = o * y, wpsi = 0.5 * (y * s);
-        acc[0] = fma(wphi, t1.x, fma(wpsi, t1.y, acc[0]));
-        acc[1] = fma(wphi, t2.x, fma(wpsi, t2.y, acc[1]));
-        acc[2] = fma(wphi, t3.x, fma(wpsi, t3.y, acc[2]));
+}
+
+// coalesced copy of one finished row (Cp doubles, 16-byte aligned on both sides) from shared memory to the history
+__device__ __forceinline__ void keep_row(double* __restrict__ g, const double* __restrict__ srow, int Cp, int tid, int nt) {
+    for (int c = tid; c < (Cp >> 1); c += nt) reinterpret_cast<double2*>(g)[c] = reinterpret_cast<const double2*>(srow)[c];
+}
+
+// Forward: ℓ_i[γ] = ϕ_i ℓ_{i−1}[γ] + ψ_i Σ_t p_t ℓ_{i−1}[γ1] ℓ_{i−1}[γ2]  (src/core.jl:121-128,178-185), every row kept:
+// row i−1 is copied to the history at the top of slice i (it is complete since the last barrier), row n after the loop.
+template <int NT>
+__device__ __noinline__ void run_slices_fwd1(int n, int Cp, double* fin, double* scr, double* cur, const Slot* s_slots,
+                                             int nslots, const Ent* s_dents, const double2* pprow, double* hist, int tid) {
+    const Pass2 P = load_pass2(s_slots, nslots, s_dents, tid, NT);
+    const int npass = (nslots + NT - 1) / NT;
+    const int wbase = tid & ~31;
+    for (int i = 1; i <= n; i++) {
+        const double* src = cur;
+        double* dst = (cur == fin) ? scr : fin;
+        keep_row(hist + (size_t)(i - 1) * Cp, src, Cp, tid, NT);
+        const double2 pp = pprow[i];
+        if (P.wg1) {
+            double s0 = lane_terms(P.w0, P.two0, P.more0, src, src, s_dents);
+            double s1 = lane_terms(P.w1, P.two1, P.more1, src, src, s_dents);
+            const double o0 = src[P.c0], o1 = src[P.c1];
+            team_reduce2(P, s0, s1);
+            if (P.lead0) dst[P.c0] = fma(pp.x, o0, pp.y * s0);
+            if (P.lead1) dst[P.c1] = fma(pp.x, o1, pp.y * s1);
+        } else if (P.wg0) {
+            double s0 = lane_terms(P.w0, P.two0, P.more0, src, src, s_dents);
+            const double o0 = src[P.c0];
+            team_reduce1(P.w0, P.wg0, s0);
+            if (P.lead0) dst[P.c0] = fma(pp.x, o0, pp.y * s0);
+        }
+        for (int q = 2; q < npass; q++) {  // oversized rows: descriptors reloaded from shared memory
+            const int wgq = (wbase + q * NT) < nslots ? (1 << s_slots[wbase + q * NT].glog) : 0;
+            if (wgq == 0) continue;
+            const LaneWork<1> wq = load_work<1>(s_slots, nslots, s_dents, tid + q * NT);
+            double sq = lane_terms(wq, WARP_ANY(wq.cnt > 1), WARP_ANY(wq.cnt > 2), src, src, s_dents);
+            const int cq = max(wq.cell, 0);
+            const double oq = src[cq];
+            team_reduce1(wq, wgq, sq);
+            if (wq.cell >= 0 && ((tid + q * NT) & (wq.gsz - 1)) == 0) dst[cq] = fma(pp.x, oq, pp.y * sq);
+        }
+        cur = dst;
+        __syncthreads();
     }
+    keep_row(hist + (size_t)n * Cp, cur, Cp, tid, NT);
+}
+
+// Backward (see the header): `cur` holds ℓ̄_n on entry; rows alternate between arow and scr; returns the buffer holding
+// ℓ̄_0.  hist = the branch's kept rows (global, row stride Cp), staged into the three rotating buffers hb[0..2] (hlen
+// doubles each): row i−1 is in use by slice i, row i−2 is landing, row i−3 is being issued — one barrier per slice.
+// lpp = the local table rows (4 double2 per row: value, ∂λ, ∂μ, ∂ϵ_0).  acc[0..2] += this thread's share of (λ̄, μ̄, ϵ̄⁰).
+__device__ __forceinline__ void bwd_leader(double* __restrict__ dst, int c, double o, double y, double s, const double2 t0,
+                                           const double2 t1, const double2 t2, const double2 t3, double (&acc)[3]) {
+    dst[c] = fma(t0.x, o, t0.y * s);
+    const double wphi = o * y, wpsi = 0.5 * (y * s);
+    acc[0] = fma(wphi, t1.x, fma(wpsi, t1.y, acc[0]));
+    acc[1] = fma(wphi, t2.x, fma(wpsi, t2.y, acc[1]));
+    acc[2] = fma(wphi, t3.x, fma(wpsi, t3.y, acc[2]));
 }
 
 template <int NT>
-__device__ __noinline__ double* run_slices_bwd(int n, int C, int Cp, double* arow, double* scr, double* cur,
+__device__ __noinline__ double* run_slices_bwd(int n, int Cp, double* arow, double* scr, double* cur,
                                                const double* __restrict__ hist, double* hb, int hlen,
                                                const Slot* s_slots, int nslots, const Ent* s_ents,
                                                const double2* s_lpp, double (&acc)[3], int tid) {
-    const int wbase = tid & ~31;
-    const LaneWork<1> w0 = load_work<1>(s_slots, nslots, s_ents, tid);
-    const LaneWork<1> w1 = load_work<1>(s_slots, nslots, s_ents, tid + NT);
-    const int wg0 = wbase < nslots ? (1 << s_slots[wbase].glog) : 0;
-    const int wg1 = (wbase + NT) < nslots ? (1 << s_slots[wbase + NT].glog) : 0;
+    const Pass2 P = load_pass2(s_slots, nslots, s_ents, tid, NT);
     const int npass = (nslots + NT - 1) / NT;
-    const bool two0 = WARP_ANY(w0.cnt > 1), more0 = WARP_ANY(w0.cnt > 2);
-    const bool two1 = WARP_ANY(w1.cnt > 1), more1 = WARP_ANY(w1.cnt > 2);
+    const int wbase = tid & ~31;
     const int n16 = Cp >> 1;  // 16-byte words per kept row
     auto issue = [&](int row, int buf) {  // row < 0: an empty group keeps the group arithmetic uniform
         if (row >= 0) copy16(reinterpret_cast<uint4*>(hb + (size_t)buf * hlen), reinterpret_cast<const uint4*>(hist + (size_t)row * Cp), n16, tid, NT);
@@ -168,12 +242,29 @@ __device__ __noinline__ double* run_slices_bwd(int n, int C, int Cp, double* aro
         double* dst = (cur == arow) ? scr : arow;
         const double* val = hb + (size_t)b * hlen;
         const double2* lp = s_lpp + (size_t)i * 4;
-        bslice_pass(w0, wg0, two0, more0, tid, src, val, dst, lp, s_ents, acc);
-        bslice_pass(w1, wg1, two1, more1, tid + NT, src, val, dst, lp, s_ents, acc);
+        const double2 t0 = lp[0], t1 = lp[1], t2 = lp[2], t3 = lp[3];
+        if (P.wg1) {
+            double s0 = lane_terms(P.w0, P.two0, P.more0, src, val, s_ents);
+            double s1 = lane_terms(P.w1, P.two1, P.more1, src, val, s_ents);
+            const double o0 = src[P.c0], y0 = val[P.c0], o1 = src[P.c1], y1 = val[P.c1];
+            team_reduce2(P, s0, s1);
+            if (P.lead0) bwd_leader(dst, P.c0, o0, y0, s0, t0, t1, t2, t3, acc);
+            if (P.lead1) bwd_leader(dst, P.c1, o1, y1, s1, t0, t1, t2, t3, acc);
+        } else if (P.wg0) {
+            double s0 = lane_terms(P.w0, P.two0, P.more0, src, val, s_ents);
+            const double o0 = src[P.c0], y0 = val[P.c0];
+            team_reduce1(P.w0, P.wg0, s0);
+            if (P.lead0) bwd_leader(dst, P.c0, o0, y0, s0, t0, t1, t2, t3, acc);
+        }
         for (int q = 2; q < npass; q++) {  // oversized rows: descriptors reloaded from shared memory
-            const LaneWork<1> wq = load_work<1>(s_slots, nslots, s_ents, tid + q * NT);
             const int wgq = (wbase + q * NT) < nslots ? (1 << s_slots[wbase + q * NT].glog) : 0;
-            bslice_pass(wq, wgq, WARP_ANY(wq.cnt > 1), WARP_ANY(wq.cnt > 2), tid + q * NT, src, val, dst, lp, s_ents, acc);
+            if (wgq == 0) continue;
+            const LaneWork<1> wq = load_work<1>(s_slots, nslots, s_ents, tid + q * NT);
+            double sq = lane_terms(wq, WARP_ANY(wq.cnt > 1), WARP_ANY(wq.cnt > 2), src, val, s_ents);
+            const int cq = max(wq.cell, 0);
+            const double oq = src[cq], yq = val[cq];
+            team_reduce1(wq, wgq, sq);
+            if (wq.cell >= 0 && ((tid + q * NT) & (wq.gsz - 1)) == 0) bwd_leader(dst, cq, oq, yq, sq, t0, t1, t2, t3, acc);
         }
         cur = dst;
         stage_wait_prev();  // everything but the newest group: row i−2 has landed
@@ -208,9 +299,10 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
     const size_t meta_bytes = (((9 * nn + 4) * sizeof(int)) + 15) & ~size_t(15);
     NodeRec* s_nrec = reinterpret_cast<NodeRec*>(smem_raw + meta_bytes);
     RevRec* s_rrec = reinterpret_cast<RevRec*>(s_nrec + nn);
-    double* zloc = reinterpret_cast<double*>(s_rrec + nn);  // [nn][8] local adjoints (see the contraction below)
-    double* lgrad = zloc + 8 * nn;                          // [nn][2] leaf branches: Σ_γ ℓ̄_n[γ]·∂ℓ_n[γ]/∂(component 1, 2)
-    double* s_red = lgrad + 2 * nn;                         // [NW*8] block_sum scratch
+    // [nn][8] local adjoints: internal/WGD/root {λ̄, μ̄, ϵ̄⁰ (slices), c̄x, c̄y (WGD, root), ϵ̄ⁿ of child 0, ϵ̄ⁿ of child 1, -};
+    // leaf branches {Σ_γ ℓ̄_n[γ]·∂ℓ_n[γ]/∂(component 1), ·/∂(component 2), ...}: row r of the Jacobian table k_tables3 built
+    double* zloc = reinterpret_cast<double*>(s_rrec + nn);
+    double* s_red = zloc + 8 * nn;                          // [NW*8] block_sum scratch
     double* s_res = s_red + NW * 8;                         // [8] block_sum results
     unsigned char* dyn = reinterpret_cast<unsigned char*>(s_res + 8);
     for (int i = tid; i < nn; i += NT) {
@@ -238,7 +330,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
         const Ent* ents = reinterpret_cast<const Ent*>(blob);
         const uint32_t* rwords = reinterpret_cast<const uint32_t*>(rblob);
         const Ent* rents = reinterpret_cast<const Ent*>(rblob);
-        long long tc0 = CLOCK64();
+        long long tc0 = CLOCK64(), acc_fsl = 0, acc_bsl = 0, acc_froot = 0;
         for (uint32_t o = tid * 128u; o < blob_bytes; o += NT * 128u) PREFETCH_L2(blob + o);
         for (uint32_t o = tid * 128u; o < rblob_bytes; o += NT * 128u) PREFETCH_L2(rblob + o);
 
@@ -258,11 +350,29 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
             reinterpret_cast<uint4*>(s_nrec)[i] = __ldg(reinterpret_cast<const uint4*>(blob) + i);
             reinterpret_cast<uint4*>(s_rrec)[i] = __ldg(reinterpret_cast<const uint4*>(rblob) + i);
         }
-        for (int i = tid; i < 10 * nn; i += NT) zloc[i] = 0.0;  // zloc and lgrad
+        for (int i = tid; i < 8 * nn; i += NT) zloc[i] = 0.0;
         __syncthreads();
         const NodeRec* const nrec = s_nrec;
         const RevRec* const rrec = s_rrec;
         double* const hist = A.hist + (size_t)(A.slot0 + blockIdx.x) * A.hist_stride;
+        // The row-1 / root lists are read once, in place (global memory through L1): pull a node's lists into L1 one node
+        // ahead, while the current node's slices run, so those reads do not pay an L2 round trip per dependent step
+        auto pf_range = [&](const unsigned char* p, uint32_t bytes, const unsigned char* lim) {
+            if (p + bytes > lim) bytes = (uint32_t)(lim - p);
+            for (uint32_t o = tid * 128u; o < bytes; o += NT * 128u) PREFETCH_L1(p + o);
+        };
+        auto pf_fwd = [&](int e) {  // forward lists of node e: [dptr .. cmp] words, [dents .. tents] entries
+            const NodeRec& Q = nrec[e];
+            pf_range(blob + (size_t)Q.dptr_off * 4, (Q.tptr_off - Q.dptr_off + 4 * Q.C + nlev + 8) * 4, blob + blob_bytes);
+            pf_range(blob + (size_t)Q.dent_off * 16, (Q.tent_off + Q.ntent - Q.dent_off) * 16, blob + blob_bytes);
+        };
+        auto pf_bwd = [&](int e) {  // transposed lists of node e
+            const RevRec& Q = rrec[e];
+            const uint32_t wend = Q.sG_off > Q.bslot_off ? Q.sG_off + 2 * nrec[e].C + 2 : Q.bslot_off + 2 * Q.nbslots;
+            pf_range(rblob + (size_t)Q.bptr_off * 4, (wend - Q.bptr_off) * 4, rblob + rblob_bytes);
+            pf_range(rblob + (size_t)Q.bent_off * 16, (Q.nbent + Q.nsFent + Q.nsGent) * 16, rblob + rblob_bytes);
+        };
+        if (M.ninner > 0) pf_fwd(M.inner[0]);
 
         const long long tcA = CLOCK64();
         // ================= phase A: leaf branches (as in k_dp, hybrid plan: value + own λ, μ) =================
@@ -353,6 +463,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
             if (C == 0) continue;
             const int kind = s_kind[e], n = s_nsl[e];
             const int Cp = (C + 1) & ~1;
+            const long long tn0 = CLOCK64();
             double* fin = rows + s_roff[e];
             double* hrow = hist + rrec[e].hoff;
             const int f = s_ch0[e], g = s_ch1[e];
@@ -383,9 +494,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
                 const double cx0 = PR.cx[e * KmaxR], cy0 = PR.cy[e * KmaxR];
                 for (int c = tid; c < C; c += NT) {
                     const double s0 = vsum<true>(g_dents, g_dptr[c], g_dptr[c + 1], 1u, finF, sF, finF, sF);
-                    const double r = fma(cy0, s0, cx0 * finF[c * sF]);
-                    cur[c] = r;
-                    hrow[c] = r;
+                    cur[c] = fma(cy0, s0, cx0 * finF[c * sF]);
                 }
             } else {
                 const int sG = RS(s_K[g]);
@@ -398,11 +507,10 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
                         const double s0 = vsum<true>(g_tents, g_tptr[c], g_tptr[c + 1], 1u, finF, sF, finG, sG);
                         const int lf = g_lossF[c], lg = g_lossG[c];
                         const double l0 = (lf >= 0 ? finF[lf * sF] : 0.0) * eg0 + (lg >= 0 ? finG[lg * sG] : 0.0) * ef0;
-                        const double r = s0 + l0;
-                        cur[c] = r;
-                        hrow[c] = r;
+                        cur[c] = s0 + l0;
                     }
                 } else {  // root (src/core.jl:130-158): clades ascending in size, one level at a time
+                    pf_bwd(e);
                     const double cx0 = PR.cx[e * KmaxR], cy0 = PR.cy[e * KmaxR];
                     const uint32_t* g_lev = reinterpret_cast<const uint32_t*>(g_lossG + C);
                     for (uint32_t L = 0; L < nlev; L++) {
@@ -430,13 +538,19 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
                         }
                         __syncthreads();
                     }
+                    acc_froot += CLOCK64() - tn0;
                     continue;
                 }
             }
             stage_wait();
             __syncthreads();  // row 1 and the staged lists are visible
-            run_slices_fused<1, false>(n, Cp, fin, scr, cur, s_slots, (int)R.nslots, s_dents, s_pp, hrow, tid, NT);
+            const long long ts0 = CLOCK64();
+            if (oi + 1 < M.ninner) pf_fwd(M.inner[oi + 1]);
+            run_slices_fwd1<NT>(n, Cp, fin, scr, cur, s_slots, (int)R.nslots, s_dents, s_pp, hrow, tid);
             __syncthreads();  // the last row is complete; the staging buffer may be reused
+            const long long ts1 = CLOCK64();
+            acc_fsl += ts1 - ts0;
+            if (A.tim && tid == 0 && oi < TIMN) A.tim[(size_t)fam * TIMW + 8 + oi] = ts1 - tn0;
         }
         const long long tcC = CLOCK64();
 
@@ -537,8 +651,8 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
                 zloc[e * 8 + 4] = s_res[0] + uG * eg0 + uF * ef0;          // c̄y = Σ Ā·(b + loss)
                 zloc[e * 8 + 5] = cy0 * uF;                                // ϵ̄ⁿ of child 0
                 zloc[e * 8 + 6] = cy0 * uG;                                // ϵ̄ⁿ of child 1
-                lgrad[f * 2 + 0] = s_res[2]; lgrad[f * 2 + 1] = s_res[3];
-                lgrad[g * 2 + 0] = s_res[6]; lgrad[g * 2 + 1] = s_res[7];
+                if (s_kind[f] == WHALE_LEAF) { zloc[f * 8 + 0] = s_res[2]; zloc[f * 8 + 1] = s_res[3]; }
+                if (s_kind[g] == WHALE_LEAF) { zloc[g * 8 + 0] = s_res[6]; zloc[g * 8 + 1] = s_res[7]; }
             }
             __syncthreads();
         }
@@ -554,6 +668,8 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
             const int Cp = (C + 1) & ~1;
             double* arow = arows + s_aoff[e];
             double* cur = arow;
+            const long long tn0 = CLOCK64();
+            pf_bwd(e);
             if (n > 0) {  // ---- slices n .. 1, transposed ----
                 const int nb16 = (int)RR.nbent, sl16 = ((int)RR.nbslots + 1) >> 1, lp16 = 4 * (n + 1);
                 const Ent* s_bents = rents + RR.bent_off;
@@ -571,9 +687,10 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
                 }
                 __syncthreads();
                 double acc[3] = {0.0, 0.0, 0.0};
-                cur = run_slices_bwd<NT>(n, C, Cp, arow, scr, arow, hist + RR.hoff, hb, (int)hlen, s_bslots, (int)RR.nbslots,
+                cur = run_slices_bwd<NT>(n, Cp, arow, scr, arow, hist + RR.hoff, hb, (int)hlen, s_bslots, (int)RR.nbslots,
                                          s_bents, s_lpp, acc, tid);
                 block_sum<3, NT>(acc, s_red, zloc + e * 8, false, tid);
+                acc_bsl += CLOCK64() - tn0;
             }
             // ---- row 1, transposed ----
             const int f = s_ch0[e], g = s_ch1[e];
@@ -607,7 +724,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
                 if (tid == 0) {
                     zloc[e * 8 + 3] = s_res[0];
                     zloc[e * 8 + 4] = s_res[1];
-                    if (isleaf) { lgrad[f * 2 + 0] = s_res[2]; lgrad[f * 2 + 1] = s_res[3]; }
+                    if (isleaf) { zloc[f * 8 + 0] = s_res[2]; zloc[f * 8 + 1] = s_res[3]; }
                 }
                 __syncthreads();
             } else {  // internal node
@@ -625,44 +742,29 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
                 if (tid == 0) {
                     zloc[e * 8 + 5] = s_res[5];  // ϵ̄ⁿ of child 0 = Σ_c Ā[c]·ℓ_G[lg(c)]
                     zloc[e * 8 + 6] = s_res[1];  // ϵ̄ⁿ of child 1 = Σ_c Ā[c]·ℓ_F[lf(c)]
-                    if (s_kind[f] == WHALE_LEAF) { lgrad[f * 2 + 0] = s_res[2]; lgrad[f * 2 + 1] = s_res[3]; }
-                    if (s_kind[g] == WHALE_LEAF) { lgrad[g * 2 + 0] = s_res[6]; lgrad[g * 2 + 1] = s_res[7]; }
+                    if (s_kind[f] == WHALE_LEAF) { zloc[f * 8 + 0] = s_res[2]; zloc[f * 8 + 1] = s_res[3]; }
+                    if (s_kind[g] == WHALE_LEAF) { zloc[g * 8 + 0] = s_res[6]; zloc[g * 8 + 1] = s_res[7]; }
                 }
                 __syncthreads();
             }
+            if (A.tim && tid == 0 && oi < TIMN) A.tim[(size_t)fam * TIMW + 8 + TIMN + oi] = CLOCK64() - tn0;
         }
         const long long tcE = CLOCK64();
 
         // ================= contraction with the table tangents =================
+        // ∂ log L_f/∂θ_k = Σ_r z_r·J[r][k]: J (k_tables3, plan G: one row per local adjoint, one column per component of the
+        // root's list) holds 0/1 for a branch's own λ, μ and the global tangents of ϵ_0, ϵ_n, cx, cy otherwise
+        __syncthreads();
         for (int k = tid; k < KR; k += NT) {
             double gk;
             if (k == 0) {
                 gk = log(Lv);
             } else {
                 gk = 0.0;
-                const int gp = PG.act[root * KmaxG + k];
-                for (int e = 0; e < nn; e++) {
-                    const int kind = s_kind[e];
-                    const double* z = zloc + e * 8;
-                    if (kind == WHALE_LEAF) {  // Σ_γ ℓ̄_n[γ]·∂ℓ_n[γ]/∂θ_k : the hybrid plan's components of this branch
-                        for (int j = 1; j < s_K[e]; j++)
-                            if (PR.act[e * KmaxR + j] == gp) gk += lgrad[e * 2 + j - 1];
-                        continue;
-                    }
-                    const int ke = A.rinv[e * KR + k];
-                    if (kind != WHALE_ROOT) {
-                        if (M.lam_slot[e] == gp) gk += z[0];
-                        if (M.mu_slot[e] == gp) gk += z[1];
-                        if (ke > 0) gk = fma(z[2], PG.eps[PG.toff[e] + ke], gk);  // ϵ_0 of the branch (row 0)
-                    }
-                    if (kind != WHALE_INTERNAL && ke > 0) gk = fma(z[3], PG.cx[e * KmaxG + ke], fma(z[4], PG.cy[e * KmaxG + ke], gk));
-                    if (kind != WHALE_WGD) {
-                        for (int j = 0; j < 2; j++) {
-                            const int c = j == 0 ? s_ch0[e] : s_ch1[e];
-                            const int kc = A.rinv[c * KR + k];
-                            if (kc > 0) gk = fma(z[5 + j], PG.eps[PG.toff[c] + s_nsl[c] * PG.K[c] + kc], gk);
-                        }
-                    }
+                const double* J = PG.jac + k;
+                for (int r = 0; r < 8 * nn; r++) {
+                    const double z = zloc[r];
+                    if (z != 0.0) gk = fma(z, __ldg(J + (size_t)r * KR), gk);
                 }
             }
             A.out_fam[(size_t)fam * KR + k] = gk;
@@ -670,14 +772,18 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
         if (A.tim && tid == 0) {
             const long long te = CLOCK64();
             long long* T = A.tim + (size_t)fam * TIMW;
-            T[0] = tcA - tc0;   // prologue
-            T[1] = tcB - tcA;   // leaf phase
-            T[2] = tcC - tcB;   // forward, internal nodes + root
-            T[3] = tcD - tcC;   // root, transposed
-            T[4] = tcE - tcD;   // internal nodes, transposed
-            T[5] = te - tcE;    // contraction
-            T[6] = te - tc0;    // total
-            T[7] = 0;
+            T[0] = tcA - tc0;                       // prologue
+            T[1] = tcB - tcA;                       // leaf phase
+            T[2] = (tcC - tcB) - acc_fsl - acc_froot;  // forward: staging + row 1 of internal/WGD nodes
+            T[3] = (tcE - tcD) - acc_bsl;           // backward: row 1 of internal/WGD nodes, transposed
+            T[4] = acc_fsl + acc_bsl;               // slices, forward + transposed
+            T[5] = acc_froot + (tcD - tcC);         // root, forward + transposed
+            T[6] = te - tc0;                        // total
+            T[7] = te - tcE;                        // contraction with the table tangents
+            if (M.ninner < TIMN) {                  // spare per-node slots: the split of [4] and [5]
+                T[8 + TIMN - 1] = acc_fsl;
+                T[8 + 2 * TIMN - 1] = acc_froot;
+            }
         }
     }
     if (A.done) {

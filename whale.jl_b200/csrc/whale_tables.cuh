@@ -24,6 +24,7 @@
 #endif
 
 constexpr unsigned TAB_FORCE_CHAIN = 1u;  // flags: run the per-slice recurrence on every branch (tests, A/B)
+constexpr unsigned TAB_JACOBIAN = 2u;     // this plan: no slice rows, the reverse pass's Jacobian table instead (see below)
 
 // species-tree metadata staged in shared memory: after an L2 flush every dependent global load of these tiny
 // arrays costs a DRAM round trip per level
@@ -250,6 +251,43 @@ __device__ __forceinline__ void tables_block(const ModelDev& M, const PlanDev& P
         __syncthreads();
         if (writer && threadIdx.x == 0 && L < 28) PL.tim[1 + L] = CLOCK64() - tk0;
     }
+    if (flags & TAB_JACOBIAN) {
+        // plan G of a reverse-mode evaluation (one table CTA): the slice rows are not needed, only the Jacobian of the
+        // quantities whose adjoints k_dp_rev accumulates per node — row r = e*8 + j (whale_rev.cuh: zloc), column k =
+        // component of the root's list:  j = 0, 1 own λ, μ (0/1; leaf branches: their components 1, 2);  2 ϵ_0 of the branch;
+        // 3, 4 the row-1 coefficients cx, cy (WGD, root);  5, 6 the last ϵ of child 0 / child 1 (Πloss)
+        const int KRr = T.K[M.root];
+        for (int idx = threadIdx.x; idx < nn * 8 * KRr; idx += blockDim.x) {
+            const int k = idx % KRr, r = idx / KRr, j = r & 7, e = r >> 3;
+            double v = 0.0;
+            if (k > 0) {
+                const int gp = PL.act[M.root * PL.Kmax + k];
+                const int kind = T.kind[e];
+                const int ke = PL.rinv[e * KRr + k];
+                if (kind == WHALE_LEAF) {
+                    if (j < 2 && j + 1 < T.K[e] && PL.act[e * PL.Kmax + j + 1] == gp) v = 1.0;
+                } else {
+                    if (kind != WHALE_ROOT) {
+                        if (j == 0 && T.ls[e] == gp) v = 1.0;
+                        if (j == 1 && T.ms[e] == gp) v = 1.0;
+                        if (j == 2 && ke > 0) v = s_e0[e * Kmax + ke];
+                    }
+                    if (kind != WHALE_INTERNAL && ke > 0) {
+                        if (j == 3) v = PL.cx[e * PL.Kmax + ke];
+                        if (j == 4) v = PL.cy[e * PL.Kmax + ke];
+                    }
+                    if (kind != WHALE_WGD && (j == 5 || j == 6)) {
+                        const int c = j == 5 ? T.ch0[e] : T.ch1[e];
+                        const int kc = PL.rinv[c * KRr + k];
+                        if (kc > 0) v = s_en[c * Kmax + kc];
+                    }
+                }
+            }
+            PL.jac[idx] = v;
+        }
+        if (threadIdx.x == 0) { PL.tim[30] = CLOCK64() - tk0; PL.tim[31] = M.nlvl; }
+        return;
+    }
     // ---- phase B: every (node, row, component) of the tables in parallel (one flat index space, 1/G per CTA) ----
     const int total = T.toff[nn - 1] + (T.nsl[nn - 1] + 1) * T.K[nn - 1];  // toff is ascending in node index
     for (int t = bid * blockDim.x + threadIdx.x; t < total; t += G * blockDim.x) {
@@ -319,7 +357,7 @@ __global__ void __launch_bounds__(TABLES_NT) k_tables3(ModelDev M, Tables3 T3, c
     EXTERN_SHARED(tsm);
     int bid = (int)blockIdx.x, pi = 0;
     while (pi < 2 && bid >= T3.n[pi]) { bid -= T3.n[pi]; pi++; }
-    tables_block(M, T3.PL[pi], x, pleaf, T3.G[pi], flags, bid, tsm);
+    tables_block(M, T3.PL[pi], x, pleaf, T3.G[pi], flags | (pi == 1 ? TAB_JACOBIAN : 0u), bid, tsm);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -136,7 +136,30 @@ static int dp_minb() {  // resident CTAs per SM the register cap is chosen for
 #else
 #define DP_VARIANTS(X) X(64, 8) X(128, 3) X(128, 4) X(128, 5) X(128, 6) X(256, 2)
 #endif
-#define REV_VARIANTS(X) DP_VARIANTS(X)
+// k_dp_rev: WHALE_REV_NT / WHALE_REV_MINB select among the compiled shapes (threads per family CTA, resident CTAs per SM)
+#ifdef WHALE_DEV_BUILD
+#define REV_VARIANTS(X) X(128, 4) X(128, 5) X(128, 6) X(128, 8)
+#else
+#define REV_VARIANTS(X) X(32, 16) X(64, 8) X(128, 3) X(128, 4) X(128, 5) X(128, 6) X(128, 8) X(256, 2)
+#endif
+static int rev_nt() {
+    static int nt = [] { int v = env_int("WHALE_REV_NT", 128); return (v == 32 || v == 64 || v == 256) ? v : 128; }();
+    return nt;
+}
+static int rev_minb() {
+    static int mb = [] {
+        const int nt = rev_nt(), v = env_int("WHALE_REV_MINB", 0);
+        if (nt == 32) return 16;
+        if (nt == 64) return 8;
+        if (nt == 256) return 2;
+#ifdef WHALE_DEV_BUILD
+        return (v == 5 || v == 6 || v == 8) ? v : 4;
+#else
+        return (v == 3 || v == 5 || v == 6 || v == 8) ? v : 4;
+#endif
+    }();
+    return mb;
+}
 constexpr int MAX_BINS = 8;
 struct Bin {
     int off, count;
@@ -486,6 +509,11 @@ int32_t whale_model_create(const whale_model_desc* d, whale_model_t* out) {
             }
         }
         CU(upload(m->rinv, &m->d_rinv));
+        double* jac = nullptr;
+        CU(cudaMalloc((void**)&jac, (size_t)nn * 8 * KR * sizeof(double)));
+        m->plan[1].owned.push_back(jac);
+        m->plan[1].dev.rinv = m->d_rinv;
+        m->plan[1].dev.jac = jac;
     }
     {
         cudaDeviceProp pr;
@@ -570,7 +598,8 @@ static cudaError_t launch_tables3(whale_model* m, const double* d_x, const doubl
     for (int i = 0; i < 3; i++) {
         const bool shapes = i == 0 && !m->leafnodes.empty();
         T3.PL[i] = pls[i]->dev;
-        T3.G[i] = (int)std::max<size_t>(1, std::min<size_t>(32, (pls[i]->tab_len + TABLES_NT - 1) / TABLES_NT));
+        // (the full plan only runs the chain over the tree's height and writes the Jacobian table: one CTA)
+        T3.G[i] = i == 1 ? 1 : (int)std::max<size_t>(1, std::min<size_t>(32, (pls[i]->tab_len + TABLES_NT - 1) / TABLES_NT));
         T3.n[i] = T3.G[i] + (shapes ? (int)m->leafnodes.size() : 0);
         total += T3.n[i];
         smem = std::max(smem, tables_smem(m, *pls[i], shapes));
@@ -661,7 +690,7 @@ static cudaError_t order_families(whale_data* D, int g, const std::vector<double
     int i = 0;
     // a bin = families that allow the same number of resident CTAs per SM (capped by the register limit):
     // a smaller shared-memory request buys nothing once registers are the limiter
-    auto cls = [&](size_t nd) { return std::min<size_t>((size_t)dp_minb(), (227 * 1024) / std::max<size_t>(nd, 1)); };
+    auto cls = [&](size_t nd) { return std::min<size_t>((size_t)(rev ? rev_minb() : dp_minb()), (227 * 1024) / std::max<size_t>(nd, 1)); };
     while (i < F) {
         Bin b{i, 0, need[perm[i]]};
         while (i < F && (cls(need[perm[i]]) == cls(b.smem) || b.count < 64 || (int)bins.size() >= MAX_BINS - 1)) { i++; b.count++; }
@@ -1106,9 +1135,9 @@ static bool build_reverse(whale_data* D) {
 }
 
 static size_t smem_need_rev(const whale_model* m, const FamHdr& h, const RevHdr& r) {  // mirrors the carve-up in k_dp_rev
-    const size_t nn = m->nn, NW = dp_nt() / 32;
+    const size_t nn = m->nn, NW = rev_nt() / 32;
     const size_t hdr = ((((9 * nn + 4) * sizeof(int)) + 15) & ~size_t(15)) + nn * (sizeof(NodeRec) + sizeof(RevRec)) +
-                       (10 * nn + NW * 8 + 8) * sizeof(double);
+                       (8 * nn + NW * 8 + 8) * sizeof(double);
     const size_t leaf = NW * ((size_t)r.leafmax * sizeof(double) + h.leaf_stage);
     const size_t back = ((size_t)r.arows_len + 3 * (size_t)r.hbuf_len) * sizeof(double);
     return hdr + ((size_t)r.rows_len + r.scr_len) * sizeof(double) + r.stage_bytes + std::max(leaf, back);
@@ -1151,7 +1180,7 @@ static size_t set_budgets_rev(whale_data* D) {
         std::vector<int> roff(nn + 1), aoff(nn + 1, 0);
         const int rows = place_rows(nn, (int)m->leafnodes.size(), m->leafnodes.data(), (int)m->inner.size(), m->inner.data(),
                                     m->child0.data(), m->child1.data(), m->kind.data(),
-                                    [&](int e2) { return (int)(Cs[e2] * (uint32_t)RS(pl.K[e2])); }, roff.data(), true);
+                                    [&](int e2) { return (int)even(Cs[e2] * (uint32_t)RS(pl.K[e2])); }, roff.data(), true);
         const int arows = place_arows((int)m->inner.size(), m->inner.data(), m->child0.data(), m->child1.data(), m->kind.data(),
                                       [&](int e2) { return (int)Cs[e2]; }, aoff.data());
         for (int e = 0; e < nn; e++) {
@@ -1190,7 +1219,7 @@ static int32_t finalize_data(whale_model* m, whale_data* D, whale_data_t* out) {
     // tangents of k_dp (also the fallback when a family does not fit the reverse kernel's working set)
     {
         const char* gm = getenv("WHALE_GRAD_MODE");
-        if (!(gm && !strcmp(gm, "fwd")) && m->plan[1].K[m->root] <= dp_nt() && build_reverse(D)) {
+        if (!(gm && !strcmp(gm, "fwd")) && tables_smem(m, m->plan[1], false) <= SMEM_MAX && build_reverse(D)) {
             const size_t need_rev = set_budgets_rev(D);
             D->rev = need_rev <= SMEM_MAX;
             if (env_int("WHALE_DEBUG", 0) >= 1)
@@ -1477,6 +1506,8 @@ int32_t whale_data_destroy(whale_data_t d) {
 }
 
 int32_t whale_data_nfam(whale_data_t d) { return d ? d->F : 0; }
+int32_t whale_data_grad_mode(whale_data_t d) { return d ? (d->rev ? 1 : 0) : -1; }
+int32_t whale_data_grad_passes(whale_data_t d) { return d ? (int32_t)d->plans.size() - 1 : -1; }
 int64_t whale_data_arena_bytes(whale_data_t d) { return d ? (int64_t)d->arena_bytes : 0; }
 int64_t whale_data_arena_dump(whale_data_t d, void* buf, int64_t cap) {
     if (!d) return 0;
@@ -1514,7 +1545,7 @@ static int32_t ensure_nowhere(whale_model* m, Plan& pl) {
 // reverse-mode gradient evaluation: [three table sets in one launch -> k_dp_rev (persistent CTAs) -> reduction in its tail]
 static int32_t enqueue_eval_rev(whale_model* m, whale_data* D, const double* d_x, int32_t condition, uint32_t flags,
                                 double* d_out, cudaStream_t st) {
-    const int F = D->F, NT = dp_nt(), MB = dp_minb();
+    const int F = D->F, NT = rev_nt(), MB = rev_minb();
     const bool prof = (flags & WHALE_PROFILE) != 0;
     Plan& pg = m->plan[1];
     CU(cudaMemsetAsync(d_out, 0, (1 + m->P) * sizeof(double), st));
@@ -1535,7 +1566,7 @@ static int32_t enqueue_eval_rev(whale_model* m, whale_data* D, const double* d_x
     const size_t tail_smem = (size_t)(NT + 2 * KR + 2) * sizeof(double);
     auto launch_bin = [&](size_t b, cudaStream_t s) {
         RevArgs a{m->dev, m->planR.dev, pg.dev, m->planL.dev, D->d_arena, D->d_hdr, D->d_rarena, D->d_rhdr, D->d_perm[1],
-                  D->d_roff[1], D->d_aoff, m->d_rinv, out_fam, D->d_hist, (unsigned long long)D->hist_stride, D->d_next + b,
+                  D->d_roff[1], D->d_aoff, out_fam, D->d_hist, (unsigned long long)D->hist_stride, D->d_next + b,
                   bins[b].off, bins[b].count, D->rev_slot0[b], prof ? D->d_tim : nullptr, fused ? D->d_done : nullptr, F,
                   condition, d_out};
 #define LAUNCHV(NTV, MBV) if (NT == NTV && MB == MBV) LAUNCH((k_dp_rev<NTV, MBV>), D->rev_grid[b], NTV, std::max(bins[b].smem, tail_smem), s, a);

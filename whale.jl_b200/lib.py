@@ -67,6 +67,8 @@ class Lib:
         L.whale_data_create.argtypes = [vp, C.POINTER(CCDDesc), C.POINTER(vp)]
         L.whale_data_destroy.argtypes = [vp]
         L.whale_data_nfam.argtypes = [vp]
+        L.whale_data_grad_mode.argtypes = [vp]
+        L.whale_data_grad_passes.argtypes = [vp]
         L.whale_data_arena_bytes.argtypes = [vp]
         L.whale_data_arena_bytes.restype = C.c_int64
         L.whale_data_arena_dump.argtypes = [vp, vp, C.c_int64]
@@ -249,7 +251,11 @@ class Lib:
     def last_phase_cycles(self, dh):
         mean, mx = np.zeros(8), np.zeros(8)
         self.check(self.L.whale_last_phase_cycles(dh, _ptr(mean, f64p), _ptr(mx, f64p)))
-        names = ["prologue", "leaf_phase", "staging", "row1", "slices", "root", "total"]
+        if self.L.whale_data_grad_mode(dh) == 1:  # reverse mode (see whalecuda.h)
+            names = ["prologue", "leaf_phase", "fwd_stage_row1", "bwd_row1", "slices_fwd_bwd", "root_fwd_bwd", "total",
+                     "contraction"]
+        else:
+            names = ["prologue", "leaf_phase", "staging", "row1", "slices", "root", "total"]
         return {n: (float(mean[i]), float(mx[i])) for i, n in enumerate(names)}
 
     def last_family_cycles(self, dh):

@@ -270,17 +270,32 @@ def c4_species_tree() -> newick.Node:
 C4_FAMILY = dict(min_leaves=60, max_leaves=100, n_trees=1000, nni_mean=12.0, q=(0.2, 0.1, 0.2, 0.1, 0.2))  # ~2,000 clades
 
 
-def generate(outdir: str, n_fam: int, seed: int, tree: newick.Node | None = None, **kw) -> str:
-    """Write `n_fam` synthetic .ale files into outdir (idempotent: reuses a complete directory)."""
+def _gen_range(args):
+    outdir, tree, seed, lo, hi, kw = args
+    for f in range(lo, hi):
+        rng = np.random.default_rng([seed, f])
+        names, bip, dip, nt = make_family(tree, rng, **kw)
+        write_ale(os.path.join(outdir, f"fam{f:06d}.ale"), names, bip, dip, nt)
+    return hi - lo
+
+
+def generate(outdir: str, n_fam: int, seed: int, tree: newick.Node | None = None, workers: int = 0, **kw) -> str:
+    """Write `n_fam` synthetic .ale files into outdir (idempotent: reuses a complete directory).  Family f is drawn from
+    its own generator seeded (seed, f), so the files do not depend on `workers` (0 = all host cores for large sets)."""
     tree = tree or c1_species_tree()
     os.makedirs(outdir, exist_ok=True)
     done = outdir.rstrip("/") + ".complete"  # sibling marker: read_ale reads every file in outdir
     if os.path.exists(done) and open(done).read().strip() == f"{n_fam} {seed} {sorted(kw.items())}":
         return outdir
-    for f in range(n_fam):
-        rng = np.random.default_rng([seed, f])
-        names, bip, dip, nt = make_family(tree, rng, **kw)
-        write_ale(os.path.join(outdir, f"fam{f:06d}.ale"), names, bip, dip, nt)
+    nw = workers or (min(os.cpu_count() or 1, 32) if n_fam >= 2000 else 1)
+    if nw > 1:
+        import multiprocessing as mp
+        step = max(1, (n_fam + 4 * nw - 1) // (4 * nw))
+        jobs = [(outdir, tree, seed, lo, min(n_fam, lo + step), kw) for lo in range(0, n_fam, step)]
+        with mp.get_context("fork").Pool(nw) as pool:
+            pool.map(_gen_range, jobs)
+    else:
+        _gen_range((outdir, tree, seed, 0, n_fam, kw))
     with open(done, "w") as fh:
         fh.write(f"{n_fam} {seed} {sorted(kw.items())}\n")
     return outdir
