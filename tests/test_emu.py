@@ -322,6 +322,7 @@ def test_emu_reverse_mode_is_default_and_persistent(monkeypatch):
     """The default gradient is the reverse-mode kernel; with ONE persistent CTA (WHALE_REV_GRID=1) every family goes
     through the same CTA's loop (history slot, shared-memory carve-up and adjoint rows reused from family to family)."""
     monkeypatch.setenv("WHALE_REV_GRID", "1")
+    monkeypatch.setenv("WHALE_GRAD_MODE", "rev")
     L2 = wlib.Lib(EMU)
     g = load_golden("c1_example1")
     mh = L2.model_create(golden_model(g))

@@ -238,3 +238,33 @@ def test_near_critical_rates(L, tmp_path):
     per-slice recurrence there) and the closed-form rows, against the oracle."""
     from conftest import near_critical_vs_oracle
     near_critical_vs_oracle(tmp_path, n_fam=6)
+
+
+@pytest.mark.parametrize("mode", ["fwd", "rev"])
+def test_gradient_modes(L, tmp_path, monkeypatch, mode):
+    """Both gradient paths against the oracle on every fixture: k_dp's forward tangents (WHALE_GRAD_MODE=fwd, parameter
+    chunks where needed) and the reverse-mode kernel k_dp_rev (=rev; the default picks per data set, see
+    whale_data_grad_mode)."""
+    monkeypatch.setenv("WHALE_GRAD_MODE", mode)
+    g = load_golden("c1_example1")
+    mh = L.model_create(golden_model(g))
+    dh = L.data_create(mh, golden_fams(g))
+    assert L.L.whale_data_grad_mode(dh) == (1 if mode == "rev" else 0)
+    L.L.whale_data_destroy(dh)
+    L.L.whale_model_destroy(mh)
+    for name in ("c1_maxn5", "c1_example1", "const_wgdturing", "mul_tree", "landplant100", "ex5_dt0.01"):
+        run_parity(L, name)
+    from conftest import synthetic_c2_shape_vs_oracle, near_critical_vs_oracle, nowhere_condition_vs_oracle, mixture_vs_oracle
+    synthetic_c2_shape_vs_oracle(tmp_path)
+    near_critical_vs_oracle(tmp_path, n_fam=4)
+    nowhere_condition_vs_oracle(L)
+    mixture_vs_oracle(tmp_path, n_fam=8)
+
+
+def test_reverse_mode_one_persistent_cta(L, monkeypatch):
+    """k_dp_rev with a single persistent CTA: all families go through one CTA's loop (history slot and shared-memory
+    carve-up reused from family to family) — same per-family results as the default launch."""
+    monkeypatch.setenv("WHALE_GRAD_MODE", "rev")
+    monkeypatch.setenv("WHALE_REV_GRID", "1")
+    run_parity(L, "c1_example1", conds=["root"])
+    run_parity(L, "landplant100", sel=list(range(0, 100, 7)), conds=["root"])

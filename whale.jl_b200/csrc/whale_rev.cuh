@@ -133,6 +133,7 @@ __device__ __forceinline__ double lane_terms(const LaneWork<1>& w, bool two, boo
     if (two) s = fma(w.pb * X[w.b1], Y[w.b2], (w.pa * X[w.a1]) * Y[w.a2]);
     else s = (w.pa * X[w.a1]) * Y[w.a2];
     if (more) {
+#pragma unroll 1
         for (int j = 2; j < w.cnt; j++) {
             const Ent en = s_ents[w.first + j * w.gsz];
             s = fma(en.p * X[en.i1], Y[en.i2], s);
@@ -159,6 +160,7 @@ __device__ __forceinline__ void team_reduce1(const LaneWork<1>& w, int wg, doubl
 
 // coalesced copy of one finished row (Cp doubles, 16-byte aligned on both sides) from shared memory to the history
 __device__ __forceinline__ void keep_row(double* __restrict__ g, const double* __restrict__ srow, int Cp, int tid, int nt) {
+#pragma unroll 1
     for (int c = tid; c < (Cp >> 1); c += nt) reinterpret_cast<double2*>(g)[c] = reinterpret_cast<const double2*>(srow)[c];
 }
 
@@ -278,6 +280,8 @@ template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
     EXTERN_SHARED(smem_raw);
     constexpr int NW = NT / 32;
+    // (rotating the warp roles per CTA so that co-resident CTAs put their critical warps on different schedulers measured
+    // 6 % SLOWER on the B200, profiles/r2_rev_rotation_ab.txt: roles stay put)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const ModelDev& M = A.M;
     const PlanDev& PR = A.PR;

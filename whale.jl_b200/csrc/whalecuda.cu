@@ -1217,9 +1217,20 @@ static int32_t finalize_data(whale_model* m, whale_data* D, whale_data_t* out) {
     const size_t SMEM_GOAL = (size_t)env_int("WHALE_SMEM_GOAL", 80000);  // default: at least two families per SM
     // Gradient mode: reverse (adjoint) DP by default — one pass whatever P is; WHALE_GRAD_MODE=fwd keeps the forward
     // tangents of k_dp (also the fallback when a family does not fit the reverse kernel's working set)
+    // Default (WHALE_GRAD_MODE unset or "auto"): reverse mode, except for the small-P / small-family corner where one
+    // forward pass is faster because a slice is a latency chain whose length does not depend on K — measured on the B200
+    // (profiles/r2_modes_*.json): C2 (P = 5, ~200 clades) 3.3 M evals/s forward vs 2.1 M reverse; C3 (P = 37) 0.60 M
+    // forward (6 passes) vs 2.5 M reverse; C4 (P = 8, ~2000 clades) 1.1e4 forward vs 2.9e4 reverse.
     {
         const char* gm = getenv("WHALE_GRAD_MODE");
-        if (!(gm && !strcmp(gm, "fwd")) && tables_smem(m, m->plan[1], false) <= SMEM_MAX && build_reverse(D)) {
+        bool want_rev = !(gm && !strcmp(gm, "fwd"));
+        if (want_rev && !(gm && !strcmp(gm, "rev"))) {
+            double clades = 0.0;
+            for (int f = 0; f < F; f++) clades += D->hdr[f].G;
+            const size_t need_fwd = set_budgets(D, 1, m->plan[1]);
+            if (m->plan[1].Kmax <= 6 && need_fwd <= SMEM_GOAL && clades / F <= 600.0) want_rev = false;
+        }
+        if (want_rev && tables_smem(m, m->plan[1], false) <= SMEM_MAX && build_reverse(D)) {
             const size_t need_rev = set_budgets_rev(D);
             D->rev = need_rev <= SMEM_MAX;
             if (env_int("WHALE_DEBUG", 0) >= 1)
