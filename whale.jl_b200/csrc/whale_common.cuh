@@ -180,6 +180,8 @@ struct PlanDev {  // tangent plan: which raw parameters each branch carries
     // Jacobian of the local quantities the adjoint pass differentiates with respect to — jac[(e*8 + j)*KR + k], KR = K[root]
     const int16_t* rinv;   // [nn][KR] component of root component k in node e's list (−1: none)
     double* jac;
+    const int* koff;       // [nn] prefix sums of K: k_tables packs its per-(node, component) shared arrays with them
+    int ktot;              // Σ_e K_e
 };
 
 #ifdef WHALE_EMU

@@ -29,7 +29,7 @@ constexpr unsigned TAB_JACOBIAN = 2u;     // this plan: no slice rows, the rever
 // species-tree metadata staged in shared memory: after an L2 flush every dependent global load of these tiny
 // arrays costs a DRAM round trip per level
 struct TabMeta {
-    const int *kind, *nsl, *ch0, *ch1, *ls, *ms, *qs, *K, *toff, *lvl_off, *lvl_nodes;
+    const int *kind, *nsl, *ch0, *ch1, *ls, *ms, *qs, *K, *toff, *lvl_off, *lvl_nodes, *koff;
     int* mode;  // 1: closed form, 0: chain
     const double *dt, *leafP, *pleaf, *x;
     const int16_t* cmap;
@@ -69,29 +69,33 @@ __device__ __forceinline__ void tables_block(const ModelDev& M, const PlanDev& P
     const bool writer = bid == 0;  // the per-branch outputs are identical in every table CTA: one writes
     const long long tk0 = CLOCK64();
     const int nn = M.nn, Kmax = PL.Kmax, P = M.n_params;
-    double* sd = reinterpret_cast<double*>(tsm);  // dt, leafP, pleaf [nn each], x [P], (α,β) [nn*Kmax*2], ϵ_0, ϵ_n [nn*Kmax each]
+    // dt, leafP, pleaf [nn each], x [P]; then per (node, component), packed with the plan's own offsets koff[e] (KT = Σ_e K_e
+    // entries, not nn·Kmax: the full plan of a branch-wise model has Kmax ≈ P but few components on most nodes):
+    // (α, β) [2·KT], whole-branch (α_n, β_n) [2·KT], ϵ_0 [KT], ϵ_n [KT]
+    const int KT = PL.ktot;
+    double* sd = reinterpret_cast<double*>(tsm);
     double* s_ab = sd + 3 * nn + P;           // per-slice (α, β) components
-    double* s_abn = s_ab + 2 * nn * Kmax;     // whole-branch (α_n, β_n) components (closed-form branches)
-    double* s_e0 = s_abn + 2 * nn * Kmax;
-    double* s_en = s_e0 + nn * Kmax;
-    int* si = reinterpret_cast<int*>(s_en + nn * Kmax);
+    double* s_abn = s_ab + 2 * KT;            // whole-branch (α_n, β_n) components (closed-form branches)
+    double* s_e0 = s_abn + 2 * KT;
+    double* s_en = s_e0 + KT;
+    int* si = reinterpret_cast<int*>(s_en + KT);
     const double* const s_eps0 = s_e0;
     // 10 arrays [nn], lvl_off [nlvl+1], lvl_nodes [nn]
-    int16_t* s_cm = reinterpret_cast<int16_t*>(si + 11 * nn + M.nlvl + 1);
+    int16_t* s_cm = reinterpret_cast<int16_t*>(si + 12 * nn + M.nlvl + 1);
     uint8_t* s_ro = reinterpret_cast<uint8_t*>(s_cm + nn * 2 * Kmax);
     {
         // one round trip: the first blockDim elements of every array are requested before anything is stored
         // (after an L2 flush each dependent round costs a DRAM latency); longer arrays finish in the loops below
         const int t = threadIdx.x, nt = blockDim.x;
         double r_dt = 0.0, r_lp = 0.0, r_pl = 0.0, r_x = 0.0;
-        int r_kind = 0, r_nsl = 0, r_c0 = 0, r_c1 = 0, r_ls = 0, r_ms = 0, r_qs = 0, r_K = 0, r_to = 0, r_ln = 0, r_lo = 0;
+        int r_kind = 0, r_nsl = 0, r_c0 = 0, r_c1 = 0, r_ls = 0, r_ms = 0, r_qs = 0, r_K = 0, r_to = 0, r_ln = 0, r_lo = 0, r_ko = 0;
         int16_t r_cm = 0;
         uint8_t r_ro = 0;
         if (t < nn) {
             r_dt = M.dt[t]; r_lp = M.leafP[t]; r_pl = pleaf ? pleaf[t] : 0.0;
             r_kind = M.kind[t]; r_nsl = M.nsl[t]; r_c0 = M.child0[t]; r_c1 = M.child1[t];
             r_ls = M.lam_slot[t]; r_ms = M.mu_slot[t]; r_qs = M.q_slot[t];
-            r_K = PL.K[t]; r_to = PL.toff[t]; r_ln = M.lvl_nodes[t];
+            r_K = PL.K[t]; r_to = PL.toff[t]; r_ln = M.lvl_nodes[t]; r_ko = PL.koff[t];
         }
         if (t <= M.nlvl) r_lo = M.lvl_off[t];
         if (t < P) r_x = x[t];
@@ -101,7 +105,7 @@ __device__ __forceinline__ void tables_block(const ModelDev& M, const PlanDev& P
             sd[t] = r_dt; sd[nn + t] = r_lp; sd[2 * nn + t] = r_pl;
             si[t] = r_kind; si[nn + t] = r_nsl; si[2 * nn + t] = r_c0; si[3 * nn + t] = r_c1;
             si[4 * nn + t] = r_ls; si[5 * nn + t] = r_ms; si[6 * nn + t] = r_qs;
-            si[7 * nn + t] = r_K; si[8 * nn + t] = r_to; si[10 * nn + M.nlvl + 1 + t] = r_ln;
+            si[7 * nn + t] = r_K; si[8 * nn + t] = r_to; si[10 * nn + M.nlvl + 1 + t] = r_ln; si[11 * nn + M.nlvl + 1 + t] = r_ko;
         }
         if (t <= M.nlvl) si[10 * nn + t] = r_lo;
         if (t < P) sd[3 * nn + t] = r_x;
@@ -112,6 +116,7 @@ __device__ __forceinline__ void tables_block(const ModelDev& M, const PlanDev& P
             si[i] = M.kind[i]; si[nn + i] = M.nsl[i]; si[2 * nn + i] = M.child0[i]; si[3 * nn + i] = M.child1[i];
             si[4 * nn + i] = M.lam_slot[i]; si[5 * nn + i] = M.mu_slot[i]; si[6 * nn + i] = M.q_slot[i];
             si[7 * nn + i] = PL.K[i]; si[8 * nn + i] = PL.toff[i]; si[10 * nn + M.nlvl + 1 + i] = M.lvl_nodes[i];
+            si[11 * nn + M.nlvl + 1 + i] = PL.koff[i];
         }
         for (int i = t + nt; i <= M.nlvl; i += nt) si[10 * nn + i] = M.lvl_off[i];
         for (int i = t + nt; i < P; i += nt) sd[3 * nn + i] = x[i];
@@ -120,7 +125,7 @@ __device__ __forceinline__ void tables_block(const ModelDev& M, const PlanDev& P
     }
     __syncthreads();
     TabMeta T{si, si + nn, si + 2 * nn, si + 3 * nn, si + 4 * nn, si + 5 * nn, si + 6 * nn, si + 7 * nn, si + 8 * nn,
-              si + 10 * nn, si + 10 * nn + M.nlvl + 1, si + 9 * nn, sd, sd + nn, sd + 2 * nn, sd + 3 * nn, s_cm, s_ro};
+              si + 10 * nn, si + 10 * nn + M.nlvl + 1, si + 11 * nn + M.nlvl + 1, si + 9 * nn, sd, sd + nn, sd + 2 * nn, sd + 3 * nn, s_cm, s_ro};
     // ---- phase A0: per-slice (α, β) of every branch and its mode — they depend on the branch's own rates only,
     //      so all nodes go in parallel (one warp per node) ----
     for (int e = warp; e < nn; e += nwarp) {
@@ -145,12 +150,12 @@ __device__ __forceinline__ void tables_block(const ModelDev& M, const PlanDev& P
                 if (closed) {  // the whole branch as one map (time n·Δt): all the chain over levels needs from this branch
                     D1 an, bn;
                     bdp_ab_t(lam, mu, t * (double)T.nsl[e], an, bn);
-                    s_abn[(e * Kmax + k) * 2 + 0] = k == 0 ? an.v : an.d;
-                    s_abn[(e * Kmax + k) * 2 + 1] = k == 0 ? bn.v : bn.d;
+                    s_abn[(T.koff[e] + k) * 2 + 0] = k == 0 ? an.v : an.d;
+                    s_abn[(T.koff[e] + k) * 2 + 1] = k == 0 ? bn.v : bn.d;
                 }
             }
-            s_ab[(e * Kmax + k) * 2 + 0] = k == 0 ? a.v : a.d;
-            s_ab[(e * Kmax + k) * 2 + 1] = k == 0 ? b.v : b.d;
+            s_ab[(T.koff[e] + k) * 2 + 0] = k == 0 ? a.v : a.d;
+            s_ab[(T.koff[e] + k) * 2 + 1] = k == 0 ? b.v : b.d;
             if (k == 0) T.mode[e] = closed;
             if (writer) {
                 PL.ab[(e * PL.Kmax + k) * 2 + 0] = k == 0 ? a.v : a.d;
@@ -172,7 +177,7 @@ __device__ __forceinline__ void tables_block(const ModelDev& M, const PlanDev& P
                 const unsigned role = k == 0 ? 0u : T.role[e * PL.Kmax + k];
                 auto child_last = [&](int jc, int child) -> D1 {  // the child's last ϵ, this lane's component
                     const int kc = k == 0 ? 0 : T.cmap[(e * 2 + jc) * Kmax + k];
-                    return mk(s_en[child * Kmax], (k > 0 && kc >= 0) ? s_en[child * Kmax + kc] : 0.0);
+                    return mk(s_en[T.koff[child]], (k > 0 && kc >= 0) ? s_en[T.koff[child] + kc] : 0.0);
                 };
                 D1 ep;
                 if (kind == WHALE_LEAF) {  // setnode! src/model.jl:170
@@ -211,11 +216,11 @@ __device__ __forceinline__ void tables_block(const ModelDev& M, const PlanDev& P
                     }
                 }
                 if (role & 16u) ep = mk(ep.v, 1.0);  // local plan: this component is ∂/∂ϵ_0 of the branch itself
-                s_e0[e * Kmax + k] = k == 0 ? ep.v : ep.d;
+                s_e0[T.koff[e] + k] = k == 0 ? ep.v : ep.d;
                 D1 en = ep, lf = mk(0.0);
                 if (n > 0 && closed) {
-                    const D1 an = mk(s_abn[(e * Kmax) * 2], k == 0 ? 0.0 : s_abn[(e * Kmax + k) * 2]);
-                    const D1 bn = mk(s_abn[(e * Kmax) * 2 + 1], k == 0 ? 0.0 : s_abn[(e * Kmax + k) * 2 + 1]);
+                    const D1 an = mk(s_abn[(T.koff[e]) * 2], k == 0 ? 0.0 : s_abn[(T.koff[e] + k) * 2]);
+                    const D1 bn = mk(s_abn[(T.koff[e]) * 2 + 1], k == 0 ? 0.0 : s_abn[(T.koff[e] + k) * 2 + 1]);
                     const D1 r = mk(1.0) / (1.0 - bn * ep);
                     en = (an + ((1.0 - an) - bn) * ep) * r;
                     // leaf clade on a leaf branch: ℓ_n = leafℙ·Π_i ϕ_i (src/core.jl:94,123) = leafℙ·ϕ over the whole
@@ -225,8 +230,8 @@ __device__ __forceinline__ void tables_block(const ModelDev& M, const PlanDev& P
                     double2* uvrow = PL.uv + T.toff[e];  // every table CTA writes the same values and reads its own
                     D1 u = ep, v = mk(1.0);
                     uvrow[k] = k == 0 ? make_double2(u.v, v.v) : make_double2(u.d, v.d);
-                    const D1 a = mk(s_ab[(e * Kmax) * 2], k == 0 ? 0.0 : s_ab[(e * Kmax + k) * 2]);
-                    const D1 b = mk(s_ab[(e * Kmax) * 2 + 1], k == 0 ? 0.0 : s_ab[(e * Kmax + k) * 2 + 1]);
+                    const D1 a = mk(s_ab[(T.koff[e]) * 2], k == 0 ? 0.0 : s_ab[(T.koff[e] + k) * 2]);
+                    const D1 b = mk(s_ab[(T.koff[e]) * 2 + 1], k == 0 ? 0.0 : s_ab[(T.koff[e] + k) * 2 + 1]);
                     const D1 c = (1.0 - a) - b;
                     for (int i = 1; i <= n; i++) {
                         const D1 un = c * u + a * v;
@@ -244,7 +249,7 @@ __device__ __forceinline__ void tables_block(const ModelDev& M, const PlanDev& P
                 } else if (kind == WHALE_LEAF) {
                     lf = mk(T.leafP[e]);
                 }
-                s_en[e * Kmax + k] = k == 0 ? en.v : en.d;
+                s_en[T.koff[e] + k] = k == 0 ? en.v : en.d;
                 if (kind == WHALE_LEAF && writer) PL.leaf[e * PL.Kmax + k] = k == 0 ? lf.v : lf.d;
             }
         }
@@ -270,7 +275,7 @@ __device__ __forceinline__ void tables_block(const ModelDev& M, const PlanDev& P
                     if (kind != WHALE_ROOT) {
                         if (j == 0 && T.ls[e] == gp) v = 1.0;
                         if (j == 1 && T.ms[e] == gp) v = 1.0;
-                        if (j == 2 && ke > 0) v = s_e0[e * Kmax + ke];
+                        if (j == 2 && ke > 0) v = s_e0[T.koff[e] + ke];
                     }
                     if (kind != WHALE_INTERNAL && ke > 0) {
                         if (j == 3) v = PL.cx[e * PL.Kmax + ke];
@@ -279,7 +284,7 @@ __device__ __forceinline__ void tables_block(const ModelDev& M, const PlanDev& P
                     if (kind != WHALE_WGD && (j == 5 || j == 6)) {
                         const int c = j == 5 ? T.ch0[e] : T.ch1[e];
                         const int kc = PL.rinv[c * KRr + k];
-                        if (kc > 0) v = s_en[c * Kmax + kc];
+                        if (kc > 0) v = s_en[T.koff[c] + kc];
                     }
                 }
             }
@@ -300,16 +305,16 @@ __device__ __forceinline__ void tables_block(const ModelDev& M, const PlanDev& P
         const int idx = t - T.toff[e];
         const int i = idx / K, k = idx - i * K;
         if (i == 0) {
-            PL.eps[t] = s_eps0[e * Kmax + k];
+            PL.eps[t] = s_eps0[T.koff[e] + k];
             PL.pp[t] = make_double2(k == 0 ? 1.0 : 0.0, k == 0 ? 1.0 : 0.0);  // ϕ_1 = 1 (src/model.jl:171)
             continue;
         }
-        const D1 a = mk(s_ab[(e * Kmax) * 2], k == 0 ? 0.0 : s_ab[(e * Kmax + k) * 2]);
-        const D1 b = mk(s_ab[(e * Kmax) * 2 + 1], k == 0 ? 0.0 : s_ab[(e * Kmax + k) * 2 + 1]);
+        const D1 a = mk(s_ab[(T.koff[e]) * 2], k == 0 ? 0.0 : s_ab[(T.koff[e] + k) * 2]);
+        const D1 b = mk(s_ab[(T.koff[e]) * 2 + 1], k == 0 ? 0.0 : s_ab[(T.koff[e] + k) * 2 + 1]);
         const D1 g = (1.0 - a) * (1.0 - b);
         D1 ep, r;  // ϵ_i and 1 / (1 − βϵ_{i−1})
         if (T.mode[e]) {
-            D1 prev = mk(s_eps0[e * Kmax], k == 0 ? 0.0 : s_eps0[e * Kmax + k]);
+            D1 prev = mk(s_eps0[T.koff[e]], k == 0 ? 0.0 : s_eps0[T.koff[e] + k]);
             if (i > 1) {
                 const unsigned role = k == 0 ? 0u : T.role[e * PL.Kmax + k];
                 D1 lam, mu, ai, bi;

@@ -390,8 +390,15 @@ static cudaError_t upload_plan(Plan& pl, int nn) {
     if ((e = cudaMalloc((void**)&cond, 4 * pl.Kmax * sizeof(double))) != cudaSuccess) return e;
     cudaMemset(cx, 0, nk); cudaMemset(cy, 0, nk); cudaMemset(leaf, 0, nk);
     cudaMemset(cond, 0, 4 * pl.Kmax * sizeof(double));
-    pl.owned = {dK, dact, dtoff, dcmap, drole, eps, pp, uv, ab, cx, cy, leaf, shapeW, cond, tim};
+    std::vector<int> koff(nn, 0);
+    int ktot = 0;
+    for (int e2 = 0; e2 < nn; e2++) { koff[e2] = ktot; ktot += pl.K[e2]; }
+    int* dkoff;
+    if ((e = upload(koff, &dkoff)) != cudaSuccess) return e;
+    pl.owned = {dK, dact, dtoff, dcmap, drole, eps, pp, uv, ab, cx, cy, leaf, shapeW, cond, tim, dkoff};
     pl.dev = PlanDev{pl.Kmax, dK, dact, dcmap, drole, dtoff, eps, pp, uv, ab, cx, cy, leaf, shapeW, cond, nullptr, nullptr, nullptr, tim};
+    pl.dev.koff = dkoff;
+    pl.dev.ktot = ktot;
     return cudaSuccess;
 }
 
@@ -557,8 +564,9 @@ static size_t smem_need(const whale_model* m, const FamHdr& h, int plan, int Kma
 
 static size_t tables_smem(const whale_model* m, const Plan& pl, bool shapes) {  // mirrors the carve-ups in k_tables
     const size_t nn = m->nn, nlvl = m->lvl_off.size() - 1;
-    const size_t ndbl = 6;
-    size_t need = (3 * nn + m->P + ndbl * nn * pl.Kmax) * sizeof(double) + (11 * nn + nlvl + 1) * sizeof(int) +
+    size_t ktot = 0;
+    for (int e = 0; e < m->nn; e++) ktot += (size_t)pl.K[e];
+    size_t need = (3 * nn + m->P + 6 * ktot) * sizeof(double) + (12 * nn + nlvl + 1) * sizeof(int) +
                   nn * 2 * pl.Kmax * sizeof(int16_t) + nn * pl.Kmax + 16;
     if (shapes)  // a leaf-shape CTA keeps its branch's projective and (ϕ, ψ) rows in shared memory
         for (int e : m->leafnodes) need = std::max(need, 2 * (size_t)(m->nsl[e] + 1) * pl.K[e] * sizeof(double2));
