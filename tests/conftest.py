@@ -263,3 +263,29 @@ def c4_shape_vs_oracle(tmp_path, n_fam=3, branch_rates=True):
     tot, _, og, _ = flat.logpdf(fm, ff, grad=True)
     assert ll == pytest.approx(tot, rel=1e-9)
     np.testing.assert_allclose(grad, og, rtol=1e-9, atol=1e-9 * np.abs(og).max())
+
+
+def backtrack_uses_kept_parameters(L):
+    """A model handle is shared by all wm(θ) copies: backtracking from a data handle must use the parameters of the
+    evaluation that produced ITS kept ℓ, not whatever was evaluated last on the model handle (round-1 advisor finding:
+    logpdf!(wm, a); logpdf(wm2, b); backtrack(wm, a) failed or sampled from the wrong distribution)."""
+    g = load_golden("c1_example1")
+    mh = L.model_create(golden_model(g))
+    dh = L.data_create(mh, golden_fams(g, [0, 7]))
+    dh2 = L.data_create(mh, golden_fams(g, [3]))
+    xa = g["xs"][-1]
+    xb = xa.copy()
+    xb[:34] -= 1.5  # much lower rates: different tables, different q/η below
+    xb[-3:] = [0.9, 0.8, 0.3]
+    U = np.random.default_rng(4).random((2, 6, 4 * 256))
+    try:
+        L.logpdf_grad(mh, dh, xa, g["m_pleaf"], 1, keep_ell=True)
+        c1, s1, n1 = L.backtrack(mh, dh, 6, U, max_nodes=256)
+        L.logpdf_grad(mh, dh2, xb, g["m_pleaf"], 1, want_grad=True)  # another batch, other parameters, same model handle
+        c2, s2, n2 = L.backtrack(mh, dh, 6, U, max_nodes=256)
+        assert np.all(s1 == 0) and np.all(s2 == 0)
+        assert np.array_equal(c1, c2) and np.array_equal(n1, n2)
+    finally:
+        L.L.whale_data_destroy(dh)
+        L.L.whale_data_destroy(dh2)
+        L.L.whale_model_destroy(mh)

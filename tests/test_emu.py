@@ -351,3 +351,8 @@ def test_emu_even_row_stride_variant(tmp_path):
     dh = L2.data_create(mh, golden_fams(g, [3]))
     L2.logpdf_grad(mh, dh, g["xs"][2], g["m_pleaf"], 1, keep_ell=True)
     np.testing.assert_allclose(L2.ell_get(dh, 0), g["ell_3"], rtol=1e-11, atol=0)
+
+
+def test_emu_backtrack_uses_kept_parameters(L):
+    from conftest import backtrack_uses_kept_parameters
+    backtrack_uses_kept_parameters(L)

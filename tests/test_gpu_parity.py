@@ -268,3 +268,8 @@ def test_reverse_mode_one_persistent_cta(L, monkeypatch):
     monkeypatch.setenv("WHALE_REV_GRID", "1")
     run_parity(L, "c1_example1", conds=["root"])
     run_parity(L, "landplant100", sel=list(range(0, 100, 7)), conds=["root"])
+
+
+def test_backtrack_uses_kept_parameters(L):
+    from conftest import backtrack_uses_kept_parameters
+    backtrack_uses_kept_parameters(L)

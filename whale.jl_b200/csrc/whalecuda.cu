@@ -220,6 +220,8 @@ struct whale_data {
     bool ev_valid = false;
     uint64_t ell_total = 0;
     bool ell_valid = false;
+    double* d_x_keep = nullptr;      // raw parameters and p_leaf of the evaluation that produced the kept ℓ: backtracking
+    double* d_pleaf_keep = nullptr;  //   must use THESE (a model handle is shared by wm(θ) copies and evaluated at many θ)
     // aggregated work counters per node (over families): Σ C_e, Σ T_e (unfiltered triples of compat clades)
     std::vector<double> aggC, aggT;
     double aggG = 0, aggTroot = 0;
@@ -1518,7 +1520,7 @@ int32_t whale_data_destroy(whale_data_t d) {
     for (auto& g : d->graphs) if (g.state == 2 && g.exec) cudaGraphExecDestroy(g.exec);
 #endif
     if (d->ev_fork) cudaEventDestroy(d->ev_fork);
-    cudaFree(d->d_ell); cudaFree(d->d_tim);
+    cudaFree(d->d_ell); cudaFree(d->d_tim); cudaFree(d->d_x_keep); cudaFree(d->d_pleaf_keep);
     for (int i = 0; i < 4; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     delete d;
     return WHALE_OK;
@@ -1625,6 +1627,14 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
     const int F = D->F;
     const bool keep = (flags & WHALE_KEEP_ELL) != 0;
     if (keep && !D->d_ell) CU(cudaMalloc((void**)&D->d_ell, std::max<uint64_t>(D->ell_total, 1) * sizeof(double)));
+    if (keep) {
+        if (!D->d_x_keep) {
+            CU(cudaMalloc((void**)&D->d_x_keep, std::max(1, m->P) * sizeof(double)));
+            CU(cudaMalloc((void**)&D->d_pleaf_keep, m->nn * sizeof(double)));
+        }
+        CU(cudaMemcpyAsync(D->d_x_keep, d_x, m->P * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(D->d_pleaf_keep, m->d_pleaf, m->nn * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
     const bool prof = (flags & WHALE_PROFILE) != 0;
     if (prof && !D->ev[0]) for (int i = 0; i < 4; i++) CU(cudaEventCreate(&D->ev[i]));
     if (prof && !D->d_tim) {
@@ -1913,7 +1923,6 @@ int32_t whale_backtrack(whale_model_t m, whale_data_t d, int32_t n_samples, cons
     if (d->m != m) return fail(WHALE_ERR_ARG, "data handle belongs to another model");
     if (n_samples <= 0 || stride <= 0 || max_nodes <= 1) return fail(WHALE_ERR_ARG, "n_samples, stride and max_nodes must be positive");
     if (!d->ell_valid || !d->d_ell) return fail(WHALE_ERR_STATE, "no ℓ kept: evaluate with WHALE_KEEP_ELL (logpdf!) first");
-    if (!m->x_host_valid) return fail(WHALE_ERR_STATE, "backtracking needs the parameters of a host-pointer evaluation");
     CU(cudaSetDevice(m->device));
     const size_t W = (size_t)d->F * n_samples;
     double* d_u = nullptr;
@@ -1931,8 +1940,8 @@ int32_t whale_backtrack(whale_model_t m, whale_data_t d, int32_t n_samples, cons
     CUB(cudaMalloc((void**)&d_t, W * max_nodes * 4)); CUB(cudaMalloc((void**)&d_p, W * max_nodes * 4));
     CUB(cudaMalloc((void**)&d_stack, W * max_nodes * sizeof(int4)));
     Plan& p0 = m->plan[0];
-    CUB(launch_tables(m, p0, m->d_x, m->d_pleaf, m->stream, false));
-    BTArgs a{m->dev, p0.dev, d->d_arena, d->d_hdr, d->d_ell, m->d_x, d_u, (long long)stride, d->F, n_samples, max_nodes,
+    CUB(launch_tables(m, p0, d->d_x_keep, d->d_pleaf_keep, m->stream, false));
+    BTArgs a{m->dev, p0.dev, d->d_arena, d->d_hdr, d->d_ell, d->d_x_keep, d_u, (long long)stride, d->F, n_samples, max_nodes,
              0, n_samples, d_cnt, d_g, d_e, d_t, d_p, d_st, d_stack};
     cudaEvent_t eb0 = nullptr, eb1 = nullptr;
     CUB(cudaEventCreate(&eb0)); CUB(cudaEventCreate(&eb1));
