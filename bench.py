@@ -1,19 +1,25 @@
 #!/usr/bin/env python
 """bench.py — family (log-likelihood + gradient) evaluations per second on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--c3-families F]
 
-Workload (BASELINE.json configs[1], "C2"): per GPU 1000 synthetic families x ~200 clades on the reference's
+Headline workload (BASELINE.json configs[1], "C2"): per GPU 1000 synthetic families x ~200 clades on the reference's
 9-taxon tree with 2 WGD nodes (Whale.extree + wgd_1/wgd_2, test/runtests.jl:8-11), ConstantDLWGD rates
 (P = 5: λ, μ, q1, q2, η), Δt = 0.05, RootCondition.  One *step* = one logpdf+∇ evaluation of every family
 for a NEW parameter vector (NUTS/MLE style: slice tables are recomputed each step).  Families shard across
 ranks (weak scaling: 1000 families per GPU); the only collective is the sum of 1+P doubles.
 
+Second leg in the same run (BASELINE.json configs[2], the north star's scaling configuration, "C3"): `--c3-families`
+(default 100000) synthetic families in TOTAL, branch-wise rates (DLWGD, P = 37), STRONG scaling: rank r holds the
+families [r·F/N, (r+1)·F/N), one MLE gradient step = every rank's reverse-mode evaluation + the same all-reduce.
+Reported under the key "c3_strong" (device-timed and end-to-end); the headline `value` stays the C2 metric.
+
 Prints ONE JSON line (rank 0).  `value` = device-timed throughput with the arena resident in HBM (CUDA events
 per step, L2 flushed between steps, max over ranks); `e2e` = the same metric through the C-ABI call with HOST
 buffers (θ H2D and loglik+grad D2H inside the timed region); `roofline` = the DP kernel against the measured
 fp64 FMA peak (the DP never leaves shared memory), `roofline_hbm` the same launch against
-MEASURED_PEAKS.json's HBM bandwidth; `cpu_baseline` = the C++ oracle port on this box's host cores.
+MEASURED_PEAKS.json's HBM bandwidth; `cpu_baseline` = the C++ oracle port on this box's host cores (all of them,
+set explicitly: torchrun exports OMP_NUM_THREADS=1).
 """
 from __future__ import annotations
 
@@ -46,12 +52,42 @@ def thetas(n, seed=0):
     return np.ascontiguousarray(x)
 
 
+def host_threads():
+    """Host cores this process may use (the CPU arms set their OpenMP thread count to this explicitly)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def dataset(rank, n_fam):
     from whale_jl_b200 import synth
-    d = os.path.join(ROOT, ".synth_cache", f"c2_seed{SEED}_rank{rank}_n{n_fam}")
+    d = synth.cache_dir(f"c2_seed{SEED}_rank{rank}_n{n_fam}")
     t0 = time.time()
-    synth.generate(d, n_fam, seed=SEED + 7919 * rank)
+    synth.generate(d, n_fam, seed=SEED + 7919 * rank, workers=min(host_threads(), 16))
     return d, time.time() - t0
+
+
+C3_SEED = 3
+
+
+def c3_dataset(rank, world, total):
+    """This rank's contiguous shard of the C3 families (strong scaling: `total` families over `world` ranks)."""
+    from whale_jl_b200 import synth
+    lo, hi = total * rank // world, total * (rank + 1) // world
+    d = synth.cache_dir(f"c3_seed{C3_SEED}_n{total}_shard{rank}of{world}")
+    t0 = time.time()
+    synth.generate(d, hi - lo, seed=C3_SEED, first=lo, workers=max(1, min(64, host_threads() // max(1, world))))
+    return d, hi - lo, time.time() - t0
+
+
+def c3_model():
+    """9-taxon tree + 2 WGDs, branch-wise rates on the log scale (DLWGD, P = 2·17 + 2 + 1 = 37; SURVEY §8d: log-rates
+    ~ N(log 0.15, 0.3²))."""
+    import whale_jl_b200 as W
+    rng = np.random.default_rng(7)
+    r = W.DLWGD(lam=list(rng.normal(np.log(0.15), 0.3, 17)), mu=list(rng.normal(np.log(0.15), 0.3, 17)), q=[0.2, 0.1], eta=0.67)
+    return W.WhaleModel(r, W.synth.c1_species_tree(), DT)
 
 
 class ClockSampler:
@@ -90,58 +126,157 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_baseline(ale_dir, budget_s=12.0, nthreads=0):
-    """The oracle port (C++ restatement of the reference loops, OpenMP over families like Threads.@threads)
-    timed on a bounded sample of the same families, logpdf + ForwardDiff-style gradient."""
+def _oracle_c2(ale_dir, limit=None):
     from oracle import flat, whale_oracle as wo
     ow = wo.WhaleModel(wo.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), wo.c1_tree(), DT)
-    files = sorted(os.listdir(ale_dir))[:128]
+    files = sorted(f for f in os.listdir(ale_dir) if f.endswith(".ale"))[:limit]
     spmap = {n.name: n.id for n in ow.order if n.isleaf()}
     ccds = [wo.CCD(wo.parse_aleobserve(os.path.join(ale_dir, f)), ow, spmap) for f in files]
-    fm, ff = flat.FlatModel(ow), flat.FlatFams(ccds, len(ow))
+    return flat, flat.FlatModel(ow), flat.FlatFams(ccds, len(ow)), len(ccds)
+
+
+def cpu_baseline(ale_dir, budget_s=12.0):
+    """The oracle port (C++ restatement of the reference loops, OpenMP over families like Threads.@threads,
+    src/core.jl:58-64) timed on ALL families of the step, logpdf + ForwardDiff-style gradient, on every host core
+    (thread count set explicitly, not taken from OMP_NUM_THREADS)."""
+    flat, fm, ff, n_fam = _oracle_c2(ale_dir)
+    nt = host_threads()
     xs = thetas(64, seed=99)
-    flat.logpdf(fm, ff, x=xs[0], grad=True, nthreads=nthreads)  # warm-up
+    flat.logpdf(fm, ff, x=xs[0], grad=True, nthreads=nt)  # warm-up
     t0, n = time.perf_counter(), 0
     while time.perf_counter() - t0 < budget_s:
-        flat.logpdf(fm, ff, x=xs[n % len(xs)], grad=True, nthreads=nthreads)
+        flat.logpdf(fm, ff, x=xs[n % len(xs)], grad=True, nthreads=nt)
         n += 1
     dt = time.perf_counter() - t0
-    cores = int(flat.lib().oracle_max_threads()) if nthreads == 0 else nthreads
-    return {"value": len(ccds) * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{len(ccds)} of the {FAMILIES_PER_GPU} C2 families x {n} evaluations (logpdf + Dual<5> gradient), "
-                      f"OMP_NUM_THREADS={cores}; JULIA_NUM_THREADS n/a (no julia in this image)"}
+    return {"value": n_fam * n / dt, "unit": UNIT, "cores": nt, "kind": "port",
+            "sample": f"all {n_fam} C2 families x {n} evaluations (logpdf + Dual<5> gradient), {nt} OpenMP threads "
+                      f"(set explicitly; OMP_NUM_THREADS={os.environ.get('OMP_NUM_THREADS', 'unset')}); "
+                      f"JULIA_NUM_THREADS n/a (no julia in this image)"}
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; the Julia original cannot run here) on the
-    same config, all host threads, each step a bounded sample of the workload."""
+    same config — every family of the step, all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import flat, whale_oracle as wo
     d, _ = dataset(0, FAMILIES_PER_GPU)
-    ow = wo.WhaleModel(wo.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), wo.c1_tree(), DT)
-    S = 256
-    spmap = {n.name: n.id for n in ow.order if n.isleaf()}
-    ccds = [wo.CCD(wo.parse_aleobserve(os.path.join(d, f)), ow, spmap) for f in sorted(os.listdir(d))[:S]]
-    fm, ff = flat.FlatModel(ow), flat.FlatFams(ccds, len(ow))
+    flat, fm, ff, S = _oracle_c2(d)
+    nt = host_threads()
     xs = thetas(args.steps + args.warmup)
     for i in range(args.warmup):
-        flat.logpdf(fm, ff, x=xs[i], grad=True)
+        flat.logpdf(fm, ff, x=xs[i], grad=True, nthreads=nt)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        flat.logpdf(fm, ff, x=xs[args.warmup + i], grad=True)
+        flat.logpdf(fm, ff, x=xs[args.warmup + i], grad=True, nthreads=nt)
     dt = time.perf_counter() - t0
-    cores = int(flat.lib().oracle_max_threads())
     val = S * args.steps / dt
-    sample = f"{S} of the {FAMILIES_PER_GPU} C2 families per step, logpdf + Dual<5> gradient, {cores} OpenMP threads"
+    sample = (f"all {S} C2 families per step, logpdf + Dual<5> gradient, {nt} OpenMP threads (set explicitly; "
+              f"OMP_NUM_THREADS={os.environ.get('OMP_NUM_THREADS', 'unset')})")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C2: 1000 synthetic families x ~200 clades, 9-taxon tree + 2 WGD, ConstantDLWGD P=5, dt=0.05"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nt, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def c3_leg(args, L, wlib, rank, world, d3, n3, gen3_s, flush, stream):
+    """BASELINE.json configs[2] (the north star's scaling configuration): `--c3-families` families in total, branch-wise
+    rates (P = 37), strong scaling over the ranks, one MLE gradient step = reverse-mode evaluation of the rank's shard +
+    all-reduce of 1+P doubles.  Device-timed (CUDA events, L2 flushed, max over ranks) and end to end (host θ in,
+    loglik+∇ out)."""
+    import torch
+    import torch.distributed as dist
+    import whale_jl_b200 as W
+    from whale_jl_b200.core import _data_handle
+    model = c3_model()
+    t0 = time.time()
+    ccds = W.read_ale_native(d3, model)
+    mh, dh = _data_handle(model, ccds)
+    pack_s = time.time() - t0
+    P = model.n_params
+    K, Wm = max(3, min(args.steps, 12)), 3
+    rng = np.random.default_rng(11)
+    x0 = model.x()
+    xs = x0[None, :] + 0.02 * rng.standard_normal((K + Wm, P))
+    xs[:, -3:] = np.clip(xs[:, -3:], 1e-3, 1 - 1e-3)
+    X = torch.tensor(xs, device="cuda", dtype=torch.float64)
+    OUT = torch.zeros(1 + P, device="cuda", dtype=torch.float64)
+    cond = 1
+
+    def step(i, flags):
+        L.logpdf_grad_async(mh, dh, X[i].data_ptr(), cond, flags, OUT.data_ptr(), stream)
+        if world > 1:
+            dist.all_reduce(OUT)
+
+    for i in range(Wm):
+        step(i, wlib.WANT_GRAD)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    kms = np.zeros((K, 3))
+    for i in range(K):
+        flush.zero_()
+        ev[i][0].record()
+        step(Wm + i, wlib.WANT_GRAD | wlib.PROFILE)
+        ev[i][1].record()
+        ev[i][1].synchronize()
+        kms[i] = L.last_kernel_ms(dh)
+    torch.cuda.synchronize()
+    total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    last = OUT.cpu().numpy().copy()
+    pin_x = torch.empty(P, dtype=torch.float64).pin_memory()
+    pin_o = torch.empty(1 + P, dtype=torch.float64).pin_memory()
+    Xd = torch.empty(P, device="cuda", dtype=torch.float64)
+
+    def e2e_step(i):
+        if world == 1:
+            return L.logpdf_grad(mh, dh, xs[i], model.p_leaf(), cond, want_grad=True)[0]
+        pin_x.copy_(torch.from_numpy(xs[i]))
+        Xd.copy_(pin_x, non_blocking=True)
+        L.logpdf_grad_async(mh, dh, Xd.data_ptr(), cond, wlib.WANT_GRAD, OUT.data_ptr(), stream)
+        dist.all_reduce(OUT)
+        pin_o.copy_(OUT, non_blocking=True)
+        torch.cuda.synchronize()
+        return float(pin_o[0])
+
+    e2e_step(0)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        ll = e2e_step(Wm + i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    flops, abytes = L.work_estimate(mh, dh, True)
+    arena = int(L.L.whale_data_arena_bytes(dh))
+    mode = "reverse" if L.L.whale_data_grad_mode(dh) == 1 else "forward"
+    passes = int(L.L.whale_data_grad_passes(dh))
+    tot = torch.tensor([total_ms, e2e_s, float(n3)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        mx = tot.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tot.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        total_ms, e2e_s, fam_total = float(mx[0]), float(mx[1]), int(round(float(sm[2])))
+    else:
+        fam_total = n3
+    L.L.whale_data_destroy(dh)
+    assert np.isfinite(ll) and abs(ll - last[0]) <= 1e-9 * abs(last[0]), (ll, last[0])
+    dp_ms = float(kms[:, 1].mean())
+    return {"workload": f"C3: {fam_total} synthetic families in total (strong scaling, {n3} on rank 0), 9-taxon tree + 2 WGD, "
+                        f"DLWGD branch-wise rates P={P}, dt={DT}, RootCondition, new theta each step",
+            "families_total": fam_total, "P": P, "grad_mode": mode, "gradient_passes": passes, "steps": K, "warmup": Wm,
+            "value": fam_total * K / (total_ms * 1e-3), "unit": UNIT, "ms_per_step": total_ms / K, "scaling": "strong",
+            "e2e": {"value": fam_total * K / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / K,
+                    "h2d_bytes_per_step": 8 * (P + model.nn), "d2h_bytes_per_step": 8 * (1 + P)},
+            "kernels_ms_rank0": {"k_tables": float(kms[:, 0].mean()), "k_dp": dp_ms, "k_reduce": float(kms[:, 2].mean())},
+            "algorithmic_tflops_rank0": flops / (dp_ms * 1e-3) / 1e12,
+            "arena_bytes_rank0": arena, "gen_s": round(gen3_s, 1), "pack_s": round(pack_s, 1), "loglik_last": float(last[0])}
 
 
 def main():
@@ -152,19 +287,27 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--families", type=int, default=FAMILIES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--c3-families", type=int, default=100000,
+                    help="total families of the strong-scaling C3 leg (BASELINE configs[2]); 0 disables the leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    # synthetic inputs first (worker processes are forked here, before this process touches CUDA)
+    d, gen_s = dataset(rank, args.families)
+    d3 = n3 = gen3_s = None
+    if args.c3_families > 0:
+        d3, n3, gen3_s = c3_dataset(rank, world, args.c3_families)
 
     import torch
     import torch.distributed as dist
     import whale_jl_b200 as W
     from whale_jl_b200 import lib as wlib
 
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
@@ -175,8 +318,7 @@ def main():
     L = wlib.get()
     L.check(L.L.whale_set_device(local))
 
-    # ---- data: generate this rank's shard, read_ale, pack once ----
-    d, gen_s = dataset(rank, args.families)
+    # ---- data: this rank's shard (generated above), read_ale, pack once ----
     model = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), W.synth.c1_species_tree(), DT)
     t0 = time.time()
     ccds = W.read_ale_native(d, model)  # whale_read_ale: parse + CCD construction + packing in the library
@@ -277,6 +419,16 @@ def main():
     e2e_val = F * world * K / e2e_s
     assert np.isfinite(ll_e2e) and abs(ll_e2e - last[0]) <= 1e-9 * abs(last[0]), (ll_e2e, last[0])
 
+    # ---- second leg: the north star's scaling configuration (C3, strong scaling) ----
+    c3 = None
+    if d3 is not None:
+        try:
+            c3 = c3_leg(args, L, wlib, rank, world, d3, n3, gen3_s, flush, stream)
+        except Exception as exc:  # the headline line must survive a failure of the second leg
+            c3 = {"error": f"{type(exc).__name__}: {exc}"}
+            if world > 1:
+                raise
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -333,7 +485,10 @@ def main():
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         "dp_phase_cycles_mean_max": phase_cycles, "tables_cycles": tables_cycles,
         "loglik_last": float(last[0]),
+        "grad_mode": "reverse" if L.L.whale_data_grad_mode(dh) == 1 else "forward",
     }
+    if c3 is not None:
+        out["c3_strong"] = c3
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(d)
     print(json.dumps(out))

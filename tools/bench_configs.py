@@ -49,7 +49,7 @@ def main():
     rng = np.random.default_rng(7)
     out = {}
     # ---- C3: branch-wise rates on the 9-taxon tree ----
-    d = synth.generate(os.path.join(ROOT, ".synth_cache", f"c3_seed3_n{args.c3_families}"), args.c3_families, seed=3)
+    d = synth.generate(synth.cache_dir(f"c3_seed3_n{args.c3_families}"), args.c3_families, seed=3)
     r = W.DLWGD(lam=list(rng.normal(np.log(0.15), 0.3, 17)), mu=list(rng.normal(np.log(0.15), 0.3, 17)), q=[0.2, 0.1], eta=0.67)
     w = W.WhaleModel(r, synth.c1_species_tree(), 0.05)
     ccd = W.read_ale_native(d, w)
@@ -66,7 +66,7 @@ def main():
         return
     # ---- C4: 30 taxa, 5 WGDs, ~2,000 clades ----
     nws = newick.nwstr(synth.c4_species_tree(), True) + ";"
-    d = synth.generate(os.path.join(ROOT, ".synth_cache", f"c4_seed4_n{args.c4_families}"), args.c4_families, seed=4,
+    d = synth.generate(synth.cache_dir(f"c4_seed4_n{args.c4_families}"), args.c4_families, seed=4,
                        tree=synth.c4_species_tree(), **synth.C4_FAMILY)
     q = [0.2, 0.1, 0.2, 0.1, 0.2]
     w = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=q, eta=0.67), newick.readnw(nws), 0.05)

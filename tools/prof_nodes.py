@@ -22,7 +22,7 @@ def main():
     import whale_jl_b200 as W
     from whale_jl_b200 import synth, lib as wlib
     from whale_jl_b200.core import _data_handle
-    d = os.path.join(ROOT, ".synth_cache", f"c2_seed2_rank0_n{args.families}")
+    d = synth.cache_dir(f"c2_seed2_rank0_n{args.families}")
     synth.generate(d, args.families, seed=2)
     w = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), synth.c1_species_tree(), 0.05)
     ccd = W.read_ale(d, w)

@@ -279,23 +279,38 @@ def _gen_range(args):
     return hi - lo
 
 
-def generate(outdir: str, n_fam: int, seed: int, tree: newick.Node | None = None, workers: int = 0, **kw) -> str:
-    """Write `n_fam` synthetic .ale files into outdir (idempotent: reuses a complete directory).  Family f is drawn from
-    its own generator seeded (seed, f), so the files do not depend on `workers` (0 = all host cores for large sets)."""
+def cache_dir(name: str) -> str:
+    """Where the benchmarks keep generated families: outside the repository (WHALE_SYNTH_CACHE or the temp directory), so
+    that a source snapshot never carries generated data."""
+    import tempfile
+    root = os.environ.get("WHALE_SYNTH_CACHE") or os.path.join(tempfile.gettempdir(), "whale_synth_cache")
+    return os.path.join(root, name)
+
+
+def generate(outdir: str, n_fam: int, seed: int, tree: newick.Node | None = None, workers: int = 0, first: int = 0,
+             **kw) -> str:
+    """Write the synthetic families first .. first + n_fam − 1 as .ale files into outdir (idempotent: reuses a complete
+    directory).  Family f is drawn from its own generator seeded (seed, f), so the files depend neither on `workers`
+    (0 = the host cores this process may use, for large sets) nor on how a set is split into shards (`first`)."""
     tree = tree or c1_species_tree()
     os.makedirs(outdir, exist_ok=True)
     done = outdir.rstrip("/") + ".complete"  # sibling marker: read_ale reads every file in outdir
-    if os.path.exists(done) and open(done).read().strip() == f"{n_fam} {seed} {sorted(kw.items())}":
+    tag = f"{n_fam} {seed} {sorted(kw.items())}" + (f" first={first}" if first else "")
+    if os.path.exists(done) and open(done).read().strip() == tag:
         return outdir
-    nw = workers or (min(os.cpu_count() or 1, 32) if n_fam >= 2000 else 1)
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    nw = workers or (min(ncpu, 64) if n_fam >= 2000 else 1)
     if nw > 1:
         import multiprocessing as mp
         step = max(1, (n_fam + 4 * nw - 1) // (4 * nw))
-        jobs = [(outdir, tree, seed, lo, min(n_fam, lo + step), kw) for lo in range(0, n_fam, step)]
+        jobs = [(outdir, tree, seed, lo, min(first + n_fam, lo + step), kw) for lo in range(first, first + n_fam, step)]
         with mp.get_context("fork").Pool(nw) as pool:
             pool.map(_gen_range, jobs)
     else:
-        _gen_range((outdir, tree, seed, 0, n_fam, kw))
+        _gen_range((outdir, tree, seed, first, first + n_fam, kw))
     with open(done, "w") as fh:
-        fh.write(f"{n_fam} {seed} {sorted(kw.items())}\n")
+        fh.write(tag + "\n")
     return outdir
