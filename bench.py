@@ -182,6 +182,38 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def setup_exchange(L, dh, rank, world):
+    """Sum over ranks: the library's one-shot peer-memory exchange (whale_peer_*: every rank stores its 1+P doubles into
+    every peer's buffer over NVLink and adds them in rank order) when CUDA IPC works between the ranks, else an NCCL
+    all-reduce (WHALE_BENCH_EXCHANGE=nccl forces that).  Returns True for the peer exchange."""
+    if world == 1:
+        return False
+    import torch
+    import torch.distributed as dist
+    ok, h = 1, bytes(64)
+    if os.environ.get("WHALE_BENCH_EXCHANGE", "peer") != "peer":
+        ok = 0
+    else:
+        try:
+            h = L.peer_export(dh, rank, world)
+        except Exception:
+            ok = 0
+    t = torch.tensor(list(h), dtype=torch.uint8, device="cuda")
+    allh = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(allh, t)
+    if ok:
+        try:
+            for q in range(world):
+                if q != rank:
+                    L.peer_import(dh, q, bytes(allh[q].cpu().tolist()))
+        except Exception as exc:
+            print(f"[bench] rank {rank}: peer import failed ({exc}); NCCL all-reduce instead", file=sys.stderr)
+            ok = 0
+    f = torch.tensor([ok], device="cuda", dtype=torch.int32)
+    dist.all_reduce(f, op=dist.ReduceOp.MIN)
+    return bool(int(f.item()))
+
+
 def c3_leg(args, L, wlib, rank, world, d3, n3, gen3_s, flush, stream):
     """BASELINE.json configs[2] (the north star's scaling configuration): `--c3-families` families in total, branch-wise
     rates (P = 37), strong scaling over the ranks, one MLE gradient step = reverse-mode evaluation of the rank's shard +
@@ -205,10 +237,12 @@ def c3_leg(args, L, wlib, rank, world, d3, n3, gen3_s, flush, stream):
     X = torch.tensor(xs, device="cuda", dtype=torch.float64)
     OUT = torch.zeros(1 + P, device="cuda", dtype=torch.float64)
     cond = 1
+    peer = setup_exchange(L, dh, rank, world)
+    PS = wlib.PEER_SUM if peer else 0
 
     def step(i, flags):
-        L.logpdf_grad_async(mh, dh, X[i].data_ptr(), cond, flags, OUT.data_ptr(), stream)
-        if world > 1:
+        L.logpdf_grad_async(mh, dh, X[i].data_ptr(), cond, flags | PS, OUT.data_ptr(), stream)
+        if world > 1 and not peer:
             dist.all_reduce(OUT)
 
     for i in range(Wm):
@@ -237,8 +271,9 @@ def c3_leg(args, L, wlib, rank, world, d3, n3, gen3_s, flush, stream):
             return L.logpdf_grad(mh, dh, xs[i], model.p_leaf(), cond, want_grad=True)[0]
         pin_x.copy_(torch.from_numpy(xs[i]))
         Xd.copy_(pin_x, non_blocking=True)
-        L.logpdf_grad_async(mh, dh, Xd.data_ptr(), cond, wlib.WANT_GRAD, OUT.data_ptr(), stream)
-        dist.all_reduce(OUT)
+        L.logpdf_grad_async(mh, dh, Xd.data_ptr(), cond, wlib.WANT_GRAD | PS, OUT.data_ptr(), stream)
+        if not peer:
+            dist.all_reduce(OUT)
         pin_o.copy_(OUT, non_blocking=True)
         torch.cuda.synchronize()
         return float(pin_o[0])
@@ -271,6 +306,7 @@ def c3_leg(args, L, wlib, rank, world, d3, n3, gen3_s, flush, stream):
     return {"workload": f"C3: {fam_total} synthetic families in total (strong scaling, {n3} on rank 0), 9-taxon tree + 2 WGD, "
                         f"DLWGD branch-wise rates P={P}, dt={DT}, RootCondition, new theta each step",
             "families_total": fam_total, "P": P, "grad_mode": mode, "gradient_passes": passes, "steps": K, "warmup": Wm,
+            "exchange": ("peer-memory one-shot sum (k_peer_sum)" if peer else "NCCL all-reduce") if world > 1 else "none",
             "value": fam_total * K / (total_ms * 1e-3), "unit": UNIT, "ms_per_step": total_ms / K, "scaling": "strong",
             "e2e": {"value": fam_total * K / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / K,
                     "h2d_bytes_per_step": 8 * (P + model.nn), "d2h_bytes_per_step": 8 * (1 + P)},
@@ -336,11 +372,13 @@ def main():
     OUT = torch.zeros(1 + P, device="cuda", dtype=torch.float64)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     stream = torch.cuda.current_stream().cuda_stream
-    FLAGS = wlib.WANT_GRAD | wlib.PROFILE
+    peer = setup_exchange(L, dh, rank, world)
+    PS = wlib.PEER_SUM if peer else 0
+    FLAGS = wlib.WANT_GRAD | wlib.PROFILE | PS
 
     def step(i, flags=FLAGS):
         L.logpdf_grad_async(mh, dh, X[i].data_ptr(), cond, flags, OUT.data_ptr(), stream)
-        if world > 1:
+        if world > 1 and not peer:
             dist.all_reduce(OUT)
 
     for i in range(Wm):
@@ -376,7 +414,7 @@ def main():
     # (rank-local work only: the number of rounds differs between ranks, so no collective may be issued here)
     t_probe = time.perf_counter()
     while len(sampler.rows) < 8 and time.perf_counter() - t_probe < 3.0:
-        for i in range(Wm):
+        for i in range(Wm):  # (no exchange here: the number of rounds differs between ranks)
             L.logpdf_grad_async(mh, dh, X[i].data_ptr(), cond, wlib.WANT_GRAD, OUT.data_ptr(), stream)
         torch.cuda.synchronize()
     clocks = sampler.stop()
@@ -396,8 +434,9 @@ def main():
             return L.logpdf_grad(mh, dh, xs[i], model.p_leaf(), cond, want_grad=True)[0]
         pin_x.copy_(torch.from_numpy(xs[i]))
         Xd.copy_(pin_x, non_blocking=True)
-        L.logpdf_grad_async(mh, dh, Xd.data_ptr(), cond, wlib.WANT_GRAD, OUT.data_ptr(), stream)
-        dist.all_reduce(OUT)
+        L.logpdf_grad_async(mh, dh, Xd.data_ptr(), cond, wlib.WANT_GRAD | PS, OUT.data_ptr(), stream)
+        if not peer:
+            dist.all_reduce(OUT)
         pin_o.copy_(OUT, non_blocking=True)
         torch.cuda.synchronize()
         return float(pin_o[0])
@@ -461,7 +500,10 @@ def main():
         "config": {"workload": f"C2: {F} synthetic families/GPU x ~200 clades (median), 9-taxon tree + 2 WGD "
                                f"(19 nodes, {int(model.n_slices.sum())} slices), ConstantDLWGD P={P}, dt={DT}, "
                                f"RootCondition, new theta each step",
-                   "families_total": F * world, "sharding": f"families/{world} ranks, all-reduce of {1 + P} f64",
+                   "families_total": F * world,
+                   "sharding": f"families/{world} ranks, sum of {1 + P} f64 per step: " +
+                               ("peer-memory one-shot exchange in the library (k_peer_sum over CUDA IPC / NVLink)" if peer
+                                else "NCCL all-reduce" if world > 1 else "single rank"),
                    "l2": "flushed between steps (256 MiB memset outside the timed events)",
                    "arena_bytes_per_gpu": int(arena_bytes), "gen_s": round(gen_s, 1), "pack_s": round(pack_s, 2)},
         "clocks": clocks,

@@ -53,6 +53,7 @@ extern "C" {
 #define WHALE_WANT_GRAD 1u  /* also return d loglik / d raw parameter                          */
 #define WHALE_KEEP_ELL 2u   /* logpdf! semantics: keep the full ℓ on the device (src/core.jl:29) */
 #define WHALE_PROFILE 4u    /* record CUDA events around each kernel (see whale_last_kernel_ms)   */
+#define WHALE_PEER_SUM 8u   /* one process per GPU: return the sum over all ranks (see whale_peer_export) */
 
 typedef struct whale_model* whale_model_t;
 typedef struct whale_data* whale_data_t;
@@ -109,6 +110,36 @@ int32_t whale_last_error(char* buf, size_t n);
 /* number of usable CUDA devices (0 when none); selects the device used by subsequent *_create calls */
 int32_t whale_device_count(void);
 int32_t whale_set_device(int32_t device);
+
+/*
+ * Several GPUs behind one handle (whale_set_devices(n, ids[])).  Families are i.i.d. terms of a sum
+ * (src/core.jl:54,63; the reference's parallel axis is Threads.@threads over families, :58-64): whale_multi_create packs
+ * the model on every listed device and shards the families over them by predicted work (longest processing time first);
+ * whale_multi_logpdf_grad evaluates all shards concurrently and adds the per-device (loglik, grad) in device-list order,
+ * so the result is bit-reproducible.  ll_fam (nullable, [n_fam]) is indexed by the ORIGINAL family order.  A device may be
+ * listed more than once (two shards on one GPU).  Without whale_set_devices the current device (whale_set_device) is used.
+ */
+typedef struct whale_multi* whale_multi_t;
+int32_t whale_set_devices(int32_t n, const int32_t* ids);
+int32_t whale_multi_create(const whale_model_desc* model, const whale_ccd_desc* data, whale_multi_t* out);
+int32_t whale_multi_destroy(whale_multi_t h);
+int32_t whale_multi_ndev(whale_multi_t h);
+int32_t whale_multi_shard_size(whale_multi_t h, int32_t i);
+int32_t whale_multi_logpdf_grad(whale_multi_t h, const double* x, const double* p_leaf, int32_t condition, uint32_t flags,
+                                double* loglik, double* grad, double* ll_fam);
+
+/*
+ * One process per GPU (torch.distributed / MPI style drivers; families sharded over the ranks like Threads.@threads shards
+ * them over threads, src/core.jl:58-64): the sum of the ranks' (loglik, grad) WITHOUT a collective library.  Each rank
+ * calls whale_peer_export (allocates its exchange buffer, returns a 64-byte CUDA IPC handle), the driver all-gathers the
+ * handles by any means, every rank calls whale_peer_import for every other rank.  From then on an evaluation with
+ * WHALE_PEER_SUM ends with a one-CTA kernel that stores the rank's 1+P doubles into every peer's buffer through NVLink
+ * peer memory and adds the world's contributions in rank order: every rank gets the same bits.  Like a collective, all
+ * ranks must issue the same sequence of WHALE_PEER_SUM evaluations.  At most 16 ranks.
+ */
+int32_t whale_peer_export(whale_data_t d, int32_t rank, int32_t world, void* handle64);
+int32_t whale_peer_import(whale_data_t d, int32_t peer, const void* handle64);
+int32_t whale_peer_ready(whale_data_t d);
 
 int32_t whale_model_create(const whale_model_desc* desc, whale_model_t* out);
 int32_t whale_model_destroy(whale_model_t m);

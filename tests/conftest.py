@@ -289,3 +289,28 @@ def backtrack_uses_kept_parameters(L):
         L.L.whale_data_destroy(dh)
         L.L.whale_data_destroy(dh2)
         L.L.whale_model_destroy(mh)
+
+
+def multi_device_vs_golden(L, devices):
+    """whale_set_devices + whale_multi_*: the families of the C1 fixture sharded over `devices` (a device may be listed
+    twice) give the full-batch golden log-likelihood, gradient and per-family values; two evaluations give identical
+    bits (fixed summation order)."""
+    g = load_golden("c1_example1")
+    fl = golden_fams(g)
+    h = L.multi_create(golden_model(g), fl, devices)
+    try:
+        assert L.L.whale_multi_ndev(h) == len(devices)
+        assert sum(L.L.whale_multi_shard_size(h, i) for i in range(len(devices))) == fl["n_fam"]
+        for kind in ("root", "none"):
+            for xi, x in enumerate(g["xs"]):
+                ll, grad, lf = L.multi_logpdf_grad(h, x, g["m_pleaf"], COND[kind], fl["n_fam"], want_grad=True, per_family=True)
+                assert ll == pytest.approx(g[f"tot_{kind}"][xi], rel=1e-9)
+                wg = g[f"grad_{kind}"][xi]
+                np.testing.assert_allclose(grad, wg, rtol=1e-9, atol=1e-9 * np.abs(wg).max())
+                np.testing.assert_allclose(lf, g["ll_fam"][xi], rtol=1e-9)
+                ll2, grad2, _ = L.multi_logpdf_grad(h, x, g["m_pleaf"], COND[kind], fl["n_fam"], want_grad=True)
+                assert ll2 == ll and np.array_equal(grad2, grad)
+    finally:
+        L.L.whale_multi_destroy(h)
+        ids = np.zeros(0, np.int32)
+        L.L.whale_set_devices(0, None)

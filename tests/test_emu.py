@@ -356,3 +356,44 @@ def test_emu_even_row_stride_variant(tmp_path):
 def test_emu_backtrack_uses_kept_parameters(L):
     from conftest import backtrack_uses_kept_parameters
     backtrack_uses_kept_parameters(L)
+
+
+def test_emu_multi_device_handle(L):
+    from conftest import multi_device_vs_golden
+    multi_device_vs_golden(L, [0, 0, 0])
+
+
+def test_emu_peer_sum_two_ranks_in_one_process(L):
+    """whale_peer_export / whale_peer_import / WHALE_PEER_SUM: two "ranks" (two data handles holding the two halves of the
+    C1 families) exchange through each other's buffers; evaluated back to back each ends with the total of both — the
+    full-batch golden value.  (In the emulation the exchange kernel does not wait for the peer's flag: rank 0's first
+    total is incomplete by construction, so rank 0 is evaluated again after rank 1 has published.)"""
+    g = load_golden("c1_example1")
+    mh = L.model_create(golden_model(g))
+    halves = [list(range(0, 6)), list(range(6, 12))]
+    dhs = [L.data_create(mh, golden_fams(g, h)) for h in halves]
+    hnd = [L.peer_export(dhs[r], r, 2) for r in range(2)]
+    for r in range(2):
+        L.peer_import(dhs[r], 1 - r, hnd[1 - r])
+        assert L.L.whale_peer_ready(dhs[r]) == 1
+    x = g["xs"][1]
+    P = len(x)
+    import ctypes as C
+    f64p = C.POINTER(C.c_double)
+
+    def ev(r, flags):
+        ll = C.c_double()
+        grad = np.zeros(P)
+        xx = np.ascontiguousarray(x)
+        pl = np.ascontiguousarray(g["m_pleaf"])
+        L.check(L.L.whale_logpdf_grad(mh, dhs[r], xx.ctypes.data_as(f64p), pl.ctypes.data_as(f64p), 1, flags, C.byref(ll),
+                                      grad.ctypes.data_as(f64p), None, None))
+        return ll.value, grad
+
+    ev(0, wlib.WANT_GRAD | wlib.PEER_SUM)              # step 1, rank 0 publishes (its own total is still partial)
+    ll1, g1 = ev(1, wlib.WANT_GRAD | wlib.PEER_SUM)    # step 1, rank 1: sees both contributions
+    assert ll1 == pytest.approx(g["tot_root"][1], rel=1e-9)
+    np.testing.assert_allclose(g1, g["grad_root"][1], rtol=1e-9, atol=1e-9 * np.abs(g["grad_root"][1]).max())
+    for dh in dhs:
+        L.L.whale_data_destroy(dh)
+    L.L.whale_model_destroy(mh)

@@ -273,3 +273,11 @@ def test_reverse_mode_one_persistent_cta(L, monkeypatch):
 def test_backtrack_uses_kept_parameters(L):
     from conftest import backtrack_uses_kept_parameters
     backtrack_uses_kept_parameters(L)
+
+
+def test_multi_device_handle(L):
+    """whale_set_devices(n, ids[]) + one handle sharded over the devices (all GPUs of the box; on a one-GPU
+    box two shards on device 0) against the full-batch golden values."""
+    from conftest import multi_device_vs_golden
+    n = L.L.whale_device_count()
+    multi_device_vs_golden(L, list(range(n)) if n > 1 else [0, 0])

@@ -241,6 +241,12 @@ struct whale_data {
     double* d_hist = nullptr;
     size_t hist_stride = 0;
     unsigned int* d_next = nullptr;
+    // peer-memory exchange (one process per GPU): own buffer, the peers' buffers as mapped here, step counter
+    int peer_rank = -1, peer_world = 0;
+    double* peer_bufs[16] = {};
+    bool peer_open[16] = {};
+    int* d_peer_status = nullptr;
+    unsigned long long peer_seq = 0;
 };
 
 // `subset`: which raw parameters this plan differentiates (empty = none: the value-only plan)
@@ -675,6 +681,7 @@ static size_t set_budgets(whale_data* D, int g, const Plan& pl) {
 
 static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, int32_t condition, uint32_t flags,
                             double* d_out, cudaStream_t st);
+static int32_t enqueue_peer_sum(whale_data* D, double* d_out, cudaStream_t st);
 static int32_t finalize_data(whale_model* m, whale_data* D, whale_data_t* out);
 
 // Launch order of plan g's families for a given per-family work vector (predicted flops at pack time, measured SM
@@ -1511,6 +1518,11 @@ int32_t whale_data_destroy(whale_data_t d) {
     for (int g = 0; g < MAXPLAN; g++) { cudaFree(d->d_perm[g]); cudaFree(d->d_roff[g]); }
     for (Plan& cp : d->chunk_plans) for (void* q : cp.owned) cudaFree(q);
     cudaFree(d->d_out_fam); cudaFree(d->d_partial); cudaFree(d->d_done);
+#ifndef WHALE_EMU
+    for (int q = 0; q < 16; q++) if (d->peer_open[q] && d->peer_bufs[q]) cudaIpcCloseMemHandle(d->peer_bufs[q]);
+#endif
+    if (d->peer_rank >= 0) cudaFree(d->peer_bufs[d->peer_rank]);
+    cudaFree(d->d_peer_status);
     cudaFree(d->d_rarena); cudaFree(d->d_rhdr); cudaFree(d->d_aoff); cudaFree(d->d_hist); cudaFree(d->d_next);
     for (int i = 0; i < MAX_BINS; i++) {
         if (d->side[i]) cudaStreamDestroy(d->side[i]);
@@ -1724,7 +1736,9 @@ int32_t whale_logpdf_grad_async(whale_model_t m, whale_data_t d, const double* d
     if (!m || !d || !d_x || !d_out) return fail(WHALE_ERR_ARG, "null argument");
     if (d->m != m) return fail(WHALE_ERR_ARG, "data handle belongs to another model");
     CU(cudaSetDevice(m->device));
-    return enqueue_eval(m, d, d_x, condition, flags, d_out, (cudaStream_t)stream);
+    int32_t rc = enqueue_eval(m, d, d_x, condition, flags, d_out, (cudaStream_t)stream);
+    if (rc == WHALE_OK && (flags & WHALE_PEER_SUM)) rc = enqueue_peer_sum(d, d_out, (cudaStream_t)stream);
+    return rc;
 }
 
 int32_t whale_logpdf_grad(whale_model_t m, whale_data_t d, const double* x, const double* p_leaf, int32_t condition,
@@ -1743,7 +1757,7 @@ int32_t whale_logpdf_grad(whale_model_t m, whale_data_t d, const double* x, cons
     // what separates the end-to-end rate from the device-timed rate for small batches.
     bool done = false;
 #ifndef WHALE_EMU
-    if (!(flags & WHALE_PROFILE) && graphs_enabled()) {
+    if (!(flags & (WHALE_PROFILE | WHALE_PEER_SUM)) && graphs_enabled()) {
         const uint32_t key = (flags & (WHALE_WANT_GRAD | WHALE_KEEP_ELL)) | ((uint32_t)condition << 8);
         GraphSlot* gs = nullptr;
         for (auto& g : d->graphs) if (g.key == key) gs = &g;
@@ -1788,6 +1802,10 @@ int32_t whale_logpdf_grad(whale_model_t m, whale_data_t d, const double* x, cons
         CU(cudaMemcpyAsync(m->d_pleaf, hp + P, nn * sizeof(double), cudaMemcpyHostToDevice, m->stream));
         int32_t rc = enqueue_eval(m, d, m->d_x, condition, flags, m->d_out, m->stream);
         if (rc != WHALE_OK) return rc;
+        if (flags & WHALE_PEER_SUM) {  // one process per GPU: the world's total comes back, on every rank
+            rc = enqueue_peer_sum(d, m->d_out, m->stream);
+            if (rc != WHALE_OK) return rc;
+        }
         CU(cudaMemcpyAsync(ho, m->d_out, (1 + P) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
         CU(cudaStreamSynchronize(m->stream));
     }
@@ -2121,6 +2139,228 @@ int32_t whale_last_tables_cycles(whale_model_t m, int32_t with_grad, double* out
     long long h[32];
     CU(cudaMemcpy(h, m->plan[with_grad ? 1 : 0].dev.tim, sizeof(h), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 32; i++) out32[i] = (double)h[i];
+    return WHALE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Several GPUs behind ONE handle: whale_set_devices picks the devices; whale_multi_create packs the
+// model once per device and shards the families over them by predicted work (longest processing time first); an
+// evaluation enqueues [θ H2D -> tables -> DP -> reduction -> result D2H] on every device's own stream, waits for all of
+// them and adds the per-device results in device-list order (fixed order: deterministic bits).  The host needs the
+// 1+P doubles anyway, so the exchange is n pinned D2H copies in flight together — no device-side collective.
+// (One process per GPU instead — the benchmark's layout — exchanges through peer memory: whale_peer_* below.)
+// ------------------------------------------------------------------------------------------------
+static std::vector<int> g_devices;
+
+struct whale_multi {
+    std::vector<whale_model*> models;
+    std::vector<whale_data*> datas;
+    std::vector<std::vector<int>> fams;  // original family indices of every shard
+    int F = 0, P = 0;
+};
+
+int32_t whale_set_devices(int32_t n, const int32_t* ids) {
+    if (n < 0 || (n > 0 && !ids)) return fail(WHALE_ERR_ARG, "bad device list");
+    const int have = whale_device_count();
+    for (int i = 0; i < n; i++)
+        if (ids[i] < 0 || ids[i] >= have) return fail(WHALE_ERR_ARG, "device %d not available (%d devices)", ids[i], have);
+    g_devices.assign(ids, ids + n);
+    return WHALE_OK;
+}
+
+int32_t whale_multi_destroy(whale_multi_t h) {
+    if (!h) return WHALE_OK;
+    for (whale_data* d : h->datas) whale_data_destroy(d);
+    for (whale_model* m : h->models) whale_model_destroy(m);
+    delete h;
+    return WHALE_OK;
+}
+
+int32_t whale_multi_create(const whale_model_desc* md, const whale_ccd_desc* cd, whale_multi_t* out) {
+    if (!md || !cd || !out) return fail(WHALE_ERR_ARG, "null argument");
+    std::vector<int> devs = g_devices;
+    if (devs.empty()) devs.push_back(g_device);
+    const int nd = (int)devs.size(), F = cd->n_fam, nn = md->n_nodes;
+    if (F < nd) return fail(WHALE_ERR_ARG, "%d families for %d devices", F, nd);
+    // LPT on a pack-independent work proxy: triples + clades of the family
+    std::vector<double> w(F);
+    for (int f = 0; f < F; f++) {
+        const int64_t c0 = cd->clade_off[f], c1 = cd->clade_off[f + 1];
+        w[f] = (double)(cd->split_off[c1] - cd->split_off[c0]) + (double)(c1 - c0);
+    }
+    std::vector<int> order(F);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return w[a] > w[b]; });
+    auto* H = new whale_multi();
+    H->F = F; H->P = md->n_params;
+    H->fams.assign(nd, {});
+    std::vector<double> load(nd, 0.0);
+    for (int f : order) {
+        int best = 0;
+        for (int i = 1; i < nd; i++) if (load[i] < load[best]) best = i;
+        H->fams[best].push_back(f);
+        load[best] += w[f];
+    }
+    const int saved = g_device;
+    for (int i = 0; i < nd; i++) {
+        std::sort(H->fams[i].begin(), H->fams[i].end());  // family order inside a shard = original order
+        // the shard's CSR arrays
+        std::vector<int64_t> clade_off(1, 0), split_off(1, 0), compat_off(1, 0);
+        std::vector<int32_t> nleaf, g1, g2, compat;
+        std::vector<double> p;
+        for (int f : H->fams[i]) {
+            const int64_t c0 = cd->clade_off[f], c1 = cd->clade_off[f + 1];
+            const int64_t s0 = cd->split_off[c0], s1 = cd->split_off[c1];
+            const int64_t sb = (int64_t)g1.size();
+            for (int64_t c = c0; c < c1; c++) { nleaf.push_back(cd->clade_nleaf[c]); split_off.push_back(sb + cd->split_off[c + 1] - s0); }
+            g1.insert(g1.end(), cd->g1 + s0, cd->g1 + s1);
+            g2.insert(g2.end(), cd->g2 + s0, cd->g2 + s1);
+            p.insert(p.end(), cd->p + s0, cd->p + s1);
+            clade_off.push_back(clade_off.back() + (c1 - c0));
+            const int64_t k0 = cd->compat_off[(int64_t)f * nn], cb = (int64_t)compat.size();
+            for (int e = 0; e < nn; e++) compat_off.push_back(cb + cd->compat_off[(int64_t)f * nn + e + 1] - k0);
+            compat.insert(compat.end(), cd->compat + k0, cd->compat + cd->compat_off[(int64_t)(f + 1) * nn]);
+        }
+        whale_ccd_desc sd{(int32_t)H->fams[i].size(), clade_off.data(), nleaf.data(), split_off.data(), g1.data(), g2.data(),
+                          p.data(), compat_off.data(), compat.data()};
+        whale_model* m = nullptr;
+        whale_data* d = nullptr;
+        int32_t rc = whale_set_device(devs[i]);
+        if (rc == WHALE_OK) rc = whale_model_create(md, &m);
+        if (rc == WHALE_OK) { H->models.push_back(m); rc = whale_data_create(m, &sd, &d); }
+        if (rc == WHALE_OK) H->datas.push_back(d);
+        if (rc != WHALE_OK) { whale_multi_destroy(H); whale_set_device(saved); return rc; }
+    }
+    whale_set_device(saved);
+    *out = H;
+    return WHALE_OK;
+}
+
+int32_t whale_multi_ndev(whale_multi_t h) { return h ? (int32_t)h->models.size() : 0; }
+int32_t whale_multi_shard_size(whale_multi_t h, int32_t i) {
+    return (h && i >= 0 && i < (int)h->fams.size()) ? (int32_t)h->fams[i].size() : -1;
+}
+
+int32_t whale_multi_logpdf_grad(whale_multi_t h, const double* x, const double* p_leaf, int32_t condition, uint32_t flags,
+                                double* loglik, double* grad, double* ll_fam) {
+    if (!h || !x || !loglik) return fail(WHALE_ERR_ARG, "null argument");
+    if (grad && !(flags & WHALE_WANT_GRAD)) return fail(WHALE_ERR_ARG, "grad requested without WHALE_WANT_GRAD");
+    if (flags & (WHALE_KEEP_ELL | WHALE_PROFILE)) return fail(WHALE_ERR_ARG, "keep_ell / profile: use the per-device handles");
+    const int nd = (int)h->models.size(), P = h->P;
+    // enqueue everything on every device before waiting for any
+    for (int i = 0; i < nd; i++) {
+        whale_model* m = h->models[i];
+        const int nn = m->nn;
+        CU(cudaSetDevice(m->device));
+        double* hp = m->h_pin;
+        memcpy(hp, x, P * sizeof(double));
+        for (int e = 0; e < nn; e++) hp[P + e] = p_leaf ? p_leaf[e] : 0.0;
+        CU(cudaMemcpyAsync(m->d_x, hp, P * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+        CU(cudaMemcpyAsync(m->d_pleaf, hp + P, nn * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+        int32_t rc = enqueue_eval(m, h->datas[i], m->d_x, condition, flags, m->d_out, m->stream);
+        if (rc != WHALE_OK) return rc;
+        CU(cudaMemcpyAsync(hp + P + nn, m->d_out, (1 + P) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    }
+    double tot = 0.0;
+    bool finite = true;
+    if (grad) for (int k = 0; k < P; k++) grad[k] = 0.0;
+    for (int i = 0; i < nd; i++) {  // fixed order: device-list order
+        whale_model* m = h->models[i];
+        CU(cudaSetDevice(m->device));
+        CU(cudaStreamSynchronize(m->stream));
+        m->x_host_valid = true;
+        const double* ho = m->h_pin + P + m->nn;
+        finite = finite && std::isfinite(ho[0]);
+        tot += ho[0];
+        if (grad) for (int k = 0; k < P; k++) grad[k] += ho[1 + k];
+    }
+    finite = finite && std::isfinite(tot);  // ℓhood src/core.jl:15 on the total
+    *loglik = finite ? tot : -INFINITY;
+    if (grad && !finite) for (int k = 0; k < P; k++) grad[k] = 0.0;
+    if (ll_fam) {
+        const bool g_ = (flags & WHALE_WANT_GRAD) != 0;
+        for (int i = 0; i < nd; i++) {
+            whale_data* d = h->datas[i];
+            whale_model* m = h->models[i];
+            CU(cudaSetDevice(m->device));
+            const size_t g = g_ ? 1 : 0;
+            const int KR = d->plans[g]->K[m->root];
+            std::vector<double> tmp((size_t)d->F * KR);
+            CU(cudaMemcpy(tmp.data(), d->d_out_fam + d->out_off[g], tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            for (int f = 0; f < d->F; f++) ll_fam[h->fams[i][f]] = tmp[(size_t)f * KR];
+        }
+    }
+    return WHALE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One process per GPU: the sum over ranks through peer memory (see k_peer_sum in whale_reduce.cuh).
+// ------------------------------------------------------------------------------------------------
+int32_t whale_peer_export(whale_data_t d, int32_t rank, int32_t world, void* handle64) {
+    if (!d || !handle64) return fail(WHALE_ERR_ARG, "null argument");
+    if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail(WHALE_ERR_ARG, "rank %d of %d (at most 16 ranks)", rank, world);
+    whale_model* m = d->m;
+    CU(cudaSetDevice(m->device));
+    const size_t n = 1 + (size_t)m->P;
+    const size_t bytes = (2 * (size_t)world * n) * sizeof(double) + 2 * (size_t)world * sizeof(unsigned long long);
+    if (!d->peer_bufs[rank] || d->peer_world != world || d->peer_rank != rank) {
+        if (d->peer_rank >= 0 && d->peer_bufs[d->peer_rank]) cudaFree(d->peer_bufs[d->peer_rank]);
+        memset(d->peer_bufs, 0, sizeof(d->peer_bufs));
+        memset(d->peer_open, 0, sizeof(d->peer_open));
+        CU(cudaMalloc((void**)&d->peer_bufs[rank], bytes));
+        CU(cudaMemset(d->peer_bufs[rank], 0, bytes));
+        if (!d->d_peer_status) { CU(cudaMalloc((void**)&d->d_peer_status, sizeof(int))); CU(cudaMemset(d->d_peer_status, 0, sizeof(int))); }
+        d->peer_rank = rank; d->peer_world = world; d->peer_seq = 0;
+    }
+#ifndef WHALE_EMU
+    cudaIpcMemHandle_t hnd;
+    CU(cudaIpcGetMemHandle(&hnd, d->peer_bufs[rank]));
+    static_assert(sizeof(hnd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &hnd, 64);
+#else
+    memset(handle64, 0, 64);
+    memcpy(handle64, &d->peer_bufs[rank], sizeof(void*));
+#endif
+    return WHALE_OK;
+}
+
+int32_t whale_peer_import(whale_data_t d, int32_t peer, const void* handle64) {
+    if (!d || !handle64) return fail(WHALE_ERR_ARG, "null argument");
+    if (d->peer_rank < 0) return fail(WHALE_ERR_STATE, "whale_peer_export first");
+    if (peer < 0 || peer >= d->peer_world) return fail(WHALE_ERR_ARG, "peer %d of %d", peer, d->peer_world);
+    if (peer == d->peer_rank) return WHALE_OK;
+    CU(cudaSetDevice(d->m->device));
+#ifndef WHALE_EMU
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, handle64, 64);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+    d->peer_bufs[peer] = (double*)p;
+    d->peer_open[peer] = true;
+#else
+    memcpy(&d->peer_bufs[peer], handle64, sizeof(void*));
+#endif
+    return WHALE_OK;
+}
+
+int32_t whale_peer_ready(whale_data_t d) {
+    if (!d || d->peer_rank < 0) return 0;
+    for (int q = 0; q < d->peer_world; q++) if (!d->peer_bufs[q]) return 0;
+    return 1;
+}
+
+// enqueue the exchange behind an evaluation that left its local (1+P) result in d_out
+static int32_t enqueue_peer_sum(whale_data* D, double* d_out, cudaStream_t st) {
+    if (!whale_peer_ready(D)) return fail(WHALE_ERR_STATE, "WHALE_PEER_SUM without a complete whale_peer_export / whale_peer_import exchange");
+    PeerArgs a{};
+    for (int q = 0; q < D->peer_world; q++) a.bufs[q] = D->peer_bufs[q];
+    a.rank = D->peer_rank; a.world = D->peer_world; a.n = 1 + D->m->P;
+    a.seq = ++D->peer_seq;
+    a.out = d_out;
+    a.status = D->d_peer_status;
+    LAUNCH(k_peer_sum, 1, 128, 0, st, a);
+    g_launches++;
+    CU(cudaGetLastError());
     return WHALE_OK;
 }
 

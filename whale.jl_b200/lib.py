@@ -15,14 +15,17 @@ LIB_PATH = os.path.join(_HERE, "libwhalecuda.so")
 
 i32p, i64p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double)
 
-WANT_GRAD, KEEP_ELL, PROFILE = 1, 2, 4
+WANT_GRAD, KEEP_ELL, PROFILE, PEER_SUM = 1, 2, 4, 8
 
 # every symbol include/whalecuda.h declares (tests check the built library exports all of them)
 SYMBOLS = ["whale_version", "whale_last_error", "whale_device_count", "whale_set_device", "whale_model_create",
            "whale_model_destroy", "whale_data_create", "whale_read_ale", "whale_data_destroy", "whale_data_nfam",
            "whale_data_arena_bytes", "whale_data_arena_dump", "whale_data_save", "whale_data_load", "whale_logpdf_grad", "whale_logpdf_grad_async", "whale_mixture_logpdf_grad",
            "whale_slices", "whale_ell_size", "whale_ell_get", "whale_backtrack", "whale_track", "whale_launch_count",
-           "whale_work_estimate", "whale_last_kernel_ms", "whale_last_phase_cycles", "whale_last_node_cycles", "whale_last_family_cycles", "whale_last_tables_cycles", "whale_last_backtrack_ms", "whale_fp64_peak"]
+           "whale_work_estimate", "whale_last_kernel_ms", "whale_last_phase_cycles", "whale_last_node_cycles", "whale_last_family_cycles", "whale_last_tables_cycles", "whale_last_backtrack_ms", "whale_fp64_peak",
+           "whale_data_grad_mode", "whale_data_grad_passes", "whale_set_devices", "whale_multi_create", "whale_multi_destroy",
+           "whale_multi_ndev", "whale_multi_shard_size", "whale_multi_logpdf_grad", "whale_peer_export", "whale_peer_import",
+           "whale_peer_ready"]
 
 
 class ModelDesc(C.Structure):
@@ -98,6 +101,15 @@ class Lib:
         L.whale_last_node_cycles.argtypes = [vp, f64p, f64p, C.c_int32]
         L.whale_last_family_cycles.argtypes = [vp, f64p]
         L.whale_last_backtrack_ms.argtypes = [vp, f64p]
+        L.whale_peer_export.argtypes = [vp, C.c_int32, C.c_int32, vp]
+        L.whale_peer_import.argtypes = [vp, C.c_int32, vp]
+        L.whale_peer_ready.argtypes = [vp]
+        L.whale_set_devices.argtypes = [C.c_int32, i32p]
+        L.whale_multi_create.argtypes = [C.POINTER(ModelDesc), C.POINTER(CCDDesc), C.POINTER(vp)]
+        L.whale_multi_destroy.argtypes = [vp]
+        L.whale_multi_ndev.argtypes = [vp]
+        L.whale_multi_shard_size.argtypes = [vp, C.c_int32]
+        L.whale_multi_logpdf_grad.argtypes = [vp, f64p, f64p, C.c_int32, C.c_uint32, f64p, f64p, f64p]
 
     def check(self, rc):
         if rc != 0:
@@ -116,6 +128,47 @@ class Lib:
         h = C.c_void_p()
         self.check(self.L.whale_model_create(C.byref(d), C.byref(h)))
         return h.value
+
+    def _model_desc(self, m):
+        keep = [np.ascontiguousarray(a) for a in
+                (m.order, m.child0, m.child1, m.kind, m.n_slices, m.slice_dt, m.leafP, m.lam_slot, m.mu_slot,
+                 m.q_slot)]
+        d = ModelDesc(m.nn, _ptr(keep[0], i32p), _ptr(keep[1], i32p), _ptr(keep[2], i32p), _ptr(keep[3], i32p),
+                      _ptr(keep[4], i32p), _ptr(keep[5], f64p), _ptr(keep[6], f64p), m.n_params,
+                      _ptr(keep[7], i32p), _ptr(keep[8], i32p), _ptr(keep[9], i32p), m.eta_slot, m.log_scale)
+        return d, keep
+
+    def multi_create(self, m, flat: dict, devices) -> int:
+        """whale_set_devices + whale_multi_create: one handle over several GPUs (families sharded by predicted work)."""
+        ids = np.ascontiguousarray(devices, np.int32)
+        self.check(self.L.whale_set_devices(len(ids), _ptr(ids, i32p)))
+        md, keep = self._model_desc(m)
+        cd = CCDDesc(flat["n_fam"], _ptr(flat["clade_off"], i64p), _ptr(flat["clade_nleaf"], i32p),
+                     _ptr(flat["split_off"], i64p), _ptr(flat["g1"], i32p), _ptr(flat["g2"], i32p),
+                     _ptr(flat["p"], f64p), _ptr(flat["compat_off"], i64p), _ptr(flat["compat"], i32p))
+        h = C.c_void_p()
+        self.check(self.L.whale_multi_create(C.byref(md), C.byref(cd), C.byref(h)))
+        return h.value
+
+    def multi_logpdf_grad(self, h, x, p_leaf, condition, n_fam, want_grad=False, per_family=False):
+        x = np.ascontiguousarray(x, np.float64)
+        pl = np.ascontiguousarray(p_leaf, np.float64)
+        ll = C.c_double()
+        g = np.zeros(len(x)) if want_grad else None
+        lf = np.zeros(n_fam) if per_family else None
+        self.check(self.L.whale_multi_logpdf_grad(h, _ptr(x, f64p), _ptr(pl, f64p), condition, WANT_GRAD if want_grad else 0,
+                                                  C.byref(ll), _ptr(g, f64p) if want_grad else None,
+                                                  _ptr(lf, f64p) if per_family else None))
+        return ll.value, g, lf
+
+    def peer_export(self, dh, rank, world) -> bytes:
+        buf = C.create_string_buffer(64)
+        self.check(self.L.whale_peer_export(dh, rank, world, buf))
+        return buf.raw
+
+    def peer_import(self, dh, peer, handle: bytes):
+        buf = C.create_string_buffer(handle, 64)
+        self.check(self.L.whale_peer_import(dh, peer, buf))
 
     def data_create(self, mh: int, flat: dict) -> int:
         d = CCDDesc(flat["n_fam"], _ptr(flat["clade_off"], i64p), _ptr(flat["clade_nleaf"], i32p),
