@@ -122,6 +122,43 @@ class FlatModel:
         self.row_off = np.concatenate([[0], np.cumsum(self.nslices + 1)]).astype(np.int64)
 
 
+def model_from_arrays(g, condition="none"):
+    """A FlatModel from the flattened arrays of a golden fixture (tests/golden/*.npz: m_* keys) — lets the live C++ oracle
+    run where /root/reference is absent (the GPU box)."""
+    fm = FlatModel.__new__(FlatModel)
+    fm.nn = len(g["m_order"])
+    for k, src, dt in (("order", "m_order", np.int32), ("child0", "m_child0", np.int32), ("child1", "m_child1", np.int32),
+                       ("kind", "m_kind", np.int32), ("nslices", "m_nslices", np.int32), ("dt", "m_dt", np.float64),
+                       ("leafP", "m_leafP", np.float64), ("pleaf", "m_pleaf", np.float64), ("lam_slot", "m_lam_slot", np.int32),
+                       ("mu_slot", "m_mu_slot", np.int32), ("q_slot", "m_q_slot", np.int32)):
+        setattr(fm, k, np.ascontiguousarray(g[src], dt))
+    fm.P = int(g["m_P"])
+    fm.x = np.ascontiguousarray(g["xs"][0], np.float64)
+    fm.c = OModel(fm.nn, _p(fm.order, i32p), _p(fm.child0, i32p), _p(fm.child1, i32p), _p(fm.kind, i32p),
+                  _p(fm.nslices, i32p), _p(fm.dt, f64p), _p(fm.leafP, f64p), _p(fm.pleaf, f64p), _p(fm.lam_slot, i32p),
+                  _p(fm.mu_slot, i32p), _p(fm.q_slot, i32p), int(g["m_eta_slot"]), int(g["m_log_scale"]), COND[condition])
+    fm.row_off = np.concatenate([[0], np.cumsum(fm.nslices + 1)]).astype(np.int64)
+    return fm
+
+
+def fams_from_arrays(g):
+    """FlatFams from a golden fixture's f_* arrays."""
+    ff = FlatFams.__new__(FlatFams)
+    ff.nn = len(g["m_order"])
+    ff.F = len(g["f_clade_off"]) - 1
+    ff.clade_off = np.ascontiguousarray(g["f_clade_off"], np.int64)
+    ff.nleaf = np.ascontiguousarray(g["f_nleaf"], np.int32)
+    ff.split_off = np.ascontiguousarray(g["f_split_off"], np.int64)
+    ff.g1 = np.ascontiguousarray(g["f_g1"], np.int32)
+    ff.g2 = np.ascontiguousarray(g["f_g2"], np.int32)
+    ff.p = np.ascontiguousarray(g["f_p"], np.float64)
+    ff.compat_off = np.ascontiguousarray(g["f_compat_off"], np.int64)
+    ff.compat = np.ascontiguousarray(g["f_compat"], np.int32)
+    ff.c = OFams(ff.F, _p(ff.clade_off, i64p), _p(ff.nleaf, i32p), _p(ff.split_off, i64p), _p(ff.g1, i32p), _p(ff.g2, i32p),
+                 _p(ff.p, f64p), _p(ff.compat_off, i64p), _p(ff.compat, i32p))
+    return ff
+
+
 class FlatFams:
     """Reference-layout CCD arena: clades sorted by size, triples in file order (0-based ids)."""
 

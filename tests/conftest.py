@@ -314,3 +314,77 @@ def multi_device_vs_golden(L, devices):
         L.L.whale_multi_destroy(h)
         ids = np.zeros(0, np.int32)
         L.L.whale_set_devices(0, None)
+
+
+def arena_cache_round_trip(L, tmp_path, n_fam=5):
+    """whale_data_save / whale_data_load: a handle rebuilt from the binary arena cache holds the same arena bytes and
+    gives bit-identical results (both gradient modes are rebuilt from the cached forward arena); a cache is refused by a
+    model with another species tree or slicing; a truncated file, a flipped byte (content hash) and a file whose hash was
+    "repaired" after an offset inside a node record was bent (structural validation) are errors, not crashes or
+    out-of-bounds reads.  Returns (save seconds, load seconds, bytes)."""
+    import struct
+    import time
+    import whale_jl_b200 as W
+    from whale_jl_b200 import lib as wlib, synth
+    from whale_jl_b200.core import _data_handle
+    d = synth.generate(str(tmp_path / "cache"), n_fam, seed=17)
+    mk = lambda dt=0.05: W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), synth.c1_species_tree(), dt)
+    w = mk()
+    a = W.read_ale(d, w)
+    path = str(tmp_path / "c.arena")
+    t0 = time.perf_counter()
+    W.save_arena(a, w, path)
+    t_save = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    b = W.load_arena(path, w)
+    t_load = time.perf_counter() - t0
+    assert len(b) == len(a)
+    _, dha = _data_handle(w, a)
+    _, dhb = _data_handle(w, b)
+    assert np.array_equal(L.arena_dump(dha), L.arena_dump(dhb))
+    la, ga = W.logpdf_and_gradient(w, a)
+    lb, gb = W.logpdf_and_gradient(w, b)
+    assert la == lb and np.array_equal(ga, gb)
+    for mode in ("rev", "fwd"):
+        os.environ["WHALE_GRAD_MODE"] = mode
+        try:
+            w3 = mk()
+            l3, g3 = W.logpdf_and_gradient(w3, W.load_arena(path, w3))
+        finally:
+            del os.environ["WHALE_GRAD_MODE"]
+        assert l3 == pytest.approx(la, rel=1e-12)
+        np.testing.assert_allclose(g3, ga, rtol=1e-9, atol=1e-12)
+    # another slicing (Δt) -> another model structure -> refused
+    with pytest.raises(wlib.WhaleCudaError, match="another model"):
+        W.load_arena(path, mk(0.1))
+    raw = open(path, "rb").read()
+    nbytes = len(raw)
+    open(path, "wb").write(raw[:len(raw) // 2])
+    with pytest.raises(wlib.WhaleCudaError, match="truncated"):
+        W.load_arena(path, w)
+    # one flipped byte in the arena: content hash
+    HDR, FAMHDR = 80, 1320  # sizeof(CacheHdr), sizeof(FamHdr); the content hash is CacheHdr's last field
+    F = struct.unpack_from("<Q", raw, 24)[0]
+    arena_bytes = struct.unpack_from("<Q", raw, 32)[0]
+    assert F == n_fam
+    arena_at = HDR + F * FAMHDR
+    assert arena_at + arena_bytes < nbytes
+    bad = bytearray(raw)
+    bad[arena_at + arena_bytes // 2] ^= 0x40
+    open(path, "wb").write(bytes(bad))
+    with pytest.raises(wlib.WhaleCudaError, match="corrupted"):
+        W.load_arena(path, w)
+    # an entry-list offset of node 0 bent far outside the blob, hash recomputed: structural validation must refuse it
+    bad = bytearray(raw)
+    struct.pack_into("<I", bad, arena_at + 12, 0x0FFFFFF0)  # NodeRec[0].dent_off of family 0
+    h = 1469598103934665603
+    for byte in bytes(bad[HDR:arena_at + arena_bytes]):
+        h = ((h ^ byte) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    struct.pack_into("<Q", bad, HDR - 8, h)
+    open(path, "wb").write(bytes(bad))
+    with pytest.raises(wlib.WhaleCudaError, match="not a valid arena"):
+        W.load_arena(path, w)
+    open(path, "wb").write(b"not a cache")
+    with pytest.raises(wlib.WhaleCudaError, match="not a whalecuda arena cache"):
+        W.load_arena(path, w)
+    return t_save, t_load, nbytes

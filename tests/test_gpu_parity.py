@@ -55,6 +55,13 @@ def test_landplant_100_families(L):
     run_parity(L, "landplant100")
 
 
+def test_landplant_tutorial_discretisation(L):
+    """docs/src/tutorial.md:103-104,131 at the tutorial's own Δt = 0.01 (21 nodes, 3 765 slices — SURVEY §8d C1): 17 of the
+    100 landplant families incl. the smallest and the largest (1 025 clades)."""
+    g = run_parity(L, "landplant_dt0.01")
+    assert int(g["m_nslices"].sum()) == 3765
+
+
 def test_slices_tables(L):
     for name in ("c1_example1", "const_wgdturing"):
         g = load_golden(name)
@@ -252,7 +259,7 @@ def test_gradient_modes(L, tmp_path, monkeypatch, mode):
     assert L.L.whale_data_grad_mode(dh) == (1 if mode == "rev" else 0)
     L.L.whale_data_destroy(dh)
     L.L.whale_model_destroy(mh)
-    for name in ("c1_maxn5", "c1_example1", "const_wgdturing", "mul_tree", "landplant100", "ex5_dt0.01"):
+    for name in ("c1_maxn5", "c1_example1", "const_wgdturing", "mul_tree", "landplant100", "ex5_dt0.01", "landplant_dt0.01"):
         run_parity(L, name)
     from conftest import synthetic_c2_shape_vs_oracle, near_critical_vs_oracle, nowhere_condition_vs_oracle, mixture_vs_oracle
     synthetic_c2_shape_vs_oracle(tmp_path)
@@ -281,3 +288,11 @@ def test_multi_device_handle(L):
     from conftest import multi_device_vs_golden
     n = L.L.whale_device_count()
     multi_device_vs_golden(L, list(range(n)) if n > 1 else [0, 0])
+
+
+def test_arena_cache_round_trip_on_device(L, tmp_path):
+    """whale_data_save / whale_data_load on the B200: byte-identical arena, bit-identical results, refusal of
+    foreign / truncated / corrupted / structurally invalid caches; prints the save and load times."""
+    from conftest import arena_cache_round_trip
+    t_save, t_load, nbytes = arena_cache_round_trip(L, tmp_path, n_fam=200)
+    print(f"arena cache: {nbytes / 1e6:.1f} MB for 200 families, save {t_save * 1e3:.1f} ms, load + repack plans {t_load * 1e3:.1f} ms")

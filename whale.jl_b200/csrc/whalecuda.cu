@@ -1427,14 +1427,71 @@ int32_t whale_read_ale(whale_model_t m, int32_t n_files, const char* const* path
 //      .ale files and running the packer.  Layout: CacheHdr | FamHdr[F] | arena bytes | famC | per-node packer facts |
 //      work | aggregates.  Plans, shared-memory budgets, launch order and calibration are rebuilt on load (they depend
 //      on the runtime configuration).  A cache is valid for the model it was packed for (structure fingerprint). ----
+constexpr uint32_t CACHE_VERSION = 2;   // file layout
+constexpr uint32_t PACKER_VERSION = 2;  // meaning of the packed bytes (NodeRec / Ent / Slot / list order); bump on any packer change
 struct CacheHdr {
     char magic[8];       // "WHALEAR1"
     uint32_t version, nn;
-    uint64_t model_fp;   // species-tree structure + slicing
+    uint64_t model_fp;   // species-tree structure + slicing + record sizes + packer version
     uint64_t F, arena_bytes, ell_total;
     int64_t algo_bytes;
     double aggG, aggTroot;
+    uint64_t content_hash;  // FNV-1a over the family headers and the arena
 };
+static uint64_t fnv1a(const void* p, size_t n, uint64_t h = 1469598103934665603ull) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+// Structural validation of a loaded arena: every offset the kernels will follow must stay inside its family's blob
+// (a truncated-then-padded, corrupted or stale-layout cache must be refused, not read out of bounds on the device).
+static const char* validate_arena(const whale_model* m, const whale_data* D, const std::vector<uint32_t>& famC) {
+    const size_t nn = (size_t)m->nn, F = (size_t)D->F, A = D->arena_host.size();
+    uint64_t ell = 0;
+    for (size_t f = 0; f < F; f++) {
+        const FamHdr& H = D->hdr[f];
+        if ((H.base & 15) || H.base > A || (uint64_t)H.blob_bytes > A - H.base) return "family blob outside the arena";
+        if ((size_t)H.blob_bytes < nn * sizeof(NodeRec) || (H.blob_bytes & 15)) return "family blob too small";
+        if (H.ell_off != ell) return "ℓ offsets inconsistent";
+        const unsigned char* blob = D->arena_host.data() + H.base;
+        const NodeRec* recs = reinterpret_cast<const NodeRec*>(blob);
+        const uint64_t W = H.blob_bytes / 4, E = H.blob_bytes / 16;
+        for (size_t e = 0; e < nn; e++) {
+            const NodeRec& R = recs[e];
+            const uint64_t C = R.C;
+            if (C != famC[f * nn + e] || C > 65535 || R.nonleaf > C) return "compat counts inconsistent";
+            const int kind = m->kind[e];
+            uint64_t tw = (kind == WHALE_INTERNAL || kind == WHALE_ROOT) ? 3 * C + 1 : 0;
+            if (kind == WHALE_ROOT) tw += (uint64_t)H.nlev + 1;
+            tw = (tw + 3) & ~3ull;
+            if ((R.dptr_off & 3) || (R.tptr_off & 3) || (R.slot_off & 3)) return "misaligned list";
+            if (R.dptr_off + C + 1 > W || R.slot_off + 2ull * R.nslots > W || R.tptr_off + tw + C > W) return "word list outside the blob";
+            if ((uint64_t)R.dent_off + R.ndent > E || (uint64_t)R.tent_off + R.ntent > E) return "entry list outside the blob";
+            if (R.sptr_off && ((uint64_t)R.sptr_off + C + 1 > W || R.sent_off > E)) return "shape list outside the blob";
+            const uint32_t* words = reinterpret_cast<const uint32_t*>(blob);
+            if (words[R.dptr_off + C] != R.ndent) return "same-branch term count inconsistent";
+            if (tw && words[R.tptr_off + C] != R.ntent) return "speciation term count inconsistent";
+            if (R.sptr_off && (uint64_t)R.sent_off + words[R.sptr_off + C] > E) return "shape list outside the blob";
+            const Ent* ents = reinterpret_cast<const Ent*>(blob);
+            const uint64_t srcC = kind == WHALE_WGD ? famC[f * nn + m->child0[e]] : C;
+            for (uint32_t t = 0; t < R.ndent; t++) if (ents[R.dent_off + t].i1 >= srcC || ents[R.dent_off + t].i2 >= srcC) return "term index out of range";
+            if (tw) {
+                const uint64_t CF = famC[f * nn + m->child0[e]], CG = famC[f * nn + m->child1[e]];
+                for (uint32_t t = 0; t < R.ntent; t++) if (ents[R.tent_off + t].i1 >= CF || ents[R.tent_off + t].i2 >= CG) return "term index out of range";
+                const int32_t* lossF = reinterpret_cast<const int32_t*>(words + R.tptr_off + C + 1);
+                for (uint64_t c = 0; c < C; c++) if (lossF[c] >= (int64_t)CF || lossF[C + c] >= (int64_t)CG) return "loss index out of range";
+            }
+            const Slot* sl = reinterpret_cast<const Slot*>(words + R.slot_off);
+            for (uint32_t i = 0; i < R.nslots; i++)
+                if (sl[i].cell >= C || (uint64_t)sl[i].first + (uint64_t)(sl[i].cnt ? sl[i].cnt - 1 : 0) * sl[i].stride >= std::max<uint64_t>(R.ndent, 1) + (sl[i].cnt ? 0 : 65536))
+                    return "lane table out of range";
+            ell += (uint64_t)(m->nsl[e] + 1) * C;
+        }
+        if (recs[m->root].C != H.G) return "root compat list is not the clade list";
+    }
+    if (ell != D->ell_total) return "ℓ size inconsistent";
+    return nullptr;
+}
 static uint64_t model_fingerprint(const whale_model* m) {
     uint64_t h = 1469598103934665603ull;
     auto mix = [&](uint64_t v) { h ^= v; h *= 1099511628211ull; };
@@ -1444,6 +1501,7 @@ static uint64_t model_fingerprint(const whale_model* m) {
         mix((uint64_t)(uint32_t)m->child0[e]); mix((uint64_t)(uint32_t)m->child1[e]); mix((uint64_t)(uint32_t)m->order[e]);
     }
     mix((uint64_t)sizeof(FamHdr)); mix((uint64_t)sizeof(NodeRec)); mix((uint64_t)HEAVY_SLOTS); mix((uint64_t)NSHAPE);
+    mix((uint64_t)sizeof(Ent)); mix((uint64_t)sizeof(Slot)); mix((uint64_t)PACKER_VERSION);
     return h;
 }
 static bool put_raw(FILE* fp, const void* p, size_t bytes) { return bytes == 0 || fwrite(p, 1, bytes, fp) == bytes; }
@@ -1462,7 +1520,8 @@ int32_t whale_data_save(whale_data_t d, const char* path) {
     if (!fp) return fail(WHALE_ERR_ARG, "cannot open %s for writing", path);
     CacheHdr h{};
     memcpy(h.magic, "WHALEAR1", 8);
-    h.version = 1; h.nn = (uint32_t)nn; h.model_fp = model_fingerprint(m);
+    h.version = CACHE_VERSION; h.nn = (uint32_t)nn; h.model_fp = model_fingerprint(m);
+    h.content_hash = fnv1a(arena.data(), arena.size(), fnv1a(d->hdr.data(), d->hdr.size() * sizeof(FamHdr)));
     h.F = F; h.arena_bytes = d->arena_bytes; h.ell_total = d->ell_total; h.algo_bytes = d->algo_bytes;
     h.aggG = d->aggG; h.aggTroot = d->aggTroot;
     std::vector<uint32_t> famC(F * nn);
@@ -1479,9 +1538,9 @@ int32_t whale_data_load(whale_model_t m, const char* path, whale_data_t* out) {
     FILE* fp = fopen(path, "rb");
     if (!fp) return fail(WHALE_ERR_ARG, "cannot open %s", path);
     CacheHdr h{};
-    if (fread(&h, sizeof(h), 1, fp) != 1 || memcmp(h.magic, "WHALEAR1", 8) != 0 || h.version != 1) {
+    if (fread(&h, sizeof(h), 1, fp) != 1 || memcmp(h.magic, "WHALEAR1", 8) != 0 || h.version != CACHE_VERSION) {
         fclose(fp);
-        return fail(WHALE_ERR_ARG, "%s is not a whalecuda arena cache (version 1)", path);
+        return fail(WHALE_ERR_ARG, "%s is not a whalecuda arena cache (version %u)", path, CACHE_VERSION);
     }
     if (h.nn != (uint32_t)m->nn || h.model_fp != model_fingerprint(m) || h.F == 0 || h.F > 0x7fffffffull) {
         fclose(fp);
@@ -1500,6 +1559,12 @@ int32_t whale_data_load(whale_model_t m, const char* path, whale_data_t* out) {
     ok = ok && fgetc(fp) == EOF;
     fclose(fp);
     if (!ok) { delete D; return fail(WHALE_ERR_ARG, "%s is truncated or has trailing bytes", path); }
+    if (fnv1a(D->arena_host.data(), D->arena_host.size(), fnv1a(D->hdr.data(), D->hdr.size() * sizeof(FamHdr))) != h.content_hash) {
+        delete D;
+        return fail(WHALE_ERR_ARG, "%s is corrupted (content hash mismatch)", path);
+    }
+    D->ell_total = h.ell_total;
+    if (const char* why = validate_arena(m, D, famC)) { delete D; return fail(WHALE_ERR_ARG, "%s is not a valid arena for this model: %s", path, why); }
     D->famC.resize(F);
     for (size_t f = 0; f < F; f++) D->famC[f].assign(famC.begin() + f * nn, famC.begin() + (f + 1) * nn);
     D->ell_total = h.ell_total;
