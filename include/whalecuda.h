@@ -236,6 +236,42 @@ int32_t whale_backtrack(whale_model_t m, whale_data_t d, int32_t n_samples, cons
                         int64_t stride, int32_t max_nodes, int32_t* node_count, int32_t* gamma, int32_t* e,
                         int32_t* t, int32_t* parent, int32_t* status);
 
+/*
+ * The same walks with the results kept on the device (persistent buffers, no padded transfers): n_samples walks per
+ * family from the kept ℓ.  uniforms may be NULL: draw k of walk w then comes from a counter-based generator keyed by
+ * (seed, w, k) on the device (the reference calls the global rand(), src/track.jl:217,274 — with host-supplied uniforms
+ * the stream is explicit and reproducible against the oracle instead).  total_nodes (nullable) = Σ node counts.
+ * Fetch with whale_trees_counts / whale_trees_get / whale_trees_view, summarise with whale_trees_summary.
+ */
+int32_t whale_backtrack_device(whale_model_t m, whale_data_t d, int32_t n_samples, const double* uniforms,
+                               int64_t stride, uint64_t seed, int32_t max_nodes, int64_t* total_nodes);
+/*
+ * track_and_sum's sampling loop in its general form (src/track.jl:47-63): sample s of family f uses posterior row
+ * theta_index[f*n_samples + s] of x[n_theta][P] (the reference draws `i = rand(1:length(df))` per family and sample;
+ * NULL: row s mod n_theta).  For every row that is used, logpdf! runs for exactly the families that drew it (value-only
+ * DP keeping ℓ, launch order = that family list) and their walks follow on the same stream; nothing returns to the host
+ * in between.  Results stay on the device like whale_backtrack_device's.
+ */
+int32_t whale_track_sample(whale_model_t m, whale_data_t d, int32_t n_theta, const double* x, const double* p_leaf,
+                           int32_t n_samples, const int32_t* theta_index, const double* uniforms, int64_t stride,
+                           uint64_t seed, int32_t max_nodes, int64_t* total_nodes);
+/* node counts and statuses ([F*n_samples], family-major) of the trees on the handle */
+int32_t whale_trees_counts(whale_data_t d, int32_t* node_count, int32_t* status);
+/* the trees in compact form: offsets[F*n_samples + 1] (rows) and total_nodes rows of (gamma, e, t, parent) — packed on
+ * the device (one warp per tree), one pinned D2H copy.  _view returns pointers into library-owned pinned memory (valid
+ * until the next backtracking call on the handle), _get copies into caller buffers. */
+int32_t whale_trees_view(whale_data_t d, const int64_t** offsets, const int32_t** nodes4, int64_t* total_nodes);
+int32_t whale_trees_get(whale_data_t d, int64_t* offsets, int32_t* nodes4);
+/*
+ * sumtrees on the device (src/rectree.jl:113-133 with the tree identity of src/track.jl:95-113: the set over nodes of
+ * (γ, e, {(γ, e) of the children}), loss nodes (loss, e, γ of the sister); the slice t is not part of it): a 64-bit
+ * identity hash per tree, then per family the distinct trees — n_distinct[F]; for family f the first n_distinct[f]
+ * entries of hash/count/first[f*n_samples ...] hold the identity, how many samples showed it and the first such sample
+ * (ascending hash; sort by count for the reference's order).  tree_hash (nullable, [F*n_samples]) = every tree's hash.
+ */
+int32_t whale_trees_summary(whale_data_t d, int32_t* n_distinct, uint64_t* hash, int32_t* count, int32_t* first,
+                            uint64_t* tree_hash);
+
 /* counters for benchmarks: kernels launched by this library since load, and the last evaluation's
  * algorithmic flop / byte counts (SURVEY §8d coefficients) */
 /*

@@ -388,3 +388,75 @@ def arena_cache_round_trip(L, tmp_path, n_fam=5):
     with pytest.raises(wlib.WhaleCudaError, match="not a whalecuda arena cache"):
         W.load_arena(path, w)
     return t_save, t_load, nbytes
+
+
+def track_sample_and_summary(L, n_samples=24, n_theta=5):
+    """whale_track_sample (per-(family, sample) posterior rows, src/track.jl:50-53) against the step-by-step sequence
+    logpdf!(θ_i) + whale_backtrack with the same uniforms; the compact tree transfer against the padded one; the device-side
+    tree identity / sumtrees table (src/track.jl:95-113, src/rectree.jl:113-133) against the exact host-side `treekey`
+    partition; and the device random stream (no host uniforms): every tree valid, the same seed gives the same trees."""
+    import whale_jl_b200 as W
+    g = load_golden("c1_example1")
+    mh = L.model_create(golden_model(g))
+    fams = [0, 4, 7, 9]
+    dh = L.data_create(mh, golden_fams(g, fams))
+    F, S, MN = len(fams), n_samples, 256
+    rng = np.random.default_rng(21)
+    X = np.stack([g["xs"][i % len(g["xs"])] for i in range(n_theta)])
+    X[:, -1] = np.clip(X[:, -1] * np.linspace(1.0, 0.8, n_theta), 0.05, 0.95)
+    ti = rng.integers(n_theta, size=(F, S)).astype(np.int32)
+    U = rng.random((F, S, 4 * MN))
+    try:
+        tot = L.track_sample(mh, dh, X, g["m_pleaf"], S, ti, U, max_nodes=MN)
+        cnt, st = L.trees_counts(dh, F * S)
+        assert np.all(st == 0) and int(cnt.sum()) == tot
+        off, nodes = L.trees_get(dh, F * S, tot)
+        off2, nodes2 = L.trees_view(dh, F * S)
+        assert np.array_equal(off, off2) and np.array_equal(nodes, nodes2)
+        nd, h, c, f1, th = L.trees_summary(dh, F, S, with_tree_hash=True)
+        trees = [[nodes[off[f * S + s]:off[f * S + s + 1]].copy() for s in range(S)] for f in range(F)]
+        # (1) step by step: for every row, logpdf! then walk with the uniforms of the samples that drew it
+        for j in range(n_theta):
+            L.logpdf_grad(mh, dh, X[j], g["m_pleaf"], 1, keep_ell=True)
+            c1, s1, n1 = L.backtrack(mh, dh, S, U, MN)
+            for f in range(F):
+                for s in range(S):
+                    if ti[f, s] == j:
+                        assert np.array_equal(n1[f, s, :c1[f, s]], trees[f][s]), (j, f, s)
+        # (2) identity classes: device hash partition == exact treekey partition; summary table == host sumtrees
+        for f in range(F):
+            keys = [W.treekey(t) for t in trees[f]]
+            for a in range(S):
+                for b in range(a + 1, S):
+                    assert (keys[a] == keys[b]) == (th[f, a] == th[f, b]), (f, a, b)
+            summ, _ = W.sumtrees(trees[f])
+            k = int(nd[f])
+            order = sorted(range(k), key=lambda i: (-int(c[f, i]), int(f1[f, i])))
+            assert [int(c[f, i]) for i in order] == [x["count"] for x in summ]
+            assert all(W.treekey(trees[f][int(f1[f, i])]) == x["key"] for i, x in zip(order, summ))
+            assert int(c[f, :k].sum()) == S
+        # (3) device random stream
+        t1 = L.track_sample(mh, dh, X, g["m_pleaf"], S, ti, None, seed=77, max_nodes=MN)
+        cA, sA = L.trees_counts(dh, F * S)
+        oA, nA = L.trees_get(dh, F * S, t1)
+        t2 = L.track_sample(mh, dh, X, g["m_pleaf"], S, ti, None, seed=77, max_nodes=MN)
+        oB, nB = L.trees_get(dh, F * S, t2)
+        assert np.all(sA == 0) and t1 == t2 and np.array_equal(oA, oB) and np.array_equal(nA, nB)
+        t3 = L.track_sample(mh, dh, X, g["m_pleaf"], S, ti, None, seed=78, max_nodes=MN)
+        oC, nC = L.trees_get(dh, F * S, t3)
+        assert not (t3 == t1 and np.array_equal(nA, nC))
+        nl = [int((g["f_nleaf"][g["f_clade_off"][f]:g["f_clade_off"][f + 1]] == 1).sum()) for f in fams]
+        for f in range(F):  # every gene leaf exactly once per tree
+            for s in range(S):
+                t = nA[oA[f * S + s]:oA[f * S + s + 1]]
+                leafbranch = g["m_kind"][t[:, 1]] == 0
+                term = t[(t[:, 0] >= 0) & (t[:, 0] < nl[f]) & leafbranch]
+                assert sorted(term[:, 0].tolist()) == list(range(nl[f]))
+        # (4) walks only, from one kept ℓ, device stream
+        L.logpdf_grad(mh, dh, X[0], g["m_pleaf"], 1, keep_ell=True)
+        t4 = L.backtrack_device(mh, dh, S, None, seed=5, max_nodes=MN)
+        c4, s4 = L.trees_counts(dh, F * S)
+        assert np.all(s4 == 0) and int(c4.sum()) == t4
+    finally:
+        L.L.whale_data_destroy(dh)
+        L.L.whale_model_destroy(mh)

@@ -36,6 +36,8 @@ inline thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 struct uint4 { unsigned x, y, z, w; };
 struct double2 { double x, y; };
 struct int4 { int x, y, z, w; };
+struct int2 { int x, y; };
+inline int2 make_int2(int x, int y) { return int2{x, y}; }
 inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 // explicit round-to-nearest ops (the emulation build is compiled with -ffp-contract=off)
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }

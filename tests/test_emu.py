@@ -380,3 +380,8 @@ def test_emu_landplant_dt001(L, monkeypatch):
     for mode in ("rev", "fwd"):
         monkeypatch.setenv("WHALE_GRAD_MODE", mode)
         run_parity(L, "landplant_dt0.01", sel=sel, conds=["root"])
+
+
+def test_emu_track_sample_and_summary(L):
+    from conftest import track_sample_and_summary
+    track_sample_and_summary(L, n_samples=12, n_theta=3)

@@ -296,3 +296,9 @@ def test_arena_cache_round_trip_on_device(L, tmp_path):
     from conftest import arena_cache_round_trip
     t_save, t_load, nbytes = arena_cache_round_trip(L, tmp_path, n_fam=200)
     print(f"arena cache: {nbytes / 1e6:.1f} MB for 200 families, save {t_save * 1e3:.1f} ms, load + repack plans {t_load * 1e3:.1f} ms")
+
+
+def test_track_sample_and_summary(L):
+    """src/track.jl:47-63 with per-(family, sample) posterior rows, compact tree transfer, device tree identity / sumtrees."""
+    from conftest import track_sample_and_summary
+    track_sample_and_summary(L, n_samples=64, n_theta=7)

@@ -1,12 +1,17 @@
 #!/usr/bin/env python
-"""Backtracking throughput (BASELINE config 5 shape): reconciled trees per second on one GPU.
+"""Backtracking throughput (BASELINE.json configs[4], "C5": posterior reconciled trees for 10^4 families at 1/2/4/8 GPUs).
 
-    python tools/bench_track.py [--families 1000] [--samples 100]
+    python tools/bench_track.py [--families 10000] [--samples 100] [--thetas 100]
+    python -m torch.distributed.run --nproc-per-node N tools/bench_track.py ...     (families sharded over ranks, no collective)
 
-logpdf! (keep ℓ) once, then `n_samples` backtracked trees per family from host-supplied uniforms; reports the
-device-side rate (CUDA events around whale_backtrack's kernels are not exposed, so this is the wall time of the
-C-ABI call, which includes uploading the uniforms and downloading the node arrays) next to the oracle's rate on
-a sample of the same families."""
+Legs (all through the C ABI, wall clock around the calls = end to end, incl. every host<->device copy):
+  walks_device_rng   whale_backtrack_device from ONE kept ℓ, uniforms drawn on the device, trees fetched in compact form
+  walks_host_stream  the same with a host-supplied uniform stream (stride 512 doubles per walk: PCIe-bound)
+  walks_padded_r1    round 1's whale_backtrack (padded outputs, stride 4*max_nodes) on a subset, for comparison
+  track_sample       track_and_sum's loop (src/track.jl:47-63): every (family, sample) draws its own posterior row out of
+                     `--thetas`; logpdf! of the families that drew a row + their walks per row
+  summary            device-side tree identity hash + per-family dedup (sumtrees)
+Prints one JSON line (rank 0)."""
 import argparse
 import json
 import os
@@ -21,65 +26,110 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--families", type=int, default=1000)
+    ap.add_argument("--families", type=int, default=10000)
     ap.add_argument("--samples", type=int, default=100)
+    ap.add_argument("--thetas", type=int, default=100)
     ap.add_argument("--max-nodes", type=int, default=384)
     args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from whale_jl_b200 import synth
+    lo, hi = args.families * rank // world, args.families * (rank + 1) // world
+    d = synth.cache_dir(f"c5_seed5_n{args.families}_shard{rank}of{world}")
+    t0 = time.time()
+    synth.generate(d, hi - lo, seed=5, first=lo, workers=max(1, min(64, len(os.sched_getaffinity(0)) // world)))
+    gen_s = time.time() - t0
     import whale_jl_b200 as W
-    from whale_jl_b200 import synth, lib as wlib
+    from whale_jl_b200 import lib as wlib
     from whale_jl_b200.core import _data_handle
-    d = synth.cache_dir(f"c5_seed5_n{args.families}")
-    synth.generate(d, args.families, seed=5)
-    w = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), synth.c1_species_tree(), 0.05)
-    ccd = W.read_ale(d, w)
     L = wlib.get()
+    L.check(L.L.whale_set_device(local))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), synth.c1_species_tree(), 0.05)
+    ccd = W.read_ale_native(d, w)
     mh, dh = _data_handle(w, ccd)
-    t0 = time.perf_counter()
-    W.logpdf_(w, ccd)
-    t_keep = time.perf_counter() - t0
     F, S, MN = len(ccd), args.samples, args.max_nodes
-    U = np.random.default_rng(0).random((F, S, 4 * MN))
-    L.backtrack(mh, dh, 2, U[:, :2], MN)  # warm-up
+    Wn = F * S
+    x0, pl = w.x(), w.p_leaf()
+
+    def sync_all():
+        if dist is not None:
+            dist.barrier()
+
+    out = {"families_total": args.families, "families_rank0": F, "samples": S, "n_gpus": world, "gen_s": round(gen_s, 1)}
+    # ---- logpdf! (keep ℓ) ----
+    L.logpdf_grad(mh, dh, x0, pl, 1, keep_ell=True)
     t0 = time.perf_counter()
-    cnt, st, nodes = L.backtrack(mh, dh, S, U, MN)
-    dt = time.perf_counter() - t0
-    assert np.all(st == 0), np.unique(st)
-    kms = L.last_backtrack_ms(dh)
-    ell_bytes = 8 * sum(L.L.whale_ell_size(dh, f) for f in range(F))
-    out = {"metric": "backtracked reconciled trees/s", "value": F * S / dt, "kernel_ms": kms,
-           "kernel_trees_per_s": F * S / (kms * 1e-3), "ell_bytes_resident": int(ell_bytes), "families": F, "samples": S,
-           "mean_nodes_per_tree": float(cnt.mean()), "call_s": dt, "logpdf_keep_ell_s": t_keep,
-           "h2d_bytes": int(U.nbytes), "d2h_bytes": int(nodes.nbytes + cnt.nbytes + st.nbytes)}
-    # fused track_and_sum loop (src/track.jl:47-63): a new θ per sample, logpdf! + one walk per family, on the device
-    T = min(S, 50)
-    rng = np.random.default_rng(1)
-    X = w.x()[None, :] * np.exp(0.03 * rng.standard_normal((T, w.n_params)))
+    L.logpdf_grad(mh, dh, x0, pl, 1, keep_ell=True)
+    out["logpdf_keep_ell_ms"] = 1e3 * (time.perf_counter() - t0)
+    # ---- walks from one kept ℓ, device stream, compact fetch ----
+    L.backtrack_device(mh, dh, S, None, seed=1, max_nodes=MN)
+    L.trees_view(dh, Wn)
+    sync_all()
+    reps = 3
+    t0 = time.perf_counter()
+    for r in range(reps):
+        tot = L.backtrack_device(mh, dh, S, None, seed=2 + r, max_nodes=MN)
+        off, nodes = L.trees_view(dh, Wn)
+    dt = (time.perf_counter() - t0) / reps
+    cnt, st = L.trees_counts(dh, Wn)
+    out["walks_device_rng"] = {"trees_per_s_rank": Wn / dt, "ms": 1e3 * dt, "kernel_ms": L.last_backtrack_ms(dh),
+                               "nodes_per_tree": tot / Wn, "d2h_bytes": int(16 * tot + 8 * (Wn + 1) + 8 * Wn),
+                               "failed": int((st != 0).sum())}
+    # ---- device summary ----
+    t0 = time.perf_counter()
+    nd, h, c, f1, _ = L.trees_summary(dh, F, S)
+    out["summary"] = {"ms": 1e3 * (time.perf_counter() - t0), "distinct_trees_per_family_mean": float(nd.mean())}
+    # ---- host-supplied stream ----
+    stride = 512
+    rng = np.random.default_rng(3 + rank)
+    nf_h = min(F, 2000)
+    # (a handle over the first nf_h families would need a second pack: time the full batch with a stream only when it fits)
+    if Wn * stride * 8 <= 6 << 30:
+        U = rng.random((F, S, stride))
+        L.backtrack_device(mh, dh, S, U, max_nodes=MN)
+        t0 = time.perf_counter()
+        tot = L.backtrack_device(mh, dh, S, U, max_nodes=MN)
+        L.trees_view(dh, Wn)
+        dt = time.perf_counter() - t0
+        cnt, st = L.trees_counts(dh, Wn)
+        out["walks_host_stream"] = {"trees_per_s_rank": Wn / dt, "ms": 1e3 * dt, "h2d_bytes": int(U.nbytes), "stride": stride,
+                                    "exhausted_or_failed": int((st != 0).sum())}
+        del U
+    # ---- track_and_sum's loop: a posterior row per (family, sample) ----
+    nt = args.thetas
+    X = x0[None, :] * np.exp(0.05 * rng.standard_normal((nt, len(x0))))
     X[:, 2:] = np.clip(X[:, 2:], 1e-3, 1 - 1e-3)
-    L.track(mh, dh, X[:2], w.p_leaf(), 1, U[:, :2], MN)  # warm-up
+    ti = rng.integers(nt, size=(F, S)).astype(np.int32)
+    L.track_sample(mh, dh, X, pl, S, ti, None, seed=9, max_nodes=MN)
+    sync_all()
     t0 = time.perf_counter()
-    c2, s2, n2, ll2 = L.track(mh, dh, X, w.p_leaf(), 1, U[:, :T], MN)
-    dtt = time.perf_counter() - t0
-    assert np.all(s2 == 0)
-    out["fused_track"] = {"thetas": T, "trees_per_s_call": F * T / dtt, "device_ms": L.last_backtrack_ms(dh),
-                          "trees_per_s_device": F * T / (L.last_backtrack_ms(dh) * 1e-3),
-                          "note": "every tree from its own posterior draw: logpdf! (keep ℓ) + walk per draw, enqueued back to back"}
-    # oracle on a sample
-    from oracle import whale_oracle as wo, flat
-    ow = wo.WhaleModel(wo.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), wo.c1_tree(), 0.05)
-    files = sorted(os.listdir(d))[:8]
-    spmap = {n.name: n.id for n in ow.order if n.isleaf()}
-    occd = [wo.CCD(wo.parse_aleobserve(os.path.join(d, f)), ow, spmap) for f in files]
-    fm, ff = flat.FlatModel(ow), flat.FlatFams(occd, len(ow))
-    t0 = time.perf_counter()
-    n = 0
-    for f in range(len(occd)):
-        for s in range(10):
-            k, arr, used = flat.backtrack(fm, ff, f, U[f, s], max_nodes=MN)
-            assert k == cnt[f, s] and np.array_equal(arr, nodes[f, s, :k]), (f, s)
-            n += 1
-    out["oracle_trees_per_s_single_thread_incl_dp"] = n / (time.perf_counter() - t0)
-    out["parity_checked_trees"] = n
-    print(json.dumps(out))
+    tot = L.track_sample(mh, dh, X, pl, S, ti, None, seed=10, max_nodes=MN)
+    off, nodes = L.trees_view(dh, Wn)
+    dt = time.perf_counter() - t0
+    cnt, st = L.trees_counts(dh, Wn)
+    out["track_sample"] = {"trees_per_s_rank": Wn / dt, "ms": 1e3 * dt, "device_ms": L.last_backtrack_ms(dh), "thetas": nt,
+                           "family_evaluations": int(sum(len(np.unique(np.nonzero(ti == j)[0])) for j in range(nt))),
+                           "failed": int((st != 0).sum())}
+    if dist is not None:
+        import torch
+        keys = [("walks_device_rng", "ms"), ("track_sample", "ms")]
+        t = torch.tensor([out[a][b] for a, b in keys], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        for (a, b), v in zip(keys, t.tolist()):
+            out[a]["ms_max_over_ranks"] = v
+            out[a]["trees_per_s_total"] = args.families * S / (v * 1e-3)
+        dist.destroy_process_group()
+    else:
+        for a in ("walks_device_rng", "track_sample"):
+            out[a]["trees_per_s_total"] = out[a]["trees_per_s_rank"]
+    if rank == 0:
+        print(json.dumps(out))
 
 
 if __name__ == "__main__":

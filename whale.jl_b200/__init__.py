@@ -13,9 +13,9 @@ from .model import WhaleModel
 from .ccd import CCD, CCDVector, NativeCCDVector, read_ale, read_ale_native, save_arena, load_arena
 from .core import (logpdf, logpdf_, loglikelihood, logpdf_and_gradient, logpdf_per_family, ell, slices, backtrack,
                    BacktrackFailed, logpdf_mixture, logpdf_mixture_and_gradient, logpdf_modelarray, condition, set_probe, track,
-                   treekey, sumtrees)
+                   treekey, sumtrees, sumtrees_device)
 
 __all__ = ["Node", "readnw", "getlca", "getleaves", "postwalk", "insertnode", "nwstr", "extree", "ConstantDLWGD",
            "DLWGD", "WhaleModel", "CCD", "CCDVector", "read_ale", "read_ale_native", "NativeCCDVector", "save_arena", "load_arena", "logpdf", "logpdf_", "loglikelihood",
            "logpdf_and_gradient", "logpdf_per_family", "ell", "slices", "backtrack", "BacktrackFailed", "logpdf_mixture", "logpdf_mixture_and_gradient", "logpdf_modelarray", "condition",
-           "set_probe", "track", "treekey", "sumtrees"]
+           "set_probe", "track", "treekey", "sumtrees", "sumtrees_device"]

@@ -194,23 +194,64 @@ def _trees_from(cnt, st, nodes, n_samples, F):
     return [[nodes[f, s, :cnt[f, s]].copy() for s in range(n_samples)] for f in range(F)]
 
 
-def track(wm: WhaleModel, xs, posterior, n: int, fun=None, seed=None, max_nodes: int = 512, return_loglik=False):
-    """`track(TreeTracker(model, data, df, fun), N)` without the summaries (src/track.jl:30-63): for each of the
-    `n` samples draw a posterior row, re-parameterise the model (`fun(model, row)`, default `model(**row)`),
-    `logpdf!` and backtrack one tree per family — fused on the device (`whale_track`: the n evaluations and walks
-    are enqueued back to back, nothing returns to the host in between).  Returns trees[family][sample] as
-    (γ, e, t, parent) arrays.  Summaries (`sumtrees`, src/rectree.jl) are host-side post-processing outside the
-    hot path."""
+def track(wm: WhaleModel, xs, posterior, n: int, fun=None, seed=None, max_nodes: int = 512, return_loglik=False,
+          shared_draws=False, device_rng=False, summary=False):
+    """`track(TreeTracker(model, data, df, fun), N)` (src/track.jl:30-63): for every family and each of its `n` samples
+    draw a posterior row `i = rand(1:length(df))` (:50-53 — independently per family AND sample, as the reference does),
+    re-parameterise the model (`fun(model, row)`, default `model(**row)`), `logpdf!` and backtrack one tree — on the
+    device (`whale_track_sample`: for every row in use, logpdf! of exactly the families that drew it and their walks,
+    enqueued back to back).  Returns trees[family][sample] as (γ, e, t, parent) arrays.
+
+    shared_draws=True is round 1's variant (one draw per sample index shared by all families, `whale_track`; the only
+    form that can also return the batch log-likelihood of every draw, `return_loglik`).  device_rng=True draws the walks'
+    uniforms on the device (seeded counter-based generator) instead of shipping a host stream.  summary=True also
+    returns the device-side `sumtrees` table (see `sumtrees_device`)."""
     rng = np.random.default_rng(seed)
     xs, _ = _as_vector(xs)
     fun = fun or (lambda m, row: m(**row))
     mh, dh = _data_handle(wm, xs)
-    rows = [posterior[int(rng.integers(len(posterior)))] for _ in range(n)]
-    X = np.stack([fun(wm, row).x() for row in rows])
-    U = rng.random((len(xs), n, 4 * max_nodes))
-    cnt, st, nodes, ll = _lib.get().track(mh, dh, X, wm.p_leaf(), CONDITIONS[wm.condition], U, max_nodes)
-    trees = _trees_from(cnt, st, nodes, n, len(xs))
-    return (trees, ll) if return_loglik else trees
+    L, F = _lib.get(), len(xs)
+    if shared_draws or return_loglik:
+        rows = [posterior[int(rng.integers(len(posterior)))] for _ in range(n)]
+        X = np.stack([fun(wm, row).x() for row in rows])
+        U = rng.random((F, n, 4 * max_nodes))
+        cnt, st, nodes, ll = L.track(mh, dh, X, wm.p_leaf(), CONDITIONS[wm.condition], U, max_nodes)
+        trees = _trees_from(cnt, st, nodes, n, F)
+        return (trees, ll) if return_loglik else trees
+    X = np.stack([fun(wm, row).x() for row in posterior])
+    ti = rng.integers(len(posterior), size=(F, n)).astype(np.int32)
+    U = None if device_rng else rng.random((F, n, 4 * max_nodes))
+    tot = L.track_sample(mh, dh, X, wm.p_leaf(), n, ti, U, seed=int(rng.integers(1 << 62)), max_nodes=max_nodes)
+    trees = _trees_compact(L, dh, F, n, tot)
+    return (trees, sumtrees_device(wm, xs, n)) if summary else trees
+
+
+def _trees_compact(L, dh, F, n, total):
+    cnt, st = L.trees_counts(dh, F * n)
+    if np.any(st == 1):
+        raise BacktrackFailed("Backtracking failed (no event selected; numerically inconsistent ℓ)")
+    if np.any(st == 2):
+        raise RuntimeError("backtrack: max_nodes too small for a sampled tree")
+    if np.any(st == 3):
+        raise RuntimeError("backtrack: uniform stream exhausted (increase the stride)")
+    off, nodes = L.trees_get(dh, F * n, total)
+    return [[nodes[off[f * n + s]:off[f * n + s + 1]] for s in range(n)] for f in range(F)]
+
+
+def sumtrees_device(wm: WhaleModel, xs, n: int):
+    """`sumtrees` (src/rectree.jl:113-133) for the trees left on the device by the last `track` / `backtrack_device`:
+    per family the distinct reconciled trees (identity as in src/track.jl:95-113, hashed on the device), most frequent
+    first (ties: first sampled first): list over families of lists of dicts {count, freq, first (sample index), hash}."""
+    xs, _ = _as_vector(xs)
+    mh, dh = _data_handle(wm, xs)
+    F = len(xs)
+    nd, h, c, f1, _ = _lib.get().trees_summary(dh, F, n)
+    out = []
+    for f in range(F):
+        k = int(nd[f])
+        order = sorted(range(k), key=lambda i: (-int(c[f, i]), int(f1[f, i])))
+        out.append([{"count": int(c[f, i]), "freq": int(c[f, i]) / n, "first": int(f1[f, i]), "hash": int(h[f, i])} for i in order])
+    return out
 
 
 def treekey(nodes) -> frozenset:

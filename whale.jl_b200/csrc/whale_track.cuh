@@ -33,15 +33,40 @@ struct BTArgs {
     int32_t* parent;
     int32_t* status;         // [F*S]
     int4* stack;             // [F*nsamp*max_nodes] scratch of this launch
+    // general form (whale_track_sample): this launch walks the listed (family, sample) pairs — the samples whose
+    // posterior draw is the θ the kept ℓ was computed for — instead of a sample range of every family
+    const int2* pairs;       // nullptr: the range form above
+    int npairs;
+    // uniforms == nullptr: draw k of walk w is a counter-based generator's output for (seed, w, k)  (the reference calls
+    // the global rand(), src/track.jl:217,274; with host-supplied uniforms the stream is explicit instead)
+    unsigned long long seed;
 };
+
+// counter-based uniform in [0, 1): splitmix64 of (seed, walk, draw), top 53 bits
+__device__ __forceinline__ double rng_u01(unsigned long long seed, unsigned long long w, unsigned long long k) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (w + 1) + 0xD1B54A32D192ED03ull * (k + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
 
 __device__ __forceinline__ double mul3(double a, double b, double c) { return __dmul_rn(__dmul_rn(a, b), c); }
 
 __global__ void __launch_bounds__(128) k_backtrack(BTArgs A) {
     const long long wl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (wl >= (long long)A.nfam * A.nsamp) return;
-    const int fam = (int)(wl / A.nsamp);
-    const long long w = (long long)fam * A.samp_total + A.samp_off + (wl - (long long)fam * A.nsamp);
+    int fam;
+    long long w;
+    if (A.pairs) {
+        if (wl >= A.npairs) return;
+        const int2 pr = A.pairs[wl];
+        fam = pr.x;
+        w = (long long)fam * A.samp_total + pr.y;
+    } else {
+        if (wl >= (long long)A.nfam * A.nsamp) return;
+        fam = (int)(wl / A.nsamp);
+        w = (long long)fam * A.samp_total + A.samp_off + (wl - (long long)fam * A.nsamp);
+    }
     const ModelDev& M = A.M;
     const PlanDev& PL = A.PL;
     const FamHdr* Hp = A.hdr + fam;
@@ -50,7 +75,8 @@ __global__ void __launch_bounds__(128) k_backtrack(BTArgs A) {
     const uint32_t* words = reinterpret_cast<const uint32_t*>(blob);
     const Ent* ents = reinterpret_cast<const Ent*>(blob);
     const double* ellf = A.ell + Hp->ell_off;
-    const double* U = A.uniforms + w * A.stride;
+    const double* U = A.uniforms ? A.uniforms + w * A.stride : nullptr;
+    auto next_u = [&](int k) -> double { return U ? U[k] : rng_u01(A.seed, (unsigned long long)w, (unsigned long long)k); };
     int32_t* o_g = A.gamma + w * A.max_nodes;
     int32_t* o_e = A.enode + w * A.max_nodes;
     int32_t* o_t = A.trow + w * A.max_nodes;
@@ -105,7 +131,7 @@ __global__ void __launch_bounds__(128) k_backtrack(BTArgs A) {
         if (t == 0) {  // inter-node :213-225
             if (kind == WHALE_LEAF) continue;
             if (used >= A.stride) { st = 3; break; }
-            double r = __dmul_rn(U[used++], L(e, c, 0));
+            double r = __dmul_rn(next_u(used++), L(e, c, 0));
             const int f = M.child0[e], h = M.child1[e];
             const int lf_ = M.nsl[f];
             if (kind == WHALE_WGD) {  // :258-266
@@ -193,7 +219,7 @@ __global__ void __launch_bounds__(128) k_backtrack(BTArgs A) {
                 nnext = 1;
             } else {
                 if (used >= A.stride) { st = 3; break; }
-                double r = __dmul_rn(U[used++], L(e, c, t));
+                double r = __dmul_rn(next_u(used++), L(e, c, t));
                 const double2 pp = PL.pp[PL.toff[e] + t];
                 r = __dadd_rn(r, -__dmul_rn(pp.x, L(e, c, t - 1)));
                 if (r < 0.0) { n0 = make_int4(e, c, t - 1, 0); nnext = 1; }
@@ -213,4 +239,124 @@ __global__ void __launch_bounds__(128) k_backtrack(BTArgs A) {
     A.node_count[w] = nnodes;
     A.status[w] = st;
     (void)nn;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Tree identity and the per-family summary of backtracked samples (src/track.jl:95-113 nodehash / cladehash,
+// src/rectree.jl:113-133 sumtrees).  The reference identifies a reconciled tree with the SET over its nodes of
+//     (γ, e, {(γ, e) of the children})        loss nodes: (loss, e, γ of the sister)
+// — the slice t of an event is not part of it.  k_tree_hash forms a 64-bit hash of that set, one thread per tree:
+// a node's children are folded commutatively into the parent (nodes are in creation order: parents first), each node's
+// key is mixed and the keys are added up (a set hash; a (γ, e) state occurs once per tree, so set = multiset).
+// k_tree_dedup sorts the n_samples hashes of one family in shared memory and writes the runs: distinct trees with
+// their counts and the first sample that showed them.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ unsigned long long key2(int g, int e) {
+    return mix64(((unsigned long long)(unsigned)(g + 2) << 32) | (unsigned long long)(unsigned)e);
+}
+
+struct HashArgs {
+    const int32_t* node_count;  // [W]
+    const int32_t* gamma;       // [W*max_nodes]
+    const int32_t* enode;
+    const int32_t* parent;
+    const int32_t* status;
+    int4* scratch;              // [W*max_nodes]: .x,.y = children key sum (u64), .z = Σ children γ, .w = #children
+    unsigned long long* hash;   // [W]
+    long long W;
+    int max_nodes;
+};
+__global__ void __launch_bounds__(128) k_tree_hash(HashArgs A) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= A.W) return;
+    const int n = A.node_count[w];
+    const int32_t* g = A.gamma + w * A.max_nodes;
+    const int32_t* e = A.enode + w * A.max_nodes;
+    const int32_t* par = A.parent + w * A.max_nodes;
+    int4* sc = A.scratch + w * A.max_nodes;
+    for (int i = 0; i < n; i++) sc[i] = make_int4(0, 0, 0, 0);
+    for (int i = 1; i < n; i++) {
+        const int p = par[i];
+        int4 v = sc[p];
+        unsigned long long acc = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
+        acc += key2(g[i], e[i]);
+        sc[p] = make_int4((int)(unsigned)(acc & 0xffffffffull), (int)(unsigned)(acc >> 32), v.z + g[i], v.w + 1);
+    }
+    unsigned long long h = 0x243F6A8885A308D3ull + (unsigned long long)n;
+    for (int i = 0; i < n; i++) {
+        unsigned long long k;
+        if (g[i] < 0) {  // loss node: (loss, e, γ of its sister)
+            const int p = par[i];
+            const int sis = (p >= 0 && sc[p].w == 2) ? sc[p].z - g[i] : -2;
+            k = mix64(key2(-1, e[i]) ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(unsigned)(sis + 2)));
+        } else {
+            const int4 v = sc[i];
+            const unsigned long long acc = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
+            k = mix64(key2(g[i], e[i]) + 0xC2B2AE3D27D4EB4Full * (acc + (unsigned long long)v.w));
+        }
+        h += mix64(k);
+    }
+    A.hash[w] = A.status[w] == 0 ? h : 0xFFFFFFFFFFFFFFFFull;  // failed walks share one bucket
+}
+
+// one CTA per family: sort (hash, sample) pairs (bitonic, padded to a power of two), then emit the runs
+__global__ void __launch_bounds__(256) k_tree_dedup(const unsigned long long* __restrict__ hash, int S, int Spad,
+                                                    int32_t* __restrict__ n_distinct, unsigned long long* __restrict__ out_hash,
+                                                    int32_t* __restrict__ out_count, int32_t* __restrict__ out_first) {
+    EXTERN_SHARED(dsm);
+    unsigned long long* hk = reinterpret_cast<unsigned long long*>(dsm);  // [Spad]
+    int* hv = reinterpret_cast<int*>(hk + Spad);                           // [Spad]
+    const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < Spad; i += nt) {
+        hk[i] = i < S ? hash[(size_t)f * S + i] : 0xFFFFFFFFFFFFFFFFull;
+        hv[i] = i < S ? i : 0x7fffffff;
+    }
+    __syncthreads();
+    for (int k = 2; k <= Spad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < Spad; i += nt) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const unsigned long long a = hk[i], b = hk[l];
+                    const int va = hv[i], vb = hv[l];
+                    const bool gt = a > b || (a == b && va > vb);  // ties: the earlier sample first
+                    if (gt == up) { hk[i] = b; hk[l] = a; hv[i] = vb; hv[l] = va; }
+                }
+            }
+            __syncthreads();
+        }
+    // runs over the first S sorted entries (padding sorts last: its sample index is larger than any real one)
+    if (tid == 0) {
+        int nd = 0;
+        for (int i = 0; i < S;) {
+            int j = i + 1;
+            while (j < S && hk[j] == hk[i]) j++;
+            out_hash[(size_t)f * S + nd] = hk[i];
+            out_count[(size_t)f * S + nd] = j - i;
+            out_first[(size_t)f * S + nd] = hv[i];
+            nd++;
+            i = j;
+        }
+        n_distinct[f] = nd;
+    }
+}
+
+// pack the walks' node rows: one warp per tree copies its node_count rows (γ, e, t, parent) to offsets[w]
+__global__ void __launch_bounds__(128) k_tree_pack(const int32_t* __restrict__ node_count, const long long* __restrict__ offsets,
+                                                   const int32_t* __restrict__ gamma, const int32_t* __restrict__ enode,
+                                                   const int32_t* __restrict__ trow, const int32_t* __restrict__ parent,
+                                                   int max_nodes, long long W, int4* __restrict__ packed) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= W) return;
+    const int n = node_count[w];
+    const long long o = offsets[w], b = w * max_nodes;
+    for (int i = lane; i < n; i += 32) packed[o + i] = make_int4(gamma[b + i], enode[b + i], trow[b + i], parent[b + i]);
 }

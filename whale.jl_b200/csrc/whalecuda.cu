@@ -241,6 +241,28 @@ struct whale_data {
     double* d_hist = nullptr;
     size_t hist_stride = 0;
     unsigned int* d_next = nullptr;
+    // backtracked trees of the last whale_backtrack / whale_track_sample call: persistent (grow-only) device and pinned host
+    // buffers; the padded per-walk rows stay on the device for whale_trees_get / whale_trees_summary
+    struct TreeBuf {
+        long long W = 0;
+        int S = 0, max_nodes = 0;
+        bool valid = false;
+        int32_t *d_cnt = nullptr, *d_st = nullptr, *d_g = nullptr, *d_e = nullptr, *d_t = nullptr, *d_p = nullptr;
+        size_t capW = 0, capN = 0;           // walks, walks*max_nodes
+        int4* d_stack = nullptr; size_t cap_stack = 0;
+        double* d_u = nullptr; size_t cap_u = 0;
+        double* d_xs = nullptr; size_t cap_xs = 0;
+        int2* d_pairs = nullptr; int* d_famlist = nullptr; size_t cap_pairs = 0;
+        long long* d_off = nullptr; size_t cap_off = 0;
+        int4* d_packed = nullptr; size_t cap_packed = 0;
+        unsigned long long* d_hash = nullptr; unsigned long long* d_dh = nullptr; int32_t *d_dc = nullptr, *d_df = nullptr, *d_nd = nullptr;
+        size_t cap_hash = 0, cap_nd = 0;
+        int32_t *h_cnt = nullptr, *h_st = nullptr; size_t hcapW = 0;      // pinned
+        long long* h_off = nullptr; size_t hcap_off = 0;
+        int32_t* h_packed = nullptr; size_t hcap_packed = 0;
+        long long total_nodes = 0;
+        bool packed_valid = false;
+    } tb;
     // peer-memory exchange (one process per GPU): own buffer, the peers' buffers as mapped here, step counter
     int peer_rank = -1, peer_world = 0;
     double* peer_bufs[16] = {};
@@ -411,6 +433,29 @@ static cudaError_t upload_plan(Plan& pl, int nn) {
 }
 
 static int g_device = 0;
+
+// grow-only device / pinned buffers (backtracking results)
+template <class T>
+static cudaError_t grow_dev(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    const size_t want = need + need / 4;
+    cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(want, 1) * sizeof(T));
+    if (e == cudaSuccess) *cap = want;
+    return e;
+}
+template <class T>
+static cudaError_t grow_pinned(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return cudaSuccess;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *cap = 0;
+    const size_t want = need + need / 4;
+    cudaError_t e = cudaMallocHost((void**)p, std::max<size_t>(want, 1) * sizeof(T));
+    if (e == cudaSuccess) *cap = want;
+    return e;
+}
+
 
 
 extern "C" {
@@ -1583,6 +1628,16 @@ int32_t whale_data_destroy(whale_data_t d) {
     for (int g = 0; g < MAXPLAN; g++) { cudaFree(d->d_perm[g]); cudaFree(d->d_roff[g]); }
     for (Plan& cp : d->chunk_plans) for (void* q : cp.owned) cudaFree(q);
     cudaFree(d->d_out_fam); cudaFree(d->d_partial); cudaFree(d->d_done);
+    {
+        auto& T = d->tb;
+        cudaFree(T.d_cnt); cudaFree(T.d_st); cudaFree(T.d_g); cudaFree(T.d_e); cudaFree(T.d_t); cudaFree(T.d_p); cudaFree(T.d_stack);
+        cudaFree(T.d_u); cudaFree(T.d_xs); cudaFree(T.d_pairs); cudaFree(T.d_famlist); cudaFree(T.d_off); cudaFree(T.d_packed);
+        cudaFree(T.d_hash); cudaFree(T.d_dh); cudaFree(T.d_dc); cudaFree(T.d_df); cudaFree(T.d_nd);
+        if (T.h_cnt) cudaFreeHost(T.h_cnt);
+        if (T.h_st) cudaFreeHost(T.h_st);
+        if (T.h_off) cudaFreeHost(T.h_off);
+        if (T.h_packed) cudaFreeHost(T.h_packed);
+    }
 #ifndef WHALE_EMU
     for (int q = 0; q < 16; q++) if (d->peer_open[q] && d->peer_bufs[q]) cudaIpcCloseMemHandle(d->peer_bufs[q]);
 #endif
@@ -1998,51 +2053,292 @@ int32_t whale_ell_get(whale_data_t d, int32_t fam, double* out) {
     return WHALE_OK;
 }
 
+// ---- backtracking: persistent buffers, walks, compaction, summaries ----
+static int32_t ensure_tree_bufs(whale_data* D, long long W, int max_nodes, size_t stack_walks) {
+    auto& T = D->tb;
+    const size_t w = (size_t)W, n = (size_t)W * max_nodes;
+    if (w > T.capW) {
+        size_t c1 = T.capW, c2 = T.capW;
+        CU(grow_dev(&T.d_cnt, &c1, w));
+        CU(grow_dev(&T.d_st, &c2, w));
+        T.capW = std::min(c1, c2);
+    }
+    if (n > T.capN) {
+        size_t c[4] = {T.capN, T.capN, T.capN, T.capN};
+        CU(grow_dev(&T.d_g, &c[0], n)); CU(grow_dev(&T.d_e, &c[1], n)); CU(grow_dev(&T.d_t, &c[2], n)); CU(grow_dev(&T.d_p, &c[3], n));
+        T.capN = std::min(std::min(c[0], c[1]), std::min(c[2], c[3]));
+    }
+    CU(grow_dev(&T.d_stack, &T.cap_stack, stack_walks * (size_t)max_nodes));
+    if (w > T.hcapW) {
+        size_t c1 = T.hcapW, c2 = T.hcapW;
+        CU(grow_pinned(&T.h_cnt, &c1, w));
+        CU(grow_pinned(&T.h_st, &c2, w));
+        T.hcapW = std::min(c1, c2);
+    }
+    T.W = W; T.max_nodes = max_nodes; T.valid = false; T.packed_valid = false;
+    return WHALE_OK;
+}
+
+// after the walks: counts and statuses to the host (pinned), total node count
+static int32_t finish_walks(whale_data* D, cudaStream_t st, int S) {
+    auto& T = D->tb;
+    CU(cudaMemcpyAsync(T.h_cnt, T.d_cnt, (size_t)T.W * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(T.h_st, T.d_st, (size_t)T.W * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    long long tot = 0;
+    for (long long w = 0; w < T.W; w++) tot += T.h_cnt[w];
+    T.total_nodes = tot;
+    T.S = S;
+    T.valid = true;
+    return WHALE_OK;
+}
+
 int32_t whale_backtrack(whale_model_t m, whale_data_t d, int32_t n_samples, const double* uniforms, int64_t stride,
                         int32_t max_nodes, int32_t* node_count, int32_t* gamma, int32_t* e, int32_t* t, int32_t* parent,
                         int32_t* status) {
     if (!m || !d || !uniforms || !node_count || !gamma || !e || !t || !parent || !status)
         return fail(WHALE_ERR_ARG, "null argument");
+    int32_t rc = whale_backtrack_device(m, d, n_samples, uniforms, stride, 0ull, max_nodes, nullptr);
+    if (rc != WHALE_OK) return rc;
+    auto& T = d->tb;
+    const size_t W = (size_t)T.W, N = W * (size_t)max_nodes;
+    memcpy(node_count, T.h_cnt, W * 4);
+    memcpy(status, T.h_st, W * 4);
+    CU(cudaMemcpy(gamma, T.d_g, N * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(e, T.d_e, N * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(t, T.d_t, N * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(parent, T.d_p, N * 4, cudaMemcpyDeviceToHost));
+    return WHALE_OK;
+}
+
+int32_t whale_backtrack_device(whale_model_t m, whale_data_t d, int32_t n_samples, const double* uniforms, int64_t stride,
+                               uint64_t seed, int32_t max_nodes, int64_t* total_nodes) {
+    if (!m || !d) return fail(WHALE_ERR_ARG, "null argument");
     if (d->m != m) return fail(WHALE_ERR_ARG, "data handle belongs to another model");
-    if (n_samples <= 0 || stride <= 0 || max_nodes <= 1) return fail(WHALE_ERR_ARG, "n_samples, stride and max_nodes must be positive");
+    if (n_samples <= 0 || max_nodes <= 1 || (uniforms && stride <= 0)) return fail(WHALE_ERR_ARG, "n_samples, stride and max_nodes must be positive");
     if (!d->ell_valid || !d->d_ell) return fail(WHALE_ERR_STATE, "no ℓ kept: evaluate with WHALE_KEEP_ELL (logpdf!) first");
     CU(cudaSetDevice(m->device));
-    const size_t W = (size_t)d->F * n_samples;
-    double* d_u = nullptr;
-    int32_t *d_cnt = nullptr, *d_g = nullptr, *d_e = nullptr, *d_t = nullptr, *d_p = nullptr, *d_st = nullptr;
-    int4* d_stack = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(d_u); cudaFree(d_cnt); cudaFree(d_g); cudaFree(d_e); cudaFree(d_t); cudaFree(d_p); cudaFree(d_st);
-        cudaFree(d_stack);
-    };
-#define CUB(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { cleanup(); return fail(WHALE_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); } } while (0)
-    CUB(cudaMalloc((void**)&d_u, W * stride * sizeof(double)));
-    CUB(cudaMemcpy(d_u, uniforms, W * stride * sizeof(double), cudaMemcpyHostToDevice));
-    CUB(cudaMalloc((void**)&d_cnt, W * 4)); CUB(cudaMalloc((void**)&d_st, W * 4));
-    CUB(cudaMalloc((void**)&d_g, W * max_nodes * 4)); CUB(cudaMalloc((void**)&d_e, W * max_nodes * 4));
-    CUB(cudaMalloc((void**)&d_t, W * max_nodes * 4)); CUB(cudaMalloc((void**)&d_p, W * max_nodes * 4));
-    CUB(cudaMalloc((void**)&d_stack, W * max_nodes * sizeof(int4)));
+    const long long W = (long long)d->F * n_samples;
+    int32_t rc = ensure_tree_bufs(d, W, max_nodes, (size_t)W);
+    if (rc != WHALE_OK) return rc;
+    auto& T = d->tb;
+    cudaStream_t st = m->stream;
+    if (uniforms) {
+        CU(grow_dev(&T.d_u, &T.cap_u, (size_t)W * stride));
+        CU(cudaMemcpyAsync(T.d_u, uniforms, (size_t)W * stride * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
     Plan& p0 = m->plan[0];
-    CUB(launch_tables(m, p0, d->d_x_keep, d->d_pleaf_keep, m->stream, false));
-    BTArgs a{m->dev, p0.dev, d->d_arena, d->d_hdr, d->d_ell, d->d_x_keep, d_u, (long long)stride, d->F, n_samples, max_nodes,
-             0, n_samples, d_cnt, d_g, d_e, d_t, d_p, d_st, d_stack};
-    cudaEvent_t eb0 = nullptr, eb1 = nullptr;
-    CUB(cudaEventCreate(&eb0)); CUB(cudaEventCreate(&eb1));
-    CUB(cudaEventRecord(eb0, m->stream));
-    LAUNCH(k_backtrack, (int)((W + 127) / 128), 128, 0, m->stream, a);
-    CUB(cudaEventRecord(eb1, m->stream));
+    CU(launch_tables(m, p0, d->d_x_keep, d->d_pleaf_keep, st, false));
+    BTArgs a{m->dev, p0.dev, d->d_arena, d->d_hdr, d->d_ell, d->d_x_keep, uniforms ? T.d_u : nullptr,
+             uniforms ? (long long)stride : (1LL << 40), d->F, n_samples, max_nodes, 0, n_samples, T.d_cnt, T.d_g, T.d_e,
+             T.d_t, T.d_p, T.d_st, T.d_stack, nullptr, 0, (unsigned long long)seed};
+    if (!d->ev[0]) for (int i = 0; i < 4; i++) CU(cudaEventCreate(&d->ev[i]));
+    CU(cudaEventRecord(d->ev[0], st));
+    LAUNCH(k_backtrack, (int)((W + 127) / 128), 128, 0, st, a);
+    CU(cudaEventRecord(d->ev[1], st));
     g_launches += 2;
-    CUB(cudaGetLastError());
-    CUB(cudaStreamSynchronize(m->stream));
-    { float ms = 0; cudaEventElapsedTime(&ms, eb0, eb1); d->last_bt_ms = ms; cudaEventDestroy(eb0); cudaEventDestroy(eb1); }
-    CUB(cudaMemcpy(node_count, d_cnt, W * 4, cudaMemcpyDeviceToHost));
-    CUB(cudaMemcpy(status, d_st, W * 4, cudaMemcpyDeviceToHost));
-    CUB(cudaMemcpy(gamma, d_g, W * max_nodes * 4, cudaMemcpyDeviceToHost));
-    CUB(cudaMemcpy(e, d_e, W * max_nodes * 4, cudaMemcpyDeviceToHost));
-    CUB(cudaMemcpy(t, d_t, W * max_nodes * 4, cudaMemcpyDeviceToHost));
-    CUB(cudaMemcpy(parent, d_p, W * max_nodes * 4, cudaMemcpyDeviceToHost));
-#undef CUB
-    cleanup();
+    rc = finish_walks(d, st, n_samples);
+    if (rc != WHALE_OK) return rc;
+    { float ms = 0; cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]); d->last_bt_ms = ms; d->ev_valid = false; }
+    if (total_nodes) *total_nodes = T.total_nodes;
+    return WHALE_OK;
+}
+
+// value-only DP keeping ℓ for a SUBSET of the families (the launch order is the given list): logpdf! for the families
+// whose sample uses this posterior draw
+static int32_t enqueue_keep_subset(whale_model* m, whale_data* D, const double* d_x, const int* d_famlist, int count, cudaStream_t st) {
+    if (count <= 0) return WHALE_OK;
+    if (!D->d_ell) CU(cudaMalloc((void**)&D->d_ell, std::max<uint64_t>(D->ell_total, 1) * sizeof(double)));
+    if (!m->attr_set) {
+#define SETATTR(NTV, MB) CU(cudaFuncSetAttribute(k_dp<NTV, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DP_VARIANTS(SETATTR)
+#undef SETATTR
+#define SETATTR(NTV, MB) CU(cudaFuncSetAttribute(k_dp_rev<NTV, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        REV_VARIANTS(SETATTR)
+#undef SETATTR
+        m->attr_set = true;
+    }
+    Plan& p0 = m->plan[0];
+    CU(launch_tables(m, p0, d_x, m->d_pleaf, st, false));
+    size_t smem = 0;
+    for (const Bin& b : D->bins[0]) smem = std::max(smem, b.smem);
+    DPArgs a{m->dev, p0.dev, D->d_arena, D->d_hdr, d_famlist, D->d_roff[0], D->d_out_fam + D->out_off[0], D->d_ell, 0, 0,
+             nullptr, nullptr, D->F, 0, 1, m->d_out};
+    const int NT = dp_nt(), MB = dp_minb();
+#define LAUNCHV(NTV, MBV) if (NT == NTV && MB == MBV) LAUNCH((k_dp<NTV, MBV>), count, NTV, smem, st, a, 0);
+    DP_VARIANTS(LAUNCHV)
+#undef LAUNCHV
+    g_launches++;
+    return WHALE_OK;
+}
+
+int32_t whale_track_sample(whale_model_t m, whale_data_t d, int32_t n_theta, const double* x, const double* p_leaf,
+                           int32_t n_samples, const int32_t* theta_index, const double* uniforms, int64_t stride,
+                           uint64_t seed, int32_t max_nodes, int64_t* total_nodes) {
+    if (!m || !d || !x) return fail(WHALE_ERR_ARG, "null argument");
+    if (d->m != m) return fail(WHALE_ERR_ARG, "data handle belongs to another model");
+    if (n_theta <= 0 || n_samples <= 0 || max_nodes <= 1 || (uniforms && stride <= 0)) return fail(WHALE_ERR_ARG, "n_theta, n_samples, stride and max_nodes must be positive");
+    CU(cudaSetDevice(m->device));
+    const int P = m->P, nn = m->nn, F = d->F, S = n_samples;
+    const long long W = (long long)F * S;
+    // group the (family, sample) pairs by posterior draw
+    std::vector<int> cnt(n_theta + 1, 0);
+    auto idx = [&](long long w) -> int { return theta_index ? theta_index[w] : (int)(w % S) % n_theta; };
+    for (long long w = 0; w < W; w++) {
+        const int j = idx(w);
+        if (j < 0 || j >= n_theta) return fail(WHALE_ERR_ARG, "theta_index out of range");
+        cnt[j + 1]++;
+    }
+    for (int j = 0; j < n_theta; j++) cnt[j + 1] += cnt[j];
+    std::vector<int2> pairs((size_t)W);
+    std::vector<int> fill(cnt.begin(), cnt.end() - 1), famlist((size_t)W), famoff(n_theta + 1, 0);
+    for (long long w = 0; w < W; w++) pairs[fill[idx(w)]++] = make_int2((int)(w / S), (int)(w % S));  // (family, sample), family-major
+    size_t nf = 0, maxgroup = 0;
+    for (int j = 0; j < n_theta; j++) {
+        famoff[j] = (int)nf;
+        for (int i = cnt[j]; i < cnt[j + 1]; i++)
+            if (i == cnt[j] || pairs[i].x != pairs[i - 1].x) famlist[nf++] = pairs[i].x;
+        maxgroup = std::max(maxgroup, (size_t)(cnt[j + 1] - cnt[j]));
+    }
+    famoff[n_theta] = (int)nf;
+    int32_t rc = ensure_tree_bufs(d, W, max_nodes, maxgroup);
+    if (rc != WHALE_OK) return rc;
+    auto& T = d->tb;
+    cudaStream_t st = m->stream;
+    if (uniforms) {
+        CU(grow_dev(&T.d_u, &T.cap_u, (size_t)W * stride));
+        CU(cudaMemcpyAsync(T.d_u, uniforms, (size_t)W * stride * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    CU(grow_dev(&T.d_xs, &T.cap_xs, (size_t)n_theta * P));
+    CU(cudaMemcpyAsync(T.d_xs, x, (size_t)n_theta * P * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (T.cap_pairs < (size_t)W) {
+        if (T.d_pairs) cudaFree(T.d_pairs);
+        if (T.d_famlist) cudaFree(T.d_famlist);
+        T.d_pairs = nullptr; T.d_famlist = nullptr; T.cap_pairs = 0;
+        CU(cudaMalloc((void**)&T.d_pairs, (size_t)W * sizeof(int2)));
+        CU(cudaMalloc((void**)&T.d_famlist, (size_t)W * sizeof(int)));
+        T.cap_pairs = (size_t)W;
+    }
+    CU(cudaMemcpyAsync(T.d_pairs, pairs.data(), (size_t)W * sizeof(int2), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(T.d_famlist, famlist.data(), nf * sizeof(int), cudaMemcpyHostToDevice, st));
+    std::vector<double> pl(nn, 0.0);
+    if (p_leaf) pl.assign(p_leaf, p_leaf + nn);
+    CU(cudaMemcpyAsync(m->d_pleaf, pl.data(), nn * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));  // the host vectors above go out of scope
+    if (!d->ev[0]) for (int i = 0; i < 4; i++) CU(cudaEventCreate(&d->ev[i]));
+    CU(cudaEventRecord(d->ev[0], st));
+    Plan& p0 = m->plan[0];
+    for (int j = 0; j < n_theta; j++) {
+        const int np = cnt[j + 1] - cnt[j];
+        if (np == 0) continue;
+        const double* d_xj = T.d_xs + (size_t)j * P;
+        // logpdf!(model(θ_j), ·) for the families that drew row j, then their walks — nothing returns to the host in between
+        rc = enqueue_keep_subset(m, d, d_xj, T.d_famlist + famoff[j], famoff[j + 1] - famoff[j], st);
+        if (rc != WHALE_OK) return rc;
+        BTArgs a{m->dev, p0.dev, d->d_arena, d->d_hdr, d->d_ell, d_xj, uniforms ? T.d_u : nullptr,
+                 uniforms ? (long long)stride : (1LL << 40), F, S, max_nodes, 0, S, T.d_cnt, T.d_g, T.d_e, T.d_t, T.d_p, T.d_st,
+                 T.d_stack, T.d_pairs + cnt[j], np, (unsigned long long)seed};
+        LAUNCH(k_backtrack, (np + 127) / 128, 128, 0, st, a);
+        g_launches++;
+    }
+    CU(cudaEventRecord(d->ev[1], st));
+    rc = finish_walks(d, st, S);
+    if (rc != WHALE_OK) return rc;
+    { float ms = 0; cudaEventElapsedTime(&ms, d->ev[0], d->ev[1]); d->last_bt_ms = ms; d->ev_valid = false; }
+    d->ell_valid = false;  // ℓ holds a mixture of draws
+    m->x_host_valid = false;
+    if (total_nodes) *total_nodes = T.total_nodes;
+    return WHALE_OK;
+}
+
+int32_t whale_trees_counts(whale_data_t d, int32_t* node_count, int32_t* status) {
+    if (!d) return fail(WHALE_ERR_ARG, "null argument");
+    if (!d->tb.valid) return fail(WHALE_ERR_STATE, "no backtracked trees on this handle");
+    if (node_count) memcpy(node_count, d->tb.h_cnt, (size_t)d->tb.W * 4);
+    if (status) memcpy(status, d->tb.h_st, (size_t)d->tb.W * 4);
+    return WHALE_OK;
+}
+
+// compact (γ, e, t, parent) rows of all walks in (family, sample) order: offsets[W+1] and total_nodes rows, in
+// library-owned pinned host memory (valid until the next backtracking call on this handle)
+int32_t whale_trees_view(whale_data_t d, const int64_t** offsets, const int32_t** nodes4, int64_t* total_nodes) {
+    if (!d) return fail(WHALE_ERR_ARG, "null argument");
+    auto& T = d->tb;
+    if (!T.valid) return fail(WHALE_ERR_STATE, "no backtracked trees on this handle");
+    whale_model* m = d->m;
+    CU(cudaSetDevice(m->device));
+    if (!T.packed_valid) {
+        const size_t W = (size_t)T.W;
+        CU(grow_pinned(&T.h_off, &T.hcap_off, W + 1));
+        long long o = 0;
+        for (size_t w = 0; w < W; w++) { T.h_off[w] = o; o += T.h_cnt[w]; }
+        T.h_off[W] = o;
+        CU(grow_dev(&T.d_off, &T.cap_off, W + 1));
+        CU(grow_dev(&T.d_packed, &T.cap_packed, (size_t)std::max<long long>(o, 1)));
+        CU(grow_pinned(&T.h_packed, &T.hcap_packed, (size_t)std::max<long long>(o, 1) * 4));
+        cudaStream_t st = m->stream;
+        CU(cudaMemcpyAsync(T.d_off, T.h_off, (W + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+        LAUNCH(k_tree_pack, (int)((W * 32 + 127) / 128), 128, 0, st, T.d_cnt, T.d_off, T.d_g, T.d_e, T.d_t, T.d_p, T.max_nodes,
+               (long long)W, T.d_packed);
+        g_launches++;
+        CU(cudaMemcpyAsync(T.h_packed, T.d_packed, (size_t)o * sizeof(int4), cudaMemcpyDeviceToHost, st));
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(st));
+        T.packed_valid = true;
+    }
+    static_assert(sizeof(long long) == sizeof(int64_t), "offsets are int64");
+    if (offsets) *offsets = reinterpret_cast<const int64_t*>(T.h_off);
+    if (nodes4) *nodes4 = T.h_packed;
+    if (total_nodes) *total_nodes = T.total_nodes;
+    return WHALE_OK;
+}
+
+int32_t whale_trees_get(whale_data_t d, int64_t* offsets, int32_t* nodes4) {
+    const int64_t* o = nullptr;
+    const int32_t* n = nullptr;
+    int64_t tot = 0;
+    int32_t rc = whale_trees_view(d, &o, &n, &tot);
+    if (rc != WHALE_OK) return rc;
+    if (offsets) memcpy(offsets, o, ((size_t)d->tb.W + 1) * sizeof(int64_t));
+    if (nodes4) memcpy(nodes4, n, (size_t)tot * 16);
+    return WHALE_OK;
+}
+
+// sumtrees on the device: identity hash of every tree, then per family the distinct trees with counts and first samples
+int32_t whale_trees_summary(whale_data_t d, int32_t* n_distinct, uint64_t* hash, int32_t* count, int32_t* first,
+                            uint64_t* tree_hash) {
+    if (!d || !n_distinct || !hash || !count || !first) return fail(WHALE_ERR_ARG, "null argument");
+    auto& T = d->tb;
+    if (!T.valid) return fail(WHALE_ERR_STATE, "no backtracked trees on this handle");
+    whale_model* m = d->m;
+    CU(cudaSetDevice(m->device));
+    const size_t W = (size_t)T.W;
+    const int S = T.S, F = (int)(W / S);
+    int Spad = 1;
+    while (Spad < S) Spad <<= 1;
+    const size_t smem = (size_t)Spad * 12;
+    if (smem > 200 * 1024) return fail(WHALE_ERR_CAPACITY, "%d samples per family: summarise on the host", S);
+    if (W > T.cap_hash) {
+        size_t c[4] = {T.cap_hash, T.cap_hash, T.cap_hash, T.cap_hash};
+        CU(grow_dev(&T.d_hash, &c[0], W)); CU(grow_dev(&T.d_dh, &c[1], W)); CU(grow_dev(&T.d_dc, &c[2], W)); CU(grow_dev(&T.d_df, &c[3], W));
+        T.cap_hash = std::min(std::min(c[0], c[1]), std::min(c[2], c[3]));
+    }
+    CU(grow_dev(&T.d_nd, &T.cap_nd, (size_t)F));
+    CU(grow_dev(&T.d_stack, &T.cap_stack, W * (size_t)T.max_nodes));  // scratch of the hash kernel
+    cudaStream_t st = m->stream;
+    HashArgs a{T.d_cnt, T.d_g, T.d_e, T.d_p, T.d_st, T.d_stack, T.d_hash, (long long)W, T.max_nodes};
+    LAUNCH(k_tree_hash, (int)((W + 127) / 128), 128, 0, st, a);
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_tree_dedup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH(k_tree_dedup, F, 256, smem, st, T.d_hash, S, Spad, T.d_nd, T.d_dh, T.d_dc, T.d_df);
+    g_launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpy(n_distinct, T.d_nd, (size_t)F * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(hash, T.d_dh, W * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(count, T.d_dc, W * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(first, T.d_df, W * 4, cudaMemcpyDeviceToHost));
+    if (tree_hash) CU(cudaMemcpy(tree_hash, T.d_hash, W * 8, cudaMemcpyDeviceToHost));
     return WHALE_OK;
 }
 

@@ -25,7 +25,8 @@ SYMBOLS = ["whale_version", "whale_last_error", "whale_device_count", "whale_set
            "whale_work_estimate", "whale_last_kernel_ms", "whale_last_phase_cycles", "whale_last_node_cycles", "whale_last_family_cycles", "whale_last_tables_cycles", "whale_last_backtrack_ms", "whale_fp64_peak",
            "whale_data_grad_mode", "whale_data_grad_passes", "whale_set_devices", "whale_multi_create", "whale_multi_destroy",
            "whale_multi_ndev", "whale_multi_shard_size", "whale_multi_logpdf_grad", "whale_peer_export", "whale_peer_import",
-           "whale_peer_ready"]
+           "whale_peer_ready", "whale_backtrack_device", "whale_track_sample", "whale_trees_counts", "whale_trees_view",
+           "whale_trees_get", "whale_trees_summary"]
 
 
 class ModelDesc(C.Structure):
@@ -101,6 +102,14 @@ class Lib:
         L.whale_last_node_cycles.argtypes = [vp, f64p, f64p, C.c_int32]
         L.whale_last_family_cycles.argtypes = [vp, f64p]
         L.whale_last_backtrack_ms.argtypes = [vp, f64p]
+        u64p = C.POINTER(C.c_uint64)
+        L.whale_backtrack_device.argtypes = [vp, vp, C.c_int32, f64p, C.c_int64, C.c_uint64, C.c_int32, i64p]
+        L.whale_track_sample.argtypes = [vp, vp, C.c_int32, f64p, f64p, C.c_int32, i32p, f64p, C.c_int64, C.c_uint64,
+                                         C.c_int32, i64p]
+        L.whale_trees_counts.argtypes = [vp, i32p, i32p]
+        L.whale_trees_view.argtypes = [vp, C.POINTER(i64p), C.POINTER(i32p), i64p]
+        L.whale_trees_get.argtypes = [vp, i64p, i32p]
+        L.whale_trees_summary.argtypes = [vp, i32p, u64p, i32p, i32p, u64p]
         L.whale_peer_export.argtypes = [vp, C.c_int32, C.c_int32, vp]
         L.whale_peer_import.argtypes = [vp, C.c_int32, vp]
         L.whale_peer_ready.argtypes = [vp]
@@ -257,6 +266,60 @@ class Lib:
         if got != n:
             raise WhaleCudaError(2, "arena dump failed")
         return buf
+
+    def backtrack_device(self, mh, dh, n_samples, uniforms=None, seed=0, max_nodes=512) -> int:
+        """whale_backtrack_device: walks from the kept ℓ, results stay on the device; returns the total node count."""
+        tot = C.c_int64()
+        if uniforms is not None:
+            U = np.ascontiguousarray(uniforms, np.float64)
+            self.check(self.L.whale_backtrack_device(mh, dh, n_samples, _ptr(U, f64p), U.shape[-1], 0, max_nodes, C.byref(tot)))
+        else:
+            self.check(self.L.whale_backtrack_device(mh, dh, n_samples, None, 0, seed, max_nodes, C.byref(tot)))
+        return tot.value
+
+    def track_sample(self, mh, dh, xs, p_leaf, n_samples, theta_index=None, uniforms=None, seed=0, max_nodes=512) -> int:
+        """whale_track_sample: per-(family, sample) posterior rows; results stay on the device; returns the total node count."""
+        X = np.ascontiguousarray(xs, np.float64)
+        pl = np.ascontiguousarray(p_leaf, np.float64)
+        ti = None if theta_index is None else np.ascontiguousarray(theta_index, np.int32)
+        tot = C.c_int64()
+        if uniforms is not None:
+            U = np.ascontiguousarray(uniforms, np.float64)
+            up, stride = _ptr(U, f64p), U.shape[-1]
+        else:
+            up, stride = None, 0
+        self.check(self.L.whale_track_sample(mh, dh, X.shape[0], _ptr(X, f64p), _ptr(pl, f64p), n_samples,
+                                             None if ti is None else _ptr(ti, i32p), up, stride, seed, max_nodes, C.byref(tot)))
+        return tot.value
+
+    def trees_counts(self, dh, W):
+        cnt, st = np.zeros(W, np.int32), np.zeros(W, np.int32)
+        self.check(self.L.whale_trees_counts(dh, _ptr(cnt, i32p), _ptr(st, i32p)))
+        return cnt, st
+
+    def trees_get(self, dh, W, total):
+        """Compact trees: (offsets[W+1], nodes[total, 4]) copied out of the library's pinned buffer."""
+        off = np.zeros(W + 1, np.int64)
+        nodes = np.zeros((max(total, 1), 4), np.int32)
+        self.check(self.L.whale_trees_get(dh, _ptr(off, i64p), _ptr(nodes, i32p)))
+        return off, nodes[:total]
+
+    def trees_view(self, dh, W):
+        """Zero-copy views of the library-owned pinned buffers (valid until the next backtracking call)."""
+        po, pn, tot = i64p(), i32p(), C.c_int64()
+        self.check(self.L.whale_trees_view(dh, C.byref(po), C.byref(pn), C.byref(tot)))
+        off = np.ctypeslib.as_array(po, shape=(W + 1,))
+        nodes = np.ctypeslib.as_array(pn, shape=(max(tot.value, 1), 4))[:tot.value]
+        return off, nodes
+
+    def trees_summary(self, dh, F, S, with_tree_hash=False):
+        nd = np.zeros(F, np.int32)
+        h, c, f1 = np.zeros(F * S, np.uint64), np.zeros(F * S, np.int32), np.zeros(F * S, np.int32)
+        th = np.zeros(F * S, np.uint64) if with_tree_hash else None
+        u64p = C.POINTER(C.c_uint64)
+        self.check(self.L.whale_trees_summary(dh, _ptr(nd, i32p), _ptr(h, u64p), _ptr(c, i32p), _ptr(f1, i32p),
+                                              _ptr(th, u64p) if with_tree_hash else None))
+        return nd, h.reshape(F, S), c.reshape(F, S), f1.reshape(F, S), (th.reshape(F, S) if with_tree_hash else None)
 
     def backtrack(self, mh, dh, n_samples, uniforms, max_nodes=512):
         """whale_backtrack: uniforms [F, n_samples, stride]; returns (counts[F,S], status[F,S], nodes[F,S,max_nodes,4])
