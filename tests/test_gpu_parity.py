@@ -302,3 +302,10 @@ def test_track_sample_and_summary(L):
     """src/track.jl:47-63 with per-(family, sample) posterior rows, compact tree transfer, device tree identity / sumtrees."""
     from conftest import track_sample_and_summary
     track_sample_and_summary(L, n_samples=64, n_theta=7)
+
+
+def test_c4_shape_16_families(L, tmp_path):
+    """BASELINE config 3 shape at 16 families (~2,000 clades each, 30 taxa + 5 WGDs): constant rates (P = 8) and
+    branch-wise rates (P = 124), both through the reverse-mode kernel, against the oracle."""
+    from conftest import c4_shape_vs_oracle
+    c4_shape_vs_oracle(tmp_path, n_fam=16)

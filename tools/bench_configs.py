@@ -70,21 +70,28 @@ def main():
                        tree=synth.c4_species_tree(), **synth.C4_FAMILY)
     q = [0.2, 0.1, 0.2, 0.1, 0.2]
     w = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=q, eta=0.67), newick.readnw(nws), 0.05)
-    ccd = W.read_ale(d, w)
+    t0 = time.perf_counter()
+    ccd = W.read_ale_native(d, w)
     mh, dh = _data_handle(w, ccd)
+    out["C4_ingest_pack_s"] = round(time.perf_counter() - t0, 2)
     x0 = w.x()
     xs = x0[None, :] * np.exp(0.03 * rng.standard_normal((args.reps + 3, len(x0))))
     xs[:, 2:] = np.clip(xs[:, 2:], 1e-3, 1 - 1e-3)
     out["C4_constant"] = dict(rate(L, mh, dh, w, xs, args.reps, len(ccd)), P=int(w.n_params),
-                              clades_median=int(np.median([len(x.nleaf) for x in ccd])))
+                              clades_median=int(np.median(ccd.n_clades)),
+                              grad_mode="reverse" if L.L.whale_data_grad_mode(dh) == 1 else "forward",
+                              gradient_passes=int(L.L.whale_data_grad_passes(dh)), arena_bytes=int(L.L.whale_data_arena_bytes(dh)))
+    L.L.whale_data_destroy(dh)
     rb = W.DLWGD(lam=list(rng.normal(np.log(0.15), 0.3, 59)), mu=list(rng.normal(np.log(0.15), 0.3, 59)), q=q, eta=0.67)
     wb = W.WhaleModel(rb, newick.readnw(nws), 0.05)
-    ccdb = W.read_ale(d, wb)
+    ccdb = W.read_ale_native(d, wb)
     mh, dh = _data_handle(wb, ccdb)
     x0 = wb.x()
     xs = x0[None, :] + 0.02 * rng.standard_normal((max(args.reps // 3, 2) + 3, len(x0)))
     xs[:, -6:] = np.clip(xs[:, -6:], 1e-3, 1 - 1e-3)
-    out["C4_branchwise"] = dict(rate(L, mh, dh, wb, xs, max(args.reps // 3, 2), len(ccdb)), P=int(wb.n_params))
+    out["C4_branchwise"] = dict(rate(L, mh, dh, wb, xs, max(args.reps // 3, 2), len(ccdb)), P=int(wb.n_params),
+                                grad_mode="reverse" if L.L.whale_data_grad_mode(dh) == 1 else "forward",
+                                gradient_passes=int(L.L.whale_data_grad_passes(dh)))
     print(json.dumps(out))
 
 
