@@ -258,13 +258,13 @@ def c3_leg(args, L, wlib, rank, world, d3, n3, gen3_s, flush, stream):
         ev[i][1].record()
     torch.cuda.synchronize()
     total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    last = OUT.cpu().numpy().copy()
     kms = np.zeros((3, 3))
     for i in range(3):
         flush.zero_()
         step(Wm + i, wlib.WANT_GRAD | wlib.PROFILE)
         torch.cuda.synchronize()
         kms[i] = L.last_kernel_ms(dh)
-    last = OUT.cpu().numpy().copy()
     pin_x = torch.empty(P, dtype=torch.float64).pin_memory()
     pin_o = torch.empty(1 + P, dtype=torch.float64).pin_memory()
     Xd = torch.empty(P, device="cuda", dtype=torch.float64)
@@ -408,6 +408,7 @@ def main():
         dist.barrier()
     wall = time.perf_counter() - wall0
     launches = L.L.whale_launch_count() - launches0
+    last = OUT.cpu().numpy().copy()  # result of the last timed step (compared with the end-to-end leg's below)
     NK = min(K, 20)
     kms = np.zeros((NK, 3))
     for i in range(NK):
@@ -419,7 +420,6 @@ def main():
     tables_cycles = L.last_tables_cycles(mh, True)
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     total_ms = float(step_ms.sum())
-    last = OUT.cpu().numpy().copy()
     # keep the GPU under the same load a little longer if the region was too short for nvidia-smi to sample
     # (rank-local work only: the number of rounds differs between ranks, so no collective may be issued here)
     t_probe = time.perf_counter()

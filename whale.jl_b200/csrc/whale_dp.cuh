@@ -74,6 +74,39 @@ __device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_g
 __device__ __forceinline__ void stage_wait_prev() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 #endif
 
+// ---- bulk asynchronous copies (cp.async.bulk: the copy engine, one issuing thread) completed on an mbarrier ----
+#ifdef WHALE_EMU
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) { *bar = 0; (void)count; }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long*, unsigned) {}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void mbar_wait(unsigned long long*, unsigned) { __syncthreads(); }  // orders the fibers behind the issuer
+__device__ __forceinline__ void fence_proxy_async() {}
+#else
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WHALE_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WHALE_MBAR_DONE;\n"
+        "bra WHALE_MBAR_WAIT;\n"
+        "WHALE_MBAR_DONE:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
 #ifdef WHALE_EMU
 #define SHFL_DOWN(v, d) emu::shfl_down(v, d)
 #define WARP_ANY(p) emu::warp_any(p)

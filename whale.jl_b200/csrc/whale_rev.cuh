@@ -308,7 +308,10 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
     double* zloc = reinterpret_cast<double*>(s_rrec + nn);
     double* s_red = zloc + 8 * nn;                          // [NW*8] block_sum scratch
     double* s_res = s_red + NW * 8;                         // [8] block_sum results
-    unsigned char* dyn = reinterpret_cast<unsigned char*>(s_res + 8);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_res + 8);  // [2] mbarrier of the list prefetches
+    unsigned char* dyn = reinterpret_cast<unsigned char*>(s_bar + 2);
+    if (tid == 0) mbar_init(s_bar, 1);
+    unsigned s2_phase = 0;
     for (int i = tid; i < nn; i += NT) {
         s_kind[i] = M.kind[i]; s_nsl[i] = M.nsl[i]; s_ch0[i] = M.child0[i]; s_ch1[i] = M.child1[i];
         s_K[i] = PR.K[i]; s_toff[i] = PR.toff[i]; s_ltoff[i] = A.PL.toff[i];
@@ -341,7 +344,10 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
         double* rows = reinterpret_cast<double*>(dyn);
         double* scr = rows + rows_len;
         unsigned char* stage = reinterpret_cast<unsigned char*>(scr + scr_len);
-        unsigned char* leaf_area = stage + stage_bytes;  // phase A only; the backward pass reuses it:
+        unsigned char* stage2 = stage + stage_bytes;     // row-1 / root lists, prefetched one node ahead (bulk copies)
+        const uint32_t stage2_bytes = Rp->stage2_bytes;
+        const bool staged2 = stage2_bytes != 0;
+        unsigned char* leaf_area = stage2 + stage2_bytes;  // phase A only; the backward pass reuses it:
         const size_t leaf_area_bytes = (size_t)leafmax * sizeof(double) + leaf_stage;
         double* arows = reinterpret_cast<double*>(leaf_area);
         double* hb = arows + Rp->arows_len;  // [3][hlen]
@@ -359,25 +365,78 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
         const NodeRec* const nrec = s_nrec;
         const RevRec* const rrec = s_rrec;
         double* const hist = A.hist + (size_t)(A.slot0 + blockIdx.x) * A.hist_stride;
-        // The row-1 / root lists are read once, in place (global memory through L1): pull a node's lists into L1 one node
-        // ahead, while the current node's slices run, so those reads do not pay an L2 round trip per dependent step
-        auto pf_range = [&](const unsigned char* p, uint32_t bytes, const unsigned char* lim) {
-            if (p + bytes > lim) bytes = (uint32_t)(lim - p);
-            for (uint32_t o = tid * 128u; o < bytes; o += NT * 128u) PREFETCH_L1(p + o);
-        };
-        auto pf_fwd = [&](int e) {  // forward lists of node e: [dptr .. cmp] words, [dents .. tents] entries
+        // The row-1 / root lists of a node (read once per evaluation) are brought into shared memory by the copy engine
+        // one node ahead — thread 0 issues cp.async.bulk copies that complete on an mbarrier while the current node's
+        // slices run.  A request lists up to six contiguous segments of the family's blobs; the consumer derives the same
+        // layout.  stage2_bytes == 0 (lists too long: large CCDs): the segments are read in place from global memory.
+        // (segment sizes are recomputed from the node records on both sides: scalars only, nothing indexed dynamically)
+        struct Lay { uint32_t a, b, c, d, e, f; };  // byte sizes of the (up to six) segments, in order
+        auto p4 = [](uint32_t w) -> uint32_t { return ((w + 3u) & ~3u) * 4u; };
+        auto fwd_lay = [&](int e) -> Lay {  // forward: [dptr] [tptr|lossF|lossG|lev] [dents] [tents]
             const NodeRec& Q = nrec[e];
-            pf_range(blob + (size_t)Q.dptr_off * 4, (Q.tptr_off - Q.dptr_off + 4 * Q.C + nlev + 8) * 4, blob + blob_bytes);
-            pf_range(blob + (size_t)Q.dent_off * 16, (Q.tent_off + Q.ntent - Q.dent_off) * 16, blob + blob_bytes);
+            const int kd = s_kind[e];
+            Lay y;
+            y.a = kd != WHALE_INTERNAL ? p4(Q.C + 1) : 0u;
+            y.b = kd != WHALE_WGD ? p4(3 * Q.C + 1 + (kd == WHALE_ROOT ? nlev + 1 : 0)) : 0u;
+            y.c = kd != WHALE_INTERNAL ? Q.ndent * 16u : 0u;
+            y.d = kd != WHALE_WGD ? Q.ntent * 16u : 0u;
+            y.e = y.f = 0u;
+            return y;
         };
-        auto pf_bwd = [&](int e) {  // transposed lists of node e
+        auto bwd_lay = [&](int e) -> Lay {  // transposed: [bptr] [sF|upF] [sG|upG] [bents] [sFents] [sGents]
             const RevRec& Q = rrec[e];
-            const uint32_t wend = Q.sG_off > Q.bslot_off ? Q.sG_off + 2 * nrec[e].C + 2 : Q.bslot_off + 2 * Q.nbslots;
-            pf_range(rblob + (size_t)Q.bptr_off * 4, (wend - Q.bptr_off) * 4, rblob + rblob_bytes);
-            pf_range(rblob + (size_t)Q.bent_off * 16, (Q.nbent + Q.nsFent + Q.nsGent) * 16, rblob + rblob_bytes);
+            const int kd = s_kind[e];
+            Lay y;
+            y.a = kd != WHALE_INTERNAL ? p4(nrec[e].C + 1) : 0u;
+            y.b = kd != WHALE_WGD ? p4(2 * nrec[s_ch0[e]].C + 1) : 0u;
+            y.c = kd != WHALE_WGD ? p4(2 * nrec[s_ch1[e]].C + 1) : 0u;
+            y.d = kd != WHALE_INTERNAL ? Q.nbent * 16u : 0u;
+            y.e = kd != WHALE_WGD ? Q.nsFent * 16u : 0u;
+            y.f = kd != WHALE_WGD ? Q.nsGent * 16u : 0u;
+            return y;
         };
-        if (M.ninner > 0) pf_fwd(M.inner[0]);
-
+        // requests must follow a barrier after which nobody reads the previous contents of stage2
+        auto s2_copy = [&](uint32_t& off, const unsigned char* src, uint32_t bytes) {
+            if (bytes) bulk_g2s(stage2 + off, src, bytes, s_bar);
+            off += bytes;
+        };
+        auto s2_request_fwd = [&](int e) {
+            if (!staged2 || tid != 0) return;
+            const Lay y = fwd_lay(e);
+            const NodeRec& Q = nrec[e];
+            fence_proxy_async();
+            mbar_expect_tx(s_bar, y.a + y.b + y.c + y.d);
+            uint32_t off = 0;
+            s2_copy(off, blob + (size_t)Q.dptr_off * 4, y.a);
+            s2_copy(off, blob + (size_t)Q.tptr_off * 4, y.b);
+            s2_copy(off, blob + (size_t)Q.dent_off * 16, y.c);
+            s2_copy(off, blob + (size_t)Q.tent_off * 16, y.d);
+        };
+        auto s2_request_bwd = [&](int e) {
+            if (!staged2 || tid != 0) return;
+            const Lay y = bwd_lay(e);
+            const RevRec& Q = rrec[e];
+            fence_proxy_async();
+            mbar_expect_tx(s_bar, y.a + y.b + y.c + y.d + y.e + y.f);
+            uint32_t off = 0;
+            s2_copy(off, rblob + (size_t)Q.bptr_off * 4, y.a);
+            s2_copy(off, rblob + (size_t)Q.sF_off * 4, y.b);
+            s2_copy(off, rblob + (size_t)Q.sG_off * 4, y.c);
+            s2_copy(off, rblob + (size_t)Q.bent_off * 16, y.d);
+            s2_copy(off, rblob + (size_t)Q.sFent_off * 16, y.e);
+            s2_copy(off, rblob + (size_t)Q.sGent_off * 16, y.f);
+        };
+        auto s2_wait = [&]() {
+            if (!staged2) return;
+            mbar_wait(s_bar, s2_phase);
+            s2_phase ^= 1u;
+        };
+        auto next_fwd = [&](int oi) -> int { for (int j = oi + 1; j < M.ninner; j++) if (nrec[M.inner[j]].C) return j; return -1; };
+        auto next_bwd = [&](int oi) -> int { for (int j = oi - 1; j >= 0; j--) if (nrec[M.inner[j]].C) return j; return -1; };
+        {
+            const int j0 = next_fwd(-1);
+            if (j0 >= 0) s2_request_fwd(M.inner[j0]);
+        }
         const long long tcA = CLOCK64();
         // ================= phase A: leaf branches (as in k_dp, hybrid plan: value + own λ, μ) =================
         for (int li = warp; li < M.nleafnodes; li += NW) {
@@ -480,10 +539,12 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
             const Ent* s_dents = ents + R.dent_off;
             const Slot* s_slots = reinterpret_cast<const Slot*>(words + R.slot_off);
             const double2* s_pp = PR.pp + s_toff[e];
-            const uint32_t* g_dptr = words + R.dptr_off;
-            const uint32_t* g_tptr = words + R.tptr_off;
-            const Ent* g_dents = ents + R.dent_off;
-            const Ent* g_tents = ents + R.tent_off;
+            // row-1 / root lists: the segments requested one node ahead (see fwd_segs for their order)
+            const Lay ly = fwd_lay(e);
+            const uint32_t* g_dptr = staged2 ? reinterpret_cast<const uint32_t*>(stage2) : words + R.dptr_off;
+            const uint32_t* g_tptr = staged2 ? reinterpret_cast<const uint32_t*>(stage2 + ly.a) : words + R.tptr_off;
+            const Ent* g_dents = staged2 ? reinterpret_cast<const Ent*>(stage2 + ly.a + ly.b) : ents + R.dent_off;
+            const Ent* g_tents = staged2 ? reinterpret_cast<const Ent*>(stage2 + ly.a + ly.b + ly.c) : ents + R.tent_off;
             if (staged && kind != WHALE_ROOT) {
                 uint4* st4 = reinterpret_cast<uint4*>(stage);
                 copy16(st4, reinterpret_cast<const uint4*>(s_dents), nd16, tid, NT);
@@ -494,10 +555,11 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
                 s_pp = reinterpret_cast<const double2*>(st4 + nd16 + sl16);
             }
             double* cur = (n & 1) ? scr : fin;
+            s2_wait();  // this node's row-1 lists have landed
             if (kind == WHALE_WGD) {  // q·Σ p ℓ_f[γ1]ℓ_f[γ2] + (1−q+2qϵ_f)·ℓ_f[γ]   src/core.jl:103-119,187-199
                 const double cx0 = PR.cx[e * KmaxR], cy0 = PR.cy[e * KmaxR];
                 for (int c = tid; c < C; c += NT) {
-                    const double s0 = vsum<true>(g_dents, g_dptr[c], g_dptr[c + 1], 1u, finF, sF, finF, sF);
+                    const double s0 = vsum<false>(g_dents, g_dptr[c], g_dptr[c + 1], 1u, finF, sF, finF, sF);
                     cur[c] = fma(cy0, s0, cx0 * finF[c * sF]);
                 }
             } else {
@@ -508,19 +570,22 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
                 const int32_t* g_lossG = g_lossF + C;
                 if (kind == WHALE_INTERNAL) {  // Πspeciation + Πloss  src/core.jl:160-176
                     for (int c = tid; c < C; c += NT) {
-                        const double s0 = vsum<true>(g_tents, g_tptr[c], g_tptr[c + 1], 1u, finF, sF, finG, sG);
+                        const double s0 = vsum<false>(g_tents, g_tptr[c], g_tptr[c + 1], 1u, finF, sF, finG, sG);
                         const int lf = g_lossF[c], lg = g_lossG[c];
                         const double l0 = (lf >= 0 ? finF[lf * sF] : 0.0) * eg0 + (lg >= 0 ? finG[lg * sG] : 0.0) * ef0;
                         cur[c] = s0 + l0;
                     }
                 } else {  // root (src/core.jl:130-158): clades ascending in size, one level at a time
-                    pf_bwd(e);
                     const double cx0 = PR.cx[e * KmaxR], cy0 = PR.cy[e * KmaxR];
                     const uint32_t* g_lev = reinterpret_cast<const uint32_t*>(g_lossG + C);
                     for (uint32_t L = 0; L < nlev; L++) {
                         const int c0 = (int)g_lev[L], c1 = (int)g_lev[L + 1];
                         int glog = 0;
-                        while (glog < 4 && ((c1 - c0) << (glog + 1)) <= 16) glog++;
+                        {   // team size from the level's shape only: as many lanes per cell as the CTA has, while a lane
+                            // still gets at least two terms
+                            const uint32_t nt_ = (g_dptr[c1] - g_dptr[c0]) + (g_tptr[c1] - g_tptr[c0]);
+                            while (glog < 5 && ((c1 - c0) << (glog + 1)) <= NT && (2u << glog) * (uint32_t)(c1 - c0) <= nt_) glog++;
+                        }
                         const int G = 1 << glog;
                         const int lanes = (c1 - c0) << glog;
                         for (int ub = 0; ub < lanes; ub += NT) {  // uniform trip count: the shuffles need whole warps
@@ -529,8 +594,8 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
                             const bool valid = u < lanes;
                             double v = 0.0;
                             if (valid) {
-                                const double a0 = vsum<true>(g_dents, g_dptr[c] + j, g_dptr[c + 1], (uint32_t)G, fin, 1, fin, 1);
-                                const double b0 = vsum<true>(g_tents, g_tptr[c] + j, g_tptr[c + 1], (uint32_t)G, finF, sF, finG, sG);
+                                const double a0 = vsum<false>(g_dents, g_dptr[c] + j, g_dptr[c + 1], (uint32_t)G, fin, 1, fin, 1);
+                                const double b0 = vsum<false>(g_tents, g_tptr[c] + j, g_tptr[c + 1], (uint32_t)G, finF, sF, finG, sG);
                                 v = fma(cx0, a0, cy0 * b0);
                             }
                             for (int step = 1; step < G; step <<= 1) v += SHFL_DOWN(v, step);
@@ -542,6 +607,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
                         }
                         __syncthreads();
                     }
+                    s2_request_bwd(e);  // the root's transposed lists, for the backward pass
                     acc_froot += CLOCK64() - tn0;
                     continue;
                 }
@@ -549,7 +615,10 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
             stage_wait();
             __syncthreads();  // row 1 and the staged lists are visible
             const long long ts0 = CLOCK64();
-            if (oi + 1 < M.ninner) pf_fwd(M.inner[oi + 1]);
+            {   // row 1 is done: the next node's row-1 lists stream in while this node's slices run
+                const int jn = next_fwd(oi);
+                if (jn >= 0) s2_request_fwd(M.inner[jn]);
+            }
             run_slices_fwd1<NT>(n, Cp, fin, scr, cur, s_slots, (int)R.nslots, s_dents, s_pp, hrow, tid);
             __syncthreads();  // the last row is complete; the staging buffer may be reused
             const long long ts1 = CLOCK64();
@@ -563,6 +632,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
         const double Lv = rows[s_roff[root] + CR - 1];
         if (!(Lv > 0.0)) {  // L <= 0 -> −Inf, zero gradient (src/core.jl:36)
             for (int k = tid; k < KR; k += NT) A.out_fam[(size_t)fam * KR + k] = k == 0 ? -dinf() : 0.0;
+            s2_wait();  // (the root's transposed lists were requested: keep the barrier's phase in step)
             continue;
         }
         // per-node local adjoints: zloc[e] = {λ̄, μ̄, ϵ̄⁰ (slices), c̄x, c̄y (WGD, root), ϵ̄ⁿ of child 0, ϵ̄ⁿ of child 1, -}
@@ -588,7 +658,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
             const int Kc = s_K[ch];
             double* Ach = isleaf ? nullptr : arows + s_aoff[ch];
             for (int c = tid; c < Cc; c += NT) {
-                const double s = vsum<true>(sent, sptr[c], sptr[c + 1], 1u, Abar, 1, Vo, sVo);
+                const double s = vsum<false>(sent, sptr[c], sptr[c + 1], 1u, Abar, 1, Vo, sVo);
                 const double au = Abar[up[c]];
                 const double v = Vch[c * sVch];
                 const double ab = coef * fma(au, eps_o, s);
@@ -617,8 +687,16 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
             const double ef0 = PR.eps[s_toff[f] + s_nsl[f] * s_K[f]], eg0 = PR.eps[s_toff[g] + s_nsl[g] * s_K[g]];
             const uint32_t* g_tptr = words + R.tptr_off;
             const uint32_t* g_lev = g_tptr + 3 * CR + 1;
-            const uint32_t* bptr = rwords + RR.bptr_off;
-            const Ent* bent = rents + RR.bent_off;
+            const Lay ly = bwd_lay(e);  // [bptr] [sF|upF] [sG|upG] [bents] [sFents] [sGents]
+            const unsigned char* sp0 = staged2 ? stage2 : rblob + (size_t)RR.bptr_off * 4;
+            const unsigned char* sp1 = staged2 ? stage2 + ly.a : rblob + (size_t)RR.sF_off * 4;
+            const unsigned char* sp2 = staged2 ? stage2 + ly.a + ly.b : rblob + (size_t)RR.sG_off * 4;
+            const unsigned char* sp3 = staged2 ? stage2 + ly.a + ly.b + ly.c : rblob + (size_t)RR.bent_off * 16;
+            const unsigned char* sp4 = staged2 ? stage2 + ly.a + ly.b + ly.c + ly.d : rblob + (size_t)RR.sFent_off * 16;
+            const unsigned char* sp5 = staged2 ? stage2 + ly.a + ly.b + ly.c + ly.d + ly.e : rblob + (size_t)RR.sGent_off * 16;
+            s2_wait();
+            const uint32_t* bptr = reinterpret_cast<const uint32_t*>(sp0);
+            const Ent* bent = reinterpret_cast<const Ent*>(sp3);
             const double seed = 1.0 / Lv;  // d log L / dL
             double acx = 0.0;
             for (int L = (int)nlev - 1; L >= 0; L--) {
@@ -633,7 +711,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
                     const int c = c0 + (u >> glog), j = u & (G - 1);
                     const bool valid = u < lanes;
                     double v = 0.0;
-                    if (valid) v = vsum<true>(bent, bptr[c] + j, bptr[c + 1], (uint32_t)G, Ab, 1, fin, 1);
+                    if (valid) v = vsum<false>(bent, bptr[c] + j, bptr[c + 1], (uint32_t)G, Ab, 1, fin, 1);
                     for (int step = 1; step < G; step <<= 1) v += SHFL_DOWN(v, step);
                     if (valid && j == 0) {
                         Ab[c] = fma(cx0, v, c == CR - 1 ? seed : 0.0);
@@ -644,8 +722,10 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
             }
             double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // Σ V_F·s_F, ū_G, lF1, lF2, (unused), ū_F, lG1, lG2
             double dummy = 0.0;
-            spec_down(f, rwords + RR.sF_off, rents + RR.sFent_off, Ab, finF, sF, finG, sG, eg0, cy0, a[0], a[1], a[2], a[3]);
-            spec_down(g, rwords + RR.sG_off, rents + RR.sGent_off, Ab, finG, sG, finF, sF, ef0, cy0, dummy, a[5], a[6], a[7]);
+            spec_down(f, reinterpret_cast<const uint32_t*>(sp1), reinterpret_cast<const Ent*>(sp4), Ab, finF, sF, finG, sG, eg0,
+                      cy0, a[0], a[1], a[2], a[3]);
+            spec_down(g, reinterpret_cast<const uint32_t*>(sp2), reinterpret_cast<const Ent*>(sp5), Ab, finG, sG, finF, sF, ef0,
+                      cy0, dummy, a[5], a[6], a[7]);
             a[4] = acx;
             block_sum<8, NT>(a, s_red, s_res, false, tid);
             if (tid == 0) {
@@ -659,6 +739,10 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
                 if (s_kind[g] == WHALE_LEAF) { zloc[g * 8 + 0] = s_res[6]; zloc[g * 8 + 1] = s_res[7]; }
             }
             __syncthreads();
+            {   // the first backward node's transposed row-1 lists stream in during its slices
+                const int jn = next_bwd(M.ninner - 1);
+                if (jn >= 0) s2_request_bwd(M.inner[jn]);
+            }
         }
         const long long tcD = CLOCK64();
 
@@ -673,7 +757,6 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
             double* arow = arows + s_aoff[e];
             double* cur = arow;
             const long long tn0 = CLOCK64();
-            pf_bwd(e);
             if (n > 0) {  // ---- slices n .. 1, transposed ----
                 const int nb16 = (int)RR.nbent, sl16 = ((int)RR.nbslots + 1) >> 1, lp16 = 4 * (n + 1);
                 const Ent* s_bents = rents + RR.bent_off;
@@ -698,21 +781,23 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
             }
             // ---- row 1, transposed ----
             const int f = s_ch0[e], g = s_ch1[e];
+            const Lay ly = bwd_lay(e);  // WGD: [bptr] [bents]; internal: [sF|upF] [sG|upG] [sFents] [sGents]
             if (kind == WHALE_WGD) {
                 // ℓ_0[c] = cy·Σ_{D(c)} p ℓ_f[i1]ℓ_f[i2] + cx·ℓ_f[c]   (the child's compat list is this node's)
                 const double* VF; int sVF;
                 leaf_or_inner_child(f, 0, VF, sVF);
                 stage_wait();
+                s2_wait();
                 __syncthreads();
                 const double cx0 = PR.cx[e * KmaxR], cy0 = PR.cy[e * KmaxR];
-                const uint32_t* bptr = rwords + RR.bptr_off;
-                const Ent* bent = rents + RR.bent_off;
+                const uint32_t* bptr = staged2 ? reinterpret_cast<const uint32_t*>(stage2) : rwords + RR.bptr_off;
+                const Ent* bent = staged2 ? reinterpret_cast<const Ent*>(stage2 + ly.a) : rents + RR.bent_off;
                 const bool isleaf = s_kind[f] == WHALE_LEAF;
                 const int Kc = s_K[f];
                 double* Ach = isleaf ? nullptr : arows + s_aoff[f];
                 double a[4] = {0.0, 0.0, 0.0, 0.0};  // c̄x, c̄y, l1, l2
                 for (int c = tid; c < C; c += NT) {
-                    const double s = vsum<true>(bent, bptr[c], bptr[c + 1], 1u, cur, 1, VF, sVF);
+                    const double s = vsum<false>(bent, bptr[c], bptr[c + 1], 1u, cur, 1, VF, sVF);
                     const double a0 = cur[c], v = VF[c * sVF];
                     const double ab = fma(cy0, s, cx0 * a0);
                     a[0] = fma(a0, v, a[0]);
@@ -736,12 +821,17 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
                 leaf_or_inner_child(f, 0, VF, sVF);
                 leaf_or_inner_child(g, 1, VG, sVG);
                 stage_wait();
+                s2_wait();
                 __syncthreads();
                 const double ef0 = PR.eps[s_toff[f] + s_nsl[f] * s_K[f]], eg0 = PR.eps[s_toff[g] + s_nsl[g] * s_K[g]];
                 double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
                 double d0 = 0.0, d1 = 0.0;
-                spec_down(f, rwords + RR.sF_off, rents + RR.sFent_off, cur, VF, sVF, VG, sVG, eg0, 1.0, d0, a[1], a[2], a[3]);
-                spec_down(g, rwords + RR.sG_off, rents + RR.sGent_off, cur, VG, sVG, VF, sVF, ef0, 1.0, d1, a[5], a[6], a[7]);
+                const uint32_t* pF = staged2 ? reinterpret_cast<const uint32_t*>(stage2) : rwords + RR.sF_off;
+                const uint32_t* pG = staged2 ? reinterpret_cast<const uint32_t*>(stage2 + ly.b) : rwords + RR.sG_off;
+                const Ent* eF = staged2 ? reinterpret_cast<const Ent*>(stage2 + ly.b + ly.c) : rents + RR.sFent_off;
+                const Ent* eG = staged2 ? reinterpret_cast<const Ent*>(stage2 + ly.b + ly.c + ly.e) : rents + RR.sGent_off;
+                spec_down(f, pF, eF, cur, VF, sVF, VG, sVG, eg0, 1.0, d0, a[1], a[2], a[3]);
+                spec_down(g, pG, eG, cur, VG, sVG, VF, sVF, ef0, 1.0, d1, a[5], a[6], a[7]);
                 block_sum<8, NT>(a, s_red, s_res, false, tid);
                 if (tid == 0) {
                     zloc[e * 8 + 5] = s_res[5];  // ϵ̄ⁿ of child 0 = Σ_c Ā[c]·ℓ_G[lg(c)]
@@ -750,6 +840,10 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
                     if (s_kind[g] == WHALE_LEAF) { zloc[g * 8 + 0] = s_res[6]; zloc[g * 8 + 1] = s_res[7]; }
                 }
                 __syncthreads();
+            }
+            {   // (both branches above end with a barrier) the next backward node's lists
+                const int jn = next_bwd(oi);
+                if (jn >= 0) s2_request_bwd(M.inner[jn]);
             }
             if (A.tim && tid == 0 && oi < TIMN) A.tim[(size_t)fam * TIMW + 8 + TIMN + oi] = CLOCK64() - tn0;
         }

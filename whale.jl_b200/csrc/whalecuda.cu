@@ -1199,10 +1199,10 @@ static bool build_reverse(whale_data* D) {
 static size_t smem_need_rev(const whale_model* m, const FamHdr& h, const RevHdr& r) {  // mirrors the carve-up in k_dp_rev
     const size_t nn = m->nn, NW = rev_nt() / 32;
     const size_t hdr = ((((9 * nn + 4) * sizeof(int)) + 15) & ~size_t(15)) + nn * (sizeof(NodeRec) + sizeof(RevRec)) +
-                       (8 * nn + NW * 8 + 8) * sizeof(double);
+                       (8 * nn + NW * 8 + 8 + 2) * sizeof(double);
     const size_t leaf = NW * ((size_t)r.leafmax * sizeof(double) + h.leaf_stage);
     const size_t back = ((size_t)r.arows_len + 3 * (size_t)r.hbuf_len) * sizeof(double);
-    return hdr + ((size_t)r.rows_len + r.scr_len) * sizeof(double) + r.stage_bytes + std::max(leaf, back);
+    return hdr + ((size_t)r.rows_len + r.scr_len) * sizeof(double) + r.stage_bytes + r.stage2_bytes + std::max(leaf, back);
 }
 
 // shared-memory budgets of the reverse-mode kernel (hybrid plan), row and adjoint-row placement; returns the largest need
@@ -1221,8 +1221,20 @@ static size_t set_budgets_rev(whale_data* D) {
         const NodeRec* recs = reinterpret_cast<const NodeRec*>(D->arena_host.data() + D->hdr[f].base);
         const RevRec* rrs = reinterpret_cast<const RevRec*>(D->rarena_host.data() + H.base);
         uint32_t mxinner = 0, mxleaf = 0, hbuf = 0;
-        size_t stg = 0;
+        size_t stg = 0, stg2 = 0;
+        auto p4 = [](size_t w) { return (w + 3) & ~size_t(3); };
         for (int e = 0; e < nn; e++) {
+            if (m->kind[e] != WHALE_LEAF) {  // row-1 / root lists, forward and transposed (the segments of fwd_segs / bwd_segs)
+                const size_t C = Cs[e], CF = Cs[m->child0[e]], CG = m->child1[e] >= 0 ? Cs[m->child1[e]] : 0;
+                const int kd = m->kind[e];
+                size_t fw = 0, bw = 0;
+                if (kd != WHALE_INTERNAL) { fw += p4(C + 1) * 4 + (size_t)recs[e].ndent * 16; bw += p4(C + 1) * 4 + (size_t)rrs[e].nbent * 16; }
+                if (kd != WHALE_WGD) {
+                    fw += p4(3 * C + 1 + (kd == WHALE_ROOT ? D->hdr[f].nlev + 1 : 0)) * 4 + (size_t)recs[e].ntent * 16;
+                    bw += p4(2 * CF + 1) * 4 + p4(2 * CG + 1) * 4 + ((size_t)rrs[e].nsFent + rrs[e].nsGent) * 16;
+                }
+                stg2 = std::max(stg2, std::max(fw, bw));
+            }
             const uint32_t K = (uint32_t)pl.K[e], ck = Cs[e] * (uint32_t)RS(K);
             const size_t n1 = (size_t)m->nsl[e] + 1;
             if (m->kind[e] == WHALE_LEAF) {
@@ -1256,6 +1268,12 @@ static size_t set_budgets_rev(whale_data* D) {
         H.hbuf_len = hbuf;
         const size_t STAGE_MAX = (size_t)env_int("WHALE_STAGE_MAX", D->F <= 160 ? 160 * 1024 : 24 * 1024);
         H.stage_bytes = 16 * stg > STAGE_MAX ? 0u : (uint32_t)(16 * stg);
+        // Prefetching the row-1 / root lists into shared memory shortens a family's critical path (−16 % cycles per C2
+        // family: root 108 k -> 43 k) but costs ~30 KB per CTA.  Measured on the B200 (profiles/r2_rev_stage2_sweep.txt):
+        // +16 % evals/s at 300 families, +8 % at 600, +2.5 % at 1000, −7 % at 12 500 (there the GPU is full and resident
+        // families per SM are what counts) — so it is on for batches of up to ~2.5 waves of CTAs.
+        const size_t STAGE2_MAX = (size_t)env_int("WHALE_STAGE2_MAX", D->F <= 160 ? 100 * 1024 : D->F <= 1500 ? 40 * 1024 : 0);
+        H.stage2_bytes = stg2 > STAGE2_MAX ? 0u : (uint32_t)stg2;
         hist_max = std::max(hist_max, (size_t)H.hist_len);
         worst = std::max(worst, smem_need_rev(m, D->hdr[f], H));
         if (env_int("WHALE_DEBUG", 0) >= 2)
