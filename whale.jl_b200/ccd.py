@@ -145,6 +145,22 @@ class CCDVector(list):
         super().__init__(items)
         self._data = {}
 
+    def __getitem__(self, i):
+        """A slice is again a batch (`ccds[:10]` keeps its own device arena across calls instead of being re-packed on
+        every evaluation)."""
+        r = super().__getitem__(i)
+        return CCDVector(r) if isinstance(i, slice) else r
+
+    def close(self):
+        """Release the device arenas of this batch (`whale_data_destroy`); they are rebuilt on the next evaluation."""
+        _release_data(self._data)
+
+    def __del__(self):
+        try:
+            _release_data(self._data)
+        except Exception:
+            pass
+
     def flatten(self, nn: int):
         """Concatenate the families into the `whale_ccd_desc` arrays (include/whalecuda.h)."""
         clade_off = np.zeros(len(self) + 1, np.int64)
@@ -165,6 +181,16 @@ class CCDVector(list):
         assert len(lens) == len(self) * nn
         return dict(n_fam=len(self), clade_off=clade_off, clade_nleaf=nleaf, split_off=split_off, g1=g1, g2=g2,
                     p=p, compat_off=compat_off, compat=compat)
+
+
+def _release_data(data: dict):
+    """Destroy the data handles a batch holds (keys: (id(lib), model handle))."""
+    from . import lib as _lib
+    for (lid, _), h in list(data.items()):
+        L = _lib.lib_by_id(lid)
+        if L is not None and h:
+            L.L.whale_data_destroy(h)
+    data.clear()
 
 
 def _ale_files(path: str) -> list[str]:
@@ -191,6 +217,15 @@ class NativeCCDVector:
 
     def __len__(self):
         return len(self.files)
+
+    def close(self):
+        _release_data(self._data)
+
+    def __del__(self):
+        try:
+            _release_data(self._data)
+        except Exception:
+            pass
 
 
 def read_ale_native(path: str, model: WhaleModel, n_threads: int = 0) -> NativeCCDVector:

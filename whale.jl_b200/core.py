@@ -30,6 +30,9 @@ def _data_handle(wm: WhaleModel, xs: CCDVector):
     return mh, xs._data[key]
 
 
+_LIST_BATCHES: "dict[tuple, CCDVector]" = {}  # plain lists of CCDs seen recently -> their batch (keeps the device arena)
+
+
 def _as_vector(x) -> tuple[CCDVector, bool]:
     if isinstance(x, NativeCCDVector):
         return x, False
@@ -38,7 +41,17 @@ def _as_vector(x) -> tuple[CCDVector, bool]:
             x._batch = CCDVector([x])
         return x._batch, True
     if not isinstance(x, CCDVector):
-        x = CCDVector(x)
+        # a plain list / tuple of CCDs (e.g. built by a comprehension): identified by its members, so that an optimisation
+        # loop calling logpdf(wm, [c1, c2, ...]) packs the device arena once, not on every call (a small LRU: the evicted
+        # batch releases its handles)
+        key = tuple(id(c) for c in x)
+        hit = _LIST_BATCHES.pop(key, None)
+        if hit is None or len(hit) != len(key) or any(a is not b for a, b in zip(hit, x)):
+            hit = CCDVector(x)
+        _LIST_BATCHES[key] = hit
+        while len(_LIST_BATCHES) > 8:
+            _LIST_BATCHES.pop(next(iter(_LIST_BATCHES))).close()
+        x = hit
     return x, False
 
 

@@ -60,6 +60,7 @@ class Lib:
                 f"{path} not found: build the CUDA library first (python -m whale_jl_b200.build or "
                 f"__graft_entry__.build()); there is no CPU fallback")
         self.path = path
+        _LIBS[id(self)] = self
         L = self.L = C.CDLL(path)
         vp = C.c_void_p
         L.whale_version.restype = C.c_int32
@@ -408,6 +409,13 @@ class Lib:
 
 
 _default: Lib | None = None
+
+
+_LIBS: dict = {}  # id(Lib) -> Lib, for finalisers that only know the id
+
+
+def lib_by_id(i: int):
+    return _LIBS.get(i)
 
 
 def get() -> Lib:

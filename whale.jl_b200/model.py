@@ -38,7 +38,7 @@ class WhaleModel:
         self.rates = rates
         self.condition = condition
         self.dt, self.minn, self.maxn = dt, minn, maxn
-        self._handle = None  # device model handle, created lazily (lib.py)
+        self._handle = None  # device model handle, created lazily (lib.py); shared by the wm(θ) copies of this model
 
         post = newick.postwalk(tree)
         leaves = newick.getleaves(tree)
