@@ -303,7 +303,7 @@ def c3_leg(args, L, wlib, rank, world, d3, n3, gen3_s, flush, stream):
         total_ms, e2e_s, fam_total = float(mx[0]), float(mx[1]), int(round(float(sm[2])))
     else:
         fam_total = n3
-    L.L.whale_data_destroy(dh)
+    ccds.close()  # releases the shard's device arena (whale_data_destroy)
     assert np.isfinite(ll) and abs(ll - last[0]) <= 1e-9 * abs(last[0]), (ll, last[0])
     dp_ms = float(kms[:, 1].mean())
     return {"workload": f"C3: {fam_total} synthetic families in total (strong scaling, {n3} on rank 0), 9-taxon tree + 2 WGD, "

@@ -60,7 +60,7 @@ def main():
     out["C3"] = dict(rate(L, mh, dh, w, xs, args.reps, len(ccd)), P=int(w.n_params),
                      grad_mode="reverse" if L.L.whale_data_grad_mode(dh) == 1 else "forward",
                      gradient_passes=int(L.L.whale_data_grad_passes(dh)))
-    L.L.whale_data_destroy(dh)
+    ccd.close()
     if only and "c4" not in only:
         print(json.dumps(out))
         return
@@ -81,7 +81,7 @@ def main():
                               clades_median=int(np.median(ccd.n_clades)),
                               grad_mode="reverse" if L.L.whale_data_grad_mode(dh) == 1 else "forward",
                               gradient_passes=int(L.L.whale_data_grad_passes(dh)), arena_bytes=int(L.L.whale_data_arena_bytes(dh)))
-    L.L.whale_data_destroy(dh)
+    ccd.close()
     rb = W.DLWGD(lam=list(rng.normal(np.log(0.15), 0.3, 59)), mu=list(rng.normal(np.log(0.15), 0.3, 59)), q=q, eta=0.67)
     wb = W.WhaleModel(rb, newick.readnw(nws), 0.05)
     ccdb = W.read_ale_native(d, wb)
