@@ -492,10 +492,10 @@ def main():
         pass
     fp64_peak = L.fp64_peak()  # measured DFMA microbenchmark on this GPU (MEASURED_PEAKS.json has no fp64 entry)
     # DRAM traffic of the k_dp launches of one step, from the committed `ncu --set full` capture of this command
-    # (profiles/r1_ncu_k_dp_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum over the step's k_dp launches)
+    # (profiles/r2_ncu_k_dp_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum over the step's k_dp launches)
     traffic, traffic_src = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_k_dp_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_k_dp_traffic.json")))
         if int(tj.get("families", 0)) == F:
             traffic, traffic_src = float(tj["dram_bytes_per_step"]), tj.get("source")
     except (OSError, ValueError, KeyError):
