@@ -29,6 +29,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <thread>
 #include <cmath>
 #include <cstdarg>
 #include <cstdint>
@@ -36,6 +38,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -432,7 +435,30 @@ static cudaError_t upload_plan(Plan& pl, int nn) {
     return cudaSuccess;
 }
 
+// fn(lo, hi) over [0, n) in chunks on the host threads (packer / budget loops over 10^5 families)
+template <class Fn>
+static void parallel_for(int n, int grain, Fn fn) {
+    static const int hw = [] { const char* s = getenv("WHALE_PACK_THREADS"); int v = s ? atoi(s) : (int)std::thread::hardware_concurrency(); return std::max(1, std::min(v, 64)); }();
+    const int nthr = std::max(1, std::min(hw, (n + grain - 1) / grain));
+    if (nthr == 1) { fn(0, n); return; }
+    std::atomic<int> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            const int lo = next.fetch_add(grain);
+            if (lo >= n) break;
+            fn(lo, std::min(n, lo + grain));
+        }
+    };
+    std::vector<std::thread> th;
+    for (int i = 0; i < nthr; i++) th.emplace_back(worker);
+    for (auto& t : th) t.join();
+}
+
 static int g_device = 0;
+static double now_s() {
+    using namespace std::chrono;
+    return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
 
 // grow-only device / pinned buffers (backtracking results)
 template <class T>
@@ -678,9 +704,11 @@ static cudaError_t launch_tables3(whale_model* m, const double* d_x, const doubl
 static size_t set_budgets(whale_data* D, int g, const Plan& pl) {
     const whale_model* m = D->m;
     const int nn = m->nn;
-    size_t worst = 0;
+    std::atomic<size_t> worst_a{0};
     D->roff_host[g].assign((size_t)D->F * nn, 0);
-    for (int f = 0; f < D->F; f++) {
+    parallel_for(D->F, 256, [&](int f_lo, int f_hi) {
+    size_t worst = 0;
+    for (int f = f_lo; f < f_hi; f++) {
         FamHdr& H = D->hdr[f];
         const std::vector<uint32_t>& Cs = D->famC[f];
         const uint32_t* ns = D->f_heavy.data() + (size_t)f * nn;  // heavy-leaf flags
@@ -721,7 +749,10 @@ static size_t set_budgets(whale_data* D, int g, const Plan& pl) {
                     H.G, H.rows_len[g], H.scr_len[g], H.prod_len[g], H.leafmax[g], H.stage_bytes[g], H.leaf_stage,
                     smem_need(m, H, g, pl.Kmax));
     }
-    return worst;
+    size_t cur = worst_a.load();
+    while (worst > cur && !worst_a.compare_exchange_weak(cur, worst)) {}
+    });
+    return worst_a.load();
 }
 
 static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, int32_t condition, uint32_t flags,
@@ -784,50 +815,48 @@ static cudaError_t order_families(whale_data* D, int g, const std::vector<double
     return cudaMemcpy(D->d_perm[g], perm.data(), (size_t)F * sizeof(int), cudaMemcpyHostToDevice);
 }
 
-int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t* out) {
-    if (!m || !d || !out) return fail(WHALE_ERR_ARG, "null argument");
-    const int nn = m->nn, F = d->n_fam;
-    if (F <= 0) return fail(WHALE_ERR_ARG, "n_fam must be positive");
-    CU(cudaSetDevice(m->device));
-    auto* D = new whale_data();
-    D->m = m;
-    D->F = F;
-    D->hdr.resize(F);
-    D->aggC.assign(nn, 0.0);
-    D->aggT.assign(nn, 0.0);
-    D->famC.resize(F);
-    std::vector<unsigned char>& A = D->arena_host;
-    D->work.assign(F, 0.0);
-    std::vector<int32_t> lidx;  // local index of clade γ at node e: lidx[e*G + γ]
-    uint64_t ell_total = 0;
-    int64_t algo_bytes = 0;
-    for (int f = 0; f < F; f++) {
+// One family of the packer: everything it contributes, self-contained, so that families can be packed on all host threads
+struct FamPack {
+    std::vector<unsigned char> blob;
+    FamHdr H;
+    std::vector<uint32_t> Cs, ndent, ntent, heavy, stage16;
+    std::vector<double> aggC, aggT;
+    double aggTroot = 0.0, work = 0.0;
+    int64_t algo = 0;
+    uint64_t ell = 0;
+    uint32_t rootwin = 0;
+};
+static int32_t pack_family(const whale_model* m, const whale_ccd_desc* d, int f, FamPack& O, std::vector<int32_t>& lidx) {
+    const int nn = m->nn;
+    O.ndent.assign(nn, 0); O.ntent.assign(nn, 0); O.heavy.assign(nn, 0); O.stage16.assign(nn, 0);
+    O.aggC.assign(nn, 0.0); O.aggT.assign(nn, 0.0);
+    O.blob.clear();
+    {
         const int64_t cb = d->clade_off[f];
         const int G = (int)(d->clade_off[f + 1] - cb);
-        if (G < 1 || G > 65535) { delete D; return fail(WHALE_ERR_ARG, "family %d: %d clades (must be 1..65535, UInt16 ids)", f, G); }
+        if (G < 1 || G > 65535) { return fail(WHALE_ERR_ARG, "family %d: %d clades (must be 1..65535, UInt16 ids)", f, G); }
         const int32_t* nleaf = d->clade_nleaf + cb;
         const int64_t* soff = d->split_off + cb;
         const int64_t* coff = d->compat_off + (int64_t)f * nn;
         lidx.assign((size_t)nn * G, -1);
-        std::vector<uint32_t>& Cs = D->famC[f];
+        std::vector<uint32_t>& Cs = O.Cs;
         Cs.assign(nn, 0);
-        FamHdr& H = D->hdr[f];
+        FamHdr& H = O.H;
         memset(&H, 0, sizeof(H));
-        H.ell_off = ell_total;
         for (int e = 0; e < nn; e++) {
             int C = (int)(coff[e + 1] - coff[e]);
             Cs[e] = C;
             int prev = -1;
             for (int j = 0; j < C; j++) {
                 int g = d->compat[coff[e] + j];
-                if (g < 0 || g >= G || g <= prev) { delete D; return fail(WHALE_ERR_ARG, "family %d node %d: compat list must be ascending clade ids", f, e); }
+                if (g < 0 || g >= G || g <= prev) { return fail(WHALE_ERR_ARG, "family %d node %d: compat list must be ascending clade ids", f, e); }
                 prev = g;
                 lidx[(size_t)e * G + g] = j;
             }
         }
-        if ((int)Cs[m->root] != G) { delete D; return fail(WHALE_ERR_ARG, "family %d: every clade must be compatible with the root", f); }
+        if ((int)Cs[m->root] != G) { return fail(WHALE_ERR_ARG, "family %d: every clade must be compatible with the root", f); }
         for (int c = 1; c < G; c++)
-            if (nleaf[c] < nleaf[c - 1]) { delete D; return fail(WHALE_ERR_ARG, "family %d: clades must be sorted by size", f); }
+            if (nleaf[c] < nleaf[c - 1]) { return fail(WHALE_ERR_ARG, "family %d: clades must be sorted by size", f); }
         // blob assembly
         std::vector<NodeRec> recs(nn);
         std::vector<uint32_t> wordsv;   // pointer / loss / level words; every array starts on a 16-byte boundary
@@ -852,8 +881,8 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
                 Te += (double)(soff[g + 1] - soff[g]);
             }
             R.nonleaf = nonleaf;
-            D->aggC[e] += C;
-            D->aggT[e] += Te;
+            O.aggC[e] = C;
+            O.aggT[e] = Te;
             // (1) same-branch terms: within-branch duplication (src/core.jl:178-185), Πroot (:151-158);
             //     for WGD nodes the same list drives Πwgdretention on the child's row (:187-194), the
             //     child's compat list being identical.
@@ -862,13 +891,13 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
             R.dent_off = (uint32_t)entsv.size();
             {
                 const int src = (kind == WHALE_WGD) ? m->child0[e] : e;
-                if (kind == WHALE_WGD && Cs[src] != (uint32_t)C) { delete D; return fail(WHALE_ERR_ARG, "family %d: WGD node %d and its child must have identical compat lists", f, e); }
+                if (kind == WHALE_WGD && Cs[src] != (uint32_t)C) { return fail(WHALE_ERR_ARG, "family %d: WGD node %d and its child must have identical compat lists", f, e); }
                 for (int j = 0; j < C; j++) {
                     int g = d->compat[coff[e] + j];
                     wordsv.push_back((uint32_t)entsv.size() - R.dent_off);
                     for (int64_t t = soff[g]; t < soff[g + 1]; t++) {
                         int g1 = d->g1[t], g2 = d->g2[t];
-                        if (g1 < 0 || g1 >= G || g2 < 0 || g2 >= G) { delete D; return fail(WHALE_ERR_ARG, "family %d: triple out of range", f); }
+                        if (g1 < 0 || g1 >= G || g2 < 0 || g2 >= G) { return fail(WHALE_ERR_ARG, "family %d: triple out of range", f); }
                         int i1 = lidx[(size_t)src * G + g1], i2 = lidx[(size_t)src * G + g2];
                         if (i1 < 0 || i2 < 0) continue;  // getl == 0 (src/ccd.jl:43)
                         entsv.push_back(Ent{(uint16_t)i1, (uint16_t)i2, 0u, d->p[t]});
@@ -883,7 +912,7 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
             pad4(wordsv);
             R.slot_off = (uint32_t)wordsv.size();
             if (kind != WHALE_ROOT && m->nsl[e] > 0) {
-                if (R.ndent > 65535) { delete D; return fail(WHALE_ERR_CAPACITY, "family %d node %d: %u same-branch terms (> 65535)", f, e, R.ndent); }
+                if (R.ndent > 65535) { return fail(WHALE_ERR_CAPACITY, "family %d node %d: %u same-branch terms (> 65535)", f, e, R.ndent); }
                 const uint32_t* dp = wordsv.data() + R.dptr_off;
                 std::vector<std::pair<int, int>> order;  // (-glog, cell)
                 std::vector<int> glogs(C);
@@ -901,7 +930,7 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
                     const uint32_t E = dp[j + 1] - dp[j], first = dp[j];
                     for (int l = 0; l < G; l++) {
                         const uint32_t cnt = (uint32_t)l < E ? (E - l + G - 1) / G : 0;
-                        if (cnt > 255) { delete D; return fail(WHALE_ERR_CAPACITY, "family %d node %d: clade with %u terms", f, e, E); }
+                        if (cnt > 255) { return fail(WHALE_ERR_CAPACITY, "family %d node %d: clade with %u terms", f, e, E); }
                         slots.push_back(Slot{(uint16_t)j, (uint8_t)gl, (uint8_t)cnt, (uint16_t)(first + l), (uint16_t)G});
                     }
                 }
@@ -979,7 +1008,7 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
                     for (int c = 0; c < G; c++)
                         if (c == 0 || nleaf[c] != nleaf[c - 1]) { wordsv.push_back((uint32_t)c); nlev++; }
                     wordsv.push_back((uint32_t)G);
-                    D->aggTroot += (double)(soff[G] - soff[0]);
+                    O.aggTroot = (double)(soff[G] - soff[0]);
                     // largest number of products one root level needs at once (Πroot + speciation terms)
                     const uint32_t* dpr = wordsv.data() + R.dptr_off;
                     const uint32_t* tpr = wordsv.data() + R.tptr_off;
@@ -1007,12 +1036,12 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
                 size_t tn16 = kind == WHALE_INTERNAL ? R.ntent : 0;
                 stage16[e] = nd16 + dp16 + tp16 + tn16 + (kind == WHALE_ROOT ? 2 * (size_t)rootwin : 0);
             }
-            ell_total += (uint64_t)(m->nsl[e] + 1) * C;
+            O.ell += (uint64_t)(m->nsl[e] + 1) * C;
         }
         pad4(wordsv);
-        D->aggG += G;
         // serialise: NodeRec[nn] | words | entries ; make offsets blob-relative
-        size_t base = (A.size() + 15) & ~size_t(15);
+        std::vector<unsigned char>& A = O.blob;
+        size_t base = 0;
         size_t words_at = (size_t)nn * sizeof(NodeRec);  // 32-byte records: 16-byte aligned
         size_t ents_at = words_at + wordsv.size() * 4;   // words padded to 4 -> 16-byte aligned
         size_t total = ents_at + entsv.size() * sizeof(Ent);
@@ -1029,25 +1058,120 @@ int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t
         memcpy(A.data() + base, recs.data(), words_at);
         if (!wordsv.empty()) memcpy(A.data() + base + words_at, wordsv.data(), wordsv.size() * 4);
         if (!entsv.empty()) memcpy(A.data() + base + ents_at, entsv.data(), entsv.size() * sizeof(Ent));
-        H.base = base;
         H.G = G;
         H.nlev = nlev;
         H.leaf_stage = (uint32_t)leaf_stage;
         H.blob_bytes = (uint32_t)total;
         H.rootwin = rootwin;
-        D->work[f] = wk;
+        O.work = wk;
         // SURVEY §8d algorithmic bytes per evaluation: 12·T + 2·Γ + 4·Σ_e C_e
-        algo_bytes += 12 * (soff[G] - soff[0]) + 2 * (int64_t)G + 4 * (int64_t)sumC;
+        O.algo = 12 * (soff[G] - soff[0]) + 2 * (int64_t)G + 4 * (int64_t)sumC;
         for (int e = 0; e < nn; e++) {
-            D->f_ndent.push_back(recs[e].ndent);
-            D->f_ntent.push_back(recs[e].ntent);
-            D->f_heavy.push_back(recs[e].nslots > HEAVY_SLOTS ? 1u : 0u);
-            D->f_stage16.push_back((uint32_t)stage16[e]);
+            O.ndent[e] = recs[e].ndent;
+            O.ntent[e] = recs[e].ntent;
+            O.heavy[e] = recs[e].nslots > HEAVY_SLOTS ? 1u : 0u;
+            O.stage16[e] = (uint32_t)stage16[e];
         }
-        D->f_rootwin.push_back(rootwin);
+        O.rootwin = rootwin;
+    
     }
+    return WHALE_OK;
+}
+
+int32_t whale_data_create(whale_model_t m, const whale_ccd_desc* d, whale_data_t* out) {
+    if (!m || !d || !out) return fail(WHALE_ERR_ARG, "null argument");
+    const int nn = m->nn, F = d->n_fam;
+    if (F <= 0) return fail(WHALE_ERR_ARG, "n_fam must be positive");
+    CU(cudaSetDevice(m->device));
+    const double t0 = now_s();
+    // pack the families on all host threads (each family's blob is self-contained), then lay the blobs out in order
+    std::vector<FamPack> packs(F);
+    int nthr = env_int("WHALE_PACK_THREADS", (int)std::thread::hardware_concurrency());
+    nthr = std::max(1, std::min(nthr, std::min(64, (F + 31) / 32)));
+    std::atomic<int> next{0};
+    std::atomic<int> failed{0};
+    std::string err;
+    int32_t err_code = WHALE_OK;
+    std::mutex err_mu;
+    auto worker = [&]() {
+        std::vector<int32_t> lidx;  // local index of clade γ at node e: lidx[e*G + γ]
+        for (;;) {
+            const int f0 = next.fetch_add(16);
+            if (f0 >= F || failed.load()) break;
+            for (int f = f0; f < std::min(F, f0 + 16); f++) {
+                const int32_t rc = pack_family(m, d, f, packs[f], lidx);
+                if (rc != WHALE_OK) {
+                    std::lock_guard<std::mutex> lk(err_mu);
+                    if (!failed.exchange(1)) { err = g_err; err_code = rc; }
+                    return;
+                }
+            }
+        }
+    };
+    if (nthr == 1) worker();
+    else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < nthr; i++) th.emplace_back(worker);
+        for (auto& t : th) t.join();
+    }
+    if (failed.load()) return fail(err_code, "%s", err.c_str());
+    auto* D = new whale_data();
+    D->m = m;
+    D->F = F;
+    D->hdr.resize(F);
+    D->aggC.assign(nn, 0.0);
+    D->aggT.assign(nn, 0.0);
+    D->famC.resize(F);
+    D->work.assign(F, 0.0);
+    D->f_ndent.resize((size_t)F * nn); D->f_ntent.resize((size_t)F * nn); D->f_heavy.resize((size_t)F * nn);
+    D->f_stage16.resize((size_t)F * nn); D->f_rootwin.resize(F);
+    uint64_t ell_total = 0;
+    int64_t algo_bytes = 0;
+    size_t bytes = 0;
+    for (int f = 0; f < F; f++) {
+        FamPack& O = packs[f];
+        D->hdr[f] = O.H;
+        D->hdr[f].base = bytes;
+        D->hdr[f].ell_off = ell_total;
+        bytes += (O.blob.size() + 15) & ~size_t(15);
+        ell_total += O.ell;
+        algo_bytes += O.algo;
+        D->famC[f].swap(O.Cs);
+        D->work[f] = O.work;
+        D->aggG += D->hdr[f].G;
+        D->aggTroot += O.aggTroot;
+        for (int e = 0; e < nn; e++) {
+            D->aggC[e] += O.aggC[e]; D->aggT[e] += O.aggT[e];
+            D->f_ndent[(size_t)f * nn + e] = O.ndent[e]; D->f_ntent[(size_t)f * nn + e] = O.ntent[e];
+            D->f_heavy[(size_t)f * nn + e] = O.heavy[e]; D->f_stage16[(size_t)f * nn + e] = O.stage16[e];
+        }
+        D->f_rootwin[f] = O.rootwin;
+    }
+    std::vector<unsigned char>& A = D->arena_host;
+    A.assign(bytes, 0);
+    {
+        std::atomic<int> nx{0};
+        auto copier = [&]() {
+            for (;;) {
+                const int f0 = nx.fetch_add(64);
+                if (f0 >= F) break;
+                for (int f = f0; f < std::min(F, f0 + 64); f++) {
+                    if (!packs[f].blob.empty()) memcpy(A.data() + D->hdr[f].base, packs[f].blob.data(), packs[f].blob.size());
+                    std::vector<unsigned char>().swap(packs[f].blob);
+                }
+            }
+        };
+        if (nthr == 1) copier();
+        else {
+            std::vector<std::thread> th;
+            for (int i = 0; i < nthr; i++) th.emplace_back(copier);
+            for (auto& t : th) t.join();
+        }
+    }
+    std::vector<FamPack>().swap(packs);
     D->ell_total = ell_total;
     D->algo_bytes = algo_bytes;
+    if (env_int("WHALE_DEBUG", 0) >= 1) fprintf(stderr, "[whale] packed %d families on %d threads in %.2f s (%zu bytes)\n", F, nthr, now_s() - t0, bytes);
     return finalize_data(m, D, out);
 }
 
@@ -1079,18 +1203,13 @@ static bool make_slots(const uint32_t* ptr, int C, std::vector<Slot>& slots) {
 }
 
 // returns false when a family cannot be represented (u16 entry indices): the handle then keeps forward tangents
-static bool build_reverse(whale_data* D) {
-    const whale_model* m = D->m;
-    const int nn = m->nn, F = D->F;
-    const std::vector<unsigned char>& A = D->arena_host;
-    std::vector<unsigned char>& RA = D->rarena_host;
-    RA.clear();
-    D->rhdr.assign(F, RevHdr{});
-    for (int f = 0; f < F; f++) {
-        const unsigned char* blob = A.data() + D->hdr[f].base;
-        const NodeRec* recs = reinterpret_cast<const NodeRec*>(blob);
-        const uint32_t* words = reinterpret_cast<const uint32_t*>(blob);
-        const Ent* ents = reinterpret_cast<const Ent*>(blob);
+// transposed lists of ONE family from its forward blob (self-contained: families are processed on all host threads)
+static bool reverse_family(const whale_model* m, const unsigned char* blobF, int nn, std::vector<unsigned char>& blob,
+                           uint32_t& hist_len) {
+    {
+        const NodeRec* recs = reinterpret_cast<const NodeRec*>(blobF);
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(blobF);
+        const Ent* ents = reinterpret_cast<const Ent*>(blobF);
         std::vector<RevRec> rr(nn);
         std::vector<uint32_t> wv;
         std::vector<Ent> ev;
@@ -1173,25 +1292,61 @@ static bool build_reverse(whale_data* D) {
         }
         pad4(wv);
         if (hoff > 0xffffffffull) return false;
-        const size_t base = (RA.size() + 15) & ~size_t(15);
         const size_t words_at = (size_t)nn * sizeof(RevRec);
         const size_t ents_at = words_at + wv.size() * 4;
         const size_t total = ents_at + ev.size() * sizeof(Ent);
         if (total > 0xffffffffull) return false;
-        RA.resize(base + total, 0);
+        blob.assign(total, 0);
         for (int e = 0; e < nn; e++) {
             RevRec& Q = rr[e];
             Q.bptr_off += (uint32_t)(words_at / 4); Q.bslot_off += (uint32_t)(words_at / 4);
             Q.sF_off += (uint32_t)(words_at / 4); Q.sG_off += (uint32_t)(words_at / 4);
             Q.bent_off += (uint32_t)(ents_at / 16); Q.sFent_off += (uint32_t)(ents_at / 16); Q.sGent_off += (uint32_t)(ents_at / 16);
         }
-        memcpy(RA.data() + base, rr.data(), words_at);
-        if (!wv.empty()) memcpy(RA.data() + base + words_at, wv.data(), wv.size() * 4);
-        if (!ev.empty()) memcpy(RA.data() + base + ents_at, ev.data(), ev.size() * sizeof(Ent));
-        RevHdr& H = D->rhdr[f];
-        H.base = base;
-        H.blob_bytes = (uint32_t)total;
-        H.hist_len = (uint32_t)hoff;
+        memcpy(blob.data(), rr.data(), words_at);
+        if (!wv.empty()) memcpy(blob.data() + words_at, wv.data(), wv.size() * 4);
+        if (!ev.empty()) memcpy(blob.data() + ents_at, ev.data(), ev.size() * sizeof(Ent));
+        hist_len = (uint32_t)hoff;
+    }
+    return true;
+}
+
+static bool build_reverse(whale_data* D) {
+    const whale_model* m = D->m;
+    const int nn = m->nn, F = D->F;
+    const std::vector<unsigned char>& A = D->arena_host;
+    std::vector<unsigned char>& RA = D->rarena_host;
+    RA.clear();
+    D->rhdr.assign(F, RevHdr{});
+    std::vector<std::vector<unsigned char>> blobs(F);
+    int nthr = env_int("WHALE_PACK_THREADS", (int)std::thread::hardware_concurrency());
+    nthr = std::max(1, std::min(nthr, std::min(64, (F + 31) / 32)));
+    std::atomic<int> next{0}, bad{0};
+    auto worker = [&]() {
+        for (;;) {
+            const int f0 = next.fetch_add(16);
+            if (f0 >= F || bad.load()) break;
+            for (int f = f0; f < std::min(F, f0 + 16); f++)
+                if (!reverse_family(m, A.data() + D->hdr[f].base, nn, blobs[f], D->rhdr[f].hist_len)) { bad.store(1); return; }
+        }
+    };
+    if (nthr == 1) worker();
+    else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < nthr; i++) th.emplace_back(worker);
+        for (auto& t : th) t.join();
+    }
+    if (bad.load()) return false;
+    size_t bytes = 0;
+    for (int f = 0; f < F; f++) {
+        D->rhdr[f].base = bytes;
+        D->rhdr[f].blob_bytes = (uint32_t)blobs[f].size();
+        bytes += (blobs[f].size() + 15) & ~size_t(15);
+    }
+    RA.assign(bytes, 0);
+    for (int f = 0; f < F; f++) {
+        if (!blobs[f].empty()) memcpy(RA.data() + D->rhdr[f].base, blobs[f].data(), blobs[f].size());
+        std::vector<unsigned char>().swap(blobs[f]);
     }
     return true;
 }
@@ -1210,12 +1365,14 @@ static size_t set_budgets_rev(whale_data* D) {
     const whale_model* m = D->m;
     const Plan& pl = m->planR;
     const int nn = m->nn;
-    size_t worst = 0;
+    std::atomic<size_t> worst_a{0}, hist_a{0};
     D->roff_host[1].assign((size_t)D->F * nn, 0);
     D->aoff_host.assign((size_t)D->F * nn, 0);
-    size_t hist_max = 0;
     auto even = [](uint32_t v) { return (v + 1) & ~1u; };
-    for (int f = 0; f < D->F; f++) {
+    auto amax = [](std::atomic<size_t>& a, size_t v) { size_t cur = a.load(); while (v > cur && !a.compare_exchange_weak(cur, v)) {} };
+    parallel_for(D->F, 256, [&](int f_lo, int f_hi) {
+    size_t worst = 0, hist_max = 0;
+    for (int f = f_lo; f < f_hi; f++) {
         RevHdr& H = D->rhdr[f];
         const std::vector<uint32_t>& Cs = D->famC[f];
         const NodeRec* recs = reinterpret_cast<const NodeRec*>(D->arena_host.data() + D->hdr[f].base);
@@ -1280,8 +1437,11 @@ static size_t set_budgets_rev(whale_data* D) {
             fprintf(stderr, "[whale] fam %d reverse: rows %u scr %u leafmax %u stage %u arows %u hbuf %u hist %u -> %zu B\n", f,
                     H.rows_len, H.scr_len, H.leafmax, H.stage_bytes, H.arows_len, H.hbuf_len, H.hist_len, smem_need_rev(m, D->hdr[f], H));
     }
-    D->hist_stride = (hist_max + 1) & ~size_t(1);
-    return worst;
+    amax(worst_a, worst);
+    amax(hist_a, hist_max);
+    });
+    D->hist_stride = (hist_a.load() + 1) & ~size_t(1);
+    return worst_a.load();
 }
 
 // Second half of whale_data_create, shared with whale_data_load: tangent plans and shared-memory budgets for this
@@ -1289,6 +1449,8 @@ static size_t set_budgets_rev(whale_data* D) {
 // Takes ownership of D (deleted on failure).
 static int32_t finalize_data(whale_model* m, whale_data* D, whale_data_t* out) {
     const int nn = m->nn, F = D->F;
+    const double tf0 = now_s();
+    const bool dbg = env_int("WHALE_DEBUG", 0) >= 1;
     std::vector<unsigned char>& A = D->arena_host;
     // ---- tangent plans: one gradient pass if every family's working set fits, else parameter chunks ----
     D->plans = {&m->plan[0], &m->plan[1]};
@@ -1369,6 +1531,7 @@ static int32_t finalize_data(whale_model* m, whale_data* D, whale_data_t* out) {
         fprintf(stderr, "[whale] %d families, P = %d: %zu gradient pass(es), worst family %zu B of shared memory\n", F, m->P,
                 D->plans.size() - 1, need1);
     if (need1 > SMEM_MAX) { delete D; return fail(WHALE_ERR_CAPACITY, "a family needs %zu bytes of shared memory (> 227 KB) even with %d parameter chunks", need1, MAXPLAN - 1); }
+    if (dbg) fprintf(stderr, "[whale] plans, reverse lists and budgets: %.2f s\n", now_s() - tf0);
     size_t outsz = 0;
     for (size_t g = 0; g < D->plans.size(); g++) {
         const Plan& pl = *D->plans[g];
@@ -1403,6 +1566,7 @@ static int32_t finalize_data(whale_model* m, whale_data* D, whale_data_t* out) {
     }
     CU(cudaEventCreateWithFlags(&D->ev_fork, cudaEventDisableTiming));
     *out = D;
+    if (dbg) fprintf(stderr, "[whale] ... + launch order and upload: %.2f s\n", now_s() - tf0);
 #ifndef WHALE_EMU
     // Calibration pass: one profiled evaluation at a benign parameter point; the measured SM cycles of every family
     // replace the packer's flop estimate as the scheduling weight (the estimate misses e.g. long leaf-branch chains).
@@ -1460,7 +1624,9 @@ int32_t whale_read_ale(whale_model_t m, int32_t n_files, const char* const* path
         }
     std::vector<std::string> files(paths, paths + n_files);
     std::vector<whale_ale::Family> fams;
+    const double tp0 = now_s();
     whale_ale::parse_all(files, sp, nn, fams, n_threads);
+    if (env_int("WHALE_DEBUG", 0) >= 1) fprintf(stderr, "[whale] parsed %d .ale files in %.2f s\n", n_files, now_s() - tp0);
     for (int f = 0; f < n_files; f++)
         if (!fams[f].error.empty()) return fail(WHALE_ERR_ARG, "%s", fams[f].error.c_str());
     // concatenate into the flattened reference layout and pack
