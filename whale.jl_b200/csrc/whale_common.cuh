@@ -129,7 +129,8 @@ struct RevHdr {
     uint32_t stage_bytes;   // staging of one node's forward lists + ϕ/ψ rows, or of its backward slice lists
     uint32_t arows_len;     // doubles: adjoint last rows, placed by (reverse) lifetime
     uint32_t hbuf_len;      // doubles: one staged history row (largest padded C of an internal/WGD node)
-    uint32_t stage2_bytes;  // row-1 / root lists of one node, prefetched by bulk copies (0: read in place)
+    uint32_t stage2_bytes;  // row-1 lists of one internal/WGD node, prefetched by bulk copies (0: read in place)
+    uint32_t root_staged;   // the root's lists fit stage + stage2 together (they are contiguous) and are prefetched too
 };
 
 struct ModelDev {  // structure arrays (device pointers), node index = id-1

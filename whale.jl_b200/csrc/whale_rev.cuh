@@ -347,6 +347,9 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
         unsigned char* stage2 = stage + stage_bytes;     // row-1 / root lists, prefetched one node ahead (bulk copies)
         const uint32_t stage2_bytes = Rp->stage2_bytes;
         const bool staged2 = stage2_bytes != 0;
+        // the root has no slices: its (largest) lists use `stage` and `stage2` together, requested once the last slice
+        // loop is over; stage2 alone only has to hold the row-1 lists of one internal/WGD node
+        const bool root_staged = Rp->root_staged != 0;
         unsigned char* leaf_area = stage2 + stage2_bytes;  // phase A only; the backward pass reuses it:
         const size_t leaf_area_bytes = (size_t)leafmax * sizeof(double) + leaf_stage;
         double* arows = reinterpret_cast<double*>(leaf_area);
@@ -396,12 +399,16 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
             return y;
         };
         // requests must follow a barrier after which nobody reads the previous contents of stage2
+        auto s2_on = [&](int e) -> bool { return e == root ? root_staged : staged2; };
+        auto s2_base = [&](int e) -> unsigned char* { return e == root ? stage : stage2; };
+        unsigned char* s2_dst = stage2;
         auto s2_copy = [&](uint32_t& off, const unsigned char* src, uint32_t bytes) {
-            if (bytes) bulk_g2s(stage2 + off, src, bytes, s_bar);
+            if (bytes) bulk_g2s(s2_dst + off, src, bytes, s_bar);
             off += bytes;
         };
         auto s2_request_fwd = [&](int e) {
-            if (!staged2 || tid != 0) return;
+            if (!s2_on(e) || tid != 0) return;
+            s2_dst = s2_base(e);
             const Lay y = fwd_lay(e);
             const NodeRec& Q = nrec[e];
             fence_proxy_async();
@@ -413,7 +420,8 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
             s2_copy(off, blob + (size_t)Q.tent_off * 16, y.d);
         };
         auto s2_request_bwd = [&](int e) {
-            if (!staged2 || tid != 0) return;
+            if (!s2_on(e) || tid != 0) return;
+            s2_dst = s2_base(e);
             const Lay y = bwd_lay(e);
             const RevRec& Q = rrec[e];
             fence_proxy_async();
@@ -426,17 +434,15 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
             s2_copy(off, rblob + (size_t)Q.sFent_off * 16, y.e);
             s2_copy(off, rblob + (size_t)Q.sGent_off * 16, y.f);
         };
-        auto s2_wait = [&]() {
-            if (!staged2) return;
+        auto s2_wait = [&](int e) {
+            if (!s2_on(e)) return;
             mbar_wait(s_bar, s2_phase);
             s2_phase ^= 1u;
         };
         auto next_fwd = [&](int oi) -> int { for (int j = oi + 1; j < M.ninner; j++) if (nrec[M.inner[j]].C) return j; return -1; };
         auto next_bwd = [&](int oi) -> int { for (int j = oi - 1; j >= 0; j--) if (nrec[M.inner[j]].C) return j; return -1; };
-        {
-            const int j0 = next_fwd(-1);
-            if (j0 >= 0) s2_request_fwd(M.inner[j0]);
-        }
+        const int j_first = next_fwd(-1);
+        if (j_first >= 0 && M.inner[j_first] != root) s2_request_fwd(M.inner[j_first]);  // streams in during the leaf phase
         const long long tcA = CLOCK64();
         // ================= phase A: leaf branches (as in k_dp, hybrid plan: value + own λ, μ) =================
         for (int li = warp; li < M.nleafnodes; li += NW) {
@@ -517,6 +523,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
             __syncthreads();
         }
         const long long tcB = CLOCK64();
+        if (j_first >= 0 && M.inner[j_first] == root) s2_request_fwd(root);  // (a tree without internal branches)
 
         // ================= phase B forward: internal, WGD and root nodes, value only, rows kept =================
         for (int oi = 0; oi < M.ninner; oi++) {
@@ -541,10 +548,12 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
             const double2* s_pp = PR.pp + s_toff[e];
             // row-1 / root lists: the segments requested one node ahead (see fwd_segs for their order)
             const Lay ly = fwd_lay(e);
-            const uint32_t* g_dptr = staged2 ? reinterpret_cast<const uint32_t*>(stage2) : words + R.dptr_off;
-            const uint32_t* g_tptr = staged2 ? reinterpret_cast<const uint32_t*>(stage2 + ly.a) : words + R.tptr_off;
-            const Ent* g_dents = staged2 ? reinterpret_cast<const Ent*>(stage2 + ly.a + ly.b) : ents + R.dent_off;
-            const Ent* g_tents = staged2 ? reinterpret_cast<const Ent*>(stage2 + ly.a + ly.b + ly.c) : ents + R.tent_off;
+            const bool st2 = s2_on(e);
+            const unsigned char* sb = s2_base(e);
+            const uint32_t* g_dptr = st2 ? reinterpret_cast<const uint32_t*>(sb) : words + R.dptr_off;
+            const uint32_t* g_tptr = st2 ? reinterpret_cast<const uint32_t*>(sb + ly.a) : words + R.tptr_off;
+            const Ent* g_dents = st2 ? reinterpret_cast<const Ent*>(sb + ly.a + ly.b) : ents + R.dent_off;
+            const Ent* g_tents = st2 ? reinterpret_cast<const Ent*>(sb + ly.a + ly.b + ly.c) : ents + R.tent_off;
             if (staged && kind != WHALE_ROOT) {
                 uint4* st4 = reinterpret_cast<uint4*>(stage);
                 copy16(st4, reinterpret_cast<const uint4*>(s_dents), nd16, tid, NT);
@@ -555,7 +564,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
                 s_pp = reinterpret_cast<const double2*>(st4 + nd16 + sl16);
             }
             double* cur = (n & 1) ? scr : fin;
-            s2_wait();  // this node's row-1 lists have landed
+            s2_wait(e);  // this node's row-1 lists have landed
             if (kind == WHALE_WGD) {  // q·Σ p ℓ_f[γ1]ℓ_f[γ2] + (1−q+2qϵ_f)·ℓ_f[γ]   src/core.jl:103-119,187-199
                 const double cx0 = PR.cx[e * KmaxR], cy0 = PR.cy[e * KmaxR];
                 for (int c = tid; c < C; c += NT) {
@@ -615,12 +624,12 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
             stage_wait();
             __syncthreads();  // row 1 and the staged lists are visible
             const long long ts0 = CLOCK64();
-            {   // row 1 is done: the next node's row-1 lists stream in while this node's slices run
-                const int jn = next_fwd(oi);
-                if (jn >= 0) s2_request_fwd(M.inner[jn]);
-            }
+            const int jn = next_fwd(oi);
+            // row 1 is done: the next node's row-1 lists stream in while this node's slices run
+            if (jn >= 0 && M.inner[jn] != root) s2_request_fwd(M.inner[jn]);
             run_slices_fwd1<NT>(n, Cp, fin, scr, cur, s_slots, (int)R.nslots, s_dents, s_pp, hrow, tid);
             __syncthreads();  // the last row is complete; the staging buffer may be reused
+            if (jn >= 0 && M.inner[jn] == root) s2_request_fwd(root);  // (the root's lists also use this node's slice buffer)
             const long long ts1 = CLOCK64();
             acc_fsl += ts1 - ts0;
             if (A.tim && tid == 0 && oi < TIMN) A.tim[(size_t)fam * TIMW + 8 + oi] = ts1 - tn0;
@@ -632,7 +641,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
         const double Lv = rows[s_roff[root] + CR - 1];
         if (!(Lv > 0.0)) {  // L <= 0 -> −Inf, zero gradient (src/core.jl:36)
             for (int k = tid; k < KR; k += NT) A.out_fam[(size_t)fam * KR + k] = k == 0 ? -dinf() : 0.0;
-            s2_wait();  // (the root's transposed lists were requested: keep the barrier's phase in step)
+            s2_wait(root);  // (the root's transposed lists were requested: keep the barrier's phase in step)
             continue;
         }
         // per-node local adjoints: zloc[e] = {λ̄, μ̄, ϵ̄⁰ (slices), c̄x, c̄y (WGD, root), ϵ̄ⁿ of child 0, ϵ̄ⁿ of child 1, -}
@@ -688,13 +697,13 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
             const uint32_t* g_tptr = words + R.tptr_off;
             const uint32_t* g_lev = g_tptr + 3 * CR + 1;
             const Lay ly = bwd_lay(e);  // [bptr] [sF|upF] [sG|upG] [bents] [sFents] [sGents]
-            const unsigned char* sp0 = staged2 ? stage2 : rblob + (size_t)RR.bptr_off * 4;
-            const unsigned char* sp1 = staged2 ? stage2 + ly.a : rblob + (size_t)RR.sF_off * 4;
-            const unsigned char* sp2 = staged2 ? stage2 + ly.a + ly.b : rblob + (size_t)RR.sG_off * 4;
-            const unsigned char* sp3 = staged2 ? stage2 + ly.a + ly.b + ly.c : rblob + (size_t)RR.bent_off * 16;
-            const unsigned char* sp4 = staged2 ? stage2 + ly.a + ly.b + ly.c + ly.d : rblob + (size_t)RR.sFent_off * 16;
-            const unsigned char* sp5 = staged2 ? stage2 + ly.a + ly.b + ly.c + ly.d + ly.e : rblob + (size_t)RR.sGent_off * 16;
-            s2_wait();
+            const unsigned char* sp0 = root_staged ? stage : rblob + (size_t)RR.bptr_off * 4;
+            const unsigned char* sp1 = root_staged ? stage + ly.a : rblob + (size_t)RR.sF_off * 4;
+            const unsigned char* sp2 = root_staged ? stage + ly.a + ly.b : rblob + (size_t)RR.sG_off * 4;
+            const unsigned char* sp3 = root_staged ? stage + ly.a + ly.b + ly.c : rblob + (size_t)RR.bent_off * 16;
+            const unsigned char* sp4 = root_staged ? stage + ly.a + ly.b + ly.c + ly.d : rblob + (size_t)RR.sFent_off * 16;
+            const unsigned char* sp5 = root_staged ? stage + ly.a + ly.b + ly.c + ly.d + ly.e : rblob + (size_t)RR.sGent_off * 16;
+            s2_wait(root);
             const uint32_t* bptr = reinterpret_cast<const uint32_t*>(sp0);
             const Ent* bent = reinterpret_cast<const Ent*>(sp3);
             const double seed = 1.0 / Lv;  // d log L / dL
@@ -787,7 +796,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
                 const double* VF; int sVF;
                 leaf_or_inner_child(f, 0, VF, sVF);
                 stage_wait();
-                s2_wait();
+                s2_wait(e);
                 __syncthreads();
                 const double cx0 = PR.cx[e * KmaxR], cy0 = PR.cy[e * KmaxR];
                 const uint32_t* bptr = staged2 ? reinterpret_cast<const uint32_t*>(stage2) : rwords + RR.bptr_off;
@@ -821,7 +830,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
                 leaf_or_inner_child(f, 0, VF, sVF);
                 leaf_or_inner_child(g, 1, VG, sVG);
                 stage_wait();
-                s2_wait();
+                s2_wait(e);
                 __syncthreads();
                 const double ef0 = PR.eps[s_toff[f] + s_nsl[f] * s_K[f]], eg0 = PR.eps[s_toff[g] + s_nsl[g] * s_K[g]];
                 double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};

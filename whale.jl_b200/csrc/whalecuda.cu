@@ -1378,7 +1378,7 @@ static size_t set_budgets_rev(whale_data* D) {
         const NodeRec* recs = reinterpret_cast<const NodeRec*>(D->arena_host.data() + D->hdr[f].base);
         const RevRec* rrs = reinterpret_cast<const RevRec*>(D->rarena_host.data() + H.base);
         uint32_t mxinner = 0, mxleaf = 0, hbuf = 0;
-        size_t stg = 0, stg2 = 0;
+        size_t stg = 0, stg2 = 0, stg_root = 0;
         auto p4 = [](size_t w) { return (w + 3) & ~size_t(3); };
         for (int e = 0; e < nn; e++) {
             if (m->kind[e] != WHALE_LEAF) {  // row-1 / root lists, forward and transposed (the segments of fwd_segs / bwd_segs)
@@ -1390,7 +1390,8 @@ static size_t set_budgets_rev(whale_data* D) {
                     fw += p4(3 * C + 1 + (kd == WHALE_ROOT ? D->hdr[f].nlev + 1 : 0)) * 4 + (size_t)recs[e].ntent * 16;
                     bw += p4(2 * CF + 1) * 4 + p4(2 * CG + 1) * 4 + ((size_t)rrs[e].nsFent + rrs[e].nsGent) * 16;
                 }
-                stg2 = std::max(stg2, std::max(fw, bw));
+                if (kd == WHALE_ROOT) stg_root = std::max(fw, bw);
+                else stg2 = std::max(stg2, std::max(fw, bw));
             }
             const uint32_t K = (uint32_t)pl.K[e], ck = Cs[e] * (uint32_t)RS(K);
             const size_t n1 = (size_t)m->nsl[e] + 1;
@@ -1425,12 +1426,18 @@ static size_t set_budgets_rev(whale_data* D) {
         H.hbuf_len = hbuf;
         const size_t STAGE_MAX = (size_t)env_int("WHALE_STAGE_MAX", D->F <= 160 ? 160 * 1024 : 24 * 1024);
         H.stage_bytes = 16 * stg > STAGE_MAX ? 0u : (uint32_t)(16 * stg);
-        // Prefetching the row-1 / root lists into shared memory shortens a family's critical path (−16 % cycles per C2
-        // family: root 108 k -> 43 k) but costs ~30 KB per CTA.  Measured on the B200 (profiles/r2_rev_stage2_sweep.txt):
-        // +16 % evals/s at 300 families, +8 % at 600, +2.5 % at 1000, −7 % at 12 500 (there the GPU is full and resident
-        // families per SM are what counts) — so it is on for batches of up to ~2.5 waves of CTAs.
-        const size_t STAGE2_MAX = (size_t)env_int("WHALE_STAGE2_MAX", D->F <= 160 ? 100 * 1024 : D->F <= 1500 ? 40 * 1024 : 0);
-        H.stage2_bytes = stg2 > STAGE2_MAX ? 0u : (uint32_t)stg2;
+        // The row-1 lists of the next internal/WGD node are prefetched into `stage2` while the current node's slices run; the
+        // root (no slices) uses `stage` + `stage2` together, so stage2 is sized for max(one non-root node, root − stage):
+        // 20–30 KB per C2 family, four families still resident per SM.  It shortens a family's critical path (−15 % cycles:
+        // root 109 k -> 44 k) — +14 % evals/s at 1000 families per GPU, +16 % at 300 — but on a full GPU (12 500 families)
+        // the latency it removes is hidden by the other resident families anyway and the extra shared-memory traffic
+        // costs 3.5 % (profiles/r2_rev_stage2_sweep.txt): on for batches of up to a few waves of CTAs.
+        const size_t STAGE2_MAX = (size_t)env_int("WHALE_STAGE2_MAX", D->F <= 160 ? 100 * 1024 : D->F <= 2500 ? 32 * 1024 : 0);
+        const size_t with_root = std::max(stg2, stg_root > H.stage_bytes ? stg_root - H.stage_bytes : (size_t)0);
+        if (H.stage_bytes == 0) { H.stage2_bytes = 0; H.root_staged = 0; }
+        else if (with_root <= STAGE2_MAX) { H.stage2_bytes = (uint32_t)std::max<size_t>(with_root, 16); H.root_staged = 1; }
+        else if (stg2 <= STAGE2_MAX) { H.stage2_bytes = (uint32_t)std::max<size_t>(stg2, 16); H.root_staged = 0; }
+        else { H.stage2_bytes = 0; H.root_staged = 0; }
         hist_max = std::max(hist_max, (size_t)H.hist_len);
         worst = std::max(worst, smem_need_rev(m, D->hdr[f], H));
         if (env_int("WHALE_DEBUG", 0) >= 2)
