@@ -140,6 +140,9 @@ int32_t whale_multi_logpdf_grad(whale_multi_t h, const double* x, const double* 
 int32_t whale_peer_export(whale_data_t d, int32_t rank, int32_t world, void* handle64);
 int32_t whale_peer_import(whale_data_t d, int32_t peer, const void* handle64);
 int32_t whale_peer_ready(whale_data_t d);
+/* the exchange alone: d_out ([1 + n_params] doubles on the device, e.g. a prior's value and gradient the driver wants
+ * summed the same way) is replaced by the sum over ranks; ordered on `stream`; counts as one WHALE_PEER_SUM step */
+int32_t whale_peer_sum_async(whale_data_t d, double* d_out, void* stream);
 
 int32_t whale_model_create(const whale_model_desc* desc, whale_model_t* out);
 int32_t whale_model_destroy(whale_model_t m);

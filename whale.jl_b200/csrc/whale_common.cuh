@@ -5,12 +5,36 @@
 // kernel logic can be exercised on a machine without a GPU.  Never shipped, never loaded by the package.
 #include "cuda_emu.h"
 #define LAUNCH(kern, grid, block, smem, st, ...) emu::launch(grid, block, smem, [=]() { kern(__VA_ARGS__); })
+#define LAUNCH_PDL(kern, grid, block, smem, st, ...) LAUNCH(kern, grid, block, smem, st, __VA_ARGS__)
+#define GRID_DEP_WAIT() ((void)0)
+#define GRID_DEP_LAUNCH() ((void)0)
 #else
 #include <cuda_runtime.h>
 #define LAUNCH(kern, grid, block, smem, st, ...) kern<<<grid, block, smem, st>>>(__VA_ARGS__)
 #define EXTERN_SHARED(name) extern __shared__ __align__(16) unsigned char name[]
+// Programmatic dependent launch: the kernel may start while its predecessor in the stream (the table kernel) is still
+// running — its prologue (species-tree metadata, node records, L2 prefetch of the family's lists) overlaps the tables;
+// GRID_DEP_WAIT() (griddepcontrol.wait) blocks until the predecessor has completed and its writes are visible.
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+#define LAUNCH_PDL(kern, grid, block, smem, st, ...) launch_pdl(kern, grid, block, smem, st, __VA_ARGS__)
+#define GRID_DEP_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define GRID_DEP_LAUNCH() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #endif
 #include <cstdint>
+#include <utility>
 
 #include "../../include/whalecuda.h"
 

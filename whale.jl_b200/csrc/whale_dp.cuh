@@ -748,6 +748,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         return ell_base + o;
     };
 
+    GRID_DEP_WAIT();  // programmatic dependent launch: everything above overlapped the table kernel
     const long long tcA = CLOCK64();
     // ================= phase A: leaf branches, one warp each (src/core.jl:83-101,121-128) =================
     for (int li = warp; li < M.nleafnodes; li += NW) {

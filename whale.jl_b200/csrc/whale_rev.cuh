@@ -443,6 +443,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
         auto next_bwd = [&](int oi) -> int { for (int j = oi - 1; j >= 0; j--) if (nrec[M.inner[j]].C) return j; return -1; };
         const int j_first = next_fwd(-1);
         if (j_first >= 0 && M.inner[j_first] != root) s2_request_fwd(M.inner[j_first]);  // streams in during the leaf phase
+        GRID_DEP_WAIT();  // programmatic dependent launch: the prologue of the CTA's first family overlapped k_tables3
         const long long tcA = CLOCK64();
         // ================= phase A: leaf branches (as in k_dp, hybrid plan: value + own λ, μ) =================
         for (int li = warp; li < M.nleafnodes; li += NW) {

@@ -61,6 +61,7 @@ __device__ void leafshapes_block(const ModelDev& M, const PlanDev& PL, const dou
 __device__ __forceinline__ void tables_block(const ModelDev& M, const PlanDev& PL, const double* __restrict__ x,
                                              const double* __restrict__ pleaf, int G, unsigned flags, int bid,
                                              unsigned char* tsm) {
+    GRID_DEP_LAUNCH();  // the DP kernel behind this one may start its prologue now (it waits before reading the tables)
     if (bid >= G) {  // tree-shape rows of one leaf branch
         leafshapes_block(M, PL, x, pleaf, bid - G, tsm);
         return;

@@ -653,6 +653,10 @@ static size_t tables_smem(const whale_model* m, const Plan& pl, bool shapes) {  
 }
 
 // K1 launch: G table CTAs (each takes 1/G of the rows) + one CTA per leaf node for the tree-shape rows
+static bool pdl_enabled() {  // programmatic dependent launch of the DP kernel behind the table kernel (WHALE_PDL=0: off)
+    static bool f = env_int("WHALE_PDL", 1) != 0;
+    return f;
+}
 static bool fused_reduce() {
     static bool f = env_int("WHALE_FUSED_REDUCE", 1) != 0;
     return f;
@@ -1913,7 +1917,12 @@ static int32_t enqueue_eval_rev(whale_model* m, whale_data* D, const double* d_x
                   D->d_roff[1], D->d_aoff, out_fam, D->d_hist, (unsigned long long)D->hist_stride, D->d_next + b,
                   bins[b].off, bins[b].count, D->rev_slot0[b], prof ? D->d_tim : nullptr, fused ? D->d_done : nullptr, F,
                   condition, d_out};
-#define LAUNCHV(NTV, MBV) if (NT == NTV && MB == MBV) LAUNCH((k_dp_rev<NTV, MBV>), D->rev_grid[b], NTV, std::max(bins[b].smem, tail_smem), s, a);
+        const bool pdl = pdl_enabled() && bins.size() == 1;
+#define LAUNCHV(NTV, MBV)                                                                                                   \
+    if (NT == NTV && MB == MBV) {                                                                                           \
+        if (pdl) LAUNCH_PDL((k_dp_rev<NTV, MBV>), D->rev_grid[b], NTV, std::max(bins[b].smem, tail_smem), s, a);            \
+        else LAUNCH((k_dp_rev<NTV, MBV>), D->rev_grid[b], NTV, std::max(bins[b].smem, tail_smem), s, a);                    \
+    }
         REV_VARIANTS(LAUNCHV)
 #undef LAUNCHV
         g_launches++;
@@ -2008,7 +2017,12 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
         const int MB = dp_minb();
         const size_t tail_smem = (size_t)(NT + 2 * pl.K[m->root] + 2) * sizeof(double);  // the fused reduction's scratch
         auto launch_bin = [&](const Bin& b, cudaStream_t s) {
-#define LAUNCHV(NTV, MBV) if (NT == NTV && MB == MBV) LAUNCH((k_dp<NTV, MBV>), b.count, NTV, std::max(b.smem, tail_smem), s, a, b.off);
+            const bool pdl = pdl_enabled() && bins.size() == 1;
+#define LAUNCHV(NTV, MBV)                                                                                                   \
+    if (NT == NTV && MB == MBV) {                                                                                           \
+        if (pdl) LAUNCH_PDL((k_dp<NTV, MBV>), b.count, NTV, std::max(b.smem, tail_smem), s, a, b.off);                      \
+        else LAUNCH((k_dp<NTV, MBV>), b.count, NTV, std::max(b.smem, tail_smem), s, a, b.off);                              \
+    }
             DP_VARIANTS(LAUNCHV)
 #undef LAUNCHV
             g_launches++;
@@ -2914,6 +2928,12 @@ static int32_t enqueue_peer_sum(whale_data* D, double* d_out, cudaStream_t st) {
     g_launches++;
     CU(cudaGetLastError());
     return WHALE_OK;
+}
+
+int32_t whale_peer_sum_async(whale_data_t d, double* d_out, void* stream) {
+    if (!d || !d_out) return fail(WHALE_ERR_ARG, "null argument");
+    CU(cudaSetDevice(d->m->device));
+    return enqueue_peer_sum(d, d_out, (cudaStream_t)stream);
 }
 
 int32_t whale_fp64_peak(double* tflops) {

@@ -25,7 +25,7 @@ SYMBOLS = ["whale_version", "whale_last_error", "whale_device_count", "whale_set
            "whale_work_estimate", "whale_last_kernel_ms", "whale_last_phase_cycles", "whale_last_node_cycles", "whale_last_family_cycles", "whale_last_tables_cycles", "whale_last_backtrack_ms", "whale_fp64_peak",
            "whale_data_grad_mode", "whale_data_grad_passes", "whale_set_devices", "whale_multi_create", "whale_multi_destroy",
            "whale_multi_ndev", "whale_multi_shard_size", "whale_multi_logpdf_grad", "whale_peer_export", "whale_peer_import",
-           "whale_peer_ready", "whale_backtrack_device", "whale_track_sample", "whale_trees_counts", "whale_trees_view",
+           "whale_peer_ready", "whale_peer_sum_async", "whale_backtrack_device", "whale_track_sample", "whale_trees_counts", "whale_trees_view",
            "whale_trees_get", "whale_trees_summary"]
 
 
@@ -114,6 +114,7 @@ class Lib:
         L.whale_peer_export.argtypes = [vp, C.c_int32, C.c_int32, vp]
         L.whale_peer_import.argtypes = [vp, C.c_int32, vp]
         L.whale_peer_ready.argtypes = [vp]
+        L.whale_peer_sum_async.argtypes = [vp, vp, vp]
         L.whale_set_devices.argtypes = [C.c_int32, i32p]
         L.whale_multi_create.argtypes = [C.POINTER(ModelDesc), C.POINTER(CCDDesc), C.POINTER(vp)]
         L.whale_multi_destroy.argtypes = [vp]
