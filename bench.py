@@ -337,7 +337,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     # synthetic inputs first (worker processes are forked here, before this process touches CUDA)
-    d, gen_s = dataset(rank, args.families)
+    d, gen_s = dataset(0 if os.environ.get("WHALE_BENCH_SAME_DATA") else rank, args.families)  # (diagnosis: every rank rank 0's shard)
     d3 = n3 = gen3_s = None
     if args.c3_families > 0:
         d3, n3, gen3_s = c3_dataset(rank, world, args.c3_families)
@@ -433,6 +433,34 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     value = F * world * K / (total_ms * 1e-3)
+    # per-rank view of the same steps (who waits for whom) and the exchange timed alone, back to back
+    ranks = None
+    if world > 1:
+        mine = torch.tensor([float(step_ms.mean()), *kms.mean(axis=0).tolist(), float(clocks["sm_mhz"] or 0),
+                             float(len(clocks["reasons"]))], device="cuda", dtype=torch.float64)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        Z = torch.zeros(1 + P, device="cuda", dtype=torch.float64)
+        NX = 200
+        evx = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(NX)]
+        for rep in range(2):  # first round: warm-up
+            dist.barrier()
+            torch.cuda.synchronize()
+            for i in range(NX):
+                evx[i][0].record()
+                if peer:
+                    L.check(L.L.whale_peer_sum_async(dh, Z.data_ptr(), stream))
+                else:
+                    dist.all_reduce(Z)
+                evx[i][1].record()
+            torch.cuda.synchronize()
+        xus = np.array([a.elapsed_time(b) for a, b in evx]) * 1e3
+        r = torch.stack(allr).cpu().numpy()
+        ranks = {"step_events_ms": r[:, 0].tolist(), "k_tables_ms": r[:, 1].tolist(), "k_dp_ms": r[:, 2].tolist(),
+                 "sm_mhz": r[:, 4].tolist(), "throttle_reasons": r[:, 5].tolist(),
+                 "exchange_alone_us_rank0": {"median": float(np.median(xus)), "p90": float(np.percentile(xus, 90)),
+                                             "note": "the exchange kernel (or the NCCL all-reduce) enqueued 200 times back to "
+                                                     "back with nothing else in the stream, CUDA event pair around each"}}
 
     # ---- e2e: the reference-facing call with HOST buffers ----
     pin_x = torch.empty(P, dtype=torch.float64).pin_memory()
@@ -541,6 +569,8 @@ def main():
         "loglik_last": float(last[0]),
         "grad_mode": "reverse" if L.L.whale_data_grad_mode(dh) == 1 else "forward",
     }
+    if ranks is not None:
+        out["ranks"] = ranks
     if c3 is not None:
         out["c3_strong"] = c3
     if world == 1 and not args.no_cpu_baseline:

@@ -704,6 +704,10 @@ static cudaError_t launch_tables3(whale_model* m, const double* d_x, const doubl
     return cudaSuccess;
 }
 
+// largest dynamic shared-memory request that still lets `per_sm` CTAs share an SM (228 KB per SM, 1 KB reserved per CTA)
+static size_t occupancy_line(int per_sm) { return (size_t)(228 * 1024) / (size_t)std::max(1, per_sm) - 1024; }
+static size_t ctas_per_sm_by_smem(size_t need) { return (size_t)(228 * 1024) / (std::min<size_t>(need, 227 * 1024) + 1024); }
+
 // shared-memory budget of every family under tangent plan `pl` (stored at index g); returns the largest need
 static size_t set_budgets(whale_data* D, int g, const Plan& pl) {
     const whale_model* m = D->m;
@@ -756,6 +760,24 @@ static size_t set_budgets(whale_data* D, int g, const Plan& pl) {
     size_t cur = worst_a.load();
     while (worst > cur && !worst_a.compare_exchange_weak(cur, worst)) {}
     });
+    // A launch requests the largest need of its bin for every CTA: a handful of families just above the size that still lets
+    // dp_minb() families share an SM would cost the whole batch a quarter of its resident families (measured on the B200:
+    // a 1000-family shard whose largest family needs 57.7 KB ran at 3 per SM, k_dp 0.338 instead of 0.280 ms).  Those few
+    // read their lists in place instead (stage_bytes = 0) when that brings them under the line.
+    const size_t line = occupancy_line(dp_minb());
+    if (worst_a.load() > line) {
+        int over = 0;
+        for (int f = 0; f < D->F; f++) over += smem_need(m, D->hdr[f], g, pl.Kmax) > line;
+        if (over * 4 <= D->F) {
+            size_t worst = 0;
+            for (int f = 0; f < D->F; f++) {
+                FamHdr& H = D->hdr[f];
+                if (smem_need(m, H, g, pl.Kmax) > line && smem_need(m, H, g, pl.Kmax) - H.stage_bytes[g] <= line) H.stage_bytes[g] = 0;
+                worst = std::max(worst, smem_need(m, H, g, pl.Kmax));
+            }
+            worst_a.store(worst);
+        }
+    }
     return worst_a.load();
 }
 
@@ -787,7 +809,7 @@ static cudaError_t order_families(whale_data* D, int g, const std::vector<double
     int i = 0;
     // a bin = families that allow the same number of resident CTAs per SM (capped by the register limit):
     // a smaller shared-memory request buys nothing once registers are the limiter
-    auto cls = [&](size_t nd) { return std::min<size_t>((size_t)(rev ? rev_minb() : dp_minb()), (227 * 1024) / std::max<size_t>(nd, 1)); };
+    auto cls = [&](size_t nd) { return std::min<size_t>((size_t)(rev ? rev_minb() : dp_minb()), ctas_per_sm_by_smem(nd)); };
     while (i < F) {
         Bin b{i, 0, need[perm[i]]};
         while (i < F && (cls(need[perm[i]]) == cls(b.smem) || b.count < 64 || (int)bins.size() >= MAX_BINS - 1)) { i++; b.count++; }
@@ -797,6 +819,10 @@ static cudaError_t order_families(whale_data* D, int g, const std::vector<double
     if (bins.size() > 1 && bins.back().count < 64) { bins[bins.size() - 2].count += bins.back().count; bins.pop_back(); }
     for (const Bin& b : bins)
         std::stable_sort(perm.begin() + b.off, perm.begin() + b.off + b.count, [&](int x, int y) { return work[x] > work[y]; });
+    if (env_int("WHALE_DEBUG_BINS", 0))
+        for (const Bin& b : bins)
+            fprintf(stderr, "[whale] plan %d%s bin: off %d count %d smem %zu (families per SM %zu); largest need %zu, smallest %zu\n", g,
+                    rev ? " (reverse)" : "", b.off, b.count, b.smem, cls(b.smem), need[perm[0]], need[perm[F - 1]]);
     if (rev) {  // persistent CTAs: as many as the GPU holds at this bin's shared-memory need, one history slot each
         D->rev_grid.clear(); D->rev_slot0.clear();
         int slot = 0;
@@ -1452,6 +1478,23 @@ static size_t set_budgets_rev(whale_data* D) {
     amax(hist_a, hist_max);
     });
     D->hist_stride = (hist_a.load() + 1) & ~size_t(1);
+    // the few families just above the rev_minb()-per-SM line read their lists in place (see set_budgets)
+    const size_t line = occupancy_line(rev_minb());
+    if (worst_a.load() > line) {
+        int over = 0;
+        for (int f = 0; f < D->F; f++) over += smem_need_rev(m, D->hdr[f], D->rhdr[f]) > line;
+        if (over * 4 <= D->F) {
+            size_t worst = 0;
+            for (int f = 0; f < D->F; f++) {
+                RevHdr& H = D->rhdr[f];
+                const size_t nd = smem_need_rev(m, D->hdr[f], H);
+                if (nd > line && nd - H.stage2_bytes <= line) { H.stage2_bytes = 0; H.root_staged = 0; }
+                else if (nd > line && nd - H.stage2_bytes - H.stage_bytes <= line) { H.stage_bytes = 0; H.stage2_bytes = 0; H.root_staged = 0; }
+                worst = std::max(worst, smem_need_rev(m, D->hdr[f], H));
+            }
+            worst_a.store(worst);
+        }
+    }
     return worst_a.load();
 }
 
