@@ -50,6 +50,8 @@ inline double __hiloint2double(int hi, int lo) {
     uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
     double d; memcpy(&d, &u, 8); return d;
 }
+inline int __double2hiint(double d) { uint64_t u; memcpy(&u, &d, 8); return (int)(uint32_t)(u >> 32); }
+inline int __double2loint(double d) { uint64_t u; memcpy(&u, &d, 8); return (int)(uint32_t)u; }
 inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 using std::min;
 using std::max;

@@ -371,6 +371,16 @@ def test_emu_peer_sum_two_ranks_in_one_process(L):
     L.L.whale_model_destroy(mh)
 
 
+@pytest.mark.parametrize("env", [{"WHALE_PEER_FUSE": "0"}, {"WHALE_GRAD_MODE": "fwd"}, {"WHALE_GRAD_MODE": "fwd", "WHALE_PEER_FUSE": "0"}])
+def test_emu_peer_sum_variants(env):
+    """The exchange as its own launch (WHALE_PEER_FUSE=0) and behind the forward-tangent kernel: process-wide switches,
+    so the two-rank test above runs again in a child process."""
+    import sys
+    out = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", __file__, "-k", "test_emu_peer_sum_two_ranks_in_one_process"],
+                         env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "1 passed" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_emu_landplant_dt001(L, monkeypatch):
     """The tutorial's Δt = 0.01 discretisation (3 765 slices): the two smallest families of the fixture, both gradient modes."""
     g = load_golden("landplant_dt0.01")

@@ -1,6 +1,8 @@
 """Parity of the CUDA path against the oracle, through the C ABI, on the B200 (-m gpu).
 
 Bar (north star): log-likelihoods and gradients within 1e-9 relative in fp64; integer packing bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -288,6 +290,34 @@ def test_multi_device_handle(L):
     from conftest import multi_device_vs_golden
     n = L.L.whale_device_count()
     multi_device_vs_golden(L, list(range(n)) if n > 1 else [0, 0])
+
+
+@pytest.mark.parametrize("env", [{}, {"WHALE_PEER_FUSE": "0"}, {"WHALE_GRAD_MODE": "fwd"}])
+def test_peer_sum_between_processes(tmp_path, env):
+    """SURVEY §8e, one process per GPU: whale_peer_export / whale_peer_import + WHALE_PEER_SUM between two (one-GPU box:
+    both on device 0, time-sliced) or four processes; every rank must see the full-batch golden total with identical bits.
+    Default = the exchange in the tail of the DP kernel; WHALE_PEER_FUSE=0 = its own launch; forward-tangent kernel."""
+    import subprocess
+    import sys
+    import glob
+    world = 2
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "peer_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(r), str(world), str(tmp_path)], env=dict(os.environ, **env),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=600)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append(o)
+    for r, p in enumerate(procs):
+        assert p.returncode == 0 and f"rank {r} ok" in outs[r], outs[r][-3000:]
+    for f0 in glob.glob(str(tmp_path / "ll_r0_*.txt")):  # same bits on every rank (fixed summation order)
+        f1 = f0.replace("ll_r0_", "ll_r1_")
+        assert open(f0).read() == open(f1).read(), (f0, open(f0).read(), open(f1).read())
 
 
 def test_arena_cache_round_trip_on_device(L, tmp_path):

@@ -245,6 +245,81 @@ __device__ __forceinline__ D1 dpowi(D1 a, int n) {  // a^n, n >= 0
 __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
 // ---------------------------------------------------------------------------------------------------------
+// One-shot sum over ranks through peer memory (one process per GPU).  Every rank owns an exchange buffer
+//   [2 parities][world slots][2n packets of 8 bytes]
+// that all peers have mapped (CUDA IPC over NVLink).  A packet carries half a double and the step's 32-bit tag in ONE
+// 64-bit store (data and flag cannot be seen apart, so no fence and no second round trip is needed — the "LL" idea of
+// collective libraries): rank r stores the 2n packets of its n = 1+P doubles into slot r of EVERY rank's buffer, then polls
+// the world's packets in its own buffer until they carry the tag and adds the slots in rank order — the same order on
+// every rank, so all ranks hold bit-identical totals.  Parity double-buffering is enough: a rank can start step s+1 only
+// after every peer has entered the exchange of step s.  The step counter lives on the device (advanced here), so the
+// exchange can ride in the tail of the DP kernel (dp_tail_reduce) or run as its own launch (k_peer_sum) alike.
+// ---------------------------------------------------------------------------------------------------------
+struct PeerDev {
+    double* bufs[16];  // exchange buffer of every rank, as mapped in THIS process (bufs[rank] = own)
+    int rank, world, n;
+    int status;        // set to 1 when a peer did not show up in time
+    unsigned long long seq;  // exchanges completed
+};
+#ifdef WHALE_EMU
+#define ST_RELAXED_SYS(p, v) (*(volatile unsigned long long*)(p) = (v))
+#define LD_RELAXED_SYS(p) (*(volatile const unsigned long long*)(p))
+#else
+#define ST_RELAXED_SYS(p, v) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory")
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+#define LD_RELAXED_SYS(p) ld_relaxed_sys_(p)
+#endif
+__host__ __device__ inline size_t peer_buf_bytes(int world, int n) { return (size_t)2 * world * 2 * n * sizeof(unsigned long long); }
+__host__ __device__ inline size_t peer_smem_bytes(int world, int n) { return (size_t)world * 2 * n * sizeof(unsigned); }
+
+// whole CTA (NT threads); `out` holds this rank's n doubles (visible to the CTA) and receives the world's total;
+// s_w: world·2n words of shared memory
+template <int NT>
+__device__ __forceinline__ void peer_exchange(PeerDev* PD, double* out, unsigned* s_w) {
+    const int tid = threadIdx.x, W = PD->world, n = PD->n, rank = PD->rank, n2 = 2 * n;
+    const unsigned long long seq = PD->seq + 1;
+    const int par = (int)(seq & 1ull);
+    const unsigned tag = (unsigned)(seq % 0xFFFFFFFFull) + 1u;  // never 0 (the buffers start zeroed)
+    for (int idx = tid; idx < W * n2; idx += NT) {
+        const int q = idx / n2, j = idx - q * n2;
+        const double v = out[j >> 1];
+        const unsigned w = (j & 1) ? (unsigned)__double2hiint(v) : (unsigned)__double2loint(v);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(PD->bufs[q]) + ((size_t)par * W + rank) * n2 + j;
+        ST_RELAXED_SYS(dst, ((unsigned long long)tag << 32) | w);
+    }
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(PD->bufs[rank]) + (size_t)par * W * n2;
+    int bad = 0;
+    for (int idx = tid; idx < W * n2; idx += NT) {
+        const long long t0 = CLOCK64();
+        unsigned long long pk;
+        while ((unsigned)((pk = LD_RELAXED_SYS(mine + idx)) >> 32) != tag) {
+#ifdef WHALE_EMU
+            break;  // (the emulation runs the ranks one after another: no waiting)
+#endif
+            if (CLOCK64() - t0 > 20000000000LL) { bad = 1; break; }  // ~10 s: a peer is gone
+        }
+        s_w[idx] = (unsigned)pk;
+    }
+    bad = __syncthreads_or(bad);
+    double t0v = 0.0;
+    for (int q = 0; q < W; q++) t0v += __hiloint2double((int)s_w[q * n2 + 1], (int)s_w[q * n2]);
+    const bool fin = isfinite(t0v) && !bad;  // ℓhood (src/core.jl:15) on the world's total
+    for (int j = tid; j < n; j += NT) {
+        double t = 0.0;
+        for (int q = 0; q < W; q++) t += __hiloint2double((int)s_w[q * n2 + 2 * j + 1], (int)s_w[q * n2 + 2 * j]);
+        out[j] = fin ? t : (j == 0 ? -dinf() : 0.0);
+    }
+    if (tid == 0) {
+        PD->seq = seq;
+        if (bad) PD->status = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Row placement in shared memory.  A branch's last row is live from the moment it is computed until its
 // parent's row 1 has been formed (the root's children until the end), so rows are placed first-fit into the
 // gaps left by rows that are already dead; the peak is ~60 % of the plain sum Σ_e C_e K_e for a 9-taxon tree.

@@ -40,6 +40,7 @@ struct DPArgs {
     int n_total;         // F
     int cond_kind, first;
     double* out;         // [1+P]
+    PeerDev* peer;       // fused exchange over ranks behind the fused reduction (nullptr: off)
 };
 // tim layout: [0..7] phases, [8 + oi] slice-loop cycles of inner node oi, [8 + TIMN + oi] staging + row-1 cycles
 constexpr int TIMN = 32, TIMW = 8 + 2 * TIMN;
@@ -622,6 +623,7 @@ struct TailArgs {
     int cond_kind, first;
     double* out;            // [1+P]
     const int* act;         // [nn * Kmax]
+    PeerDev* peer;          // one process per GPU: the sum over ranks follows in the same CTA (nullptr: off)
 };
 // `count` = families this CTA finished (1 for k_dp; the persistent CTAs of k_dp_rev report their share on exit)
 template <int NT>
@@ -678,6 +680,10 @@ __device__ __forceinline__ void dp_tail_reduce(const TailArgs& A, int count, dou
         else A.out[1 + A.act[root * Kmax + k]] = finite ? s_tot[k] : 0.0;
     }
     if (tid == 0) *A.done = 0u;
+    if (A.peer) {  // WHALE_PEER_SUM of a one-pass evaluation: `out` is complete, exchange it right here
+        __syncthreads();
+        peer_exchange<NT>(A.peer, A.out, reinterpret_cast<unsigned*>(s_tot));
+    }
 }
 
 template <int NT, int MINB>
@@ -1040,7 +1046,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         }
     }
     if (A.done) {
-        const TailArgs TA{A.done, A.n_total, M.root, PL.K, PL.Kmax, A.out_fam, PL.cond, A.cond_kind, A.first, A.out, PL.act};
+        const TailArgs TA{A.done, A.n_total, M.root, PL.K, PL.Kmax, A.out_fam, PL.cond, A.cond_kind, A.first, A.out, PL.act, A.peer};
         dp_tail_reduce<NT>(TA, 1, reinterpret_cast<double*>(smem_raw));
     }
 }

@@ -139,74 +139,8 @@ __global__ void __launch_bounds__(256) k_dfma(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// One-shot sum over ranks through peer memory (one process per GPU).  Every rank owns an exchange
-// buffer  [2 parities][world slots][n doubles] | [2][world] sequence flags  that all peers have mapped (CUDA IPC over
-// NVLink).  Rank r stores its n = 1+P doubles into slot r of EVERY rank's buffer, fences, then publishes the step's
-// sequence number in flag r of every rank; it then waits for the world's flags in its own buffer and adds the slots in
-// rank order — the same order on every rank, so all ranks hold bit-identical totals.  Parity double-buffering is
-// enough: a rank can start step s+1 only after every peer has entered the exchange of step s.
-// ---------------------------------------------------------------------------------------------------------
-struct PeerArgs {
-    double* bufs[16];  // exchange buffer of every rank, as mapped in THIS process (bufs[rank] = own)
-    int rank, world, n;
-    unsigned long long seq;
-    double* out;       // local (1+P) result of this rank's evaluation; overwritten with the world's total
-    int* status;       // set to 1 when a peer did not show up in time
-};
-#ifdef WHALE_EMU
-#define ST_RELEASE_SYS(p, v) (*(volatile unsigned long long*)(p) = (v))
-#define LD_ACQUIRE_SYS(p) (*(volatile const unsigned long long*)(p))
-#define FENCE_SYS() __threadfence()
-#else
-#define ST_RELEASE_SYS(p, v) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory")
-__device__ __forceinline__ unsigned long long ld_acquire_sys_(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-#define LD_ACQUIRE_SYS(p) ld_acquire_sys_(p)
-#define FENCE_SYS() __threadfence_system()
-#endif
-__global__ void __launch_bounds__(128) k_peer_sum(PeerArgs A) {
-    const int tid = threadIdx.x, W = A.world, n = A.n, par = (int)(A.seq & 1ull);
-    const size_t slots = (size_t)2 * W * n;  // doubles before the flags
-    for (int q = 0; q < W; q++) {
-        double* dst = A.bufs[q] + ((size_t)par * W + A.rank) * n;
-        for (int j = tid; j < n; j += blockDim.x) dst[j] = A.out[j];
-    }
-    FENCE_SYS();
-    __syncthreads();
-    if (tid < W) {
-        unsigned long long* f = reinterpret_cast<unsigned long long*>(A.bufs[tid] + slots) + (size_t)par * W + A.rank;
-        ST_RELEASE_SYS(f, A.seq);
-    }
-    __shared__ int s_bad;
-    if (tid == 0) s_bad = 0;
-    __syncthreads();
-    if (tid < W) {
-        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(A.bufs[A.rank] + slots) + (size_t)par * W + tid;
-        const long long t0 = CLOCK64();
-        while (LD_ACQUIRE_SYS(f) != A.seq) {
-            if (CLOCK64() - t0 > 20000000000LL) { s_bad = 1; break; }  // ~10 s: a peer is gone
-#ifdef WHALE_EMU
-            break;
-#endif
-        }
-    }
-    __syncthreads();
-    const double* mine = A.bufs[A.rank] + (size_t)par * W * n;
-    __shared__ int s_fin;
-    if (tid == 0) {
-        double t = 0.0;
-        for (int q = 0; q < W; q++) t += mine[(size_t)q * n];
-        s_fin = (isfinite(t) && !s_bad) ? 1 : 0;  // ℓhood (src/core.jl:15) on the world's total
-        if (s_bad) *A.status = 1;
-    }
-    __syncthreads();
-    for (int j = tid; j < n; j += blockDim.x) {
-        double t = 0.0;
-        for (int q = 0; q < W; q++) t += mine[(size_t)q * n + j];
-        A.out[j] = s_fin ? t : (j == 0 ? -dinf() : 0.0);
-    }
+// the exchange as its own launch (evaluations in several passes, whale_peer_sum_async); see peer_exchange in whale_common.cuh
+__global__ void __launch_bounds__(128) k_peer_sum(PeerDev* PD, double* out) {
+    EXTERN_SHARED(psm);
+    peer_exchange<128>(PD, out, reinterpret_cast<unsigned*>(psm));
 }

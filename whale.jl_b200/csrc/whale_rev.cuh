@@ -49,6 +49,7 @@ struct RevArgs {
     unsigned int* done;
     int n_total, cond_kind;
     double* out;
+    PeerDev* peer;  // fused exchange over ranks behind the fused reduction (nullptr: off)
 };
 
 // Σ_t p_t·X[i1·sx]·Y[i2·sy] over entries tb, tb+step, ... < te; two entries in flight
@@ -895,7 +896,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp_rev(RevArgs A) {
         }
     }
     if (A.done) {
-        TailArgs TA{A.done, A.n_total, root, PG.K, KmaxG, A.out_fam, PG.cond, A.cond_kind, 1, A.out, PG.act};
+        TailArgs TA{A.done, A.n_total, root, PG.K, KmaxG, A.out_fam, PG.cond, A.cond_kind, 1, A.out, PG.act, A.peer};
         dp_tail_reduce<NT>(TA, nfam_done, reinterpret_cast<double*>(smem_raw));
     }
 }

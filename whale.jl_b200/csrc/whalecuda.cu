@@ -270,8 +270,9 @@ struct whale_data {
     int peer_rank = -1, peer_world = 0;
     double* peer_bufs[16] = {};
     bool peer_open[16] = {};
-    int* d_peer_status = nullptr;
-    unsigned long long peer_seq = 0;
+    PeerDev* d_peer = nullptr;   // device-resident exchange state (buffers of all ranks, step counter)
+    bool peer_uploaded = false;
+    bool peer_fused = false;     // the evaluation just enqueued carried the exchange in the DP kernel's tail
 };
 
 // `subset`: which raw parameters this plan differentiates (empty = none: the value-only plan)
@@ -657,6 +658,10 @@ static bool pdl_enabled() {  // programmatic dependent launch of the DP kernel b
     static bool f = env_int("WHALE_PDL", 1) != 0;
     return f;
 }
+static bool peer_fusion() {  // WHALE_PEER_FUSE=0: the exchange over ranks always as its own launch (k_peer_sum)
+    static bool f = env_int("WHALE_PEER_FUSE", 1) != 0;
+    return f;
+}
 static bool fused_reduce() {
     static bool f = env_int("WHALE_FUSED_REDUCE", 1) != 0;
     return f;
@@ -784,6 +789,7 @@ static size_t set_budgets(whale_data* D, int g, const Plan& pl) {
 static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, int32_t condition, uint32_t flags,
                             double* d_out, cudaStream_t st);
 static int32_t enqueue_peer_sum(whale_data* D, double* d_out, cudaStream_t st);
+static int32_t peer_state(whale_data* D, PeerDev** out);
 static int32_t finalize_data(whale_model* m, whale_data* D, whale_data_t* out);
 
 // Launch order of plan g's families for a given per-family work vector (predicted flops at pack time, measured SM
@@ -1880,7 +1886,7 @@ int32_t whale_data_destroy(whale_data_t d) {
     for (int q = 0; q < 16; q++) if (d->peer_open[q] && d->peer_bufs[q]) cudaIpcCloseMemHandle(d->peer_bufs[q]);
 #endif
     if (d->peer_rank >= 0) cudaFree(d->peer_bufs[d->peer_rank]);
-    cudaFree(d->d_peer_status);
+    cudaFree(d->d_peer);
     cudaFree(d->d_rarena); cudaFree(d->d_rhdr); cudaFree(d->d_aoff); cudaFree(d->d_hist); cudaFree(d->d_next);
     for (int i = 0; i < MAX_BINS; i++) {
         if (d->side[i]) cudaStreamDestroy(d->side[i]);
@@ -1954,12 +1960,19 @@ static int32_t enqueue_eval_rev(whale_model* m, whale_data* D, const double* d_x
     double* out_fam = D->d_out_fam + D->out_off[1];
     const bool fused = fused_reduce() && (size_t)F * KR <= ((size_t)1 << 20) && KR <= 1024;
     const std::vector<Bin>& bins = D->bins[1];
-    const size_t tail_smem = (size_t)(NT + 2 * KR + 2) * sizeof(double);
+    size_t tail_smem = (size_t)(NT + 2 * KR + 2) * sizeof(double);
+    PeerDev* peer = nullptr;  // the sum over ranks rides in the tail of the same kernel (one pass, fused reduction)
+    if ((flags & WHALE_PEER_SUM) && fused && peer_fusion()) {
+        int32_t rcp = peer_state(D, &peer);
+        if (rcp != WHALE_OK) return rcp;
+        tail_smem = std::max(tail_smem, peer_smem_bytes(D->peer_world, 1 + m->P));
+        D->peer_fused = true;
+    }
     auto launch_bin = [&](size_t b, cudaStream_t s) {
         RevArgs a{m->dev, m->planR.dev, pg.dev, m->planL.dev, D->d_arena, D->d_hdr, D->d_rarena, D->d_rhdr, D->d_perm[1],
                   D->d_roff[1], D->d_aoff, out_fam, D->d_hist, (unsigned long long)D->hist_stride, D->d_next + b,
                   bins[b].off, bins[b].count, D->rev_slot0[b], prof ? D->d_tim : nullptr, fused ? D->d_done : nullptr, F,
-                  condition, d_out};
+                  condition, d_out, peer};
         const bool pdl = pdl_enabled() && bins.size() == 1;
 #define LAUNCHV(NTV, MBV)                                                                                                   \
     if (NT == NTV && MB == MBV) {                                                                                           \
@@ -2028,7 +2041,7 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
     const int NT = dp_nt();
     if (grad && D->rev) {
         if (keep) {  // logpdf! + gradient: ℓ comes from the value-only forward kernel, the gradient from the reverse pass
-            int32_t rck = enqueue_eval(m, D, d_x, condition, flags & ~WHALE_WANT_GRAD, d_out, st);
+            int32_t rck = enqueue_eval(m, D, d_x, condition, flags & ~(WHALE_WANT_GRAD | WHALE_PEER_SUM), d_out, st);
             if (rck != WHALE_OK) return rck;
         }
         return enqueue_eval_rev(m, D, d_x, condition, flags, d_out, st);
@@ -2053,12 +2066,18 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
         double* out_fam = D->d_out_fam + D->out_off[g];
         // the ℓ kept for backtracking is written by the first pass only (values do not depend on the chunk)
         DPArgs a{m->dev, pl.dev, D->d_arena, D->d_hdr, D->d_perm[g], D->d_roff[g], out_fam, (keep && first) ? D->d_ell : nullptr, (int)g,
-                 keep ? 0 : 1, (prof && first) ? D->d_tim : nullptr, nullptr, F, condition, first ? 1 : 0, d_out};
+                 keep ? 0 : 1, (prof && first) ? D->d_tim : nullptr, nullptr, F, condition, first ? 1 : 0, d_out, nullptr};
         // K3 rides in the tail of K2 (the last CTA to finish reduces) unless the sum is too long for one CTA
         const bool fused = fused_reduce() && (size_t)F * pl.K[m->root] <= ((size_t)1 << 20) && pl.K[m->root] <= 1024;
         if (fused) a.done = D->d_done;
         const int MB = dp_minb();
-        const size_t tail_smem = (size_t)(NT + 2 * pl.K[m->root] + 2) * sizeof(double);  // the fused reduction's scratch
+        size_t tail_smem = (size_t)(NT + 2 * pl.K[m->root] + 2) * sizeof(double);  // the fused reduction's scratch
+        if ((flags & WHALE_PEER_SUM) && fused && g1 - g0 == 1 && peer_fusion()) {  // one pass: the sum over ranks rides in the tail
+            int32_t rcp = peer_state(D, &a.peer);
+            if (rcp != WHALE_OK) return rcp;
+            tail_smem = std::max(tail_smem, peer_smem_bytes(D->peer_world, 1 + m->P));
+            D->peer_fused = true;
+        }
         auto launch_bin = [&](const Bin& b, cudaStream_t s) {
             const bool pdl = pdl_enabled() && bins.size() == 1;
 #define LAUNCHV(NTV, MBV)                                                                                                   \
@@ -2104,8 +2123,9 @@ int32_t whale_logpdf_grad_async(whale_model_t m, whale_data_t d, const double* d
     if (!m || !d || !d_x || !d_out) return fail(WHALE_ERR_ARG, "null argument");
     if (d->m != m) return fail(WHALE_ERR_ARG, "data handle belongs to another model");
     CU(cudaSetDevice(m->device));
+    d->peer_fused = false;
     int32_t rc = enqueue_eval(m, d, d_x, condition, flags, d_out, (cudaStream_t)stream);
-    if (rc == WHALE_OK && (flags & WHALE_PEER_SUM)) rc = enqueue_peer_sum(d, d_out, (cudaStream_t)stream);
+    if (rc == WHALE_OK && (flags & WHALE_PEER_SUM) && !d->peer_fused) rc = enqueue_peer_sum(d, d_out, (cudaStream_t)stream);
     return rc;
 }
 
@@ -2168,9 +2188,10 @@ int32_t whale_logpdf_grad(whale_model_t m, whale_data_t d, const double* x, cons
     if (!done) {
         CU(cudaMemcpyAsync(m->d_x, hp, P * sizeof(double), cudaMemcpyHostToDevice, m->stream));
         CU(cudaMemcpyAsync(m->d_pleaf, hp + P, nn * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+        d->peer_fused = false;
         int32_t rc = enqueue_eval(m, d, m->d_x, condition, flags, m->d_out, m->stream);
         if (rc != WHALE_OK) return rc;
-        if (flags & WHALE_PEER_SUM) {  // one process per GPU: the world's total comes back, on every rank
+        if ((flags & WHALE_PEER_SUM) && !d->peer_fused) {  // one process per GPU: the world's total comes back, on every rank
             rc = enqueue_peer_sum(d, m->d_out, m->stream);
             if (rc != WHALE_OK) return rc;
         }
@@ -2911,15 +2932,15 @@ int32_t whale_peer_export(whale_data_t d, int32_t rank, int32_t world, void* han
     whale_model* m = d->m;
     CU(cudaSetDevice(m->device));
     const size_t n = 1 + (size_t)m->P;
-    const size_t bytes = (2 * (size_t)world * n) * sizeof(double) + 2 * (size_t)world * sizeof(unsigned long long);
+    const size_t bytes = peer_buf_bytes(world, (int)n);
     if (!d->peer_bufs[rank] || d->peer_world != world || d->peer_rank != rank) {
         if (d->peer_rank >= 0 && d->peer_bufs[d->peer_rank]) cudaFree(d->peer_bufs[d->peer_rank]);
         memset(d->peer_bufs, 0, sizeof(d->peer_bufs));
         memset(d->peer_open, 0, sizeof(d->peer_open));
         CU(cudaMalloc((void**)&d->peer_bufs[rank], bytes));
         CU(cudaMemset(d->peer_bufs[rank], 0, bytes));
-        if (!d->d_peer_status) { CU(cudaMalloc((void**)&d->d_peer_status, sizeof(int))); CU(cudaMemset(d->d_peer_status, 0, sizeof(int))); }
-        d->peer_rank = rank; d->peer_world = world; d->peer_seq = 0;
+        if (!d->d_peer) CU(cudaMalloc((void**)&d->d_peer, sizeof(PeerDev)));
+        d->peer_rank = rank; d->peer_world = world; d->peer_uploaded = false;
     }
 #ifndef WHALE_EMU
     cudaIpcMemHandle_t hnd;
@@ -2946,6 +2967,7 @@ int32_t whale_peer_import(whale_data_t d, int32_t peer, const void* handle64) {
     CU(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
     d->peer_bufs[peer] = (double*)p;
     d->peer_open[peer] = true;
+    d->peer_uploaded = false;
 #else
     memcpy(&d->peer_bufs[peer], handle64, sizeof(void*));
 #endif
@@ -2958,16 +2980,26 @@ int32_t whale_peer_ready(whale_data_t d) {
     return 1;
 }
 
+// the device-resident exchange state, uploaded once every peer's buffer is known
+static int32_t peer_state(whale_data* D, PeerDev** out) {
+    if (!whale_peer_ready(D)) return fail(WHALE_ERR_STATE, "WHALE_PEER_SUM without a complete whale_peer_export / whale_peer_import exchange");
+    if (!D->peer_uploaded) {
+        PeerDev h{};
+        for (int q = 0; q < D->peer_world; q++) h.bufs[q] = D->peer_bufs[q];
+        h.rank = D->peer_rank; h.world = D->peer_world; h.n = 1 + D->m->P; h.status = 0; h.seq = 0;
+        CU(cudaMemcpy(D->d_peer, &h, sizeof(h), cudaMemcpyHostToDevice));
+        D->peer_uploaded = true;
+    }
+    *out = D->d_peer;
+    return WHALE_OK;
+}
+
 // enqueue the exchange behind an evaluation that left its local (1+P) result in d_out
 static int32_t enqueue_peer_sum(whale_data* D, double* d_out, cudaStream_t st) {
-    if (!whale_peer_ready(D)) return fail(WHALE_ERR_STATE, "WHALE_PEER_SUM without a complete whale_peer_export / whale_peer_import exchange");
-    PeerArgs a{};
-    for (int q = 0; q < D->peer_world; q++) a.bufs[q] = D->peer_bufs[q];
-    a.rank = D->peer_rank; a.world = D->peer_world; a.n = 1 + D->m->P;
-    a.seq = ++D->peer_seq;
-    a.out = d_out;
-    a.status = D->d_peer_status;
-    LAUNCH(k_peer_sum, 1, 128, 0, st, a);
+    PeerDev* pd = nullptr;
+    int32_t rc = peer_state(D, &pd);
+    if (rc != WHALE_OK) return rc;
+    LAUNCH(k_peer_sum, 1, 128, peer_smem_bytes(D->peer_world, 1 + D->m->P), st, pd, d_out);
     g_launches++;
     CU(cudaGetLastError());
     return WHALE_OK;
