@@ -73,6 +73,7 @@ inline thread_local Cta* g_cta = nullptr;
 inline thread_local Barrier* g_bar = nullptr;
 inline thread_local std::vector<Barrier>* g_wbar = nullptr;
 inline thread_local unsigned char* g_smem = nullptr;
+inline thread_local size_t g_smem_bytes = 0;
 inline thread_local const std::function<void()>* g_body = nullptr;
 inline void yield() {
     Cta* c = g_cta;
@@ -102,6 +103,7 @@ inline void run_cta(int b, int grid, int block, size_t smem, const std::function
     cta.ctx.resize(block); cta.done.assign(block, 0); cta.or_phase.assign(block, 0);
     g_cta = &cta; g_bar = &bar; g_wbar = &wb; g_body = &body;
     g_smem = (unsigned char*)(((uintptr_t)sm.data() + 15) & ~(uintptr_t)15);
+    g_smem_bytes = smem;
     blockIdx.x = b; blockDim.x = block; gridDim.x = grid;
     for (int t = 0; t < block; t++) {
         getcontext(&cta.ctx[t]);

@@ -6,6 +6,7 @@
 #include "cuda_emu.h"
 #define LAUNCH(kern, grid, block, smem, st, ...) emu::launch(grid, block, smem, [=]() { kern(__VA_ARGS__); })
 #define LAUNCH_PDL(kern, grid, block, smem, st, ...) LAUNCH(kern, grid, block, smem, st, __VA_ARGS__)
+#define DYN_SMEM_BYTES() ((unsigned)emu::g_smem_bytes)
 #define GRID_DEP_WAIT() ((void)0)
 #define GRID_DEP_LAUNCH() ((void)0)
 #else
@@ -30,6 +31,13 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block
     return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 #define LAUNCH_PDL(kern, grid, block, smem, st, ...) launch_pdl(kern, grid, block, smem, st, __VA_ARGS__)
+// dynamic shared memory of this launch (the bin's largest need: a smaller family has spare room behind its own carve-up)
+static __device__ __forceinline__ unsigned dyn_smem_bytes_() {
+    unsigned v;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(v));
+    return v;
+}
+#define DYN_SMEM_BYTES() dyn_smem_bytes_()
 #define GRID_DEP_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 #define GRID_DEP_LAUNCH() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #endif

@@ -607,8 +607,9 @@ int32_t whale_model_create(const whale_model_desc* d, whale_model_t* out) {
         CU(cudaGetDeviceProperties(&pr, g_device));
         m->n_sm = std::max(1, pr.multiProcessorCount);
     }
-    CU(cudaMalloc((void**)&m->d_x, std::max(1, m->P) * sizeof(double)));
-    CU(cudaMalloc((void**)&m->d_pleaf, nn * sizeof(double)));
+    // θ and the leaf parameters live in ONE allocation ([P] | [nn]) so a host-pointer evaluation uploads both with one copy
+    CU(cudaMalloc((void**)&m->d_x, (std::max(1, m->P) + nn) * sizeof(double)));
+    m->d_pleaf = m->d_x + std::max(1, m->P);
     CU(cudaMemset(m->d_pleaf, 0, nn * sizeof(double)));
     CU(cudaMalloc((void**)&m->d_out, (1 + m->P) * sizeof(double)));
     CU(cudaMallocHost((void**)&m->h_pin, (2 + 2 * m->P + nn) * sizeof(double)));
@@ -625,7 +626,7 @@ int32_t whale_model_destroy(whale_model_t m) {
     for (void* p : m->planR.owned) cudaFree(p);
     for (void* p : m->planL.owned) cudaFree(p);
     cudaFree(m->d_rinv);
-    cudaFree(m->d_x); cudaFree(m->d_pleaf); cudaFree(m->d_out);
+    cudaFree(m->d_x); cudaFree(m->d_out);
     if (m->h_pin) cudaFreeHost(m->h_pin);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
@@ -758,8 +759,8 @@ static size_t set_budgets(whale_data* D, int g, const Plan& pl) {
         H.stage_bytes[g] = 16 * stg > STAGE_MAX ? 0u : (uint32_t)(16 * stg);
         worst = std::max(worst, smem_need(m, H, g, pl.Kmax));
         if (env_int("WHALE_DEBUG", 0) >= 2)
-            fprintf(stderr, "[whale] fam %d plan %d: G %u rows %u scr %u prod %u leafmax %u stage %u leaf_stage %u -> %zu B\n", f, g,
-                    H.G, H.rows_len[g], H.scr_len[g], H.prod_len[g], H.leafmax[g], H.stage_bytes[g], H.leaf_stage,
+            fprintf(stderr, "[whale] fam %d plan %d: G %u root levels %u (window %u) rows %u scr %u prod %u leafmax %u stage %u leaf_stage %u -> %zu B\n", f, g,
+                    H.G, H.nlev, H.rootwin, H.rows_len[g], H.scr_len[g], H.prod_len[g], H.leafmax[g], H.stage_bytes[g], H.leaf_stage,
                     smem_need(m, H, g, pl.Kmax));
     }
     size_t cur = worst_a.load();
@@ -1777,6 +1778,20 @@ static const char* validate_arena(const whale_model* m, const whale_data* D, con
             ell += (uint64_t)(m->nsl[e] + 1) * C;
         }
         if (recs[m->root].C != H.G) return "root compat list is not the clade list";
+        {   // root levels: every Πroot term of a cell must point below the cell's level (the kernels rely on it)
+            const NodeRec& R = recs[m->root];
+            const uint32_t* words = reinterpret_cast<const uint32_t*>(blob);
+            const Ent* ents = reinterpret_cast<const Ent*>(blob);
+            const uint32_t* dptr = words + R.dptr_off;
+            const uint32_t* lev = words + R.tptr_off + 3 * (size_t)R.C + 1;
+            if (H.nlev == 0 || lev[0] != 0 || lev[H.nlev] != R.C) return "root levels inconsistent";
+            for (uint32_t L = 0; L < H.nlev; L++) {
+                if (lev[L] >= lev[L + 1]) return "root levels inconsistent";
+                for (uint32_t c = lev[L]; c < lev[L + 1]; c++)
+                    for (uint32_t t = dptr[c]; t < dptr[c + 1]; t++)
+                        if (ents[R.dent_off + t].i1 >= lev[L] || ents[R.dent_off + t].i2 >= lev[L]) return "root term above its level";
+            }
+        }
     }
     if (ell != D->ell_total) return "ℓ size inconsistent";
     return nullptr;
@@ -2118,6 +2133,12 @@ static int32_t enqueue_eval(whale_model* m, whale_data* D, const double* d_x, in
     return WHALE_OK;
 }
 
+// host-pointer evaluations: hp = [x (P) | p_leaf (nn)] in pinned memory -> d_x | d_pleaf (adjacent when P >= 1)
+static cudaError_t upload_theta(whale_model* m, const double* hp) {
+    if (m->P >= 1) return cudaMemcpyAsync(m->d_x, hp, (size_t)(m->P + m->nn) * sizeof(double), cudaMemcpyHostToDevice, m->stream);
+    return cudaMemcpyAsync(m->d_pleaf, hp, (size_t)m->nn * sizeof(double), cudaMemcpyHostToDevice, m->stream);
+}
+
 int32_t whale_logpdf_grad_async(whale_model_t m, whale_data_t d, const double* d_x, int32_t condition,
                                 uint32_t flags, double* d_out, void* stream) {
     if (!m || !d || !d_x || !d_out) return fail(WHALE_ERR_ARG, "null argument");
@@ -2154,8 +2175,7 @@ int32_t whale_logpdf_grad(whale_model_t m, whale_data_t d, const double* x, cons
             cudaGraph_t graph = nullptr;
             bool ok = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
             if (ok) {
-                ok = cudaMemcpyAsync(m->d_x, hp, P * sizeof(double), cudaMemcpyHostToDevice, m->stream) == cudaSuccess &&
-                     cudaMemcpyAsync(m->d_pleaf, hp + P, nn * sizeof(double), cudaMemcpyHostToDevice, m->stream) == cudaSuccess &&
+                ok = upload_theta(m, hp) == cudaSuccess &&
                      enqueue_eval(m, d, m->d_x, condition, flags, m->d_out, m->stream) == WHALE_OK &&
                      cudaMemcpyAsync(ho, m->d_out, (1 + P) * sizeof(double), cudaMemcpyDeviceToHost, m->stream) == cudaSuccess;
                 ok = (cudaStreamEndCapture(m->stream, &graph) == cudaSuccess) && ok && graph;
@@ -2174,8 +2194,7 @@ int32_t whale_logpdf_grad(whale_model_t m, whale_data_t d, const double* x, cons
         } else if (gs->state == 0) {
             gs->state = 1;
             const int64_t l0 = g_launches.load();
-            CU(cudaMemcpyAsync(m->d_x, hp, P * sizeof(double), cudaMemcpyHostToDevice, m->stream));
-            CU(cudaMemcpyAsync(m->d_pleaf, hp + P, nn * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+            CU(upload_theta(m, hp));
             int32_t rc0 = enqueue_eval(m, d, m->d_x, condition, flags, m->d_out, m->stream);
             if (rc0 != WHALE_OK) return rc0;
             gs->launches = g_launches.load() - l0;
@@ -2186,8 +2205,7 @@ int32_t whale_logpdf_grad(whale_model_t m, whale_data_t d, const double* x, cons
     }
 #endif
     if (!done) {
-        CU(cudaMemcpyAsync(m->d_x, hp, P * sizeof(double), cudaMemcpyHostToDevice, m->stream));
-        CU(cudaMemcpyAsync(m->d_pleaf, hp + P, nn * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+        CU(upload_theta(m, hp));
         d->peer_fused = false;
         int32_t rc = enqueue_eval(m, d, m->d_x, condition, flags, m->d_out, m->stream);
         if (rc != WHALE_OK) return rc;
@@ -2885,8 +2903,7 @@ int32_t whale_multi_logpdf_grad(whale_multi_t h, const double* x, const double* 
         double* hp = m->h_pin;
         memcpy(hp, x, P * sizeof(double));
         for (int e = 0; e < nn; e++) hp[P + e] = p_leaf ? p_leaf[e] : 0.0;
-        CU(cudaMemcpyAsync(m->d_x, hp, P * sizeof(double), cudaMemcpyHostToDevice, m->stream));
-        CU(cudaMemcpyAsync(m->d_pleaf, hp + P, nn * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+        CU(upload_theta(m, hp));
         int32_t rc = enqueue_eval(m, h->datas[i], m->d_x, condition, flags, m->d_out, m->stream);
         if (rc != WHALE_OK) return rc;
         CU(cudaMemcpyAsync(hp + P + nn, m->d_out, (1 + P) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
