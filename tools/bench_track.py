@@ -67,6 +67,25 @@ def main():
     t0 = time.perf_counter()
     L.logpdf_grad(mh, dh, x0, pl, 1, keep_ell=True)
     out["logpdf_keep_ell_ms"] = 1e3 * (time.perf_counter() - t0)
+    # HBM roofline of the ℓ-keeping mode: the evaluation streams every ℓ row it forms to HBM once and reads the
+    # packed arena once; kernel time from the library's CUDA events (WHALE_PROFILE)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    ell_bytes = 8 * int(sum(L.L.whale_ell_size(dh, f) for f in range(F)))
+    arena = int(L.L.whale_data_arena_bytes(dh))
+    kd = []
+    for _ in range(3):
+        L.logpdf_grad(mh, dh, x0, pl, 1, keep_ell=True, profile=True)
+        kd.append(L.last_kernel_ms(dh)[1])
+    kdp = float(np.mean(kd))
+    out["keep_ell_roofline"] = {"bound": "hbm", "kernel": "k_dp (value plan, KEEP_ELL)", "ell_bytes_written": ell_bytes,
+                                "arena_bytes_read": arena, "k_dp_ms": kdp, "achieved": (ell_bytes + arena) / (kdp * 1e-3) / 1e9,
+                                "peak": hbm_peak, "unit": "GB/s", "frac": (ell_bytes + arena) / (kdp * 1e-3) / 1e9 / hbm_peak,
+                                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}
     # ---- walks from one kept ℓ, device stream, compact fetch ----
     L.backtrack_device(mh, dh, S, None, seed=1, max_nodes=MN)
     L.trees_view(dh, Wn)
@@ -81,7 +100,15 @@ def main():
     out["walks_device_rng"] = {"trees_per_s_rank": Wn / dt, "ms": 1e3 * dt, "kernel_ms": L.last_backtrack_ms(dh),
                                "nodes_per_tree": tot / Wn, "d2h_bytes": int(16 * tot + 8 * (Wn + 1) + 8 * Wn),
                                "failed": int((st != 0).sum())}
+    # k_backtrack against the HBM roofline: a walk reads ℓ cells scattered over its family's kept matrix (32-byte sectors,
+    # mostly L2 hits: S walks share one family's ℓ) and writes 16 bytes per tree node; the algorithmic floor is one read of
+    # the kept ℓ + the node records.  DRAM bytes measured by ncu: profiles/r2_ncu_k_backtrack_summary.txt
+    kb_ms = float(L.last_backtrack_ms(dh))
+    out["backtrack_roofline"] = {"bound": "hbm", "kernel": "k_backtrack", "kernel_ms": kb_ms,
+                                 "algorithmic_bytes": int(ell_bytes + 16 * tot), "achieved": (ell_bytes + 16 * tot) / (kb_ms * 1e-3) / 1e9,
+                                 "peak": hbm_peak, "unit": "GB/s", "frac": (ell_bytes + 16 * tot) / (kb_ms * 1e-3) / 1e9 / hbm_peak}
     # ---- device summary ----
+    L.trees_summary(dh, F, S)  # (first call allocates)
     t0 = time.perf_counter()
     nd, h, c, f1, _ = L.trees_summary(dh, F, S)
     out["summary"] = {"ms": 1e3 * (time.perf_counter() - t0), "distinct_trees_per_family_mean": float(nd.mean())}
