@@ -270,8 +270,8 @@ def c3_leg(args, L, wlib, rank, world, d3, n3, gen3_s, flush, stream):
     Xd = torch.empty(P, device="cuda", dtype=torch.float64)
 
     def e2e_step(i):
-        if world == 1:
-            return L.logpdf_grad(mh, dh, xs[i], model.p_leaf(), cond, want_grad=True)[0]
+        if world == 1 or peer:
+            return L.logpdf_grad(mh, dh, xs[i], model.p_leaf(), cond, want_grad=True, peer_sum=peer)[0]
         pin_x.copy_(torch.from_numpy(xs[i]))
         Xd.copy_(pin_x, non_blocking=True)
         L.logpdf_grad_async(mh, dh, Xd.data_ptr(), cond, wlib.WANT_GRAD | PS, OUT.data_ptr(), stream)
@@ -468,8 +468,8 @@ def main():
     Xd = torch.empty(P, device="cuda", dtype=torch.float64)
 
     def e2e_step(i):
-        if world == 1:  # exactly the call the Julia glue makes: host pointers in, host pointers out
-            return L.logpdf_grad(mh, dh, xs[i], model.p_leaf(), cond, want_grad=True)[0]
+        if world == 1 or peer:  # exactly the call the Julia glue makes: host pointers in, host pointers out (N > 1: + WHALE_PEER_SUM)
+            return L.logpdf_grad(mh, dh, xs[i], model.p_leaf(), cond, want_grad=True, peer_sum=peer)[0]
         pin_x.copy_(torch.from_numpy(xs[i]))
         Xd.copy_(pin_x, non_blocking=True)
         L.logpdf_grad_async(mh, dh, Xd.data_ptr(), cond, wlib.WANT_GRAD | PS, OUT.data_ptr(), stream)

@@ -133,9 +133,12 @@ int32_t whale_multi_logpdf_grad(whale_multi_t h, const double* x, const double* 
  * them over threads, src/core.jl:58-64): the sum of the ranks' (loglik, grad) WITHOUT a collective library.  Each rank
  * calls whale_peer_export (allocates its exchange buffer, returns a 64-byte CUDA IPC handle), the driver all-gathers the
  * handles by any means, every rank calls whale_peer_import for every other rank.  From then on an evaluation with
- * WHALE_PEER_SUM ends with a one-CTA kernel that stores the rank's 1+P doubles into every peer's buffer through NVLink
- * peer memory and adds the world's contributions in rank order: every rank gets the same bits.  Like a collective, all
- * ranks must issue the same sequence of WHALE_PEER_SUM evaluations.  At most 16 ranks.
+ * WHALE_PEER_SUM ends with the exchange: the rank stores its 1+P doubles into every peer's buffer through NVLink peer
+ * memory (64-bit packets carrying data and the step's tag together: no fence, one hop), waits for the world's packets in
+ * its own buffer and adds the contributions in rank order: every rank gets the same bits.  One-pass evaluations run it in
+ * the last CTA of the DP kernel (no extra launch), others as a one-CTA kernel.  Like a collective, all ranks must issue the
+ * same sequence of WHALE_PEER_SUM evaluations.  At most 16 ranks.  A peer that does not show up within ~10 s makes the
+ * result -Inf (and zero gradient) instead of hanging.
  */
 int32_t whale_peer_export(whale_data_t d, int32_t rank, int32_t world, void* handle64);
 int32_t whale_peer_import(whale_data_t d, int32_t peer, const void* handle64);

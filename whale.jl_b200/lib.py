@@ -216,8 +216,11 @@ class Lib:
         return h.value, ncl
 
     def logpdf_grad(self, mh, dh, x, p_leaf, condition, want_grad=False, keep_ell=False, per_family=False,
-                    per_family_grad=False, profile=False):
-        flags = (WANT_GRAD if want_grad else 0) | (KEEP_ELL if keep_ell else 0) | (PROFILE if profile else 0)
+                    per_family_grad=False, profile=False, peer_sum=False):
+        """whale_logpdf_grad with host buffers.  peer_sum: one process per GPU — the returned (loglik, grad) is the sum over
+        all ranks (whale_peer_export / whale_peer_import done before; every rank must make the same calls)."""
+        flags = ((WANT_GRAD if want_grad else 0) | (KEEP_ELL if keep_ell else 0) | (PROFILE if profile else 0) |
+                 (PEER_SUM if peer_sum else 0))
         if not (per_family or per_family_grad):
             # the call an optimiser / sampler makes every iteration: argument buffers are kept per handle pair (building
             # ctypes pointers from numpy arrays costs ~3 µs each, three of them per call — 3 % of a 0.3 ms evaluation)
