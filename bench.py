@@ -309,7 +309,7 @@ def c3_leg(args, L, wlib, rank, world, d3, n3, gen3_s, flush, stream):
     return {"workload": f"C3: {fam_total} synthetic families in total (strong scaling, {n3} on rank 0), 9-taxon tree + 2 WGD, "
                         f"DLWGD branch-wise rates P={P}, dt={DT}, RootCondition, new theta each step",
             "families_total": fam_total, "P": P, "grad_mode": mode, "gradient_passes": passes, "steps": K, "warmup": Wm,
-            "exchange": ("peer-memory one-shot sum (k_peer_sum)" if peer else "NCCL all-reduce") if world > 1 else "none",
+            "exchange": ("peer-memory packet exchange fused into the tail of k_dp_rev" if peer else "NCCL all-reduce") if world > 1 else "none",
             "value": fam_total * K / (total_ms * 1e-3), "unit": UNIT, "ms_per_step": total_ms / K, "scaling": "strong",
             "e2e": {"value": fam_total * K / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / K,
                     "h2d_bytes_per_step": 8 * (P + model.nn), "d2h_bytes_per_step": 8 * (1 + P)},
@@ -540,7 +540,7 @@ def main():
                                f"RootCondition, new theta each step",
                    "families_total": F * world,
                    "sharding": f"families/{world} ranks, sum of {1 + P} f64 per step: " +
-                               ("peer-memory one-shot exchange in the library (k_peer_sum over CUDA IPC / NVLink)" if peer
+                               ("peer-memory packet exchange in the library (CUDA IPC / NVLink), fused into the tail of the DP kernel" if peer
                                 else "NCCL all-reduce" if world > 1 else "single rank"),
                    "l2": "flushed between steps (256 MiB memset outside the timed event pairs)",
                    "timing": "K steps enqueued back to back, one CUDA event pair per step on the launching stream, one "
