@@ -371,6 +371,39 @@ def test_emu_peer_sum_two_ranks_in_one_process(L):
     L.L.whale_model_destroy(mh)
 
 
+@pytest.mark.parametrize("mode", ["fwd", "rev"])
+def test_emu_occupancy_line_unstages_outliers(mode, tmp_path):
+    """A launch requests its bin's largest shared-memory need for every CTA, so the few families just above the size that
+    still lets four of them share an SM read their lists in place (set_budgets / set_budgets_rev).  With the line lowered
+    (WHALE_OCC_LINE) to a size that exactly two of twelve C2-shaped families exceed, the batch must become ONE bin at or
+    below the line and the results must still match the oracle (staged and unstaged families in the same launch).
+    Process-wide switches: child processes."""
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import pathlib\nfrom whale_jl_b200 import lib as wlib\nfrom conftest import synthetic_c2_shape_vs_oracle\n"
+            "wlib.use(wlib.Lib(%r))\nsynthetic_c2_shape_vs_oracle(pathlib.Path(%r), n_fam=12)\nprint('ok')\n"
+            % (ROOT, os.path.join(ROOT, "tests"), EMU, str(tmp_path)))
+
+    def run(env):
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900,
+                             env=dict(os.environ, WHALE_GRAD_MODE=mode, WHALE_DEBUG="2", WHALE_DEBUG_BINS="1", WHALE_CALIBRATE="0", **env))
+        assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+        fam_key, bin_key = (" reverse: ", "plan 1 (reverse) bin") if mode == "rev" else (" plan 1: ", "plan 1 bin")
+        lines = out.stderr.splitlines()
+        needs = [int(ln.split("-> ")[1].split()[0]) for ln in lines if fam_key in ln and "-> " in ln][:12]  # first handle
+        bins = [ln for ln in lines if bin_key in ln]
+        return needs, bins
+
+    needs, _ = run({})
+    assert len(needs) == 12
+    top = sorted(needs)
+    line = (top[-3] + top[-2]) // 2  # exactly two families above
+    _, bins2 = run({"WHALE_OCC_LINE": str(line)})  # (the per-family debug lines show the needs BEFORE the rule)
+    assert line < max(needs)
+    first = bins2[0]
+    assert "count 12" in first and int(first.split(" smem ")[1].split()[0]) <= line, bins2
+
+
 @pytest.mark.parametrize("env", [{"WHALE_PEER_FUSE": "0"}, {"WHALE_GRAD_MODE": "fwd"}, {"WHALE_GRAD_MODE": "fwd", "WHALE_PEER_FUSE": "0"}])
 def test_emu_peer_sum_variants(env):
     """The exchange as its own launch (WHALE_PEER_FUSE=0) and behind the forward-tangent kernel: process-wide switches,

@@ -711,7 +711,10 @@ static cudaError_t launch_tables3(whale_model* m, const double* d_x, const doubl
 }
 
 // largest dynamic shared-memory request that still lets `per_sm` CTAs share an SM (228 KB per SM, 1 KB reserved per CTA)
-static size_t occupancy_line(int per_sm) { return (size_t)(228 * 1024) / (size_t)std::max(1, per_sm) - 1024; }
+static size_t occupancy_line(int per_sm) {  // (WHALE_OCC_LINE: another line, for tests of the unstaging rule on small families)
+    static const int forced = env_int("WHALE_OCC_LINE", 0);
+    return forced > 0 ? (size_t)forced : (size_t)(228 * 1024) / (size_t)std::max(1, per_sm) - 1024;
+}
 static size_t ctas_per_sm_by_smem(size_t need) { return (size_t)(228 * 1024) / (std::min<size_t>(need, 227 * 1024) + 1024); }
 
 // shared-memory budget of every family under tangent plan `pl` (stored at index g); returns the largest need
