@@ -220,6 +220,7 @@ inline cudaError_t cudaFreeHost(void* p) { free(p); return 0; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return 0; }
+inline cudaError_t cudaMemGetInfo(size_t* fre, size_t* tot) { *fre = (size_t)8 << 30; *tot = (size_t)16 << 30; return 0; }  // (pretend: 8 GiB free)
 inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }

@@ -425,6 +425,10 @@ def test_emu_landplant_dt001(L, monkeypatch):
         run_parity(L, "landplant_dt0.01", sel=sel, conds=["root"])
 
 
-def test_emu_track_sample_and_summary(L):
+@pytest.mark.parametrize("slots", ["16", "2", "1"])
+def test_emu_track_sample_and_summary(L, monkeypatch, slots):
+    """slots: posterior draws per batch of whale_track_sample (one walk launch per batch) — all draws in one batch, two
+    batches with a short last one, and the draw-by-draw path."""
     from conftest import track_sample_and_summary
+    monkeypatch.setenv("WHALE_TRACK_SLOTS", slots)
     track_sample_and_summary(L, n_samples=12, n_theta=3)

@@ -328,8 +328,11 @@ def test_arena_cache_round_trip_on_device(L, tmp_path):
     print(f"arena cache: {nbytes / 1e6:.1f} MB for 200 families, save {t_save * 1e3:.1f} ms, load + repack plans {t_load * 1e3:.1f} ms")
 
 
-def test_track_sample_and_summary(L):
-    """src/track.jl:47-63 with per-(family, sample) posterior rows, compact tree transfer, device tree identity / sumtrees."""
+@pytest.mark.parametrize("slots", ["16", "3", "1"])
+def test_track_sample_and_summary(L, monkeypatch, slots):
+    """src/track.jl:47-63 with per-(family, sample) posterior rows, compact tree transfer, device tree identity / sumtrees.
+    slots = posterior draws per batch: one batch / three batches (last one short) / draw by draw."""
+    monkeypatch.setenv("WHALE_TRACK_SLOTS", slots)
     from conftest import track_sample_and_summary
     track_sample_and_summary(L, n_samples=64, n_theta=7)
 

@@ -40,6 +40,15 @@ struct BTArgs {
     // uniforms == nullptr: draw k of walk w is a counter-based generator's output for (seed, w, k)  (the reference calls
     // the global rand(), src/track.jl:217,274; with host-supplied uniforms the stream is explicit instead)
     unsigned long long seed;
+    // batched form (whale_track_sample): the launch covers the pairs of `nslots` consecutive posterior draws; slot s owns
+    // the pairs [slot_off[s], slot_off[s+1]) of this launch, its own slice tables, parameter row x + s·P and kept ℓ at
+    // ell + s·ell_stride (nslots == 0: one draw, the members above)
+    int nslots;
+    const int* slot_off;            // [nslots+1]
+    const double* const* slot_eps;  // [nslots]
+    const double2* const* slot_pp;  // [nslots]
+    int P;
+    unsigned long long ell_stride;  // doubles
 };
 
 // counter-based uniform in [0, 1): splitmix64 of (seed, walk, draw), top 53 bits
@@ -69,12 +78,27 @@ __global__ void __launch_bounds__(128) k_backtrack(BTArgs A) {
     }
     const ModelDev& M = A.M;
     const PlanDev& PL = A.PL;
+    const double* eps_tab = PL.eps;
+    const double2* pp_tab = PL.pp;
+    const double* xv = A.x;
+    const double* ell_base = A.ell;
+    if (A.nslots > 0) {  // the draw this pair belongs to: last slot whose first pair is <= wl
+        int lo = 0, hi = A.nslots - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((long long)A.slot_off[mid] <= wl) lo = mid; else hi = mid - 1;
+        }
+        eps_tab = A.slot_eps[lo];
+        pp_tab = A.slot_pp[lo];
+        xv = A.x + (size_t)lo * A.P;
+        ell_base = A.ell + (size_t)lo * A.ell_stride;
+    }
     const FamHdr* Hp = A.hdr + fam;
     const unsigned char* blob = A.arena + Hp->base;
     const NodeRec* nrec = reinterpret_cast<const NodeRec*>(blob);
     const uint32_t* words = reinterpret_cast<const uint32_t*>(blob);
     const Ent* ents = reinterpret_cast<const Ent*>(blob);
-    const double* ellf = A.ell + Hp->ell_off;
+    const double* ellf = ell_base + Hp->ell_off;
     const double* U = A.uniforms ? A.uniforms + w * A.stride : nullptr;
     auto next_u = [&](int k) -> double { return U ? U[k] : rng_u01(A.seed, (unsigned long long)w, (unsigned long long)k); };
     int32_t* o_g = A.gamma + w * A.max_nodes;
@@ -99,7 +123,7 @@ __global__ void __launch_bounds__(128) k_backtrack(BTArgs A) {
     auto cmp_of = [&](int e) -> const uint32_t* { return words + nrec[e].tptr_off + tpwords(e); };
     auto L = [&](int e, int c, int t) -> double { return ell_node(e)[(size_t)t * nrec[e].C + c]; };
     auto Llast = [&](int e, int c) -> double { return L(e, c, M.nsl[e]); };
-    auto eps_last = [&](int e) -> double { return PL.eps[PL.toff[e] + M.nsl[e]]; };  // plan 0: K = 1
+    auto eps_last = [&](int e) -> double { return eps_tab[PL.toff[e] + M.nsl[e]]; };  // plan 0: K = 1
 
     int nnodes = 0, used = 0, sp = 0, st = 0;
     auto add_node = [&](int g, int e, int t, int par) -> int {
@@ -135,7 +159,7 @@ __global__ void __launch_bounds__(128) k_backtrack(BTArgs A) {
             const int f = M.child0[e], h = M.child1[e];
             const int lf_ = M.nsl[f];
             if (kind == WHALE_WGD) {  // :258-266
-                const double q = A.x[M.q_slot[e]];
+                const double q = xv[M.q_slot[e]];
                 const double wgt = __dadd_rn(__dadd_rn(1.0, -q), mul3(2.0, q, eps_last(f)));
                 r = __dadd_rn(r, -__dmul_rn(wgt, Llast(f, c)));
                 if (r < 0.0) { n0 = make_int4(f, c, lf_, 0); nnext = 1; }
@@ -171,8 +195,8 @@ __global__ void __launch_bounds__(128) k_backtrack(BTArgs A) {
                         }
                     }
                 } else {  // root :245-256, :369-414
-                    const double eta = A.x[M.eta_slot];
-                    const double eps = PL.eps[PL.toff[e]];
+                    const double eta = xv[M.eta_slot];
+                    const double eps = eps_tab[PL.toff[e]];
                     const double xi = __dadd_rn(1.0, -__dmul_rn(__dadd_rn(1.0, -eta), eps));
                     const double ome = __dadd_rn(1.0, -eta), omeps = __dadd_rn(1.0, -eps), xi2 = __dmul_rn(xi, xi);
                     const uint32_t* dptr = words + R.dptr_off;
@@ -220,7 +244,7 @@ __global__ void __launch_bounds__(128) k_backtrack(BTArgs A) {
             } else {
                 if (used >= A.stride) { st = 3; break; }
                 double r = __dmul_rn(next_u(used++), L(e, c, t));
-                const double2 pp = PL.pp[PL.toff[e] + t];
+                const double2 pp = pp_tab[PL.toff[e] + t];
                 r = __dadd_rn(r, -__dmul_rn(pp.x, L(e, c, t - 1)));
                 if (r < 0.0) { n0 = make_int4(e, c, t - 1, 0); nnext = 1; }
                 const uint32_t* dptr = words + R.dptr_off;

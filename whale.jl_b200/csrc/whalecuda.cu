@@ -265,6 +265,12 @@ struct whale_data {
         int32_t* h_packed = nullptr; size_t hcap_packed = 0;
         long long total_nodes = 0;
         bool packed_valid = false;
+        // batched whale_track_sample: value-only plan clones (own slice-table buffers) and ℓ buffers for `nslot` posterior
+        // draws evaluated back to back before ONE walk launch over all their (family, sample) pairs
+        std::vector<Plan> slot_plans;
+        double* d_ell_slots = nullptr; size_t cap_ell_slots = 0;
+        const double** d_slot_eps = nullptr; const double2** d_slot_pp = nullptr; int* d_slot_off = nullptr;
+        int nslot = 0;  // capacity of d_slot_off (ints)
     } tb;
     // peer-memory exchange (one process per GPU): own buffer, the peers' buffers as mapped here, step counter
     int peer_rank = -1, peer_world = 0;
@@ -1899,6 +1905,8 @@ int32_t whale_data_destroy(whale_data_t d) {
         if (T.h_st) cudaFreeHost(T.h_st);
         if (T.h_off) cudaFreeHost(T.h_off);
         if (T.h_packed) cudaFreeHost(T.h_packed);
+        for (Plan& sp : T.slot_plans) for (void* p : sp.owned) cudaFree(p);
+        cudaFree(T.d_ell_slots); cudaFree((void*)T.d_slot_eps); cudaFree((void*)T.d_slot_pp); cudaFree(T.d_slot_off);
     }
 #ifndef WHALE_EMU
     for (int q = 0; q < 16; q++) if (d->peer_open[q] && d->peer_bufs[q]) cudaIpcCloseMemHandle(d->peer_bufs[q]);
@@ -2437,9 +2445,10 @@ int32_t whale_backtrack_device(whale_model_t m, whale_data_t d, int32_t n_sample
 
 // value-only DP keeping ℓ for a SUBSET of the families (the launch order is the given list): logpdf! for the families
 // whose sample uses this posterior draw
-static int32_t enqueue_keep_subset(whale_model* m, whale_data* D, const double* d_x, const int* d_famlist, int count, cudaStream_t st) {
+static int32_t enqueue_keep_subset(whale_model* m, whale_data* D, const double* d_x, const int* d_famlist, int count, cudaStream_t st,
+                                   Plan* slot_plan = nullptr, double* slot_ell = nullptr) {
     if (count <= 0) return WHALE_OK;
-    if (!D->d_ell) CU(cudaMalloc((void**)&D->d_ell, std::max<uint64_t>(D->ell_total, 1) * sizeof(double)));
+    if (!slot_ell && !D->d_ell) CU(cudaMalloc((void**)&D->d_ell, std::max<uint64_t>(D->ell_total, 1) * sizeof(double)));
     if (!m->attr_set) {
 #define SETATTR(NTV, MB) CU(cudaFuncSetAttribute(k_dp<NTV, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         DP_VARIANTS(SETATTR)
@@ -2449,11 +2458,11 @@ static int32_t enqueue_keep_subset(whale_model* m, whale_data* D, const double* 
 #undef SETATTR
         m->attr_set = true;
     }
-    Plan& p0 = m->plan[0];
+    Plan& p0 = slot_plan ? *slot_plan : m->plan[0];
     CU(launch_tables(m, p0, d_x, m->d_pleaf, st, false));
     size_t smem = 0;
     for (const Bin& b : D->bins[0]) smem = std::max(smem, b.smem);
-    DPArgs a{m->dev, p0.dev, D->d_arena, D->d_hdr, d_famlist, D->d_roff[0], D->d_out_fam + D->out_off[0], D->d_ell, 0, 0,
+    DPArgs a{m->dev, p0.dev, D->d_arena, D->d_hdr, d_famlist, D->d_roff[0], D->d_out_fam + D->out_off[0], slot_ell ? slot_ell : D->d_ell, 0, 0,
              nullptr, nullptr, D->F, 0, 1, m->d_out};
     const int NT = dp_nt(), MB = dp_minb();
 #define LAUNCHV(NTV, MBV) if (NT == NTV && MB == MBV) LAUNCH((k_dp<NTV, MBV>), count, NTV, smem, st, a, 0);
@@ -2492,9 +2501,20 @@ int32_t whale_track_sample(whale_model_t m, whale_data_t d, int32_t n_theta, con
         maxgroup = std::max(maxgroup, (size_t)(cnt[j + 1] - cnt[j]));
     }
     famoff[n_theta] = (int)nf;
-    int32_t rc = ensure_tree_bufs(d, W, max_nodes, maxgroup);
-    if (rc != WHALE_OK) return rc;
     auto& T = d->tb;
+    // posterior draws handled per batch (see below): limited by free device memory (an ℓ buffer each)
+    int nslot = std::min(n_theta, env_int("WHALE_TRACK_SLOTS", 16));
+    {
+        size_t fre = 0, tot = 0;
+        const size_t ellb = std::max<uint64_t>(d->ell_total, 1) * sizeof(double);
+        if (cudaMemGetInfo(&fre, &tot) != cudaSuccess) { cudaGetLastError(); fre = 0; }
+        fre += T.cap_ell_slots * sizeof(double);  // what we already hold counts as available
+        nslot = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(nslot, 1), (fre / 2) / ellb));
+    }
+    size_t maxbatch = 0;
+    for (int j0 = 0; j0 < n_theta; j0 += nslot) maxbatch = std::max(maxbatch, (size_t)(cnt[std::min(n_theta, j0 + nslot)] - cnt[j0]));
+    int32_t rc = ensure_tree_bufs(d, W, max_nodes, std::max(maxgroup, maxbatch));
+    if (rc != WHALE_OK) return rc;
     cudaStream_t st = m->stream;
     if (uniforms) {
         CU(grow_dev(&T.d_u, &T.cap_u, (size_t)W * stride));
@@ -2519,18 +2539,73 @@ int32_t whale_track_sample(whale_model_t m, whale_data_t d, int32_t n_theta, con
     if (!d->ev[0]) for (int i = 0; i < 4; i++) CU(cudaEventCreate(&d->ev[i]));
     CU(cudaEventRecord(d->ev[0], st));
     Plan& p0 = m->plan[0];
-    for (int j = 0; j < n_theta; j++) {
-        const int np = cnt[j + 1] - cnt[j];
-        if (np == 0) continue;
-        const double* d_xj = T.d_xs + (size_t)j * P;
-        // logpdf!(model(θ_j), ·) for the families that drew row j, then their walks — nothing returns to the host in between
-        rc = enqueue_keep_subset(m, d, d_xj, T.d_famlist + famoff[j], famoff[j + 1] - famoff[j], st);
-        if (rc != WHALE_OK) return rc;
-        BTArgs a{m->dev, p0.dev, d->d_arena, d->d_hdr, d->d_ell, d_xj, uniforms ? T.d_u : nullptr,
-                 uniforms ? (long long)stride : (1LL << 40), F, S, max_nodes, 0, S, T.d_cnt, T.d_g, T.d_e, T.d_t, T.d_p, T.d_st,
-                 T.d_stack, T.d_pairs + cnt[j], np, (unsigned long long)seed};
-        LAUNCH(k_backtrack, (np + 127) / 128, 128, 0, st, a);
-        g_launches++;
+    // Batches of `nslot` posterior draws: logpdf!(model(θ_j), ·) for the families that drew row j into slot j's own ℓ and
+    // slice tables, back to back, then ONE walk launch over all the batch's pairs (a launch per draw holds ~W/n_theta
+    // walks — a few CTAs per SM — and cost 2.5 ms per draw on C5 where all 10^6 walks together take 28 ms).  Nothing
+    // returns to the host in between.  Slots are limited by free device memory (an ℓ buffer each); one slot = the
+    // draw-by-draw path.
+    if (nslot > 1) {
+        CU(grow_dev(&T.d_ell_slots, &T.cap_ell_slots, (size_t)nslot * d->ell_total));
+        if ((int)T.slot_plans.size() < nslot) {
+            const size_t have = T.slot_plans.size();
+            T.slot_plans.resize(nslot);
+            for (size_t q = have; q < (size_t)nslot; q++) {
+                build_plan(*m, std::vector<char>(), T.slot_plans[q]);
+                CU(upload_plan(T.slot_plans[q], nn));
+            }
+            cudaFree((void*)T.d_slot_eps); cudaFree((void*)T.d_slot_pp);
+            T.d_slot_eps = nullptr; T.d_slot_pp = nullptr;
+            std::vector<const double*> he(nslot);
+            std::vector<const double2*> hp2(nslot);
+            for (int q = 0; q < nslot; q++) { he[q] = T.slot_plans[q].dev.eps; hp2[q] = T.slot_plans[q].dev.pp; }
+            CU(cudaMalloc((void**)&T.d_slot_eps, nslot * sizeof(double*)));
+            CU(cudaMalloc((void**)&T.d_slot_pp, nslot * sizeof(double2*)));
+            CU(cudaMemcpy((void*)T.d_slot_eps, he.data(), nslot * sizeof(double*), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy((void*)T.d_slot_pp, hp2.data(), nslot * sizeof(double2*), cudaMemcpyHostToDevice));
+        }
+        // per batch: the pair offsets of its draws relative to the batch's first pair, nb + 1 entries
+        std::vector<int> relx, batch_at;
+        for (int j0 = 0; j0 < n_theta; j0 += nslot) {
+            const int j1 = std::min(n_theta, j0 + nslot);
+            batch_at.push_back((int)relx.size());
+            for (int j = j0; j <= j1; j++) relx.push_back(cnt[j] - cnt[j0]);
+        }
+        if ((int)relx.size() > T.nslot) {
+            cudaFree(T.d_slot_off); T.d_slot_off = nullptr; T.nslot = 0;
+            CU(cudaMalloc((void**)&T.d_slot_off, relx.size() * sizeof(int)));
+            T.nslot = (int)relx.size();
+        }
+        CU(cudaMemcpy(T.d_slot_off, relx.data(), relx.size() * sizeof(int), cudaMemcpyHostToDevice));
+        int bi = 0;
+        for (int j0 = 0; j0 < n_theta; j0 += nslot, bi++) {
+            const int j1 = std::min(n_theta, j0 + nslot), nb = j1 - j0;
+            const int np = cnt[j1] - cnt[j0];
+            if (np == 0) continue;
+            for (int j = j0; j < j1; j++) {
+                rc = enqueue_keep_subset(m, d, T.d_xs + (size_t)j * P, T.d_famlist + famoff[j], famoff[j + 1] - famoff[j], st,
+                                         &T.slot_plans[j - j0], T.d_ell_slots + (size_t)(j - j0) * d->ell_total);
+                if (rc != WHALE_OK) return rc;
+            }
+            BTArgs a{m->dev, p0.dev, d->d_arena, d->d_hdr, T.d_ell_slots, T.d_xs + (size_t)j0 * P, uniforms ? T.d_u : nullptr,
+                     uniforms ? (long long)stride : (1LL << 40), F, S, max_nodes, 0, S, T.d_cnt, T.d_g, T.d_e, T.d_t, T.d_p, T.d_st,
+                     T.d_stack, T.d_pairs + cnt[j0], np, (unsigned long long)seed,
+                     nb, T.d_slot_off + batch_at[bi], T.d_slot_eps, T.d_slot_pp, P, (unsigned long long)d->ell_total};
+            LAUNCH(k_backtrack, (np + 127) / 128, 128, 0, st, a);
+            g_launches++;
+        }
+    } else {
+        for (int j = 0; j < n_theta; j++) {
+            const int np = cnt[j + 1] - cnt[j];
+            if (np == 0) continue;
+            const double* d_xj = T.d_xs + (size_t)j * P;
+            rc = enqueue_keep_subset(m, d, d_xj, T.d_famlist + famoff[j], famoff[j + 1] - famoff[j], st);
+            if (rc != WHALE_OK) return rc;
+            BTArgs a{m->dev, p0.dev, d->d_arena, d->d_hdr, d->d_ell, d_xj, uniforms ? T.d_u : nullptr,
+                     uniforms ? (long long)stride : (1LL << 40), F, S, max_nodes, 0, S, T.d_cnt, T.d_g, T.d_e, T.d_t, T.d_p, T.d_st,
+                     T.d_stack, T.d_pairs + cnt[j], np, (unsigned long long)seed};
+            LAUNCH(k_backtrack, (np + 127) / 128, 128, 0, st, a);
+            g_launches++;
+        }
     }
     CU(cudaEventRecord(d->ev[1], st));
     rc = finish_walks(d, st, S);
