@@ -729,12 +729,7 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
     // dependent L2 round trip at every node of phase B
     NodeRec* s_nrec = reinterpret_cast<NodeRec*>(smem_raw + meta_bytes);
     const NodeRec* const nrec = s_nrec;
-#ifdef WHALE_NODE_PREFETCH
-    unsigned long long* const s_bar = reinterpret_cast<unsigned long long*>(smem_raw + meta_bytes + (size_t)nn * sizeof(NodeRec));  // mbarrier of the list copies
-    const size_t hdr_bytes = meta_bytes + (size_t)nn * sizeof(NodeRec) + 16;
-#else
     const size_t hdr_bytes = meta_bytes + (size_t)nn * sizeof(NodeRec);
-#endif
     double* rows = reinterpret_cast<double*>(smem_raw + hdr_bytes);
     double* scr = rows + rows_len;
     unsigned char* stage = reinterpret_cast<unsigned char*>(scr + scr_len);
@@ -748,9 +743,6 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         s_roff[i] = (int)A.roff[(size_t)fam * nn + i];
     }
     for (int i = tid; i < nn * 2 * Kmax; i += NT) s_cmap[i] = PL.cmap[i];
-#ifdef WHALE_NODE_PREFETCH
-    if (tid == 0) mbar_init(s_bar, 1);
-#endif
     for (int i = tid; i < nn * 3; i += NT)
         reinterpret_cast<uint4*>(s_nrec)[i] = __ldg(reinterpret_cast<const uint4*>(g_nrec) + i);
     __syncthreads();
@@ -853,81 +845,6 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
     const long long tcB = CLOCK64();
 
     // ================= phase B: internal, WGD and root nodes, whole CTA =================
-#ifdef WHALE_NODE_PREFETCH
-    // (experiment) two staging buffers — `stage` and the spare room behind the family's carve-up — filled by bulk copies
-    // (one issuing thread, mbarrier completion); the next node's lists stream in while the current node runs.  The
-    // buffer is selected by an OFFSET from `stage`, so every staged pointer stays a shared-memory address for the compiler.
-    struct NodeStage { int nd16, sl16, dp16, tp16, tn16, pp16, total; };
-    auto stage_of = [&](int e2) -> NodeStage {
-        const NodeRec& R2 = nrec[e2];
-        const int kd = s_kind[e2], C2 = (int)R2.C, K2 = s_K[e2];
-        NodeStage q;
-        q.nd16 = (kd == WHALE_ROOT) ? 0 : (int)R2.ndent;
-        q.sl16 = (kd == WHALE_ROOT) ? 0 : (((int)R2.nslots + 1) >> 1);
-        q.dp16 = (C2 + 1 + 3) >> 2;
-        q.tp16 = (kd == WHALE_WGD) ? 0 : ((3 * C2 + 1 + (kd == WHALE_ROOT ? (int)nlev + 1 : 0) + 3) >> 2);
-        q.tn16 = (kd == WHALE_INTERNAL) ? (int)R2.ntent : 0;
-        q.pp16 = (K2 <= 8) ? (s_nsl[e2] + 1) * K2 : 0;
-        q.total = q.nd16 + q.sl16 + q.dp16 + q.tp16 + q.tn16 + q.pp16 + (kd == WHALE_ROOT ? 2 * (int)Hp->rootwin : 0);
-        return q;
-    };
-    unsigned bar_phase = 0;
-    auto issue_node = [&](int e2, unsigned off16) {  // thread 0: one bulk copy per segment, completing on s_bar
-        if (tid != 0) return;
-        const NodeRec& R2 = nrec[e2];
-        const NodeStage q = stage_of(e2);
-        uint4* buf = reinterpret_cast<uint4*>(stage) + off16;
-        uint4* b5 = buf + q.nd16 + q.sl16;
-        fence_proxy_async();
-        mbar_expect_tx(s_bar, 16u * (unsigned)(q.nd16 + q.sl16 + q.dp16 + q.tp16 + q.tn16 + q.pp16));
-        if (q.nd16) bulk_g2s(buf, ents + R2.dent_off, 16u * q.nd16, s_bar);
-        if (q.sl16) bulk_g2s(buf + q.nd16, words + R2.slot_off, 16u * q.sl16, s_bar);
-        if (q.dp16) bulk_g2s(b5, words + R2.dptr_off, 16u * q.dp16, s_bar);
-        if (q.tp16) bulk_g2s(b5 + q.dp16, words + R2.tptr_off, 16u * q.tp16, s_bar);
-        if (q.tn16) bulk_g2s(b5 + q.dp16 + q.tp16, ents + R2.tent_off, 16u * q.tn16, s_bar);
-        if (q.pp16) bulk_g2s(b5 + q.dp16 + q.tp16 + q.tn16, PL.pp + s_toff[e2], 16u * q.pp16, s_bar);
-    };
-    const unsigned cap0 = stage_bytes >> 4;
-    const unsigned cap1 = staged ? ((DYN_SMEM_BYTES() - (unsigned)(stage + stage_bytes - smem_raw)) >> 4) : 0u;
-    int pre_e = -1;          // node whose lists were requested ahead
-    unsigned pre_off = 0;    // ... into the buffer at this offset (16-byte units from `stage`)
-    for (int oi = 0; oi < M.ninner; oi++) {
-        const int e = M.inner[oi];
-        const NodeRec R = nrec[e];
-        const int C = (int)R.C;
-        if (C == 0) continue;
-        const int kind = s_kind[e], K = s_K[e], n = s_nsl[e];
-        double* fin = rows + s_roff[e];
-        double* ellp = ell_of(e);
-        const bool pps = K <= 8;
-
-        const long long tst = CLOCK64();
-        const NodeStage Q = stage_of(e);
-        const int nd16 = Q.nd16, sl16 = Q.sl16, dp16 = Q.dp16, tp16 = Q.tp16, tn16 = Q.tn16, pp16 = Q.pp16;
-        unsigned cur_off = 0;
-        const Ent* s_dents = ents + R.dent_off;
-        const Slot* s_slots = reinterpret_cast<const Slot*>(words + R.slot_off);
-        const uint32_t* s_dptr = words + R.dptr_off;
-        const uint32_t* s_tptr = words + R.tptr_off;
-        const Ent* s_tents = ents + R.tent_off;
-        const double2* s_pp = PL.pp + s_toff[e];
-        if (staged) {
-            if (pre_e == e) cur_off = pre_off;
-            else issue_node(e, 0u);
-            mbar_wait(s_bar, bar_phase);
-            bar_phase ^= 1u;
-        }
-        uint4* st4 = reinterpret_cast<uint4*>(stage) + cur_off;
-        uint4* st5 = st4 + nd16 + sl16;
-        if (staged) {
-            s_dents = reinterpret_cast<const Ent*>(st4);
-            s_slots = reinterpret_cast<const Slot*>(st4 + nd16);
-            s_dptr = reinterpret_cast<const uint32_t*>(st5);
-            s_tptr = reinterpret_cast<const uint32_t*>(st5 + dp16);
-            s_tents = reinterpret_cast<const Ent*>(st5 + dp16 + tp16);
-            s_pp = reinterpret_cast<const double2*>(st5 + dp16 + tp16 + tn16);
-        }
-#else
     for (int oi = 0; oi < M.ninner; oi++) {
         const int e = M.inner[oi];
         const NodeRec R = nrec[e];
@@ -969,7 +886,6 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
             s_tents = reinterpret_cast<const Ent*>(st5 + dp16 + tp16);
             s_pp = reinterpret_cast<const double2*>(st5 + dp16 + tp16 + tn16);
         }
-#endif
         const int32_t* s_lossF = reinterpret_cast<const int32_t*>(s_tptr + C + 1);
         const int32_t* s_lossG = s_lossF + C;
         const uint32_t* s_lev = reinterpret_cast<const uint32_t*>(s_lossG + C);
@@ -995,17 +911,6 @@ __global__ void __launch_bounds__(NT, MINB) k_dp(DPArgs A, int perm_off) {
         const int16_t* mapG = s_cmap + (e * 2 + 1) * Kmax;
         double* cur = (n & 1) ? scr : fin;  // row i lives in fin iff (n − i) is even
         __syncthreads();  // staged lists visible
-#ifdef WHALE_NODE_PREFETCH
-        if (staged && kind != WHALE_ROOT) {  // request the next node's lists into the other buffer
-            int en = -1;
-            for (int j = oi + 1; j < M.ninner && en < 0; j++) if (nrec[M.inner[j]].C) en = M.inner[j];
-            const unsigned other = cur_off == 0u ? cap0 : 0u;
-            if (en >= 0 && (unsigned)stage_of(en).total <= (other == 0u ? cap0 : cap1)) {
-                issue_node(en, other);
-                pre_e = en; pre_off = other;
-            }
-        }
-#endif
 
         if (kind == WHALE_WGD) {
             // q·Σ p ℓ_f[γ1]ℓ_f[γ2] + (1−q+2qϵ_f)·ℓ_f[γ]   src/core.jl:103-119,187-199

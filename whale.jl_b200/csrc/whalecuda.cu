@@ -642,16 +642,9 @@ int32_t whale_model_destroy(whale_model_t m) {
 // ---- the packer: reference-layout CSR -> per-branch resolved device arena ----
 static inline void pad4(std::vector<uint32_t>& w) { while (w.size() & 3) w.push_back(0); }
 
-static constexpr size_t node_prefetch_bytes() {  // the mbarrier of k_dp's list copies (WHALE_NODE_PREFETCH experiment build)
-#ifdef WHALE_NODE_PREFETCH
-    return 16;
-#else
-    return 0;
-#endif
-}
 static size_t smem_need(const whale_model* m, const FamHdr& h, int plan, int Kmax_) {  // mirrors the carve-up in k_dp
     const size_t nn = m->nn, Kmax = Kmax_, NW = dp_nt() / 32;
-    const size_t hdr = ((((7 * nn + 1) * sizeof(int) + nn * 2 * Kmax * sizeof(int16_t)) + 15) & ~size_t(15)) + nn * sizeof(NodeRec) + node_prefetch_bytes();
+    const size_t hdr = ((((7 * nn + 1) * sizeof(int) + nn * 2 * Kmax * sizeof(int16_t)) + 15) & ~size_t(15)) + nn * sizeof(NodeRec);
     return hdr + ((size_t)h.rows_len[plan] + h.scr_len[plan] + h.prod_len[plan]) * sizeof(double) +
            h.stage_bytes[plan] + NW * ((size_t)h.leafmax[plan] * sizeof(double) + h.leaf_stage);
 }
