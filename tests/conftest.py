@@ -87,6 +87,32 @@ def run_parity(L, name, rtol=1e-9, sel=None, conds=None, check_family=True):
     return g
 
 
+def repeated_calls_parity(L, name, rounds=3):
+    """The same (flags, condition) evaluated many times on ONE handle with changing θ — the pattern of an optimiser; from the
+    third call on a host-pointer evaluation may be a CUDA-graph replay (WHALE_GRAPHS) — gradient, value-only and ℓ-keeping
+    calls interleaved, each checked against the golden values."""
+    g = load_golden(name)
+    mh = L.model_create(golden_model(g))
+    dh = L.data_create(mh, golden_fams(g))
+    kinds = [k[4:] for k in g if k.startswith("tot_")]
+    try:
+        for r in range(rounds):
+            for kind in kinds:
+                for xi, x in enumerate(g["xs"]):
+                    want, wg = g[f"tot_{kind}"][xi], g[f"grad_{kind}"][xi]
+                    ll, grad, _, _ = L.logpdf_grad(mh, dh, x, g["m_pleaf"], COND[kind], want_grad=True)
+                    assert ll == pytest.approx(want, rel=1e-9), (name, r, kind, xi)
+                    np.testing.assert_allclose(grad, wg, rtol=1e-9, atol=1e-9 * np.abs(wg).max())
+                    ll0, _, _, _ = L.logpdf_grad(mh, dh, x, g["m_pleaf"], COND[kind])
+                    assert ll0 == pytest.approx(want, rel=1e-9)
+                    llk, gk, _, _ = L.logpdf_grad(mh, dh, x, g["m_pleaf"], COND[kind], want_grad=True, keep_ell=True)
+                    assert llk == pytest.approx(want, rel=1e-9)
+                    np.testing.assert_allclose(gk, wg, rtol=1e-9, atol=1e-9 * np.abs(wg).max())
+    finally:
+        L.L.whale_data_destroy(dh)
+        L.L.whale_model_destroy(mh)
+
+
 def mixture_vs_oracle(tmp_path, n_fam=6, seed=11):
     """Mixture of two ConstantDLWGD components on synthetic families: value and gradient (w.r.t. both components'
     raw parameters and the log mixture weights) composed from the oracle's per-family outputs."""

@@ -292,6 +292,27 @@ def test_multi_device_handle(L):
     multi_device_vs_golden(L, list(range(n)) if n > 1 else [0, 0])
 
 
+@pytest.mark.parametrize("graphs", ["auto", "1", "0"])
+def test_repeated_calls_graph_replay(graphs):
+    """Host-pointer evaluations are replayed as one CUDA graph from the third call with the same (flags, condition) on
+    (automatic for single-bin handles; WHALE_GRAPHS=1 / 0 forces it): repeated gradient / value / ℓ-keeping calls with
+    changing θ on one handle stay on the golden values in every mode, reverse (C1, P = 37) and forward (constant rates)
+    kernels.  Process-wide switch: child processes."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from whale_jl_b200 import lib as wlib\nfrom conftest import repeated_calls_parity\n"
+            "L = wlib.Lib()\nrepeated_calls_parity(L, 'c1_example1')\nrepeated_calls_parity(L, 'const_wgdturing')\nprint('ok')\n"
+            % (os.path.dirname(here), here))
+    env = dict(os.environ)
+    env.pop("WHALE_GRAPHS", None)
+    if graphs != "auto":
+        env["WHALE_GRAPHS"] = graphs
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout[-1500:] + out.stderr[-3000:]
+
+
 @pytest.mark.parametrize("env", [{}, {"WHALE_PEER_FUSE": "0"}, {"WHALE_GRAD_MODE": "fwd"}])
 def test_peer_sum_between_processes(tmp_path, env):
     """SURVEY §8e, one process per GPU: whale_peer_export / whale_peer_import + WHALE_PEER_SUM between two (one-GPU box:

@@ -179,11 +179,14 @@ struct GraphSlot {  // one captured evaluation per (flags, condition)
 #endif
     int64_t launches = 0;
 };
-static bool graphs_enabled() {
-    // opt-in: on B200 replaying the multi-stream evaluation as a graph measured SLOWER end to end than plain
-    // launches (0.53 vs 0.48 ms per C2 step), so the default is off
-    static bool on = [] { const char* s = getenv("WHALE_GRAPHS"); return s && atoi(s) != 0; }();
-    return on;
+// Host-pointer evaluations replayed as ONE CUDA graph (H2D of θ, the kernels, D2H of the result).  WHALE_GRAPHS=1 / 0
+// forces it on / off; unset = automatic: on when the evaluation is a single chain of launches (every plan in one
+// shared-memory bin) — measured on the B200, C2: 0.2986 vs 0.3112 ms per call end to end (+4.2 %).  With several bins the
+// evaluation forks onto side streams, and replaying THAT as a graph measured slower than plain launches in round 1
+// (0.53 vs 0.48 ms), so it stays on the plain path.
+static int graphs_mode() {  // -1 automatic, 0 off, 1 on
+    static int mode = [] { const char* s = getenv("WHALE_GRAPHS"); return s ? (atoi(s) != 0 ? 1 : 0) : -1; }();
+    return mode;
 }
 
 struct whale_data {
@@ -2177,7 +2180,10 @@ int32_t whale_logpdf_grad(whale_model_t m, whale_data_t d, const double* x, cons
     // what separates the end-to-end rate from the device-timed rate for small batches.
     bool done = false;
 #ifndef WHALE_EMU
-    if (!(flags & (WHALE_PROFILE | WHALE_PEER_SUM)) && graphs_enabled()) {
+    bool use_graph = !(flags & (WHALE_PROFILE | WHALE_PEER_SUM)) && graphs_mode() != 0;
+    if (use_graph && graphs_mode() < 0)  // automatic: single-bin plans only
+        for (size_t g = 0; g < d->plans.size() && g < (size_t)MAXPLAN; g++) use_graph = use_graph && d->bins[g].size() <= 1;
+    if (use_graph) {
         const uint32_t key = (flags & (WHALE_WANT_GRAD | WHALE_KEEP_ELL)) | ((uint32_t)condition << 8);
         GraphSlot* gs = nullptr;
         for (auto& g : d->graphs) if (g.key == key) gs = &g;
