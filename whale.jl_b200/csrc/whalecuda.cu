@@ -2179,12 +2179,20 @@ int32_t whale_logpdf_grad(whale_model_t m, whale_data_t d, const double* x, cons
     // ONE CUDA graph from the second call with the same (flags, condition) on: the host-side launch cost is
     // what separates the end-to-end rate from the device-timed rate for small batches.
     bool done = false;
+    // the evaluation + (one process per GPU, WHALE_PEER_SUM) the sum over ranks, in the DP kernel's tail or as its own launch;
+    // the exchange keeps its step counter on the device, so it can be part of a captured graph like everything else
+    auto enqueue_all = [&]() -> int32_t {
+        d->peer_fused = false;
+        int32_t rc = enqueue_eval(m, d, m->d_x, condition, flags, m->d_out, m->stream);
+        if (rc == WHALE_OK && (flags & WHALE_PEER_SUM) && !d->peer_fused) rc = enqueue_peer_sum(d, m->d_out, m->stream);
+        return rc;
+    };
 #ifndef WHALE_EMU
-    bool use_graph = !(flags & (WHALE_PROFILE | WHALE_PEER_SUM)) && graphs_mode() != 0;
+    bool use_graph = !(flags & WHALE_PROFILE) && graphs_mode() != 0;
     if (use_graph && graphs_mode() < 0)  // automatic: single-bin plans only
         for (size_t g = 0; g < d->plans.size() && g < (size_t)MAXPLAN; g++) use_graph = use_graph && d->bins[g].size() <= 1;
     if (use_graph) {
-        const uint32_t key = (flags & (WHALE_WANT_GRAD | WHALE_KEEP_ELL)) | ((uint32_t)condition << 8);
+        const uint32_t key = (flags & (WHALE_WANT_GRAD | WHALE_KEEP_ELL | WHALE_PEER_SUM)) | ((uint32_t)condition << 8);
         GraphSlot* gs = nullptr;
         for (auto& g : d->graphs) if (g.key == key) gs = &g;
         if (!gs) { d->graphs.push_back(GraphSlot{key, 0, nullptr}); gs = &d->graphs.back(); }
@@ -2192,8 +2200,7 @@ int32_t whale_logpdf_grad(whale_model_t m, whale_data_t d, const double* x, cons
             cudaGraph_t graph = nullptr;
             bool ok = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
             if (ok) {
-                ok = upload_theta(m, hp) == cudaSuccess &&
-                     enqueue_eval(m, d, m->d_x, condition, flags, m->d_out, m->stream) == WHALE_OK &&
+                ok = upload_theta(m, hp) == cudaSuccess && enqueue_all() == WHALE_OK &&
                      cudaMemcpyAsync(ho, m->d_out, (1 + P) * sizeof(double), cudaMemcpyDeviceToHost, m->stream) == cudaSuccess;
                 ok = (cudaStreamEndCapture(m->stream, &graph) == cudaSuccess) && ok && graph;
             }
@@ -2212,7 +2219,7 @@ int32_t whale_logpdf_grad(whale_model_t m, whale_data_t d, const double* x, cons
             gs->state = 1;
             const int64_t l0 = g_launches.load();
             CU(upload_theta(m, hp));
-            int32_t rc0 = enqueue_eval(m, d, m->d_x, condition, flags, m->d_out, m->stream);
+            int32_t rc0 = enqueue_all();
             if (rc0 != WHALE_OK) return rc0;
             gs->launches = g_launches.load() - l0;
             CU(cudaMemcpyAsync(ho, m->d_out, (1 + P) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
@@ -2223,13 +2230,8 @@ int32_t whale_logpdf_grad(whale_model_t m, whale_data_t d, const double* x, cons
 #endif
     if (!done) {
         CU(upload_theta(m, hp));
-        d->peer_fused = false;
-        int32_t rc = enqueue_eval(m, d, m->d_x, condition, flags, m->d_out, m->stream);
+        int32_t rc = enqueue_all();
         if (rc != WHALE_OK) return rc;
-        if ((flags & WHALE_PEER_SUM) && !d->peer_fused) {  // one process per GPU: the world's total comes back, on every rank
-            rc = enqueue_peer_sum(d, m->d_out, m->stream);
-            if (rc != WHALE_OK) return rc;
-        }
         CU(cudaMemcpyAsync(ho, m->d_out, (1 + P) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
         CU(cudaStreamSynchronize(m->stream));
     }
