@@ -137,8 +137,9 @@ int32_t whale_multi_logpdf_grad(whale_multi_t h, const double* x, const double* 
  * memory (64-bit packets carrying data and the step's tag together: no fence, one hop), waits for the world's packets in
  * its own buffer and adds the contributions in rank order: every rank gets the same bits.  One-pass evaluations run it in
  * the last CTA of the DP kernel (no extra launch), others as a one-CTA kernel.  Like a collective, all ranks must issue the
- * same sequence of WHALE_PEER_SUM evaluations.  At most 16 ranks.  A peer that does not show up within ~10 s makes the
- * result -Inf (and zero gradient) instead of hanging.
+ * same sequence of WHALE_PEER_SUM evaluations.  At most 16 ranks.  A peer that does not show up within WHALE_PEER_TIMEOUT_S
+ * (environment, default 60) seconds makes the result -Inf (and zero gradient) instead of hanging: synchronise the ranks
+ * (a barrier of the driver's own) before the first such evaluation if their set-up times differ by more than that.
  */
 int32_t whale_peer_export(whale_data_t d, int32_t rank, int32_t world, void* handle64);
 int32_t whale_peer_import(whale_data_t d, int32_t peer, const void* handle64);

@@ -268,6 +268,7 @@ struct PeerDev {
     int rank, world, n;
     int status;        // set to 1 when a peer did not show up in time
     unsigned long long seq;  // exchanges completed
+    long long timeout_cycles;  // how long to wait for a peer's packets (SM clock cycles; WHALE_PEER_TIMEOUT_S, default 60 s)
 };
 #ifdef WHALE_EMU
 #define ST_RELAXED_SYS(p, v) (*(volatile unsigned long long*)(p) = (v))
@@ -308,7 +309,7 @@ __device__ __forceinline__ void peer_exchange(PeerDev* PD, double* out, unsigned
 #ifdef WHALE_EMU
             break;  // (the emulation runs the ranks one after another: no waiting)
 #endif
-            if (CLOCK64() - t0 > 20000000000LL) { bad = 1; break; }  // ~10 s: a peer is gone
+            if (CLOCK64() - t0 > PD->timeout_cycles) { bad = 1; break; }  // a peer is gone
         }
         s_w[idx] = (unsigned)pk;
     }

@@ -3090,6 +3090,7 @@ static int32_t peer_state(whale_data* D, PeerDev** out) {
         PeerDev h{};
         for (int q = 0; q < D->peer_world; q++) h.bufs[q] = D->peer_bufs[q];
         h.rank = D->peer_rank; h.world = D->peer_world; h.n = 1 + D->m->P; h.status = 0; h.seq = 0;
+        h.timeout_cycles = (long long)std::max(1, env_int("WHALE_PEER_TIMEOUT_S", 60)) * 2000000000LL;  // ~2 GHz SM clock
         CU(cudaMemcpy(D->d_peer, &h, sizeof(h), cudaMemcpyHostToDevice));
         D->peer_uploaded = true;
     }
