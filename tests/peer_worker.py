@@ -59,6 +59,15 @@ def main():
                     assert np.allclose(grad, wg, rtol=1e-9, atol=1e-9 * np.abs(wg).max()), (rank, xi)
                 with open(os.path.join(d, f"ll_r{rank}_{rep}_{xi}_{int(want_grad)}.txt"), "w") as fh:
                     fh.write(ll.value.hex())
+    # the exchange alone (whale_peer_sum_async) on a caller-owned device buffer: 1 + P doubles, here (rank + 1) * (j + 1)
+    import torch
+    torch.cuda.set_device(rank % ndev)
+    P = len(g["xs"][0])
+    buf = (rank + 1) * torch.arange(1, 2 + P, device="cuda", dtype=torch.float64)
+    L.check(L.L.whale_peer_sum_async(dh, buf.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    want = sum(r + 1 for r in range(world)) * np.arange(1, 2 + P, dtype=np.float64)
+    assert np.array_equal(buf.cpu().numpy(), want), (rank, buf.cpu().numpy()[:4], want[:4])
     L.L.whale_data_destroy(dh)
     L.L.whale_model_destroy(mh)
     print(f"rank {rank} ok")
