@@ -281,7 +281,8 @@ def c3_leg(args, L, wlib, rank, world, d3, n3, gen3_s, flush, stream):
         torch.cuda.synchronize()
         return float(pin_o[0])
 
-    e2e_step(0)
+    for i in range(Wm):  # (the third call with the same flags is the first CUDA-graph replay: keep the capture out of the timing)
+        e2e_step(i)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
