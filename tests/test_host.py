@@ -150,3 +150,16 @@ def test_sumtrees_identity_ignores_slice_times():
     assert summary[0]["tree"] is a and summary[1]["tree"] is c
     assert clades[(4, 6, frozenset({(2, 5), (3, 4)}))] == 3 and clades[(-1, 2, 0)] == 4
     assert W.sumtrees([]) == ([], {})
+
+
+def test_empty_batch_is_zero():
+    """`logpdf(wm, CCD[])` is the empty sum minus 0·condition (src/core.jl:54,63): 0 and a zero gradient, without touching
+    the device (the C ABI itself rejects n_fam = 0 with WHALE_ERR_ARG)."""
+    import whale_jl_b200 as W
+    from whale_jl_b200 import synth
+    w = W.WhaleModel(W.ConstantDLWGD(lam=0.2, mu=0.3, q=[0.2, 0.1], eta=0.67), synth.c1_species_tree(), 0.05)
+    assert W.logpdf(w, []) == 0.0
+    ll, g = W.logpdf_and_gradient(w, [])
+    assert ll == 0.0 and g.shape == (w.n_params,) and not g.any()
+    lf, gf = W.logpdf_per_family(w, [], grad=True)
+    assert lf.shape == (0,) and gf.shape == (0, w.n_params)

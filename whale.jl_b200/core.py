@@ -57,6 +57,10 @@ def _as_vector(x) -> tuple[CCDVector, bool]:
 
 def _eval(wm: WhaleModel, x, grad=False, keep=False, per_family=False, per_family_grad=False):
     xs, single = _as_vector(x)
+    if len(xs) == 0:  # an empty Vector{CCD}: Σ over nothing − 0·condition (src/core.jl:54,63); nothing to pack or launch
+        P = wm.n_params
+        return (0.0, np.zeros(P) if grad else None, np.zeros(0) if per_family else None,
+                np.zeros((0, P)) if per_family_grad else None)
     mh, dh = _data_handle(wm, xs)
     # a single CCD is the *unconditioned* likelihood (src/core.jl:29-43); vectors subtract N·condition (:46-64)
     cond = 0 if single else CONDITIONS[wm.condition]
