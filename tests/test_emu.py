@@ -371,6 +371,43 @@ def test_emu_peer_sum_two_ranks_in_one_process(L):
     L.L.whale_model_destroy(mh)
 
 
+def test_emu_packer_rejects_malformed_input(L):
+    """whale_data_create validates what it is handed instead of reading out of bounds: empty batch, more than 65 535 clades
+    (the reference's UInt16 clade ids, src/ccd.jl:13-33), clades not sorted by size, a compat list that is not ascending,
+    a clade incompatible with the root, a triple pointing outside the family — each WHALE_ERR_ARG with a message."""
+    g = load_golden("c1_example1")
+    mh = L.model_create(golden_model(g))
+    nn = len(g["m_order"])
+    good = golden_fams(g, [3])
+
+    def expect(fl, msg):
+        with pytest.raises(wlib.WhaleCudaError, match=msg):
+            L.data_create(mh, fl)
+
+    try:
+        expect(dict(good, n_fam=0), "n_fam must be positive")
+        big = 70000
+        expect(dict(n_fam=1, clade_off=np.array([0, big], np.int64), clade_nleaf=np.ones(big, np.int32),
+                    split_off=np.zeros(big + 1, np.int64), g1=np.zeros(1, np.int32), g2=np.zeros(1, np.int32),
+                    p=np.zeros(1), compat_off=np.zeros(nn + 1, np.int64), compat=np.zeros(1, np.int32)), "65535")
+        bad = dict(good, clade_nleaf=good["clade_nleaf"].copy())
+        bad["clade_nleaf"][0], bad["clade_nleaf"][-1] = bad["clade_nleaf"][-1], bad["clade_nleaf"][0]
+        expect(bad, "sorted by size")
+        bad = dict(good, compat=good["compat"].copy())
+        # swap two entries of the first node's list that has at least two
+        for e in range(nn):
+            a, b = int(good["compat_off"][e]), int(good["compat_off"][e + 1])
+            if b - a >= 2:
+                bad["compat"][a], bad["compat"][a + 1] = bad["compat"][a + 1], bad["compat"][a]
+                break
+        expect(bad, "ascending")
+        bad = dict(good, g1=good["g1"].copy())
+        bad["g1"][0] = 10 ** 6
+        expect(bad, "triple out of range")
+    finally:
+        L.L.whale_model_destroy(mh)
+
+
 @pytest.mark.parametrize("mode", ["fwd", "rev"])
 def test_emu_occupancy_line_unstages_outliers(mode, tmp_path):
     """A launch requests its bin's largest shared-memory need for every CTA, so the few families just above the size that
